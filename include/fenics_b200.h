@@ -1,0 +1,173 @@
+/* fenics_b200 -- C ABI of the B200-native time-step hot path (assembly + Krylov solves).
+ *
+ * The reference (ATMackay/fenics) has no FFI of its own: its hot path is the dolfin 2019.1.0 Python
+ * calls made inside each script's `while t < Tf` loop.  Every entry point below states the
+ * reference call (file:line) it replaces.  All `double*`/`int*` arguments documented "device" are
+ * CUDA device pointers on the plan's device (torch CUDA tensors on the Python side); "host" are
+ * ordinary host pointers.  Every call returns 0 on success or a negative fx_status; the message is
+ * available from fx_last_error().  All device work is enqueued on `stream` (a cudaStream_t passed as
+ * void*) and is asynchronous unless stated.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef FENICS_B200_H
+#define FENICS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fx_plan fx_plan;
+
+typedef enum {
+  FX_OK = 0,
+  FX_ERR_ARG = -1,      /* bad argument (null pointer, unknown id, size mismatch)            */
+  FX_ERR_CUDA = -2,     /* CUDA runtime error (message holds cudaGetErrorString)             */
+  FX_ERR_NOCONV = -3,   /* Krylov solver hit maxit or diverged (dolfin raises RuntimeError)  */
+  FX_ERR_UNSUPPORTED = -4
+} fx_status;
+
+/* Function spaces of function_spaces(mesh, 2) (lid-driven-cavity/fenics_fem.py:262-287,
+ * buoyancy-driven-flow/fenics_fem.py:448-468, "flow between eccentrically rotating
+ * cylinders"/fenics_base.py:470-502).  Local dofs are component-blocked in UFC order.       */
+typedef enum {
+  FX_SPACE_W = 0,  /* (P2)^2 x (DG0)^3, 15 local dofs: ux 0-5 | uy 6-11 | D0 12 | D1 13 | D2 14 */
+  FX_SPACE_ZC = 1, /* (P2)^3, 18 local dofs                                                     */
+  FX_SPACE_Q = 2,  /* P1, 3 local dofs                                                          */
+  FX_SPACE_ZD = 3, /* (DG0)^3                                                                   */
+  FX_SPACE_QT = 4, /* DG0                                                                       */
+  FX_SPACE_V = 5,  /* (P2)^2, 12 local dofs (post-loop diagnostics)                             */
+  FX_NSPACES = 6
+} fx_space;
+
+/* Slots of the coefficient ("state") table handed to the assembly calls: state[f] is a device
+ * vector in the dof order of the named space, or NULL when the form does not read it.  The names
+ * are the reference's (solution_functions, lid-driven-cavity/fenics_fem.py:227-247).          */
+typedef enum {
+  FX_F_W0 = 0, FX_F_W12, FX_F_WS, FX_F_W1,                 /* W  */
+  FX_F_P0, FX_F_P1, FX_F_RHO0, FX_F_RHO12, FX_F_RHO1,      /* Q  */
+  FX_F_T0, FX_F_T1, FX_F_THETA0, FX_F_THERM_INV,           /* Q  */
+  FX_F_TAU0, FX_F_TAU12, FX_F_TAU1,                        /* Zc */
+  FX_F_KAPP,                                               /* Qt */
+  FX_F_RES_TEST,                                           /* Zd: project(restau0, Zd)          */
+  FX_F_RES_ORTH,                                           /* Zc: project(restau0-res_test, Zc) */
+  FX_F_QT_A,                                               /* Qt scratch (res_orth_norm_sq)     */
+  FX_F_Q_A,                                                /* Q  scratch                        */
+  FX_NFIELDS = 24
+} fx_field;
+
+/* Slots of the parameter table (host doubles). */
+typedef enum {
+  FX_P_DT = 0, FX_P_RE, FX_P_WE, FX_P_BETAV, FX_P_C1, FX_P_C2, FX_P_TH, FX_P_CONV, FX_P_MA,
+  FX_P_PR, FX_P_RA, FX_P_DI, FX_P_VH, FX_P_BI, FX_P_T0, FX_P_TH_HOT, FX_P_AL1, FX_P_AL2,
+  FX_P_LAMBDA_D, FX_P_B_FENE, FX_P_A0, FX_P_EPS, FX_P_T,
+  FX_NPARAMS = 24
+} fx_param;
+
+/* Forms.  Bilinear forms produce CSR values on the pattern of their space, linear forms a vector,
+ * functionals one double.  "cfg1" = lid-driven-cavity/incomp_LDC.py, "cfg2" =
+ * lid-driven-cavity/comp_LDC_mesh_convergence.py (line numbers of each form in DESIGN.md).     */
+typedef enum {
+  /* generic */
+  FX_FORM_MASS_ZC = 1, /* inner(w,Pv)*dx on Zc  (dolfin project(), mass matrix)   */
+  FX_FORM_MASS_Q,      /* on Q                                                     */
+  /* cfg1: bilinear */
+  FX_FORM_C1_A1 = 100, FX_FORM_C1_A2, FX_FORM_C1_A5, FX_FORM_C1_A7, FX_FORM_C1_A4,
+  /* cfg1: linear */
+  FX_FORM_C1_L1 = 120, FX_FORM_C1_L2, FX_FORM_C1_L5, FX_FORM_C1_L7, FX_FORM_C1_L4,
+  FX_FORM_LDC_L_RES_ORTH, /* inner(w, restau0 - res_test)*dx on Zc (incomp_LDC.py:305)        */
+  /* cfg1: functionals */
+  FX_FORM_C1_EK = 140, FX_FORM_C1_EE,
+  /* cfg2: bilinear */
+  FX_FORM_C2_A0 = 200, FX_FORM_C2_A1, FX_FORM_C2_A2, FX_FORM_C2_A5, FX_FORM_C2_A7, FX_FORM_C2_A4,
+  /* cfg2: linear */
+  FX_FORM_C2_L0 = 220, FX_FORM_C2_L1, FX_FORM_C2_L2, FX_FORM_C2_L5, FX_FORM_C2_L7, FX_FORM_C2_L4,
+  FX_FORM_C2_L_RHO1,      /* inner(q, rho0 + Ma^2/Re (p1-p0))*dx (comp_LDC_mesh_convergence.py:501-502) */
+  /* cfg2: functionals */
+  FX_FORM_C2_EK = 240, FX_FORM_C2_EE
+} fx_form;
+
+/* DG0 projections (diagonal mass => cell average), dolfin project(expr, Zd|Qt).               */
+typedef enum {
+  FX_EXPR_LDC_RESTAU = 1,   /* restau0 -> Zd   (incomp_LDC.py:300-304)                     */
+  FX_EXPR_RES_ORTH_SQ,      /* inner(res_orth,res_orth) -> Qt (:306)                       */
+  FX_EXPR_SQRT_QT_A,        /* (QT_A)**0.5 -> Qt (:307-308)                                */
+  FX_EXPR_H_KAPP            /* h*kapp -> Qt (:434)                                         */
+} fx_expr;
+
+typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;
+typedef enum { FX_PC_NONE = 0, FX_PC_JACOBI = 1, FX_PC_ILU0 = 2 } fx_pc;
+
+typedef struct {
+  int iterations;
+  int converged;      /* 1 converged, 0 maxit, -1 breakdown/diverged          */
+  double residual;    /* final (preconditioned) residual 2-norm               */
+  double residual0;   /* reference norm the relative tolerance is applied to  */
+} fx_solve_info;
+
+const char* fx_last_error(void);
+int fx_version(void);
+
+/* ---- plan: mesh + dofmaps -> device-resident geometry, CSR patterns, scatter maps ----------
+ * Replaces what dolfin builds on every assemble() call (SparsityPatternBuilder, DofMap tabulation;
+ * e.g. lid-driven-cavity/incomp_LDC.py:328) -- built once here.  All inputs are HOST arrays:
+ * xy[nv*2], cells[nc*3] (vertices ascending per cell, UFC), cell_dofs[s] = nc*ld(s) ints (row-major,
+ * dolfin's V.dofmap().cell_dofs(c)) or NULL if the space is unused; boundary facets as (cell, local
+ * facet opposite local vertex i, marker).                                                     */
+int fx_plan_create(const double* xy, int nv, const int* cells, int nc,
+                   const int* const* cell_dofs, const int* bfacet_cell, const int* bfacet_local,
+                   const int* bfacet_marker, int nbf, int device, fx_plan** out);
+void fx_plan_destroy(fx_plan* plan);
+int fx_plan_set_markers(fx_plan* plan, const int* bfacet_marker, int nbf);
+
+int fx_space_dim(const fx_plan* plan, int space);
+int fx_space_local_dim(int space);
+/* CSR pattern of space x space (DOLFIN's full cell-block pattern, columns ascending):
+ * device pointers owned by the plan.                                                          */
+int fx_pattern(const fx_plan* plan, int space, int* n, int* nnz, const int** rowptr_dev,
+               const int** col_dev);
+/* geometry produced by the K1 kernel, device, SoA [6][nc]: K00,K01,K10,K11 (=J^-1), |detJ|, h   */
+int fx_geometry(const fx_plan* plan, const double** geom_dev);
+
+/* ---- assembly (assemble(a), assemble(L), assemble(functional)) ----------------------------- */
+int fx_assemble_matrix(fx_plan* plan, int form, const double* const* state, const double* params,
+                       double* val_dev, void* stream);
+int fx_assemble_vector(fx_plan* plan, int form, const double* const* state, const double* params,
+                       double* b_dev, void* stream);
+/* synchronous: waits for `stream`, writes one host double */
+int fx_assemble_scalar(fx_plan* plan, int form, const double* const* state, const double* params,
+                       double* out_host, void* stream);
+/* asynchronous variant: result lands in out_dev[0] */
+int fx_assemble_scalar_dev(fx_plan* plan, int form, const double* const* state,
+                           const double* params, double* out_dev, void* stream);
+int fx_project_dg0(fx_plan* plan, int expr, const double* const* state, const double* params,
+                   double* out_dev, void* stream);
+/* which quadrature degree the kernels of `form` use: q[0]=dx degree, q[1]=ds degree (-1: none) */
+int fx_form_info(int form, int* rank, int* space, int* qdeg);
+
+/* ---- DirichletBC.apply(A, b) (incomp_LDC.py:330): identity rows, b[row]=g ------------------ */
+int fx_apply_bc(fx_plan* plan, int space, double* val_dev, double* b_dev, const int* rows_dev,
+                const double* g_dev, int n, void* stream);
+
+/* ---- linear algebra ------------------------------------------------------------------------ */
+int fx_spmv(fx_plan* plan, int space, const double* val_dev, const double* x_dev, double* y_dev,
+            void* stream);
+int fx_axpy(int n, double alpha, const double* x_dev, double* y_dev, void* stream);
+int fx_dot(fx_plan* plan, int n, const double* x_dev, const double* y_dev, double* out_host,
+           void* stream);                      /* synchronous */
+int fx_norm(fx_plan* plan, int n, const double* x_dev, int kind /*0 l2, 1 linf*/, double* out_host,
+            void* stream);                     /* synchronous; norm(vec,'l2'|'linf')          */
+
+/* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
+ * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
+ * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default
+ * for left preconditioning).  Synchronous when `info` is non-NULL (waits, fills info, returns
+ * FX_ERR_NOCONV on failure); fully asynchronous when info==NULL (poll fx_solve_result later). */
+int fx_krylov_solve(fx_plan* plan, int space, const double* val_dev, double* x_dev,
+                    const double* b_dev, int method, int pc, double rtol, double atol, int maxit,
+                    fx_solve_info* info, void* stream);
+/* result of the most recent asynchronous solve on `space` (synchronises `stream`) */
+int fx_solve_result(fx_plan* plan, int space, fx_solve_info* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
