@@ -1,0 +1,249 @@
+// CUDA kernels for finite-element assembly (K1-K5 of SURVEY.md 2.3) and their launchers.
+// The element arithmetic lives in fx_assemble.h / fx_forms_*.h; this file is the thread mapping.
+#include "fx_plan.h"
+#include "fx_registry.h"
+
+namespace fx {
+
+// ---- K1 geometry ---------------------------------------------------------------------------------
+__global__ void k_geometry(const double* __restrict__ xy, const int* __restrict__ cells, int nc,
+                           double* __restrict__ geom) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc) compute_geo(xy, cells, c, nc, geom);
+}
+__global__ void k_facet_geometry(const double* __restrict__ xy, const int* __restrict__ cells,
+                                 const int* __restrict__ bf_cell, const int* __restrict__ bf_local, int nbf,
+                                 double* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < nbf) compute_facet_geo(xy, cells, bf_cell[f], bf_local[f], f, nbf, out);
+}
+
+int launch_geometry(fx_plan* P, cudaStream_t st) {
+  k_geometry<<<(P->nc + 255) / 256, 256, 0, st>>>(P->xy, P->cells, P->nc, P->geom);
+  if (P->nbf > 0)
+    k_facet_geometry<<<(P->nbf + 127) / 128, 128, 0, st>>>(P->xy, P->cells, P->bf_cell, P->bf_local, P->nbf,
+                                                           P->bf_geo);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+// ---- K2/K3 cell kernels: grid (cell blocks, test components), block (32 cells, nb basis fns) ------
+template <class F>
+__global__ void __launch_bounds__(CB * 6) k_cell_matrix(const __grid_constant__ AsmArgs a) {
+  using Sp = typename F::Space;
+  extern __shared__ double smem[];
+  const int cell0 = blockIdx.x * CB;
+  if constexpr (F::NP > 0) {
+    cell_phase1<F>(a, cell0, threadIdx.y * CB + threadIdx.x, blockDim.x * blockDim.y, smem);
+    __syncthreads();
+  }
+  static_for<0, Sp::NCOMP>([&](auto ic) {
+    constexpr int I = decltype(ic)::value;
+    if (blockIdx.y == I) mat_rows<F, I>(a, cell0, threadIdx.x, threadIdx.y, smem);
+  });
+}
+
+template <class F>
+__global__ void __launch_bounds__(CB * 6) k_cell_vector(const __grid_constant__ AsmArgs a) {
+  using Sp = typename F::Space;
+  extern __shared__ double smem[];
+  const int cell0 = blockIdx.x * CB;
+  if constexpr (F::NP > 0) {
+    cell_phase1<F>(a, cell0, threadIdx.y * CB + threadIdx.x, blockDim.x * blockDim.y, smem);
+    __syncthreads();
+  }
+  static_for<0, Sp::NCOMP>([&](auto ic) {
+    constexpr int I = decltype(ic)::value;
+    if (blockIdx.y == I) vec_rows<F, I>(a, cell0, threadIdx.x, threadIdx.y, smem);
+  });
+}
+
+// ---- K4 exterior-facet kernels: one thread per (boundary facet, local test dof) -------------------
+template <class F>
+__global__ void k_facet_matrix(const __grid_constant__ AsmArgs a) {
+  constexpr int LD = F::Space::LD;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.m.nbf * LD) facet_mat_row<F>(a, idx / LD, idx % LD);
+}
+template <class F>
+__global__ void k_facet_vector(const __grid_constant__ AsmArgs a) {
+  constexpr int LD = F::Space::LD;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.m.nbf * LD) facet_vec_row<F>(a, idx / LD, idx % LD);
+}
+
+// ---- K5 functionals: per-cell value, deterministic two-stage reduction ----------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_cell_scalar(const __grid_constant__ AsmArgs a) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = (c < a.m.nc) ? cell_functional<F>(a, c) : 0.0;
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict__ part, int n,
+                                                       double* __restrict__ out) {
+  __shared__ double sh[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i];
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+template <class E>
+__global__ void __launch_bounds__(256) k_project_dg0(const __grid_constant__ AsmArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.m.nc) cell_project_dg0<E>(a, c);
+}
+
+// ---- launchers ------------------------------------------------------------------------------------
+template <class F>
+static int run_matrix(fx_plan* P, AsmArgs a, cudaStream_t st) {
+  using Sp = typename F::Space;
+  const DevPattern& pat = P->sp[space_id<Sp>::v];
+  if (!pat.has_csr) return set_error(FX_ERR_ARG, "space %d has no dofmap/pattern in this plan", space_id<Sp>::v);
+  a.rowptr = pat.rowptr;
+  a.pos = pat.pos;
+  FX_CUDA(cudaMemsetAsync(a.val, 0, sizeof(double) * (size_t)pat.nnz, st));
+  constexpr int NQ = tri_npts(F::QDEG);
+  constexpr size_t smem = sizeof(double) * (size_t)F::NP * NQ * CB;
+  static bool attr_done = false;
+  if (smem > 48 * 1024 && !attr_done) {
+    FX_CUDA(cudaFuncSetAttribute(k_cell_matrix<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((P->nc + CB - 1) / CB, Sp::NCOMP), block(CB, Sp::maxnb());
+  k_cell_matrix<F><<<grid, block, smem, st>>>(a);
+  count_launch(1);
+  if constexpr (F::Facet::present) {
+    if (P->nbf > 0) {
+      const int n = P->nbf * Sp::LD;
+      k_facet_matrix<F><<<(n + 127) / 128, 128, 0, st>>>(a);
+      count_launch(1);
+    }
+  }
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+template <class F>
+static int run_vector(fx_plan* P, AsmArgs a, cudaStream_t st) {
+  using Sp = typename F::Space;
+  const DevPattern& pat = P->sp[space_id<Sp>::v];
+  if (!pat.present) return set_error(FX_ERR_ARG, "space %d has no dofmap in this plan", space_id<Sp>::v);
+  FX_CUDA(cudaMemsetAsync(a.vec, 0, sizeof(double) * (size_t)pat.n, st));
+  constexpr int NQ = tri_npts(F::QDEG);
+  constexpr size_t smem = sizeof(double) * (size_t)F::NP * NQ * CB;
+  static bool attr_done = false;
+  if (smem > 48 * 1024 && !attr_done) {
+    FX_CUDA(cudaFuncSetAttribute(k_cell_vector<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((P->nc + CB - 1) / CB, Sp::NCOMP), block(CB, Sp::maxnb());
+  k_cell_vector<F><<<grid, block, smem, st>>>(a);
+  count_launch(1);
+  if constexpr (F::Facet::present) {
+    if (P->nbf > 0) {
+      const int n = P->nbf * Sp::LD;
+      k_facet_vector<F><<<(n + 127) / 128, 128, 0, st>>>(a);
+      count_launch(1);
+    }
+  }
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+template <class F>
+static int run_scalar(fx_plan* P, AsmArgs a, double* out_dev, cudaStream_t st) {
+  const int nb = (P->nc + 255) / 256;
+  if (nb > P->part_cap) return set_error(FX_ERR_ARG, "partial buffer too small");
+  a.part = P->part;
+  k_cell_scalar<F><<<nb, 256, 0, st>>>(a);
+  k_sum_partials<<<1, 1024, 0, st>>>(P->part, nb, out_dev);
+  count_launch(2);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+template <class E>
+static int run_dg0(fx_plan* P, AsmArgs a, cudaStream_t st) {
+  k_project_dg0<E><<<(P->nc + 255) / 256, 256, 0, st>>>(a);
+  count_launch(1);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int launch_matrix(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
+  switch (form) {
+#define X(id, F) case id: return run_matrix<F>(P, a, st);
+    FX_MATRIX_FORMS(X)
+#undef X
+  }
+  return set_error(FX_ERR_ARG, "unknown bilinear form id %d", form);
+}
+
+int launch_vector(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
+  const bool conv0 = a.p.v[ldc::P_CONV] == 0.0;
+  switch (form) {
+#define X(id, F) case id: return run_vector<F>(P, a, st);
+#define XC(id, F0, F1) case id: return conv0 ? run_vector<F0>(P, a, st) : run_vector<F1>(P, a, st);
+    FX_VECTOR_FORMS(X, XC)
+#undef X
+#undef XC
+  }
+  return set_error(FX_ERR_ARG, "unknown linear form id %d", form);
+}
+
+int launch_scalar(fx_plan* P, int form, const AsmArgs& a, double* out_dev, cudaStream_t st) {
+  switch (form) {
+#define X(id, F) case id: return run_scalar<F>(P, a, out_dev, st);
+    FX_SCALAR_FORMS(X)
+#undef X
+  }
+  return set_error(FX_ERR_ARG, "unknown functional id %d", form);
+}
+
+int launch_dg0(fx_plan* P, int expr, const AsmArgs& a, cudaStream_t st) {
+  switch (expr) {
+#define X(id, E) case id: return run_dg0<E>(P, a, st);
+    FX_DG0_EXPRS(X)
+#undef X
+  }
+  return set_error(FX_ERR_ARG, "unknown DG0 expression id %d", expr);
+}
+
+int form_info(int form, int* rank, int* space, int* qdeg) {
+  switch (form) {
+#define X(id, F) case id: *rank = 2; *space = space_id<typename F::Space>::v; qdeg[0] = F::QDEG; qdeg[1] = facet_qdeg<F>(); return FX_OK;
+    FX_MATRIX_FORMS(X)
+#undef X
+#define X(id, F) case id: *rank = 1; *space = space_id<typename F::Space>::v; qdeg[0] = F::QDEG; qdeg[1] = facet_qdeg<F>(); return FX_OK;
+#define XC(id, F0, F1) case id: *rank = 1; *space = space_id<typename F0::Space>::v; qdeg[0] = F1::QDEG; qdeg[1] = -1; return FX_OK;
+    FX_VECTOR_FORMS(X, XC)
+#undef X
+#undef XC
+#define X(id, F) case id: *rank = 0; *space = -1; qdeg[0] = F::QDEG; qdeg[1] = -1; return FX_OK;
+    FX_SCALAR_FORMS(X)
+#undef X
+  }
+  return set_error(FX_ERR_ARG, "unknown form id %d", form);
+}
+
+}  // namespace fx

@@ -1,0 +1,298 @@
+// extern "C" entry points declared in include/fenics_b200.h + plan construction.
+#include <atomic>
+#include <cstring>
+
+#include "fx_plan.h"
+#include "fx_plan_host.h"
+
+namespace fx {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches.load(); }
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+template <class T>
+static int upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0) return FX_OK;
+  FX_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+  FX_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return FX_OK;
+}
+
+int ensure_work(fx_plan* P, size_t n) {
+  if (P->work_n >= n) return FX_OK;
+  if (P->work) cudaFree(P->work);
+  P->work = nullptr;
+  P->work_n = 0;
+  FX_CUDA(cudaMalloc((void**)&P->work, sizeof(double) * n * KRYLOV_NWORK));
+  P->work_n = n;
+  return FX_OK;
+}
+
+static AsmArgs make_args(const fx_plan* P, const double* const* state, const double* params) {
+  AsmArgs a{};
+  a.m = P->view();
+  for (int i = 0; i < NFIELDS; ++i) a.s.f[i] = state ? state[i] : nullptr;
+  for (int i = 0; i < NPARAMS; ++i) a.p.v[i] = params ? params[i] : 0.0;
+  a.marker_mask = -1;
+  return a;
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" {
+
+const char* fx_last_error(void) { return last_error().c_str(); }
+int fx_version(void) { return 100; }
+long long fx_launch_count(void) { return launch_count(); }
+int fx_copy_to_host(void* dst, const void* src, long long nbytes) {
+  if (!dst || !src || nbytes < 0) return set_error(FX_ERR_ARG, "fx_copy_to_host: bad argument");
+  FX_CUDA(cudaMemcpy(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost));
+  return FX_OK;
+}
+int fx_space_local_dim(int space) { return (space >= 0 && space < S_N) ? space_ld(space) : FX_ERR_ARG; }
+
+int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int* const* cell_dofs,
+                   const int* bfacet_cell, const int* bfacet_local, const int* bfacet_marker, int nbf, int device,
+                   fx_plan** out) {
+  if (!xy || !cells || !cell_dofs || !out || nv <= 0 || nc <= 0 || nbf < 0)
+    return set_error(FX_ERR_ARG, "fx_plan_create: bad argument");
+  for (int c = 0; c < nc; ++c) {
+    const int* v = cells + 3 * (size_t)c;
+    if (!(v[0] >= 0 && v[0] < v[1] && v[1] < v[2] && v[2] < nv))
+      return set_error(FX_ERR_ARG, "fx_plan_create: cell %d vertices not ascending / out of range (UFC order)", c);
+  }
+  for (int f = 0; f < nbf; ++f)
+    if (bfacet_cell[f] < 0 || bfacet_cell[f] >= nc || bfacet_local[f] < 0 || bfacet_local[f] > 2 ||
+        bfacet_marker[f] < 0 || bfacet_marker[f] > 30)
+      return set_error(FX_ERR_ARG, "fx_plan_create: bad boundary facet %d", f);
+  FX_CUDA(cudaSetDevice(device));
+  fx_plan* P = new fx_plan();
+  P->device = device;
+  P->nv = nv; P->nc = nc; P->nbf = nbf;
+  int rc = FX_OK;
+  auto fail = [&](int code) { fx_plan_destroy(P); return code; };
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(set_error(FX_ERR_CUDA, "no device %d", device));
+  P->num_sms = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) return fail(set_error(FX_ERR_UNSUPPORTED, "device lacks cooperative launch"));
+  if ((rc = upload(&P->xy, xy, 2 * (size_t)nv))) return fail(rc);
+  if ((rc = upload(&P->cells, cells, 3 * (size_t)nc))) return fail(rc);
+  if ((rc = upload(&P->bf_cell, bfacet_cell, (size_t)nbf))) return fail(rc);
+  if ((rc = upload(&P->bf_local, bfacet_local, (size_t)nbf))) return fail(rc);
+  if ((rc = upload(&P->bf_marker, bfacet_marker, (size_t)nbf))) return fail(rc);
+  if (cudaMalloc((void**)&P->geom, sizeof(double) * 6 * (size_t)nc) != cudaSuccess ||
+      cudaMalloc((void**)&P->bf_geo, sizeof(double) * (3 * (size_t)nbf + 1)) != cudaSuccess)
+    return fail(set_error(FX_ERR_CUDA, "cudaMalloc geometry failed"));
+  size_t maxn = 0;
+  for (int s = 0; s < S_N; ++s) {
+    if (!cell_dofs[s]) continue;
+    HostPattern hp;
+    std::string err;
+    const bool want = (s == S_W || s == S_ZC || s == S_Q || s == S_V);
+    if (!build_pattern(cell_dofs[s], nc, space_ld(s), want, hp, err))
+      return fail(set_error(FX_ERR_ARG, "fx_plan_create: space %d: %s", s, err.c_str()));
+    DevPattern& d = P->sp[s];
+    d.n = hp.n; d.nnz = hp.nnz; d.ld = hp.ld; d.present = true; d.has_csr = want;
+    if ((rc = upload(&d.dm_t, hp.dm_t.data(), hp.dm_t.size()))) return fail(rc);
+    if (want) {
+      if ((rc = upload(&d.rowptr, hp.rowptr.data(), hp.rowptr.size()))) return fail(rc);
+      if ((rc = upload(&d.col, hp.col.data(), hp.col.size()))) return fail(rc);
+      if ((rc = upload(&d.pos, hp.pos.data(), hp.pos.size()))) return fail(rc);
+    }
+    maxn = std::max(maxn, (size_t)hp.n);
+  }
+  P->part_cap = std::max((nc + 255) / 256, 148 * 8);
+  if (cudaMalloc((void**)&P->part, sizeof(double) * P->part_cap) != cudaSuccess ||
+      cudaMalloc((void**)&P->scal, sizeof(double) * 64) != cudaSuccess ||
+      cudaMalloc((void**)&P->red, sizeof(double) * 2 * RED_SLOTS * MAX_GRID) != cudaSuccess ||
+      cudaMalloc((void**)&P->info, sizeof(fx_solve_info) * FX_NTICKETS) != cudaSuccess)
+    return fail(set_error(FX_ERR_CUDA, "cudaMalloc scratch failed"));
+  cudaMemset(P->info, 0, sizeof(fx_solve_info) * FX_NTICKETS);
+  if ((rc = ensure_work(P, maxn))) return fail(rc);
+  if ((rc = launch_geometry(P, 0))) return fail(rc);
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(set_error(FX_ERR_CUDA, "geometry kernel failed"));
+  *out = P;
+  return FX_OK;
+}
+
+void fx_plan_destroy(fx_plan* P) {
+  if (!P) return;
+  cudaFree(P->xy); cudaFree(P->cells); cudaFree(P->geom);
+  cudaFree(P->bf_cell); cudaFree(P->bf_local); cudaFree(P->bf_marker); cudaFree(P->bf_geo);
+  for (int s = 0; s < S_N; ++s) {
+    cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t);
+  }
+  cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
+  delete P;
+}
+
+int fx_plan_set_markers(fx_plan* P, const int* m, int nbf) {
+  if (!P || !m || nbf != P->nbf) return set_error(FX_ERR_ARG, "fx_plan_set_markers: bad argument");
+  for (int f = 0; f < nbf; ++f)
+    if (m[f] < 0 || m[f] > 30) return set_error(FX_ERR_ARG, "marker out of range [0,30]");
+  FX_CUDA(cudaMemcpy(P->bf_marker, m, sizeof(int) * nbf, cudaMemcpyHostToDevice));
+  return FX_OK;
+}
+
+int fx_space_dim(const fx_plan* P, int space) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].present) return FX_ERR_ARG;
+  return P->sp[space].n;
+}
+
+int fx_pattern(const fx_plan* P, int space, int* n, int* nnz, const int** rowptr, const int** col) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr)
+    return set_error(FX_ERR_ARG, "fx_pattern: space %d has no pattern", space);
+  if (n) *n = P->sp[space].n;
+  if (nnz) *nnz = P->sp[space].nnz;
+  if (rowptr) *rowptr = P->sp[space].rowptr;
+  if (col) *col = P->sp[space].col;
+  return FX_OK;
+}
+
+int fx_geometry(const fx_plan* P, const double** geom) {
+  if (!P || !geom) return set_error(FX_ERR_ARG, "fx_geometry: bad argument");
+  *geom = P->geom;
+  return FX_OK;
+}
+
+int fx_assemble_matrix(fx_plan* P, int form, const double* const* state, const double* params, double* val,
+                       void* stream) {
+  if (!P || !val) return set_error(FX_ERR_ARG, "fx_assemble_matrix: bad argument");
+  AsmArgs a = make_args(P, state, params);
+  a.val = val;
+  return launch_matrix(P, form, a, (cudaStream_t)stream);
+}
+
+int fx_assemble_vector(fx_plan* P, int form, const double* const* state, const double* params, double* b,
+                       void* stream) {
+  if (!P || !b) return set_error(FX_ERR_ARG, "fx_assemble_vector: bad argument");
+  AsmArgs a = make_args(P, state, params);
+  a.vec = b;
+  return launch_vector(P, form, a, (cudaStream_t)stream);
+}
+
+int fx_assemble_scalar_dev(fx_plan* P, int form, const double* const* state, const double* params,
+                           double* out_dev, void* stream) {
+  if (!P || !out_dev) return set_error(FX_ERR_ARG, "fx_assemble_scalar_dev: bad argument");
+  AsmArgs a = make_args(P, state, params);
+  return launch_scalar(P, form, a, out_dev, (cudaStream_t)stream);
+}
+
+int fx_assemble_scalar(fx_plan* P, int form, const double* const* state, const double* params, double* out,
+                       void* stream) {
+  if (!P || !out) return set_error(FX_ERR_ARG, "fx_assemble_scalar: bad argument");
+  int rc = fx_assemble_scalar_dev(P, form, state, params, P->scal, stream);
+  if (rc) return rc;
+  FX_CUDA(cudaMemcpyAsync(out, P->scal, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FX_OK;
+}
+
+int fx_project_dg0(fx_plan* P, int expr, const double* const* state, const double* params, double* out_dev,
+                   void* stream) {
+  if (!P || !out_dev) return set_error(FX_ERR_ARG, "fx_project_dg0: bad argument");
+  AsmArgs a = make_args(P, state, params);
+  a.vec = out_dev;
+  return launch_dg0(P, expr, a, (cudaStream_t)stream);
+}
+
+int fx_form_info(int form, int* rank, int* space, int* qdeg) {
+  if (!rank || !space || !qdeg) return set_error(FX_ERR_ARG, "fx_form_info: bad argument");
+  return form_info(form, rank, space, qdeg);
+}
+
+int fx_apply_bc(fx_plan* P, int space, double* val, double* b, const int* rows, const double* g, int n,
+                void* stream) {
+  if (!P || space < 0 || space >= S_N || (n > 0 && (!rows || !g)))
+    return set_error(FX_ERR_ARG, "fx_apply_bc: bad argument");
+  return la_apply_bc(P, space, val, b, rows, g, n, (cudaStream_t)stream);
+}
+
+int fx_spmv(fx_plan* P, int space, const double* val, const double* x, double* y, void* stream) {
+  if (!P || space < 0 || space >= S_N || !val || !x || !y) return set_error(FX_ERR_ARG, "fx_spmv: bad argument");
+  return la_spmv(P, space, val, x, y, (cudaStream_t)stream);
+}
+
+int fx_axpy(int n, double alpha, const double* x, double* y, void* stream) {
+  if (n < 0 || !x || !y) return set_error(FX_ERR_ARG, "fx_axpy: bad argument");
+  return la_axpy(n, alpha, x, y, (cudaStream_t)stream);
+}
+
+int fx_dot(fx_plan* P, int n, const double* x, const double* y, double* out, void* stream) {
+  if (!P || n < 0 || !x || !y || !out) return set_error(FX_ERR_ARG, "fx_dot: bad argument");
+  int rc = la_dot(P, n, x, y, P->scal + 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  FX_CUDA(cudaMemcpyAsync(out, P->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FX_OK;
+}
+
+int fx_norm(fx_plan* P, int n, const double* x, int kind, double* out, void* stream) {
+  if (!P || n < 0 || !x || !out) return set_error(FX_ERR_ARG, "fx_norm: bad argument");
+  int rc = la_norm(P, n, x, kind, P->scal + 2, (cudaStream_t)stream);
+  if (rc) return rc;
+  FX_CUDA(cudaMemcpyAsync(out, P->scal + 2, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FX_OK;
+}
+
+int fx_dot_dev(fx_plan* P, int n, const double* x, const double* y, double* out_dev, void* stream) {
+  if (!P || n < 0 || !x || !y || !out_dev) return set_error(FX_ERR_ARG, "fx_dot_dev: bad argument");
+  return la_dot(P, n, x, y, out_dev, (cudaStream_t)stream);
+}
+
+int fx_norm_dev(fx_plan* P, int n, const double* x, int kind, double* out_dev, void* stream) {
+  if (!P || n < 0 || !x || !out_dev) return set_error(FX_ERR_ARG, "fx_norm_dev: bad argument");
+  return la_norm(P, n, x, kind, out_dev, (cudaStream_t)stream);
+}
+
+int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void* stream) {
+  if (!P || first < 0 || count < 1 || first + count > FX_NTICKETS || !info)
+    return set_error(FX_ERR_ARG, "fx_solve_results: bad argument");
+  FX_CUDA(cudaMemcpyAsync(info, P->info + first, sizeof(fx_solve_info) * count, cudaMemcpyDeviceToHost,
+                          (cudaStream_t)stream));
+  FX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FX_OK;
+}
+
+int fx_krylov_solve_async(fx_plan* P, int space, const double* val, double* x, const double* b, int method,
+                          int pc, double rtol, double atol, int maxit, int ticket, void* stream) {
+  if (!P || space < 0 || space >= S_N || !val || !x || !b || maxit < 0 || ticket < 0 || ticket >= FX_NTICKETS)
+    return set_error(FX_ERR_ARG, "fx_krylov_solve_async: bad argument");
+  return la_krylov(P, space, val, x, b, method, pc, rtol, atol, maxit, ticket, (cudaStream_t)stream);
+}
+
+int fx_krylov_solve(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
+                    double rtol, double atol, int maxit, fx_solve_info* info, void* stream) {
+  const int ticket = FX_NTICKETS - 1;
+  int rc = fx_krylov_solve_async(P, space, val, x, b, method, pc, rtol, atol, maxit, ticket, stream);
+  if (rc) return rc;
+  fx_solve_info local;
+  rc = fx_solve_results(P, ticket, 1, &local, stream);
+  if (rc) return rc;
+  if (info) *info = local;
+  if (local.converged != 1)
+    return set_error(FX_ERR_NOCONV, "Krylov solver did not converge: %d iterations, residual %.3e (ref %.3e), status %d",
+                     local.iterations, local.residual, local.residual0, local.converged);
+  return FX_OK;
+}
+
+}  // extern "C"

@@ -155,29 +155,29 @@ FX_HD void tri_point(int i, double& xi, double& et, double& w) {
   if constexpr (Q <= 1) {
     xi = 1.0 / 3; et = 1.0 / 3; w = 0.5;
   } else if constexpr (Q == 2) {
-    constexpr double T[3][2] = {{1.0 / 6, 1.0 / 6}, {1.0 / 6, 2.0 / 3}, {2.0 / 3, 1.0 / 6}};
+    static constexpr double T[3][2] = {{1.0 / 6, 1.0 / 6}, {1.0 / 6, 2.0 / 3}, {2.0 / 3, 1.0 / 6}};
     xi = T[i][0]; et = T[i][1]; w = 1.0 / 6;
   } else if constexpr (Q == 3) {
     constexpr double a = 0.659027622374092, b = 0.231933368553031, c = 0.109039009072877;
-    constexpr double T[6][2] = {{a, b}, {a, c}, {b, a}, {b, c}, {c, a}, {c, b}};
+    static constexpr double T[6][2] = {{a, b}, {a, c}, {b, a}, {b, c}, {c, a}, {c, b}};
     xi = T[i][0]; et = T[i][1]; w = 1.0 / 12;
   } else if constexpr (Q == 4) {
     constexpr double a = 0.816847572980459, b = 0.091576213509771;
     constexpr double c = 0.108103018168070, d = 0.445948490915965;
-    constexpr double T[6][2] = {{a, b}, {b, a}, {b, b}, {c, d}, {d, c}, {d, d}};
+    static constexpr double T[6][2] = {{a, b}, {b, a}, {b, b}, {c, d}, {d, c}, {d, d}};
     xi = T[i][0]; et = T[i][1];
     w = i < 3 ? 0.109951743655322 / 2 : 0.223381589678011 / 2;
   } else if constexpr (Q == 5) {
     constexpr double a = 0.79742698535308720, b = 0.10128650732345633;
     constexpr double c = 0.05971587178976981, d = 0.47014206410511505;
-    constexpr double T[7][2] = {{1.0 / 3, 1.0 / 3}, {a, b}, {b, a}, {b, b}, {c, d}, {d, c}, {d, d}};
+    static constexpr double T[7][2] = {{1.0 / 3, 1.0 / 3}, {a, b}, {b, a}, {b, b}, {c, d}, {d, c}, {d, d}};
     xi = T[i][0]; et = T[i][1];
     w = i == 0 ? 0.225 / 2 : (i < 4 ? 0.12593918054482717 / 2 : 0.13239415278850616 / 2);
   } else if constexpr (Q == 6) {
     constexpr double a1 = 0.873821971016996, b1 = 0.063089014491502;
     constexpr double a2 = 0.501426509658179, b2 = 0.249286745170910;
     constexpr double a = 0.636502499121399, b = 0.310352451033785, c = 0.053145049844816;
-    constexpr double T[12][2] = {{a1, b1}, {b1, a1}, {b1, b1}, {a2, b2}, {b2, a2}, {b2, b2},
+    static constexpr double T[12][2] = {{a1, b1}, {b1, a1}, {b1, b1}, {a2, b2}, {b2, a2}, {b2, b2},
                                  {a, b}, {b, a}, {a, c}, {c, a}, {b, c}, {c, b}};
     xi = T[i][0]; et = T[i][1];
     w = i < 3 ? 0.050844906370207 / 2 : (i < 6 ? 0.116786275726379 / 2 : 0.082851075618374 / 2);

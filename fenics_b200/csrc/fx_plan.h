@@ -1,0 +1,87 @@
+// Internal: the plan object behind the C ABI (device-resident mesh, dofmaps, patterns, scratch).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fenics_b200.h"
+#include "fx_assemble.h"
+
+namespace fx {
+
+std::string& last_error();
+void count_launch(int n);
+int set_error(int code, const char* fmt, ...);
+
+#define FX_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fx::set_error(FX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                           __FILE__, __LINE__);                                                \
+  } while (0)
+
+struct DevPattern {
+  int n = 0, nnz = 0, ld = 0;
+  bool present = false, has_csr = false;
+  int* rowptr = nullptr;
+  int* col = nullptr;
+  uint8_t* pos = nullptr;
+  int* dm_t = nullptr;
+};
+
+constexpr int KRYLOV_NWORK = 8;
+constexpr int RED_SLOTS = 4;       // values reduced at once
+constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
+
+}  // namespace fx
+
+struct fx_plan {
+  int device = 0, num_sms = 0;
+  int nv = 0, nc = 0, nbf = 0;
+  double* xy = nullptr;
+  int* cells = nullptr;
+  double* geom = nullptr;
+  int *bf_cell = nullptr, *bf_local = nullptr, *bf_marker = nullptr;
+  double* bf_geo = nullptr;
+  fx::DevPattern sp[fx::S_N];
+  // scratch
+  double* part = nullptr;      // per-block partial sums of functionals / dots
+  int part_cap = 0;
+  double* scal = nullptr;      // device scalars (results of fx_assemble_scalar etc.)
+  double* work = nullptr;      // Krylov work vectors, KRYLOV_NWORK x work_n
+  size_t work_n = 0;
+  double* red = nullptr;       // grid-reduction scratch 2 x RED_SLOTS x MAX_GRID
+  fx_solve_info* info = nullptr;  // device, FX_NTICKETS result slots
+
+  fx::MeshView view() const {
+    fx::MeshView m;
+    m.nc = nc; m.geom = geom;
+    for (int s = 0; s < fx::S_N; ++s) m.dm[s] = sp[s].dm_t;
+    m.nbf = nbf; m.bf_cell = bf_cell; m.bf_local = bf_local; m.bf_marker = bf_marker; m.bf_geo = bf_geo;
+    return m;
+  }
+};
+
+namespace fx {
+int ensure_work(fx_plan* plan, size_t n);
+// launchers implemented in fx_asm.cu
+int launch_geometry(fx_plan* plan, cudaStream_t st);
+int launch_matrix(fx_plan* plan, int form, const AsmArgs& base, cudaStream_t st);
+int launch_vector(fx_plan* plan, int form, const AsmArgs& base, cudaStream_t st);
+int launch_scalar(fx_plan* plan, int form, const AsmArgs& base, double* out_dev, cudaStream_t st);
+int launch_dg0(fx_plan* plan, int expr, const AsmArgs& base, cudaStream_t st);
+int form_info(int form, int* rank, int* space, int* qdeg);
+// fx_la.cu
+int la_spmv(fx_plan* plan, int space, const double* val, const double* x, double* y, cudaStream_t st);
+int la_apply_bc(fx_plan* plan, int space, double* val, double* b, const int* rows, const double* g, int n,
+                cudaStream_t st);
+int la_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st);
+int la_dot(fx_plan* plan, int n, const double* x, const double* y, double* out_dev, cudaStream_t st);
+int la_norm(fx_plan* plan, int n, const double* x, int kind, double* out_dev, cudaStream_t st);
+int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
+              double rtol, double atol, int maxit, int ticket, cudaStream_t st);
+}  // namespace fx

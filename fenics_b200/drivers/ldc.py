@@ -1,0 +1,250 @@
+"""Lid-driven-cavity time loops on the GPU:
+
+  IncompLDC  config 1  lid-driven-cavity/incomp_LDC.py:280-447   (incompressible Oldroyd-B)
+  CompLDC    config 2  lid-driven-cavity/comp_LDC_mesh_convergence.py:376-565 (compressible Oldroyd-B)
+
+Each `step()` issues the same sequence of assemble / bc.apply / solve / project calls as the reference
+loop body, in the same order (forms see the coefficient values present at assemble time).  All fields
+stay on the device; per step only the energies (and solver outcomes) reach the host.
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _abi as abi
+from .. import la
+from .._lib import check, lib
+from ..dolfin_api import (ConsistentProjection, DirichletBC, Function, Problem, assemble,
+                          assemble_scalar_async, project)
+from ..la import Matrix, Plan, Vector
+from ..mesh import DOLFIN_EPS
+from ..spaces import function_spaces
+
+
+def lid_bcs(W, L=1.0):
+    """bcu = [noslip, drive1] (incomp_LDC.py:171-226); returns (bcs, time holder)."""
+    top_bound = 1.0
+    tt = {"t": 0.0}
+
+    def ulidreg(x):  # Expression(('8*(1.0+tanh(8*t-4.0))*(x[0]*(L-x[0]))*(x[0]*(L-x[0]))','0'))
+        f = 8 * (1.0 + np.tanh(8 * tt["t"] - 4.0)) * (x[:, 0] * (L - x[:, 0])) ** 2
+        return np.column_stack([f, np.zeros_like(f)])
+
+    noslip = DirichletBC(W.sub(0), (0.0, 0.0), lambda x, on_boundary: np.ones(np.shape(x[0]), dtype=bool) & on_boundary)
+    drive1 = DirichletBC(W.sub(0), ulidreg, lambda x, on_boundary: (x[1] > top_bound - DOLFIN_EPS) & on_boundary)
+    return [noslip, drive1], tt
+
+
+class _LDC:
+    solver = ("bicgstab", "default")   # what the reference passes to solve()
+    pressure_method = "bicgstab"       # reference; "cg" is the north_star upgrade (A5 is symmetric)
+    STATE_FIELDS = ()                  # fields carried from step to step (host<->device in e2e mode)
+
+    def _setup(self, mesh, dofmaps, device):
+        self.mesh = mesh
+        W, V, _, _, Zd, Zc, Q, Qt, _ = function_spaces(mesh, 2, dofmaps)
+        self.S = dict(W=W, V=V, Zd=Zd, Zc=Zc, Q=Q, Qt=Qt)
+        self.plan = Plan(mesh, [W, Zc, Q, Zd, Qt, V], device)
+        self.pr = Problem(self.plan)
+        for k, v in self.p.items():
+            self.pr.set_param(getattr(abi, "FX_P_" + k.upper()), v)
+        F = lambda s: Function(self.S[s], self.plan)  # noqa: E731
+        b = self.pr.bind
+        self.w0, self.w12, self.ws, self.w1 = (b(s, F("W")) for s in (abi.FX_F_W0, abi.FX_F_W12, abi.FX_F_WS, abi.FX_F_W1))
+        self.p0, self.p1 = b(abi.FX_F_P0, F("Q")), b(abi.FX_F_P1, F("Q"))
+        self.tau0_vec, self.tau1_vec = b(abi.FX_F_TAU0, F("Zc")), b(abi.FX_F_TAU1, F("Zc"))
+        self.kapp = b(abi.FX_F_KAPP, F("Qt"))
+        self.res_test = b(abi.FX_F_RES_TEST, F("Zd"))
+        self.res_orth = b(abi.FX_F_RES_ORTH, F("Zc"))
+        self.res_orth_norm_sq = b(abi.FX_F_QT_A, F("Qt"))
+        self.err = F("Qt")
+        self.bcu, self._bct = lid_bcs(W)
+        # reusable tensors (the reference allocates new PETSc objects on every assemble() call)
+        self.AW, self.AZ, self.AQ = Matrix(self.plan, "W"), Matrix(self.plan, "Zc"), Matrix(self.plan, "Q")
+        self.bW, self.bZ, self.bQ = Vector(self.plan, "W"), Vector(self.plan, "Zc"), Vector(self.plan, "Q")
+        self.scal = torch.zeros(8, dtype=torch.float64, device="cuda:%d" % self.plan.device)
+        self._scal_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+        f = self.pr.form
+        self.proj_res_orth = ConsistentProjection(f(abi.FX_FORM_MASS_ZC), f(abi.FX_FORM_LDC_L_RES_ORTH))
+        self.solve_rtol = None       # None -> parameters["krylov_solver"] (PETSc default 1e-5)
+        self.projection_rtol = None  # None -> 1e-13 (dolfin's project uses LU)
+        self.check = True            # synchronous convergence check after every solve (dolfin behaviour)
+        self.last_info = []
+        self.solve_labels = []
+        self._ticket = 0
+        self.profile = None          # set to a list to record (label, start_event, end_event) per phase
+
+    # -- helpers -------------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def _phase(self, label):
+        if self.profile is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.profile.append((label, e0, e1))
+
+    def _solve(self, A, x, b, method=None, pc=None, rtol=None, label=""):
+        method = method or self.solver[0]
+        pc = pc or self.solver[1]
+        rtol = self.solve_rtol if rtol is None else rtol
+        self.solve_labels.append("%s:%s:%s" % (label, A.space, method))
+        with self._phase("solve:%s:%s:%s" % (label, A.space, method)):
+            if self.check:
+                self.last_info.append(la.krylov_solve(A, x.vector(), b, method, pc, rtol=rtol))
+            else:
+                la.krylov_solve(A, x.vector(), b, method, pc, rtol=rtol, ticket=self._ticket)
+                self._ticket += 1
+
+    def _project_consistent(self, proj, out, A, b, label):
+        with self._phase("assemble_matrix:%s:%s" % (label, A.space)):
+            assemble(proj.mass_form, tensor=A)
+        with self._phase("assemble_vector:%s:%s" % (label, A.space)):
+            assemble(proj.rhs_form, tensor=b)
+        rtol = 1e-13 if self.projection_rtol is None else self.projection_rtol
+        self._solve(A, out, b, "cg", "jacobi", rtol=rtol, label=label)
+
+    def lps_indicator(self):
+        """kappa of the LPS stabilisation (incomp_LDC.py:300-308 == comp_LDC_mesh_convergence.py:393-401)."""
+        e = self.pr.expr
+        with self._phase("project_dg0:restau"):
+            project(e(abi.FX_EXPR_LDC_RESTAU), self.S["Zd"], function=self.res_test)
+        self._project_consistent(self.proj_res_orth, self.res_orth, self.AZ, self.bZ, "res_orth")
+        with self._phase("project_dg0:kappa"):
+            project(e(abi.FX_EXPR_RES_ORTH_SQ), self.S["Qt"], function=self.res_orth_norm_sq)
+            project(e(abi.FX_EXPR_SQRT_QT_A), self.S["Qt"], function=self.kapp)
+
+    def _system(self, label, a_id, L_id, A, b, x, bcs=(), **kw):
+        f = self.pr.form
+        with self._phase("assemble_matrix:%s:%s" % (label, A.space)):
+            assemble(f(a_id), tensor=A)
+        with self._phase("assemble_vector:%s:%s" % (label, A.space)):
+            assemble(f(L_id), tensor=b)
+        if bcs:
+            with self._phase("bc:%s" % label):
+                for bc in bcs:
+                    bc.apply(A, b)
+        self._solve(A, x, b, label=label, **kw)
+
+    def _begin_step(self):
+        self.last_info, self.solve_labels, self._ticket = [], [], 0
+
+    def _finish_step(self):
+        """one host sync per step: energies (+ solver outcomes when running asynchronously)."""
+        if not self.check:
+            infos = la.solve_results(self.plan, 0, self._ticket)
+            self.last_info = infos
+            bad = [i for i, s in enumerate(infos) if s.converged != 1]
+            if bad:
+                s = infos[bad[0]]
+                raise RuntimeError("*** Error: Unable to solve linear system: solve %s of the step: %d iterations, "
+                                   "residual %.3e, status %d" % (self.solve_labels[bad[0]], s.iterations, s.residual,
+                                                                 s.converged))
+        self._scal_host.copy_(self.scal, non_blocking=False)
+        return self._scal_host.numpy()
+
+    # -- host <-> device state transfer (end-to-end mode of bench.py, I/O hand-off) -----------------
+    def state_functions(self):
+        return [getattr(self, n) for n in self.STATE_FIELDS]
+
+    def result_functions(self):
+        return [getattr(self, n) for n in self.RESULT_FIELDS]
+
+
+class IncompLDC(_LDC):
+    STATE_FIELDS = ("w0", "p0", "tau0_vec", "w1", "tau1_vec")
+    RESULT_FIELDS = ("w1", "p1", "tau1_vec")
+
+    def __init__(self, mesh, dofmaps=None, dt=0.005, Re=0.5, We=0.25, betav=0.5, c1=0.05, c2=0.01, th=1.0,
+                 conv=None, device=None):
+        if conv is None:
+            conv = 0.0 if Re < 1 else 1.0  # incomp_LDC.py:49,93-94
+        self.p = dict(dt=dt, Re=Re, We=We, betav=betav, c1=c1, c2=c2, th=th, conv=conv)
+        self._setup(mesh, dofmaps, device)
+        self.t = dt  # :277
+        self.err_array = []
+
+    def step(self):
+        self._begin_step()
+        self._bct["t"] = self.t  # ulidreg.t = t  :293
+        self.lps_indicator()  # :300-309
+        self._system("u12", abi.FX_FORM_C1_A1, abi.FX_FORM_C1_L1, self.AW, self.bW, self.w12, self.bcu)  # :317-331
+        self._system("us", abi.FX_FORM_C1_A2, abi.FX_FORM_C1_L2, self.AW, self.bW, self.ws, self.bcu)  # :355-363
+        self._system("p", abi.FX_FORM_C1_A5, abi.FX_FORM_C1_L5, self.AQ, self.bQ, self.p1, (),
+                     method=self.pressure_method)  # :370-375 (bcp = [])
+        self._system("u1", abi.FX_FORM_C1_A7, abi.FX_FORM_C1_L7, self.AW, self.bW, self.w1, self.bcu)  # :379-394
+        self._system("tau", abi.FX_FORM_C1_A4, abi.FX_FORM_C1_L4, self.AZ, self.bZ, self.tau1_vec, ())  # :400-416
+        f = self.pr.form
+        with self._phase("functionals"):
+            assemble_scalar_async(f(abi.FX_FORM_C1_EK), self.scal, 0)  # :420
+            assemble_scalar_async(f(abi.FX_FORM_C1_EE), self.scal, 1)  # :421
+            t_rec = self.t
+            self.t += self.p["dt"]  # :429
+            project(self.pr.expr(abi.FX_EXPR_H_KAPP), self.S["Qt"], function=self.err)  # :434
+            ev = self.err.vector()
+            check(lib.fx_norm_dev(self.plan.h, ev.size(), la._ptr(ev.t), 0, C.c_void_p(self.scal.data_ptr() + 16),
+                                  la._stream()))  # norm(err.vector(),'l2') :435
+        vals = self._finish_step()
+        self.err_array.append(float(vals[2]))
+        diverged = False
+        if self.t > 0.5 and len(self.err_array) > 1 and self.err_array[-2] != 0.0:
+            diverged = self.err_array[-1] / self.err_array[-2] > 1.1  # :437-441
+        self.w0.assign(self.w1)  # :444-447
+        self.p0.assign(self.p1)
+        self.tau0_vec.assign(self.tau1_vec)
+        return dict(t=t_rec, E_k=float(vals[0]), E_e=float(vals[1]), err=self.err_array[-1], diverged=diverged)
+
+    def fields(self):
+        p = self.p1.vector().get_local()
+        return dict(w1=self.w1.vector().get_local(), p1=p - p.mean(), tau1=self.tau1_vec.vector().get_local(),
+                    kapp=self.kapp.vector().get_local())
+
+
+class CompLDC(_LDC):
+    STATE_FIELDS = ("w0", "p0", "tau0_vec", "rho0", "w1", "tau1_vec")
+    RESULT_FIELDS = ("w1", "p1", "tau1_vec", "rho1")
+
+    def __init__(self, mesh, dofmaps=None, dt=0.001, Re=10.0, We=0.25, Ma=0.001, betav=0.5, c1=0.1, c2=0.01,
+                 th=1.0, conv=1.0, device=None):
+        self.p = dict(dt=dt, Re=Re, We=We, Ma=Ma, betav=betav, c1=c1, c2=c2, th=th, conv=conv)
+        self._setup(mesh, dofmaps, device)
+        b, F = self.pr.bind, lambda s: Function(self.S[s], self.plan)  # noqa: E731
+        self.rho0, self.rho12, self.rho1 = b(abi.FX_F_RHO0, F("Q")), b(abi.FX_F_RHO12, F("Q")), b(abi.FX_F_RHO1, F("Q"))
+        f = self.pr.form
+        self.proj_rho1 = ConsistentProjection(f(abi.FX_FORM_MASS_Q), f(abi.FX_FORM_C2_L_RHO1))
+        self.rho0.vector().t.fill_(1.0)  # rho0 = project(1.0, Q)  :285-286
+        self.t = dt  # :373
+
+    def step(self):
+        self._begin_step()
+        self._bct["t"] = self.t
+        self.lps_indicator()  # :393-402
+        self._system("rho12", abi.FX_FORM_C2_A0, abi.FX_FORM_C2_L0, self.AQ, self.bQ, self.rho12, ())  # :417-426
+        self._system("u12", abi.FX_FORM_C2_A1, abi.FX_FORM_C2_L1, self.AW, self.bW, self.w12, self.bcu)  # :430-447
+        self._system("us", abi.FX_FORM_C2_A2, abi.FX_FORM_C2_L2, self.AW, self.bW, self.ws, self.bcu)  # :458-476
+        self._system("p", abi.FX_FORM_C2_A5, abi.FX_FORM_C2_L5, self.AQ, self.bQ, self.p1, (),
+                     method=self.pressure_method)  # :483-497
+        self._project_consistent(self.proj_rho1, self.rho1, self.AQ, self.bQ, "rho1")  # :501-502
+        self._system("u1", abi.FX_FORM_C2_A7, abi.FX_FORM_C2_L7, self.AW, self.bW, self.w1, self.bcu)  # :506-519
+        self._system("tau", abi.FX_FORM_C2_A4, abi.FX_FORM_C2_L4, self.AZ, self.bZ, self.tau1_vec, ())  # :528-544
+        f = self.pr.form
+        with self._phase("functionals"):
+            assemble_scalar_async(f(abi.FX_FORM_C2_EK), self.scal, 0)  # :548
+            assemble_scalar_async(f(abi.FX_FORM_C2_EE), self.scal, 1)  # :549
+        vals = self._finish_step()
+        t_rec = self.t
+        self.w0.assign(self.w1)  # :558-562
+        self.rho0.assign(self.rho1)
+        self.p0.assign(self.p1)
+        self.tau0_vec.assign(self.tau1_vec)
+        self.t += self.p["dt"]
+        return dict(t=t_rec, E_k=float(vals[0]), E_e=float(vals[1]))
+
+    def fields(self):
+        g = lambda f: f.vector().get_local()  # noqa: E731
+        return dict(w1=g(self.w1), p1=g(self.p1), tau1=g(self.tau1_vec), rho1=g(self.rho1), rho12=g(self.rho12),
+                    kapp=g(self.kapp))

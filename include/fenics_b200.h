@@ -105,6 +105,10 @@ typedef struct {
 
 const char* fx_last_error(void);
 int fx_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long fx_launch_count(void);
+/* synchronous device -> host copy of plan-owned data (patterns, geometry) for inspection/tests */
+int fx_copy_to_host(void* dst_host, const void* src_dev, long long nbytes);
 
 /* ---- plan: mesh + dofmaps -> device-resident geometry, CSR patterns, scatter maps ----------
  * Replaces what dolfin builds on every assemble() call (SparsityPatternBuilder, DofMap tabulation;
@@ -155,17 +159,27 @@ int fx_dot(fx_plan* plan, int n, const double* x_dev, const double* y_dev, doubl
            void* stream);                      /* synchronous */
 int fx_norm(fx_plan* plan, int n, const double* x_dev, int kind /*0 l2, 1 linf*/, double* out_host,
             void* stream);                     /* synchronous; norm(vec,'l2'|'linf')          */
+/* asynchronous variants: the result lands in out_dev[0] */
+int fx_dot_dev(fx_plan* plan, int n, const double* x_dev, const double* y_dev, double* out_dev,
+               void* stream);
+int fx_norm_dev(fx_plan* plan, int n, const double* x_dev, int kind, double* out_dev, void* stream);
 
 /* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default
- * for left preconditioning).  Synchronous when `info` is non-NULL (waits, fills info, returns
- * FX_ERR_NOCONV on failure); fully asynchronous when info==NULL (poll fx_solve_result later). */
+ * for left preconditioning).  Synchronous: waits for the solve, fills *info (may be NULL) and
+ * returns FX_ERR_NOCONV on failure, like dolfin's RuntimeError.                                 */
 int fx_krylov_solve(fx_plan* plan, int space, const double* val_dev, double* x_dev,
                     const double* b_dev, int method, int pc, double rtol, double atol, int maxit,
                     fx_solve_info* info, void* stream);
-/* result of the most recent asynchronous solve on `space` (synchronises `stream`) */
-int fx_solve_result(fx_plan* plan, int space, fx_solve_info* info, void* stream);
+/* Asynchronous variant: returns after enqueueing; the outcome is written to the plan's result slot
+ * `ticket` (0 <= ticket < FX_NTICKETS) and fetched later with fx_solve_results.                */
+#define FX_NTICKETS 64
+int fx_krylov_solve_async(fx_plan* plan, int space, const double* val_dev, double* x_dev,
+                          const double* b_dev, int method, int pc, double rtol, double atol,
+                          int maxit, int ticket, void* stream);
+/* waits for `stream`, copies result slots [first, first+count) to info_host */
+int fx_solve_results(fx_plan* plan, int first, int count, fx_solve_info* info_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,231 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libfenics_b200.so) and is checked against the oracle on the same seeded inputs.
+
+Tolerances (north_star): assembled matrices/vectors 1e-12 relative, fields after K steps 1e-8 relative;
+sparsity patterns bit-exact."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+import fxt_common as lc
+from fenics_b200 import _abi as abi
+from oracle import configs, fem
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from fenics_b200 import dolfin_api as dapi  # noqa: E402
+from fenics_b200 import la, mesh as pmesh  # noqa: E402
+from fenics_b200.drivers import ldc  # noqa: E402
+
+TOL = 1e-12
+
+
+def _pair(kind, n=6, shuffle=False, **kw):
+    """(oracle config, gpu driver) on the same mesh with the SAME dof numbering."""
+    m = pmesh.Skew_Mesh(n, 1, 1)
+    drv_cls = ldc.IncompLDC if kind == 1 else ldc.CompLDC
+    ocl_cls = configs.IncompLDC if kind == 1 else configs.CompLDC
+    dofmaps = None
+    if shuffle:
+        tmp = drv_cls(m, **kw)
+        rng = np.random.default_rng(3)
+        dofmaps = {k: rng.permutation(s.dim())[s.cell_dofs].astype(np.int32) for k, s in tmp.S.items()}
+        del tmp
+    drv = drv_cls(m, dofmaps=dofmaps, **kw)
+    om = fem.Mesh(m.coordinates(), m.cells())
+    assert np.array_equal(om.bfacet_cell, m.bfacet_cell) and np.array_equal(om.bfacet_local, m.bfacet_local)
+    ocl = ocl_cls(om, dofmaps={k: s.cell_dofs for k, s in drv.S.items()}, **kw)
+    return ocl, drv
+
+
+def _push_state(ocl, drv):
+    for slot, attr in lc.FIELD_ATTR.items():
+        fo, fd = getattr(ocl, attr, None), getattr(drv, attr, None)
+        if fo is not None and fd is not None:
+            fd.vector().set_local(fo.vec)
+
+
+def test_geometry_and_patterns_bit_exact():
+    ocl, drv = _pair(2, n=7, shuffle=True)
+    g = drv.plan.geometry_host()
+    assert lc.rel_err(g[4], np.abs(ocl.mesh.detJ)) < 1e-15 and lc.rel_err(g[5], ocl.mesh.h) < 1e-15
+    from oracle.ufl_lite import dx, inner
+    for name in ("W", "Zc", "Q"):
+        rp, col = drv.plan.pattern_host(name)
+        A = fem.assemble(inner(fem.TrialFunction(ocl.S[name]), fem.TestFunction(ocl.S[name])) * dx)
+        assert np.array_equal(rp, A.indptr) and np.array_equal(col, A.indices)
+
+
+@pytest.mark.parametrize("kind,shuffle", [(1, False), (1, True), (2, False), (2, True)])
+def test_forms_match_oracle(kind, shuffle):
+    ocl, drv = _pair(kind, shuffle=shuffle)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    table = lc.C1_FORMS if kind == 1 else lc.C2_FORMS
+    for name, (fid, space) in table.items():
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        if name.startswith("a"):
+            err = lc.csr_rel_err(got.to_scipy(), ref)
+        else:
+            err = lc.rel_err(got.get_local(), ref)
+        assert err < TOL, (name, err)
+    ek = abi.FX_FORM_C1_EK if kind == 1 else abi.FX_FORM_C2_EK
+    ee = abi.FX_FORM_C1_EE if kind == 1 else abi.FX_FORM_C2_EE
+    r = fem.assemble(ocl.E_k_form)
+    assert abs(dapi.assemble(drv.pr.form(ek)) - r) < TOL * abs(r)
+    r = fem.assemble(ocl.E_e_form)
+    assert abs(dapi.assemble(drv.pr.form(ee)) - r) < 1e-11 * max(1.0, abs(r))
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_lps_indicator_matches_oracle(kind):
+    ocl, drv = _pair(kind)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    ocl._lps_indicator()
+    drv.lps_indicator()
+    assert lc.rel_err(drv.res_test.vector().get_local(), ocl.last["res_test"]) < TOL
+    assert lc.rel_err(drv.res_orth.vector().get_local(), ocl.last["res_orth"]) < 1e-10
+    assert lc.rel_err(drv.res_orth_norm_sq.vector().get_local(), ocl.last["res_orth_norm_sq"]) < 1e-10
+    assert lc.rel_err(drv.kapp.vector().get_local(), ocl.last["kapp"]) < 1e-10
+
+
+def test_bc_apply_matches_oracle():
+    ocl, drv = _pair(1)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    for o, d in ((ocl, drv),):
+        o._bct["t"] = d._bct["t"] = 0.45
+    A, b = fem.assemble(ocl.forms["a1"]), fem.assemble(ocl.forms["L1"])
+    [bc.apply(A, b) for bc in ocl.bcu]
+    Ad, bd = dapi.assemble(drv.pr.form(abi.FX_FORM_C1_A1)), dapi.assemble(drv.pr.form(abi.FX_FORM_C1_L1))
+    [bc.apply(Ad, bd) for bc in drv.bcu]
+    for bo, bdv in zip(ocl.bcu, drv.bcu):
+        assert np.array_equal(bo.dofs, bdv.dofs)
+    assert lc.csr_rel_err(Ad.to_scipy(), A) < TOL
+    assert lc.rel_err(bd.get_local(), b) < TOL
+
+
+def test_spmv_and_blas1():
+    ocl, drv = _pair(2, n=9)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    rng = np.random.default_rng(0)
+    for name, fid in (("W", abi.FX_FORM_C2_A1), ("Zc", abi.FX_FORM_C2_A4), ("Q", abi.FX_FORM_C2_A5)):
+        A = dapi.assemble(drv.pr.form(fid))
+        x = la.Vector(drv.plan, name)
+        xv = rng.standard_normal(x.size())
+        x.set_local(xv)
+        y = A * x
+        assert lc.rel_err(y.get_local(), A.to_scipy() @ xv) < 1e-13
+        # linearity: A(ax+z) = aAx + Az
+        z = la.Vector(drv.plan, name)
+        zv = rng.standard_normal(x.size())
+        z.set_local(zv)
+        z.axpy(2.5, x)
+        assert lc.rel_err((A * z).get_local(), A.to_scipy() @ (zv + 2.5 * xv)) < 1e-13
+        assert abs(x.inner(z) - xv @ (zv + 2.5 * xv)) < 1e-12 * abs(xv @ (zv + 2.5 * xv))
+        assert abs(x.norm("l2") - np.linalg.norm(xv)) < 1e-13 * np.linalg.norm(xv)
+        assert x.norm("linf") == np.abs(xv).max()
+
+
+@pytest.mark.parametrize("method,pc", [("bicgstab", "jacobi"), ("bicgstab", "none"), ("cg", "jacobi")])
+def test_krylov_against_direct(method, pc):
+    ocl, drv = _pair(2, n=10)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    rng = np.random.default_rng(1)
+    cases = [("Q", abi.FX_FORM_C2_A5), ("Zc", abi.FX_FORM_MASS_ZC)]
+    if method == "bicgstab":
+        cases.append(("W", abi.FX_FORM_C2_A7))
+    for name, fid in cases:
+        A = dapi.assemble(drv.pr.form(fid))
+        b = la.Vector(drv.plan, name)
+        bv = rng.standard_normal(b.size())
+        b.set_local(bv)
+        x = la.Vector(drv.plan, name)
+        info = la.krylov_solve(A, x, b, method, pc, rtol=1e-13, maxit=20000)
+        ref = spla.splu(A.to_scipy().tocsc()).solve(bv)
+        assert info.converged == 1 and info.iterations > 0
+        assert lc.rel_err(x.get_local(), ref) < 1e-9, (name, info.iterations)
+        # warm start from the converged solution returns immediately
+        info2 = la.krylov_solve(A, x, b, method, pc, rtol=1e-10)
+        assert info2.iterations == 0
+
+
+def test_krylov_nonconvergence_raises():
+    ocl, drv = _pair(2, n=8)
+    A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
+    b = la.Vector(drv.plan, "Q")
+    b.set_local(np.random.default_rng(2).standard_normal(b.size()))
+    x = la.Vector(drv.plan, "Q")
+    with pytest.raises(RuntimeError):
+        la.krylov_solve(A, x, b, "cg", "jacobi", rtol=1e-14, maxit=2)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_k_steps_match_oracle(kind):
+    """fields after K steps within 1e-8 relative (north_star); oracle solves exactly (LU), the GPU
+    Krylov solves are tightened to 1e-13."""
+    K = 4
+    ocl, drv = _pair(kind, n=8)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    for o in (ocl, drv):
+        o.t = 0.45  # lid speed ramp is O(1) here (8(1+tanh(8t-4)))
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        assert abs(ro["E_k"] - rd["E_k"]) < 1e-8 * abs(ro["E_k"])
+        assert abs(ro["E_e"] - rd["E_e"]) < 1e-8 * max(abs(ro["E_e"]), 1e-12)
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+    assert all(i.converged == 1 for i in drv.last_info)
+
+
+def test_async_step_equals_sync_step():
+    _, a = _pair(2, n=8)
+    _, b = _pair(2, n=8)
+    b.check = False
+    for d in (a, b):
+        d.t = 0.45
+        d.solve_rtol = 1e-12
+    for _ in range(2):
+        ra, rb = a.step(), b.step()
+    assert ra["E_k"] == rb["E_k"] and ra["E_e"] == rb["E_e"]  # deterministic kernels: bitwise equal
+    assert len(b.last_info) == 8 and all(i.converged == 1 for i in b.last_info)
+
+
+def test_full_size_properties():
+    """n=192 (999 558 DOFs, BASELINE.json): size-independent identities."""
+    m = pmesh.Skew_Mesh(192, 1, 1)
+    drv = ldc.CompLDC(m)
+    assert drv.S["W"].dim() + drv.S["Zc"].dim() + drv.S["Q"].dim() == 999558
+    n, nnz, _, _ = drv.plan.pattern("W")
+    assert (n, nnz) == (517634, 12767236)
+    assert drv.plan.pattern("Zc")[1] == 15289353 and drv.plan.pattern("Q")[1] == 259201
+    # mass matrix: sum of all entries = area of the (mapped) unit square; rows of the stiffness sum to 0
+    MQ = dapi.assemble(drv.pr.form(abi.FX_FORM_MASS_Q))
+    one = la.Vector(drv.plan, "Q")
+    one.t.fill_(1.0)
+    area = one.inner(MQ * one)
+    assert abs(area - 1.0) < 1e-10
+    K = dapi.assemble(drv.pr.form(abi.FX_FORM_C1_A5))
+    assert (K * one).norm("linf") < 1e-11
+    # solve + residual check on the big W system
+    drv.t = 0.45
+    drv.solve_rtol = 1e-10
+    r = drv.step()
+    assert np.isfinite(r["E_k"]) and r["E_k"] > 0
+    A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A7))
+    b = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_L7))
+    x = la.Vector(drv.plan, "W")
+    info = la.krylov_solve(A, x, b, "bicgstab", "jacobi", rtol=1e-12)
+    res = A * x
+    res.axpy(-1.0, b)
+    assert res.norm("l2") < 1e-9 * b.norm("l2"), info.iterations
