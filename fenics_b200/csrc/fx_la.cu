@@ -278,8 +278,17 @@ __global__ void __launch_bounds__(256) k_bicgstab(const __grid_constant__ KArgs 
   if (!(rn == rn)) { finish(a, 0, -1, rn, bn); return; }
   if (rn <= tol) { finish(a, 0, 1, rn, bn); return; }
   double rho = acc[0], rho_old = 1.0, alpha = 1.0, omega = 1.0;
+  double rhn = rn;  // ||rhat||
+  int restarts = 0;
   for (int it = 1; it <= a.maxit; ++it) {
-    if (rho == 0.0 || omega == 0.0) { finish(a, it - 1, -1, rn, bn); return; }
+    // (rhat, r) ~ 0 or omega ~ 0: the recurrence has broken down (e.g. a residual supported on
+    // Dirichlet rows only is annihilated in one step, leaving rhat orthogonal to r).  Restart with
+    // rhat = r, the standard cure; give up after a few consecutive restarts.
+    if (fabs(rho) <= 1e-14 * rhn * rn || omega == 0.0) {
+      if (++restarts > 50) { finish(a, it - 1, -1, rn, bn); return; }
+      for (int i = gt; i < n; i += gs) { rh[i] = r[i]; p[i] = 0.0; v[i] = 0.0; }
+      rho = rn * rn; rhn = rn; rho_old = 1.0; alpha = 1.0; omega = 1.0;
+    }
     const double beta = (rho / rho_old) * (alpha / omega);
     for (int i = gt; i < n; i += gs) p[i] = r[i] + beta * (p[i] - omega * v[i]);
     grid.sync();

