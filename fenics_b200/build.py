@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 SO = os.path.join(HERE, "libfenics_b200.so")
-SOURCES = ["fx_asm.cu", "fx_la.cu", "fx_capi.cu"]
+SOURCES = ["fx_asm.cu", "fx_la.cu", "fx_krylov.cu", "fx_capi.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
@@ -24,7 +24,7 @@ def _nvcc():
 
 
 def _deps():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hs.append(os.path.join(HERE, "..", "include", "fenics_b200.h"))
     return hs
 

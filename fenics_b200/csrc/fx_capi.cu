@@ -116,6 +116,8 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
       if ((rc = upload(&d.rowptr, hp.rowptr.data(), hp.rowptr.size()))) return fail(rc);
       if ((rc = upload(&d.col, hp.col.data(), hp.col.size()))) return fail(rc);
       if ((rc = upload(&d.pos, hp.pos.data(), hp.pos.size()))) return fail(rc);
+      if ((rc = upload(&d.rowblk, hp.rowblk.data(), hp.rowblk.size()))) return fail(rc);
+      d.nrowblk = (int)hp.rowblk.size() - 1;
     }
     maxn = std::max(maxn, (size_t)hp.n);
   }
@@ -138,7 +140,7 @@ void fx_plan_destroy(fx_plan* P) {
   cudaFree(P->xy); cudaFree(P->cells); cudaFree(P->geom);
   cudaFree(P->bf_cell); cudaFree(P->bf_local); cudaFree(P->bf_marker); cudaFree(P->bf_geo);
   for (int s = 0; s < S_N; ++s) {
-    cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t);
+    cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
   }
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;

@@ -1,0 +1,263 @@
+// Krylov solvers (K9/K10 of SURVEY.md 2.3) as ONE persistent cooperative kernel per solve.
+//   * k_bicgstab: left-preconditioned BiCGStab, PETSc KSPBCGS semantics
+//   * k_cg:       preconditioned CG in the Chronopoulos-Gear form (one fused reduction per iteration)
+// SpMV (CSR-stream through shared memory), fused vector updates, dot products and the convergence test
+// all run on the device, separated by grid.sync(); reductions are deterministic two-stage sums so every
+// CTA takes the same branch.  Preconditioner: Jacobi (M = diag A) or none.
+// Replaces PETSc KSP behind dolfin solve(A, x, b, "bicgstab", "default")
+// (lid-driven-cavity/incomp_LDC.py:331 and every other solve site).
+#include <cooperative_groups.h>
+
+#include "fx_la_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fx {
+
+struct KArgs {
+  CsrView A;
+  double* x;
+  const double* b;
+  double* w;    // KRYLOV_NWORK x n work vectors
+  double* red;  // 2 x RED_SLOTS x MAX_GRID
+  double rtol, atol, dtol;
+  int maxit, pc;
+  fx_solve_info* info;
+};
+
+// Deterministic grid-wide sum of NV values: block partials -> scratch -> grid.sync -> every CTA sums
+// all partials in the same order (bitwise identical result in every CTA).  `phase` alternates the
+// scratch half so a fast CTA cannot overwrite partials a slow CTA is still reading.
+template <int NV>
+__device__ __forceinline__ void grid_sum(cg::grid_group& grid, double (&v)[NV], double* red, int& phase,
+                                         double* sh) {
+  double* buf = red + (size_t)(phase & 1) * RED_SLOTS * MAX_GRID;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = block_sum_bcast(v[i], sh);
+    if (threadIdx.x == 0) buf[i * MAX_GRID + blockIdx.x] = s;
+  }
+  grid.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) s += buf[i * MAX_GRID + j];
+    v[i] = block_sum_bcast(s, sh);
+  }
+  ++phase;
+}
+
+__device__ __forceinline__ void finish(const KArgs& a, int it, int conv, double rn, double bn) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.info->iterations = it;
+    a.info->converged = conv;
+    a.info->residual = rn;
+    a.info->residual0 = bn;
+  }
+}
+
+__device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc) {
+  if (pc != FX_PC_JACOBI) return 1.0;
+  double dg = 0.0;
+  for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j)
+    if (A.col[j] == row) dg = A.val[j];
+  return dg != 0.0 ? 1.0 / dg : 1.0;
+}
+
+// ---- BiCGStab -------------------------------------------------------------------------------------------
+// The recurrence runs on M^-1 A; the monitored norm is ||M^-1 r||_2 and the test is
+// ||r|| <= max(rtol ||M^-1 b||, atol) (PETSc default for left preconditioning).
+__global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constant__ KArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[33];
+  __shared__ double prod[SPMV_NNZB];
+  const CsrView& A = a.A;
+  const int n = A.n;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  double* r = a.w;
+  double* rh = a.w + (size_t)n;
+  double* p = a.w + 2 * (size_t)n;
+  double* v = a.w + 3 * (size_t)n;
+  double* s = a.w + 4 * (size_t)n;
+  double* t = a.w + 5 * (size_t)n;
+  double* dinv = a.w + 6 * (size_t)n;
+  int phase = 0;
+
+  // setup: dinv, r = M^-1 (b - A x), rhat = r, p = v = 0
+  double acc[2] = {0.0, 0.0};
+  spmv_stream(A, a.x, prod, [&](int row, double ax) {
+    const double di = row_diag_inv(A, row, a.pc);
+    const double ri = di * (a.b[row] - ax), bi = di * a.b[row];
+    dinv[row] = di; r[row] = ri; rh[row] = ri; p[row] = 0.0; v[row] = 0.0;
+    acc[0] += ri * ri; acc[1] += bi * bi;
+  });
+  grid_sum<2>(grid, acc, a.red, phase, sh);
+  double rn = sqrt(acc[0]);
+  const double bn = sqrt(acc[1]);
+  const double tol = fmax(a.rtol * bn, a.atol);
+  if (!(rn == rn)) { finish(a, 0, -1, rn, bn); return; }
+  if (rn <= tol) { finish(a, 0, 1, rn, bn); return; }
+  double rho = acc[0], rho_old = 1.0, alpha = 1.0, omega = 1.0;
+  double rhn = rn;  // ||rhat||
+  int restarts = 0;
+  for (int it = 1; it <= a.maxit; ++it) {
+    // (rhat, r) ~ 0 or omega ~ 0: the recurrence has broken down (e.g. a residual supported on
+    // Dirichlet rows only is annihilated in one step, leaving rhat orthogonal to r).  Restart with
+    // rhat = r, the standard cure.
+    if (fabs(rho) <= 1e-14 * rhn * rn || omega == 0.0) {
+      if (++restarts > 50) { finish(a, it - 1, -1, rn, bn); return; }
+      for (int i = gt; i < n; i += gs) { rh[i] = r[i]; p[i] = 0.0; v[i] = 0.0; }
+      rho = rn * rn; rhn = rn; rho_old = 1.0; alpha = 1.0; omega = 1.0;
+    }
+    const double beta = (rho / rho_old) * (alpha / omega);
+    for (int i = gt; i < n; i += gs) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+    grid.sync();
+    double d1[1] = {0.0};
+    spmv_stream(A, p, prod, [&](int row, double ap) {
+      const double vi = dinv[row] * ap;
+      v[row] = vi;
+      d1[0] += rh[row] * vi;
+    });
+    grid_sum<1>(grid, d1, a.red, phase, sh);
+    if (d1[0] == 0.0) { finish(a, it - 1, -1, rn, bn); return; }
+    alpha = rho / d1[0];
+    double d2[1] = {0.0};
+    for (int i = gt; i < n; i += gs) {
+      const double si = r[i] - alpha * v[i];
+      s[i] = si;
+      d2[0] += si * si;
+    }
+    grid_sum<1>(grid, d2, a.red, phase, sh);
+    if (sqrt(d2[0]) <= tol) {  // early exit on the half step (KSPBCGS does the same)
+      for (int i = gt; i < n; i += gs) a.x[i] += alpha * p[i];
+      finish(a, it, 1, sqrt(d2[0]), bn);
+      return;
+    }
+    double d3[2] = {0.0, 0.0};
+    spmv_stream(A, s, prod, [&](int row, double as) {
+      const double ti = dinv[row] * as;
+      t[row] = ti;
+      d3[0] += ti * s[row];
+      d3[1] += ti * ti;
+    });
+    grid_sum<2>(grid, d3, a.red, phase, sh);
+    if (d3[1] == 0.0) { finish(a, it, -1, sqrt(d2[0]), bn); return; }
+    omega = d3[0] / d3[1];
+    double d4[2] = {0.0, 0.0};
+    for (int i = gt; i < n; i += gs) {
+      a.x[i] += alpha * p[i] + omega * s[i];
+      const double ri = s[i] - omega * t[i];
+      r[i] = ri;
+      d4[0] += rh[i] * ri;
+      d4[1] += ri * ri;
+    }
+    grid_sum<2>(grid, d4, a.red, phase, sh);
+    rho_old = rho;
+    rho = d4[0];
+    rn = sqrt(d4[1]);
+    if (!(rn == rn) || rn > a.dtol * bn) { finish(a, it, -1, rn, bn); return; }
+    if (rn <= tol) { finish(a, it, 1, rn, bn); return; }
+  }
+  finish(a, a.maxit, 0, rn, bn);
+}
+
+// ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
+// u = M^-1 r, w = A u, p = u + beta p, s = w + beta s (= A p).  One SpMV and ONE fused reduction
+// (gamma = (r,u), delta = (w,u), ||u||^2) per iteration: two grid barriers instead of three.
+// Monitored norm ||M^-1 r||_2 (PETSc default for KSPCG).
+__global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[33];
+  __shared__ double prod[SPMV_NNZB];
+  const CsrView& A = a.A;
+  const int n = A.n;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  double* r = a.w;
+  double* u = a.w + (size_t)n;
+  double* w = a.w + 2 * (size_t)n;
+  double* p = a.w + 3 * (size_t)n;
+  double* s = a.w + 4 * (size_t)n;
+  double* dinv = a.w + 5 * (size_t)n;
+  int phase = 0;
+  double acc[3] = {0.0, 0.0, 0.0};
+  spmv_stream(A, a.x, prod, [&](int row, double ax) {
+    const double di = row_diag_inv(A, row, a.pc);
+    const double ri = a.b[row] - ax, ui = di * ri, bi = di * a.b[row];
+    dinv[row] = di; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
+    acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
+  });
+  grid_sum<3>(grid, acc, a.red, phase, sh);
+  double gamma = acc[0], un = sqrt(acc[1]);
+  const double bn = sqrt(acc[2]);
+  const double tol = fmax(a.rtol * bn, a.atol);
+  if (!(un == un)) { finish(a, 0, -1, un, bn); return; }
+  if (un <= tol) { finish(a, 0, 1, un, bn); return; }
+  double d0[1] = {0.0};
+  spmv_stream(A, u, prod, [&](int row, double au) {
+    w[row] = au;
+    d0[0] += au * u[row];
+  });
+  grid_sum<1>(grid, d0, a.red, phase, sh);
+  if (!(d0[0] > 0.0)) { finish(a, 0, -1, un, bn); return; }
+  double alpha = gamma / d0[0], beta = 0.0;
+  for (int it = 1; it <= a.maxit; ++it) {
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int i = gt; i < n; i += gs) {
+      const double pi = u[i] + beta * p[i];
+      const double si = w[i] + beta * s[i];
+      p[i] = pi; s[i] = si;
+      a.x[i] += alpha * pi;
+      const double ri = r[i] - alpha * si;
+      r[i] = ri;
+      const double ui = dinv[i] * ri;
+      u[i] = ui;
+      d[0] += ri * ui;
+      d[1] += ui * ui;
+    }
+    grid.sync();
+    spmv_stream(A, u, prod, [&](int row, double au) {
+      w[row] = au;
+      d[2] += au * u[row];
+    });
+    grid_sum<3>(grid, d, a.red, phase, sh);
+    un = sqrt(d[1]);
+    if (!(un == un) || un > a.dtol * bn) { finish(a, it, -1, un, bn); return; }
+    if (un <= tol) { finish(a, it, 1, un, bn); return; }
+    beta = d[0] / gamma;
+    const double denom = d[2] - beta * d[0] / alpha;
+    if (!(denom > 0.0)) { finish(a, it, -1, un, bn); return; }  // not SPD / breakdown
+    alpha = d[0] / denom;
+    gamma = d[0];
+  }
+  finish(a, a.maxit, 0, un, bn);
+}
+
+int la_krylov(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
+              double rtol, double atol, int maxit, int ticket, cudaStream_t st) {
+  const DevPattern& p = P->sp[space];
+  if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
+  if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB)
+    return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg available)", method);
+  if (pc != FX_PC_NONE && pc != FX_PC_JACOBI)
+    return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi available)", pc);
+  int rc = ensure_work(P, (size_t)p.n);
+  if (rc) return rc;
+  KArgs ka;
+  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk};
+  ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
+  ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
+  ka.info = P->info + ticket;
+  void* fn = method == FX_KSP_CG ? (void*)k_cg : (void*)k_bicgstab;
+  int per_sm = 0;
+  FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LA_THREADS, 0));
+  if (per_sm < 1) return set_error(FX_ERR_CUDA, "Krylov kernel does not fit on an SM");
+  // one CTA per row block up to the co-resident limit; small systems get a small grid (cheap barriers)
+  int grid = max(1, min(min(per_sm, 8) * P->num_sms, p.nrowblk));
+  grid = min(grid, MAX_GRID);
+  void* args[] = {(void*)&ka};
+  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LA_THREADS), args, 0, st));
+  count_launch(1);
+  return FX_OK;
+}
+
+}  // namespace fx

@@ -31,6 +31,8 @@ struct DevPattern {
   int* col = nullptr;
   uint8_t* pos = nullptr;
   int* dm_t = nullptr;
+  int* rowblk = nullptr;
+  int nrowblk = 0;
 };
 
 constexpr int KRYLOV_NWORK = 8;

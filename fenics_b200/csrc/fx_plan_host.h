@@ -16,7 +16,25 @@ struct HostPattern {
   std::vector<int> rowptr, col;
   std::vector<uint8_t> pos;  // [(a*ld+b)*nc + cell] = offset of column dof(b) within row dof(a)
   std::vector<int> dm_t;     // transposed dofmap [a*nc + cell]
+  std::vector<int> rowblk;   // SpMV row blocks: rows [rowblk[k], rowblk[k+1]) hold <= SPMV_NNZB nnz, <= SPMV_ROWB rows
 };
+
+constexpr int SPMV_NNZB = 2048;  // nonzeros staged in shared memory per row block
+constexpr int SPMV_ROWB = 256;   // rows per row block (one thread each in the reduce phase)
+
+inline void build_rowblocks(HostPattern& P) {
+  P.rowblk.clear();
+  P.rowblk.push_back(0);
+  int start = 0;
+  for (int r = 0; r < P.n; ++r) {
+    const int nnz_if = P.rowptr[r + 1] - P.rowptr[start];
+    if (nnz_if > SPMV_NNZB || r + 1 - start > SPMV_ROWB) {
+      P.rowblk.push_back(r);  // close the block before row r (every row has <= 256 <= NNZB entries)
+      start = r;
+    }
+  }
+  P.rowblk.push_back(P.n);
+}
 
 inline void parallel_for(long n, const std::function<void(long, long)>& fn) {
   unsigned nt = std::thread::hardware_concurrency();
@@ -109,6 +127,7 @@ inline bool build_pattern(const int* cell_dofs, int nc, int ld, bool want_patter
       }
     }
   });
+  build_rowblocks(P);
   return true;
 }
 
