@@ -70,7 +70,7 @@ __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc
 __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[33];
-  __shared__ double prod[SPMV_NNZB];
+  __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
 __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[33];
-  __shared__ double prod[SPMV_NNZB];
+  __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -252,7 +252,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LA_THREADS, 0));
   if (per_sm < 1) return set_error(FX_ERR_CUDA, "Krylov kernel does not fit on an SM");
   // one CTA per row block up to the co-resident limit; small systems get a small grid (cheap barriers)
-  int grid = max(1, min(min(per_sm, 8) * P->num_sms, p.nrowblk));
+  int grid = max(1, min(min(per_sm, 8) * P->num_sms, (p.nrowblk + LA_WARPS - 1) / LA_WARPS));
   grid = min(grid, MAX_GRID);
   void* args[] = {(void*)&ka};
   FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LA_THREADS), args, 0, st));

@@ -8,7 +8,7 @@ namespace fx {
 // ---- SpMV -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LA_THREADS, 4) k_spmv(const __grid_constant__ CsrView A,
                                                         const double* __restrict__ x, double* __restrict__ y) {
-  __shared__ double prod[SPMV_NNZB];
+  __shared__ double prod[SPMV_SMEM_DOUBLES];
   spmv_stream(A, x, prod, [&](int row, double s) { y[row] = s; });
 }
 
@@ -16,7 +16,7 @@ int la_spmv(fx_plan* P, int space, const double* val, const double* x, double* y
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
   CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk};
-  const int nb = max(1, min(p.nrowblk, P->num_sms * 8));
+  const int nb = max(1, min((p.nrowblk + LA_WARPS - 1) / LA_WARPS, P->num_sms * 8));
   k_spmv<<<nb, LA_THREADS, 0, st>>>(A, x, y);
   count_launch(1);
   FX_CUDA(cudaGetLastError());

@@ -7,6 +7,8 @@
 namespace fx {
 
 constexpr int LA_THREADS = 256;
+constexpr int LA_WARPS = LA_THREADS / 32;
+constexpr int SPMV_SMEM_DOUBLES = LA_WARPS * SPMV_NNZB;  // shared staging per CTA (32 KB)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -34,36 +36,64 @@ __device__ __forceinline__ double block_sum_bcast(double v, double* sh) {
   return sh[32];
 }
 
+// streaming (read-once) loads: non-coherent path, do not allocate in L1 so the x-gather lines stay
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 struct CsrView {
   int n;
   const int* rowptr;
   const int* col;
-  const double* val;
+  const double* val;   // must not be written while a kernel using ld_stream on it runs
   const int* rowblk;
   int nrowblk;
 };
 
-// CSR-stream SpMV (rows of 7-57 nonzeros are too short for a warp per row): a CTA takes a block of
-// consecutive rows holding <= SPMV_NNZB nonzeros, streams val[j]*x[col[j]] into shared memory with
-// fully coalesced val/col loads (many independent loads in flight per thread), then one thread per
-// row sums its slice and runs the fused epilogue epi(row, (A x)[row]).
-// `x` may have been written earlier in the same (cooperative) kernel: no __restrict__, no ld.nc.
+// CSR-stream SpMV at warp granularity (rows of 7-57 nonzeros are too short for a warp per row and a
+// thread per row cannot coalesce): a warp takes a block of consecutive rows holding <= SPMV_NNZB
+// nonzeros (<= 32 rows), streams val[j]*x[col[j]] into its private shared-memory slice with fully
+// coalesced val/col loads, 8 independent loads per lane in flight, then one lane per row sums its
+// slice and runs the fused epilogue epi(row, (A x)[row]).  Only __syncwarp() -- warps of a CTA drift
+// apart, so streaming and reducing overlap on the SM.
+// `x` may have been written earlier in the same (cooperative) kernel: plain coherent loads.
 template <class Epi>
-__device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, double* prod, Epi&& epi) {
-  for (int k = blockIdx.x; k < A.nrowblk; k += gridDim.x) {
+__device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, double* smem, Epi&& epi) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* prod = smem + wib * SPMV_NNZB;
+  const int nw = gridDim.x * LA_WARPS;
+  for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
     const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
     const int j0 = A.rowptr[r0], j1 = A.rowptr[r1];
-#pragma unroll 4
-    for (int j = j0 + threadIdx.x; j < j1; j += LA_THREADS) prod[j - j0] = A.val[j] * x[A.col[j]];
-    __syncthreads();
-    if (threadIdx.x < r1 - r0) {
-      const int row = r0 + threadIdx.x;
+    for (int jb = j0; jb < j1; jb += 256) {
+      int c[8];
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u * 32 + lane;
+        c[u] = (j < j1) ? ld_stream(A.col + j) : -1;
+        v[u] = (j < j1) ? ld_stream(A.val + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c[u] >= 0) prod[jb - j0 + u * 32 + lane] = v[u] * x[c[u]];
+    }
+    __syncwarp();
+    if (lane < r1 - r0) {
+      const int row = r0 + lane;
       const int s0 = A.rowptr[row] - j0, s1 = A.rowptr[row + 1] - j0;
       double s = 0.0;
       for (int j = s0; j < s1; ++j) s += prod[j];
       epi(row, s);
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 

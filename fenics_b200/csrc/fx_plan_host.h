@@ -19,8 +19,8 @@ struct HostPattern {
   std::vector<int> rowblk;   // SpMV row blocks: rows [rowblk[k], rowblk[k+1]) hold <= SPMV_NNZB nnz, <= SPMV_ROWB rows
 };
 
-constexpr int SPMV_NNZB = 2048;  // nonzeros staged in shared memory per row block
-constexpr int SPMV_ROWB = 256;   // rows per row block (one thread each in the reduce phase)
+constexpr int SPMV_NNZB = 512;  // nonzeros staged in shared memory per row block (one warp each)
+constexpr int SPMV_ROWB = 32;   // rows per row block (one lane each in the reduce phase)
 
 inline void build_rowblocks(HostPattern& P) {
   P.rowblk.clear();
