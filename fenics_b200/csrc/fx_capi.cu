@@ -121,6 +121,18 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
     }
     maxn = std::max(maxn, (size_t)hp.n);
   }
+  size_t maxnnz = 0, maxblk = 0;
+  for (int s = 0; s < S_N; ++s) {
+    maxnnz = std::max(maxnnz, (size_t)P->sp[s].nnz);
+    maxblk = std::max(maxblk, (size_t)P->sp[s].nrowblk);
+  }
+  if (maxnnz > 0 &&
+      (cudaMalloc((void**)&P->cval, sizeof(double) * maxnnz) != cudaSuccess ||
+       cudaMalloc((void**)&P->ccol, sizeof(int) * maxnnz) != cudaSuccess ||
+       cudaMalloc((void**)&P->crs, sizeof(int) * maxn) != cudaSuccess ||
+       cudaMalloc((void**)&P->cre, sizeof(int) * maxn) != cudaSuccess ||
+       cudaMalloc((void**)&P->cblkend, sizeof(int) * (maxblk + 1)) != cudaSuccess))
+    return fail(set_error(FX_ERR_CUDA, "cudaMalloc compacted-matrix buffers failed"));
   P->part_cap = std::max((nc + 255) / 256, 148 * 8);
   if (cudaMalloc((void**)&P->part, sizeof(double) * P->part_cap) != cudaSuccess ||
       cudaMalloc((void**)&P->scal, sizeof(double) * 64) != cudaSuccess ||
@@ -142,6 +154,7 @@ void fx_plan_destroy(fx_plan* P) {
   for (int s = 0; s < S_N; ++s) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
   }
+  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->crs); cudaFree(P->cre); cudaFree(P->cblkend);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;
 }

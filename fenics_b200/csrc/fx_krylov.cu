@@ -32,18 +32,19 @@ template <int NV>
 __device__ __forceinline__ void grid_sum(cg::grid_group& grid, double (&v)[NV], double* red, int& phase,
                                          double* sh) {
   double* buf = red + (size_t)(phase & 1) * RED_SLOTS * MAX_GRID;
+  block_sum_bcast_n<NV>(v, sh);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const double s = block_sum_bcast(v[i], sh);
-    if (threadIdx.x == 0) buf[i * MAX_GRID + blockIdx.x] = s;
+    for (int i = 0; i < NV; ++i) buf[i * MAX_GRID + blockIdx.x] = v[i];
   }
   grid.sync();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     double s = 0.0;
     for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) s += buf[i * MAX_GRID + j];
-    v[i] = block_sum_bcast(s, sh);
+    v[i] = s;
   }
+  block_sum_bcast_n<NV>(v, sh);
   ++phase;
 }
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc
 // ||r|| <= max(rtol ||M^-1 b||, atol) (PETSc default for left preconditioning).
 __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[33];
+  __shared__ double sh[3 * 33];
   __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
   double* dinv = a.w + 6 * (size_t)n;
   int phase = 0;
 
-  // setup: dinv, r = M^-1 (b - A x), rhat = r, p = v = 0
+  // setup: compacted matrix, dinv, r = M^-1 (b - A x), rhat = r, p = v = 0
+  if (A.rs != nullptr) compact_zeros(A);
   double acc[2] = {0.0, 0.0};
   spmv_stream(A, a.x, prod, [&](int row, double ax) {
     const double di = row_diag_inv(A, row, a.pc);
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
 // Monitored norm ||M^-1 r||_2 (PETSc default for KSPCG).
 __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[33];
+  __shared__ double sh[3 * 33];
   __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
   double* s = a.w + 4 * (size_t)n;
   double* dinv = a.w + 5 * (size_t)n;
   int phase = 0;
+  if (A.rs != nullptr) compact_zeros(A);
   double acc[3] = {0.0, 0.0, 0.0};
   spmv_stream(A, a.x, prod, [&](int row, double ax) {
     const double di = row_diag_inv(A, row, a.pc);
@@ -243,7 +246,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
-  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk};
+  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->crs, P->cre, P->cblkend, P->ccol, P->cval};
   ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_spmv(const __grid_constant__ 
 int la_spmv(fx_plan* P, int space, const double* val, const double* x, double* y, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk};
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr};
   const int nb = max(1, min((p.nrowblk + LA_WARPS - 1) / LA_WARPS, P->num_sms * 8));
   k_spmv<<<nb, LA_THREADS, 0, st>>>(A, x, y);
   count_launch(1);

@@ -35,27 +35,97 @@ __device__ __forceinline__ double block_sum_bcast(double v, double* sh) {
   __syncthreads();
   return sh[32];
 }
+// NV sums at once (same barriers as one): sh must hold NV*33 doubles
+template <int NV>
+__device__ __forceinline__ void block_sum_bcast_n(double (&v)[NV], double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i * 33 + w] = v[i];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = (lane < nw) ? sh[i * 33 + lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) sh[i * 33 + 32] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sh[i * 33 + 32];
+}
 
-// streaming (read-once) loads: non-coherent path, do not allocate in L1 so the x-gather lines stay
+// streaming (read-once) loads: do not allocate in L1 so the x-gather lines stay resident
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 
+// CSR matrix on the plan's pattern, optionally with a zero-compacted copy (see compact_zeros).
 struct CsrView {
   int n;
   const int* rowptr;
   const int* col;
-  const double* val;   // must not be written while a kernel using ld_stream on it runs
+  const double* val;
   const int* rowblk;
   int nrowblk;
+  // compacted copy (structural zeros of the DOLFIN cell-block pattern dropped); null = not compacted
+  int* rs;      // [n] first entry of row
+  int* re;      // [n] one past the last entry of row
+  int* blkend;  // [nrowblk] one past the last entry of the row block
+  int* col2;
+  double* val2;
 };
+
+// Drop exactly-zero entries, row block by row block, into (col2, val2) at the block's original offset.
+// DOLFIN's pattern stores every (test dof, trial dof) pair of every cell whether or not the form
+// couples them: 20-60 % of the stored values of the W and Zc matrices are exact
+// zeros, which a Krylov solve would otherwise stream from HBM twice per iteration.  The warp that
+// compacts a block is the warp that later streams it, so no grid barrier is needed in between.
+__device__ __forceinline__ void compact_zeros(const CsrView& A) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nw = gridDim.x * LA_WARPS;
+  for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
+    const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
+    const int j0 = A.rowptr[r0];
+    const int row = r0 + lane;
+    const bool act = row < r1;
+    int b = 0, e = 0, cnt = 0;
+    if (act) {
+      b = A.rowptr[row]; e = A.rowptr[row + 1];
+      for (int j = b; j < e; ++j) cnt += (A.val[j] != 0.0);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (act) {
+      int dst = j0 + incl - cnt;
+      A.rs[row] = dst;
+      A.re[row] = dst + cnt;
+      for (int j = b; j < e; ++j) {
+        const double v = A.val[j];
+        if (v != 0.0) { A.val2[dst] = v; A.col2[dst] = A.col[j]; ++dst; }
+      }
+    }
+    if (lane == 0) A.blkend[k] = j0 + total;
+    __syncwarp();
+  }
+}
 
 // CSR-stream SpMV at warp granularity (rows of 7-57 nonzeros are too short for a warp per row and a
 // thread per row cannot coalesce): a warp takes a block of consecutive rows holding <= SPMV_NNZB
@@ -69,17 +139,20 @@ __device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, d
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* prod = smem + wib * SPMV_NNZB;
   const int nw = gridDim.x * LA_WARPS;
+  const bool compact = A.rs != nullptr;
+  const int* col = compact ? A.col2 : A.col;
+  const double* val = compact ? A.val2 : A.val;
   for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
     const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
-    const int j0 = A.rowptr[r0], j1 = A.rowptr[r1];
+    const int j0 = A.rowptr[r0], j1 = compact ? A.blkend[k] : A.rowptr[r1];
     for (int jb = j0; jb < j1; jb += 256) {
       int c[8];
       double v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int j = jb + u * 32 + lane;
-        c[u] = (j < j1) ? ld_stream(A.col + j) : -1;
-        v[u] = (j < j1) ? ld_stream(A.val + j) : 0.0;
+        c[u] = (j < j1) ? ld_stream(col + j) : -1;
+        v[u] = (j < j1) ? ld_stream(val + j) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
@@ -88,7 +161,8 @@ __device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, d
     __syncwarp();
     if (lane < r1 - r0) {
       const int row = r0 + lane;
-      const int s0 = A.rowptr[row] - j0, s1 = A.rowptr[row + 1] - j0;
+      const int s0 = (compact ? A.rs[row] : A.rowptr[row]) - j0;
+      const int s1 = (compact ? A.re[row] : A.rowptr[row + 1]) - j0;
       double s = 0.0;
       for (int j = s0; j < s1; ++j) s += prod[j];
       epi(row, s);

@@ -58,6 +58,9 @@ struct fx_plan {
   size_t work_n = 0;
   double* red = nullptr;       // grid-reduction scratch 2 x RED_SLOTS x MAX_GRID
   fx_solve_info* info = nullptr;  // device, FX_NTICKETS result slots
+  // zero-compacted matrix copy used inside the Krylov kernels (sized for the largest pattern)
+  double* cval = nullptr;
+  int *ccol = nullptr, *crs = nullptr, *cre = nullptr, *cblkend = nullptr;
 
   fx::MeshView view() const {
     fx::MeshView m;
