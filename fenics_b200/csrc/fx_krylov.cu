@@ -1,6 +1,7 @@
 // Krylov solvers (K9/K10 of SURVEY.md 2.3) as ONE persistent cooperative kernel per solve.
-//   * k_bicgstab: left-preconditioned BiCGStab, PETSc KSPBCGS semantics
-//   * k_cg:       preconditioned CG in the Chronopoulos-Gear form (one fused reduction per iteration)
+//   * k_bicgstab:  left-preconditioned BiCGStab, PETSc KSPBCGS semantics
+//   * k_cg:        preconditioned CG in the Chronopoulos-Gear form (one fused reduction per iteration)
+//   * k_pcg_res<R>: pipelined CG for small systems, matrix slice resident in shared memory
 // SpMV (CSR-stream through shared memory), fused vector updates, dot products and the convergence test
 // all run on the device, separated by grid.sync(); reductions are deterministic two-stage sums so every
 // CTA takes the same branch.  Preconditioner: Jacobi (M = diag A) or none.
@@ -235,6 +236,213 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
   finish(a, a.maxit, 0, un, bn);
 }
 
+// ---- pipelined CG (Ghysels-Vanroose), matrix resident in shared memory -----------------------------------
+// Small systems (the P1 pressure/density matrices: 37k rows, 3 MB at n=192) need ~10^3 iterations of
+// microseconds each: the cost is latency, not bandwidth.  Two measures:
+//  (1) the pipelined recurrence (u = M^-1 r, w = A u, m = M^-1 w, n = A m; z, q, s, p auxiliary) makes
+//      the SpMV independent of the iteration's dot products, so ONE grid barrier per iteration serves
+//      both the reduction and the SpMV's data dependency, and every vector update lives in the SpMV
+//      epilogue (the lane that sums row i owns entry i of every vector): an iteration is one pass;
+//  (2) each warp keeps its <= R row blocks (zero-compacted values, columns, row offsets) in shared
+//      memory for the whole solve, so an iteration issues only the m-gather and its own-row updates.
+// The recurrences lose a few digits of attainable accuracy: la_krylov selects this kernel only for
+// rtol >= 1e-9 and when the matrix fits (R <= PCG_MAXR row blocks per warp with one CTA per SM).
+constexpr int PCG_MAXR = 3;
+__host__ __device__ constexpr size_t pcg_smem_bytes(int R) {
+  return (size_t)LA_WARPS * ((size_t)R * SPMV_NNZB * (sizeof(double) + sizeof(int)) + SPMV_NNZB * sizeof(double));
+}
+
+template <int R>
+__global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant__ KArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[3 * 33];
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const CsrView& A = a.A;
+  const size_t n = (size_t)A.n;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nw = gridDim.x * LA_WARPS, gw = blockIdx.x * LA_WARPS + wib;
+  // per-warp shared slices
+  double* sval = reinterpret_cast<double*>(dyn) + (size_t)wib * R * SPMV_NNZB;
+  double* prod = reinterpret_cast<double*>(dyn) + (size_t)LA_WARPS * R * SPMV_NNZB + (size_t)wib * SPMV_NNZB;
+  int* scol = reinterpret_cast<int*>(dyn + (size_t)LA_WARPS * (R + 1) * SPMV_NNZB * sizeof(double)) +
+              (size_t)wib * R * SPMV_NNZB;
+  double* r = a.w;
+  double* u = a.w + n;
+  double* w = a.w + 2 * n;
+  double* z = a.w + 3 * n;
+  double* q = a.w + 4 * n;
+  double* s = a.w + 5 * n;
+  double* p = a.w + 6 * n;
+  double* dinv = a.w + 7 * n;
+  double* mbuf[2] = {a.w + 8 * n, a.w + 9 * n};
+  // row-block registers: my row, slice of `prod` holding my row, entries in the block
+  int my_row[R], my_s0[R], my_s1[R], blk_nnz[R];
+  double my_dinv[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int k = gw + rr * nw;
+    my_row[rr] = -1; my_s0[rr] = 0; my_s1[rr] = 0; blk_nnz[rr] = 0; my_dinv[rr] = 1.0;
+    if (k < A.nrowblk) {
+      const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
+      const int row = r0 + lane;
+      const bool act = row < r1;
+      int b = 0, e = 0, cnt = 0;
+      double dg = 0.0;
+      if (act) {
+        b = A.rowptr[row]; e = A.rowptr[row + 1];
+        for (int j = b; j < e; ++j) {
+          const double v = A.val[j];
+          cnt += (v != 0.0);
+          if (A.col[j] == row) dg = v;
+        }
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      blk_nnz[rr] = __shfl_sync(0xffffffffu, incl, 31);
+      if (act) {
+        int dst = incl - cnt;
+        my_row[rr] = row; my_s0[rr] = dst; my_s1[rr] = dst + cnt;
+        my_dinv[rr] = (a.pc == FX_PC_JACOBI && dg != 0.0) ? 1.0 / dg : 1.0;
+        for (int j = b; j < e; ++j) {
+          const double v = A.val[j];
+          if (v != 0.0) { sval[rr * SPMV_NNZB + dst] = v; scol[rr * SPMV_NNZB + dst] = A.col[j]; ++dst; }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // y_row = sum_j val_j x[col_j] for my rows, from the resident slices
+  auto spmv_res = [&](const double* x, double (&y)[R]) {
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int nnz = blk_nnz[rr];
+      const double* sv = sval + rr * SPMV_NNZB;
+      const int* sc = scol + rr * SPMV_NNZB;
+      for (int jb = 0; jb < nnz; jb += 128) {
+        double t[4];
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int j = jb + uu * 32 + lane;
+          t[uu] = (j < nnz) ? x[sc[j]] : 0.0;
+        }
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int j = jb + uu * 32 + lane;
+          if (j < nnz) prod[j] = sv[j] * t[uu];
+        }
+      }
+      __syncwarp();
+      double acc = 0.0;
+      for (int j = my_s0[rr]; j < my_s1[rr]; ++j) acc += prod[j];
+      y[rr] = acc;
+      __syncwarp();
+    }
+  };
+  int phase = 0;
+  double y[R];
+  // r = b - A x, u = M^-1 r
+  double acc1[1] = {0.0};
+  spmv_res(a.x, y);
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = my_row[rr];
+    if (row >= 0) {
+      const double ri = a.b[row] - y[rr], bi = my_dinv[rr] * a.b[row];
+      dinv[row] = my_dinv[rr]; r[row] = ri; u[row] = my_dinv[rr] * ri;
+      z[row] = 0.0; q[row] = 0.0; s[row] = 0.0; p[row] = 0.0;
+      acc1[0] += bi * bi;
+    }
+  }
+  grid_sum<1>(grid, acc1, a.red, phase, sh);
+  const double bn = sqrt(acc1[0]);
+  const double tol = fmax(a.rtol * bn, a.atol);
+  // w = A u, m = M^-1 w
+  double d[3] = {0.0, 0.0, 0.0};  // gamma = (r,u), delta = (w,u), ||u||^2
+  spmv_res(u, y);
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = my_row[rr];
+    if (row >= 0) {
+      const double ui = u[row];
+      w[row] = y[rr];
+      mbuf[0][row] = my_dinv[rr] * y[rr];
+      d[0] += r[row] * ui; d[1] += y[rr] * ui; d[2] += ui * ui;
+    }
+  }
+  grid_sum<3>(grid, d, a.red, phase, sh);
+  double gamma_old = 1.0, alpha = 1.0, un = sqrt(d[2]);
+  for (int it = 0; it <= a.maxit; ++it) {
+    un = sqrt(d[2]);
+    if (!(un == un) || un > a.dtol * bn) { finish(a, it, -1, un, bn); return; }
+    if (un <= tol) { finish(a, it, 1, un, bn); return; }
+    if (it == a.maxit) break;
+    const double gamma = d[0], delta = d[1];
+    double beta = 0.0;
+    if (it > 0) {
+      beta = gamma / gamma_old;
+      const double den = delta - beta * gamma / alpha;
+      if (!(den > 0.0)) { finish(a, it, -1, un, bn); return; }
+      alpha = gamma / den;
+    } else {
+      if (!(delta > 0.0)) { finish(a, it, -1, un, bn); return; }
+      alpha = gamma / delta;
+    }
+    gamma_old = gamma;
+    const double* m = mbuf[it & 1];
+    double* mn = mbuf[(it + 1) & 1];
+    // own-row operands first (independent of the gather): their latency overlaps the SpMV
+    double zo[R], qo[R], so[R], po[R], uo[R], wo[R], ro[R], mo[R], xo[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int row = my_row[rr];
+      if (row >= 0) {
+        zo[rr] = z[row]; qo[rr] = q[row]; so[rr] = s[row]; po[rr] = p[row]; uo[rr] = u[row];
+        wo[rr] = w[row]; ro[rr] = r[row]; mo[rr] = m[row]; xo[rr] = a.x[row];
+      }
+    }
+    spmv_res(m, y);
+    d[0] = d[1] = d[2] = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int row = my_row[rr];
+      if (row >= 0) {
+        const double zi = y[rr] + beta * zo[rr];
+        const double qi = mo[rr] + beta * qo[rr];
+        const double si = wo[rr] + beta * so[rr];
+        const double pi = uo[rr] + beta * po[rr];
+        z[row] = zi; q[row] = qi; s[row] = si; p[row] = pi;
+        a.x[row] = xo[rr] + alpha * pi;
+        const double ri = ro[rr] - alpha * si;
+        const double ui = uo[rr] - alpha * qi;
+        const double wi = wo[rr] - alpha * zi;
+        r[row] = ri; u[row] = ui; w[row] = wi;
+        mn[row] = my_dinv[rr] * wi;
+        d[0] += ri * ui; d[1] += wi * ui; d[2] += ui * ui;
+      }
+    }
+    grid_sum<3>(grid, d, a.red, phase, sh);
+  }
+  finish(a, a.maxit, 0, un, bn);
+}
+
+template <int R>
+static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
+  const size_t smem = pcg_smem_bytes(R);
+  static bool attr_done = false;
+  if (!attr_done) {
+    FX_CUDA(cudaFuncSetAttribute(k_pcg_res<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  void* args[] = {(void*)&ka};
+  FX_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_res<R>, dim3(grid), dim3(LA_THREADS), args, smem, st));
+  count_launch(1);
+  return FX_OK;
+}
+
 int la_krylov(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
@@ -250,11 +458,22 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
+  // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
+  if (method == FX_KSP_CG && rtol >= 1e-9) {
+    const int warps = P->num_sms * LA_WARPS;
+    const int R = (p.nrowblk + warps - 1) / warps;
+    if (R <= PCG_MAXR) {
+      const int grid = min(P->num_sms, (p.nrowblk + LA_WARPS - 1) / LA_WARPS);
+      if (R <= 1) return launch_pcg_res<1>(P, ka, grid, st);
+      if (R == 2) return launch_pcg_res<2>(P, ka, grid, st);
+      return launch_pcg_res<3>(P, ka, grid, st);
+    }
+  }
   void* fn = method == FX_KSP_CG ? (void*)k_cg : (void*)k_bicgstab;
   int per_sm = 0;
   FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LA_THREADS, 0));
   if (per_sm < 1) return set_error(FX_ERR_CUDA, "Krylov kernel does not fit on an SM");
-  // one CTA per row block up to the co-resident limit; small systems get a small grid (cheap barriers)
+  // one CTA per 8 row blocks up to the co-resident limit; small systems get a small grid (cheap barriers)
   int grid = max(1, min(min(per_sm, 8) * P->num_sms, (p.nrowblk + LA_WARPS - 1) / LA_WARPS));
   grid = min(grid, MAX_GRID);
   void* args[] = {(void*)&ka};

@@ -35,7 +35,7 @@ struct DevPattern {
   int nrowblk = 0;
 };
 
-constexpr int KRYLOV_NWORK = 8;
+constexpr int KRYLOV_NWORK = 12;
 constexpr int RED_SLOTS = 4;       // values reduced at once
 constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
 
