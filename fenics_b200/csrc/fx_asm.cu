@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict_
   if (threadIdx.x == 0) out[0] = v;
 }
 
+template <class F>
+__global__ void __launch_bounds__(256) k_facet_scalar(const __grid_constant__ AsmArgs a) {
+  __shared__ double sh[32];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = (f < a.m.nbf) ? facet_functional<F>(a, f) : 0.0;
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = v;
+}
+
 template <class E>
 __global__ void __launch_bounds__(256) k_project_dg0(const __grid_constant__ AsmArgs a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,6 +191,26 @@ static int run_scalar(fx_plan* P, AsmArgs a, double* out_dev, cudaStream_t st) {
   return FX_OK;
 }
 
+template <class F>
+static int run_facet_scalar(fx_plan* P, AsmArgs a, double* out_dev, cudaStream_t st) {
+  const int nb = max(1, (P->nbf + 255) / 256);
+  if (nb > P->part_cap) return set_error(FX_ERR_ARG, "partial buffer too small");
+  a.part = P->part;
+  k_facet_scalar<F><<<nb, 256, 0, st>>>(a);
+  k_sum_partials<<<1, 1024, 0, st>>>(P->part, nb, out_dev);
+  count_launch(2);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+// config 4 functors are written for lambda_D = 0 (phi_def == 1); anything else is rejected loudly
+static int check_form_params(int form, const AsmArgs& a) {
+  if (form >= FX_FORM_C4_A0 && form <= FX_FORM_C4_FORCE_Y && a.p.v[jbp::P_LAMBDA_D] != 0.0)
+    return set_error(FX_ERR_UNSUPPORTED, "config-4 forms are implemented for lambda_D = 0 only (got %g)",
+                     a.p.v[jbp::P_LAMBDA_D]);
+  return FX_OK;
+}
+
 template <class E>
 static int run_dg0(fx_plan* P, AsmArgs a, cudaStream_t st) {
   k_project_dg0<E><<<(P->nc + 255) / 256, 256, 0, st>>>(a);
@@ -191,6 +220,7 @@ static int run_dg0(fx_plan* P, AsmArgs a, cudaStream_t st) {
 }
 
 int launch_matrix(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
+  if (int rc = check_form_params(form, a)) return rc;
   switch (form) {
 #define X(id, F) case id: return run_matrix<F>(P, a, st);
     FX_MATRIX_FORMS(X)
@@ -201,6 +231,7 @@ int launch_matrix(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
 
 int launch_vector(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
   const bool conv0 = a.p.v[ldc::P_CONV] == 0.0;
+  if (int rc = check_form_params(form, a)) return rc;
   switch (form) {
 #define X(id, F) case id: return run_vector<F>(P, a, st);
 #define XC(id, F0, F1) case id: return conv0 ? run_vector<F0>(P, a, st) : run_vector<F1>(P, a, st);
@@ -212,9 +243,13 @@ int launch_vector(fx_plan* P, int form, const AsmArgs& a, cudaStream_t st) {
 }
 
 int launch_scalar(fx_plan* P, int form, const AsmArgs& a, double* out_dev, cudaStream_t st) {
+  if (int rc = check_form_params(form, a)) return rc;
   switch (form) {
 #define X(id, F) case id: return run_scalar<F>(P, a, out_dev, st);
     FX_SCALAR_FORMS(X)
+#undef X
+#define X(id, F) case id: return run_facet_scalar<F>(P, a, out_dev, st);
+    FX_FACET_SCALAR_FORMS(X)
 #undef X
   }
   return set_error(FX_ERR_ARG, "unknown functional id %d", form);
@@ -241,6 +276,9 @@ int form_info(int form, int* rank, int* space, int* qdeg) {
 #undef XC
 #define X(id, F) case id: *rank = 0; *space = -1; qdeg[0] = F::QDEG; qdeg[1] = -1; return FX_OK;
     FX_SCALAR_FORMS(X)
+#undef X
+#define X(id, F) case id: *rank = 0; *space = -1; qdeg[0] = -1; qdeg[1] = F::QDEG; return FX_OK;
+    FX_FACET_SCALAR_FORMS(X)
 #undef X
   }
   return set_error(FX_ERR_ARG, "unknown form id %d", form);

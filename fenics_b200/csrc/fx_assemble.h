@@ -326,7 +326,7 @@ FX_HD void facet_mat_row(const AsmArgs& a, int f, int arow) {
   using FF = typename F::Facet;
   constexpr int NQ = seg_npts(FF::QDEG);
   const int marker = a.m.bf_marker[f];
-  if (a.marker_mask != -1 && !((a.marker_mask >> marker) & 1)) return;
+  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return;  // ds(i) vs ds
   const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
   const Geo g = load_geo(a.m, cell);
   const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
@@ -353,7 +353,7 @@ FX_HD void facet_vec_row(const AsmArgs& a, int f, int arow) {
   using FF = typename F::Facet;
   constexpr int NQ = seg_npts(FF::QDEG);
   const int marker = a.m.bf_marker[f];
-  if (a.marker_mask != -1 && !((a.marker_mask >> marker) & 1)) return;
+  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return;  // ds(i) vs ds
   const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
   const Geo g = load_geo(a.m, cell);
   const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
@@ -386,6 +386,25 @@ FX_HD double cell_functional(const AsmArgs& a, int cell) {
     sum += w * F::integrand(PtArgs{a.m, a.s, a.p, cell, g, xi, et, 0.0, 0.0});
   }
   return sum * g.adet;
+}
+
+// exterior-facet functional (assemble(expr*ds(i))): one thread per boundary facet
+template <class F>
+FX_HD double facet_functional(const AsmArgs& a, int f) {
+  constexpr int NQ = seg_npts(F::QDEG);
+  const int marker = a.m.bf_marker[f];
+  if (F::MARKERS != -1 && !((F::MARKERS >> marker) & 1)) return 0.0;
+  const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
+  const Geo g = load_geo(a.m, cell);
+  const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
+  double sum = 0.0;
+  for (int q = 0; q < NQ; ++q) {
+    double s, w, xi, et;
+    seg_point<F::QDEG>(q, s, w);
+    facet_ref_point(lf, s, xi, et);
+    sum += w * F::integrand(PtArgs{a.m, a.s, a.p, cell, g, xi, et, nx, ny});
+  }
+  return sum * len;
 }
 
 // project(expr, DG0-space): b = sum_q w_q |detJ| f_q, M = |detJ|/2 (1-point rule), x = b / M

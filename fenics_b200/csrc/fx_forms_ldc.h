@@ -444,6 +444,7 @@ struct C2_L0 {
 struct C2_A12_Facet {
   using Space = SpW;
   static constexpr bool present = true;
+  static constexpr int MARKERS = -1;  // un-indexed ds: every exterior facet
   static constexpr int QDEG = 3, NP = 2;
   FX_HD static void point(const PtArgs& x, double* d) { d[0] = x.nx; d[1] = x.ny; }
   template <class A> FX_HDC static void terms(A& a, const double* d, const Par& p) {
@@ -484,6 +485,7 @@ template <bool HALF>
 struct C2_L12_Facet {
   using Space = SpW;
   static constexpr bool present = true;
+  static constexpr int MARKERS = -1;
   static constexpr int QDEG = 4, NP = 2;
   FX_HD static void point(const PtArgs& x, double* d) {
     P2Phys b; P1Phys b1;
@@ -605,6 +607,7 @@ struct C2_A7 {
 struct C2_L7_Facet {
   using Space = SpW;
   static constexpr bool present = true;
+  static constexpr int MARKERS = -1;  // un-indexed ds: every exterior facet
   static constexpr int QDEG = 3, NP = 2;
   FX_HD static void point(const PtArgs& x, double* d) {
     P1Phys b1;

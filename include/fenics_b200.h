@@ -82,7 +82,14 @@ typedef enum {
   FX_FORM_C2_L0 = 220, FX_FORM_C2_L1, FX_FORM_C2_L2, FX_FORM_C2_L5, FX_FORM_C2_L7, FX_FORM_C2_L4,
   FX_FORM_C2_L_RHO1,      /* inner(q, rho0 + Ma^2/Re (p1-p0))*dx (comp_LDC_mesh_convergence.py:501-502) */
   /* cfg2: functionals */
-  FX_FORM_C2_EK = 240, FX_FORM_C2_EE
+  FX_FORM_C2_EK = 240, FX_FORM_C2_EE,
+  /* cfg4 = "flow between eccentrically rotating cylinders"/fenepmp_jbp.py (lambda_D = 0): bilinear */
+  FX_FORM_C4_A0 = 400, FX_FORM_C4_A2, FX_FORM_C4_A5, FX_FORM_C4_A6, FX_FORM_C4_A7, FX_FORM_C4_A4, FX_FORM_C4_A9,
+  /* cfg4: linear */
+  FX_FORM_C4_L0 = 420, FX_FORM_C4_L2, FX_FORM_C4_L5, FX_FORM_C4_L6, FX_FORM_C4_L7, FX_FORM_C4_L4, FX_FORM_C4_L9,
+  FX_FORM_C4_L_RES_ORTH,
+  /* cfg4: functionals; torque / force_x / force_y are exterior-facet integrals over ds(0) (fenepmp_jbp.py:639-649) */
+  FX_FORM_C4_EK = 440, FX_FORM_C4_EE, FX_FORM_C4_TORQUE, FX_FORM_C4_FORCE_X, FX_FORM_C4_FORCE_Y
 } fx_form;
 
 /* DG0 projections (diagonal mass => cell average), dolfin project(expr, Zd|Qt).               */
@@ -90,7 +97,8 @@ typedef enum {
   FX_EXPR_LDC_RESTAU = 1,   /* restau0 -> Zd   (incomp_LDC.py:300-304)                     */
   FX_EXPR_RES_ORTH_SQ,      /* inner(res_orth,res_orth) -> Qt (:306)                       */
   FX_EXPR_SQRT_QT_A,        /* (QT_A)**0.5 -> Qt (:307-308)                                */
-  FX_EXPR_H_KAPP            /* h*kapp -> Qt (:434)                                         */
+  FX_EXPR_H_KAPP,           /* h*kapp -> Qt (:434)                                         */
+  FX_EXPR_C4_RESTAU         /* cfg4 restau0 -> Zd (fenepmp_jbp.py:462-467)                 */
 } fx_expr;
 
 typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;

@@ -662,3 +662,22 @@ def norm(vec, kind="l2"):
     if kind == "linf":
         return float(np.max(np.abs(vec)))
     raise ValueError(kind)
+
+
+def annulus_mesh(n_theta, n_r, x_1=-0.8, y_1=0.0, r_a=1.0, x_2=0.0, y_2=0.0, r_b=2.0):
+    """Structured O-grid stand-in for JBP_mesh (mshr Circle - Circle, fenics_base.py:70-91): journal
+    circle (x_1,y_1,r_a) inside bearing circle (x_2,y_2,r_b), linear blend in the radial direction
+    (synthetic input S2)."""
+    th = 2.0 * np.pi * np.arange(n_theta) / n_theta
+    inner_c = np.stack([x_1 + r_a * np.cos(th), y_1 + r_a * np.sin(th)], 1)
+    outer_c = np.stack([x_2 + r_b * np.cos(th), y_2 + r_b * np.sin(th)], 1)
+    rows = [inner_c + (outer_c - inner_c) * (k / n_r) for k in range(n_r + 1)]
+    coords = np.concatenate(rows, 0)
+    cells = []
+    for k in range(n_r):
+        for i in range(n_theta):
+            a, b = k * n_theta + i, k * n_theta + (i + 1) % n_theta
+            c, d = a + n_theta, b + n_theta
+            cells.append(sorted((a, b, d)))
+            cells.append(sorted((a, c, d)))
+    return Mesh(coords, np.array(cells))

@@ -62,6 +62,9 @@ class Expr:
     def __pos__(self):
         return self
 
+    def __abs__(self):
+        return Math("abs", self)
+
     def __mul__(self, o):
         if isinstance(o, Measure):
             return Form([Integral(self, o.kind, o.subdomain_id)])
@@ -136,6 +139,10 @@ class Expr:
 
 def _is_zero(e):
     return isinstance(e, Zero)
+
+
+def _is_scalar_const(e):
+    return isinstance(e, Const) and e.shape == () and e._deg == 0
 
 
 def _zeros(ctx, shape):
@@ -298,6 +305,8 @@ class Sum(Expr):
             return b
         if _is_zero(b):
             return a
+        if _is_scalar_const(a) and _is_scalar_const(b):  # UFL folds ScalarValue + ScalarValue
+            return as_expr(float(a.value) + float(b.value))
         return Sum(a, b)
 
     def _ev(self, ctx):
@@ -327,6 +336,8 @@ class Neg(Expr):
             return a
         if isinstance(a, Neg):
             return a.a
+        if _is_scalar_const(a):
+            return as_expr(-float(a.value))
         return Neg(a)
 
     def _ev(self, ctx):
@@ -382,6 +393,8 @@ class Product(Expr):
             raise ValueError("Product needs a scalar operand")
         if _is_zero(a) or _is_zero(b):
             return Zero(b.shape)
+        if _is_scalar_const(a) and _is_scalar_const(b):
+            return as_expr(float(a.value) * float(b.value))
         return Product(a, b)
 
     def _ev(self, ctx):
@@ -415,6 +428,8 @@ class Division(Expr):
             raise ValueError("division by non-scalar")
         if _is_zero(a):
             return a
+        if _is_scalar_const(a) and _is_scalar_const(b):
+            return as_expr(float(a.value) / float(b.value))
         return Division(a, b)
 
     def _ev(self, ctx):
@@ -459,6 +474,8 @@ class Power(Expr):
             return a
         if _is_zero(a):
             return a
+        if _is_scalar_const(a):
+            return as_expr(float(a.value) ** p)
         return Power(a, p)
 
     def _ev(self, ctx):

@@ -157,6 +157,9 @@ int emu_assemble_scalar(void* p, int form, const double* const* state, const dou
 #define X(id, F) case id: for (int c = 0; c < P->nc; ++c) sum += cell_functional<F>(a, c); *out = sum; return 0;
     FX_SCALAR_FORMS(X)
 #undef X
+#define X(id, F) case id: for (int f = 0; f < P->nbf; ++f) sum += facet_functional<F>(a, f); *out = sum; return 0;
+    FX_FACET_SCALAR_FORMS(X)
+#undef X
   }
   return FX_ERR_ARG;
 }
@@ -181,6 +184,12 @@ int emu_form_qdeg(int form, int* qdx, int* qds, double conv) {
     FX_VECTOR_FORMS(X, XC)
 #undef X
 #undef XC
+#define X(id, F) case id: *qdx = F::QDEG; *qds = -1; return 0;
+    FX_SCALAR_FORMS(X)
+#undef X
+#define X(id, F) case id: *qdx = -1; *qds = F::QDEG; return 0;
+    FX_FACET_SCALAR_FORMS(X)
+#undef X
   }
   return FX_ERR_ARG;
 }

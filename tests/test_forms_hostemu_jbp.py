@@ -1,0 +1,80 @@
+"""Config 4 ("flow between eccentrically rotating cylinders"/fenepmp_jbp.py) functors, run through the CPU
+emulation of the CUDA element kernels, against the oracle's UFL-semantics evaluation.  1e-12 relative for
+polynomial integrands; the FENE / SU forms are non-polynomial but both sides use the same quadrature
+rule (the UFL-estimated degree, asserted below), so the same tolerance applies."""
+import numpy as np
+import pytest
+
+import fxt_common as lc
+import fxt_jbp as jb
+from fenics_b200 import _abi as abi
+from fxt_emu import EmuPlan
+from oracle import fem
+from oracle.configs_jbp import FenepmpJBP
+from oracle.ufl_lite import dx, inner
+
+TOL = 1e-12
+
+
+def _setup(nt=16, nr=4, shuffle=False, **kw):
+    mesh = fem.annulus_mesh(nt, nr)
+    cfg = FenepmpJBP(mesh, **kw)
+    if shuffle:
+        rng = np.random.default_rng(5)
+        dm = {k: rng.permutation(s.dim)[s.cell_dofs] for k, s in cfg.S.items()}
+        cfg = FenepmpJBP(mesh, dofmaps=dm, **kw)
+    jb.randomize(cfg)
+    plan = EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local,
+                   mesh.bfacet_marker)
+    return mesh, cfg, plan
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_cfg4_forms(shuffle):
+    mesh, cfg, plan = _setup(shuffle=shuffle)
+    assert set(np.unique(mesh.bfacet_marker)) == {0, 1}
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    for name, (fid, space) in jb.C4_FORMS.items():
+        ref = fem.assemble(cfg.forms[name])
+        if name.startswith("a"):
+            err = lc.csr_rel_err(plan.assemble_matrix(fid, space, st, par), ref)
+        else:
+            err = lc.rel_err(plan.assemble_vector(fid, space, st, par), ref)
+        assert err < TOL, (name, err)
+        degs = {k: d for k, _, d in fem.quadrature_degrees(cfg.forms[name], mesh)}
+        q = plan.form_qdeg(fid)
+        assert q[0] == degs["dx"] and q[1] == degs.get("ds", -1), (name, q, degs)
+
+
+def test_cfg4_su_density_matrix_with_flow():
+    """a6's SU term is identically zero in the script (u12 is never solved for); exercise it with u12 != 0."""
+    mesh, cfg, plan = _setup()
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    assert np.abs(cfg.w12.vec).max() > 0.1
+    ref = fem.assemble(cfg.forms["a6"])
+    got = plan.assemble_matrix(abi.FX_FORM_C4_A6, "Q", st, par)
+    assert lc.csr_rel_err(got, ref) < TOL
+    mass = fem.assemble((1.0 / cfg.p["dt"]) * fem.TrialFunction(cfg.S["Q"]) * fem.TestFunction(cfg.S["Q"]) * dx)
+    assert abs(ref - mass).max() > 1e-3 * abs(mass).max()  # the SU part is really there
+
+
+def test_cfg4_lps_and_functionals():
+    mesh, cfg, plan = _setup()
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    cfg.lps_indicator()
+    last = cfg.last
+    res_test = plan.project_dg0(abi.FX_EXPR_C4_RESTAU, "Zd", st, par)
+    assert lc.rel_err(res_test, last["res_test"]) < TOL
+    st[abi.FX_F_RES_TEST] = res_test
+    b = plan.assemble_vector(abi.FX_FORM_C4_L_RES_ORTH, "Zc", st, par)
+    M = plan.assemble_matrix(abi.FX_FORM_MASS_ZC, "Zc", st, par)
+    assert lc.rel_err(fem.solve_lu(M, b), last["res_orth"]) < 1e-10
+    for fid, form in ((abi.FX_FORM_C4_EK, cfg.E_k_form), (abi.FX_FORM_C4_EE, cfg.E_e_form),
+                      (abi.FX_FORM_C4_TORQUE, cfg.torque_form), (abi.FX_FORM_C4_FORCE_X, cfg.force_x_form),
+                      (abi.FX_FORM_C4_FORCE_Y, cfg.force_y_form)):
+        ref = fem.assemble(form)
+        got = plan.assemble_scalar(fid, st, par)
+        assert abs(got - ref) < 1e-11 * max(1.0, abs(ref)), (fid, got, ref)
+        degs = {k: d for k, _, d in fem.quadrature_degrees(form, mesh)}
+        q = plan.form_qdeg(fid)
+        assert (q[0], q[1]) == (degs.get("dx", -1), degs.get("ds", -1)), (fid, q, degs)

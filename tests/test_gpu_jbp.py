@@ -1,0 +1,90 @@
+"""GPU parity tests of config 4 (FENE-P-MP journal bearing) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import fxt_common as lc
+import fxt_jbp as jb
+from fenics_b200 import _abi as abi
+from oracle import fem
+from oracle.configs_jbp import FenepmpJBP as OracleJBP
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from fenics_b200 import dolfin_api as dapi  # noqa: E402
+from fenics_b200 import ensemble, la  # noqa: E402
+from fenics_b200.drivers import jbp  # noqa: E402
+
+TOL = 1e-12
+
+
+def _pair(nt=16, nr=4, **kw):
+    drv = jbp.FenepmpJBP(n_theta=nt, n_r=nr, **kw)
+    m = drv.mesh
+    om = fem.Mesh(m.coordinates(), m.cells())
+    assert np.array_equal(om.bfacet_cell, m.bfacet_cell) and np.array_equal(om.bfacet_local, m.bfacet_local)
+    ocl = OracleJBP(om, dofmaps={k: s.cell_dofs for k, s in drv.S.items()}, **kw)
+    assert np.array_equal(om.bfacet_marker, m.bfacet_marker)
+    return ocl, drv
+
+
+def _push(ocl, drv):
+    for slot, attr in jb.FIELD_ATTR.items():
+        getattr(drv, attr).vector().set_local(getattr(ocl, attr).vec)
+
+
+def test_cfg4_forms_and_functionals_match_oracle():
+    ocl, drv = _pair()
+    jb.randomize(ocl)
+    _push(ocl, drv)
+    for name, (fid, space) in jb.C4_FORMS.items():
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        err = lc.csr_rel_err(got.to_scipy(), ref) if name.startswith("a") else lc.rel_err(got.get_local(), ref)
+        assert err < TOL, (name, err)
+    for fid, form in ((abi.FX_FORM_C4_EK, ocl.E_k_form), (abi.FX_FORM_C4_EE, ocl.E_e_form),
+                      (abi.FX_FORM_C4_TORQUE, ocl.torque_form), (abi.FX_FORM_C4_FORCE_X, ocl.force_x_form),
+                      (abi.FX_FORM_C4_FORCE_Y, ocl.force_y_form)):
+        ref = fem.assemble(form)
+        assert abs(dapi.assemble(drv.pr.form(fid)) - ref) < 1e-11 * max(1.0, abs(ref)), fid
+    ocl.lps_indicator()
+    drv.lps_indicator()
+    assert lc.rel_err(drv.res_test.vector().get_local(), ocl.last["res_test"]) < TOL
+    assert lc.rel_err(drv.kapp.vector().get_local(), ocl.last["kapp"]) < 1e-10
+    for bo, bd in zip(ocl.bcu + ocl.bcT, drv.bcu + drv.bcT):
+        assert np.array_equal(bo.dofs, bd.dofs)
+
+
+def test_cfg4_lambda_d_nonzero_is_rejected_loudly():
+    with pytest.raises(NotImplementedError):
+        jbp.FenepmpJBP(n_theta=8, n_r=2, lambda_d=0.05)
+    _, drv = _pair(nt=8, nr=2)
+    drv.pr.set_param(abi.FX_P_LAMBDA_D, 0.05)
+    with pytest.raises(Exception) as e:
+        dapi.assemble(drv.pr.form(abi.FX_FORM_C4_A4))
+    assert "lambda_D" in str(e.value)
+
+
+def test_cfg4_k_steps_match_oracle():
+    """fields + journal load/torque after K steps within 1e-8 relative (north_star)."""
+    K = 4
+    ocl, drv = _pair(nt=24, nr=6, We=0.5)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    ocl.t = drv.t = 0.45  # spin ramp 0.5(1+tanh(8(t-0.5))) is O(1) here
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        for k in ("E_k", "E_e", "torque", "F_x", "F_y"):
+            assert abs(ro[k] - rd[k]) < 1e-8 * max(abs(ro[k]), 1e-10), (k, ro[k], rd[k])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+    assert all(i.converged == 1 for i in drv.last_info) and len(drv.last_info) == 8
+
+
+def test_cfg4_ensemble_single_rank():
+    res = ensemble.run_fenepmp_sweep(steps=2, n_theta=16, n_r=4)
+    assert len(res) == 12 and [r["We"] for r in res[:4]] == [0.001, 0.1, 0.5, 1.0]
+    assert all(np.isfinite(r["torque"]) and np.isfinite(r["chi"]) for r in res)
