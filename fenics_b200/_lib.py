@@ -51,6 +51,9 @@ def _load():
         "fx_norm": (i, [vp, i, vp, i, dp, vp]),
         "fx_dot_dev": (i, [vp, i, vp, vp, vp, vp]),
         "fx_norm_dev": (i, [vp, i, vp, i, vp, vp]),
+        "fx_lincomb3_dev": (i, [i, vp, vp, vp, vp, vp, vp]),
+        "fx_dotw_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
+        "fx_plan_set_owned_cells": (i, [vp, i]),
         "fx_krylov_solve": (i, [vp, i, vp, vp, vp, i, i, d, d, i, C.POINTER(SolveInfo), vp]),
         "fx_krylov_solve_async": (i, [vp, i, vp, vp, vp, i, i, d, d, i, i, vp]),
         "fx_solve_results": (i, [vp, i, i, C.POINTER(SolveInfo), vp]),

@@ -94,7 +94,7 @@ template <class F>
 __global__ void __launch_bounds__(256) k_cell_scalar(const __grid_constant__ AsmArgs a) {
   __shared__ double sh[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  double v = (c < a.m.nc) ? cell_functional<F>(a, c) : 0.0;
+  double v = (c < a.nc_owned) ? cell_functional<F>(a, c) : 0.0;
   v = block_sum(v, sh);
   if (threadIdx.x == 0) a.part[blockIdx.x] = v;
 }

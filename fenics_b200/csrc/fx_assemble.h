@@ -60,7 +60,8 @@ struct AsmArgs {
   // vector / scalar output
   double* vec;
   double* part;  // per-block partial sums (functionals)
-  int marker_mask;  // facet kernels: bitmask of boundary markers to integrate over (-1 = all)
+  int marker_mask;  // unused (facet functors carry their own MARKERS mask)
+  int nc_owned;     // functionals: integrate over cells [0, nc_owned) only (partitioned mode)
 };
 
 struct PtArgs {
@@ -395,6 +396,7 @@ FX_HD double facet_functional(const AsmArgs& a, int f) {
   const int marker = a.m.bf_marker[f];
   if (F::MARKERS != -1 && !((F::MARKERS >> marker) & 1)) return 0.0;
   const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
+  if (cell >= a.nc_owned) return 0.0;
   const Geo g = load_geo(a.m, cell);
   const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
   double sum = 0.0;

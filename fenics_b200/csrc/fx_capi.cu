@@ -50,6 +50,7 @@ static AsmArgs make_args(const fx_plan* P, const double* const* state, const dou
   for (int i = 0; i < NFIELDS; ++i) a.s.f[i] = state ? state[i] : nullptr;
   for (int i = 0; i < NPARAMS; ++i) a.p.v[i] = params ? params[i] : 0.0;
   a.marker_mask = -1;
+  a.nc_owned = P->nc_owned;
   return a;
 }
 
@@ -87,6 +88,7 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
   fx_plan* P = new fx_plan();
   P->device = device;
   P->nv = nv; P->nc = nc; P->nbf = nbf;
+  P->nc_owned = nc;
   int rc = FX_OK;
   auto fail = [&](int code) { fx_plan_destroy(P); return code; };
   cudaDeviceProp prop;
@@ -277,6 +279,24 @@ int fx_dot_dev(fx_plan* P, int n, const double* x, const double* y, double* out_
 int fx_norm_dev(fx_plan* P, int n, const double* x, int kind, double* out_dev, void* stream) {
   if (!P || n < 0 || !x || !out_dev) return set_error(FX_ERR_ARG, "fx_norm_dev: bad argument");
   return la_norm(P, n, x, kind, out_dev, (cudaStream_t)stream);
+}
+
+int fx_lincomb3_dev(int n, double* out, const double* coef, const double* x, const double* y, const double* z,
+                    void* stream) {
+  if (n < 0 || !out || !coef || !x || !y || !z) return set_error(FX_ERR_ARG, "fx_lincomb3_dev: bad argument");
+  return la_lincomb3(n, out, coef, x, y, z, (cudaStream_t)stream);
+}
+
+int fx_dotw_dev(fx_plan* P, int n, const double* x, const double* y, const double* w, double* out_dev,
+                void* stream) {
+  if (!P || n < 0 || !x || !y || !w || !out_dev) return set_error(FX_ERR_ARG, "fx_dotw_dev: bad argument");
+  return la_dotw(P, n, x, y, w, out_dev, (cudaStream_t)stream);
+}
+
+int fx_plan_set_owned_cells(fx_plan* P, int nc_owned) {
+  if (!P || nc_owned < 0 || nc_owned > P->nc) return set_error(FX_ERR_ARG, "fx_plan_set_owned_cells: bad argument");
+  P->nc_owned = nc_owned;
+  return FX_OK;
 }
 
 int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void* stream) {

@@ -60,6 +60,31 @@ int la_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st) {
   return FX_OK;
 }
 
+// out = c0 x + c1 y + c2 z, coefficients in device memory (partitioned Krylov: no host round trip)
+__global__ void k_lincomb3(int n, double* out, const double* __restrict__ coef, const double* x, const double* y,
+                           const double* z) {
+  const double c0 = coef[0], c1 = coef[1], c2 = coef[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = c0 * x[i] + c1 * y[i] + c2 * z[i];
+}
+int la_lincomb3(int n, double* out, const double* coef, const double* x, const double* y, const double* z,
+                cudaStream_t st) {
+  if (n <= 0) return FX_OK;
+  k_lincomb3<<<min((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, out, coef, x, y, z);
+  count_launch(1);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+__global__ void __launch_bounds__(256) k_dotw_partial(int n, const double* __restrict__ x,
+                                                      const double* __restrict__ y, const double* __restrict__ w,
+                                                      double* __restrict__ part) {
+  __shared__ double sh[33];
+  double v = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += w[i] * x[i] * y[i];
+  v = block_sum_bcast(v, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
 // mode 0: dot(x,y) partials, 1: max|x| partials
 __global__ void __launch_bounds__(256) k_dot_partial(int n, const double* __restrict__ x,
                                                      const double* __restrict__ y, int mode,
@@ -110,6 +135,14 @@ __global__ void __launch_bounds__(256) k_finish(const double* __restrict__ part,
 int la_dot(fx_plan* P, int n, const double* x, const double* y, double* out_dev, cudaStream_t st) {
   const int nb = max(1, min((n + 255) / 256, min(P->part_cap, 148 * 4)));
   k_dot_partial<<<nb, 256, 0, st>>>(n, x, y, 0, P->part);
+  k_finish<<<1, 256, 0, st>>>(P->part, nb, 0, out_dev);
+  count_launch(2);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+int la_dotw(fx_plan* P, int n, const double* x, const double* y, const double* w, double* out_dev, cudaStream_t st) {
+  const int nb = max(1, min((n + 255) / 256, min(P->part_cap, 148 * 4)));
+  k_dotw_partial<<<nb, 256, 0, st>>>(n, x, y, w, P->part);
   k_finish<<<1, 256, 0, st>>>(P->part, nb, 0, out_dev);
   count_launch(2);
   FX_CUDA(cudaGetLastError());

@@ -44,6 +44,7 @@ constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
 struct fx_plan {
   int device = 0, num_sms = 0;
   int nv = 0, nc = 0, nbf = 0;
+  int nc_owned = 0;  // functionals integrate over cells [0, nc_owned) (partitioned mode; default nc)
   double* xy = nullptr;
   int* cells = nullptr;
   double* geom = nullptr;
@@ -87,6 +88,8 @@ int la_apply_bc(fx_plan* plan, int space, double* val, double* b, const int* row
 int la_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st);
 int la_dot(fx_plan* plan, int n, const double* x, const double* y, double* out_dev, cudaStream_t st);
 int la_norm(fx_plan* plan, int n, const double* x, int kind, double* out_dev, cudaStream_t st);
+int la_lincomb3(int n, double* out, const double* coef, const double* x, const double* y, const double* z, cudaStream_t st);
+int la_dotw(fx_plan* plan, int n, const double* x, const double* y, const double* w, double* out_dev, cudaStream_t st);
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
 }  // namespace fx

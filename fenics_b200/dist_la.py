@@ -1,0 +1,181 @@
+"""Distributed (mesh-partitioned) Krylov solvers: SURVEY.md 8e.2.
+
+Per rank: the local matrix (owned rows complete, ghost rows replaced by identity rows), local vectors with
+owned + ghost entries.  One iteration = halo exchange of the SpMV input (all_to_all of packed interface
+values), the rank-local CSR-stream SpMV (`fx_spmv`), owner-masked dot products (`fx_dotw_dev`) all-reduced
+as ONE small tensor per reduction point, and fused vector updates whose scalar coefficients stay in device
+memory (`fx_lincomb3_dev`) -- the host only reads the residual norm once per iteration for the stopping
+test.  Jacobi preconditioning (identical to the serial solver, so iteration counts match the 1-GPU run).
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _abi as abi
+from . import la
+from ._lib import SolveInfo, check, lib
+
+
+class DistContext:
+    """owner masks / halos of one LocalPartition on a device, plus scratch."""
+
+    def __init__(self, plan, lp, group=None):
+        self.plan, self.lp, self.group = plan, lp, group
+        dev = "cuda:%d" % plan.device
+        self.mask = {k: torch.as_tensor(lp.owned[k].astype("float64"), device=dev) for k in lp.owned}
+        self.ghost_rows = {k: torch.as_tensor((~lp.owned[k]).nonzero()[0].astype("int32"), device=dev) for k in lp.owned}
+        self.zeros = {k: torch.zeros(len(self.ghost_rows[k]), dtype=torch.float64, device=dev) for k in lp.owned}
+        self.scal = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.coef = torch.zeros(3, dtype=torch.float64, device=dev)
+        self._work = {}
+
+    def work(self, space, n, count):
+        key = (space, count)
+        if key not in self._work:
+            self._work[key] = [torch.zeros(n, dtype=torch.float64, device=self.scal.device) for _ in range(count)]
+        return self._work[key]
+
+    def halo_update(self, space, vec):
+        self.lp.halo[space].update(vec.t if hasattr(vec, "t") and not torch.is_tensor(vec) else vec, self.group)
+
+    def seal_ghost_rows(self, A, b):
+        """ghost rows -> identity rows, b_ghost = 0 (keeps every iterate finite; dots ignore ghosts)."""
+        rows = self.ghost_rows[A.space]
+        if len(rows):
+            check(lib.fx_apply_bc(self.plan.h, abi.SPACE_ID[A.space], la._ptr(A.val), la._ptr(b.t) if b is not None else None,
+                                  la._ptr(rows), la._ptr(self.zeros[A.space]), len(rows), la._stream()))
+
+    def dots(self, space, pairs):
+        """all-reduced owner-masked dot products of the given (x, y) tensor pairs -> device tensor view."""
+        n = self.mask[space].numel()
+        for i, (x, y) in enumerate(pairs):
+            check(lib.fx_dotw_dev(self.plan.h, n, la._ptr(x), la._ptr(y), la._ptr(self.mask[space]),
+                                  C.c_void_p(self.scal.data_ptr() + 8 * i), la._stream()))
+        out = self.scal[:len(pairs)]
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+
+def _lincomb(n, out, c0, x, c1, y, c2, z, coef):
+    """out = c0 x + c1 y + c2 z with 0-d device tensors (or floats) as coefficients."""
+    coef[0], coef[1], coef[2] = c0, c1, c2
+    check(lib.fx_lincomb3_dev(n, la._ptr(out), la._ptr(coef), la._ptr(x), la._ptr(y), la._ptr(z), la._stream()))
+
+
+def _spmv(ctx, A, x, y):
+    ctx.lp.halo[A.space].update(x, ctx.group)
+    check(lib.fx_spmv(A.plan.h, abi.SPACE_ID[A.space], la._ptr(A.val), la._ptr(x), la._ptr(y), la._stream()))
+
+
+def _diag_inv(ctx, A, pc):
+    """Jacobi: 1/diag(A) by one SpMV-free pass: diag = A * e_i is not available, so read it from CSR."""
+    n = A.n
+    if pc in ("none",):
+        return torch.ones(n, dtype=torch.float64, device=A.val.device)
+    key = ("diagpos", A.space)
+    if key not in ctx._work:
+        rp, col = A.plan.pattern_host(A.space)
+        import numpy as np
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        pos = np.flatnonzero(col == rows)
+        assert len(pos) == n, "pattern lacks a diagonal entry"
+        ctx._work[key] = torch.as_tensor(pos, dtype=torch.int64, device=A.val.device)
+    d = A.val.index_select(0, ctx._work[key])
+    return torch.where(d != 0, 1.0 / d, torch.ones_like(d))
+
+
+def krylov_solve(ctx, A, x, b, method="bicgstab", pc="default", rtol=1e-5, atol=1e-50, maxit=10000):
+    """Distributed solve(A, x, b, method, pc); x, b are la.Vector on the local (owned+ghost) dofs.
+    Same stopping rule as the 1-GPU kernels: ||M^-1 r|| <= max(rtol ||M^-1 b||, atol).  Returns SolveInfo;
+    raises RuntimeError like dolfin when not converged."""
+    if pc == "default":
+        pc = "jacobi"
+    if method not in ("bicgstab", "cg") or pc not in ("jacobi", "none"):
+        raise ValueError("distributed solver supports bicgstab/cg with jacobi/none")
+    sp, n = A.space, A.n
+    ctx.seal_ghost_rows(A, b)
+    dinv = _diag_inv(ctx, A, pc)
+    xt, bt, coef = x.t, b.t, ctx.coef
+    info = SolveInfo()
+    if method == "cg":
+        r, u, p, q = ctx.work(sp, n, 4)
+        _spmv(ctx, A, xt, q)
+        torch.sub(bt, q, out=r)
+        torch.mul(dinv, r, out=u)
+        p.copy_(u)
+        bu = dinv * bt
+        d = ctx.dots(sp, [(r, u), (u, u), (bu, bu)]).clone()
+        gamma, un, bn = d[0].clone(), float(d[1].sqrt()), float(d[2].sqrt())
+        tol = max(rtol * bn, atol)
+        it = 0
+        while un > tol and it < maxit:
+            it += 1
+            _spmv(ctx, A, p, q)
+            pq = ctx.dots(sp, [(p, q)])[0].clone()
+            alpha = gamma / pq
+            _lincomb(n, xt, 1.0, xt, alpha, p, 0.0, p, coef)
+            _lincomb(n, r, 1.0, r, -alpha, q, 0.0, q, coef)
+            torch.mul(dinv, r, out=u)
+            d = ctx.dots(sp, [(r, u), (u, u)]).clone()
+            beta = d[0] / gamma
+            gamma = d[0].clone()
+            _lincomb(n, p, 1.0, u, beta, p, 0.0, p, coef)
+            un = float(d[1].sqrt())  # the one host read per iteration
+            if not (un == un):
+                break
+        info.iterations, info.residual, info.residual0 = it, un, bn
+        info.converged = 1 if un <= tol else (0 if it >= maxit else -1)
+    else:
+        r, rh, p, v, s, t = ctx.work(sp, n, 6)
+        _spmv(ctx, A, xt, v)
+        torch.sub(bt, v, out=r)
+        r.mul_(dinv)
+        rh.copy_(r)
+        p.zero_()
+        v.zero_()
+        bu = dinv * bt
+        d = ctx.dots(sp, [(r, r), (bu, bu)]).clone()
+        rho, rn, bn = d[0].clone(), float(d[0].sqrt()), float(d[1].sqrt())
+        tol = max(rtol * bn, atol)
+        one = torch.ones((), dtype=torch.float64, device=xt.device)
+        rho_old, alpha, omega = one.clone(), one.clone(), one.clone()
+        rhn, it, restarts = rn, 0, 0
+        while rn > tol and it < maxit:
+            it += 1
+            if abs(float(rho)) <= 1e-14 * rhn * rn or float(omega) == 0.0:  # breakdown -> restart with rhat = r
+                restarts += 1
+                if restarts > 50:
+                    break
+                rh.copy_(r)
+                p.zero_()
+                v.zero_()
+                rho = torch.as_tensor(rn * rn, dtype=torch.float64, device=xt.device)
+                rhn = rn
+                rho_old, alpha, omega = one.clone(), one.clone(), one.clone()
+            beta = (rho / rho_old) * (alpha / omega)
+            _lincomb(n, p, 1.0, r, beta, p, -beta * omega, v, coef)
+            _spmv(ctx, A, p, v)
+            v.mul_(dinv)
+            rv = ctx.dots(sp, [(rh, v)])[0].clone()
+            alpha = rho / rv
+            _lincomb(n, s, 1.0, r, -alpha, v, 0.0, v, coef)
+            _spmv(ctx, A, s, t)
+            t.mul_(dinv)
+            d = ctx.dots(sp, [(t, s), (t, t)]).clone()
+            omega = d[0] / d[1]
+            _lincomb(n, xt, 1.0, xt, alpha, p, omega, s, coef)
+            _lincomb(n, r, 1.0, s, -omega, t, 0.0, t, coef)
+            d = ctx.dots(sp, [(rh, r), (r, r)]).clone()
+            rho_old, rho = rho, d[0].clone()
+            rn = float(d[1].sqrt())  # the one host read per iteration
+            if not (rn == rn):
+                break
+        info.iterations, info.residual, info.residual0 = it, rn, bn
+        info.converged = 1 if rn <= tol else (0 if it >= maxit else -1)
+    ctx.lp.halo[sp].update(xt, ctx.group)  # the solution's ghost entries are coefficients of the next forms
+    if info.converged != 1 and la.parameters["krylov_solver"]["error_on_nonconvergence"]:
+        raise RuntimeError("*** Error: Unable to solve linear system (distributed %s): %d iterations, residual %.3e"
+                           % (method, info.iterations, info.residual))
+    return info

@@ -16,12 +16,23 @@ _FACET_VERTS = np.array([[1, 2], [0, 2], [0, 1]])  # local facet i is opposite l
 
 
 class Mesh:
-    def __init__(self, coordinates, cells):
+    def __init__(self, coordinates, cells, boundary_facets=None):
+        """boundary_facets = (cell, local facet, marker) arrays overrides the exterior-facet search: a
+        partition's sub-mesh has artificial exterior facets along the cut that are NOT domain boundary."""
         self._x = np.ascontiguousarray(coordinates, dtype=np.float64)
         c = np.sort(np.asarray(cells, dtype=np.int64), axis=1)  # UFC: ascending vertex ids
         self._cells = np.ascontiguousarray(c.astype(np.int32))
-        self._find_exterior_facets()
-        self.bfacet_marker = np.zeros(len(self.bfacet_cell), dtype=np.int32)
+        if boundary_facets is None:
+            self._find_exterior_facets()
+            self.bfacet_marker = np.zeros(len(self.bfacet_cell), dtype=np.int32)
+        else:
+            bc, bl, bm = boundary_facets
+            self.bfacet_cell = np.ascontiguousarray(bc, dtype=np.int32)
+            self.bfacet_local = np.ascontiguousarray(bl, dtype=np.int32)
+            self.bfacet_marker = np.ascontiguousarray(bm, dtype=np.int32)
+            fv = _FACET_VERTS[self.bfacet_local]
+            self.bfacet_verts = np.take_along_axis(c[self.bfacet_cell], fv, axis=1)
+            self.bfacet_mid = self._x[self.bfacet_verts].mean(axis=1) if len(bc) else np.zeros((0, 2))
 
     # -- dolfin-like accessors ------------------------------------------------------------------
     def coordinates(self):

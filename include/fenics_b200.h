@@ -172,6 +172,19 @@ int fx_dot_dev(fx_plan* plan, int n, const double* x_dev, const double* y_dev, d
                void* stream);
 int fx_norm_dev(fx_plan* plan, int n, const double* x_dev, int kind, double* out_dev, void* stream);
 
+/* ---- building blocks of the mesh-partitioned (multi-GPU) mode: SURVEY.md 8e.2 ----------------
+ * Each rank owns a plan on its sub-mesh (owned cells + the ghost cells touching an owned dof).
+ * out = c[0] x + c[1] y + c[2] z with the three coefficients read from DEVICE memory (so a Krylov
+ * iteration needs no host round trip for its scalars); out may alias x, y or z.                */
+int fx_lincomb3_dev(int n, double* out_dev, const double* coef_dev, const double* x_dev,
+                    const double* y_dev, const double* z_dev, void* stream);
+/* out_dev[0] = sum_i w_i x_i y_i  (w = 1 on owned dofs, 0 on ghosts: rank-local part of a dot)   */
+int fx_dotw_dev(fx_plan* plan, int n, const double* x_dev, const double* y_dev, const double* w_dev,
+                double* out_dev, void* stream);
+/* functionals integrate over cells [0, nc_owned) only (owned cells are numbered first) and over
+ * the boundary facets of those cells; pass nc (the default) to integrate over every local cell. */
+int fx_plan_set_owned_cells(fx_plan* plan, int nc_owned);
+
 /* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default

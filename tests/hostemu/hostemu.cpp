@@ -36,6 +36,7 @@ static AsmArgs make_args(const EmuPlan* P, const double* const* state, const dou
   for (int i = 0; i < NFIELDS; ++i) a.s.f[i] = state ? state[i] : nullptr;
   for (int i = 0; i < NPARAMS; ++i) a.p.v[i] = params ? params[i] : 0.0;
   a.marker_mask = -1;
+  a.nc_owned = P->nc;
   return a;
 }
 

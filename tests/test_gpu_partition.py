@@ -1,0 +1,27 @@
+"""GPU: the mesh-partitioned driver through torchrun.  On a 1-GPU box this runs world_size 1 (the
+partition machinery with a single part: sealed ghost rows, owner-masked dots, device-resident scalars);
+with >= 2 visible GPUs it runs world_size 2 over NCCL."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partitioned_cfg2_matches_single_gpu():
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dist_check.py"),
+           "12", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"] and out["world"] == world and out["max_rel_err"] < 1e-8

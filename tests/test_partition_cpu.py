@@ -1,0 +1,100 @@
+"""CPU tests of the mesh-partition host logic: ownership, sub-mesh completeness
+(assembling on a rank's sub-mesh reproduces its owned rows of the global matrix with no communication),
+and the halo exchange under gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fenics_b200 import mesh as pmesh
+from fenics_b200.partition import LocalPartition, rcb_partition
+from fenics_b200.spaces import function_spaces
+from oracle import fem
+from oracle.ufl_lite import dx, grad, inner
+
+
+def _global(n=8):
+    m = pmesh.Skew_Mesh(n, 1, 1)
+    W, V, _, _, Zd, Zc, Q, Qt, _ = function_spaces(m)
+    return m, dict(W=W, V=V, Zd=Zd, Zc=Zc, Q=Q, Qt=Qt)
+
+
+def test_rcb_balanced():
+    pts = np.random.default_rng(0).random((1000, 2))
+    for P in (2, 3, 4, 8):
+        part = rcb_partition(pts, P)
+        cnt = np.bincount(part, minlength=P)
+        assert cnt.sum() == 1000 and cnt.max() - cnt.min() <= P
+
+
+@pytest.mark.parametrize("nparts", [2, 4])
+def test_every_dof_owned_once_and_submesh_rows_complete(nparts):
+    m, S = _global(8)
+    parts = [LocalPartition(m, S, nparts, r) for r in range(nparts)]
+    for k in S:
+        owned_global = np.concatenate([lp.l2g[k][lp.owned[k]] for lp in parts])
+        assert np.array_equal(np.sort(owned_global), np.arange(S[k].dim()))  # partition of the dofs
+    # global Q stiffness+mass and Zc mass with the oracle; local assembly on each sub-mesh must
+    # reproduce the owned rows exactly up to summation order
+    om = fem.Mesh(m.coordinates(), m.cells())
+    for k, comps in (("Q", ["P1"]), ("Zc", ["P2"] * 3)):
+        Vg = fem.FunctionSpace(om, comps, S[k].cell_dofs)
+        u, v = fem.TrialFunction(Vg), fem.TestFunction(Vg)
+        Ag = fem.assemble(inner(u, v) * dx + (inner(grad(u), grad(v)) * dx if k == "Q" else 0)).tocsr()
+        for lp in parts:
+            lm = fem.Mesh(lp.mesh.coordinates(), lp.mesh.cells())
+            Vl = fem.FunctionSpace(lm, comps, lp.spaces[k].cell_dofs)
+            ul, vl = fem.TrialFunction(Vl), fem.TestFunction(Vl)
+            Al = fem.assemble(inner(ul, vl) * dx + (inner(grad(ul), grad(vl)) * dx if k == "Q" else 0)).tocsr()
+            rows = np.flatnonzero(lp.owned[k])
+            g = lp.l2g[k]
+            sub = Ag[g[rows]][:, g].toarray()  # owned global rows restricted to the local columns
+            assert np.abs(Al[rows].toarray() - sub).max() < 1e-13 * abs(Ag).max()
+            # and those rows have no column outside the sub-mesh
+            assert abs(abs(Ag[g[rows]]).sum() - abs(sub).sum()) < 1e-12 * abs(Ag).sum()
+    # boundary facets of the sub-mesh are true domain-boundary facets only
+    for lp in parts:
+        mid = lp.mesh.bfacet_mid
+        on_bnd = (np.abs(mid[:, 0]) < 1e-12) | (np.abs(mid[:, 0] - 1) < 1e-12) | (mid[:, 1] < 1e-9) | (mid[:, 1] > 1 - 1e-12)
+        assert on_bnd.all()
+        assert lp.nc_owned == (lp.part == lp.rank).sum()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _halo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, S = _global(6)
+    lp = LocalPartition(m, S, world, rank)
+    ok = True
+    for k in ("W", "Zc", "Q"):
+        v = torch.full((len(lp.l2g[k]),), -1.0, dtype=torch.float64)
+        owned = torch.as_tensor(lp.owned[k])
+        v[owned] = torch.as_tensor(lp.l2g[k][lp.owned[k]], dtype=torch.float64)
+        lp.halo[k].update(v)
+        ok = ok and bool(torch.equal(v, torch.as_tensor(lp.l2g[k], dtype=torch.float64)))
+        ok = ok and (~lp.owned[k]).sum() == sum(lp.halo[k].recv_counts)
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=180) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert res == {0: True, 1: True}
