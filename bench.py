@@ -251,8 +251,15 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     top = max((r_ for r_ in rows if "gbs" in r_), key=lambda r_: r_["ms"])
+    traffic = None
+    try:  # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled to this launch
+        tk = json.load(open(os.path.join(ROOT, "profiles", "r01_top_kernel_traffic.json")))
+        if top["phase"].startswith("solve:") and ":W:bicgstab" in top["phase"] and args.n == 192:
+            traffic = tk["dram_bytes_per_iteration"] * top["iterations"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": top["phase"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": top["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": top["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "launch_ms": top["ms"], "alg_bytes_per_launch": top["alg_bytes"], "iterations": top.get("iterations")}
     total_ms = sum(r_["ms"] for r_ in rows)
     share = {}
