@@ -46,6 +46,7 @@ def _load():
         "fx_form_info": (i, [i, ip, ip, ip]),
         "fx_apply_bc": (i, [vp, i, vp, vp, vp, vp, i, vp]),
         "fx_spmv": (i, [vp, i, vp, vp, vp, vp]),
+        "fx_spmv_variant": (i, [vp, i, vp, vp, vp, i, vp]),
         "fx_axpy": (i, [i, d, vp, vp, vp]),
         "fx_dot": (i, [vp, i, vp, vp, dp, vp]),
         "fx_norm": (i, [vp, i, vp, i, dp, vp]),

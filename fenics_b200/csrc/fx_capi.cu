@@ -248,6 +248,11 @@ int fx_spmv(fx_plan* P, int space, const double* val, const double* x, double* y
   return la_spmv(P, space, val, x, y, (cudaStream_t)stream);
 }
 
+int fx_spmv_variant(fx_plan* P, int space, const double* val, const double* x, double* y, int variant, void* stream) {
+  if (!P || space < 0 || space >= S_N || !val || !x || !y) return set_error(FX_ERR_ARG, "fx_spmv_variant: bad argument");
+  return la_spmv_variant(P, space, val, x, y, variant, (cudaStream_t)stream);
+}
+
 int fx_axpy(int n, double alpha, const double* x, double* y, void* stream) {
   if (n < 0 || !x || !y) return set_error(FX_ERR_ARG, "fx_axpy: bad argument");
   return la_axpy(n, alpha, x, y, (cudaStream_t)stream);

@@ -12,6 +12,72 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_spmv(const __grid_constant__ 
   spmv_stream(A, x, prod, [&](int row, double s) { y[row] = s; });
 }
 
+// CSR-vector variant kept for A/B measurements (tools/spmv_bench.py): TPR lanes per row, RU rows in
+// flight per sub-warp, no shared memory.
+template <int TPR, int RU>
+__global__ void __launch_bounds__(LA_THREADS, 4) k_spmv_vec(const __grid_constant__ CsrView A,
+                                                            const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int SPW = 32 / TPR;  // sub-warps per warp
+  const int lane = threadIdx.x % TPR, subw = (threadIdx.x & 31) / TPR;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int base = warp * SPW * RU; base < A.n; base += nwarp * SPW * RU) {  // warp-uniform trip count
+    const int r0 = base + subw * RU;
+    int b[RU], e[RU];
+    double acc[RU];
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+      const int row = r0 + i;
+      b[i] = row < A.n ? A.rowptr[row] + lane : 0;
+      e[i] = row < A.n ? A.rowptr[row + 1] : 0;
+      acc[i] = 0.0;
+    }
+    bool any = true;
+    while (any) {
+      any = false;
+      int c[RU];
+      double v[RU];
+#pragma unroll
+      for (int i = 0; i < RU; ++i) {
+        c[i] = -1;
+        if (b[i] < e[i]) { c[i] = ld_stream(A.col + b[i]); v[i] = ld_stream(A.val + b[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < RU; ++i)
+        if (c[i] >= 0) {
+          acc[i] += v[i] * x[c[i]];
+          b[i] += TPR;
+          any = any || (b[i] < e[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o, TPR);
+      if (lane == 0 && r0 + i < A.n) y[r0 + i] = acc[i];
+    }
+  }
+}
+
+int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, double* y, int variant,
+                    cudaStream_t st) {
+  const DevPattern& p = P->sp[space];
+  if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int nb = P->num_sms * 8;
+  switch (variant) {
+    case 0: return la_spmv(P, space, val, x, y, st);
+    case 1: k_spmv_vec<4, 4><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    case 2: k_spmv_vec<8, 4><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    case 3: k_spmv_vec<8, 2><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    case 4: k_spmv_vec<16, 2><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    case 5: k_spmv_vec<4, 8><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    default: return set_error(FX_ERR_ARG, "unknown SpMV variant %d", variant);
+  }
+  count_launch(1);
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
 int la_spmv(fx_plan* P, int space, const double* val, const double* x, double* y, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);

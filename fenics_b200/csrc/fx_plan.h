@@ -83,6 +83,8 @@ int launch_dg0(fx_plan* plan, int expr, const AsmArgs& base, cudaStream_t st);
 int form_info(int form, int* rank, int* space, int* qdeg);
 // fx_la.cu
 int la_spmv(fx_plan* plan, int space, const double* val, const double* x, double* y, cudaStream_t st);
+int la_spmv_variant(fx_plan* plan, int space, const double* val, const double* x, double* y, int variant,
+                    cudaStream_t st);
 int la_apply_bc(fx_plan* plan, int space, double* val, double* b, const int* rows, const double* g, int n,
                 cudaStream_t st);
 int la_axpy(int n, double alpha, const double* x, double* y, cudaStream_t st);

@@ -162,6 +162,9 @@ int fx_apply_bc(fx_plan* plan, int space, double* val_dev, double* b_dev, const 
 /* ---- linear algebra ------------------------------------------------------------------------ */
 int fx_spmv(fx_plan* plan, int space, const double* val_dev, const double* x_dev, double* y_dev,
             void* stream);
+/* tuning aid (tools/spmv_bench.py): 0 = the production CSR-stream kernel, 1.. = CSR-vector variants */
+int fx_spmv_variant(fx_plan* plan, int space, const double* val_dev, const double* x_dev, double* y_dev,
+                    int variant, void* stream);
 int fx_axpy(int n, double alpha, const double* x_dev, double* y_dev, void* stream);
 int fx_dot(fx_plan* plan, int n, const double* x_dev, const double* y_dev, double* out_host,
            void* stream);                      /* synchronous */
