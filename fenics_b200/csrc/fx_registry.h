@@ -1,6 +1,7 @@
 // Form registry: maps the public form ids (include/fenics_b200.h) to the hand-written functors.
-// X(id, Functor).  Used by fx_kernels.cu (CUDA launchers) and tests/hostemu (CPU emulation).
+// X(id, Functor).  Used by fx_asm.cu (CUDA launchers) and tests/hostemu (CPU emulation).
 #pragma once
+#include "fx_forms_dgp.h"
 #include "fx_forms_jbp.h"
 #include "fx_forms_ldc.h"
 
@@ -26,7 +27,15 @@
   X(FX_FORM_C4_A6, fx::jbp::SU_RHO_A6)      \
   X(FX_FORM_C4_A7, fx::jbp::C4_A7)          \
   X(FX_FORM_C4_A4, fx::jbp::C4_A4)          \
-  X(FX_FORM_C4_A9, fx::jbp::C4_A9)
+  X(FX_FORM_C4_A9, fx::jbp::C4_A9)          \
+  X(FX_FORM_C5_A0, fx::ldc::C2_A0)          \
+  X(FX_FORM_C5_A1, fx::dgp::C5_A12<true>)   \
+  X(FX_FORM_C5_A2, fx::dgp::C5_A12<false>)  \
+  X(FX_FORM_C5_A5, fx::dgp::C5_A5)          \
+  X(FX_FORM_C5_A6, fx::jbp::SU_RHO_A6)      \
+  X(FX_FORM_C5_A7, fx::dgp::C5_A7)          \
+  X(FX_FORM_C5_A4, fx::dgp::C5_A4)          \
+  X(FX_FORM_C5_A8, fx::dgp::C5_A8)
 
 #define FX_VECTOR_FORMS(X, XC)                              \
   XC(FX_FORM_C1_L1, fx::ldc::C1_L1<4>, fx::ldc::C1_L1<5>)   \
@@ -49,7 +58,20 @@
   X(FX_FORM_C4_L7, fx::jbp::C4_L7)                          \
   X(FX_FORM_C4_L4, fx::jbp::C4_L4)                          \
   X(FX_FORM_C4_L9, fx::jbp::C4_L9)                          \
-  X(FX_FORM_C4_L_RES_ORTH, fx::jbp::C4_L_RES_ORTH)
+  X(FX_FORM_C4_L_RES_ORTH, fx::jbp::C4_L_RES_ORTH)          \
+  X(FX_FORM_C5_L0, fx::ldc::C2_L0)                          \
+  X(FX_FORM_C5_L1, fx::dgp::C5_L12<true>)                   \
+  X(FX_FORM_C5_L2, fx::dgp::C5_L12<false>)                  \
+  X(FX_FORM_C5_L5, fx::dgp::C5_L5)                          \
+  X(FX_FORM_C5_L6, fx::jbp::SU_RHO_L6)                      \
+  X(FX_FORM_C5_L7, fx::dgp::C5_L7)                          \
+  X(FX_FORM_C5_L4, fx::jbp::C4_L4)                          \
+  X(FX_FORM_C5_L8, fx::dgp::C5_L8)                          \
+  X(FX_FORM_C5_L_RES_ORTH, fx::dgp::C5_L_RES_ORTH)          \
+  X(FX_FORM_C5_L_THETA0, fx::dgp::C5_L_THETA<fx::ldc::F_T0>) \
+  X(FX_FORM_C5_L_THETA1, fx::dgp::C5_L_THETA<fx::ldc::F_T1>) \
+  X(FX_FORM_C5_L_THERM_INV, fx::dgp::C5_L_THERM_INV)        \
+  X(FX_FORM_C5_L_RHO1, fx::dgp::C5_L_RHO1)
 
 #define FX_SCALAR_FORMS(X)              \
   X(FX_FORM_C1_EK, fx::ldc::C1_EK)      \
@@ -57,19 +79,23 @@
   X(FX_FORM_C2_EK, fx::ldc::C2_EK)      \
   X(FX_FORM_C2_EE, fx::ldc::LDC_EE)     \
   X(FX_FORM_C4_EK, fx::ldc::C2_EK)      \
-  X(FX_FORM_C4_EE, fx::jbp::C4_EE)
+  X(FX_FORM_C4_EE, fx::jbp::C4_EE)      \
+  X(FX_FORM_C5_EK, fx::ldc::C2_EK)      \
+  X(FX_FORM_C5_EE, fx::dgp::C5_EE)
 
 #define FX_FACET_SCALAR_FORMS(X)                    \
   X(FX_FORM_C4_TORQUE, fx::jbp::C4_JOURNAL<0>)      \
   X(FX_FORM_C4_FORCE_X, fx::jbp::C4_JOURNAL<1>)     \
-  X(FX_FORM_C4_FORCE_Y, fx::jbp::C4_JOURNAL<2>)
+  X(FX_FORM_C4_FORCE_Y, fx::jbp::C4_JOURNAL<2>)     \
+  X(FX_FORM_C5_NUS, fx::dgp::C5_NUS)
 
 #define FX_DG0_EXPRS(X)                           \
   X(FX_EXPR_LDC_RESTAU, fx::ldc::E_LDC_RESTAU)    \
   X(FX_EXPR_RES_ORTH_SQ, fx::ldc::E_RES_ORTH_SQ)  \
   X(FX_EXPR_SQRT_QT_A, fx::ldc::E_SQRT_QT_A)      \
   X(FX_EXPR_H_KAPP, fx::ldc::E_H_KAPP)            \
-  X(FX_EXPR_C4_RESTAU, fx::jbp::E_C4_RESTAU)
+  X(FX_EXPR_C4_RESTAU, fx::jbp::E_C4_RESTAU)      \
+  X(FX_EXPR_C5_RESTAU, fx::dgp::E_C5_RESTAU)
 
 namespace fx {
 template <class F> constexpr bool has_facet() { return F::Facet::present; }

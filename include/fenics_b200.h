@@ -89,7 +89,16 @@ typedef enum {
   FX_FORM_C4_L0 = 420, FX_FORM_C4_L2, FX_FORM_C4_L5, FX_FORM_C4_L6, FX_FORM_C4_L7, FX_FORM_C4_L4, FX_FORM_C4_L9,
   FX_FORM_C4_L_RES_ORTH,
   /* cfg4: functionals; torque / force_x / force_y are exterior-facet integrals over ds(0) (fenepmp_jbp.py:639-649) */
-  FX_FORM_C4_EK = 440, FX_FORM_C4_EE, FX_FORM_C4_TORQUE, FX_FORM_C4_FORCE_X, FX_FORM_C4_FORCE_Y
+  FX_FORM_C4_EK = 440, FX_FORM_C4_EE, FX_FORM_C4_TORQUE, FX_FORM_C4_FORCE_X, FX_FORM_C4_FORCE_Y,
+  /* cfg5 = buoyancy-driven-flow/compressible_dgp.py: bilinear */
+  FX_FORM_C5_A0 = 500, FX_FORM_C5_A1, FX_FORM_C5_A2, FX_FORM_C5_A5, FX_FORM_C5_A6, FX_FORM_C5_A7, FX_FORM_C5_A4,
+  FX_FORM_C5_A8,
+  /* cfg5: linear (incl. the right-hand sides of the in-loop project(.., Q) calls :405,:408,:530,:581) */
+  FX_FORM_C5_L0 = 520, FX_FORM_C5_L1, FX_FORM_C5_L2, FX_FORM_C5_L5, FX_FORM_C5_L6, FX_FORM_C5_L7, FX_FORM_C5_L4,
+  FX_FORM_C5_L8, FX_FORM_C5_L_RES_ORTH, FX_FORM_C5_L_THETA0, FX_FORM_C5_L_THETA1, FX_FORM_C5_L_THERM_INV,
+  FX_FORM_C5_L_RHO1,
+  /* cfg5: functionals; NUS = assemble(-inner(grad(theta1), n)*ds(2)) with theta1 in field FX_F_Q_A (:581-583) */
+  FX_FORM_C5_EK = 540, FX_FORM_C5_EE, FX_FORM_C5_NUS
 } fx_form;
 
 /* DG0 projections (diagonal mass => cell average), dolfin project(expr, Zd|Qt).               */
@@ -98,7 +107,8 @@ typedef enum {
   FX_EXPR_RES_ORTH_SQ,      /* inner(res_orth,res_orth) -> Qt (:306)                       */
   FX_EXPR_SQRT_QT_A,        /* (QT_A)**0.5 -> Qt (:307-308)                                */
   FX_EXPR_H_KAPP,           /* h*kapp -> Qt (:434)                                         */
-  FX_EXPR_C4_RESTAU         /* cfg4 restau0 -> Zd (fenepmp_jbp.py:462-467)                 */
+  FX_EXPR_C4_RESTAU,        /* cfg4 restau0 -> Zd (fenepmp_jbp.py:462-467)                 */
+  FX_EXPR_C5_RESTAU         /* cfg5 restau0 -> Zd (compressible_dgp.py:382-386)            */
 } fx_expr;
 
 typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;

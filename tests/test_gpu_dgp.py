@@ -1,0 +1,68 @@
+"""GPU parity tests of config 5 (compressible buoyancy-driven flow) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import fxt_common as lc
+import fxt_dgp as dg
+from fenics_b200 import _abi as abi
+from oracle import fem
+from oracle.configs_dgp import CompDGP as OracleDGP
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from fenics_b200 import dolfin_api as dapi  # noqa: E402
+from fenics_b200.drivers import dgp  # noqa: E402
+
+TOL = 1e-12
+
+
+def _pair(n=6, **kw):
+    drv = dgp.CompDGP(mesh_resolution=n, **kw)
+    m = drv.mesh
+    om = fem.Mesh(m.coordinates(), m.cells())
+    ocl = OracleDGP(om, dofmaps={k: s.cell_dofs for k, s in drv.S.items()}, **kw)
+    assert np.array_equal(om.bfacet_marker, m.bfacet_marker)
+    return ocl, drv
+
+
+def test_cfg5_forms_match_oracle():
+    ocl, drv = _pair()
+    dg.randomize(ocl)
+    for slot, attr in dg.FIELD_ATTR.items():
+        getattr(drv, attr).vector().set_local(getattr(ocl, attr).vec)
+    for name, (fid, space) in dg.C5_FORMS.items():
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        err = lc.csr_rel_err(got.to_scipy(), ref) if name.startswith("a") else lc.rel_err(got.get_local(), ref)
+        assert err < TOL, (name, err)
+    for fid, form in ((abi.FX_FORM_C5_EK, ocl.E_k_form), (abi.FX_FORM_C5_EE, ocl.E_e_form),
+                      (abi.FX_FORM_C5_NUS, ocl.nus_form)):
+        ref = fem.assemble(form)
+        assert abs(dapi.assemble(drv.pr.form(fid)) - ref) < 1e-11 * max(1.0, abs(ref)), fid
+    for bo, bd in zip(ocl.bcu + ocl.bcT, drv.bcu + drv.bcT):
+        assert np.array_equal(bo.dofs, bd.dofs)
+
+
+def test_cfg5_k_steps_match_oracle():
+    """fields + Nusselt number after K steps within 1e-8 relative (north_star)."""
+    K = 3
+    ocl, drv = _pair(n=8)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    ocl.t = drv.t = 1.4  # thermal ramp 0.5(1+tanh(4(t-1.5))) is O(1) here
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        for k in ("E_k", "E_e", "Nus"):
+            assert abs(ro[k] - rd[k]) < 1e-8 * max(abs(ro[k]), 1e-10), (k, ro[k], rd[k])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+
+
+def test_cfg5_faithful_first_roll_fails_like_the_reference():
+    drv = dgp.CompDGP(mesh_resolution=4, faithful_first_roll=True)
+    with pytest.raises(RuntimeError):
+        drv.step()
