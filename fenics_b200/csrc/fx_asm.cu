@@ -27,35 +27,45 @@ int launch_geometry(fx_plan* P, cudaStream_t st) {
   return FX_OK;
 }
 
-// ---- K2/K3 cell kernels: grid (cell blocks, test components), block (32 cells, nb basis fns) ------
-template <class F>
-__global__ void __launch_bounds__(CB * 6) k_cell_matrix(const __grid_constant__ AsmArgs a) {
+// ---- K2/K3 cell kernels: grid = cell blocks of 32, block = (32 cells, 6 | 3 row warps) --------------
+// Phase 1 (pointwise data of 32 cells x NQ points -> shared memory) runs ONCE per cell block; the LD rows
+// of the element tensor are then dealt to the warps as "row tasks": warp y takes rows y, y+ny, ... so
+// every warp works on one (test component, basis function) at a time (warp-uniform dispatch).
+template <class F, bool MATRIX>
+__device__ __forceinline__ void cell_rows_dispatch(const AsmArgs& a, int cell0, const double* smem) {
   using Sp = typename F::Space;
+  for (int t0 = 0; t0 < Sp::LD; t0 += blockDim.y) {
+    const int task = t0 + threadIdx.y;  // local row index, uniform within the warp
+    static_for<0, Sp::NCOMP>([&](auto ic) {
+      constexpr int I = decltype(ic)::value;
+      if (task >= Sp::off(I) && task < Sp::off(I) + Sp::nb(I)) {
+        if constexpr (MATRIX) mat_rows<F, I>(a, cell0, threadIdx.x, task - Sp::off(I), smem);
+        else vec_rows<F, I>(a, cell0, threadIdx.x, task - Sp::off(I), smem);
+      }
+    });
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(CB * 6, 4) k_cell_matrix(const __grid_constant__ AsmArgs a) {
   extern __shared__ double smem[];
   const int cell0 = blockIdx.x * CB;
   if constexpr (F::NP > 0) {
     cell_phase1<F>(a, cell0, threadIdx.y * CB + threadIdx.x, blockDim.x * blockDim.y, smem);
     __syncthreads();
   }
-  static_for<0, Sp::NCOMP>([&](auto ic) {
-    constexpr int I = decltype(ic)::value;
-    if (blockIdx.y == I) mat_rows<F, I>(a, cell0, threadIdx.x, threadIdx.y, smem);
-  });
+  cell_rows_dispatch<F, true>(a, cell0, smem);
 }
 
 template <class F>
 __global__ void __launch_bounds__(CB * 6) k_cell_vector(const __grid_constant__ AsmArgs a) {
-  using Sp = typename F::Space;
   extern __shared__ double smem[];
   const int cell0 = blockIdx.x * CB;
   if constexpr (F::NP > 0) {
     cell_phase1<F>(a, cell0, threadIdx.y * CB + threadIdx.x, blockDim.x * blockDim.y, smem);
     __syncthreads();
   }
-  static_for<0, Sp::NCOMP>([&](auto ic) {
-    constexpr int I = decltype(ic)::value;
-    if (blockIdx.y == I) vec_rows<F, I>(a, cell0, threadIdx.x, threadIdx.y, smem);
-  });
+  cell_rows_dispatch<F, false>(a, cell0, smem);
 }
 
 // ---- K4 exterior-facet kernels: one thread per (boundary facet, local test dof) -------------------
@@ -138,7 +148,7 @@ static int run_matrix(fx_plan* P, AsmArgs a, cudaStream_t st) {
     FX_CUDA(cudaFuncSetAttribute(k_cell_matrix<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid((P->nc + CB - 1) / CB, Sp::NCOMP), block(CB, Sp::maxnb());
+  dim3 grid((P->nc + CB - 1) / CB), block(CB, Sp::maxnb());
   k_cell_matrix<F><<<grid, block, smem, st>>>(a);
   count_launch(1);
   if constexpr (F::Facet::present) {
@@ -165,7 +175,7 @@ static int run_vector(fx_plan* P, AsmArgs a, cudaStream_t st) {
     FX_CUDA(cudaFuncSetAttribute(k_cell_vector<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid((P->nc + CB - 1) / CB, Sp::NCOMP), block(CB, Sp::maxnb());
+  dim3 grid((P->nc + CB - 1) / CB), block(CB, Sp::maxnb());
   k_cell_vector<F><<<grid, block, smem, st>>>(a);
   count_launch(1);
   if constexpr (F::Facet::present) {

@@ -287,7 +287,25 @@ FX_HD void mat_rows(const AsmArgs& a, int cell0, int lane, int k, const double* 
     for (int j = 0; j < F::NP; ++j) d[j] = smem[(j * NQ + q) * CB + lane];
     row_qp<F, I>(g, k, xi, et, w * g.adet, d, a.p, acc);
   }
-  scatter_row<Sp>(a, cell, Sp::off(I) + k, acc);
+  // scatter only the entries this form can make non-zero (the values buffer was zeroed): the rest of
+  // DOLFIN's cell-block pattern stays an explicit 0.0, exactly as after PETSc ADD_VALUES of zeros
+  {
+    const long nc = a.m.nc;
+    const int arow = Sp::off(I) + k;
+    const int r = a.m.dm[space_id<Sp>::v][arow * nc + cell];
+    double* row = a.val + a.rowptr[r];
+    const uint8_t* pp = a.pos + (long)arow * Sp::LD * nc + cell;
+    static_for<0, Sp::NCOMP>([&](auto jc) {
+      constexpr int J = decltype(jc)::value;
+      constexpr int s0 = Sp::slot0(J), o = Sp::off(J);
+      constexpr bool used = row_uses<F, I>(s0) ||
+                            (Sp::kind(J) != DG0 && (row_uses<F, I>(s0 + 1) || row_uses<F, I>(s0 + 2)));
+      if constexpr (used) {
+#pragma unroll
+        for (int l = 0; l < Sp::nb(J); ++l) atomic_add(row + pp[(o + l) * nc], acc[o + l]);
+      }
+    });
+  }
 }
 
 template <class F, int I>
