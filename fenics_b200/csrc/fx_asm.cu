@@ -218,6 +218,9 @@ static int check_form_params(int form, const AsmArgs& a) {
   if (form >= FX_FORM_C4_A0 && form <= FX_FORM_C4_FORCE_Y && a.p.v[jbp::P_LAMBDA_D] != 0.0)
     return set_error(FX_ERR_UNSUPPORTED, "config-4 forms are implemented for lambda_D = 0 only (got %g)",
                      a.p.v[jbp::P_LAMBDA_D]);
+  if (form >= FX_FORM_C3_A0 && form <= FX_FORM_C3_FORCE_Y && (a.p.v[jbp::P_A0] != 0.0 || a.p.v[ldc::P_CONV] == 0.0))
+    return set_error(FX_ERR_UNSUPPORTED, "config-3 forms are implemented for A_0 = 0 and conv != 0 only (got %g, %g)",
+                     a.p.v[jbp::P_A0], a.p.v[ldc::P_CONV]);
   return FX_OK;
 }
 

@@ -2,6 +2,7 @@
 // X(id, Functor).  Used by fx_asm.cu (CUDA launchers) and tests/hostemu (CPU emulation).
 #pragma once
 #include "fx_forms_dgp.h"
+#include "fx_forms_ewm.h"
 #include "fx_forms_jbp.h"
 #include "fx_forms_ldc.h"
 
@@ -21,6 +22,14 @@
   X(FX_FORM_C2_A5, fx::ldc::C2_A5)          \
   X(FX_FORM_C2_A7, fx::ldc::C2_A7)          \
   X(FX_FORM_C2_A4, fx::ldc::LDC_A4)         \
+  X(FX_FORM_C3_A0, fx::ldc::C2_A0)          \
+  X(FX_FORM_C3_A1, fx::ewm::C3_A1)          \
+  X(FX_FORM_C3_A2, fx::jbp::C4_A2)          \
+  X(FX_FORM_C3_A5, fx::ewm::C3_A5)          \
+  X(FX_FORM_C3_A6, fx::jbp::SU_RHO_A6)      \
+  X(FX_FORM_C3_A7, fx::ewm::C3_A7)          \
+  X(FX_FORM_C3_A4, fx::ewm::C3_A4)          \
+  X(FX_FORM_C3_A9, fx::ewm::C3_A9)          \
   X(FX_FORM_C4_A0, fx::ldc::C2_A0)          \
   X(FX_FORM_C4_A2, fx::jbp::C4_A2)          \
   X(FX_FORM_C4_A5, fx::jbp::C4_A5)          \
@@ -51,6 +60,14 @@
   X(FX_FORM_C2_L7, fx::ldc::C2_L7)                          \
   X(FX_FORM_C2_L4, fx::ldc::LDC_L4<true>)                   \
   X(FX_FORM_C2_L_RHO1, fx::ldc::C2_L_RHO1)                  \
+  X(FX_FORM_C3_L0, fx::ldc::C2_L0)                          \
+  X(FX_FORM_C3_L1, fx::ewm::C3_L1)                          \
+  X(FX_FORM_C3_L2, fx::ewm::C3_L2)                          \
+  X(FX_FORM_C3_L5, fx::ewm::C3_L5)                          \
+  X(FX_FORM_C3_L6, fx::jbp::SU_RHO_L6)                      \
+  X(FX_FORM_C3_L7, fx::ewm::C3_L7)                          \
+  X(FX_FORM_C3_L4, fx::ewm::C3_L4)                          \
+  X(FX_FORM_C3_L9, fx::ewm::C3_L9)                          \
   X(FX_FORM_C4_L0, fx::ldc::C2_L0)                          \
   X(FX_FORM_C4_L2, fx::jbp::C4_L2)                          \
   X(FX_FORM_C4_L5, fx::jbp::C4_L5)                          \
@@ -78,12 +95,17 @@
   X(FX_FORM_C1_EE, fx::ldc::LDC_EE)     \
   X(FX_FORM_C2_EK, fx::ldc::C2_EK)      \
   X(FX_FORM_C2_EE, fx::ldc::LDC_EE)     \
+  X(FX_FORM_C3_EK, fx::ldc::C2_EK)      \
+  X(FX_FORM_C3_EE, fx::dgp::C5_EE)      \
   X(FX_FORM_C4_EK, fx::ldc::C2_EK)      \
   X(FX_FORM_C4_EE, fx::jbp::C4_EE)      \
   X(FX_FORM_C5_EK, fx::ldc::C2_EK)      \
   X(FX_FORM_C5_EE, fx::dgp::C5_EE)
 
 #define FX_FACET_SCALAR_FORMS(X)                    \
+  X(FX_FORM_C3_TORQUE, fx::ewm::C3_JOURNAL<0>)      \
+  X(FX_FORM_C3_FORCE_X, fx::ewm::C3_JOURNAL<1>)     \
+  X(FX_FORM_C3_FORCE_Y, fx::ewm::C3_JOURNAL<2>)     \
   X(FX_FORM_C4_TORQUE, fx::jbp::C4_JOURNAL<0>)      \
   X(FX_FORM_C4_FORCE_X, fx::jbp::C4_JOURNAL<1>)     \
   X(FX_FORM_C4_FORCE_Y, fx::jbp::C4_JOURNAL<2>)     \

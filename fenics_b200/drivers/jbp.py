@@ -69,7 +69,7 @@ class FenepmpJBP(_LDC):
         tt = self._bct = {"t": 0.0}
 
         def wspin(x):  # Expression w, ramped spin of the journal  (:249)
-            g = 0.5 * (1.0 + np.tanh(8 * (tt["t"] - 0.5)))
+            g = 0.5 * (1.0 + np.tanh(8 * (tt["t"] - 0.5))) if getattr(self, "ramp", True) else 1.0
             return np.column_stack([g * (x[:, 1] - y_1) / r_a, -g * (x[:, 0] - x_1) / r_a])
 
         spin = DirichletBC(W.sub(0), wspin, in0)

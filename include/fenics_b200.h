@@ -83,6 +83,15 @@ typedef enum {
   FX_FORM_C2_L_RHO1,      /* inner(q, rho0 + Ma^2/Re (p1-p0))*dx (comp_LDC_mesh_convergence.py:501-502) */
   /* cfg2: functionals */
   FX_FORM_C2_EK = 240, FX_FORM_C2_EE,
+  /* cfg3 = "flow between eccentrically rotating cylinders"/incompressible_benchmarkEWM.py at its own
+   * A_0 = k_ewm = B = 0 (time loop :465-782; parameter FX_P_AL1 carries `al`): bilinear */
+  FX_FORM_C3_A0 = 300, FX_FORM_C3_A1, FX_FORM_C3_A2, FX_FORM_C3_A5, FX_FORM_C3_A6, FX_FORM_C3_A7, FX_FORM_C3_A4,
+  FX_FORM_C3_A9,
+  /* cfg3: linear */
+  FX_FORM_C3_L0 = 320, FX_FORM_C3_L1, FX_FORM_C3_L2, FX_FORM_C3_L5, FX_FORM_C3_L6, FX_FORM_C3_L7, FX_FORM_C3_L4,
+  FX_FORM_C3_L9,
+  /* cfg3: functionals; torque / forces over ds(0) with sigmacon (:690-707) */
+  FX_FORM_C3_EK = 340, FX_FORM_C3_EE, FX_FORM_C3_TORQUE, FX_FORM_C3_FORCE_X, FX_FORM_C3_FORCE_Y,
   /* cfg4 = "flow between eccentrically rotating cylinders"/fenepmp_jbp.py (lambda_D = 0): bilinear */
   FX_FORM_C4_A0 = 400, FX_FORM_C4_A2, FX_FORM_C4_A5, FX_FORM_C4_A6, FX_FORM_C4_A7, FX_FORM_C4_A4, FX_FORM_C4_A9,
   /* cfg4: linear */

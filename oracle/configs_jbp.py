@@ -86,7 +86,7 @@ class FenepmpJBP:
         self._tt = {"t": 0.0}
 
         def wspin(x):  # Expression w (:249)
-            f = 0.5 * (1.0 + np.tanh(8 * (self._tt["t"] - 0.5)))
+            f = 0.5 * (1.0 + np.tanh(8 * (self._tt["t"] - 0.5))) if getattr(self, "ramp", True) else 1.0
             return np.stack([f * (x[:, 1] - y_1) / r_a, -f * (x[:, 0] - x_1) / r_a], 1)
 
         spin = fem.DirichletBC(S["W"], (0, 1), wspin, self.in_omega0)
