@@ -155,6 +155,7 @@ void fx_plan_destroy(fx_plan* P) {
   cudaFree(P->bf_cell); cudaFree(P->bf_local); cudaFree(P->bf_marker); cudaFree(P->bf_geo);
   for (int s = 0; s < S_N; ++s) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
+    cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows);
   }
   cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->crs); cudaFree(P->cre); cudaFree(P->cblkend);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
@@ -301,6 +302,27 @@ int fx_dotw_dev(fx_plan* P, int n, const double* x, const double* y, const doubl
 int fx_plan_set_owned_cells(fx_plan* P, int nc_owned) {
   if (!P || nc_owned < 0 || nc_owned > P->nc) return set_error(FX_ERR_ARG, "fx_plan_set_owned_cells: bad argument");
   P->nc_owned = nc_owned;
+  return FX_OK;
+}
+
+int fx_plan_set_eliminated_dofs(fx_plan* P, int space, const int* rows, int n) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr || n < 0 || (n > 0 && !rows))
+    return set_error(FX_ERR_ARG, "fx_plan_set_eliminated_dofs: bad argument");
+  DevPattern& d = P->sp[space];
+  cudaFree(d.elim); cudaFree(d.elim_rows);
+  d.elim = nullptr; d.elim_rows = nullptr; d.nelim = 0;
+  if (n == 0) return FX_OK;
+  std::vector<uint8_t> mask((size_t)d.n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (rows[i] < 0 || rows[i] >= d.n || mask[rows[i]])
+      return set_error(FX_ERR_ARG, "fx_plan_set_eliminated_dofs: row %d out of range or repeated", rows[i]);
+    mask[rows[i]] = 1;
+  }
+  FX_CUDA(cudaMalloc((void**)&d.elim, (size_t)d.n));
+  FX_CUDA(cudaMalloc((void**)&d.elim_rows, sizeof(int) * (size_t)n));
+  FX_CUDA(cudaMemcpy(d.elim, mask.data(), (size_t)d.n, cudaMemcpyHostToDevice));
+  FX_CUDA(cudaMemcpy(d.elim_rows, rows, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  d.nelim = n;
   return FX_OK;
 }
 

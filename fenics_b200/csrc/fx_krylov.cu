@@ -58,7 +58,18 @@ __device__ __forceinline__ void finish(const KArgs& a, int it, int conv, double 
   }
 }
 
+// Leaving a solve: record the outcome, then recover the eliminated rows from the final x.  Every CTA
+// takes the same exit (deterministic reductions), so the barrier is safe.
+__device__ __forceinline__ void leave(cg::grid_group& grid, const KArgs& a, int it, int conv, double rn, double bn) {
+  finish(a, it, conv, rn, bn);
+  if (a.A.elim != nullptr) {
+    grid.sync();
+    if (back_substitute(a.A, a.x, a.b) != 0) a.info->converged = -3;
+  }
+}
+
 __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc) {
+  if (A.elim != nullptr && A.elim[row]) return 0.0;  // eliminated rows stay identically zero in the iteration
   if (pc != FX_PC_JACOBI) return 1.0;
   double dg = 0.0;
   for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j)
@@ -71,7 +82,7 @@ __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc
 // ||r|| <= max(rtol ||M^-1 b||, atol) (PETSc default for left preconditioning).
 __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[3 * 33];
+  __shared__ double sh[4 * 33];
   __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
@@ -86,20 +97,21 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
   int phase = 0;
 
   // setup: compacted matrix, dinv, r = M^-1 (b - A x), rhat = r, p = v = 0
-  if (A.rs != nullptr) compact_zeros(A);
-  double acc[2] = {0.0, 0.0};
+  double acc[3] = {0.0, 0.0, 0.0};
+  if (A.rs != nullptr) acc[2] = (double)compact_zeros(A);
   spmv_stream(A, a.x, prod, [&](int row, double ax) {
     const double di = row_diag_inv(A, row, a.pc);
     const double ri = di * (a.b[row] - ax), bi = di * a.b[row];
     dinv[row] = di; r[row] = ri; rh[row] = ri; p[row] = 0.0; v[row] = 0.0;
     acc[0] += ri * ri; acc[1] += bi * bi;
   });
-  grid_sum<2>(grid, acc, a.red, phase, sh);
+  grid_sum<3>(grid, acc, a.red, phase, sh);
+  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
   const double tol = fmax(a.rtol * bn, a.atol);
-  if (!(rn == rn)) { finish(a, 0, -1, rn, bn); return; }
-  if (rn <= tol) { finish(a, 0, 1, rn, bn); return; }
+  if (!(rn == rn)) { leave(grid, a, 0, -1, rn, bn); return; }
+  if (rn <= tol) { leave(grid, a, 0, 1, rn, bn); return; }
   double rho = acc[0], rho_old = 1.0, alpha = 1.0, omega = 1.0;
   double rhn = rn;  // ||rhat||
   int restarts = 0;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
     // Dirichlet rows only is annihilated in one step, leaving rhat orthogonal to r).  Restart with
     // rhat = r, the standard cure.
     if (fabs(rho) <= 1e-14 * rhn * rn || omega == 0.0) {
-      if (++restarts > 50) { finish(a, it - 1, -1, rn, bn); return; }
+      if (++restarts > 50) { leave(grid, a, it - 1, -1, rn, bn); return; }
       for (int i = gt; i < n; i += gs) { rh[i] = r[i]; p[i] = 0.0; v[i] = 0.0; }
       rho = rn * rn; rhn = rn; rho_old = 1.0; alpha = 1.0; omega = 1.0;
     }
@@ -122,7 +134,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
       d1[0] += rh[row] * vi;
     });
     grid_sum<1>(grid, d1, a.red, phase, sh);
-    if (d1[0] == 0.0) { finish(a, it - 1, -1, rn, bn); return; }
+    if (d1[0] == 0.0) { leave(grid, a, it - 1, -1, rn, bn); return; }
     alpha = rho / d1[0];
     double d2[1] = {0.0};
     for (int i = gt; i < n; i += gs) {
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
     grid_sum<1>(grid, d2, a.red, phase, sh);
     if (sqrt(d2[0]) <= tol) {  // early exit on the half step (KSPBCGS does the same)
       for (int i = gt; i < n; i += gs) a.x[i] += alpha * p[i];
-      finish(a, it, 1, sqrt(d2[0]), bn);
+      leave(grid, a, it, 1, sqrt(d2[0]), bn);
       return;
     }
     double d3[2] = {0.0, 0.0};
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
       d3[1] += ti * ti;
     });
     grid_sum<2>(grid, d3, a.red, phase, sh);
-    if (d3[1] == 0.0) { finish(a, it, -1, sqrt(d2[0]), bn); return; }
+    if (d3[1] == 0.0) { leave(grid, a, it, -1, sqrt(d2[0]), bn); return; }
     omega = d3[0] / d3[1];
     double d4[2] = {0.0, 0.0};
     for (int i = gt; i < n; i += gs) {
@@ -158,10 +170,10 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
     rho_old = rho;
     rho = d4[0];
     rn = sqrt(d4[1]);
-    if (!(rn == rn) || rn > a.dtol * bn) { finish(a, it, -1, rn, bn); return; }
-    if (rn <= tol) { finish(a, it, 1, rn, bn); return; }
+    if (!(rn == rn) || rn > a.dtol * bn) { leave(grid, a, it, -1, rn, bn); return; }
+    if (rn <= tol) { leave(grid, a, it, 1, rn, bn); return; }
   }
-  finish(a, a.maxit, 0, rn, bn);
+  leave(grid, a, a.maxit, 0, rn, bn);
 }
 
 // ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
 // Monitored norm ||M^-1 r||_2 (PETSc default for KSPCG).
 __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[3 * 33];
+  __shared__ double sh[4 * 33];
   __shared__ double prod[SPMV_SMEM_DOUBLES];
   const CsrView& A = a.A;
   const int n = A.n;
@@ -182,27 +194,28 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
   double* s = a.w + 4 * (size_t)n;
   double* dinv = a.w + 5 * (size_t)n;
   int phase = 0;
-  if (A.rs != nullptr) compact_zeros(A);
-  double acc[3] = {0.0, 0.0, 0.0};
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (A.rs != nullptr) acc[3] = (double)compact_zeros(A);
   spmv_stream(A, a.x, prod, [&](int row, double ax) {
     const double di = row_diag_inv(A, row, a.pc);
     const double ri = a.b[row] - ax, ui = di * ri, bi = di * a.b[row];
     dinv[row] = di; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
     acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
   });
-  grid_sum<3>(grid, acc, a.red, phase, sh);
+  grid_sum<4>(grid, acc, a.red, phase, sh);
+  if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }
   double gamma = acc[0], un = sqrt(acc[1]);
   const double bn = sqrt(acc[2]);
   const double tol = fmax(a.rtol * bn, a.atol);
-  if (!(un == un)) { finish(a, 0, -1, un, bn); return; }
-  if (un <= tol) { finish(a, 0, 1, un, bn); return; }
+  if (!(un == un)) { leave(grid, a, 0, -1, un, bn); return; }
+  if (un <= tol) { leave(grid, a, 0, 1, un, bn); return; }
   double d0[1] = {0.0};
   spmv_stream(A, u, prod, [&](int row, double au) {
     w[row] = au;
     d0[0] += au * u[row];
   });
   grid_sum<1>(grid, d0, a.red, phase, sh);
-  if (!(d0[0] > 0.0)) { finish(a, 0, -1, un, bn); return; }
+  if (!(d0[0] > 0.0)) { leave(grid, a, 0, -1, un, bn); return; }
   double alpha = gamma / d0[0], beta = 0.0;
   for (int it = 1; it <= a.maxit; ++it) {
     double d[3] = {0.0, 0.0, 0.0};
@@ -225,15 +238,15 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
     });
     grid_sum<3>(grid, d, a.red, phase, sh);
     un = sqrt(d[1]);
-    if (!(un == un) || un > a.dtol * bn) { finish(a, it, -1, un, bn); return; }
-    if (un <= tol) { finish(a, it, 1, un, bn); return; }
+    if (!(un == un) || un > a.dtol * bn) { leave(grid, a, it, -1, un, bn); return; }
+    if (un <= tol) { leave(grid, a, it, 1, un, bn); return; }
     beta = d[0] / gamma;
     const double denom = d[2] - beta * d[0] / alpha;
-    if (!(denom > 0.0)) { finish(a, it, -1, un, bn); return; }  // not SPD / breakdown
+    if (!(denom > 0.0)) { leave(grid, a, it, -1, un, bn); return; }  // not SPD / breakdown
     alpha = d[0] / denom;
     gamma = d[0];
   }
-  finish(a, a.maxit, 0, un, bn);
+  leave(grid, a, a.maxit, 0, un, bn);
 }
 
 // ---- pipelined CG (Ghysels-Vanroose), matrix resident in shared memory -----------------------------------
@@ -454,12 +467,13 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
-  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->crs, P->cre, P->cblkend, P->ccol, P->cval};
+  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->crs, P->cre, P->cblkend, P->ccol, P->cval,
+                 p.nelim > 0 ? p.elim : nullptr, p.elim_rows, p.nelim};
   ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
-  if (method == FX_KSP_CG && rtol >= 1e-9) {
+  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0) {
     const int warps = P->num_sms * LA_WARPS;
     const int R = (p.nrowblk + warps - 1) / warps;
     if (R <= PCG_MAXR) {

@@ -86,6 +86,11 @@ struct CsrView {
   int* blkend;  // [nrowblk] one past the last entry of the row block
   int* col2;
   double* val2;
+  // block-triangular elimination (null = off): rows with elim[row] != 0 are left out of the Krylov
+  // iteration and recovered by back_substitute(); requires A[active, eliminated] == 0
+  const unsigned char* elim;
+  const int* elim_rows;
+  int nelim;
 };
 
 // Drop exactly-zero entries, row block by row block, into (col2, val2) at the block's original offset.
@@ -93,9 +98,12 @@ struct CsrView {
 // couples them: 20-60 % of the stored values of the W and Zc matrices are exact
 // zeros, which a Krylov solve would otherwise stream from HBM twice per iteration.  The warp that
 // compacts a block is the warp that later streams it, so no grid barrier is needed in between.
-__device__ __forceinline__ void compact_zeros(const CsrView& A) {
+// With elimination on, eliminated rows become empty in the copy (never streamed); the return value
+// counts non-zero couplings A[active, eliminated] seen by this thread (must total 0).
+__device__ __forceinline__ int compact_zeros(const CsrView& A) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nw = gridDim.x * LA_WARPS;
+  int bad = 0;
   for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
     const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
     const int j0 = A.rowptr[r0];
@@ -104,7 +112,17 @@ __device__ __forceinline__ void compact_zeros(const CsrView& A) {
     int b = 0, e = 0, cnt = 0;
     if (act) {
       b = A.rowptr[row]; e = A.rowptr[row + 1];
-      for (int j = b; j < e; ++j) cnt += (A.val[j] != 0.0);
+      if (A.elim != nullptr && A.elim[row]) {
+        e = b;  // eliminated row: empty
+      } else if (A.elim != nullptr) {
+        for (int j = b; j < e; ++j) {
+          const bool nz = A.val[j] != 0.0;
+          cnt += nz;
+          bad += (nz && A.elim[A.col[j]]);
+        }
+      } else {
+        for (int j = b; j < e; ++j) cnt += (A.val[j] != 0.0);
+      }
     }
     int incl = cnt;
 #pragma unroll
@@ -125,6 +143,36 @@ __device__ __forceinline__ void compact_zeros(const CsrView& A) {
     if (lane == 0) A.blkend[k] = j0 + total;
     __syncwarp();
   }
+  return bad;
+}
+
+// x[row] = (b[row] - sum_{j != row} A[row,j] x[j]) / A[row,row] for the eliminated rows, 16 lanes per row
+// (exact for a trailing block with diagonal self-coupling, e.g. the DG0 DEVSS rows of the W systems).
+// Returns the number of non-zero couplings between DIFFERENT eliminated rows seen by this thread.
+__device__ __forceinline__ int back_substitute(const CsrView& A, double* x, const double* b) {
+  int bad = 0;
+  const int sub = threadIdx.x & 15;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, ng = (gridDim.x * blockDim.x) >> 4;
+  const int rounds = (A.nelim + ng - 1) / ng;  // uniform trip count: the shuffles need whole warps
+  for (int it = 0; it < rounds; ++it) {
+    const int k = it * ng + g;
+    const int row = k < A.nelim ? A.elim_rows[k] : -1;
+    double s = 0.0, dg = 0.0;
+    if (row >= 0)
+      for (int j = A.rowptr[row] + sub; j < A.rowptr[row + 1]; j += 16) {
+        const int c = A.col[j];
+        const double v = A.val[j];
+        if (c == row) dg = v;
+        else if (v != 0.0) { s += v * x[c]; bad += A.elim[c]; }
+      }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o, 16);
+    }
+    if (row >= 0 && sub == 0) x[row] = (b[row] - s) / dg;
+  }
+  return bad;
 }
 
 // CSR-stream SpMV at warp granularity (rows of 7-57 nonzeros are too short for a warp per row and a

@@ -33,6 +33,10 @@ struct DevPattern {
   int* dm_t = nullptr;
   int* rowblk = nullptr;
   int nrowblk = 0;
+  // block-triangular elimination (fx_plan_set_eliminated_dofs): trailing rows solved by back-substitution
+  uint8_t* elim = nullptr;    // [n] 1 = eliminated row
+  int* elim_rows = nullptr;   // [nelim]
+  int nelim = 0;
 };
 
 constexpr int KRYLOV_NWORK = 12;

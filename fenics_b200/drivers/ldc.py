@@ -41,12 +41,14 @@ class _LDC:
     solver = ("bicgstab", "default")   # what the reference passes to solve()
     pressure_method = "bicgstab"       # reference; "cg" is the north_star upgrade (A5 is symmetric)
     STATE_FIELDS = ()                  # fields carried from step to step (host<->device in e2e mode)
+    eliminate_devss = True             # W solves: iterate on the velocity rows, back-substitute the DG0 DEVSS rows
 
     def _setup(self, mesh, dofmaps, device):
         self.mesh = mesh
         W, V, _, _, Zd, Zc, Q, Qt, _ = function_spaces(mesh, 2, dofmaps)
         self.S = dict(W=W, V=V, Zd=Zd, Zc=Zc, Q=Q, Qt=Qt)
         self.plan = Plan(mesh, [W, Zc, Q, Zd, Qt, V], device)
+        self.set_devss_elimination(self.eliminate_devss)
         self.pr = Problem(self.plan)
         for k, v in self.p.items():
             self.pr.set_param(getattr(abi, "FX_P_" + k.upper()), v)
@@ -75,6 +77,14 @@ class _LDC:
         self.solve_labels = []
         self._ticket = 0
         self.profile = None          # set to a list to record (label, start_event, end_event) per phase
+
+    def set_devss_elimination(self, on):
+        """The W systems are block lower triangular: the rows tested with R read (u, D) but no momentum row
+        reads D, and D-D is the diagonal DG0 mass (e.g. incomp_LDC.py:317-325).  With elimination on the
+        Krylov kernels iterate on the velocity block and recover D by exact back-substitution."""
+        self.eliminate_devss = bool(on)
+        rows = np.unique(self.S["W"].cell_dofs[:, 12:15]) if on else np.zeros(0, dtype=np.int32)
+        self.plan.set_eliminated_dofs("W", rows)
 
     # -- helpers -------------------------------------------------------------------------------------
     @contextlib.contextmanager

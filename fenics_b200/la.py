@@ -62,6 +62,12 @@ class Plan:
         m = np.ascontiguousarray(markers, dtype=np.int32)
         check(lib.fx_plan_set_markers(self.h, m.ctypes.data, len(m)))
 
+    def set_eliminated_dofs(self, space, rows):
+        """Krylov solves on `space` iterate on the other rows and back-substitute these (block-triangular
+        systems, fx_plan_set_eliminated_dofs); an empty list switches it off."""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        check(lib.fx_plan_set_eliminated_dofs(self.h, abi.SPACE_ID[space], r.ctypes.data, len(r)))
+
     def dim(self, space):
         return lib.fx_space_dim(self.h, abi.SPACE_ID[space])
 

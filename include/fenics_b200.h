@@ -207,6 +207,18 @@ int fx_dotw_dev(fx_plan* plan, int n, const double* x_dev, const double* y_dev, 
  * the boundary facets of those cells; pass nc (the default) to integrate over every local cell. */
 int fx_plan_set_owned_cells(fx_plan* plan, int nc_owned);
 
+/* Block-triangular elimination for the Krylov solves on `space`.  The W systems of every loop
+ * (a1/a2/a7, e.g. incomp_LDC.py:317-325) are block lower triangular: the DEVSS rows
+ * (D - grad u, R) read the velocity but the momentum rows never read D, and the D-D block is the
+ * diagonal DG0 mass.  With rows[0..n) registered (host array of dof indices), fx_krylov_solve*
+ * iterates on the remaining rows only and recovers the registered rows afterwards by exact
+ * back-substitution x_i = (b_i - sum_{j!=i} A_ij x_j) / A_ii: same linear system, same solution
+ * to the requested tolerance, fewer and cheaper iterations.  The structure is verified on the device
+ * at every solve: a non-zero A[active, eliminated] or A[eliminated, other eliminated] entry makes
+ * the solve fail with converged = -3.  n = 0 switches elimination off.  The convergence test then
+ * monitors the residual of the active rows.                                                     */
+int fx_plan_set_eliminated_dofs(fx_plan* plan, int space, const int* rows, int n);
+
 /* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default

@@ -158,6 +158,49 @@ def test_krylov_against_direct(method, pc):
         assert info2.iterations == 0
 
 
+def test_devss_elimination_same_solution():
+    """W systems are block lower triangular; iterating on the velocity rows and back-substituting the DG0
+    rows gives the LU solution like the full iteration does.  (Iteration counts are not comparable at equal
+    rtol: the full iteration's reference norm ||M^-1 b|| includes the DG0 rows.)"""
+    ocl, drv = _pair(2, n=12)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    rng = np.random.default_rng(3)
+    for fid in (abi.FX_FORM_C2_A1, abi.FX_FORM_C2_A7):
+        A = dapi.assemble(drv.pr.form(fid))
+        b = la.Vector(drv.plan, "W")
+        bv = rng.standard_normal(b.size())
+        b.set_local(bv)
+        for bc in drv.bcu:
+            bc.apply(A, b)
+        ref = spla.splu(A.to_scipy().tocsc()).solve(b.get_local())
+        its = {}
+        for on in (False, True):
+            drv.set_devss_elimination(on)
+            x = la.Vector(drv.plan, "W")
+            info = la.krylov_solve(A, x, b, "bicgstab", "jacobi", rtol=1e-13, maxit=20000)
+            assert info.converged == 1
+            assert lc.rel_err(x.get_local(), ref) < 1e-9, (fid, on)
+            its[on] = info.iterations
+        assert its[True] > 0 and its[False] > 0
+
+
+def test_elimination_rejects_matrices_that_are_not_block_triangular():
+    ocl, drv = _pair(2, n=8)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A4))  # stress matrix: every component couples
+    b = la.Vector(drv.plan, "Zc")
+    b.set_local(np.ones(b.size()))
+    x = la.Vector(drv.plan, "Zc")
+    drv.plan.set_eliminated_dofs("Zc", np.unique(drv.S["Zc"].cell_dofs[:, 12:18]))
+    with pytest.raises(RuntimeError) as e:
+        la.krylov_solve(A, x, b, "bicgstab", "jacobi")
+    assert "status -3" in str(e.value)
+    drv.plan.set_eliminated_dofs("Zc", [])
+    assert la.krylov_solve(A, x, b, "bicgstab", "jacobi").converged == 1
+
+
 def test_krylov_nonconvergence_raises():
     ocl, drv = _pair(2, n=8)
     A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
