@@ -133,3 +133,28 @@ def pressure_study(n, steps=2):
 
 if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[3] == "p":
     pressure_study(n, steps)
+
+
+def block_jacobi_cg(A, b, bs, rtol=1e-5, maxit=20000):
+    """PCG with exact solves on diagonal blocks of `bs` consecutive rows."""
+    n = len(b)
+    A = A.tocsr()
+    blocks = [(s, min(n, s + bs)) for s in range(0, n, bs)]
+    inv = [np.linalg.inv(A[s:e, s:e].toarray()) for s, e in blocks]
+
+    def M(r):
+        z = np.empty_like(r)
+        for (s, e), Bi in zip(blocks, inv):
+            z[s:e] = Bi @ r[s:e]
+        return z
+    x = np.zeros_like(b); r = b.copy(); z = M(r); p = z.copy(); rz = r @ z
+    r0 = np.linalg.norm(M(b))
+    for it in range(1, maxit + 1):
+        q = A @ p
+        a = rz / (p @ q)
+        x += a * p; r -= a * q
+        z = M(r)
+        if np.linalg.norm(z) <= rtol * r0:
+            return x, it
+        rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
+    return x, maxit
