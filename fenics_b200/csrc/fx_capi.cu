@@ -131,9 +131,11 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
   if (maxnnz > 0 &&
       (cudaMalloc((void**)&P->cval, sizeof(double) * maxnnz) != cudaSuccess ||
        cudaMalloc((void**)&P->ccol, sizeof(int) * maxnnz) != cudaSuccess ||
-       cudaMalloc((void**)&P->crs, sizeof(int) * maxn) != cudaSuccess ||
        cudaMalloc((void**)&P->cre, sizeof(int) * maxn) != cudaSuccess ||
-       cudaMalloc((void**)&P->cblkend, sizeof(int) * (maxblk + 1)) != cudaSuccess))
+       cudaMalloc((void**)&P->cdesc, sizeof(int4) * (maxblk + 1)) != cudaSuccess ||
+       cudaMalloc((void**)&P->cprefix, sizeof(int) * (maxblk + 2)) != cudaSuccess ||
+       cudaMalloc((void**)&P->scanpart, sizeof(int) * MAX_GRID) != cudaSuccess ||
+       cudaMalloc((void**)&P->bar, 64) != cudaSuccess))
     return fail(set_error(FX_ERR_CUDA, "cudaMalloc compacted-matrix buffers failed"));
   P->part_cap = std::max((nc + 255) / 256, 148 * 8);
   if (cudaMalloc((void**)&P->part, sizeof(double) * P->part_cap) != cudaSuccess ||
@@ -157,7 +159,7 @@ void fx_plan_destroy(fx_plan* P) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
     cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows);
   }
-  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->crs); cudaFree(P->cre); cudaFree(P->cblkend);
+  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->bar);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;
 }

@@ -9,40 +9,57 @@
 // (lid-driven-cavity/incomp_LDC.py:331 and every other solve site).
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <vector>
+
 #include "fx_la_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace fx {
 
+// optional phase timestamps (FX_KRYLOV_PROF=1): block 0 / thread 0 stamps %globaltimer at phase boundaries
+__device__ unsigned long long g_prof[1024];
+__device__ unsigned long long g_prof_warp[8192];  // per-warp end of the first SpMV of iteration 2
+__device__ __forceinline__ void stamp(int prof, int& np) {
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0 && np < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_prof[np++] = t;
+  }
+}
+
 struct KArgs {
+  int prof;
   CsrView A;
   double* x;
   const double* b;
   double* w;    // KRYLOV_NWORK x n work vectors
   double* red;  // 2 x RED_SLOTS x MAX_GRID
+  unsigned* bar;  // grid-barrier counter (zeroed before the launch)
   double rtol, atol, dtol;
   int maxit, pc;
   fx_solve_info* info;
 };
 
-// Deterministic grid-wide sum of NV values: block partials -> scratch -> grid.sync -> every CTA sums
+// Deterministic grid-wide sum of NV values: block partials -> scratch -> grid barrier -> every CTA sums
 // all partials in the same order (bitwise identical result in every CTA).  `phase` alternates the
 // scratch half so a fast CTA cannot overwrite partials a slow CTA is still reading.
 template <int NV>
-__device__ __forceinline__ void grid_sum(cg::grid_group& grid, double (&v)[NV], double* red, int& phase,
-                                         double* sh) {
+__device__ __forceinline__ void grid_sum(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
   double* buf = red + (size_t)(phase & 1) * RED_SLOTS * MAX_GRID;
   block_sum_bcast_n<NV>(v, sh);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) buf[i * MAX_GRID + blockIdx.x] = v[i];
   }
-  grid.sync();
+  bar.sync();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     double s = 0.0;
-    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) s += buf[i * MAX_GRID + j];
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) s += __ldcg(buf + i * MAX_GRID + j);
     v[i] = s;
   }
   block_sum_bcast_n<NV>(v, sh);
@@ -60,10 +77,10 @@ __device__ __forceinline__ void finish(const KArgs& a, int it, int conv, double 
 
 // Leaving a solve: record the outcome, then recover the eliminated rows from the final x.  Every CTA
 // takes the same exit (deterministic reductions), so the barrier is safe.
-__device__ __forceinline__ void leave(cg::grid_group& grid, const KArgs& a, int it, int conv, double rn, double bn) {
+__device__ __forceinline__ void leave(GridBar& bar, const KArgs& a, int it, int conv, double rn, double bn) {
   finish(a, it, conv, rn, bn);
   if (a.A.elim != nullptr) {
-    grid.sync();
+    bar.sync();
     if (back_substitute(a.A, a.x, a.b) != 0) a.info->converged = -3;
   }
 }
@@ -77,13 +94,22 @@ __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc
   return dg != 0.0 ? 1.0 / dg : 1.0;
 }
 
+struct Ops2 { double a, b; };
+struct Ops3 { double a, b, c; };
+
 // ---- BiCGStab -------------------------------------------------------------------------------------------
 // The recurrence runs on M^-1 A; the monitored norm is ||M^-1 r||_2 and the test is
 // ||r|| <= max(rtol ||M^-1 b||, atol) (PETSc default for left preconditioning).
-__global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constant__ KArgs a) {
-  cg::grid_group grid = cg::this_grid();
+// Four grid barriers per iteration: the scalars of the second half step ((t,s), (t,t), (rhat,s), (rhat,t))
+// are reduced together, which gives omega, rho_new = (rhat, s - omega t) and, from (s,s), the residual
+// norm ||s - omega t|| without a reduction of their own, so x, r and the next search direction p are
+// updated in ONE pass over the vectors.  A residual that the recurrence reports as converged is
+// confirmed with a true norm before the solve returns.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __grid_constant__ KArgs a) {
   __shared__ double sh[4 * 33];
-  __shared__ double prod[SPMV_SMEM_DOUBLES];
+  __shared__ int sh_i[64];
+  extern __shared__ __align__(16) double prod[];  // (THREADS/32) x SPMV_NNZB
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -95,95 +121,129 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_bicgstab(const __grid_constan
   double* t = a.w + 5 * (size_t)n;
   double* dinv = a.w + 6 * (size_t)n;
   int phase = 0;
+  GridBar bar;
+  bar.init(a.bar);
 
-  // setup: compacted matrix, dinv, r = M^-1 (b - A x), rhat = r, p = v = 0
+  // setup: compacted matrix, balanced partition, dinv, r = M^-1 (b - A x), rhat = p = r, v = 0
   double acc[3] = {0.0, 0.0, 0.0};
-  if (A.rs != nullptr) acc[2] = (double)compact_zeros(A);
-  spmv_stream(A, a.x, prod, [&](int row, double ax) {
-    const double di = row_diag_inv(A, row, a.pc);
-    const double ri = di * (a.b[row] - ax), bi = di * a.b[row];
-    dinv[row] = di; r[row] = ri; rh[row] = ri; p[row] = 0.0; v[row] = 0.0;
-    acc[0] += ri * ri; acc[1] += bi * bi;
-  });
-  grid_sum<3>(grid, acc, a.red, phase, sh);
+  acc[2] = (double)compact_zeros(A);
+  bar.sync();
+  const BlockRange rg = balance_partition(A, bar, sh_i);
+  spmv_stream_c(A, rg, a.x, prod,
+                [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
+                [&](int row, double ax, const Ops2& o) {
+                  const double ri = o.a * (o.b - ax), bi = o.a * o.b;
+                  dinv[row] = o.a; r[row] = ri; rh[row] = ri; p[row] = ri; v[row] = 0.0;
+                  acc[0] += ri * ri; acc[1] += bi * bi;
+                });
+  grid_sum<3>(bar, acc, a.red, phase, sh);
   if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
   const double tol = fmax(a.rtol * bn, a.atol);
-  if (!(rn == rn)) { leave(grid, a, 0, -1, rn, bn); return; }
-  if (rn <= tol) { leave(grid, a, 0, 1, rn, bn); return; }
-  double rho = acc[0], rho_old = 1.0, alpha = 1.0, omega = 1.0;
+  if (!(rn == rn)) { leave(bar, a, 0, -1, rn, bn); return; }
+  if (rn <= tol) { leave(bar, a, 0, 1, rn, bn); return; }
+  double rho = acc[0];
   double rhn = rn;  // ||rhat||
   int restarts = 0;
+  int np = 0;
+  stamp(a.prof, np);
   for (int it = 1; it <= a.maxit; ++it) {
-    // (rhat, r) ~ 0 or omega ~ 0: the recurrence has broken down (e.g. a residual supported on
-    // Dirichlet rows only is annihilated in one step, leaving rhat orthogonal to r).  Restart with
-    // rhat = r, the standard cure.
-    if (fabs(rho) <= 1e-14 * rhn * rn || omega == 0.0) {
-      if (++restarts > 50) { leave(grid, a, it - 1, -1, rn, bn); return; }
-      for (int i = gt; i < n; i += gs) { rh[i] = r[i]; p[i] = 0.0; v[i] = 0.0; }
-      rho = rn * rn; rhn = rn; rho_old = 1.0; alpha = 1.0; omega = 1.0;
-    }
-    const double beta = (rho / rho_old) * (alpha / omega);
-    for (int i = gt; i < n; i += gs) p[i] = r[i] + beta * (p[i] - omega * v[i]);
-    grid.sync();
+    // v = M^-1 A p, (rhat, v)
     double d1[1] = {0.0};
-    spmv_stream(A, p, prod, [&](int row, double ap) {
-      const double vi = dinv[row] * ap;
-      v[row] = vi;
-      d1[0] += rh[row] * vi;
-    });
-    grid_sum<1>(grid, d1, a.red, phase, sh);
-    if (d1[0] == 0.0) { leave(grid, a, it - 1, -1, rn, bn); return; }
-    alpha = rho / d1[0];
+    spmv_stream_c(A, rg, p, prod,
+                  [&](int row) { return Ops2{dinv[row], rh[row]}; },
+                  [&](int row, double ap, const Ops2& o) {
+                    const double vi = o.a * ap;
+                    v[row] = vi;
+                    d1[0] += o.b * vi;
+                  });
+    if (a.prof && it == 2 && (threadIdx.x & 31) == 0) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      const int gw_ = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+      if (gw_ < 8192) g_prof_warp[gw_] = tt;
+    }
+    stamp(a.prof, np);
+    grid_sum<1>(bar, d1, a.red, phase, sh);
+    stamp(a.prof, np);
+    if (d1[0] == 0.0) { leave(bar, a, it - 1, -1, rn, bn); return; }
+    const double alpha = rho / d1[0];
     double d2[1] = {0.0};
     for (int i = gt; i < n; i += gs) {
       const double si = r[i] - alpha * v[i];
       s[i] = si;
       d2[0] += si * si;
     }
-    grid_sum<1>(grid, d2, a.red, phase, sh);
-    if (sqrt(d2[0]) <= tol) {  // early exit on the half step (KSPBCGS does the same)
+    stamp(a.prof, np);
+    grid_sum<1>(bar, d2, a.red, phase, sh);
+    stamp(a.prof, np);
+    const double ss = d2[0];
+    if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
       for (int i = gt; i < n; i += gs) a.x[i] += alpha * p[i];
-      leave(grid, a, it, 1, sqrt(d2[0]), bn);
+      leave(bar, a, it, 1, sqrt(ss), bn);
       return;
     }
-    double d3[2] = {0.0, 0.0};
-    spmv_stream(A, s, prod, [&](int row, double as) {
-      const double ti = dinv[row] * as;
-      t[row] = ti;
-      d3[0] += ti * s[row];
-      d3[1] += ti * ti;
-    });
-    grid_sum<2>(grid, d3, a.red, phase, sh);
-    if (d3[1] == 0.0) { leave(grid, a, it, -1, sqrt(d2[0]), bn); return; }
-    omega = d3[0] / d3[1];
-    double d4[2] = {0.0, 0.0};
+    // t = M^-1 A s and the four scalars of the second half step
+    double d3[4] = {0.0, 0.0, 0.0, 0.0};
+    spmv_stream_c(A, rg, s, prod,
+                  [&](int row) { return Ops3{dinv[row], s[row], rh[row]}; },
+                  [&](int row, double as, const Ops3& o) {
+                    const double ti = o.a * as;
+                    t[row] = ti;
+                    d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
+                  });
+    stamp(a.prof, np);
+    grid_sum<4>(bar, d3, a.red, phase, sh);
+    stamp(a.prof, np);
+    if (d3[1] == 0.0) { leave(bar, a, it, -1, sqrt(ss), bn); return; }
+    const double omega = d3[0] / d3[1];
+    double rho_new = d3[2] - omega * d3[3];
+    double rn2 = ss - 2.0 * omega * d3[0] + omega * omega * d3[1];  // ||s - omega t||^2
+    rn = sqrt(fmax(rn2, 0.0));
+    if (!(rn2 == rn2) || rn > a.dtol * bn) { leave(bar, a, it, -1, rn, bn); return; }
+    // (rhat, r) ~ 0 or omega ~ 0: the recurrence has broken down (e.g. a residual supported on
+    // Dirichlet rows only is annihilated in one step, leaving rhat orthogonal to r).  Restart with
+    // rhat = r, the standard cure.
+    const bool restart = fabs(rho_new) <= 1e-14 * rhn * rn || omega == 0.0;
+    if (restart && ++restarts > 50) { leave(bar, a, it, -1, rn, bn); return; }
+    const double beta = restart ? 0.0 : (rho_new / rho) * (alpha / omega);
+    // x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v)   [restart: rhat = p = r]
+    const bool check = rn <= 2.0 * tol;  // confirm with a true norm
+    double d4[1] = {0.0};
     for (int i = gt; i < n; i += gs) {
-      a.x[i] += alpha * p[i] + omega * s[i];
+      const double pi = p[i];
+      a.x[i] += alpha * pi + omega * s[i];
       const double ri = s[i] - omega * t[i];
       r[i] = ri;
-      d4[0] += rh[i] * ri;
-      d4[1] += ri * ri;
+      p[i] = ri + beta * (pi - omega * v[i]);
+      if (restart) rh[i] = ri;
+      d4[0] += ri * ri;
     }
-    grid_sum<2>(grid, d4, a.red, phase, sh);
-    rho_old = rho;
-    rho = d4[0];
-    rn = sqrt(d4[1]);
-    if (!(rn == rn) || rn > a.dtol * bn) { leave(grid, a, it, -1, rn, bn); return; }
-    if (rn <= tol) { leave(grid, a, it, 1, rn, bn); return; }
+    stamp(a.prof, np);
+    if (check || restart) {
+      grid_sum<1>(bar, d4, a.red, phase, sh);
+      rn = sqrt(d4[0]);
+      if (rn <= tol) { leave(bar, a, it, 1, rn, bn); return; }
+      if (restart) { rho_new = d4[0]; rhn = rn; }
+    } else {
+      bar.sync();
+    }
+    stamp(a.prof, np);
+    rho = rho_new;
   }
-  leave(grid, a, a.maxit, 0, rn, bn);
+  leave(bar, a, a.maxit, 0, rn, bn);
 }
 
 // ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
 // u = M^-1 r, w = A u, p = u + beta p, s = w + beta s (= A p).  One SpMV and ONE fused reduction
 // (gamma = (r,u), delta = (w,u), ||u||^2) per iteration: two grid barriers instead of three.
 // Monitored norm ||M^-1 r||_2 (PETSc default for KSPCG).
-__global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KArgs a) {
-  cg::grid_group grid = cg::this_grid();
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_constant__ KArgs a) {
   __shared__ double sh[4 * 33];
-  __shared__ double prod[SPMV_SMEM_DOUBLES];
+  __shared__ int sh_i[64];
+  extern __shared__ __align__(16) double prod[];
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -194,28 +254,34 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
   double* s = a.w + 4 * (size_t)n;
   double* dinv = a.w + 5 * (size_t)n;
   int phase = 0;
+  GridBar bar;
+  bar.init(a.bar);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  if (A.rs != nullptr) acc[3] = (double)compact_zeros(A);
-  spmv_stream(A, a.x, prod, [&](int row, double ax) {
-    const double di = row_diag_inv(A, row, a.pc);
-    const double ri = a.b[row] - ax, ui = di * ri, bi = di * a.b[row];
-    dinv[row] = di; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
-    acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
-  });
-  grid_sum<4>(grid, acc, a.red, phase, sh);
+  acc[3] = (double)compact_zeros(A);
+  bar.sync();
+  const BlockRange rg = balance_partition(A, bar, sh_i);
+  spmv_stream_c(A, rg, a.x, prod,
+                [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
+                [&](int row, double ax, const Ops2& o) {
+                  const double ri = o.b - ax, ui = o.a * ri, bi = o.a * o.b;
+                  dinv[row] = o.a; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
+                  acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
+                });
+  grid_sum<4>(bar, acc, a.red, phase, sh);
   if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }
   double gamma = acc[0], un = sqrt(acc[1]);
   const double bn = sqrt(acc[2]);
   const double tol = fmax(a.rtol * bn, a.atol);
-  if (!(un == un)) { leave(grid, a, 0, -1, un, bn); return; }
-  if (un <= tol) { leave(grid, a, 0, 1, un, bn); return; }
+  if (!(un == un)) { leave(bar, a, 0, -1, un, bn); return; }
+  if (un <= tol) { leave(bar, a, 0, 1, un, bn); return; }
   double d0[1] = {0.0};
-  spmv_stream(A, u, prod, [&](int row, double au) {
-    w[row] = au;
-    d0[0] += au * u[row];
-  });
-  grid_sum<1>(grid, d0, a.red, phase, sh);
-  if (!(d0[0] > 0.0)) { leave(grid, a, 0, -1, un, bn); return; }
+  spmv_stream_c(A, rg, u, prod, [&](int row) { return Ops2{u[row], 0.0}; },
+                [&](int row, double au, const Ops2& o) {
+                  w[row] = au;
+                  d0[0] += au * o.a;
+                });
+  grid_sum<1>(bar, d0, a.red, phase, sh);
+  if (!(d0[0] > 0.0)) { leave(bar, a, 0, -1, un, bn); return; }
   double alpha = gamma / d0[0], beta = 0.0;
   for (int it = 1; it <= a.maxit; ++it) {
     double d[3] = {0.0, 0.0, 0.0};
@@ -231,22 +297,23 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_cg(const __grid_constant__ KA
       d[0] += ri * ui;
       d[1] += ui * ui;
     }
-    grid.sync();
-    spmv_stream(A, u, prod, [&](int row, double au) {
-      w[row] = au;
-      d[2] += au * u[row];
-    });
-    grid_sum<3>(grid, d, a.red, phase, sh);
+    bar.sync();
+    spmv_stream_c(A, rg, u, prod, [&](int row) { return Ops2{u[row], 0.0}; },
+                  [&](int row, double au, const Ops2& o) {
+                    w[row] = au;
+                    d[2] += au * o.a;
+                  });
+    grid_sum<3>(bar, d, a.red, phase, sh);
     un = sqrt(d[1]);
-    if (!(un == un) || un > a.dtol * bn) { leave(grid, a, it, -1, un, bn); return; }
-    if (un <= tol) { leave(grid, a, it, 1, un, bn); return; }
+    if (!(un == un) || un > a.dtol * bn) { leave(bar, a, it, -1, un, bn); return; }
+    if (un <= tol) { leave(bar, a, it, 1, un, bn); return; }
     beta = d[0] / gamma;
     const double denom = d[2] - beta * d[0] / alpha;
-    if (!(denom > 0.0)) { leave(grid, a, it, -1, un, bn); return; }  // not SPD / breakdown
+    if (!(denom > 0.0)) { leave(bar, a, it, -1, un, bn); return; }  // not SPD / breakdown
     alpha = d[0] / denom;
     gamma = d[0];
   }
-  leave(grid, a, a.maxit, 0, un, bn);
+  leave(bar, a, a.maxit, 0, un, bn);
 }
 
 // ---- pipelined CG (Ghysels-Vanroose), matrix resident in shared memory -----------------------------------
@@ -267,7 +334,8 @@ __host__ __device__ constexpr size_t pcg_smem_bytes(int R) {
 
 template <int R>
 __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant__ KArgs a) {
-  cg::grid_group grid = cg::this_grid();
+  GridBar bar;
+  bar.init(a.bar);
   __shared__ double sh[3 * 33];
   extern __shared__ __align__(16) unsigned char dyn[];
   const CsrView& A = a.A;
@@ -370,7 +438,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       acc1[0] += bi * bi;
     }
   }
-  grid_sum<1>(grid, acc1, a.red, phase, sh);
+  grid_sum<1>(bar, acc1, a.red, phase, sh);
   const double bn = sqrt(acc1[0]);
   const double tol = fmax(a.rtol * bn, a.atol);
   // w = A u, m = M^-1 w
@@ -386,7 +454,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       d[0] += r[row] * ui; d[1] += y[rr] * ui; d[2] += ui * ui;
     }
   }
-  grid_sum<3>(grid, d, a.red, phase, sh);
+  grid_sum<3>(bar, d, a.red, phase, sh);
   double gamma_old = 1.0, alpha = 1.0, un = sqrt(d[2]);
   for (int it = 0; it <= a.maxit; ++it) {
     un = sqrt(d[2]);
@@ -437,7 +505,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         d[0] += ri * ui; d[1] += wi * ui; d[2] += ui * ui;
       }
     }
-    grid_sum<3>(grid, d, a.red, phase, sh);
+    grid_sum<3>(bar, d, a.red, phase, sh);
   }
   finish(a, a.maxit, 0, un, bn);
 }
@@ -467,8 +535,12 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
-  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->crs, P->cre, P->cblkend, P->ccol, P->cval,
-                 p.nelim > 0 ? p.elim : nullptr, p.elim_rows, p.nelim};
+  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->cdesc, P->cre, P->ccol, P->cval,
+                 p.nelim > 0 ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart};
+  ka.bar = P->bar;
+  static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
+  ka.prof = prof_env;
+  FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
   ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
@@ -483,16 +555,59 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
       return launch_pcg_res<3>(P, ka, grid, st);
     }
   }
-  void* fn = method == FX_KSP_CG ? (void*)k_cg : (void*)k_bicgstab;
+  // big CTAs (1024 threads, one per SM) keep the grid barrier cheap: its cost grows with the number of
+  // arriving CTAs, and every iteration crosses four of them
+  static const int threads_env = getenv("FX_KRYLOV_THREADS") ? atoi(getenv("FX_KRYLOV_THREADS")) : 1024;
+  const int threads = threads_env == 256 ? 256 : 1024;
+  void* fn = method == FX_KSP_CG ? (threads == 256 ? (void*)k_cg<256> : (void*)k_cg<1024>)
+                                 : (threads == 256 ? (void*)k_bicgstab<256> : (void*)k_bicgstab<1024>);
+  const size_t smem = sizeof(double) * (threads / 32) * SPMV_NNZB;
+  static bool attr_done[4] = {false, false, false, false};
+  const int ai = (method == FX_KSP_CG ? 0 : 1) + (threads == 256 ? 0 : 2);
+  if (!attr_done[ai]) {
+    FX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[ai] = true;
+  }
   int per_sm = 0;
-  FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LA_THREADS, 0));
+  FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
   if (per_sm < 1) return set_error(FX_ERR_CUDA, "Krylov kernel does not fit on an SM");
-  // one CTA per 8 row blocks up to the co-resident limit; small systems get a small grid (cheap barriers)
-  int grid = max(1, min(min(per_sm, 8) * P->num_sms, (p.nrowblk + LA_WARPS - 1) / LA_WARPS));
+  // one warp per 1-2 row blocks up to the co-resident limit; small systems get a small grid (cheap barriers)
+  const int wpb = threads / 32;
+  int grid = max(1, min(min(per_sm, 1024 / threads) * P->num_sms, (p.nrowblk + wpb - 1) / wpb));
   grid = min(grid, MAX_GRID);
   void* args[] = {(void*)&ka};
-  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LA_THREADS), args, 0, st));
+  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st));
   count_launch(1);
+  if (prof_env && method == FX_KSP_BICGSTAB && p.n > 100000) {  // debugging aid: per-phase microseconds of iterations 2..4
+    static unsigned long long h[1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+    fprintf(stderr, "[krylov prof] space %d grid %d:", space, grid);
+    for (int it = 1; it < 4; ++it) {
+      fprintf(stderr, "  |");
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %.1f", (double)(h[1 + 8 * it + k] - h[8 * it + k]) * 1e-3);
+    }
+    fprintf(stderr, "\n");
+    static unsigned long long hw[8192];
+    cudaMemcpyFromSymbol(hw, g_prof_warp, sizeof(hw));
+    const int nwarp = grid * wpb;
+    // SpMV1 of iteration 2 started at h[8] (block 0's view); per-warp finish offsets
+    std::vector<double> dt;
+    for (int i = 0; i < nwarp && i < 8192; ++i) dt.push_back((double)(long long)(hw[i] - h[8]) * 1e-3);
+    std::vector<double> srt(dt);
+    std::sort(srt.begin(), srt.end());
+    fprintf(stderr, "[krylov prof] warp finish (us after start) min %.1f p10 %.1f med %.1f p90 %.1f max %.1f\n", srt[0],
+            srt[nwarp / 10], srt[nwarp / 2], srt[nwarp * 9 / 10], srt[nwarp - 1]);
+    // per-CTA max and spread
+    double cmax_min = 1e9, cmax_max = 0, spread = 0;
+    for (int c = 0; c < grid; ++c) {
+      double mx = 0, mn = 1e9;
+      for (int w2 = 0; w2 < wpb; ++w2) { mx = std::max(mx, dt[c * wpb + w2]); mn = std::min(mn, dt[c * wpb + w2]); }
+      cmax_min = std::min(cmax_min, mx); cmax_max = std::max(cmax_max, mx); spread += (mx - mn) / grid;
+    }
+    fprintf(stderr, "[krylov prof] per-CTA slowest warp: fastest CTA %.1f slowest CTA %.1f; mean in-CTA spread %.1f\n", cmax_min,
+            cmax_max, spread);
+  }
   return FX_OK;
 }
 

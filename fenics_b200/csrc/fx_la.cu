@@ -9,7 +9,7 @@ namespace fx {
 __global__ void __launch_bounds__(LA_THREADS, 4) k_spmv(const __grid_constant__ CsrView A,
                                                         const double* __restrict__ x, double* __restrict__ y) {
   __shared__ double prod[SPMV_SMEM_DOUBLES];
-  spmv_stream(A, x, prod, [&](int row, double s) { y[row] = s; });
+  spmv_stream(A, round_robin_range(A), x, prod, [&](int row, double s) { y[row] = s; });
 }
 
 // CSR-vector variant kept for A/B measurements (tools/spmv_bench.py): TPR lanes per row, RU rows in
@@ -62,7 +62,7 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
                     cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   const int nb = P->num_sms * 8;
   switch (variant) {
     case 0: return la_spmv(P, space, val, x, y, st);
@@ -81,7 +81,7 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
 int la_spmv(fx_plan* P, int space, const double* val, const double* x, double* y, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   const int nb = max(1, min((p.nrowblk + LA_WARPS - 1) / LA_WARPS, P->num_sms * 8));
   k_spmv<<<nb, LA_THREADS, 0, st>>>(A, x, y);
   count_launch(1);

@@ -80,10 +80,9 @@ struct CsrView {
   const double* val;
   const int* rowblk;
   int nrowblk;
-  // compacted copy (structural zeros of the DOLFIN cell-block pattern dropped); null = not compacted
-  int* rs;      // [n] first entry of row
-  int* re;      // [n] one past the last entry of row
-  int* blkend;  // [nrowblk] one past the last entry of the row block
+  // compacted copy (structural zeros of the DOLFIN cell-block pattern dropped); desc == null: not compacted
+  int4* desc;   // [nrowblk] {first row, rows, first entry, one past the last entry} of the row block
+  int* re;      // [n] one past the last entry of row (rows of a block are stored back to back)
   int* col2;
   double* val2;
   // block-triangular elimination (null = off): rows with elim[row] != 0 are left out of the Krylov
@@ -91,20 +90,55 @@ struct CsrView {
   const unsigned char* elim;
   const int* elim_rows;
   int nelim;
+  // cost-balanced contiguous partition of the row blocks over the warps (balance_partition)
+  int* blkprefix;  // [nrowblk + 1] exclusive prefix of the per-block cost
+  int* scanpart;   // [gridDim] scratch of the scan
 };
+
+// Grid barrier for cooperative (co-resident) launches.  Unlike cooperative_groups' grid.sync(), whose
+// waiting thread polls with ld.acquire -- every poll invalidates the SM's whole L1 (CCTL.IVALL), which
+// evicts the x-gather lines of the CTAs still working on that SM -- the wait here polls with relaxed
+// loads and acquires once.  Monotonic counter, zeroed by the host before every launch.
+struct GridBar {
+  unsigned* ctr;
+  unsigned target;
+  __device__ __forceinline__ void init(unsigned* c) { ctr = c; target = 0; }
+  __device__ __forceinline__ void sync() {
+    target += gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();  // release: everything this CTA wrote (bar.sync above orders the other threads' stores)
+      atomicAdd(ctr, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      } while ((int)(v - target) < 0);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    }
+    __syncthreads();
+  }
+};
+
+// The warp processes row blocks k0, k0+kstep, ... < k1.
+struct BlockRange {
+  int k0, k1, kstep;
+};
+__device__ __forceinline__ BlockRange round_robin_range(const CsrView& A) {
+  const int wpb = blockDim.x >> 5;
+  return BlockRange{(int)(blockIdx.x * wpb + (threadIdx.x >> 5)), A.nrowblk, (int)(gridDim.x * wpb)};
+}
 
 // Drop exactly-zero entries, row block by row block, into (col2, val2) at the block's original offset.
 // DOLFIN's pattern stores every (test dof, trial dof) pair of every cell whether or not the form
 // couples them: 20-60 % of the stored values of the W and Zc matrices are exact
-// zeros, which a Krylov solve would otherwise stream from HBM twice per iteration.  The warp that
-// compacts a block is the warp that later streams it, so no grid barrier is needed in between.
+// zeros, which a Krylov solve would otherwise stream from HBM twice per iteration.
 // With elimination on, eliminated rows become empty in the copy (never streamed); the return value
 // counts non-zero couplings A[active, eliminated] seen by this thread (must total 0).
 __device__ __forceinline__ int compact_zeros(const CsrView& A) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nw = gridDim.x * LA_WARPS;
+  const int lane = threadIdx.x & 31;
+  const BlockRange rg = round_robin_range(A);
   int bad = 0;
-  for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
+  for (int k = rg.k0; k < rg.k1; k += rg.kstep) {
     const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
     const int j0 = A.rowptr[r0];
     const int row = r0 + lane;
@@ -133,17 +167,88 @@ __device__ __forceinline__ int compact_zeros(const CsrView& A) {
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (act) {
       int dst = j0 + incl - cnt;
-      A.rs[row] = dst;
       A.re[row] = dst + cnt;
       for (int j = b; j < e; ++j) {
         const double v = A.val[j];
         if (v != 0.0) { A.val2[dst] = v; A.col2[dst] = A.col[j]; ++dst; }
       }
     }
-    if (lane == 0) A.blkend[k] = j0 + total;
+    if (lane == 0) A.desc[k] = make_int4(r0, r1 - r0, j0, j0 + total);
     __syncwarp();
   }
   return bad;
+}
+
+// A row block costs a warp its entries plus a fixed latency chain (descriptor -> values/columns -> x
+// gather -> row sums -> epilogue), worth about this many entries of streaming.
+constexpr int BLOCK_OVERHEAD_NNZ = 192;
+
+// After compact_zeros + a grid barrier: split the row blocks into one contiguous range per warp of
+// (nearly) equal cost and return this warp's range.  Round-robin dealing leaves some warps one block
+// ahead of others (5 vs 6 blocks at n=192: every barrier waits ~20 % for the stragglers).
+// Distributed scan: each CTA sums its chunk of blocks, a barrier, offsets from the CTAs before it, a
+// barrier, then two binary searches per warp.  sh_i: 64 ints of shared memory.
+__device__ __forceinline__ BlockRange balance_partition(const CsrView& A, GridBar& bar, int* sh_i) {
+  const int nb = A.nrowblk, G = gridDim.x, wpb = blockDim.x >> 5;
+  const int L = (nb + G - 1) / G;
+  const int c0 = min(nb, (int)blockIdx.x * L), c1 = min(nb, c0 + L);
+  // chunk-local inclusive scan by one warp (chunks are a few dozen blocks)
+  if (threadIdx.x < 32) {
+    int run = 0;
+    for (int base = c0; base < c1; base += 32) {
+      const int k = base + threadIdx.x;
+      int v = 0;
+      if (k < c1) {
+        const int4 d = __ldcg(A.desc + k);
+        v = d.w - d.z + BLOCK_OVERHEAD_NNZ;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)threadIdx.x >= o) v += t;
+      }
+      if (k < c1) A.blkprefix[k + 1] = run + v;  // inclusive, chunk-local
+      run += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (threadIdx.x == 0) A.scanpart[blockIdx.x] = run;
+  }
+  bar.sync();
+  // offset of my chunk and the grand total
+  int off = 0, tot = 0;
+  for (int j = threadIdx.x; j < G; j += blockDim.x) {
+    const int v = __ldcg(A.scanpart + j);
+    tot += v;
+    if (j < (int)blockIdx.x) off += v;
+  }
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_down_sync(0xffffffffu, off, o);
+      tot += __shfl_down_sync(0xffffffffu, tot, o);
+    }
+    __syncthreads();
+    if (lane == 0) { sh_i[w] = off; sh_i[32 + w] = tot; }
+    __syncthreads();
+    off = 0; tot = 0;
+    for (int i = 0; i < wpb; ++i) { off += sh_i[i]; tot += sh_i[32 + i]; }
+  }
+  for (int k = c0 + threadIdx.x; k < c1; k += blockDim.x) A.blkprefix[k + 1] = __ldcg(A.blkprefix + k + 1) + off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.blkprefix[0] = 0;
+  bar.sync();
+  // warp w owns the blocks whose prefix lies in [w*tot/nw, (w+1)*tot/nw)
+  const long long nw = (long long)G * wpb, w = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  auto lower = [&](long long target) {
+    int lo = 0, hi = nb;  // smallest k in [0, nb] with prefix[k] >= target
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((long long)__ldcg(A.blkprefix + mid) >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  const int k0 = (w == 0) ? 0 : lower((w * tot) / nw);
+  const int k1 = (w == nw - 1) ? nb : lower(((w + 1) * tot) / nw);
+  return BlockRange{k0, k1, 1};
 }
 
 // x[row] = (b[row] - sum_{j != row} A[row,j] x[j]) / A[row,row] for the eliminated rows, 16 lanes per row
@@ -182,17 +287,64 @@ __device__ __forceinline__ int back_substitute(const CsrView& A, double* x, cons
 // slice and runs the fused epilogue epi(row, (A x)[row]).  Only __syncwarp() -- warps of a CTA drift
 // apart, so streaming and reducing overlap on the SM.
 // `x` may have been written earlier in the same (cooperative) kernel: plain coherent loads.
+// This is the plain-CSR variant (stand-alone SpMV); the Krylov kernels use spmv_stream_c below.
 template <class Epi>
-__device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, double* smem, Epi&& epi) {
+__device__ __forceinline__ void spmv_stream(const CsrView& A, const BlockRange rg, const double* x, double* smem,
+                                            Epi&& epi) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* prod = smem + wib * SPMV_NNZB;
-  const int nw = gridDim.x * LA_WARPS;
-  const bool compact = A.rs != nullptr;
-  const int* col = compact ? A.col2 : A.col;
-  const double* val = compact ? A.val2 : A.val;
-  for (int k = blockIdx.x * LA_WARPS + wib; k < A.nrowblk; k += nw) {
+  for (int k = rg.k0; k < rg.k1; k += rg.kstep) {
     const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
-    const int j0 = A.rowptr[r0], j1 = compact ? A.blkend[k] : A.rowptr[r1];
+    const int j0 = A.rowptr[r0], j1 = A.rowptr[r1];
+    for (int jb = j0; jb < j1; jb += 256) {
+      int c[8];
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u * 32 + lane;
+        c[u] = (j < j1) ? ld_stream(A.col + j) : -1;
+        v[u] = (j < j1) ? ld_stream(A.val + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c[u] >= 0) prod[jb - j0 + u * 32 + lane] = v[u] * x[c[u]];
+    }
+    __syncwarp();
+    if (lane < r1 - r0) {
+      const int row = r0 + lane;
+      const int s0 = A.rowptr[row] - j0, s1 = A.rowptr[row + 1] - j0;
+      double s = 0.0;
+      for (int j = s0; j < s1; ++j) s += prod[j];
+      epi(row, s);
+    }
+    __syncwarp();
+  }
+}
+
+// Compacted variant inside the persistent Krylov kernels.  A row block costs a chain of dependent memory
+// round trips, and with ~5 blocks per warp and SpMV that chain -- not bandwidth -- sets the pace, so it is
+// kept short: ONE 16-byte descriptor per block (prefetched a block ahead), and everything that depends only
+// on the row -- its end offset and the epilogue's operands, fetched by pre(row) -- is requested BEFORE the
+// value/column stream so all of it is in flight together; row starts come from the neighbour lane.
+//   pre(row)            -> Ops (plain struct of the vector entries the epilogue needs)
+//   post(row, Ax, ops)  epilogue
+template <class Pre, class Post>
+__device__ __forceinline__ void spmv_stream_c(const CsrView& A, const BlockRange rg, const double* x, double* smem,
+                                              Pre&& pre, Post&& post) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* prod = smem + wib * SPMV_NNZB;
+  const int* col = A.col2;
+  const double* val = A.val2;
+  int4 d = (rg.k0 < rg.k1) ? __ldcg(A.desc + rg.k0) : make_int4(0, 0, 0, 0);
+  for (int k = rg.k0; k < rg.k1; k += rg.kstep) {
+    const int kn = k + rg.kstep;
+    const int4 dn = (kn < rg.k1) ? __ldcg(A.desc + kn) : make_int4(0, 0, 0, 0);
+    const int r0 = d.x, nr = d.y, j0 = d.z, j1 = d.w;
+    const int row = r0 + lane;
+    const bool act = lane < nr;
+    const int e1 = act ? __ldcg(A.re + row) : j0;
+    decltype(pre(0)) ops{};
+    if (act) ops = pre(row);
     for (int jb = j0; jb < j1; jb += 256) {
       int c[8];
       double v[8];
@@ -207,15 +359,16 @@ __device__ __forceinline__ void spmv_stream(const CsrView& A, const double* x, d
         if (c[u] >= 0) prod[jb - j0 + u * 32 + lane] = v[u] * x[c[u]];
     }
     __syncwarp();
-    if (lane < r1 - r0) {
-      const int row = r0 + lane;
-      const int s0 = (compact ? A.rs[row] : A.rowptr[row]) - j0;
-      const int s1 = (compact ? A.re[row] : A.rowptr[row + 1]) - j0;
+    const int s1 = e1 - j0;
+    int s0 = __shfl_up_sync(0xffffffffu, s1, 1);
+    if (lane == 0) s0 = 0;
+    if (act) {
       double s = 0.0;
       for (int j = s0; j < s1; ++j) s += prod[j];
-      epi(row, s);
+      post(row, s, ops);
     }
     __syncwarp();
+    d = dn;
   }
 }
 

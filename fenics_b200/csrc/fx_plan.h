@@ -65,7 +65,10 @@ struct fx_plan {
   fx_solve_info* info = nullptr;  // device, FX_NTICKETS result slots
   // zero-compacted matrix copy used inside the Krylov kernels (sized for the largest pattern)
   double* cval = nullptr;
-  int *ccol = nullptr, *crs = nullptr, *cre = nullptr, *cblkend = nullptr;
+  int *ccol = nullptr, *cre = nullptr;
+  int4* cdesc = nullptr;  // per-row-block descriptors of the compacted copy
+  int *cprefix = nullptr, *scanpart = nullptr;  // nnz-balanced partition of the row blocks (balance_partition)
+  unsigned* bar = nullptr;                      // grid-barrier counter of the persistent Krylov kernels
 
   fx::MeshView view() const {
     fx::MeshView m;
