@@ -59,6 +59,7 @@ def _load():
         "fx_krylov_solve": (i, [vp, i, vp, vp, vp, i, i, d, d, i, C.POINTER(SolveInfo), vp]),
         "fx_krylov_solve_async": (i, [vp, i, vp, vp, vp, i, i, d, d, i, i, vp]),
         "fx_solve_results": (i, [vp, i, i, C.POINTER(SolveInfo), vp]),
+        "fx_solve_results_async": (i, [vp, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -337,6 +337,14 @@ int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void
   return FX_OK;
 }
 
+int fx_solve_results_async(fx_plan* P, int first, int count, fx_solve_info* info, void* stream) {
+  if (!P || first < 0 || count < 1 || first + count > FX_NTICKETS || !info)
+    return set_error(FX_ERR_ARG, "fx_solve_results_async: bad argument");
+  FX_CUDA(cudaMemcpyAsync(info, P->info + first, sizeof(fx_solve_info) * count, cudaMemcpyDeviceToHost,
+                          (cudaStream_t)stream));
+  return FX_OK;
+}
+
 int fx_krylov_solve_async(fx_plan* P, int space, const double* val, double* x, const double* b, int method,
                           int pc, double rtol, double atol, int maxit, int ticket, void* stream) {
   if (!P || space < 0 || space >= S_N || !val || !x || !b || maxit < 0 || ticket < 0 || ticket >= FX_NTICKETS)

@@ -170,9 +170,16 @@ class DirichletBC:
         if self._rows is None:
             self._rows = torch.as_tensor(self.dofs.astype(np.int32), device=dev)
             self._g = torch.empty(n, dtype=torch.float64, device=dev)
-            self._gpinned = torch.empty(n, dtype=torch.float64).pin_memory()
-        self._gpinned.numpy()[:] = self.values()
-        self._g.copy_(self._gpinned, non_blocking=True)
+            # page-locked staging ring: the host may run ahead of the device (pipelined time loops), so a
+            # staging buffer is rewritten only after the copy that last read it has completed
+            self._gpinned = [(torch.empty(n, dtype=torch.float64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._gi = 0
+        stage, ev = self._gpinned[self._gi]
+        self._gi = (self._gi + 1) % len(self._gpinned)
+        ev.synchronize()  # no-op until the ring wraps around
+        stage.numpy()[:] = self.values()
+        self._g.copy_(stage, non_blocking=True)
+        ev.record()
         check(lib.fx_apply_bc(plan.h, abi.SPACE_ID[self.root.name], la._ptr(A.val) if A is not None else None,
                               la._ptr(b.t) if b is not None else None, la._ptr(self._rows), la._ptr(self._g), n,
                               la._stream()))

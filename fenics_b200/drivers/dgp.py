@@ -113,7 +113,7 @@ class CompDGP(_LDC):
         vals = self._finish_step()
         t_rec = self.t
         self.t += self.p["dt"]                          # :591
-        return dict(t=t_rec, E_k=float(vals[0]), E_e=float(vals[1]), Nus=float(vals[2]))
+        return self._result(t_rec, vals, dict(E_k=0, E_e=1, Nus=2))
 
     def fields(self):
         g = lambda fn: fn.vector().get_local()  # noqa: E731

@@ -125,8 +125,7 @@ class FenepmpJBP(_LDC):
         vals = self._finish_step()
         t_rec = self.t
         self.t += self.p["dt"]                          # :690
-        return dict(t=t_rec, E_k=float(vals[0]), E_e=float(vals[1]), torque=float(vals[2]), F_x=float(vals[3]),
-                    F_y=float(vals[4]))
+        return self._result(t_rec, vals, dict(E_k=0, E_e=1, torque=2, F_x=3, F_y=4))
 
     def fields(self):
         g = lambda fn: fn.vector().get_local()  # noqa: E731

@@ -15,7 +15,7 @@ import torch
 
 from .. import _abi as abi
 from .. import la
-from .._lib import check, lib
+from .._lib import SolveInfo, check, lib
 from ..dolfin_api import (ConsistentProjection, DirichletBC, Function, Problem, assemble,
                           assemble_scalar_async, project)
 from ..la import Matrix, Plan, Vector
@@ -37,11 +37,45 @@ def lid_bcs(W, L=1.0):
     return [noslip, drive1], tt
 
 
+class PendingStep(dict):
+    """Result of a pipelined step: the values are on their way to page-locked host memory.  Reading any
+    item waits for that step (not for later ones), raises like dolfin if one of its solves failed, and
+    fills the dict."""
+
+    def __init__(self, drv, slot, static):
+        super().__init__(static)
+        self._drv, self._slot = drv, slot
+
+    def resolve(self):
+        if self._drv is not None:
+            drv, self._drv = self._drv, None
+            try:
+                vals = drv._resolve_slot(self._slot)
+            except Exception:
+                self._drv = drv
+                raise
+            super().update({k: float(vals[i]) for k, i in self._slot["names"].items()})
+        return self
+
+    def __getitem__(self, k):
+        if not dict.__contains__(self, k):
+            self.resolve()
+        return dict.__getitem__(self, k)
+
+    def keys(self):
+        return self.resolve() and dict.keys(self)
+
+    def items(self):
+        return self.resolve() and dict.items(self)
+
+
 class _LDC:
     solver = ("bicgstab", "default")   # what the reference passes to solve()
     pressure_method = "bicgstab"       # reference; "cg" is the north_star upgrade (A5 is symmetric)
     STATE_FIELDS = ()                  # fields carried from step to step (host<->device in e2e mode)
     eliminate_devss = True             # W solves: iterate on the velocity rows, back-substitute the DG0 DEVSS rows
+    pipeline = False                   # with check=False: step() returns a PendingStep instead of syncing, so the
+                                       # host enqueues step k+1 while step k runs (solver failures raise on access)
 
     def _setup(self, mesh, dofmaps, device):
         self.mesh = mesh
@@ -143,17 +177,66 @@ class _LDC:
     def _begin_step(self):
         self.last_info, self.solve_labels, self._ticket = [], [], 0
 
-    def _finish_step(self):
-        """one host sync per step: energies (+ solver outcomes when running asynchronously)."""
+    def _check_infos(self, infos, labels):
+        bad = [i for i, s in enumerate(infos) if s.converged != 1]
+        if bad:
+            s = infos[bad[0]]
+            raise RuntimeError("*** Error: Unable to solve linear system: solve %s of the step: %d iterations, "
+                               "residual %.3e, status %d" % (labels[bad[0]], s.iterations, s.residual, s.converged))
+
+    def _resolve_slot(self, slot):
+        if slot["pending"]:
+            slot["event"].synchronize()
+            slot["pending"] = False
+            n = slot["count"]
+            infos = list((SolveInfo * n).from_buffer_copy(slot["info"].numpy()[:n * C.sizeof(SolveInfo)].tobytes()))
+            slot["infos"], slot["vals"] = infos, slot["scal"].numpy().copy()
+            self.last_info, self.solve_labels = infos, slot["labels"]
+            self._check_infos(infos, slot["labels"])
+        return slot["vals"]
+
+    def sync(self):
+        """wait for every pipelined step still in flight (raises if one of its solves failed)."""
+        for slot in getattr(self, "_slots", []):
+            if slot.get("owner") is not None:
+                slot.pop("owner").resolve()
+            self._resolve_slot(slot)
+
+    def _result(self, t_rec, vals, names):
+        """names: result key -> index into the step's scalar buffer."""
+        if isinstance(vals, dict):  # pipelined: a ring slot
+            vals["names"] = names
+            vals["owner"] = PendingStep(self, vals, dict(t=t_rec))
+            return vals["owner"]
+        out = dict(t=t_rec)
+        out.update({k: float(vals[i]) for k, i in names.items()})
+        return out
+
+    def _finish_step(self, allow_pipeline=True):
+        """one host sync per step: energies (+ solver outcomes when running asynchronously); in pipelined
+        mode no sync at all: the copies are enqueued behind the step and an event marks their arrival."""
+        if self.pipeline and not self.check and allow_pipeline:
+            if not hasattr(self, "_slots"):
+                mk = lambda: dict(scal=torch.zeros(8, dtype=torch.float64).pin_memory(),  # noqa: E731
+                                  info=torch.zeros(64 * C.sizeof(SolveInfo), dtype=torch.uint8).pin_memory(),
+                                  event=torch.cuda.Event(), pending=False, vals=None)
+                self._slots, self._slot_i = [mk(), mk()], 0
+            slot = self._slots[self._slot_i]
+            self._slot_i ^= 1
+            if slot.get("owner") is not None:  # two steps old: long finished; fill it in before its buffers are reused
+                slot.pop("owner").resolve()
+            self._resolve_slot(slot)
+            slot["scal"].copy_(self.scal, non_blocking=True)
+            if self._ticket:
+                check(lib.fx_solve_results_async(self.plan.h, 0, self._ticket, C.c_void_p(slot["info"].data_ptr()),
+                                                 la._stream()))
+            slot["event"].record()
+            slot.update(pending=True, count=self._ticket, labels=list(self.solve_labels))
+            return slot
         if not self.check:
             infos = la.solve_results(self.plan, 0, self._ticket)
             self.last_info = infos
-            bad = [i for i, s in enumerate(infos) if s.converged != 1]
-            if bad:
-                s = infos[bad[0]]
-                raise RuntimeError("*** Error: Unable to solve linear system: solve %s of the step: %d iterations, "
-                                   "residual %.3e, status %d" % (self.solve_labels[bad[0]], s.iterations, s.residual,
-                                                                 s.converged))
+            self._check_infos(infos, self.solve_labels)
         self._scal_host.copy_(self.scal, non_blocking=False)
         return self._scal_host.numpy()
 
@@ -198,7 +281,7 @@ class IncompLDC(_LDC):
             ev = self.err.vector()
             check(lib.fx_norm_dev(self.plan.h, ev.size(), la._ptr(ev.t), 0, C.c_void_p(self.scal.data_ptr() + 16),
                                   la._stream()))  # norm(err.vector(),'l2') :435
-        vals = self._finish_step()
+        vals = self._finish_step(allow_pipeline=False)  # the divergence test below needs this step's error norm
         self.err_array.append(float(vals[2]))
         diverged = False
         if self.t > 0.5 and len(self.err_array) > 1 and self.err_array[-2] != 0.0:
@@ -252,7 +335,7 @@ class CompLDC(_LDC):
         self.p0.assign(self.p1)
         self.tau0_vec.assign(self.tau1_vec)
         self.t += self.p["dt"]
-        return dict(t=t_rec, E_k=float(vals[0]), E_e=float(vals[1]))
+        return self._result(t_rec, vals, dict(E_k=0, E_e=1))
 
     def fields(self):
         g = lambda f: f.vector().get_local()  # noqa: E731

@@ -235,6 +235,9 @@ int fx_krylov_solve_async(fx_plan* plan, int space, const double* val_dev, doubl
                           int maxit, int ticket, void* stream);
 /* waits for `stream`, copies result slots [first, first+count) to info_host */
 int fx_solve_results(fx_plan* plan, int first, int count, fx_solve_info* info_host, void* stream);
+/* same copy, enqueued on `stream` without waiting (info_host should be page-locked); the caller
+ * synchronises with an event before reading -- lets a time loop enqueue step k+1 while step k runs */
+int fx_solve_results_async(fx_plan* plan, int first, int count, fx_solve_info* info_host, void* stream);
 
 #ifdef __cplusplus
 }

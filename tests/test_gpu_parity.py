@@ -245,6 +245,29 @@ def test_async_step_equals_sync_step():
     assert len(b.last_info) == 8 and all(i.converged == 1 for i in b.last_info)
 
 
+def test_pipelined_steps_match_synchronous_steps():
+    """pipeline=True: step() returns before the GPU finishes; values arrive with the step's event."""
+    _, a = _pair(2, n=8)
+    _, b = _pair(2, n=8)
+    b.check, b.pipeline = False, True
+    for d in (a, b):
+        d.t = 0.45
+        d.solve_rtol = 1e-12
+    ra = [a.step() for _ in range(4)]
+    rb = [b.step() for _ in range(4)]
+    assert all(type(r).__name__ == "PendingStep" for r in rb)
+    for x, y in zip(ra, rb):
+        assert x["t"] == y["t"]
+        assert abs(x["E_k"] - y["E_k"]) < 1e-9 * abs(x["E_k"]) and abs(x["E_e"] - y["E_e"]) < 1e-9 * abs(x["E_e"])
+    b.sync()
+    assert len(b.last_info) == len(a.last_info) and all(i.converged == 1 for i in b.last_info)
+    # a failing solve surfaces when its step is read
+    b.solve_rtol = 1e-30
+    bad = b.step()
+    with pytest.raises(RuntimeError):
+        bad["E_k"]
+
+
 def test_full_size_properties():
     """n=192 (999 558 DOFs, BASELINE.json): size-independent identities."""
     m = pmesh.Skew_Mesh(192, 1, 1)
