@@ -262,8 +262,13 @@ def test_pipelined_steps_match_synchronous_steps():
     b.sync()
     assert len(b.last_info) == len(a.last_info) and all(i.converged == 1 for i in b.last_info)
     # a failing solve surfaces when its step is read
-    b.solve_rtol = 1e-30
-    bad = b.step()
+    ks = la.parameters["krylov_solver"]
+    old = ks["maximum_iterations"]
+    ks["maximum_iterations"] = 1
+    try:
+        bad = b.step()
+    finally:
+        ks["maximum_iterations"] = old
     with pytest.raises(RuntimeError):
         bad["E_k"]
 
