@@ -39,6 +39,7 @@ struct KArgs {
   double* w;    // KRYLOV_NWORK x n work vectors
   double* red;  // 2 x RED_SLOTS x MAX_GRID
   unsigned* bar;  // grid-barrier counter (zeroed before the launch)
+  int red_atomic;  // grid sums through fp64 atomics (3 rotating accumulators) instead of per-CTA partials
   double rtol, atol, dtol;
   int maxit, pc;
   fx_solve_info* info;
@@ -64,6 +65,34 @@ __device__ __forceinline__ void grid_sum(GridBar& bar, double (&v)[NV], double* 
   }
   block_sum_bcast_n<NV>(v, sh);
   ++phase;
+}
+
+// Variant for latency-bound solves: the CTA sums are added into one of three rotating accumulators with
+// fp64 atomics (fire-and-forget REDs ahead of the barrier's fence), so after the barrier every thread
+// reads the NV totals directly -- no partials array to re-read, no second block reduction.  The sum order
+// varies from run to run (last-bit differences), but every CTA reads the same totals, so control flow
+// stays uniform.  Accumulator (phase+1)%3 is cleared by CTA 0 before it arrives: everybody finished
+// reading it before arriving at the previous barrier, and nobody adds to it until this barrier opens.
+template <int NV>
+__device__ __forceinline__ void grid_sum_atomic(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
+  double* acc = red + (size_t)2 * RED_SLOTS * MAX_GRID;  // [3][RED_SLOTS]
+  double* cur = acc + (phase % 3) * RED_SLOTS;
+  block_sum_bcast_n<NV>(v, sh);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (threadIdx.x == i) atomicAdd(cur + i, v[i]);
+  if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + RED_SLOTS)
+    acc[((phase + 1) % 3) * RED_SLOTS + threadIdx.x - 32] = 0.0;
+  bar.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldcg(cur + i);
+  ++phase;
+}
+
+template <int NV>
+__device__ __forceinline__ void gsum(const KArgs& a, GridBar& bar, double (&v)[NV], int& phase, double* sh) {
+  if (a.red_atomic) grid_sum_atomic<NV>(bar, v, a.red, phase, sh);
+  else grid_sum<NV>(bar, v, a.red, phase, sh);
 }
 
 __device__ __forceinline__ void finish(const KArgs& a, int it, int conv, double rn, double bn) {
@@ -136,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
                   dinv[row] = o.a; r[row] = ri; rh[row] = ri; p[row] = ri; v[row] = 0.0;
                   acc[0] += ri * ri; acc[1] += bi * bi;
                 });
-  grid_sum<3>(bar, acc, a.red, phase, sh);
+  gsum<3>(a, bar, acc, phase, sh);
   if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
@@ -165,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
       if (gw_ < 8192) g_prof_warp[gw_] = tt;
     }
     stamp(a.prof, np);
-    grid_sum<1>(bar, d1, a.red, phase, sh);
+    gsum<1>(a, bar, d1, phase, sh);
     stamp(a.prof, np);
     if (d1[0] == 0.0) { leave(bar, a, it - 1, -1, rn, bn); return; }
     const double alpha = rho / d1[0];
@@ -176,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
       d2[0] += si * si;
     }
     stamp(a.prof, np);
-    grid_sum<1>(bar, d2, a.red, phase, sh);
+    gsum<1>(a, bar, d2, phase, sh);
     stamp(a.prof, np);
     const double ss = d2[0];
     if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
@@ -194,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
                     d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
                   });
     stamp(a.prof, np);
-    grid_sum<4>(bar, d3, a.red, phase, sh);
+    gsum<4>(a, bar, d3, phase, sh);
     stamp(a.prof, np);
     if (d3[1] == 0.0) { leave(bar, a, it, -1, sqrt(ss), bn); return; }
     const double omega = d3[0] / d3[1];
@@ -222,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     }
     stamp(a.prof, np);
     if (check || restart) {
-      grid_sum<1>(bar, d4, a.red, phase, sh);
+      gsum<1>(a, bar, d4, phase, sh);
       rn = sqrt(d4[0]);
       if (rn <= tol) { leave(bar, a, it, 1, rn, bn); return; }
       if (restart) { rho_new = d4[0]; rhn = rn; }
@@ -267,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                   dinv[row] = o.a; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
                   acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
                 });
-  grid_sum<4>(bar, acc, a.red, phase, sh);
+  gsum<4>(a, bar, acc, phase, sh);
   if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }
   double gamma = acc[0], un = sqrt(acc[1]);
   const double bn = sqrt(acc[2]);
@@ -280,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                   w[row] = au;
                   d0[0] += au * o.a;
                 });
-  grid_sum<1>(bar, d0, a.red, phase, sh);
+  gsum<1>(a, bar, d0, phase, sh);
   if (!(d0[0] > 0.0)) { leave(bar, a, 0, -1, un, bn); return; }
   double alpha = gamma / d0[0], beta = 0.0;
   for (int it = 1; it <= a.maxit; ++it) {
@@ -303,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                     w[row] = au;
                     d[2] += au * o.a;
                   });
-    grid_sum<3>(bar, d, a.red, phase, sh);
+    gsum<3>(a, bar, d, phase, sh);
     un = sqrt(d[1]);
     if (!(un == un) || un > a.dtol * bn) { leave(bar, a, it, -1, un, bn); return; }
     if (un <= tol) { leave(bar, a, it, 1, un, bn); return; }
@@ -438,7 +467,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       acc1[0] += bi * bi;
     }
   }
-  grid_sum<1>(bar, acc1, a.red, phase, sh);
+  gsum<1>(a, bar, acc1, phase, sh);
   const double bn = sqrt(acc1[0]);
   const double tol = fmax(a.rtol * bn, a.atol);
   // w = A u, m = M^-1 w
@@ -454,8 +483,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       d[0] += r[row] * ui; d[1] += y[rr] * ui; d[2] += ui * ui;
     }
   }
-  grid_sum<3>(bar, d, a.red, phase, sh);
+  gsum<3>(a, bar, d, phase, sh);
   double gamma_old = 1.0, alpha = 1.0, un = sqrt(d[2]);
+  int np = 0;
   for (int it = 0; it <= a.maxit; ++it) {
     un = sqrt(d[2]);
     if (!(un == un) || un > a.dtol * bn) { finish(a, it, -1, un, bn); return; }
@@ -485,7 +515,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         wo[rr] = w[row]; ro[rr] = r[row]; mo[rr] = m[row]; xo[rr] = a.x[row];
       }
     }
+    stamp(a.prof, np);
     spmv_res(m, y);
+    stamp(a.prof, np);
     d[0] = d[1] = d[2] = 0.0;
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
@@ -505,7 +537,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         d[0] += ri * ui; d[1] += wi * ui; d[2] += ui * ui;
       }
     }
-    grid_sum<3>(bar, d, a.red, phase, sh);
+    stamp(a.prof, np);
+    gsum<3>(a, bar, d, phase, sh);
+    stamp(a.prof, np);
   }
   finish(a, a.maxit, 0, un, bn);
 }
@@ -521,6 +555,17 @@ static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
   void* args[] = {(void*)&ka};
   FX_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_res<R>, dim3(grid), dim3(LA_THREADS), args, smem, st));
   count_launch(1);
+  if (ka.prof) {  // debugging aid: microseconds of [own-row loads | SpMV | updates | reduction+barrier], iterations 10..13
+    static unsigned long long h[1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+    fprintf(stderr, "[pcg prof] grid %d R %d:", grid, R);
+    for (int it = 10; it < 14; ++it) {
+      fprintf(stderr, "  |");
+      for (int k = 0; k < 4; ++k) fprintf(stderr, " %.2f", (double)(h[4 * it + k + 1] - h[4 * it + k]) * 1e-3);
+    }
+    fprintf(stderr, "\n");
+  }
   return FX_OK;
 }
 
@@ -541,6 +586,9 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
   ka.prof = prof_env;
   FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
+  static const int red_env = getenv("FX_RED_ATOMIC") ? atoi(getenv("FX_RED_ATOMIC")) : 1;
+  ka.red_atomic = red_env;
+  if (red_env) FX_CUDA(cudaMemsetAsync(P->red + (size_t)2 * RED_SLOTS * MAX_GRID, 0, sizeof(double) * 3 * RED_SLOTS, st));
   ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
