@@ -158,3 +158,22 @@ def block_jacobi_cg(A, b, bs, rtol=1e-5, maxit=20000):
             return x, it
         rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
     return x, maxit
+
+
+def two_level_cg(A, b, dinv, agg, rtol=1e-5, maxit=20000):
+    """PCG with the additive two-level preconditioner M^-1 = D^-1 + P E^-1 P^T (P = aggregate indicators)."""
+    n, k = len(b), agg.max() + 1
+    P = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, k))
+    Ei = np.linalg.inv((P.T @ A @ P).toarray())
+    M = lambda r: dinv * r + P @ (Ei @ (P.T @ r))  # noqa: E731
+    x = np.zeros_like(b); r = b.copy(); z = M(r); p = z.copy(); rz = r @ z
+    r0 = np.linalg.norm(M(b))
+    for it in range(1, maxit + 1):
+        q = A @ p
+        a = rz / (p @ q)
+        x += a * p; r -= a * q
+        z = M(r)
+        if np.linalg.norm(z) <= rtol * r0:
+            return x, it
+        rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
+    return x, maxit
