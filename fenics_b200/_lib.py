@@ -56,6 +56,7 @@ def _load():
         "fx_dotw_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
         "fx_plan_set_owned_cells": (i, [vp, i]),
         "fx_plan_set_eliminated_dofs": (i, [vp, i, vp, i]),
+        "fx_plan_set_aggregates": (i, [vp, i, vp, i]),
         "fx_krylov_solve": (i, [vp, i, vp, vp, vp, i, i, d, d, i, C.POINTER(SolveInfo), vp]),
         "fx_krylov_solve_async": (i, [vp, i, vp, vp, vp, i, i, d, d, i, i, vp]),
         "fx_solve_results": (i, [vp, i, i, C.POINTER(SolveInfo), vp]),

@@ -120,6 +120,7 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
       if ((rc = upload(&d.pos, hp.pos.data(), hp.pos.size()))) return fail(rc);
       if ((rc = upload(&d.rowblk, hp.rowblk.data(), hp.rowblk.size()))) return fail(rc);
       d.nrowblk = (int)hp.rowblk.size() - 1;
+      d.rowblk_h = hp.rowblk;
     }
     maxn = std::max(maxn, (size_t)hp.n);
   }
@@ -157,9 +158,9 @@ void fx_plan_destroy(fx_plan* P) {
   cudaFree(P->bf_cell); cudaFree(P->bf_local); cudaFree(P->bf_marker); cudaFree(P->bf_geo);
   for (int s = 0; s < S_N; ++s) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
-    cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows);
+    cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows); cudaFree(P->sp[s].agg);
   }
-  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->bar);
+  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;
 }
@@ -334,6 +335,48 @@ int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void
   FX_CUDA(cudaMemcpyAsync(info, P->info + first, sizeof(fx_solve_info) * count, cudaMemcpyDeviceToHost,
                           (cudaStream_t)stream));
   FX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return FX_OK;
+}
+
+int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr || k < 0 || (k > 0 && !agg))
+    return set_error(FX_ERR_ARG, "fx_plan_set_aggregates: bad argument");
+  DevPattern& d = P->sp[space];
+  cudaFree(d.agg);
+  d.agg = nullptr; d.nagg = 0;
+  if (k == 0) return FX_OK;
+  if (k % 32 != 0 || k > COARSE_KMAX)
+    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: k must be a multiple of 32 and <= %d", COARSE_KMAX);
+  std::vector<int> count(k, 0);
+  for (int i = 0; i < d.n; ++i) {
+    if (agg[i] < 0 || agg[i] >= k) return set_error(FX_ERR_ARG, "fx_plan_set_aggregates: agg[%d] = %d out of range", i, agg[i]);
+    ++count[agg[i]];
+  }
+  for (int g = 0; g < k; ++g)
+    if (count[g] == 0) return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: aggregate %d is empty", g);
+  // the resident CG kernel gives CTA c the row blocks c*8 .. c*8+7 (one per warp); each CTA keeps the rows of
+  // (P^T A P)^-1 of the aggregates its rows touch in shared memory
+  int grid = 0;
+  if (!pcg_resident_config(P, d.nrowblk, &grid) )
+    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: space %d is too large for the resident CG kernel", space);
+  int nl_max = 0;
+  for (int c = 0; c < grid; ++c) {
+    std::vector<char> seen(k, 0);
+    int nl = 0;
+    for (int b = c * 8; b < std::min(d.nrowblk, c * 8 + 8); ++b)
+      for (int r = d.rowblk_h[b]; r < d.rowblk_h[b + 1]; ++r)
+        if (!seen[agg[r]]) { seen[agg[r]] = 1; ++nl; }
+    nl_max = std::max(nl_max, nl);
+  }
+  if (nl_max > COARSE_NLMAX)
+    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: a CTA's rows touch %d aggregates (limit %d): aggregates "
+                     "are not local in the dof numbering", nl_max, COARSE_NLMAX);
+  if (!P->coarse) {
+    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * COARSE_KMAX * COARSE_KMAX + 3 * COARSE_KMAX)));
+  }
+  FX_CUDA(cudaMalloc((void**)&d.agg, sizeof(int) * (size_t)d.n));
+  FX_CUDA(cudaMemcpy(d.agg, agg, sizeof(int) * (size_t)d.n, cudaMemcpyHostToDevice));
+  d.nagg = k;
   return FX_OK;
 }
 

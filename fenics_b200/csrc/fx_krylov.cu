@@ -31,7 +31,17 @@ __device__ __forceinline__ void stamp(int prof, int& np) {
   }
 }
 
+// two-level preconditioner of k_pcg_res (fx_plan_set_aggregates); agg == null: plain Jacobi
+struct Coarse {
+  const int* agg;  // [n]
+  int k;           // aggregates (multiple of 32, <= COARSE_KMAX)
+  double* E0;      // k x k
+  double* E1;      // k x k (ping-pong partner of the blocked inversion)
+  double* cvec;    // [3][COARSE_KMAX] rotating coarse right-hand sides
+};
+
 struct KArgs {
+  Coarse cz;
   int prof;
   CsrView A;
   double* x;
@@ -361,6 +371,101 @@ __host__ __device__ constexpr size_t pcg_smem_bytes(int R) {
   return (size_t)LA_WARPS * ((size_t)R * SPMV_NNZB * (sizeof(double) + sizeof(int)) + SPMV_NNZB * sizeof(double));
 }
 
+// shared memory of the coarse correction: rows of E^-1 for the CTA's aggregates, the coarse vector, per-CTA
+// partial sums, the corrections, the aggregate list and the aggregate -> slot map
+constexpr int COARSE_LD = COARSE_KMAX + 8;  // row stride of the resident E^-1 rows (bank-conflict-free dots)
+__host__ __device__ constexpr size_t pcg_coarse_smem_bytes() {
+  return sizeof(double) * ((size_t)COARSE_NLMAX * COARSE_LD + COARSE_KMAX + 2 * COARSE_NLMAX) +
+         sizeof(int) * (COARSE_NLMAX + COARSE_KMAX + 4);
+}
+
+// In-place blocked Gauss-Jordan inversion of the SPD k x k matrix E0 (row major) across the grid:
+// block size 32, K = k/32 steps, step p rewrites every 32x32 tile from the OLD matrix
+//   (p,p) -> P^-1   (p,j) -> P^-1 A_pj   (i,p) -> -A_ip P^-1   (i,j) -> A_ij - A_ip P^-1 A_pj,   P = A_pp
+// into the ping-pong partner, so one grid barrier per step suffices.  Every CTA that owns tiles inverts
+// the pivot block itself (one warp, shared memory).  scratch: 4 x 32 x 33 doubles.  Returns the buffer
+// holding the inverse.
+__device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k, GridBar& bar, double* scratch) {
+  const int K = k >> 5, tiles = K * K, tid = threadIdx.x, lane = threadIdx.x & 31;
+  double* sP = scratch;
+  double* sA = scratch + 32 * 33;
+  double* sB = scratch + 2 * 32 * 33;
+  double* sT = scratch + 3 * 32 * 33;
+  double* Ein = E0;
+  double* Eout = E1;
+  for (int p = 0; p < K; ++p) {
+    if ((int)blockIdx.x < tiles) {
+      for (int e = tid; e < 1024; e += blockDim.x) {
+        const int r = e >> 5, c = e & 31;
+        sP[r * 33 + c] = __ldcg(Ein + (size_t)(p * 32 + r) * k + p * 32 + c);
+      }
+      __syncthreads();
+      if (tid < 32) {  // Gauss-Jordan without pivoting (SPD), lane = row
+        for (int c = 0; c < 32; ++c) {
+          const double pinv = 1.0 / sP[c * 33 + c];
+          __syncwarp();
+          double pv = sP[c * 33 + lane];
+          pv = (lane == c) ? pinv : pv * pinv;
+          __syncwarp();
+          sP[c * 33 + lane] = pv;
+          __syncwarp();
+          if (lane != c) {
+            const double f = sP[lane * 33 + c];
+            for (int j = 0; j < 32; ++j) {
+              const double base = (j == c) ? 0.0 : sP[lane * 33 + j];
+              sP[lane * 33 + j] = base - f * sP[c * 33 + j];
+            }
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int i = t / K, j = t % K;
+        for (int e = tid; e < 1024; e += blockDim.x) {
+          const int r = e >> 5, c = e & 31;
+          if (i != p) sA[r * 33 + c] = __ldcg(Ein + (size_t)(i * 32 + r) * k + p * 32 + c);
+          if (j != p) sB[r * 33 + c] = __ldcg(Ein + (size_t)(p * 32 + r) * k + j * 32 + c);
+        }
+        __syncthreads();
+        if (i != p && j != p) {
+          for (int e = tid; e < 1024; e += blockDim.x) {
+            const int r = e >> 5, c = e & 31;
+            double acc = 0.0;
+            for (int q = 0; q < 32; ++q) acc += sP[r * 33 + q] * sB[q * 33 + c];
+            sT[r * 33 + c] = acc;
+          }
+          __syncthreads();
+        }
+        for (int e = tid; e < 1024; e += blockDim.x) {
+          const int r = e >> 5, c = e & 31;
+          double out;
+          if (i == p && j == p) {
+            out = sP[r * 33 + c];
+          } else if (i == p) {
+            double acc = 0.0;
+            for (int q = 0; q < 32; ++q) acc += sP[r * 33 + q] * sB[q * 33 + c];
+            out = acc;
+          } else if (j == p) {
+            double acc = 0.0;
+            for (int q = 0; q < 32; ++q) acc += sA[r * 33 + q] * sP[q * 33 + c];
+            out = -acc;
+          } else {
+            double acc = 0.0;
+            for (int q = 0; q < 32; ++q) acc += sA[r * 33 + q] * sT[q * 33 + c];
+            out = __ldcg(Ein + (size_t)(i * 32 + r) * k + j * 32 + c) - acc;
+          }
+          Eout[(size_t)(i * 32 + r) * k + j * 32 + c] = out;
+        }
+        __syncthreads();
+      }
+    }
+    bar.sync();
+    double* tmp = Ein; Ein = Eout; Eout = tmp;
+  }
+  return Ein;
+}
+
 template <int R>
 __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant__ KArgs a) {
   GridBar bar;
@@ -416,7 +521,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       if (act) {
         int dst = incl - cnt;
         my_row[rr] = row; my_s0[rr] = dst; my_s1[rr] = dst + cnt;
-        my_dinv[rr] = (a.pc == FX_PC_JACOBI && dg != 0.0) ? 1.0 / dg : 1.0;
+        my_dinv[rr] = (a.pc != FX_PC_NONE && dg != 0.0) ? 1.0 / dg : 1.0;
         for (int j = b; j < e; ++j) {
           const double v = A.val[j];
           if (v != 0.0) { sval[rr * SPMV_NNZB + dst] = v; scol[rr * SPMV_NNZB + dst] = A.col[j]; ++dst; }
@@ -425,6 +530,101 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
     }
   }
   __syncwarp();
+  // ---- two-level preconditioner M^-1 = D^-1 + P E^-1 P^T, E = P^T A P (aggregates a.cz.agg) --------------
+  const bool coarse = a.cz.agg != nullptr;
+  const int ck = a.cz.k;
+  double* einv_s = reinterpret_cast<double*>(dyn + pcg_smem_bytes(R));  // [nl][ck]
+  double* c_s = einv_s + (size_t)COARSE_NLMAX * COARSE_LD;               // [ck]
+  double* cpart = c_s + COARSE_KMAX;                                     // [nl]
+  double* e_s = cpart + COARSE_NLMAX;                                    // [nl]
+  int* list = reinterpret_cast<int*>(e_s + COARSE_NLMAX);                // [nl]
+  int* slot_of = list + COARSE_NLMAX;                                    // [ck]
+  int* nl_s = slot_of + COARSE_KMAX;
+  int my_slot[R], my_agg[R], nl = 0, cph = 0;
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) { my_slot[rr] = 0; my_agg[rr] = 0; }
+  if (coarse) {
+    for (int i = threadIdx.x; i < ck; i += blockDim.x) slot_of[i] = -1;
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (my_row[rr] >= 0) { my_agg[rr] = a.cz.agg[my_row[rr]]; slot_of[my_agg[rr]] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cnt = 0;
+      for (int g = 0; g < ck; ++g)
+        if (slot_of[g] == 0) {
+          slot_of[g] = min(cnt, COARSE_NLMAX - 1);  // the host checked cnt <= COARSE_NLMAX
+          if (cnt < COARSE_NLMAX) list[cnt] = g;
+          ++cnt;
+        }
+      nl_s[0] = min(cnt, COARSE_NLMAX);
+    }
+    __syncthreads();
+    nl = nl_s[0];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (my_row[rr] >= 0) my_slot[rr] = slot_of[my_agg[rr]];
+    // E = P^T A P from the resident slices
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ck * ck; i += gridDim.x * blockDim.x) a.cz.E0[i] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * COARSE_KMAX; i += gridDim.x * blockDim.x) a.cz.cvec[i] = 0.0;
+    bar.sync();
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (my_row[rr] >= 0)
+        for (int j = my_s0[rr]; j < my_s1[rr]; ++j)
+          atomicAdd(a.cz.E0 + (size_t)my_agg[rr] * ck + a.cz.agg[scol[rr * SPMV_NNZB + j]], sval[rr * SPMV_NNZB + j]);
+    bar.sync();
+    const double* Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, einv_s);
+    for (int sidx = 0; sidx < nl; ++sidx)
+      for (int h = threadIdx.x; h < ck; h += blockDim.x)
+        einv_s[(size_t)sidx * COARSE_LD + h] = __ldcg(Einv + (size_t)list[sidx] * ck + h);
+    __syncthreads();
+  }
+  // restriction: add this CTA's part of P^T v to the current coarse right-hand side (before a grid barrier).
+  // A warp's 32 consecutive rows fall into a few aggregates: lanes of one aggregate are summed with
+  // shuffles and their first lane issues ONE global reduction.
+  auto coarse_restrict = [&](const double (&v)[R]) {
+    double* cur = a.cz.cvec + (cph % 3) * COARSE_KMAX;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int g = (my_row[rr] >= 0) ? my_agg[rr] : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, g);
+      double sum = 0.0;
+#pragma unroll 8
+      for (int src = 0; src < 32; ++src) {
+        const double o = __shfl_sync(0xffffffffu, v[rr], src);
+        if ((peers >> src) & 1u) sum += o;
+      }
+      if (g >= 0 && lane == __ffs(peers) - 1) atomicAdd(cur + g, sum);
+    }
+    if (blockIdx.x == 0)  // clear the buffer of the next application (nobody reads or adds to it now)
+      for (int i = threadIdx.x; i < ck; i += blockDim.x) a.cz.cvec[((cph + 1) % 3) * COARSE_KMAX + i] = 0.0;
+  };
+  // after that barrier: e[rr] = (E^-1 P^T v)[aggregate of my row]
+  auto coarse_correct = [&](double (&e)[R]) {
+    const double* cur = a.cz.cvec + (cph % 3) * COARSE_KMAX;
+    for (int i = threadIdx.x; i < ck; i += blockDim.x) c_s[i] = __ldcg(cur + i);
+    __syncthreads();
+    const int seg = threadIdx.x & 7, len = ck >> 3;
+    for (int s0 = 0; s0 < nl; s0 += (int)(blockDim.x >> 3)) {
+      const int sl = s0 + (threadIdx.x >> 3);
+      double acc = 0.0;
+      if (sl < nl) {
+        const double* row = einv_s + (size_t)sl * COARSE_LD + seg;
+        const double* cc = c_s + seg;
+        for (int i = 0; i < len; ++i) acc += row[i * 8] * cc[i * 8];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (sl < nl && seg == 0) e_s[sl] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) e[rr] = (my_row[rr] >= 0) ? e_s[my_slot[rr]] : 0.0;
+    ++cph;
+  };
   // y_row = sum_j val_j x[col_j] for my rows, from the resident slices
   auto spmv_res = [&](const double* x, double (&y)[R]) {
 #pragma unroll
@@ -453,15 +653,25 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
     }
   };
   int phase = 0;
-  double y[R];
+  double y[R], ec[R], tmp[R];
   // r = b - A x, u = M^-1 r
   double acc1[1] = {0.0};
   spmv_res(a.x, y);
+  if (coarse) {  // ||M^-1 b||: restrict b, barrier, correct
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) tmp[rr] = (my_row[rr] >= 0) ? a.b[my_row[rr]] : 0.0;
+    coarse_restrict(tmp);
+    bar.sync();
+    coarse_correct(ec);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) tmp[rr] = (my_row[rr] >= 0) ? a.b[my_row[rr]] - y[rr] : 0.0;
+    coarse_restrict(tmp);  // for u = M^-1 r below
+  }
 #pragma unroll
   for (int rr = 0; rr < R; ++rr) {
     const int row = my_row[rr];
     if (row >= 0) {
-      const double ri = a.b[row] - y[rr], bi = my_dinv[rr] * a.b[row];
+      const double ri = a.b[row] - y[rr], bi = my_dinv[rr] * a.b[row] + (coarse ? ec[rr] : 0.0);
       dinv[row] = my_dinv[rr]; r[row] = ri; u[row] = my_dinv[rr] * ri;
       z[row] = 0.0; q[row] = 0.0; s[row] = 0.0; p[row] = 0.0;
       acc1[0] += bi * bi;
@@ -470,12 +680,20 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
   gsum<1>(a, bar, acc1, phase, sh);
   const double bn = sqrt(acc1[0]);
   const double tol = fmax(a.rtol * bn, a.atol);
+  if (coarse) {  // finish u = D^-1 r + P E^-1 P^T r and publish it for the product below
+    coarse_correct(ec);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (my_row[rr] >= 0) u[my_row[rr]] += ec[rr];
+    bar.sync();
+  }
   // w = A u, m = M^-1 w
   double d[3] = {0.0, 0.0, 0.0};  // gamma = (r,u), delta = (w,u), ||u||^2
   spmv_res(u, y);
 #pragma unroll
   for (int rr = 0; rr < R; ++rr) {
     const int row = my_row[rr];
+    tmp[rr] = y[rr];
     if (row >= 0) {
       const double ui = u[row];
       w[row] = y[rr];
@@ -483,7 +701,15 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       d[0] += r[row] * ui; d[1] += y[rr] * ui; d[2] += ui * ui;
     }
   }
+  if (coarse) coarse_restrict(tmp);
   gsum<3>(a, bar, d, phase, sh);
+  if (coarse) {
+    coarse_correct(ec);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+      if (my_row[rr] >= 0) mbuf[0][my_row[rr]] += ec[rr];
+    bar.sync();
+  }
   double gamma_old = 1.0, alpha = 1.0, un = sqrt(d[2]);
   int np = 0;
   for (int it = 0; it <= a.maxit; ++it) {
@@ -534,11 +760,22 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         const double wi = wo[rr] - alpha * zi;
         r[row] = ri; u[row] = ui; w[row] = wi;
         mn[row] = my_dinv[rr] * wi;
+        tmp[rr] = wi;
         d[0] += ri * ui; d[1] += wi * ui; d[2] += ui * ui;
+      } else {
+        tmp[rr] = 0.0;
       }
     }
     stamp(a.prof, np);
+    if (coarse) coarse_restrict(tmp);
     gsum<3>(a, bar, d, phase, sh);
+    if (coarse) {  // m_new = D^-1 w + P E^-1 P^T w, visible to every CTA before the next product
+      coarse_correct(ec);
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr)
+        if (my_row[rr] >= 0) mn[my_row[rr]] += ec[rr];
+      bar.sync();
+    }
     stamp(a.prof, np);
   }
   finish(a, a.maxit, 0, un, bn);
@@ -546,11 +783,11 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
 
 template <int R>
 static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
-  const size_t smem = pcg_smem_bytes(R);
-  static bool attr_done = false;
-  if (!attr_done) {
+  const size_t smem = pcg_smem_bytes(R) + (ka.cz.agg != nullptr ? pcg_coarse_smem_bytes() : 0);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     FX_CUDA(cudaFuncSetAttribute(k_pcg_res<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_smem = smem;
   }
   void* args[] = {(void*)&ka};
   FX_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_res<R>, dim3(grid), dim3(LA_THREADS), args, smem, st));
@@ -569,20 +806,35 @@ static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
   return FX_OK;
 }
 
+bool pcg_resident_config(const fx_plan* P, int nrowblk, int* grid) {
+  if (nrowblk > P->num_sms * LA_WARPS) return false;  // one row block per warp, one CTA per SM
+  *grid = min(P->num_sms, (nrowblk + LA_WARPS - 1) / LA_WARPS);
+  return true;
+}
+
 int la_krylov(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
   if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB)
     return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg available)", method);
-  if (pc != FX_PC_NONE && pc != FX_PC_JACOBI)
-    return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi available)", pc);
+  if (pc != FX_PC_NONE && pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE)
+    return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, jacobi_coarse available)", pc);
+  int grid1 = 0;
+  if (pc == FX_PC_JACOBI_COARSE &&
+      (method != FX_KSP_CG || p.nagg == 0 || rtol < 1e-9 || p.nelim != 0 || !pcg_resident_config(P, p.nrowblk, &grid1)))
+    return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates), "
+                     "rtol >= 1e-9 and a system that fits the resident CG kernel");
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
   ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->cdesc, P->cre, P->ccol, P->cval,
                  p.nelim > 0 ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart};
   ka.bar = P->bar;
+  ka.cz = Coarse{nullptr, 0, nullptr, nullptr, nullptr};
+  if (pc == FX_PC_JACOBI_COARSE)
+    ka.cz = Coarse{p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX * COARSE_KMAX,
+                   P->coarse + (size_t)2 * COARSE_KMAX * COARSE_KMAX};
   static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
   ka.prof = prof_env;
   FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));

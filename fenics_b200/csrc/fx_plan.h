@@ -34,12 +34,17 @@ struct DevPattern {
   int* rowblk = nullptr;
   int nrowblk = 0;
   // block-triangular elimination (fx_plan_set_eliminated_dofs): trailing rows solved by back-substitution
+  std::vector<int> rowblk_h;  // host copy of rowblk
+  int* agg = nullptr;         // [n] aggregate of each dof (fx_plan_set_aggregates), null = none
+  int nagg = 0;
   uint8_t* elim = nullptr;    // [n] 1 = eliminated row
   int* elim_rows = nullptr;   // [nelim]
   int nelim = 0;
 };
 
 constexpr int KRYLOV_NWORK = 12;
+constexpr int COARSE_KMAX = 256;   // aggregates of the two-level preconditioner
+constexpr int COARSE_NLMAX = 48;   // aggregates one CTA of the resident CG kernel may touch
 constexpr int RED_SLOTS = 4;       // values reduced at once
 constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
 
@@ -68,6 +73,7 @@ struct fx_plan {
   int *ccol = nullptr, *cre = nullptr;
   int4* cdesc = nullptr;  // per-row-block descriptors of the compacted copy
   int *cprefix = nullptr, *scanpart = nullptr;  // nnz-balanced partition of the row blocks (balance_partition)
+  double* coarse = nullptr;                     // two-level preconditioner scratch: E0, E1 (256^2 each), cvec [3][256]
   unsigned* bar = nullptr;                      // grid-barrier counter of the persistent Krylov kernels
 
   fx::MeshView view() const {
@@ -99,6 +105,7 @@ int la_dot(fx_plan* plan, int n, const double* x, const double* y, double* out_d
 int la_norm(fx_plan* plan, int n, const double* x, int kind, double* out_dev, cudaStream_t st);
 int la_lincomb3(int n, double* out, const double* coef, const double* x, const double* y, const double* z, cudaStream_t st);
 int la_dotw(fx_plan* plan, int n, const double* x, const double* y, const double* w, double* out_dev, cudaStream_t st);
+bool pcg_resident_config(const fx_plan* plan, int nrowblk, int* grid);  // R == 1 configuration of k_pcg_res
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
 }  // namespace fx

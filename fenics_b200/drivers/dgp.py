@@ -98,7 +98,7 @@ class CompDGP(_LDC):
         self._system("u12", A.FX_FORM_C5_A1, A.FX_FORM_C5_L1, self.AW, self.bW, self.w12, self.bcu)   # :432-447
         self._system("us", A.FX_FORM_C5_A2, A.FX_FORM_C5_L2, self.AW, self.bW, self.ws, self.bcu)     # :473-489
         self._system("p", A.FX_FORM_C5_A5, A.FX_FORM_C5_L5, self.AQ, self.bQ, self.p1, (),
-                     method=self.pressure_method)                                                      # :493-506
+                     method=self.pressure_method, pc=self._pressure_pc())                                                      # :493-506
         self._system("rho1su", A.FX_FORM_C5_A6, A.FX_FORM_C5_L6, self.AQ, self.bQ, self.rho1, ())     # :510-525 (dead)
         self._project_consistent(self.proj_rho1, self.rho1, self.AQ, self.bQ, "rho1")                 # :529-530
         self._system("u1", A.FX_FORM_C5_A7, A.FX_FORM_C5_L7, self.AW, self.bW, self.w1, self.bcu)     # :533-543

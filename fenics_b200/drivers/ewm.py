@@ -60,7 +60,7 @@ class EwmJBP(FenepmpJBP):
         self._system("u12", A.FX_FORM_C3_A1, A.FX_FORM_C3_L1, self.AW, self.bW, self.w12, self.bcu)    # :517-537
         self._system("us", A.FX_FORM_C3_A2, A.FX_FORM_C3_L2, self.AW, self.bW, self.ws, self.bcu)      # :563-581
         self._system("p", A.FX_FORM_C3_A5, A.FX_FORM_C3_L5, self.AQ, self.bQ, self.p1, (),
-                     method=self.pressure_method)                                                       # :586-598
+                     method=self.pressure_method, pc=self._pressure_pc())                                                       # :586-598
         self._system("rho1", A.FX_FORM_C3_A6, A.FX_FORM_C3_L6, self.AQ, self.bQ, self.rho1, ())        # :603-615
         self._system("u1", A.FX_FORM_C3_A7, A.FX_FORM_C3_L7, self.AW, self.bW, self.w1, self.bcu,
                      rtol=min(self.direct_rtol, self.solve_rtol))                                       # :617-629

@@ -112,7 +112,7 @@ class FenepmpJBP(_LDC):
         self._system("rho12", A.FX_FORM_C4_A0, A.FX_FORM_C4_L0, self.AQ, self.bQ, self.rho12, ())      # :501-510
         self._system("us", A.FX_FORM_C4_A2, A.FX_FORM_C4_L2, self.AW, self.bW, self.ws, self.bcu)      # :513-531
         self._system("p", A.FX_FORM_C4_A5, A.FX_FORM_C4_L5, self.AQ, self.bQ, self.p1, (),
-                     method=self.pressure_method)                                                       # :536-549
+                     method=self.pressure_method, pc=self._pressure_pc())                                                       # :536-549
         self._system("rho1", A.FX_FORM_C4_A6, A.FX_FORM_C4_L6, self.AQ, self.bQ, self.rho1, ())        # :553-570
         self._system("u1", A.FX_FORM_C4_A7, A.FX_FORM_C4_L7, self.AW, self.bW, self.w1, self.bcu)      # :573-586
         self._system("tau", A.FX_FORM_C4_A4, A.FX_FORM_C4_L4, self.AZ, self.bZ, self.tau1_vec, ())     # :595-611

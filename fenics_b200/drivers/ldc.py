@@ -20,6 +20,7 @@ from ..dolfin_api import (ConsistentProjection, DirichletBC, Function, Problem, 
                           assemble_scalar_async, project)
 from ..la import Matrix, Plan, Vector
 from ..mesh import DOLFIN_EPS
+from ..partition import rcb_partition
 from ..spaces import function_spaces
 
 
@@ -72,6 +73,7 @@ class PendingStep(dict):
 class _LDC:
     solver = ("bicgstab", "default")   # what the reference passes to solve()
     pressure_method = "bicgstab"       # reference; "cg" is the north_star upgrade (A5 is symmetric)
+    pressure_pc = None                 # "jacobi_coarse" after enable_pressure_coarse() (CG only)
     STATE_FIELDS = ()                  # fields carried from step to step (host<->device in e2e mode)
     eliminate_devss = True             # W solves: iterate on the velocity rows, back-substitute the DG0 DEVSS rows
     pipeline = False                   # with check=False: step() returns a PendingStep instead of syncing, so the
@@ -111,6 +113,21 @@ class _LDC:
         self.solve_labels = []
         self._ticket = 0
         self.profile = None          # set to a list to record (label, start_event, end_event) per phase
+
+    def enable_pressure_coarse(self, k=256):
+        """Two-level preconditioner (Jacobi + aggregate coarse correction, fx_plan_set_aggregates) for the CG
+        pressure solve; aggregates = recursive coordinate bisection of the P1 dof coordinates.  Only for
+        non-singular pressure matrices (the compressible loops: the Ma^2/dt mass term).  Returns whether the
+        library accepted the aggregates."""
+        Q = self.S["Q"]
+        k = min(int(k), (Q.dim() // 8) // 32 * 32)  # >= 8 dofs per aggregate, multiple of 32
+        ok = k >= 32 and self.plan.set_aggregates("Q", rcb_partition(Q.tabulate_dof_coordinates(), k), k)
+        self.pressure_pc = "jacobi_coarse" if ok else None
+        return bool(ok)
+
+    def _pressure_pc(self):
+        rtol = la.parameters["krylov_solver"]["relative_tolerance"] if self.solve_rtol is None else self.solve_rtol
+        return self.pressure_pc if (self.pressure_method == "cg" and rtol >= 1e-9) else None
 
     def set_devss_elimination(self, on):
         """The W systems are block lower triangular: the rows tested with R read (u, D) but no momentum row
@@ -268,7 +285,7 @@ class IncompLDC(_LDC):
         self._system("u12", abi.FX_FORM_C1_A1, abi.FX_FORM_C1_L1, self.AW, self.bW, self.w12, self.bcu)  # :317-331
         self._system("us", abi.FX_FORM_C1_A2, abi.FX_FORM_C1_L2, self.AW, self.bW, self.ws, self.bcu)  # :355-363
         self._system("p", abi.FX_FORM_C1_A5, abi.FX_FORM_C1_L5, self.AQ, self.bQ, self.p1, (),
-                     method=self.pressure_method)  # :370-375 (bcp = [])
+                     method=self.pressure_method, pc=self._pressure_pc())  # :370-375 (bcp = [])
         self._system("u1", abi.FX_FORM_C1_A7, abi.FX_FORM_C1_L7, self.AW, self.bW, self.w1, self.bcu)  # :379-394
         self._system("tau", abi.FX_FORM_C1_A4, abi.FX_FORM_C1_L4, self.AZ, self.bZ, self.tau1_vec, ())  # :400-416
         f = self.pr.form
@@ -320,7 +337,7 @@ class CompLDC(_LDC):
         self._system("u12", abi.FX_FORM_C2_A1, abi.FX_FORM_C2_L1, self.AW, self.bW, self.w12, self.bcu)  # :430-447
         self._system("us", abi.FX_FORM_C2_A2, abi.FX_FORM_C2_L2, self.AW, self.bW, self.ws, self.bcu)  # :458-476
         self._system("p", abi.FX_FORM_C2_A5, abi.FX_FORM_C2_L5, self.AQ, self.bQ, self.p1, (),
-                     method=self.pressure_method)  # :483-497
+                     method=self.pressure_method, pc=self._pressure_pc())  # :483-497
         self._project_consistent(self.proj_rho1, self.rho1, self.AQ, self.bQ, "rho1")  # :501-502
         self._system("u1", abi.FX_FORM_C2_A7, abi.FX_FORM_C2_L7, self.AW, self.bW, self.w1, self.bcu)  # :506-519
         self._system("tau", abi.FX_FORM_C2_A4, abi.FX_FORM_C2_L4, self.AZ, self.bZ, self.tau1_vec, ())  # :528-544

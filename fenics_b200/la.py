@@ -9,7 +9,8 @@ from . import _abi as abi
 from ._lib import SolveInfo, check, lib
 
 _KSP = {"bicgstab": abi.FX_KSP_BICGSTAB, "cg": abi.FX_KSP_CG, "gmres": abi.FX_KSP_GMRES}
-_PC = {"none": abi.FX_PC_NONE, "jacobi": abi.FX_PC_JACOBI, "ilu": abi.FX_PC_ILU0, "default": abi.FX_PC_JACOBI}
+_PC = {"none": abi.FX_PC_NONE, "jacobi": abi.FX_PC_JACOBI, "ilu": abi.FX_PC_ILU0, "default": abi.FX_PC_JACOBI,
+       "jacobi_coarse": abi.FX_PC_JACOBI_COARSE}
 
 # mirror of dolfin's global `parameters["krylov_solver"]` (PETSc defaults)
 parameters = {"krylov_solver": {"relative_tolerance": 1e-5, "absolute_tolerance": 1e-50,
@@ -67,6 +68,16 @@ class Plan:
         systems, fx_plan_set_eliminated_dofs); an empty list switches it off."""
         r = np.ascontiguousarray(rows, dtype=np.int32)
         check(lib.fx_plan_set_eliminated_dofs(self.h, abi.SPACE_ID[space], r.ctypes.data, len(r)))
+
+    def set_aggregates(self, space, agg, k):
+        """aggregates of the two-level preconditioner "jacobi_coarse" (fx_plan_set_aggregates); returns False
+        (and leaves the space without aggregates) when the library cannot use them for this space."""
+        a = np.ascontiguousarray(agg, dtype=np.int32)
+        rc = lib.fx_plan_set_aggregates(self.h, abi.SPACE_ID[space], a.ctypes.data, int(k))
+        if rc == abi.FX_ERR_UNSUPPORTED:
+            return False
+        check(rc)
+        return True
 
     def dim(self, space):
         return lib.fx_space_dim(self.h, abi.SPACE_ID[space])

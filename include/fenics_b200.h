@@ -121,7 +121,10 @@ typedef enum {
 } fx_expr;
 
 typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;
-typedef enum { FX_PC_NONE = 0, FX_PC_JACOBI = 1, FX_PC_ILU0 = 2 } fx_pc;
+typedef enum {
+  FX_PC_NONE = 0, FX_PC_JACOBI = 1, FX_PC_ILU0 = 2,
+  FX_PC_JACOBI_COARSE = 3 /* Jacobi + aggregate coarse-grid correction, see fx_plan_set_aggregates */
+} fx_pc;
 
 typedef struct {
   int iterations;
@@ -218,6 +221,17 @@ int fx_plan_set_owned_cells(fx_plan* plan, int nc_owned);
  * the solve fail with converged = -3.  n = 0 switches elimination off.  The convergence test then
  * monitors the residual of the active rows.                                                     */
 int fx_plan_set_eliminated_dofs(fx_plan* plan, int space, const int* rows, int n);
+
+/* Aggregates for the two-level preconditioner FX_PC_JACOBI_COARSE of the CG solves on `space`:
+ *   M^-1 = D^-1 + P (P^T A P)^-1 P^T,   P = indicator vectors of k aggregates of dofs (agg[i] in [0,k)).
+ * Stands where the reference asks PETSc for "amg"/"default" on the pressure system
+ * (incompressible_benchmarkEWM.py:441-451): Jacobi-CG needs O(1/h) iterations of microseconds each; the
+ * coarse space removes the smooth error modes that cost most of them.  The coarse matrix is rebuilt
+ * from the current matrix values and inverted on the device inside every solve.  Requirements:
+ * k a multiple of 32, k <= 256, every aggregate non-empty, A non-singular, and the system small enough
+ * for the shared-memory-resident CG kernel with aggregates local to its row blocks; returns
+ * FX_ERR_UNSUPPORTED (and leaves the space without aggregates) otherwise.  k = 0 removes them.       */
+int fx_plan_set_aggregates(fx_plan* plan, int space, const int* agg, int k);
 
 /* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,

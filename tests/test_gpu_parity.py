@@ -201,6 +201,33 @@ def test_elimination_rejects_matrices_that_are_not_block_triangular():
     assert la.krylov_solve(A, x, b, "bicgstab", "jacobi").converged == 1
 
 
+def test_two_level_pressure_preconditioner():
+    """CG with Jacobi + aggregate coarse correction: same solution as LU within the tolerance, fewer
+    iterations than Jacobi-CG; the coarse matrix is rebuilt and inverted on the device in every solve."""
+    ocl, drv = _pair(2, n=40)
+    lc.randomize(ocl)
+    _push_state(ocl, drv)
+    assert drv.enable_pressure_coarse(k=64)
+    A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
+    b = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_L5))
+    ref = spla.splu(A.to_scipy().tocsc()).solve(b.get_local())
+    its = {}
+    for pc in ("jacobi", "jacobi_coarse"):
+        x = la.Vector(drv.plan, "Q")
+        info = la.krylov_solve(A, x, b, "cg", pc, rtol=1e-9, maxit=20000)
+        assert info.converged == 1
+        assert lc.rel_err(x.get_local(), ref) < 1e-6, (pc, lc.rel_err(x.get_local(), ref))
+        its[pc] = info.iterations
+    assert its["jacobi_coarse"] < 0.6 * its["jacobi"], its
+    # not usable: BiCGStab, tight tolerances, spaces without aggregates -> loud errors, no silent fallback
+    x = la.Vector(drv.plan, "Q")
+    for kw in (dict(method="bicgstab", rtol=1e-5), dict(method="cg", rtol=1e-12)):
+        with pytest.raises(Exception) as e:
+            la.krylov_solve(A, x, b, kw["method"], "jacobi_coarse", rtol=kw["rtol"])
+        assert "jacobi_coarse" in str(e.value)
+    assert drv.plan.set_aggregates("Q", [], 0)
+
+
 def test_krylov_nonconvergence_raises():
     ocl, drv = _pair(2, n=8)
     A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))

@@ -14,6 +14,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 drv = ldc.CompLDC(pmesh.Skew_Mesh(n, 1, 1))
 drv.t = 0.45
 drv.pressure_method = "cg"
+if not os.environ.get("FX_NO_COARSE"):
+    drv.enable_pressure_coarse(256)
 for _ in range(steps):
     out = drv.step()
 torch.cuda.synchronize()

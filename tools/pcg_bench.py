@@ -19,15 +19,19 @@ drv.step()
 A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
 b = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_L5))
 x = la.Vector(drv.plan, "Q")
+pc = "jacobi"
+if os.environ.get("FX_COARSE"):
+    assert drv.enable_pressure_coarse(int(os.environ["FX_COARSE"]))
+    pc = "jacobi_coarse"
 res = []
 for rep in range(6):
     x.t.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    info = la.krylov_solve(A, x, b, "cg", "jacobi", rtol=1e-5)
+    info = la.krylov_solve(A, x, b, "cg", pc, rtol=1e-5)
     e1.record()
     torch.cuda.synchronize()
     res.append((e0.elapsed_time(e1), info.iterations))
 ms, its = min(res)
-print(json.dumps(dict(variant=os.environ.get("FX_PCG_VARIANT", "default"), n=n, dofs=A.n, ms=round(ms, 3), iterations=its,
+print(json.dumps(dict(pc=pc, variant=os.environ.get("FX_PCG_VARIANT", "default"), n=n, dofs=A.n, ms=round(ms, 3), iterations=its,
                       us_per_iteration=round(1e3 * ms / its, 3), checksum=float(x.t.double().sum()))))
