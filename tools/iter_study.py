@@ -177,3 +177,30 @@ def two_level_cg(A, b, dinv, agg, rtol=1e-5, maxit=20000):
             return x, it
         rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn
     return x, maxit
+
+
+def bicgstab_two_level(A, b, dinv, agg, rtol=1e-5, maxit=10000):
+    """left-preconditioned BiCGStab with M^-1 = D^-1 + P (P^T A P)^-1 P^T."""
+    n, k = len(b), agg.max() + 1
+    P = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, k))
+    Ei = np.linalg.inv((P.T @ A @ P).toarray())
+    M = lambda r: dinv * r + P @ (Ei @ (P.T @ r))  # noqa: E731
+    x = np.zeros_like(b)
+    r = M(b - A @ x)
+    r0 = np.linalg.norm(M(b))
+    rh = r.copy(); p = r.copy(); rho = rh @ r
+    for it in range(1, maxit + 1):
+        v = M(A @ p)
+        alpha = rho / (rh @ v)
+        s_ = r - alpha * v
+        t = M(A @ s_)
+        om = (t @ s_) / (t @ t)
+        x += alpha * p + om * s_
+        r = s_ - om * t
+        if np.linalg.norm(r) <= rtol * r0:
+            return x, it
+        rho_n = rh @ r
+        beta = rho_n / rho * alpha / om
+        rho = rho_n
+        p = r + beta * (p - om * v)
+    return x, maxit
