@@ -328,6 +328,9 @@ __device__ __forceinline__ void spmv_stream(const CsrView& A, const BlockRange r
 // value/column stream so all of it is in flight together; row starts come from the neighbour lane.
 //   pre(row)            -> Ops (plain struct of the vector entries the epilogue needs)
 //   post(row, Ax, ops)  epilogue
+#ifndef SPMV_INFLIGHT
+#define SPMV_INFLIGHT 8  // value/column loads per lane in flight (x 32 lanes = entries per pass)
+#endif
 template <class Pre, class Post>
 __device__ __forceinline__ void spmv_stream_c(const CsrView& A, const BlockRange rg, const double* x, double* smem,
                                               Pre&& pre, Post&& post) {
@@ -345,17 +348,17 @@ __device__ __forceinline__ void spmv_stream_c(const CsrView& A, const BlockRange
     const int e1 = act ? __ldcg(A.re + row) : j0;
     decltype(pre(0)) ops{};
     if (act) ops = pre(row);
-    for (int jb = j0; jb < j1; jb += 256) {
-      int c[8];
-      double v[8];
+    for (int jb = j0; jb < j1; jb += 32 * SPMV_INFLIGHT) {
+      int c[SPMV_INFLIGHT];
+      double v[SPMV_INFLIGHT];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < SPMV_INFLIGHT; ++u) {
         const int j = jb + u * 32 + lane;
         c[u] = (j < j1) ? ld_stream(col + j) : -1;
         v[u] = (j < j1) ? ld_stream(val + j) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < SPMV_INFLIGHT; ++u)
         if (c[u] >= 0) prod[jb - j0 + u * 32 + lane] = v[u] * x[c[u]];
     }
     __syncwarp();
