@@ -300,6 +300,28 @@ def test_pipelined_steps_match_synchronous_steps():
         bad["E_k"]
 
 
+def test_extrapolated_initial_guess_same_solution_fewer_iterations():
+    """x0 = 2 x^n - x^(n-1) instead of x^n: the converged fields agree to the solver tolerance and the
+    solves need fewer iterations."""
+    _, a = _pair(2, n=16)
+    _, b = _pair(2, n=16)
+    b.extrapolate_guess = True
+    for d in (a, b):
+        d.t = 0.45
+        d.solve_rtol = 1e-11
+        d.pressure_method = "cg"
+    ia = ib = 0
+    for _ in range(6):
+        ra, rb = a.step(), b.step()
+        ia += sum(i.iterations for i in a.last_info)
+        ib += sum(i.iterations for i in b.last_info)
+    assert abs(ra["E_k"] - rb["E_k"]) < 1e-7 * abs(ra["E_k"]) and abs(ra["E_e"] - rb["E_e"]) < 1e-7 * abs(ra["E_e"])
+    fa, fb = a.fields(), b.fields()
+    for k in ("w1", "tau1", "rho1"):
+        assert lc.rel_err(fb[k], fa[k]) < 1e-7, k
+    assert ib < ia, (ia, ib)
+
+
 def test_full_size_properties():
     """n=192 (999 558 DOFs, BASELINE.json): size-independent identities."""
     m = pmesh.Skew_Mesh(192, 1, 1)
