@@ -32,5 +32,5 @@ NSPACES = ENUM["FX_NSPACES"]
 NFIELDS = ENUM["FX_NFIELDS"]
 NPARAMS = ENUM["FX_NPARAMS"]
 SPACE_ID = {"W": ENUM["FX_SPACE_W"], "Zc": ENUM["FX_SPACE_ZC"], "Q": ENUM["FX_SPACE_Q"],
-            "Zd": ENUM["FX_SPACE_ZD"], "Qt": ENUM["FX_SPACE_QT"], "V": ENUM["FX_SPACE_V"]}
-SPACE_LD = {"W": 15, "Zc": 18, "Q": 3, "Zd": 3, "Qt": 1, "V": 12}
+            "Zd": ENUM["FX_SPACE_ZD"], "Qt": ENUM["FX_SPACE_QT"], "V": ENUM["FX_SPACE_V"], "Vs": ENUM["FX_SPACE_VS"]}
+SPACE_LD = {"W": 15, "Zc": 18, "Q": 3, "Zd": 3, "Qt": 1, "V": 12, "Vs": 6}

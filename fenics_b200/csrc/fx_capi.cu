@@ -108,7 +108,7 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
     if (!cell_dofs[s]) continue;
     HostPattern hp;
     std::string err;
-    const bool want = (s == S_W || s == S_ZC || s == S_Q || s == S_V);
+    const bool want = (s == S_W || s == S_ZC || s == S_Q || s == S_V || s == S_VS);
     if (!build_pattern(cell_dofs[s], nc, space_ld(s), want, hp, err))
       return fail(set_error(FX_ERR_ARG, "fx_plan_create: space %d: %s", s, err.c_str()));
     DevPattern& d = P->sp[s];

@@ -63,9 +63,10 @@ using SpQ = SpaceT<P1>;
 using SpZd = SpaceT<DG0, DG0, DG0>;
 using SpQt = SpaceT<DG0>;
 using SpV = SpaceT<P2, P2>;
+using SpVs = SpaceT<P2>;
 
 // runtime ids must match include/fenics_b200.h fx_space
-enum SpaceId : int { S_W = 0, S_ZC = 1, S_Q = 2, S_ZD = 3, S_QT = 4, S_V = 5, S_N = 6 };
+enum SpaceId : int { S_W = 0, S_ZC = 1, S_Q = 2, S_ZD = 3, S_QT = 4, S_V = 5, S_VS = 6, S_N = 7 };
 template <class Sp> struct space_id;
 template <> struct space_id<SpW> { static constexpr int v = S_W; };
 template <> struct space_id<SpZc> { static constexpr int v = S_ZC; };
@@ -73,9 +74,10 @@ template <> struct space_id<SpQ> { static constexpr int v = S_Q; };
 template <> struct space_id<SpZd> { static constexpr int v = S_ZD; };
 template <> struct space_id<SpQt> { static constexpr int v = S_QT; };
 template <> struct space_id<SpV> { static constexpr int v = S_V; };
+template <> struct space_id<SpVs> { static constexpr int v = S_VS; };
 
 FX_HDC int space_ld(int s) {
-  return s == S_W ? 15 : s == S_ZC ? 18 : s == S_Q ? 3 : s == S_ZD ? 3 : s == S_QT ? 1 : 12;
+  return s == S_W ? 15 : s == S_ZC ? 18 : s == S_Q ? 3 : s == S_ZD ? 3 : s == S_QT ? 1 : s == S_V ? 12 : 6;
 }
 
 // ---- compile-time loop ----------------------------------------------------------------------

@@ -642,5 +642,36 @@ struct C2_L7 {
   }
 };
 
+// ---- post-loop diagnostics: stream function on the scalar P2 space V.sub(0).collapse() -------------------
+// (lid-driven-cavity/fenics_fem.py:340-378; slots of the single P2 component: QV, QX, QY)
+struct STREAM_A {  // a = inner(grad(psi), grad(phi))*dx
+  using Space = SpVs; using Facet = NoFacet;
+  static constexpr int QDEG = 2, NP = 0;
+  FX_HD static void point(const PtArgs&, double*) {}
+  template <class A> FX_HDC static void terms(A& a, const double*, const Par&) {
+    a.template add<QX, QX>(1.0);
+    a.template add<QY, QY>(1.0);
+  }
+};
+// L = inner(u[1].dx(0) - u[0].dx(1), phi)*dx   [COMP: rho1 times each derivative, fenics_fem.py:371]
+template <bool COMP>
+struct STREAM_L {
+  using Space = SpVs; using Facet = NoFacet;
+  static constexpr int QDEG = COMP ? 4 : 3, NP = 1;
+  FX_HD static void point(const PtArgs& x, double* d) {
+    P2Phys b;
+    p2_phys(x.xi, x.et, x.g, b);
+    const Vel u = eval_vel(x.m, x.s.f[F_W1], x.cell, b);
+    double rho = 1.0;
+    if (COMP) {
+      P1Phys b1;
+      p1_phys(x.xi, x.et, x.g, b1);
+      rho = eval_q(x.m, x.s.f[F_RHO1], x.cell, b1).v;
+    }
+    d[0] = rho * (u.g10 - u.g01);
+  }
+  template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) { a.template add<QV>(d[0]); }
+};
+
 }  // namespace ldc
 }  // namespace fx

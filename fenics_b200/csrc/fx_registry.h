@@ -11,6 +11,7 @@
 #define FX_MATRIX_FORMS(X)                  \
   X(FX_FORM_MASS_ZC, fx::ldc::MASS_ZC)      \
   X(FX_FORM_MASS_Q, fx::ldc::MASS_Q)        \
+  X(FX_FORM_STREAM_A, fx::ldc::STREAM_A)    \
   X(FX_FORM_C1_A1, fx::ldc::C1_A1)          \
   X(FX_FORM_C1_A2, fx::ldc::C1_A2)          \
   X(FX_FORM_C1_A5, fx::ldc::C1_A5)          \
@@ -49,6 +50,8 @@
 #define FX_VECTOR_FORMS(X, XC)                              \
   XC(FX_FORM_C1_L1, fx::ldc::C1_L1<4>, fx::ldc::C1_L1<5>)   \
   XC(FX_FORM_C1_L2, fx::ldc::C1_L2<4>, fx::ldc::C1_L2<5>)   \
+  X(FX_FORM_STREAM_L, fx::ldc::STREAM_L<false>)             \
+  X(FX_FORM_COMP_STREAM_L, fx::ldc::STREAM_L<true>)         \
   X(FX_FORM_C1_L5, fx::ldc::C1_L5)                          \
   X(FX_FORM_C1_L7, fx::ldc::C1_L7)                          \
   X(FX_FORM_C1_L4, fx::ldc::LDC_L4<false>)                  \

@@ -21,7 +21,7 @@ from ..dolfin_api import (ConsistentProjection, DirichletBC, Function, Problem, 
 from ..la import Matrix, Plan, Vector
 from ..mesh import DOLFIN_EPS
 from ..partition import rcb_partition
-from ..spaces import function_spaces
+from ..spaces import FunctionSpace, function_spaces
 
 
 def lid_bcs(W, L=1.0):
@@ -84,8 +84,9 @@ class _LDC:
     def _setup(self, mesh, dofmaps, device):
         self.mesh = mesh
         W, V, _, _, Zd, Zc, Q, Qt, _ = function_spaces(mesh, 2, dofmaps)
-        self.S = dict(W=W, V=V, Zd=Zd, Zc=Zc, Q=Q, Qt=Qt)
-        self.plan = Plan(mesh, [W, Zc, Q, Zd, Qt, V], device)
+        Vs = FunctionSpace(mesh, "Vs", (dofmaps or {}).get("Vs"))  # V.sub(0).collapse(): stream function
+        self.S = dict(W=W, V=V, Zd=Zd, Zc=Zc, Q=Q, Qt=Qt, Vs=Vs)
+        self.plan = Plan(mesh, [W, Zc, Q, Zd, Qt, V, Vs], device)
         self.set_devss_elimination(self.eliminate_devss)
         self.pr = Problem(self.plan)
         for k, v in self.p.items():
@@ -115,6 +116,33 @@ class _LDC:
         self.solve_labels = []
         self._ticket = 0
         self.profile = None          # set to a list to record (label, start_event, end_event) per phase
+
+    # -- post-loop diagnostics (lid-driven-cavity/fenics_fem.py:340-417) ------------------------------
+    def stream_function(self, compressible=False, rtol=1e-12):
+        """stream_function(u1) / comp_stream_function(rho1, u1): -lap(psi) = curl(u1) [rho1-weighted] on the
+        scalar P2 space, psi = 0 on the whole boundary.  The reference solves directly (assemble_system +
+        LU); here CG + Jacobi to `rtol`.  `project(u1, V)` before the call (incomp_LDC.py:457) is the
+        identity for the P2 velocity of w1.  Returns the Function psi."""
+        Vs = self.S["Vs"]
+        if not hasattr(self, "_psi"):
+            self._psi = Function(Vs, self.plan)
+            self._Apsi, self._bpsi = Matrix(self.plan, "Vs"), Vector(self.plan, "Vs")
+            self._bcpsi = DirichletBC(Vs, 0.0, lambda x, on_boundary: on_boundary)
+        f = self.pr.form
+        assemble(f(abi.FX_FORM_STREAM_A), tensor=self._Apsi)
+        assemble(f(abi.FX_FORM_COMP_STREAM_L if compressible else abi.FX_FORM_STREAM_L), tensor=self._bpsi)
+        self._bcpsi.apply(self._Apsi, self._bpsi)
+        la.krylov_solve(self._Apsi, self._psi.vector(), self._bpsi, "cg", "jacobi", rtol=rtol, maxit=100000)
+        return self._psi
+
+    def min_location(self, fn):
+        """min_location(u, mesh): coordinates of the dofs holding the minimum of `fn`."""
+        v = fn.vector().get_local()
+        return fn.function_space().tabulate_dof_coordinates()[np.where(v == v.min())]
+
+    def max_location(self, fn):
+        v = fn.vector().get_local()
+        return fn.function_space().tabulate_dof_coordinates()[np.where(v == v.max())]
 
     def enable_pressure_coarse(self, k=256):
         """Two-level preconditioner (Jacobi + aggregate coarse correction, fx_plan_set_aggregates) for the CG

@@ -11,6 +11,7 @@ import numpy as np
 ELEMENTS = {  # space name -> scalar components (UFC local order is component-blocked)
     "W": ("P2", "P2", "DG0", "DG0", "DG0"),
     "V": ("P2", "P2"),
+    "Vs": ("P2",),  # V.sub(0).collapse(): the stream-function space (fenics_fem.py:342)
     "Zc": ("P2", "P2", "P2"),
     "Zd": ("DG0", "DG0", "DG0"),
     "Q": ("P1",),

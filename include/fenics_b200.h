@@ -35,7 +35,8 @@ typedef enum {
   FX_SPACE_ZD = 3, /* (DG0)^3                                                                   */
   FX_SPACE_QT = 4, /* DG0                                                                       */
   FX_SPACE_V = 5,  /* (P2)^2, 12 local dofs (post-loop diagnostics)                             */
-  FX_NSPACES = 6
+  FX_SPACE_VS = 6, /* P2 scalar, 6 local dofs: V.sub(0).collapse() of stream_function()           */
+  FX_NSPACES = 7
 } fx_space;
 
 /* Slots of the coefficient ("state") table handed to the assembly calls: state[f] is a device
@@ -69,6 +70,10 @@ typedef enum {
   /* generic */
   FX_FORM_MASS_ZC = 1, /* inner(w,Pv)*dx on Zc  (dolfin project(), mass matrix)   */
   FX_FORM_MASS_Q,      /* on Q                                                     */
+  /* post-loop diagnostics: stream_function / comp_stream_function (lid-driven-cavity/fenics_fem.py:340-378) */
+  FX_FORM_STREAM_A = 10,      /* inner(grad(psi), grad(phi))*dx on VS                              */
+  FX_FORM_STREAM_L,           /* inner(u[1].dx(0) - u[0].dx(1), phi)*dx, u = velocity of FX_F_W1   */
+  FX_FORM_COMP_STREAM_L,      /* inner(rho*u[1].dx(0) - rho*u[0].dx(1), phi)*dx, rho = FX_F_RHO1   */
   /* cfg1: bilinear */
   FX_FORM_C1_A1 = 100, FX_FORM_C1_A2, FX_FORM_C1_A5, FX_FORM_C1_A7, FX_FORM_C1_A4,
   /* cfg1: linear */

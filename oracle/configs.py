@@ -57,8 +57,33 @@ def make_spaces(mesh, dofmaps=None):
     """function_spaces(mesh, 2) (lid-driven-cavity/fenics_fem.py:262-287): the spaces the loops use."""
     dm = dofmaps or {}
     comps = {"W": ["P2", "P2", "DG0", "DG0", "DG0"], "V": ["P2", "P2"], "Zc": ["P2"] * 3,
-             "Zd": ["DG0"] * 3, "Q": ["P1"], "Qt": ["DG0"]}
+             "Zd": ["DG0"] * 3, "Q": ["P1"], "Qt": ["DG0"], "Vs": ["P2"]}
     return {k: fem.FunctionSpace(mesh, c, dm.get(k), name=k) for k, c in comps.items()}
+
+
+def stream_function(S, u, rho=None):
+    """stream_function(u) / comp_stream_function(rho, u) (lid-driven-cavity/fenics_fem.py:340-378) on
+    V.sub(0).collapse() = scalar P2: -lap(psi) = curl(u) [rho-weighted], psi = 0 on DomainBoundary(),
+    direct solve.  `u[1].dx(0) - u[0].dx(1)` is written grad(u)[1,0] - grad(u)[0,1] (same UFL degree).
+    Returns (psi dof vector, A, b)."""
+    Vs = S["Vs"]
+    psi, phi = fem.TrialFunction(Vs), fem.TestFunction(Vs)
+    gu = grad(u)
+    a = inner(grad(psi), grad(phi)) * dx
+    if rho is None:
+        L = inner(gu[1, 0] - gu[0, 1], phi) * dx
+    else:
+        L = inner(rho * gu[1, 0] - rho * gu[0, 1], phi) * dx
+    A, b = fem.assemble(a), fem.assemble(L)
+    bc = fem.DirichletBC(Vs, (0,), 0.0, lambda x: np.ones(len(x), dtype=bool))
+    bc.apply(A, b)
+    return fem.solve_lu(A, b), a, L
+
+
+def min_location(vec, space):
+    """min_location(u, mesh) (fenics_fem.py:402-417): coordinates of the dofs holding the minimum."""
+    xy = space.tabulate_dof_coordinates()
+    return xy[np.where(vec == vec.min())]
 
 
 def lid_boundary_conditions(W, L=1.0):

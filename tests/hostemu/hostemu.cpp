@@ -104,7 +104,7 @@ void* emu_plan_create(const double* xy, int nv, const int* cells, int nc, const 
   std::string err;
   for (int s = 0; s < S_N; ++s) {
     if (!cell_dofs[s]) continue;
-    const bool want = (s == S_W || s == S_ZC || s == S_Q || s == S_V);
+    const bool want = (s == S_W || s == S_ZC || s == S_Q || s == S_V || s == S_VS);
     if (!build_pattern(cell_dofs[s], nc, space_ld(s), want, P->pat[s], err)) {
       std::fprintf(stderr, "emu_plan_create: %s\n", err.c_str());
       delete P;

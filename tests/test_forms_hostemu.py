@@ -121,3 +121,18 @@ def test_lps_projections_and_functionals(kind):
         brho = plan.assemble_vector(abi.FX_FORM_C2_L_RHO1, "Q", st, par)
         ref = fem.assemble(inner(fem.TestFunction(cfg.S["Q"]), cfg.rho1_expr) * dx)
         assert lc.rel_err(brho, ref) < TOL
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_stream_function_forms(shuffle):
+    """stream_function / comp_stream_function (lid-driven-cavity/fenics_fem.py:340-378) on the scalar P2
+    space V.sub(0).collapse()."""
+    mesh, cfg, plan = _setup(2, shuffle=shuffle)
+    st, par = lc.state_of(cfg), lc.params_of(cfg)
+    for rho, fid in ((None, abi.FX_FORM_STREAM_L), (cfg.rho1.expr(), abi.FX_FORM_COMP_STREAM_L)):
+        _, a, L = configs.stream_function(cfg.S, cfg.u1, rho)
+        assert lc.csr_rel_err(plan.assemble_matrix(abi.FX_FORM_STREAM_A, "Vs", st, par), fem.assemble(a)) < TOL
+        assert lc.rel_err(plan.assemble_vector(fid, "Vs", st, par), fem.assemble(L)) < TOL
+        for form, f in ((a, abi.FX_FORM_STREAM_A), (L, fid)):
+            degs = {k: d for k, _, d in fem.quadrature_degrees(form, mesh)}
+            assert plan.form_qdeg(f)[0] == degs["dx"], (f, plan.form_qdeg(f), degs)

@@ -322,6 +322,27 @@ def test_extrapolated_initial_guess_same_solution_fewer_iterations():
     assert ib < ia, (ia, ib)
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+def test_stream_function_and_min_location(kind):
+    """post-loop diagnostics of the cavity scripts (incomp_LDC.py:457-460, comp_LDC_mesh_convergence.py:
+    604-607): psi within 1e-8, eye of the vortex at the same dof."""
+    ocl, drv = _pair(kind, n=10)
+    for o in (ocl, drv):
+        o.t = 0.45
+        o.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    for _ in range(3):
+        ocl.step()
+        drv.step()
+    rho = ocl.rho1.expr() if kind == 2 else None
+    psi_o, _, _ = configs.stream_function(ocl.S, ocl.u1, rho)
+    psi = drv.stream_function(compressible=(kind == 2))
+    assert lc.rel_err(psi.vector().get_local(), psi_o) < 1e-8
+    lo, ld = configs.min_location(psi_o, ocl.S["Vs"]), drv.min_location(psi)
+    assert lo.shape == ld.shape and np.allclose(lo, ld, atol=0, rtol=0)
+    assert 0.2 < ld[0][0] < 0.8 and 0.5 < ld[0][1] < 1.0  # the primary vortex sits under the lid
+
+
 def test_full_size_properties():
     """n=192 (999 558 DOFs, BASELINE.json): size-independent identities."""
     m = pmesh.Skew_Mesh(192, 1, 1)
