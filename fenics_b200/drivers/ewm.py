@@ -63,7 +63,7 @@ class EwmJBP(FenepmpJBP):
                      method=self.pressure_method, pc=self._pressure_pc())                                                       # :586-598
         self._system("rho1", A.FX_FORM_C3_A6, A.FX_FORM_C3_L6, self.AQ, self.bQ, self.rho1, ())        # :603-615
         self._system("u1", A.FX_FORM_C3_A7, A.FX_FORM_C3_L7, self.AW, self.bW, self.w1, self.bcu,
-                     rtol=min(self.direct_rtol, self.solve_rtol))                                       # :617-629
+                     rtol=self.direct_rtol if self.solve_rtol is None else min(self.direct_rtol, self.solve_rtol))                                       # :617-629
         self._system("T", A.FX_FORM_C3_A9, A.FX_FORM_C3_L9, self.AQ, self.bQ, self.T1, self.bcT)       # :641-656
         if self.p["We"] > 0.00001 or self.prepass:                                                      # :660
             self._system("tau", A.FX_FORM_C3_A4, A.FX_FORM_C3_L4, self.AZ, self.bZ, self.tau1_vec, ())  # :663-677
