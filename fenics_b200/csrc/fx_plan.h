@@ -44,7 +44,7 @@ struct DevPattern {
 
 constexpr int KRYLOV_NWORK = 12;
 constexpr int COARSE_KMAX = 256;   // aggregates of the two-level preconditioner
-constexpr int COARSE_NLMAX = 48;   // aggregates one CTA of the resident CG kernel may touch
+constexpr int COARSE_NLMAX = 64;   // aggregates one CTA of the resident CG kernel may touch
 constexpr int RED_SLOTS = 4;       // values reduced at once
 constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
 
