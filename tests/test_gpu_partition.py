@@ -16,11 +16,14 @@ if not torch.cuda.is_available():
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_partitioned_cfg2_matches_single_gpu():
+@pytest.mark.parametrize("cfg,port", [("cfg2", 29611), ("cfg4", 29612), ("cfg5", 29613)])
+def test_partitioned_matches_single_gpu(cfg, port):
+    """fields, energies and the boundary functionals (journal torque / load, Nusselt number) of the
+    partitioned drivers against the single-GPU drivers."""
     world = 2 if torch.cuda.device_count() >= 2 else 1
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dist_check.py"),
-           "12", "3"]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"),
+           "10", "2", "0", cfg]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
