@@ -57,6 +57,9 @@ def _load():
         "fx_plan_set_owned_cells": (i, [vp, i]),
         "fx_plan_set_eliminated_dofs": (i, [vp, i, vp, i]),
         "fx_plan_set_aggregates": (i, [vp, i, vp, i]),
+        "fx_peer_region_bytes": (C.c_longlong, [C.c_longlong]),
+        "fx_plan_set_peer_regions": (i, [vp, i, i, vp, C.c_longlong]),
+        "fx_plan_set_halo": (i, [vp, i, i, vp, vp, vp, vp]),
         "fx_krylov_solve": (i, [vp, i, vp, vp, vp, i, i, d, d, i, C.POINTER(SolveInfo), vp]),
         "fx_krylov_solve_async": (i, [vp, i, vp, vp, vp, i, i, d, d, i, i, vp]),
         "fx_solve_results": (i, [vp, i, i, C.POINTER(SolveInfo), vp]),

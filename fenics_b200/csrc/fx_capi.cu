@@ -159,6 +159,7 @@ void fx_plan_destroy(fx_plan* P) {
   for (int s = 0; s < S_N; ++s) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
     cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows); cudaFree(P->sp[s].agg);
+    cudaFree(P->sp[s].s_first); cudaFree(P->sp[s].s_peer); cudaFree(P->sp[s].s_local); cudaFree(P->sp[s].s_remote);
   }
   cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
@@ -308,25 +309,99 @@ int fx_plan_set_owned_cells(fx_plan* P, int nc_owned) {
   return FX_OK;
 }
 
+// device row mask of a space = eliminated rows (bit 0) | ghost rows (bit 1) | interface rows (bit 2)
+static int rebuild_mask(DevPattern& d) {
+  cudaFree(d.elim);
+  d.elim = nullptr;
+  if (d.elim_h.empty() && d.halo_h.empty()) return FX_OK;
+  std::vector<uint8_t> m((size_t)d.n, 0);
+  for (int i = 0; i < d.n; ++i)
+    m[i] = (d.elim_h.empty() ? 0 : d.elim_h[i]) | (d.halo_h.empty() ? 0 : d.halo_h[i]);
+  FX_CUDA(cudaMalloc((void**)&d.elim, (size_t)d.n));
+  FX_CUDA(cudaMemcpy(d.elim, m.data(), (size_t)d.n, cudaMemcpyHostToDevice));
+  return FX_OK;
+}
+
 int fx_plan_set_eliminated_dofs(fx_plan* P, int space, const int* rows, int n) {
   if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr || n < 0 || (n > 0 && !rows))
     return set_error(FX_ERR_ARG, "fx_plan_set_eliminated_dofs: bad argument");
   DevPattern& d = P->sp[space];
-  cudaFree(d.elim); cudaFree(d.elim_rows);
-  d.elim = nullptr; d.elim_rows = nullptr; d.nelim = 0;
-  if (n == 0) return FX_OK;
-  std::vector<uint8_t> mask((size_t)d.n, 0);
-  for (int i = 0; i < n; ++i) {
-    if (rows[i] < 0 || rows[i] >= d.n || mask[rows[i]])
-      return set_error(FX_ERR_ARG, "fx_plan_set_eliminated_dofs: row %d out of range or repeated", rows[i]);
-    mask[rows[i]] = 1;
+  cudaFree(d.elim_rows);
+  d.elim_rows = nullptr; d.nelim = 0;
+  d.elim_h.clear();
+  if (n > 0) {
+    std::vector<uint8_t> mask((size_t)d.n, 0);
+    for (int i = 0; i < n; ++i) {
+      if (rows[i] < 0 || rows[i] >= d.n || mask[rows[i]])
+        return set_error(FX_ERR_ARG, "fx_plan_set_eliminated_dofs: row %d out of range or repeated", rows[i]);
+      mask[rows[i]] = 1;
+    }
+    d.elim_h.swap(mask);
+    FX_CUDA(cudaMalloc((void**)&d.elim_rows, sizeof(int) * (size_t)n));
+    FX_CUDA(cudaMemcpy(d.elim_rows, rows, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    d.nelim = n;
   }
-  FX_CUDA(cudaMalloc((void**)&d.elim, (size_t)d.n));
-  FX_CUDA(cudaMalloc((void**)&d.elim_rows, sizeof(int) * (size_t)n));
-  FX_CUDA(cudaMemcpy(d.elim, mask.data(), (size_t)d.n, cudaMemcpyHostToDevice));
-  FX_CUDA(cudaMemcpy(d.elim_rows, rows, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-  d.nelim = n;
+  return rebuild_mask(d);
+}
+
+long long fx_peer_region_bytes(long long nmax) {
+  return nmax < 0 ? 0 : (long long)sizeof(double) * dist_region_doubles(nmax);
+}
+
+int fx_plan_set_peer_regions(fx_plan* P, int rank, int world, void* const* regions, long long nmax) {
+  if (!P || world < 0 || world > DIST_MAXW || (world > 1 && (rank < 0 || rank >= world || !regions || nmax < 1)))
+    return set_error(FX_ERR_ARG, "fx_plan_set_peer_regions: bad argument (world <= %d)", DIST_MAXW);
+  P->dist = DistDev();
+  if (world <= 1) return FX_OK;
+  for (int q = 0; q < world; ++q) {
+    if (!regions[q]) return set_error(FX_ERR_ARG, "fx_plan_set_peer_regions: region %d is null", q);
+    P->dist.region[q] = static_cast<double*>(regions[q]);
+  }
+  P->dist.rank = rank; P->dist.world = world; P->dist.nmax = nmax;
   return FX_OK;
+}
+
+int fx_plan_set_halo(fx_plan* P, int space, int nsend, const int* peer, const int* local, const int* remote,
+                     const unsigned char* ghost) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr || nsend < 0 || (nsend > 0 && (!peer || !local || !remote)))
+    return set_error(FX_ERR_ARG, "fx_plan_set_halo: bad argument");
+  DevPattern& d = P->sp[space];
+  cudaFree(d.s_first); cudaFree(d.s_peer); cudaFree(d.s_local); cudaFree(d.s_remote);
+  d.s_first = d.s_peer = d.s_local = d.s_remote = nullptr;
+  d.nsend = 0; d.has_halo = false;
+  d.halo_h.clear();
+  if (!ghost) return rebuild_mask(d);  // halo removed
+  std::vector<uint8_t> m((size_t)d.n, 0);
+  for (int i = 0; i < d.n; ++i) m[i] = ghost[i] ? 2 : 0;
+  // sort the (dof, destination) pairs by dof; the last pair of a dof carries DIST_LAST
+  std::vector<int> order(nsend);
+  for (int k = 0; k < nsend; ++k) {
+    order[k] = k;
+    if (local[k] < 0 || local[k] >= d.n || ghost[local[k]] || peer[k] < 0 || peer[k] >= DIST_MAXW || remote[k] < 0)
+      return set_error(FX_ERR_ARG, "fx_plan_set_halo: pair %d (dof %d -> rank %d slot %d) is invalid", k, local[k], peer[k], remote[k]);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return local[a] < local[b]; });
+  std::vector<int> first((size_t)d.n, -1), hp(nsend), hl(nsend), hr(nsend);
+  for (int k = 0; k < nsend; ++k) {
+    const int o = order[k];
+    hl[k] = local[o]; hr[k] = remote[o]; hp[k] = peer[o];
+    if (first[hl[k]] < 0) first[hl[k]] = k;
+    m[hl[k]] |= 4;
+    if (k + 1 == nsend || local[order[k + 1]] != hl[k]) hp[k] |= DIST_LAST;
+  }
+  FX_CUDA(cudaMalloc((void**)&d.s_first, sizeof(int) * (size_t)d.n));
+  FX_CUDA(cudaMemcpy(d.s_first, first.data(), sizeof(int) * (size_t)d.n, cudaMemcpyHostToDevice));
+  if (nsend > 0) {
+    FX_CUDA(cudaMalloc((void**)&d.s_peer, sizeof(int) * (size_t)nsend));
+    FX_CUDA(cudaMalloc((void**)&d.s_local, sizeof(int) * (size_t)nsend));
+    FX_CUDA(cudaMalloc((void**)&d.s_remote, sizeof(int) * (size_t)nsend));
+    FX_CUDA(cudaMemcpy(d.s_peer, hp.data(), sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+    FX_CUDA(cudaMemcpy(d.s_local, hl.data(), sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+    FX_CUDA(cudaMemcpy(d.s_remote, hr.data(), sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+  }
+  d.nsend = nsend; d.has_halo = true;
+  d.halo_h.swap(m);
+  return rebuild_mask(d);
 }
 
 int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void* stream) {

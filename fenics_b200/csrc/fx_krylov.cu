@@ -41,6 +41,7 @@ struct Coarse {
 };
 
 struct KArgs {
+  DistDev dd;  // mesh-partitioned run (world > 1): peer-mapped work regions, halo push lists
   Coarse cz;
   int prof;
   CsrView A;
@@ -58,8 +59,8 @@ struct KArgs {
 // Deterministic grid-wide sum of NV values: block partials -> scratch -> grid barrier -> every CTA sums
 // all partials in the same order (bitwise identical result in every CTA).  `phase` alternates the
 // scratch half so a fast CTA cannot overwrite partials a slow CTA is still reading.
-template <int NV>
-__device__ __forceinline__ void grid_sum(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
+template <int NV, class Bar>
+__device__ __forceinline__ void grid_sum(Bar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
   double* buf = red + (size_t)(phase & 1) * RED_SLOTS * MAX_GRID;
   block_sum_bcast_n<NV>(v, sh);
   if (threadIdx.x == 0) {
@@ -83,8 +84,8 @@ __device__ __forceinline__ void grid_sum(GridBar& bar, double (&v)[NV], double* 
 // varies from run to run (last-bit differences), but every CTA reads the same totals, so control flow
 // stays uniform.  Accumulator (phase+1)%3 is cleared by CTA 0 before it arrives: everybody finished
 // reading it before arriving at the previous barrier, and nobody adds to it until this barrier opens.
-template <int NV>
-__device__ __forceinline__ void grid_sum_atomic(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
+template <int NV, class Bar>
+__device__ __forceinline__ void grid_sum_atomic(Bar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
   double* acc = red + (size_t)2 * RED_SLOTS * MAX_GRID;  // [3][RED_SLOTS]
   double* cur = acc + (phase % 3) * RED_SLOTS;
   block_sum_bcast_n<NV>(v, sh);
@@ -93,15 +94,40 @@ __device__ __forceinline__ void grid_sum_atomic(GridBar& bar, double (&v)[NV], d
     if (threadIdx.x == i) atomicAdd(cur + i, v[i]);
   if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + RED_SLOTS)
     acc[((phase + 1) % 3) * RED_SLOTS + threadIdx.x - 32] = 0.0;
-  bar.sync();
+  if (!bar.dist()) {
+    bar.sync();
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = __ldcg(cur + i);
+    for (int i = 0; i < NV; ++i) v[i] = __ldcg(cur + i);
+  } else {
+    // partitioned run: CTA 0 hands this GPU's totals to every peer (P2P stores into their regions) between
+    // the local and the cross-GPU part of the barrier; everybody then adds the per-rank totals in rank
+    // order, so all GPUs hold bitwise identical sums and take the same branches.  The own total is read
+    // from the local accumulator: it is complete when the local part of the barrier opens, whereas CTA 0's
+    // payload may still be running when the peers' flags (the only other thing a CTA waits for) are in.
+    const DistDev& dd = *bar.dd;
+    bar.sync_with([&] {
+      const long long slot = dist_xred_off(dd.nmax) + (long long)((bar.xepoch & 1ull) * DIST_MAXW + dd.rank) * RED_SLOTS;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const double t = __ldcg(cur + i);
+        for (int q = 0; q < dd.world; ++q)
+          if (q != dd.rank) dd.region[q][slot + i] = t;
+      }
+    });
+    const double* mine = dd.region[dd.rank] + dist_xred_off(dd.nmax) + (long long)(bar.xepoch & 1ull) * DIST_MAXW * RED_SLOTS;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = 0.0;
+      for (int q = 0; q < dd.world; ++q) t += __ldcg(q == dd.rank ? cur + i : mine + q * RED_SLOTS + i);
+      v[i] = t;
+    }
+  }
   ++phase;
 }
 
-template <int NV>
-__device__ __forceinline__ void gsum(const KArgs& a, GridBar& bar, double (&v)[NV], int& phase, double* sh) {
-  if (a.red_atomic) grid_sum_atomic<NV>(bar, v, a.red, phase, sh);
+template <int NV, class Bar>
+__device__ __forceinline__ void gsum(const KArgs& a, Bar& bar, double (&v)[NV], int& phase, double* sh) {
+  if (a.red_atomic || bar.dist()) grid_sum_atomic<NV>(bar, v, a.red, phase, sh);
   else grid_sum<NV>(bar, v, a.red, phase, sh);
 }
 
@@ -116,16 +142,35 @@ __device__ __forceinline__ void finish(const KArgs& a, int it, int conv, double 
 
 // Leaving a solve: record the outcome, then recover the eliminated rows from the final x.  Every CTA
 // takes the same exit (deterministic reductions), so the barrier is safe.
-__device__ __forceinline__ void leave(GridBar& bar, const KArgs& a, int it, int conv, double rn, double bn) {
-  finish(a, it, conv, rn, bn);
-  if (a.A.elim != nullptr) {
+template <class Bar>
+__device__ __forceinline__ void leave(Bar& bar, const KArgs& a, int it, int conv, double rn, double bn) {
+  finish(a, it, bar.dead ? -4 : conv, rn, bn);
+  if (bar.dist()) {
+    // partitioned run: the solution's ghost entries are coefficients of the next forms.  Owners store their
+    // interface values into the neighbours' exchange slot (P2P), a barrier, ghosts copy them out.
+    // Eliminated rows are skipped: every rank back-substitutes the DG0 rows of its ghost cells itself
+    // (those rows are complete on the sub-mesh).
+    const DistDev& dd = a.dd;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    bar.sync();  // x is final on every rank
+    for (int k = gt; k < dd.nsend; k += gs) {
+      const int i = dd.s_local[k];
+      if (!(a.A.elim[i] & MASK_ELIM))
+        dd.region[dd.s_peer[k] & (DIST_MAXW - 1)][(long long)DIST_XH * dd.nmax + dd.s_remote[k]] = a.x[i];
+    }
+    bar.sync();
+    const double* xh = a.w + (size_t)DIST_XH * dd.nmax;
+    for (int i = gt; i < a.A.n; i += gs)
+      if ((a.A.elim[i] & MASK_INACTIVE) == MASK_GHOST) a.x[i] = __ldcg(xh + i);
+  }
+  if (a.A.elim != nullptr && a.A.nelim > 0) {
     bar.sync();
     if (back_substitute(a.A, a.x, a.b) != 0) a.info->converged = -3;
   }
+  bar.save();
 }
-
 __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc) {
-  if (A.elim != nullptr && A.elim[row]) return 0.0;  // eliminated rows stay identically zero in the iteration
+  if (A.elim != nullptr && (A.elim[row] & MASK_INACTIVE)) return 0.0;  // eliminated / ghost rows stay identically zero in the iteration
   if (pc != FX_PC_JACOBI) return 1.0;
   double dg = 0.0;
   for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j)
@@ -144,7 +189,7 @@ struct Ops3 { double a, b, c; };
 // norm ||s - omega t|| without a reduction of their own, so x, r and the next search direction p are
 // updated in ONE pass over the vectors.  A residual that the recurrence reports as converged is
 // confirmed with a true norm before the solve returns.
-template <int THREADS>
+template <int THREADS, bool DIST>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __grid_constant__ KArgs a) {
   __shared__ double sh[4 * 33];
   __shared__ int sh_i[64];
@@ -152,16 +197,21 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  // work vectors (stride nmax in a partitioned run: the same vector sits at the same offset on every GPU);
+  // p (index 2) and s (index 4) are SpMV inputs: their ghost entries are written by the owners' halo pushes
+  // and never locally
+  const size_t ld = DIST ? (size_t)a.dd.nmax : (size_t)n;
+  const unsigned char* mask = DIST ? A.elim : nullptr;
   double* r = a.w;
-  double* rh = a.w + (size_t)n;
-  double* p = a.w + 2 * (size_t)n;
-  double* v = a.w + 3 * (size_t)n;
-  double* s = a.w + 4 * (size_t)n;
-  double* t = a.w + 5 * (size_t)n;
-  double* dinv = a.w + 6 * (size_t)n;
+  double* rh = a.w + ld;
+  double* p = a.w + 2 * ld;
+  double* v = a.w + 3 * ld;
+  double* s = a.w + 4 * ld;
+  double* t = a.w + 5 * ld;
+  double* dinv = a.w + 6 * ld;
   int phase = 0;
-  GridBar bar;
-  bar.init(a.bar);
+  GridBarT<DIST> bar;
+  bar.init(a.bar, &a.dd);
 
   // setup: compacted matrix, balanced partition, dinv, r = M^-1 (b - A x), rhat = p = r, v = 0
   double acc[3] = {0.0, 0.0, 0.0};
@@ -172,11 +222,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
                 [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
                 [&](int row, double ax, const Ops2& o) {
                   const double ri = o.a * (o.b - ax), bi = o.a * o.b;
-                  dinv[row] = o.a; r[row] = ri; rh[row] = ri; p[row] = ri; v[row] = 0.0;
+                  dinv[row] = o.a; r[row] = ri; rh[row] = ri; v[row] = 0.0;
+                  const unsigned char mk = mask != nullptr ? mask[row] : 0;
+                  if (!(mk & MASK_GHOST)) p[row] = ri;
+                  if (mk & MASK_IFACE) push_iface(a.dd, 2, row, ri);
                   acc[0] += ri * ri; acc[1] += bi * bi;
                 });
   gsum<3>(a, bar, acc, phase, sh);
-  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
+  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); bar.save(); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
   const double tol = fmax(a.rtol * bn, a.atol);
@@ -210,8 +263,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     const double alpha = rho / d1[0];
     double d2[1] = {0.0};
     for (int i = gt; i < n; i += gs) {
+      const unsigned char mk = mask != nullptr ? mask[i] : 0;
+      if (mk & MASK_GHOST) continue;
       const double si = r[i] - alpha * v[i];
       s[i] = si;
+      if (mk & MASK_IFACE) push_iface(a.dd, 4, i, si);
       d2[0] += si * si;
     }
     stamp(a.prof, np);
@@ -219,7 +275,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     stamp(a.prof, np);
     const double ss = d2[0];
     if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
-      for (int i = gt; i < n; i += gs) a.x[i] += alpha * p[i];
+      for (int i = gt; i < n; i += gs)
+        if (mask == nullptr || !(mask[i] & MASK_GHOST)) a.x[i] += alpha * p[i];
       leave(bar, a, it, 1, sqrt(ss), bn);
       return;
     }
@@ -251,11 +308,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     const bool check = rn <= 2.0 * tol;  // confirm with a true norm
     double d4[1] = {0.0};
     for (int i = gt; i < n; i += gs) {
+      const unsigned char mk = mask != nullptr ? mask[i] : 0;
+      if (mk & MASK_GHOST) continue;
       const double pi = p[i];
       a.x[i] += alpha * pi + omega * s[i];
       const double ri = s[i] - omega * t[i];
       r[i] = ri;
-      p[i] = ri + beta * (pi - omega * v[i]);
+      const double pn = ri + beta * (pi - omega * v[i]);
+      p[i] = pn;
+      if (mk & MASK_IFACE) push_iface(a.dd, 2, i, pn);
       if (restart) rh[i] = ri;
       d4[0] += ri * ri;
     }
@@ -278,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
 // u = M^-1 r, w = A u, p = u + beta p, s = w + beta s (= A p).  One SpMV and ONE fused reduction
 // (gamma = (r,u), delta = (w,u), ||u||^2) per iteration: two grid barriers instead of three.
 // Monitored norm ||M^-1 r||_2 (PETSc default for KSPCG).
-template <int THREADS>
+template <int THREADS, bool DIST>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_constant__ KArgs a) {
   __shared__ double sh[4 * 33];
   __shared__ int sh_i[64];
@@ -286,15 +347,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   const CsrView& A = a.A;
   const int n = A.n;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  // u (index 1) is the SpMV input: its ghost entries come from the owners' halo pushes (partitioned run)
+  const size_t ld = DIST ? (size_t)a.dd.nmax : (size_t)n;
+  const unsigned char* mask = DIST ? A.elim : nullptr;
   double* r = a.w;
-  double* u = a.w + (size_t)n;
-  double* w = a.w + 2 * (size_t)n;
-  double* p = a.w + 3 * (size_t)n;
-  double* s = a.w + 4 * (size_t)n;
-  double* dinv = a.w + 5 * (size_t)n;
+  double* u = a.w + ld;
+  double* w = a.w + 2 * ld;
+  double* p = a.w + 3 * ld;
+  double* s = a.w + 4 * ld;
+  double* dinv = a.w + 5 * ld;
   int phase = 0;
-  GridBar bar;
-  bar.init(a.bar);
+  GridBarT<DIST> bar;
+  bar.init(a.bar, &a.dd);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   acc[3] = (double)compact_zeros(A);
   bar.sync();
@@ -303,11 +367,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                 [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
                 [&](int row, double ax, const Ops2& o) {
                   const double ri = o.b - ax, ui = o.a * ri, bi = o.a * o.b;
-                  dinv[row] = o.a; r[row] = ri; u[row] = ui; p[row] = 0.0; s[row] = 0.0;
+                  dinv[row] = o.a; r[row] = ri; p[row] = 0.0; s[row] = 0.0;
+                  const unsigned char mk = mask != nullptr ? mask[row] : 0;
+                  if (!(mk & MASK_GHOST)) u[row] = ui;
+                  if (mk & MASK_IFACE) push_iface(a.dd, 1, row, ui);
                   acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
                 });
   gsum<4>(a, bar, acc, phase, sh);
-  if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }
+  if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); bar.save(); return; }
   double gamma = acc[0], un = sqrt(acc[1]);
   const double bn = sqrt(acc[2]);
   const double tol = fmax(a.rtol * bn, a.atol);
@@ -325,6 +392,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   for (int it = 1; it <= a.maxit; ++it) {
     double d[3] = {0.0, 0.0, 0.0};
     for (int i = gt; i < n; i += gs) {
+      const unsigned char mk = mask != nullptr ? mask[i] : 0;
+      if (mk & MASK_GHOST) continue;
       const double pi = u[i] + beta * p[i];
       const double si = w[i] + beta * s[i];
       p[i] = pi; s[i] = si;
@@ -333,6 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
       r[i] = ri;
       const double ui = dinv[i] * ri;
       u[i] = ui;
+      if (mk & MASK_IFACE) push_iface(a.dd, 1, i, ui);
       d[0] += ri * ui;
       d[1] += ui * ui;
     }
@@ -469,7 +539,7 @@ __device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k,
 template <int R>
 __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant__ KArgs a) {
   GridBar bar;
-  bar.init(a.bar);
+  bar.init(a.bar, &a.dd);
   __shared__ double sh[3 * 33];
   extern __shared__ __align__(16) unsigned char dyn[];
   const CsrView& A = a.A;
@@ -825,12 +895,24 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
       (method != FX_KSP_CG || p.nagg == 0 || rtol < 1e-9 || p.nelim != 0 || !pcg_resident_config(P, p.nrowblk, &grid1)))
     return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates), "
                      "rtol >= 1e-9 and a system that fits the resident CG kernel");
+  const bool part = P->dist.world > 1;  // mesh-partitioned run: fused halo pushes + cross-GPU barriers
+  if (part && !p.has_halo)
+    return set_error(FX_ERR_ARG, "partitioned plan: space %d has no halo (fx_plan_set_halo)", space);
+  if (part && (size_t)p.n > (size_t)P->dist.nmax)
+    return set_error(FX_ERR_ARG, "partitioned plan: space %d has %d dofs, peer regions hold %lld", space, p.n, P->dist.nmax);
+  if (part && pc == FX_PC_JACOBI_COARSE)
+    return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse is not available on a partitioned plan");
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
   ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->cdesc, P->cre, P->ccol, P->cval,
-                 p.nelim > 0 ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart};
+                 (p.nelim > 0 || part) ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart};
   ka.bar = P->bar;
+  ka.dd = P->dist;
+  if (part) {
+    ka.dd.nsend = p.nsend; ka.dd.s_first = p.s_first; ka.dd.s_peer = p.s_peer;
+    ka.dd.s_local = p.s_local; ka.dd.s_remote = p.s_remote;
+  }
   ka.cz = Coarse{nullptr, 0, nullptr, nullptr, nullptr};
   if (pc == FX_PC_JACOBI_COARSE)
     ka.cz = Coarse{p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX * COARSE_KMAX,
@@ -841,11 +923,11 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   static const int red_env = getenv("FX_RED_ATOMIC") ? atoi(getenv("FX_RED_ATOMIC")) : 1;
   ka.red_atomic = red_env;
   if (red_env) FX_CUDA(cudaMemsetAsync(P->red + (size_t)2 * RED_SLOTS * MAX_GRID, 0, sizeof(double) * 3 * RED_SLOTS, st));
-  ka.x = x; ka.b = b; ka.w = P->work; ka.red = P->red;
+  ka.x = x; ka.b = b; ka.w = part ? P->dist.region[P->dist.rank] : P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
-  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0) {
+  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part) {
     const int warps = P->num_sms * LA_WARPS;
     const int R = (p.nrowblk + warps - 1) / warps;
     if (R <= PCG_MAXR) {
@@ -858,12 +940,13 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   // big CTAs (1024 threads, one per SM) keep the grid barrier cheap: its cost grows with the number of
   // arriving CTAs, and every iteration crosses four of them
   static const int threads_env = getenv("FX_KRYLOV_THREADS") ? atoi(getenv("FX_KRYLOV_THREADS")) : 1024;
-  const int threads = threads_env == 256 ? 256 : 1024;
-  void* fn = method == FX_KSP_CG ? (threads == 256 ? (void*)k_cg<256> : (void*)k_cg<1024>)
-                                 : (threads == 256 ? (void*)k_bicgstab<256> : (void*)k_bicgstab<1024>);
+  const int threads = (threads_env == 256 && !part) ? 256 : 1024;
+  void* fn = method == FX_KSP_CG ? (threads == 256 ? (void*)k_cg<256, false> : (void*)k_cg<1024, false>)
+                                 : (threads == 256 ? (void*)k_bicgstab<256, false> : (void*)k_bicgstab<1024, false>);
+  if (part) fn = method == FX_KSP_CG ? (void*)k_cg<1024, true> : (void*)k_bicgstab<1024, true>;
   const size_t smem = sizeof(double) * (threads / 32) * SPMV_NNZB;
-  static bool attr_done[4] = {false, false, false, false};
-  const int ai = (method == FX_KSP_CG ? 0 : 1) + (threads == 256 ? 0 : 2);
+  static bool attr_done[6] = {false, false, false, false, false, false};
+  const int ai = (method == FX_KSP_CG ? 0 : 1) + (part ? 4 : (threads == 256 ? 0 : 2));
   if (!attr_done[ai]) {
     FX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[ai] = true;

@@ -85,8 +85,10 @@ struct CsrView {
   int* re;      // [n] one past the last entry of row (rows of a block are stored back to back)
   int* col2;
   double* val2;
-  // block-triangular elimination (null = off): rows with elim[row] != 0 are left out of the Krylov
-  // iteration and recovered by back_substitute(); requires A[active, eliminated] == 0
+  // per-row mask (null = none): MASK_ELIM rows are left out of the Krylov iteration and recovered by
+  // back_substitute() (requires A[active, eliminated] == 0); MASK_GHOST rows belong to another rank of a
+  // partitioned run (empty in the compacted copy, their vector entries arrive by halo pushes);
+  // MASK_IFACE marks owned rows some neighbour holds as ghosts
   const unsigned char* elim;
   const int* elim_rows;
   int nelim;
@@ -94,30 +96,117 @@ struct CsrView {
   int* blkprefix;  // [nrowblk + 1] exclusive prefix of the per-block cost
   int* scanpart;   // [gridDim] scratch of the scan
 };
+constexpr unsigned char MASK_ELIM = 1, MASK_GHOST = 2, MASK_IFACE = 4, MASK_INACTIVE = MASK_ELIM | MASK_GHOST;
+
+// ---- mesh-partitioned runs: peer-mapped symmetric regions (one per GPU, same layout) -------------------
+// Every rank's Krylov work vectors, cross-GPU reduction slots and barrier flags live in a region that all
+// peers map over NVLink (fx_plan_set_peer_regions; torch symmetric memory on the host side).  The
+// persistent Krylov kernels then do their own halo exchange (P2P stores of interface values straight into
+// the neighbour's copy of the same work vector, issued by the thread that computed the value), their own
+// cross-GPU reductions and barriers: no NCCL call and no host round trip inside a solve.
+// value `val` of interface dof i of work vector j -> the ghost slot of every neighbour that reads it
+__device__ __forceinline__ void push_iface(const DistDev& dd, int j, int i, double val) {
+  int k = dd.s_first[i];
+  for (;;) {
+    const int pe = dd.s_peer[k];
+    dd.region[pe & (DIST_MAXW - 1)][(long long)j * dd.nmax + dd.s_remote[k]] = val;
+    if (pe & DIST_LAST) break;
+    ++k;
+  }
+}
 
 // Grid barrier for cooperative (co-resident) launches.  Unlike cooperative_groups' grid.sync(), whose
 // waiting thread polls with ld.acquire -- every poll invalidates the SM's whole L1 (CCTL.IVALL), which
 // evicts the x-gather lines of the CTAs still working on that SM -- the wait here polls with relaxed
 // loads and acquires once.  Monotonic counter, zeroed by the host before every launch.
-struct GridBar {
+// With a DistDev of world > 1 the barrier spans the GPUs of the partition: when all local CTAs have
+// arrived, CTA 0 runs an optional payload (the cross-GPU part of a reduction), then raises this rank's
+// epoch flag in every peer's region; every CTA waits for the local counter AND the peers' flags.  Epochs
+// are 64-bit and continue across solves (persisted in the region), so stale flags never match.  A peer
+// that never arrives (a rank died) trips a 10 s timeout: the barrier goes dead (all later waits fall
+// through) and the solve reports converged = -4 instead of hanging the GPU.
+template <bool DIST>
+struct GridBarT {
   unsigned* ctr;
   unsigned target;
-  __device__ __forceinline__ void init(unsigned* c) { ctr = c; target = 0; }
-  __device__ __forceinline__ void sync() {
+  const DistDev* dd;
+  unsigned long long xepoch;
+  bool dead;
+  __device__ __forceinline__ constexpr bool dist() const { return DIST; }
+  __device__ __forceinline__ unsigned long long* xflags(int q) const {
+    return reinterpret_cast<unsigned long long*>(dd->region[q] + dist_flag_off(dd->nmax));
+  }
+  __device__ __forceinline__ void init(unsigned* c, const DistDev* d = nullptr) {
+    ctr = c; target = 0; dd = d; xepoch = 0; dead = false;
+    if (dist()) {
+      const unsigned long long* st = reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax));
+      xepoch = __ldcg(st);
+      dead = __ldcg(st + 1) != 0;
+    }
+  }
+  // persist the epoch for the next solve (every exit path, block 0 / thread 0)
+  __device__ __forceinline__ void save() const {
+    if (dist() && blockIdx.x == 0 && threadIdx.x == 0)
+      *reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax)) = xepoch;
+  }
+  template <class Payload>
+  __device__ __forceinline__ void sync_with(Payload&& payload) {
     target += gridDim.x;
+    const bool x = dist();
+    if (x) ++xepoch;
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();  // release: everything this CTA wrote (bar.sync above orders the other threads' stores)
+      if (x) __threadfence_system(); else __threadfence();  // release everything this CTA wrote
       atomicAdd(ctr, 1u);
       unsigned v;
+      if (x && blockIdx.x == 0) {
+        do {
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence_system();  // all local CTAs' writes (halo pushes, reduction atomics) are ordered before ...
+        payload();
+        __threadfence_system();  // ... this rank's flag in every peer's region
+        for (int q = 0; q < dd->world; ++q)
+          if (q != dd->rank)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(xflags(q) + dd->rank), "l"(xepoch) : "memory");
+      }
       do {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       } while ((int)(v - target) < 0);
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (x) {
+        unsigned long long t0 = 0, f;
+        unsigned long long* deadflag = reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax)) + 1;
+        for (int q = 0; q < dd->world && !dead; ++q) {
+          if (q == dd->rank) continue;
+          const unsigned long long* fp = xflags(dd->rank) + q;
+          unsigned spins = 0;
+          for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fp) : "memory");
+            if ((long long)(f - xepoch) >= 0) break;
+            if ((++spins & 0x3ffu) == 0) {
+              if (__ldcg(deadflag) != 0) { dead = true; break; }  // another CTA gave up: all give up together
+              unsigned long long now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 10000000000ull) { dead = true; *deadflag = 1ull; break; }
+            }
+          }
+          // acquire on the flag itself: pairs with the peer's fence + flag store
+          if (!dead) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fp) : "memory");
+        }
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      } else {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      }
     }
-    __syncthreads();
+    if (x) dead = __syncthreads_or(dead);
+    else __syncthreads();
+  }
+  __device__ __forceinline__ void sync() {
+    sync_with([] {});
   }
 };
+typedef GridBarT<false> GridBar;
 
 // The warp processes row blocks k0, k0+kstep, ... < k1.
 struct BlockRange {
@@ -146,13 +235,13 @@ __device__ __forceinline__ int compact_zeros(const CsrView& A) {
     int b = 0, e = 0, cnt = 0;
     if (act) {
       b = A.rowptr[row]; e = A.rowptr[row + 1];
-      if (A.elim != nullptr && A.elim[row]) {
-        e = b;  // eliminated row: empty
+      if (A.elim != nullptr && (A.elim[row] & MASK_INACTIVE)) {
+        e = b;  // eliminated or ghost row: empty
       } else if (A.elim != nullptr) {
         for (int j = b; j < e; ++j) {
           const bool nz = A.val[j] != 0.0;
           cnt += nz;
-          bad += (nz && A.elim[A.col[j]]);
+          bad += (nz && (A.elim[A.col[j]] & MASK_ELIM));
         }
       } else {
         for (int j = b; j < e; ++j) cnt += (A.val[j] != 0.0);
@@ -188,7 +277,8 @@ constexpr int BLOCK_OVERHEAD_NNZ = 192;
 // ahead of others (5 vs 6 blocks at n=192: every barrier waits ~20 % for the stragglers).
 // Distributed scan: each CTA sums its chunk of blocks, a barrier, offsets from the CTAs before it, a
 // barrier, then two binary searches per warp.  sh_i: 64 ints of shared memory.
-__device__ __forceinline__ BlockRange balance_partition(const CsrView& A, GridBar& bar, int* sh_i) {
+template <class Bar>
+__device__ __forceinline__ BlockRange balance_partition(const CsrView& A, Bar& bar, int* sh_i) {
   const int nb = A.nrowblk, G = gridDim.x, wpb = blockDim.x >> 5;
   const int L = (nb + G - 1) / G;
   const int c0 = min(nb, (int)blockIdx.x * L), c1 = min(nb, c0 + L);
@@ -268,7 +358,7 @@ __device__ __forceinline__ int back_substitute(const CsrView& A, double* x, cons
         const int c = A.col[j];
         const double v = A.val[j];
         if (c == row) dg = v;
-        else if (v != 0.0) { s += v * x[c]; bad += A.elim[c]; }
+        else if (v != 0.0) { s += v * x[c]; bad += (A.elim[c] & MASK_ELIM); }
       }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {

@@ -37,9 +37,28 @@ struct DevPattern {
   std::vector<int> rowblk_h;  // host copy of rowblk
   int* agg = nullptr;         // [n] aggregate of each dof (fx_plan_set_aggregates), null = none
   int nagg = 0;
-  uint8_t* elim = nullptr;    // [n] 1 = eliminated row
+  uint8_t* elim = nullptr;    // [n] row mask: bit 0 eliminated, bit 1 ghost, bit 2 interface (fx_la_common.cuh MASK_*)
   int* elim_rows = nullptr;   // [nelim]
   int nelim = 0;
+  std::vector<uint8_t> elim_h, halo_h;  // host copies of the two mask sources (rebuild_mask)
+  // halo push lists of a partitioned run (fx_plan_set_halo), sorted by local dof
+  bool has_halo = false;
+  int nsend = 0;
+  int *s_first = nullptr, *s_peer = nullptr, *s_local = nullptr, *s_remote = nullptr;
+};
+
+// peer-mapped regions of a partitioned run, as the Krylov kernels see them (layout: fx_la_common.cuh)
+constexpr int DIST_MAXW = 8;
+struct DistDev {
+  int rank = 0, world = 0;       // world <= 1: single GPU
+  double* region[DIST_MAXW] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // region[rank] is mine
+  long long nmax = 0;            // stride of the work vectors inside a region (>= local n of every space)
+  // halo push lists of the space being solved (fx_plan_set_halo), sorted by local dof
+  int nsend = 0;                 // (dof, destination) pairs
+  const int* s_first = nullptr;  // [n] first pair of an interface dof (MASK_IFACE rows only)
+  const int* s_peer = nullptr;   // [nsend] destination rank | DIST_LAST
+  const int* s_local = nullptr;  // [nsend] my local dof index
+  const int* s_remote = nullptr; // [nsend] the destination's local (ghost) dof index
 };
 
 constexpr int KRYLOV_NWORK = 12;
@@ -47,6 +66,15 @@ constexpr int COARSE_KMAX = 256;   // aggregates of the two-level preconditioner
 constexpr int COARSE_NLMAX = 64;   // aggregates one CTA of the resident CG kernel may touch
 constexpr int RED_SLOTS = 4;       // values reduced at once
 constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
+
+constexpr int DIST_LAST = 0x100;   // s_peer flag: last destination of this dof
+constexpr int DIST_XH = 8;         // work-vector slot the solution's interface values are exchanged through
+// region layout in doubles: [KRYLOV_NWORK * nmax work][2 * DIST_MAXW * RED_SLOTS xred][DIST_MAXW flags][2 state]
+__host__ __device__ inline long long dist_xred_off(long long nmax) { return (long long)KRYLOV_NWORK * nmax; }
+__host__ __device__ inline long long dist_flag_off(long long nmax) { return dist_xred_off(nmax) + 2 * DIST_MAXW * RED_SLOTS; }
+__host__ __device__ inline long long dist_state_off(long long nmax) { return dist_flag_off(nmax) + DIST_MAXW; }
+__host__ __device__ inline long long dist_region_doubles(long long nmax) { return dist_state_off(nmax) + 2; }
+
 
 }  // namespace fx
 
@@ -75,6 +103,7 @@ struct fx_plan {
   int *cprefix = nullptr, *scanpart = nullptr;  // nnz-balanced partition of the row blocks (balance_partition)
   double* coarse = nullptr;                     // two-level preconditioner scratch: E0, E1 (256^2 each), cvec [3][256]
   unsigned* bar = nullptr;                      // grid-barrier counter of the persistent Krylov kernels
+  fx::DistDev dist;                             // world > 1: mesh-partitioned run (fx_plan_set_peer_regions)
 
   fx::MeshView view() const {
     fx::MeshView m;

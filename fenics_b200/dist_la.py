@@ -1,13 +1,21 @@
 """Distributed (mesh-partitioned) Krylov solvers: SURVEY.md 8e.2.
 
-Per rank: the local matrix (owned rows complete, ghost rows replaced by identity rows), local vectors with
-owned + ghost entries.  One iteration = halo exchange of the SpMV input (all_to_all of packed interface
+Per rank: the local matrix (owned rows complete), local vectors with owned + ghost entries.  Two paths:
+
+* **fused** (default on a CUDA/NCCL process group): every rank's Krylov work vectors live in a symmetric
+  memory region all peers map over NVLink (`fx_plan_set_peer_regions`, `fx_plan_set_halo`); the SAME
+  persistent kernels as the single-GPU solves then store interface values straight into the neighbours'
+  ghost slots, close every grid barrier with a cross-GPU flag exchange and sum the dot products across
+  ranks -- one kernel launch per solve per rank, no NCCL call, no host read inside a solve.
+* **host-driven** (`fused=False`; the cross-check, and what the gloo CPU tests of the host logic mirror):
+  ghost rows replaced by identity rows, one iteration = halo exchange of the SpMV input (all_to_all of packed interface
 values), the rank-local CSR-stream SpMV (`fx_spmv`), owner-masked dot products (`fx_dotw_dev`) all-reduced
 as ONE small tensor per reduction point, and fused vector updates whose scalar coefficients stay in device
 memory (`fx_lincomb3_dev`) -- the host only reads the residual norm once per iteration for the stopping
 test.  Jacobi preconditioning (identical to the serial solver, so iteration counts match the 1-GPU run).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -20,15 +28,55 @@ from ._lib import SolveInfo, check, lib
 class DistContext:
     """owner masks / halos of one LocalPartition on a device, plus scratch."""
 
-    def __init__(self, plan, lp, group=None):
+    def __init__(self, plan, lp, group=None, fused=None):
         self.plan, self.lp, self.group = plan, lp, group
         dev = "cuda:%d" % plan.device
+        on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if fused is None:
+            fused = on and dist.get_backend(group) == "nccl" and os.environ.get("FX_DIST_FUSED", "1") != "0"
+        self.fused = bool(fused)
+        if self.fused:
+            self._setup_fused(dev)
         self.mask = {k: torch.as_tensor(lp.owned[k].astype("float64"), device=dev) for k in lp.owned}
         self.ghost_rows = {k: torch.as_tensor((~lp.owned[k]).nonzero()[0].astype("int32"), device=dev) for k in lp.owned}
         self.zeros = {k: torch.zeros(len(self.ghost_rows[k]), dtype=torch.float64, device=dev) for k in lp.owned}
         self.scal = torch.zeros(16, dtype=torch.float64, device=dev)
         self.coef = torch.zeros(3, dtype=torch.float64, device=dev)
         self._work = {}
+
+    def _setup_fused(self, dev):
+        """symmetric (peer-mapped) region per rank + push lists of every space with a CSR pattern."""
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm_mem
+        lp, group = self.lp, self.group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nmax = int(lp.n_local_max)
+        nbytes = int(lib.fx_peer_region_bytes(nmax))
+        self._region = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._region.zero_()
+        pg = group if group is not None else dist.group.WORLD
+        self._hdl = symm_mem.rendezvous(self._region, group=pg.group_name if hasattr(pg, "group_name") else pg)
+        torch.cuda.synchronize()
+        dist.barrier(group)  # every region is zero before anybody's first solve
+        ptrs = (C.c_void_p * world)(*[int(p) for p in self._hdl.buffer_ptrs])
+        check(lib.fx_plan_set_peer_regions(self.plan.h, rank, world, ptrs, nmax))
+        self._keep = []
+        for sp in ("W", "Zc", "Q"):
+            if sp not in lp.halo:
+                continue
+            h = lp.halo[sp]
+            peer = np.ascontiguousarray(np.repeat(np.arange(world), h.send_counts), dtype=np.int32)
+            local = np.ascontiguousarray(h.send_idx_np, dtype=np.int32)
+            remote = np.ascontiguousarray(h.send_remote_np, dtype=np.int32)
+            ghost = np.ascontiguousarray(~lp.owned[sp], dtype=np.uint8)
+            check(lib.fx_plan_set_halo(self.plan.h, abi.SPACE_ID[sp], len(peer), peer.ctypes.data, local.ctypes.data,
+                                       remote.ctypes.data, ghost.ctypes.data))
+
+    def close(self):
+        """detach the plan from the peer regions (before the symmetric memory goes away)."""
+        if self.fused and self.plan.h:
+            lib.fx_plan_set_peer_regions(self.plan.h, 0, 0, None, 0)
+            self.fused = False
 
     def work(self, space, n, count):
         key = (space, count)
@@ -95,6 +143,14 @@ def krylov_solve(ctx, A, x, b, method="bicgstab", pc="default", rtol=1e-5, atol=
     if method not in ("bicgstab", "cg") or pc not in ("jacobi", "none"):
         raise ValueError("distributed solver supports bicgstab/cg with jacobi/none")
     sp, n = A.space, A.n
+    if ctx.fused:
+        info = SolveInfo()
+        rc = lib.fx_krylov_solve(ctx.plan.h, abi.SPACE_ID[sp], la._ptr(A.val), la._ptr(x.t), la._ptr(b.t),
+                                 la._KSP[method], la._PC[pc], float(rtol), float(atol), int(maxit), C.byref(info), la._stream())
+        if rc == abi.FX_ERR_NOCONV and not la.parameters["krylov_solver"]["error_on_nonconvergence"]:
+            return info
+        check(rc)
+        return info
     ctx.seal_ghost_rows(A, b)
     dinv = _diag_inv(ctx, A, pc)
     xt, bt, coef = x.t, b.t, ctx.coef

@@ -22,7 +22,7 @@ _RESULT_SPACE = dict(w1="W", p1="Q", tau1_vec="Zc", rho1="Q", T1="Q")
 
 def distributed(base):
     class Dist(base):
-        def __init__(self, mesh, rank=None, world=None, group=None, **kw):
+        def __init__(self, mesh, rank=None, world=None, group=None, fused=None, **kw):
             on = dist.is_available() and dist.is_initialized()
             self.rank = (dist.get_rank(group) if on else 0) if rank is None else rank
             self.world = (dist.get_world_size(group) if on else 1) if world is None else world
@@ -32,7 +32,7 @@ def distributed(base):
             if issubclass(base, EwmJBP) and kw.get("dt") is None:  # dt = c hmin^2 of the GLOBAL mesh (:164, :461-462)
                 kw["dt"] = (1.0 if kw.get("prepass") else 10.0) * mesh.hmin() ** 2
             super().__init__(self.lp.mesh, dofmaps=self.lp.dofmaps(), **kw)
-            self.ctx = dist_la.DistContext(self.plan, self.lp, group)
+            self.ctx = dist_la.DistContext(self.plan, self.lp, group, fused=fused)
             check(lib.fx_plan_set_owned_cells(self.plan.h, self.lp.nc_owned))
             self.group = group
 

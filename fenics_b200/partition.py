@@ -46,8 +46,11 @@ class Halo:
     """ghost <- owner exchange of one space.  send_idx / recv_idx are local dof indices, concatenated in
     rank order; send_counts[q] values go to rank q, recv_counts[q] come from rank q."""
 
-    def __init__(self, send_idx, send_counts, recv_idx, recv_counts):
+    def __init__(self, send_idx, send_counts, recv_idx, recv_counts, send_remote=None):
         self.send_idx_np, self.recv_idx_np = send_idx, recv_idx
+        # send_remote[k]: index of send_idx[k]'s dof in the DESTINATION rank's local numbering (its ghost
+        # slot) -- what the fused Krylov kernels store to over NVLink (fx_plan_set_halo)
+        self.send_remote_np = send_remote
         self.send_counts, self.recv_counts = [int(c) for c in send_counts], [int(c) for c in recv_counts]
         self._dev = {}
 
@@ -119,7 +122,7 @@ class LocalPartition:
             self.owned[k] = owner[k][l2g] == rank
             self.spaces[k] = FunctionSpace(self.mesh, k, cell_dofs=np.searchsorted(l2g, G[k][self.cells_global]),
                                            comps=ELEMENTS.get(k))
-            send_idx, send_counts, recv_idx, recv_counts = [], [], [], []
+            send_idx, send_counts, recv_idx, recv_counts, send_remote = [], [], [], [], []
             for q in range(nparts):
                 if q == rank:
                     send_counts.append(0)
@@ -128,12 +131,14 @@ class LocalPartition:
                 # what q needs from me: dofs in q's sub-mesh that I own (sorted by global id on both sides)
                 need_q = dofsets[k][q][owner[k][dofsets[k][q]] == rank]
                 send_idx.append(np.searchsorted(l2g, need_q))
+                send_remote.append(np.searchsorted(dofsets[k][q], need_q))
                 send_counts.append(len(need_q))
                 mine_q = l2g[owner[k][l2g] == q]
                 recv_idx.append(np.searchsorted(l2g, mine_q))
                 recv_counts.append(len(mine_q))
             cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.zeros(0, dtype=np.int64)  # noqa: E731
-            self.halo[k] = Halo(cat(send_idx), send_counts, cat(recv_idx), recv_counts)
+            self.halo[k] = Halo(cat(send_idx), send_counts, cat(recv_idx), recv_counts, cat(send_remote))
+        self.n_local_max = max(len(d) for ds in dofsets.values() for d in ds)  # same on every rank
 
     def dofmaps(self):
         return {k: s.cell_dofs for k, s in self.spaces.items()}

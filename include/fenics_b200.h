@@ -238,6 +238,32 @@ int fx_plan_set_eliminated_dofs(fx_plan* plan, int space, const int* rows, int n
  * FX_ERR_UNSUPPORTED (and leaves the space without aggregates) otherwise.  k = 0 removes them.       */
 int fx_plan_set_aggregates(fx_plan* plan, int space, const int* agg, int k);
 
+/* ---- mesh-partitioned runs: one process per GPU, one plan per sub-mesh ---------------
+ * The partitioned analogue of what PETSc's MPI Mat/Vec + VecScatter do under dolfin's solve() when the
+ * reference is run with mpirun, re-designed for NVLink peer memory: every rank owns a
+ * "region" of fx_peer_region_bytes(nmax) bytes that all ranks of the box have mapped into their address
+ * space (torch symmetric memory, cudaIpc or cuMem fabric handles -- the library only sees pointers).
+ * It holds the rank's Krylov work vectors (stride nmax doubles, nmax >= the local dimension of every
+ * space on every rank), cross-GPU reduction slots and barrier flags.  Regions must be zero-filled, and
+ * that zero-fill complete on EVERY rank, before any rank's first solve.
+ * With regions and halos registered, fx_krylov_solve* runs the same persistent kernels, which then
+ *   - treat ghost rows as absent (owned rows must be complete: assemble over owned + ghost cells),
+ *   - store every freshly computed interface value of an SpMV input vector straight into the ghost
+ *     slot of each neighbour's copy of that vector (P2P stores over NVLink, no pack/send/unpack),
+ *   - close every grid barrier with a cross-GPU epoch-flag exchange, and sum dot products across ranks in
+ *     rank order (bitwise identical on all ranks, so all ranks take the same branches),
+ *   - refresh the ghost entries of the solution x before returning.
+ * No NCCL call and no host synchronisation happens inside a solve.  All ranks must issue the same
+ * sequence of solves.  A peer that stops responding trips a 10 s device-side timeout: converged = -4.
+ * world <= 1 removes the regions (single-GPU behaviour).                                            */
+long long fx_peer_region_bytes(long long nmax);
+int fx_plan_set_peer_regions(fx_plan* plan, int rank, int world, void* const* regions, long long nmax);
+/* Halo of one space: ghost[i] != 0 marks local dofs owned by another rank (host array, length dim);
+ * (peer[k], local[k], remote[k]), k < nsend: the owned local dof local[k] is ghost dof remote[k] (in
+ * rank peer[k]'s local numbering) on rank peer[k].  Host arrays, copied.  ghost == NULL removes it.   */
+int fx_plan_set_halo(fx_plan* plan, int space, int nsend, const int* peer, const int* local, const int* remote,
+                     const unsigned char* ghost);
+
 /* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default
