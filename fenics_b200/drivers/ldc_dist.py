@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 from .. import dist_la
 from .._lib import check, lib
-from ..partition import LocalPartition
+from ..partition import LocalPartition, rcb_partition
 from ..spaces import function_spaces
 from .dgp import CompDGP
 from .ewm import EwmJBP
@@ -22,7 +22,7 @@ _RESULT_SPACE = dict(w1="W", p1="Q", tau1_vec="Zc", rho1="Q", T1="Q")
 
 def distributed(base):
     class Dist(base):
-        def __init__(self, mesh, rank=None, world=None, group=None, fused=None, **kw):
+        def __init__(self, mesh, rank=None, world=None, group=None, fused=None, replicate_q=None, **kw):
             on = dist.is_available() and dist.is_initialized()
             self.rank = (dist.get_rank(group) if on else 0) if rank is None else rank
             self.world = (dist.get_world_size(group) if on else 1) if world is None else world
@@ -35,6 +35,20 @@ def distributed(base):
             self.ctx = dist_la.DistContext(self.plan, self.lp, group, fused=fused)
             check(lib.fx_plan_set_owned_cells(self.plan.h, self.lp.nc_owned))
             self.group = group
+            # the small P1 systems are solved redundantly on every rank (dist_la.ReplicatedSolver)
+            rep = (self.world > 1 and self.ctx.fused) if replicate_q is None else replicate_q
+            self.rep_q = dist_la.ReplicatedSolver(self.ctx, mesh, Q, "Q") if rep else None
+
+        def enable_pressure_coarse(self, k=256):
+            """two-level preconditioner of the CG pressure solve: available on a partition only through the
+            replicated Q solves (aggregates of the GLOBAL P1 space)."""
+            if self.rep_q is None:
+                return False
+            Q = self.global_spaces["Q"]
+            k = min(int(k), (Q.dim() // 8) // 32 * 32)
+            ok = k >= 32 and self.rep_q.gplan.set_aggregates("Q", rcb_partition(Q.tabulate_dof_coordinates(), k), k)
+            self.pressure_pc = "jacobi_coarse" if ok else None
+            return bool(ok)
 
         def _solve(self, A, x, b, method=None, pc=None, rtol=None, label=""):
             method = method or self.solver[0]
@@ -42,7 +56,10 @@ def distributed(base):
             rtol = (self.solve_rtol if rtol is None else rtol) or 1e-5
             self.solve_labels.append("%s:%s:%s" % (label, A.space, method))
             with self._phase("solve:%s:%s:%s" % (label, A.space, method)):
-                self.last_info.append(dist_la.krylov_solve(self.ctx, A, x.vector(), b, method, pc, rtol=rtol))
+                if self.rep_q is not None and A.space == "Q":
+                    self.last_info.append(self.rep_q.solve(A, x.vector(), b, method, pc, rtol))
+                else:
+                    self.last_info.append(dist_la.krylov_solve(self.ctx, A, x.vector(), b, method, pc, rtol=rtol))
 
         def _finish_step(self, allow_pipeline=True):
             if self.world > 1:

@@ -56,6 +56,7 @@ if bench_n:
     del d, s
     db = Dist(make_mesh(bench_n), device=local, **params)
     db.pressure_method = "cg"
+    out["pressure_coarse"] = bool(db.enable_pressure_coarse())
     if cfg != "cfg5":
         db.t = 0.45
     for _ in range(2):
@@ -72,6 +73,14 @@ if bench_n:
         dist.barrier()
     out.update(bench_n=bench_n, ms_per_step=(time.perf_counter() - t0) / nb * 1e3,
                bench_iters=dict(zip(db.solve_labels, [i.iterations for i in db.last_info])))
+    db.profile = []
+    db.step()
+    torch.cuda.synchronize()
+    ph = {}
+    for lab, a, b in db.profile:
+        ph[lab] = ph.get(lab, 0.0) + a.elapsed_time(b)
+    out["phases_ms"] = {k: round(v, 3) for k, v in sorted(ph.items(), key=lambda kv: -kv[1])[:12]}
+    out["fused"] = bool(db.ctx.fused)
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
