@@ -84,7 +84,7 @@ __device__ __forceinline__ void grid_sum(Bar& bar, double (&v)[NV], double* red,
 // varies from run to run (last-bit differences), but every CTA reads the same totals, so control flow
 // stays uniform.  Accumulator (phase+1)%3 is cleared by CTA 0 before it arrives: everybody finished
 // reading it before arriving at the previous barrier, and nobody adds to it until this barrier opens.
-template <int NV, class Bar>
+template <int NV, bool PUSHED, class Bar>
 __device__ __forceinline__ void grid_sum_atomic(Bar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
   double* acc = red + (size_t)2 * RED_SLOTS * MAX_GRID;  // [3][RED_SLOTS]
   double* cur = acc + (phase % 3) * RED_SLOTS;
@@ -94,40 +94,29 @@ __device__ __forceinline__ void grid_sum_atomic(Bar& bar, double (&v)[NV], doubl
     if (threadIdx.x == i) atomicAdd(cur + i, v[i]);
   if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + RED_SLOTS)
     acc[((phase + 1) % 3) * RED_SLOTS + threadIdx.x - 32] = 0.0;
+  bar.template sync_x<NV, PUSHED>(cur);
   if (!bar.dist()) {
-    bar.sync();
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = __ldcg(cur + i);
   } else {
-    // partitioned run: CTA 0 hands this GPU's totals to every peer (P2P stores into their regions) between
-    // the local and the cross-GPU part of the barrier; everybody then adds the per-rank totals in rank
-    // order, so all GPUs hold bitwise identical sums and take the same branches.  The own total is read
-    // from the local accumulator: it is complete when the local part of the barrier opens, whereas CTA 0's
-    // payload may still be running when the peers' flags (the only other thing a CTA waits for) are in.
+    // partitioned run: the barrier handed this GPU's totals to every peer and left theirs in bar.xs.
+    // Everybody adds the per-rank totals in rank order, so all GPUs hold bitwise identical sums and take
+    // the same branches.
     const DistDev& dd = *bar.dd;
-    bar.sync_with([&] {
-      const long long slot = dist_xred_off(dd.nmax) + (long long)((bar.xepoch & 1ull) * DIST_MAXW + dd.rank) * RED_SLOTS;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const double t = __ldcg(cur + i);
-        for (int q = 0; q < dd.world; ++q)
-          if (q != dd.rank) dd.region[q][slot + i] = t;
-      }
-    });
-    const double* mine = dd.region[dd.rank] + dist_xred_off(dd.nmax) + (long long)(bar.xepoch & 1ull) * DIST_MAXW * RED_SLOTS;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       double t = 0.0;
-      for (int q = 0; q < dd.world; ++q) t += __ldcg(q == dd.rank ? cur + i : mine + q * RED_SLOTS + i);
+      for (int q = 0; q < dd.world; ++q) t += (q == dd.rank) ? __ldcg(cur + i) : bar.xs[q * RED_SLOTS + i];
       v[i] = t;
     }
   }
   ++phase;
 }
 
-template <int NV, class Bar>
+// PUSHED = false: no thread stored halo values to a peer since the previous barrier
+template <int NV, bool PUSHED = true, class Bar>
 __device__ __forceinline__ void gsum(const KArgs& a, Bar& bar, double (&v)[NV], int& phase, double* sh) {
-  if (a.red_atomic || bar.dist()) grid_sum_atomic<NV>(bar, v, a.red, phase, sh);
+  if (a.red_atomic || bar.dist()) grid_sum_atomic<NV, PUSHED>(bar, v, a.red, phase, sh);
   else grid_sum<NV>(bar, v, a.red, phase, sh);
 }
 
@@ -210,8 +199,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
   double* t = a.w + 5 * ld;
   double* dinv = a.w + 6 * ld;
   int phase = 0;
+  __shared__ double sh_x[DIST ? DIST_MAXW * RED_SLOTS : 1];
   GridBarT<DIST> bar;
-  bar.init(a.bar, &a.dd);
+  bar.init(a.bar, &a.dd, sh_x);
 
   // setup: compacted matrix, balanced partition, dinv, r = M^-1 (b - A x), rhat = p = r, v = 0
   double acc[3] = {0.0, 0.0, 0.0};
@@ -257,18 +247,27 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
       if (gw_ < 8192) g_prof_warp[gw_] = tt;
     }
     stamp(a.prof, np);
-    gsum<1>(a, bar, d1, phase, sh);
+    gsum<1, false>(a, bar, d1, phase, sh);
     stamp(a.prof, np);
     if (d1[0] == 0.0) { leave(bar, a, it - 1, -1, rn, bn); return; }
     const double alpha = rho / d1[0];
     double d2[1] = {0.0};
-    for (int i = gt; i < n; i += gs) {
-      const unsigned char mk = mask != nullptr ? mask[i] : 0;
-      if (mk & MASK_GHOST) continue;
+    // partitioned run: interface entries first, so their P2P stores are acknowledged while the rest of the
+    // pass runs (the barrier's system-scope fence then finds nothing in flight)
+    auto upd_s = [&](int i, bool iface) {
       const double si = r[i] - alpha * v[i];
       s[i] = si;
-      if (mk & MASK_IFACE) push_iface(a.dd, 4, i, si);
+      if (iface) push_iface(a.dd, 4, i, si);
       d2[0] += si * si;
+    };
+    if (DIST)
+      for (int k = gt; k < a.dd.nsend; k += gs) {
+        const int i = a.dd.s_local[k];
+        if (k == 0 || a.dd.s_local[k - 1] != i) upd_s(i, true);
+      }
+    for (int i = gt; i < n; i += gs) {
+      if (DIST && (mask[i] & (MASK_GHOST | MASK_IFACE))) continue;
+      upd_s(i, false);
     }
     stamp(a.prof, np);
     gsum<1>(a, bar, d2, phase, sh);
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
                     d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
                   });
     stamp(a.prof, np);
-    gsum<4>(a, bar, d3, phase, sh);
+    gsum<4, false>(a, bar, d3, phase, sh);
     stamp(a.prof, np);
     if (d3[1] == 0.0) { leave(bar, a, it, -1, sqrt(ss), bn); return; }
     const double omega = d3[0] / d3[1];
@@ -307,18 +306,25 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     // x += alpha p + omega s;  r = s - omega t;  p = r + beta (p - omega v)   [restart: rhat = p = r]
     const bool check = rn <= 2.0 * tol;  // confirm with a true norm
     double d4[1] = {0.0};
-    for (int i = gt; i < n; i += gs) {
-      const unsigned char mk = mask != nullptr ? mask[i] : 0;
-      if (mk & MASK_GHOST) continue;
+    auto upd_p = [&](int i, bool iface) {
       const double pi = p[i];
       a.x[i] += alpha * pi + omega * s[i];
       const double ri = s[i] - omega * t[i];
       r[i] = ri;
       const double pn = ri + beta * (pi - omega * v[i]);
       p[i] = pn;
-      if (mk & MASK_IFACE) push_iface(a.dd, 2, i, pn);
+      if (iface) push_iface(a.dd, 2, i, pn);
       if (restart) rh[i] = ri;
       d4[0] += ri * ri;
+    };
+    if (DIST)
+      for (int k = gt; k < a.dd.nsend; k += gs) {
+        const int i = a.dd.s_local[k];
+        if (k == 0 || a.dd.s_local[k - 1] != i) upd_p(i, true);
+      }
+    for (int i = gt; i < n; i += gs) {
+      if (DIST && (mask[i] & (MASK_GHOST | MASK_IFACE))) continue;
+      upd_p(i, false);
     }
     stamp(a.prof, np);
     if (check || restart) {
@@ -357,8 +363,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   double* s = a.w + 4 * ld;
   double* dinv = a.w + 5 * ld;
   int phase = 0;
+  __shared__ double sh_x[DIST ? DIST_MAXW * RED_SLOTS : 1];
   GridBarT<DIST> bar;
-  bar.init(a.bar, &a.dd);
+  bar.init(a.bar, &a.dd, sh_x);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   acc[3] = (double)compact_zeros(A);
   bar.sync();
@@ -386,14 +393,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                   w[row] = au;
                   d0[0] += au * o.a;
                 });
-  gsum<1>(a, bar, d0, phase, sh);
+  gsum<1, false>(a, bar, d0, phase, sh);
   if (!(d0[0] > 0.0)) { leave(bar, a, 0, -1, un, bn); return; }
   double alpha = gamma / d0[0], beta = 0.0;
   for (int it = 1; it <= a.maxit; ++it) {
     double d[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < n; i += gs) {
-      const unsigned char mk = mask != nullptr ? mask[i] : 0;
-      if (mk & MASK_GHOST) continue;
+    auto upd = [&](int i, bool iface) {
       const double pi = u[i] + beta * p[i];
       const double si = w[i] + beta * s[i];
       p[i] = pi; s[i] = si;
@@ -402,9 +407,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
       r[i] = ri;
       const double ui = dinv[i] * ri;
       u[i] = ui;
-      if (mk & MASK_IFACE) push_iface(a.dd, 1, i, ui);
+      if (iface) push_iface(a.dd, 1, i, ui);
       d[0] += ri * ui;
       d[1] += ui * ui;
+    };
+    if (DIST)  // interface entries first: their P2P stores are acknowledged while the rest of the pass runs
+      for (int k = gt; k < a.dd.nsend; k += gs) {
+        const int i = a.dd.s_local[k];
+        if (k == 0 || a.dd.s_local[k - 1] != i) upd(i, true);
+      }
+    for (int i = gt; i < n; i += gs) {
+      if (DIST && (mask[i] & (MASK_GHOST | MASK_IFACE))) continue;
+      upd(i, false);
     }
     bar.sync();
     spmv_stream_c(A, rg, u, prod, [&](int row) { return Ops2{u[row], 0.0}; },
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
                     w[row] = au;
                     d[2] += au * o.a;
                   });
-    gsum<3>(a, bar, d, phase, sh);
+    gsum<3, false>(a, bar, d, phase, sh);
     un = sqrt(d[1]);
     if (!(un == un) || un > a.dtol * bn) { leave(bar, a, it, -1, un, bn); return; }
     if (un <= tol) { leave(bar, a, it, 1, un, bn); return; }
@@ -961,7 +975,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   void* args[] = {(void*)&ka};
   FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st));
   count_launch(1);
-  if (prof_env && method == FX_KSP_BICGSTAB && p.n > 100000) {  // debugging aid: per-phase microseconds of iterations 2..4
+  if (prof_env && method == FX_KSP_BICGSTAB && p.n > 100000 && (!part || P->dist.rank == 0)) {  // debugging aid: per-phase microseconds of iterations 2..4
     static unsigned long long h[1024];
     cudaStreamSynchronize(st);
     cudaMemcpyFromSymbol(h, g_prof, sizeof(h));

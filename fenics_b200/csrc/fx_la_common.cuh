@@ -119,92 +119,120 @@ __device__ __forceinline__ void push_iface(const DistDev& dd, int j, int i, doub
 // waiting thread polls with ld.acquire -- every poll invalidates the SM's whole L1 (CCTL.IVALL), which
 // evicts the x-gather lines of the CTAs still working on that SM -- the wait here polls with relaxed
 // loads and acquires once.  Monotonic counter, zeroed by the host before every launch.
-// With a DistDev of world > 1 the barrier spans the GPUs of the partition: when all local CTAs have
-// arrived, CTA 0 runs an optional payload (the cross-GPU part of a reduction), then raises this rank's
-// epoch flag in every peer's region; every CTA waits for the local counter AND the peers' flags.  Epochs
-// are 64-bit and continue across solves (persisted in the region), so stale flags never match.  A peer
-// that never arrives (a rank died) trips a 10 s timeout: the barrier goes dead (all later waits fall
-// through) and the solve reports converged = -4 instead of hanging the GPU.
+//
+// DIST (mesh-partitioned run): the barrier spans the GPUs of the partition and carries up to RED_SLOTS
+// reduction values with it.  Every CTA arrives at the local counter; when all have, thread 0 of CTA 0
+// stores one LL line per value {lo, epoch, hi, epoch} into every peer's region -- data and flag travel
+// together, so no fence separates them -- and meanwhile warp 1 of EVERY CTA polls the lines the peers
+// store into this GPU's region (one lane per line, in parallel), acquires, and leaves the peers' values
+// in shared memory.  A CTA passes when the local counter is full and every peer's line of this epoch is
+// in: that implies the peer's CTAs all arrived, and (their system-scope fences precede their arrival) that
+// the halo values they pushed are visible here.  Lines are double-buffered by epoch parity: a peer can
+// be at most one barrier ahead.  Epochs continue across solves (persisted in the region).  A peer that
+// never arrives trips a 10 s timeout: the barrier goes dead (all later waits fall through, together on
+// all CTAs) and the solve reports converged = -4 instead of hanging the GPU.
 template <bool DIST>
 struct GridBarT {
   unsigned* ctr;
   unsigned target;
   const DistDev* dd;
-  unsigned long long xepoch;
+  unsigned xepoch;
   bool dead;
+  double* xs;  // shared memory [DIST_MAXW * RED_SLOTS]: the peers' values of the latest barrier
   __device__ __forceinline__ constexpr bool dist() const { return DIST; }
-  __device__ __forceinline__ unsigned long long* xflags(int q) const {
-    return reinterpret_cast<unsigned long long*>(dd->region[q] + dist_flag_off(dd->nmax));
+  __device__ __forceinline__ unsigned long long* state() const {
+    return reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax));
   }
-  __device__ __forceinline__ void init(unsigned* c, const DistDev* d = nullptr) {
-    ctr = c; target = 0; dd = d; xepoch = 0; dead = false;
-    if (dist()) {
-      const unsigned long long* st = reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax));
-      xepoch = __ldcg(st);
-      dead = __ldcg(st + 1) != 0;
+  __device__ __forceinline__ uint4* line(int dst, unsigned parity, int src, int i) const {
+    return reinterpret_cast<uint4*>(dd->region[dst] + dist_xred_off(dd->nmax)) + ((parity * DIST_MAXW + src) * RED_SLOTS + i);
+  }
+  __device__ __forceinline__ void init(unsigned* c, const DistDev* d = nullptr, double* xs_shared = nullptr) {
+    ctr = c; target = 0; dd = d; xepoch = 0; dead = false; xs = xs_shared;
+    if (DIST) {
+      xepoch = (unsigned)__ldcg(state());
+      dead = __ldcg(state() + 1) != 0;
     }
   }
   // persist the epoch for the next solve (every exit path, block 0 / thread 0)
   __device__ __forceinline__ void save() const {
-    if (dist() && blockIdx.x == 0 && threadIdx.x == 0)
-      *reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax)) = xepoch;
+    if (DIST && blockIdx.x == 0 && threadIdx.x == 0) *state() = xepoch;
   }
-  template <class Payload>
-  __device__ __forceinline__ void sync_with(Payload&& payload) {
+  __device__ __forceinline__ void wait_local() {
+    unsigned v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  // NV > 0: cur[0..NV) are this GPU's totals (device accumulators, complete once the local counter is full).
+  // PUSHED: this CTA may have stored to peer memory since the previous barrier (system-scope release).
+  template <int NV, bool PUSHED>
+  __device__ __forceinline__ void sync_x(const double* cur) {
     target += gridDim.x;
-    const bool x = dist();
-    if (x) ++xepoch;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (x) __threadfence_system(); else __threadfence();  // release everything this CTA wrote
-      atomicAdd(ctr, 1u);
-      unsigned v;
-      if (x && blockIdx.x == 0) {
-        do {
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while ((int)(v - target) < 0);
-        __threadfence_system();  // all local CTAs' writes (halo pushes, reduction atomics) are ordered before ...
-        payload();
-        __threadfence_system();  // ... this rank's flag in every peer's region
-        for (int q = 0; q < dd->world; ++q)
-          if (q != dd->rank)
-            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(xflags(q) + dd->rank), "l"(xepoch) : "memory");
-      }
-      do {
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      } while ((int)(v - target) < 0);
-      if (x) {
-        unsigned long long t0 = 0, f;
-        unsigned long long* deadflag = reinterpret_cast<unsigned long long*>(dd->region[dd->rank] + dist_state_off(dd->nmax)) + 1;
-        for (int q = 0; q < dd->world && !dead; ++q) {
-          if (q == dd->rank) continue;
-          const unsigned long long* fp = xflags(dd->rank) + q;
-          unsigned spins = 0;
-          for (;;) {
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fp) : "memory");
-            if ((long long)(f - xepoch) >= 0) break;
-            if ((++spins & 0x3ffu) == 0) {
-              if (__ldcg(deadflag) != 0) { dead = true; break; }  // another CTA gave up: all give up together
-              unsigned long long now;
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > 10000000000ull) { dead = true; *deadflag = 1ull; break; }
-            }
-          }
-          // acquire on the flag itself: pairs with the peer's fence + flag store
-          if (!dead) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(fp) : "memory");
-        }
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      } else {
+    if (!DIST) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();  // release: everything this CTA wrote (the barrier above orders the other threads' stores)
+        atomicAdd(ctr, 1u);
+        wait_local();
+        unsigned v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       }
+      __syncthreads();
+      return;
     }
-    if (x) dead = __syncthreads_or(dead);
-    else __syncthreads();
+    const unsigned e = ++xepoch, par = e & 1u;
+    constexpr int NVS = NV > 0 ? NV : 1;
+    const int L = (dd->world - 1) * NVS;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (PUSHED) __threadfence_system(); else __threadfence();
+      atomicAdd(ctr, 1u);
+      if (blockIdx.x == 0) {
+        wait_local();
+        __threadfence_system();  // the local CTAs' releases are ordered before the lines below (cumulativity)
+        double t[NVS];
+#pragma unroll
+        for (int i = 0; i < NVS; ++i) t[i] = (i < NV) ? __ldcg(cur + i) : 0.0;
+        for (int q = 0; q < dd->world; ++q) {
+          if (q == dd->rank) continue;
+#pragma unroll
+          for (int i = 0; i < NVS; ++i) {
+            const unsigned lo = (unsigned)__double2loint(t[i]), hi = (unsigned)__double2hiint(t[i]);
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line(q, par, dd->rank, i)), "r"(lo), "r"(e),
+                         "r"(hi), "r"(e) : "memory");
+          }
+        }
+      }
+      wait_local();
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } else if (threadIdx.x >= 32 && (int)threadIdx.x < 32 + L && !dead) {
+      const int k = threadIdx.x - 32, qq = k / NVS, i = k - qq * NVS;
+      const int q = qq + (qq >= dd->rank ? 1 : 0);
+      const uint4* lp = line(dd->rank, par, q, i);
+      unsigned long long* deadflag = state() + 1;
+      unsigned long long t0 = 0;
+      unsigned spins = 0, w0, w1, w2, w3;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "l"(lp) : "memory");
+        if (w1 == e && w3 == e) break;
+        if ((++spins & 0x3ffu) == 0) {
+          if (__ldcg(deadflag) != 0) { dead = true; break; }  // somebody gave up: all give up together
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) { dead = true; *deadflag = 1ull; break; }
+        }
+      }
+      if (!dead) {
+        unsigned f;  // acquire on the line's flag word: pairs with the peer's fence + line store
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(reinterpret_cast<const unsigned*>(lp) + 1) : "memory");
+        xs[q * RED_SLOTS + i] = __hiloint2double((int)w2, (int)w0);
+      }
+    }
+    dead = __syncthreads_or(dead);
   }
-  __device__ __forceinline__ void sync() {
-    sync_with([] {});
-  }
+  __device__ __forceinline__ void sync() { sync_x<0, true>(nullptr); }
 };
 typedef GridBarT<false> GridBar;
 

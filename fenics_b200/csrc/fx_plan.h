@@ -69,10 +69,12 @@ constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size
 
 constexpr int DIST_LAST = 0x100;   // s_peer flag: last destination of this dof
 constexpr int DIST_XH = 8;         // work-vector slot the solution's interface values are exchanged through
-// region layout in doubles: [KRYLOV_NWORK * nmax work][2 * DIST_MAXW * RED_SLOTS xred][DIST_MAXW flags][2 state]
+// region layout in doubles: [KRYLOV_NWORK * nmax work vectors][2 x DIST_MAXW x RED_SLOTS 16-byte LL lines][2 state]
+// An LL line {lo32, epoch, hi32, epoch} carries one double of a cross-GPU reduction TOGETHER with the barrier
+// epoch it belongs to (two 8-byte halves, each written atomically: the protocol of NCCL's LL primitives), so
+// the data needs no fence + separate flag; line [parity of the epoch][source rank][value].
 __host__ __device__ inline long long dist_xred_off(long long nmax) { return (long long)KRYLOV_NWORK * nmax; }
-__host__ __device__ inline long long dist_flag_off(long long nmax) { return dist_xred_off(nmax) + 2 * DIST_MAXW * RED_SLOTS; }
-__host__ __device__ inline long long dist_state_off(long long nmax) { return dist_flag_off(nmax) + DIST_MAXW; }
+__host__ __device__ inline long long dist_state_off(long long nmax) { return dist_xred_off(nmax) + 2 * DIST_MAXW * RED_SLOTS * 2; }
 __host__ __device__ inline long long dist_region_doubles(long long nmax) { return dist_state_off(nmax) + 2; }
 
 

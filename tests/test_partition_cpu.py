@@ -98,3 +98,48 @@ def test_halo_exchange_world2_gloo():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert res == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("nparts", [2, 4, 8])
+def test_push_lists_address_the_same_global_dof_on_both_sides(nparts):
+    """the (peer, local, remote) triples handed to fx_plan_set_halo: `remote` is the destination rank's
+    local index of the same GLOBAL dof, it is a ghost there, every ghost of every rank is written by
+    exactly one owner, and n_local_max bounds every local dimension on every rank."""
+    m, S = _global(8)
+    parts = [LocalPartition(m, S, nparts, r) for r in range(nparts)]
+    assert len({lp.n_local_max for lp in parts}) == 1
+    for k in S:
+        written = [np.zeros(len(lp.l2g[k]), dtype=int) for lp in parts]
+        for r, lp in enumerate(parts):
+            h = lp.halo[k]
+            assert len(lp.l2g[k]) <= lp.n_local_max
+            peer = np.repeat(np.arange(nparts), h.send_counts)
+            assert len(peer) == len(h.send_idx_np) == len(h.send_remote_np)
+            assert lp.owned[k][h.send_idx_np].all()  # only owners push
+            for q, lo, re in zip(peer, h.send_idx_np, h.send_remote_np):
+                assert q != r and parts[q].l2g[k][re] == lp.l2g[k][lo] and not parts[q].owned[k][re]
+                written[q][re] += 1
+        for lp, w in zip(parts, written):
+            assert np.array_equal(w, (~lp.owned[k]).astype(int))
+
+
+def test_replicated_solver_row_maps():
+    """dist_la.ReplicatedSolver's premise: an owned row of the local DOLFIN pattern has the same length as the
+    global row and, l2g being monotone, the same column order -- checked here with the host pattern builder
+    of the oracle (the GPU class asserts the same on the device patterns)."""
+    m, S = _global(6)
+    g_cd = S["Q"].cell_dofs
+    rows_g = [set() for _ in range(S["Q"].dim())]
+    for c in g_cd:
+        for a in c:
+            rows_g[a].update(c.tolist())
+    for r in range(3):
+        lp = LocalPartition(m, S, 3, r)
+        l_cd, l2g = lp.spaces["Q"].cell_dofs, lp.l2g["Q"]
+        assert np.all(np.diff(l2g) > 0)
+        rows_l = [set() for _ in range(len(l2g))]
+        for c in l_cd:
+            for a in c:
+                rows_l[a].update(c.tolist())
+        for i in np.flatnonzero(lp.owned["Q"]):
+            assert sorted(l2g[sorted(rows_l[i])].tolist()) == sorted(rows_g[l2g[i]])
