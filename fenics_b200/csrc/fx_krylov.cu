@@ -2,6 +2,7 @@
 //   * k_bicgstab:  left-preconditioned BiCGStab, PETSc KSPBCGS semantics
 //   * k_cg:        preconditioned CG in the Chronopoulos-Gear form (one fused reduction per iteration)
 //   * k_pcg_res<R>: pipelined CG for small systems, matrix slice resident in shared memory
+//   * k_gmres:     left-preconditioned restarted GMRES(30), PETSc KSPGMRES defaults
 // SpMV (CSR-stream through shared memory), fused vector updates, dot products and the convergence test
 // all run on the device, separated by grid.sync(); reductions are deterministic two-stage sums so every
 // CTA takes the same branch.  Preconditioner: Jacobi (M = diag A) or none.
@@ -54,6 +55,8 @@ struct KArgs {
   double rtol, atol, dtol;
   int maxit, pc;
   fx_solve_info* info;
+  double* basis;    // GMRES: (GMRES_M + 1) x n Krylov basis
+  double* red_big;  // GMRES: 2 x GMRES_NRED x MAX_GRID block partials of the Gram-Schmidt coefficients
 };
 
 // Deterministic grid-wide sum of NV values: block partials -> scratch -> grid barrier -> every CTA sums
@@ -437,6 +440,163 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
     gamma = d[0];
   }
   leave(bar, a, a.maxit, 0, un, bn);
+}
+
+// ---- restarted GMRES -----------------------------------------------------------------------------------------
+// Left-preconditioned GMRES(30) with classical Gram-Schmidt, PETSc KSPGMRES's defaults (restart 30,
+// monitored norm ||M^-1 r||, which the Givens recurrence delivers for free).  Two grid barriers per
+// iteration:
+//   * w = M^-1 A v_j and ALL Gram-Schmidt coefficients (w, v_k), k <= j, in the SpMV epilogue (the lane
+//     that sums row i owns entry i of every basis vector), ONE fused deterministic reduction of up to 30
+//     values;
+//   * w -= sum_k h_k v_k and ||w||^2 in one pass, stored UNnormalised as v_{j+1}: the factor 1 / h_{j+1,j}
+//     is a scalar every thread knows after the second reduction, so it is folded into the next SpMV
+//     epilogue, the coefficients and the final update instead of costing a pass and a barrier of its own.
+// The small least-squares problem (Givens rotations, back substitution) is solved redundantly by every CTA
+// in shared memory from bitwise identical sums, so all CTAs take the same branches.  A cycle that the
+// recurrence reports as converged is confirmed by the true residual at the start of the next one.
+constexpr int GMRES_M = 30;
+constexpr int GMRES_NRED = 32;
+
+template <int NV>
+__device__ __forceinline__ void grid_sum_big(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
+  double* buf = red + (size_t)(phase & 1) * GMRES_NRED * MAX_GRID;
+  block_sum_bcast_n<NV>(v, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) buf[i * MAX_GRID + blockIdx.x] = v[i];
+  }
+  bar.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double t = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) t += __ldcg(buf + i * MAX_GRID + j);
+    v[i] = t;
+  }
+  block_sum_bcast_n<NV>(v, sh);
+  ++phase;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_gmres(const __grid_constant__ KArgs a) {
+  __shared__ double sh[GMRES_NRED * 33];
+  __shared__ int sh_i[64];
+  __shared__ double H[(GMRES_M + 1) * GMRES_M];  // column j at H + j * (GMRES_M + 1)
+  __shared__ double cs[GMRES_M], sn[GMRES_M], g[GMRES_M + 1], scale[GMRES_M + 1], coef[GMRES_M + 1];
+  extern __shared__ __align__(16) double prod[];
+  const CsrView& A = a.A;
+  const int n = A.n;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  double* dinv = a.w;
+  double* w = a.w + (size_t)n;
+  double* V = a.basis;
+  int phase = 0, phase_big = 0;
+  GridBar bar;
+  bar.init(a.bar);
+  double bad[1] = {(double)compact_zeros(A)};
+  bar.sync();
+  const BlockRange rg = balance_partition(A, bar, sh_i);
+  double bn = 0.0, tol = 0.0, rn = 0.0;
+  int it = 0;
+  for (int cycle = 0;; ++cycle) {
+    // v_0 = r = M^-1 (b - A x), unnormalised
+    double acc[3] = {0.0, 0.0, cycle == 0 ? bad[0] : 0.0};
+    spmv_stream_c(A, rg, a.x, prod,
+                  [&](int row) { return Ops2{cycle == 0 ? row_diag_inv(A, row, a.pc) : dinv[row], a.b[row]}; },
+                  [&](int row, double ax, const Ops2& o) {
+                    const double ri = o.a * (o.b - ax), bi = o.a * o.b;
+                    if (cycle == 0) dinv[row] = o.a;
+                    V[row] = ri;
+                    acc[0] += ri * ri; acc[1] += bi * bi;
+                  });
+    gsum<3>(a, bar, acc, phase, sh);
+    if (cycle == 0) {
+      if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0
+      bn = sqrt(acc[1]);
+      tol = fmax(a.rtol * bn, a.atol);
+    }
+    rn = sqrt(acc[0]);
+    if (!(rn == rn) || rn > a.dtol * bn) { leave(bar, a, it, -1, rn, bn); return; }
+    if (rn <= tol) { leave(bar, a, it, 1, rn, bn); return; }
+    if (it >= a.maxit) { leave(bar, a, it, 0, rn, bn); return; }
+    __syncthreads();
+    if (threadIdx.x == 0) { g[0] = rn; scale[0] = 1.0 / rn; }
+    __syncthreads();
+    int m = 0;  // basis vectors used by this cycle's update
+    for (int j = 0; j < GMRES_M && it < a.maxit; ++j) {
+      ++it;
+      const double* vj = V + (size_t)j * n;
+      const double sj = scale[j];
+      double hacc[GMRES_NRED];
+#pragma unroll
+      for (int k = 0; k < GMRES_NRED; ++k) hacc[k] = 0.0;
+      spmv_stream_c(A, rg, vj, prod, [&](int row) { return Ops2{dinv[row], 0.0}; },
+                    [&](int row, double av, const Ops2& o) {
+                      const double wi = o.a * sj * av;
+                      w[row] = wi;
+#pragma unroll
+                      for (int k = 0; k < GMRES_M; ++k)
+                        if (k <= j) hacc[k] += wi * V[(size_t)k * n + row];
+                    });
+      grid_sum_big<GMRES_NRED>(bar, hacc, a.red_big, phase_big, sh);
+      // h_k = (w, v_k) = scale_k * (w, v_k raw);  w -= sum_k h_k v_k = sum_k (h_k scale_k) v_k raw
+      __syncthreads();
+      double* Hj = H + j * (GMRES_M + 1);
+#pragma unroll
+      for (int k = 0; k < GMRES_M; ++k)
+        if (k <= j && threadIdx.x == 0) { Hj[k] = hacc[k] * scale[k]; coef[k] = Hj[k] * scale[k]; }
+      __syncthreads();
+      double nacc[1] = {0.0};
+      double* vn = V + (size_t)(j + 1) * n;
+      for (int i = gt; i < n; i += gs) {
+        double wi = w[i];
+        for (int k = 0; k <= j; ++k) wi -= coef[k] * V[(size_t)k * n + i];
+        vn[i] = wi;
+        nacc[0] += wi * wi;
+      }
+      gsum<1>(a, bar, nacc, phase, sh);
+      const double hn = sqrt(nacc[0]);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        // previous rotations on the new column, then the rotation that annihilates h_{j+1,j}
+        for (int k = 0; k < j; ++k) {
+          const double t0 = cs[k] * Hj[k] + sn[k] * Hj[k + 1];
+          Hj[k + 1] = -sn[k] * Hj[k] + cs[k] * Hj[k + 1];
+          Hj[k] = t0;
+        }
+        const double den = sqrt(Hj[j] * Hj[j] + hn * hn);
+        cs[j] = den > 0.0 ? Hj[j] / den : 1.0;
+        sn[j] = den > 0.0 ? hn / den : 0.0;
+        Hj[j] = den;
+        g[j + 1] = -sn[j] * g[j];
+        g[j] = cs[j] * g[j];
+        scale[j + 1] = hn > 0.0 ? 1.0 / hn : 0.0;
+      }
+      __syncthreads();
+      m = j + 1;
+      rn = fabs(g[j + 1]);
+      if (!(rn == rn) || rn <= tol || hn == 0.0) break;
+    }
+    // y = R^-1 g (back substitution), x += sum_k y_k v_k = sum_k (y_k scale_k) v_k raw
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = m - 1; k >= 0; --k) {
+        double t0 = g[k];
+        for (int l = k + 1; l < m; ++l) t0 -= H[l * (GMRES_M + 1) + k] * coef[l];
+        const double d = H[k * (GMRES_M + 1) + k];
+        coef[k] = d != 0.0 ? t0 / d : 0.0;  // y_k
+      }
+      for (int k = 0; k < m; ++k) coef[k] *= scale[k];
+    }
+    __syncthreads();
+    for (int i = gt; i < n; i += gs) {
+      double xi = a.x[i];
+      for (int k = 0; k < m; ++k) xi += coef[k] * V[(size_t)k * n + i];
+      a.x[i] = xi;
+    }
+    if (!(rn == rn)) { leave(bar, a, it, -1, rn, bn); return; }
+    bar.sync();  // x complete before the next cycle's residual
+  }
 }
 
 // ---- pipelined CG (Ghysels-Vanroose), matrix resident in shared memory -----------------------------------
@@ -900,8 +1060,8 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
               double rtol, double atol, int maxit, int ticket, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB)
-    return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg available)", method);
+  if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB && method != FX_KSP_GMRES)
+    return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg, gmres available)", method);
   if (pc != FX_PC_NONE && pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE)
     return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, jacobi_coarse available)", pc);
   int grid1 = 0;
@@ -940,6 +1100,35 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   ka.x = x; ka.b = b; ka.w = part ? P->dist.region[P->dist.rank] : P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
+  ka.basis = nullptr; ka.red_big = nullptr;
+  if (method == FX_KSP_GMRES) {
+    if (part) return set_error(FX_ERR_UNSUPPORTED, "gmres is not available on a partitioned plan (bicgstab, cg are)");
+    if (pc == FX_PC_JACOBI_COARSE) return set_error(FX_ERR_UNSUPPORTED, "gmres: preconditioners none, jacobi");
+    const size_t need = (size_t)(GMRES_M + 1) * (size_t)p.n;
+    if (P->gmres_cap < need) {
+      cudaFree(P->gmres_basis);
+      P->gmres_basis = nullptr; P->gmres_cap = 0;
+      FX_CUDA(cudaMalloc((void**)&P->gmres_basis, sizeof(double) * need));
+      P->gmres_cap = need;
+    }
+    if (!P->red_big) FX_CUDA(cudaMalloc((void**)&P->red_big, sizeof(double) * 2 * GMRES_NRED * MAX_GRID));
+    ka.basis = P->gmres_basis; ka.red_big = P->red_big;
+    constexpr int T = 256;
+    const size_t smem = sizeof(double) * (T / 32) * SPMV_NNZB;
+    static bool attr = false;
+    if (!attr) {
+      FX_CUDA(cudaFuncSetAttribute(k_gmres<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    int per_sm = 0;
+    FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gmres<T>, T, smem));
+    if (per_sm < 1) return set_error(FX_ERR_CUDA, "GMRES kernel does not fit on an SM");
+    const int grid = max(1, min(min(per_sm * P->num_sms, MAX_GRID), (p.nrowblk + T / 32 - 1) / (T / 32)));
+    void* gargs[] = {(void*)&ka};
+    FX_CUDA(cudaLaunchCooperativeKernel((void*)k_gmres<T>, dim3(grid), dim3(T), gargs, smem, st));
+    count_launch(1);
+    return FX_OK;
+  }
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
   if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part) {
     const int warps = P->num_sms * LA_WARPS;

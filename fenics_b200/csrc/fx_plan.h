@@ -105,6 +105,9 @@ struct fx_plan {
   int *cprefix = nullptr, *scanpart = nullptr;  // nnz-balanced partition of the row blocks (balance_partition)
   double* coarse = nullptr;                     // two-level preconditioner scratch: E0, E1 (256^2 each), cvec [3][256]
   unsigned* bar = nullptr;                      // grid-barrier counter of the persistent Krylov kernels
+  double* gmres_basis = nullptr;                // GMRES Krylov basis, (restart + 1) x n, allocated on first use
+  size_t gmres_cap = 0;
+  double* red_big = nullptr;                    // GMRES: block partials of the Gram-Schmidt coefficients
   fx::DistDev dist;                             // world > 1: mesh-partitioned run (fx_plan_set_peer_regions)
 
   fx::MeshView view() const {

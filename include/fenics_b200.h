@@ -264,8 +264,9 @@ int fx_plan_set_peer_regions(fx_plan* plan, int rank, int world, void* const* re
 int fx_plan_set_halo(fx_plan* plan, int space, int nsend, const int* peer, const int* local, const int* remote,
                      const unsigned char* ghost);
 
-/* solve(A, x, b, "bicgstab"|"cg", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
- * solve; x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
+/* solve(A, x, b, "bicgstab"|"cg"|"gmres", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
+ * solve (gmres: restart 30, classical Gram-Schmidt, PETSc KSPGMRES defaults; single-GPU plans); pc none,
+ * jacobi or jacobi_coarse -- FX_PC_ILU0 returns FX_ERR_UNSUPPORTED.  x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default
  * for left preconditioning).  Synchronous: waits for the solve, fills *info (may be NULL) and
  * returns FX_ERR_NOCONV on failure, like dolfin's RuntimeError.                                 */

@@ -134,14 +134,15 @@ def test_spmv_and_blas1():
         assert x.norm("linf") == np.abs(xv).max()
 
 
-@pytest.mark.parametrize("method,pc", [("bicgstab", "jacobi"), ("bicgstab", "none"), ("cg", "jacobi")])
+@pytest.mark.parametrize("method,pc", [("bicgstab", "jacobi"), ("bicgstab", "none"), ("cg", "jacobi"),
+                                       ("gmres", "jacobi"), ("gmres", "none")])
 def test_krylov_against_direct(method, pc):
     ocl, drv = _pair(2, n=10)
     lc.randomize(ocl)
     _push_state(ocl, drv)
     rng = np.random.default_rng(1)
     cases = [("Q", abi.FX_FORM_C2_A5), ("Zc", abi.FX_FORM_MASS_ZC)]
-    if method == "bicgstab":
+    if method in ("bicgstab", "gmres"):
         cases.append(("W", abi.FX_FORM_C2_A7))
     for name, fid in cases:
         A = dapi.assemble(drv.pr.form(fid))
