@@ -363,6 +363,7 @@ class IncompLDC(_LDC):
 
 
 class CompLDC(_LDC):
+    """lid-driven-cavity/comp_LDC_mesh_convergence.py:376-565 (config 2)."""
     STATE_FIELDS = ("w0", "p0", "tau0_vec", "rho0", "w1", "tau1_vec")
     RESULT_FIELDS = ("w1", "p1", "tau1_vec", "rho1")
 
@@ -406,3 +407,13 @@ class CompLDC(_LDC):
         g = lambda f: f.vector().get_local()  # noqa: E731
         return dict(w1=g(self.w1), p1=g(self.p1), tau1=g(self.tau1_vec), rho1=g(self.rho1), rho12=g(self.rho12),
                     kapp=g(self.kapp))
+
+
+class CompLDCSweep(CompLDC):
+    """lid-driven-cavity/comp_LDC.py:364-594, the Re / We / Ma sweep script.  Its loop is config
+    2's loop statement for statement, except that the convective terms of the two velocity predictor steps are
+    written `Re*conv*dot(u, nabla_grad(u))` (:418, :468) where the mesh-convergence script has `conv*...`: the
+    same form functors with the parameter slot FX_P_CONV holding Re*conv."""
+
+    def __init__(self, mesh, dofmaps=None, Re=10.0, conv=1.0, **kw):
+        super().__init__(mesh, dofmaps=dofmaps, Re=Re, conv=Re * conv, **kw)

@@ -234,6 +234,7 @@ class IncompLDC(_LDCBase):
 
 class CompLDC(_LDCBase):
     """Config 2: lid-driven-cavity/comp_LDC_mesh_convergence.py time loop :376-565."""
+    RE_CONV = False
 
     def __init__(self, mesh, dofmaps=None, dt=0.001, Re=10.0, We=0.25, Ma=0.001, betav=0.5,
                  c1=0.1, c2=0.01, th=1.0, conv=1):
@@ -261,6 +262,8 @@ class CompLDC(_LDCBase):
     def _forms(self):
         S, p = self.S, self.p
         dt, Re, We, Ma, betav, th, conv = (p[k] for k in ("dt", "Re", "We", "Ma", "betav", "th", "conv"))
+        if self.RE_CONV:  # comp_LDC.py:418,468 write Re*conv*dot(u, nabla_grad(u)) where the mesh-convergence script has conv*...
+            conv = Re * conv
         W, Q, Zc = S["W"], S["Q"], S["Zc"]
         u, D_vec = fem.TrialFunction(W, (0, 1)), fem.TrialFunction(W, (2, 3, 4))
         v, R_vec = fem.TestFunction(W, (0, 1)), fem.TestFunction(W, (2, 3, 4))
@@ -365,3 +368,10 @@ class CompLDC(_LDCBase):
     def fields(self):
         return dict(w1=self.w1.vec, p1=self.p1.vec, tau1=self.tau1_vec.vec, rho1=self.rho1.vec,
                     rho12=self.rho12.vec, kapp=self.kapp.vec)
+
+
+class CompLDCSweep(CompLDC):
+    """lid-driven-cavity/comp_LDC.py time loop :364-594 (the Re/We/Ma sweep script).  Statement for statement
+    the loop of comp_LDC_mesh_convergence.py (the commented-out stress / temperature half steps aside), except
+    that the convective terms of the two velocity predictor steps carry `Re*conv` (:418, :468)."""
+    RE_CONV = True

@@ -136,3 +136,27 @@ def test_stream_function_forms(shuffle):
         for form, f in ((a, abi.FX_FORM_STREAM_A), (L, fid)):
             degs = {k: d for k, _, d in fem.quadrature_degrees(form, mesh)}
             assert plan.form_qdeg(f)[0] == degs["dx"], (f, plan.form_qdeg(f), degs)
+
+
+def test_comp_ldc_sweep_script_forms():
+    """lid-driven-cavity/comp_LDC.py:364-594 = cfg2's loop with Re*conv in the two predictor steps (:418, :468):
+    the cfg2 functors with FX_P_CONV = Re*conv reproduce the oracle's transcription of THAT script."""
+    mesh = fem.skew_mesh(5)
+    cfg = configs.CompLDCSweep(mesh, Re=3.0, conv=0.7)
+    lc.randomize(cfg)
+    plan = EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local, mesh.bfacet_marker)
+    st, par = lc.state_of(cfg), lc.params_of(cfg)
+    par[lc.PARAM_SLOT["conv"]] = 3.0 * 0.7  # what drivers.ldc.CompLDCSweep passes
+    other = configs.CompLDC(mesh, dofmaps=lc.dofmaps_of(cfg), Re=3.0, conv=0.7)
+    for name, (fid, space) in lc.C2_FORMS.items():
+        ref = fem.assemble(cfg.forms[name])
+        if name.startswith("a"):
+            err = lc.csr_rel_err(plan.assemble_matrix(fid, space, st, par), ref)
+        else:
+            err = lc.rel_err(plan.assemble_vector(fid, space, st, par), ref)
+        assert err < TOL, (name, err)
+    # and the two scripts really differ there (so the test above is not vacuous)
+    for a, b in zip(lc.FIELD_ATTR.values(), lc.FIELD_ATTR.values()):
+        if hasattr(cfg, a) and hasattr(other, a) and hasattr(getattr(cfg, a), "vec"):
+            getattr(other, a).vec[:] = getattr(cfg, a).vec
+    assert lc.rel_err(fem.assemble(other.forms["L2"]), fem.assemble(cfg.forms["L2"])) > 1e-6

@@ -372,3 +372,21 @@ def test_full_size_properties():
     res = A * x
     res.axpy(-1.0, b)
     assert res.norm("l2") < 1e-9 * b.norm("l2"), info.iterations
+
+
+def test_comp_ldc_sweep_script_steps():
+    """drivers.ldc.CompLDCSweep (lid-driven-cavity/comp_LDC.py:364-594) against the oracle's transcription of
+    that script: fields after K steps within 1e-8."""
+    m = pmesh.Skew_Mesh(8, 1, 1)
+    drv = ldc.CompLDCSweep(m, Re=5.0, We=0.5, Ma=0.01)
+    ocl = configs.CompLDCSweep(fem.Mesh(m.coordinates(), m.cells()), dofmaps={k: s.cell_dofs for k, s in drv.S.items()},
+                               Re=5.0, We=0.5, Ma=0.01)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    drv.t = ocl.t = 0.45
+    for _ in range(3):
+        ro, rd = ocl.step(), drv.step()
+        assert abs(ro["E_k"] - rd["E_k"]) < 1e-8 * abs(ro["E_k"])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
