@@ -121,6 +121,8 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
       if ((rc = upload(&d.rowblk, hp.rowblk.data(), hp.rowblk.size()))) return fail(rc);
       d.nrowblk = (int)hp.rowblk.size() - 1;
       d.rowblk_h = hp.rowblk;
+      for (int b = 0; b < d.nrowblk; ++b)
+        d.maxblknnz = std::max(d.maxblknnz, hp.rowptr[hp.rowblk[b + 1]] - hp.rowptr[hp.rowblk[b]]);
     }
     maxn = std::max(maxn, (size_t)hp.n);
   }
@@ -430,23 +432,25 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
   }
   for (int g = 0; g < k; ++g)
     if (count[g] == 0) return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: aggregate %d is empty", g);
-  // the resident CG kernel gives CTA c the row blocks c*8 .. c*8+7 (one per warp); each CTA keeps the rows of
-  // (P^T A P)^-1 of the aggregates its rows touch in shared memory
-  int grid = 0;
-  if (!pcg_resident_config(P, d.nrowblk, &grid) )
+  // the resident CG kernel gives CTA c the row blocks c*8R .. c*8R+8R-1 (R per warp); each CTA keeps the rows
+  // of (P^T A P)^-1 of the aggregates its rows touch in shared memory
+  const PcgConfig cfg = pcg_resident_config(P, d.nrowblk, d.maxblknnz);
+  if (cfg.R == 0)
     return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: space %d is too large for the resident CG kernel", space);
+  const int per_cta = 8 * cfg.R;
   int nl_max = 0;
-  for (int c = 0; c < grid; ++c) {
+  for (int c = 0; c < cfg.grid; ++c) {
     std::vector<char> seen(k, 0);
     int nl = 0;
-    for (int b = c * 8; b < std::min(d.nrowblk, c * 8 + 8); ++b)
+    for (int b = c * per_cta; b < std::min(d.nrowblk, (c + 1) * per_cta); ++b)
       for (int r = d.rowblk_h[b]; r < d.rowblk_h[b + 1]; ++r)
         if (!seen[agg[r]]) { seen[agg[r]] = 1; ++nl; }
     nl_max = std::max(nl_max, nl);
   }
-  if (nl_max > COARSE_NLMAX)
+  if (nl_max > cfg.nlmax)
     return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: a CTA's rows touch %d aggregates (limit %d): aggregates "
-                     "are not local in the dof numbering", nl_max, COARSE_NLMAX);
+                     "are not local in the dof numbering", nl_max, cfg.nlmax);
+  d.agg_nl = nl_max;
   if (!P->coarse) {
     FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * COARSE_KMAX * COARSE_KMAX + 3 * COARSE_KMAX)));
   }

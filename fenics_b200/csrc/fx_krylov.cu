@@ -34,6 +34,8 @@ __device__ __forceinline__ void stamp(int prof, int& np) {
 
 // two-level preconditioner of k_pcg_res (fx_plan_set_aggregates); agg == null: plain Jacobi
 struct Coarse {
+  int slice;       // k_pcg_res: entries of shared memory per resident row block (>= the largest block, multiple of 32)
+  int nlmax;       // k_pcg_res: rows of E^-1 a CTA can keep in shared memory (<= COARSE_NLMAX)
   const int* agg;  // [n]
   int k;           // aggregates (multiple of 32, <= COARSE_KMAX)
   double* E0;      // k x k
@@ -610,16 +612,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gmres(const __grid_constant__ KA
 //      memory for the whole solve, so an iteration issues only the m-gather and its own-row updates.
 // The recurrences lose a few digits of attainable accuracy: la_krylov selects this kernel only for
 // rtol >= 1e-9 and when the matrix fits (R <= PCG_MAXR row blocks per warp with one CTA per SM).
-constexpr int PCG_MAXR = 3;
-__host__ __device__ constexpr size_t pcg_smem_bytes(int R) {
-  return (size_t)LA_WARPS * ((size_t)R * SPMV_NNZB * (sizeof(double) + sizeof(int)) + SPMV_NNZB * sizeof(double));
+constexpr int PCG_MAXR = 4;
+// per CTA: R resident row blocks per warp (`slice` values + columns each) and one staging slice per warp.
+// P1 row blocks are row-limited (32 rows x <= 9 entries), so `slice` is ~288 rather than SPMV_NNZB = 512:
+// that is what lets R = 4 blocks per warp (148 k pressure rows, n = 384) stay resident.
+__host__ __device__ constexpr size_t pcg_smem_bytes(int R, int slice) {
+  return (size_t)LA_WARPS * ((size_t)R * slice * (sizeof(double) + sizeof(int)) + slice * sizeof(double));
 }
 
 // shared memory of the coarse correction: rows of E^-1 for the CTA's aggregates, the coarse vector, per-CTA
 // partial sums, the corrections, the aggregate list and the aggregate -> slot map
 constexpr int COARSE_LD = COARSE_KMAX + 8;  // row stride of the resident E^-1 rows (bank-conflict-free dots)
-__host__ __device__ constexpr size_t pcg_coarse_smem_bytes() {
-  return sizeof(double) * ((size_t)COARSE_NLMAX * COARSE_LD + COARSE_KMAX + 2 * COARSE_NLMAX) +
+__host__ __device__ constexpr size_t pcg_coarse_smem_bytes(int nlmax) {
+  return sizeof(double) * ((size_t)nlmax * COARSE_LD + COARSE_KMAX + 2 * COARSE_NLMAX) +
          sizeof(int) * (COARSE_NLMAX + COARSE_KMAX + 4);
 }
 
@@ -721,10 +726,10 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nw = gridDim.x * LA_WARPS, gw = blockIdx.x * LA_WARPS + wib;
   // per-warp shared slices
-  double* sval = reinterpret_cast<double*>(dyn) + (size_t)wib * R * SPMV_NNZB;
-  double* prod = reinterpret_cast<double*>(dyn) + (size_t)LA_WARPS * R * SPMV_NNZB + (size_t)wib * SPMV_NNZB;
-  int* scol = reinterpret_cast<int*>(dyn + (size_t)LA_WARPS * (R + 1) * SPMV_NNZB * sizeof(double)) +
-              (size_t)wib * R * SPMV_NNZB;
+  const int SL = a.cz.slice;
+  double* sval = reinterpret_cast<double*>(dyn) + (size_t)wib * R * SL;
+  double* prod = reinterpret_cast<double*>(dyn) + (size_t)LA_WARPS * R * SL + (size_t)wib * SL;
+  int* scol = reinterpret_cast<int*>(dyn + (size_t)LA_WARPS * (R + 1) * SL * sizeof(double)) + (size_t)wib * R * SL;
   double* r = a.w;
   double* u = a.w + n;
   double* w = a.w + 2 * n;
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
   double my_dinv[R];
 #pragma unroll
   for (int rr = 0; rr < R; ++rr) {
-    const int k = gw + rr * nw;
+    const int k = gw * R + rr;  // contiguous blocks per warp and CTA: few aggregates per CTA
     my_row[rr] = -1; my_s0[rr] = 0; my_s1[rr] = 0; blk_nnz[rr] = 0; my_dinv[rr] = 1.0;
     if (k < A.nrowblk) {
       const int r0 = A.rowblk[k], r1 = A.rowblk[k + 1];
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         my_dinv[rr] = (a.pc != FX_PC_NONE && dg != 0.0) ? 1.0 / dg : 1.0;
         for (int j = b; j < e; ++j) {
           const double v = A.val[j];
-          if (v != 0.0) { sval[rr * SPMV_NNZB + dst] = v; scol[rr * SPMV_NNZB + dst] = A.col[j]; ++dst; }
+          if (v != 0.0) { sval[rr * SL + dst] = v; scol[rr * SL + dst] = A.col[j]; ++dst; }
         }
       }
     }
@@ -777,8 +782,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
   // ---- two-level preconditioner M^-1 = D^-1 + P E^-1 P^T, E = P^T A P (aggregates a.cz.agg) --------------
   const bool coarse = a.cz.agg != nullptr;
   const int ck = a.cz.k;
-  double* einv_s = reinterpret_cast<double*>(dyn + pcg_smem_bytes(R));  // [nl][ck]
-  double* c_s = einv_s + (size_t)COARSE_NLMAX * COARSE_LD;               // [ck]
+  const int NLMAX = a.cz.nlmax;
+  double* einv_s = reinterpret_cast<double*>(dyn + pcg_smem_bytes(R, SL));  // [nl][ck]
+  double* c_s = einv_s + (size_t)NLMAX * COARSE_LD;                          // [ck]
   double* cpart = c_s + COARSE_KMAX;                                     // [nl]
   double* e_s = cpart + COARSE_NLMAX;                                    // [nl]
   int* list = reinterpret_cast<int*>(e_s + COARSE_NLMAX);                // [nl]
@@ -798,11 +804,11 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
       int cnt = 0;
       for (int g = 0; g < ck; ++g)
         if (slot_of[g] == 0) {
-          slot_of[g] = min(cnt, COARSE_NLMAX - 1);  // the host checked cnt <= COARSE_NLMAX
-          if (cnt < COARSE_NLMAX) list[cnt] = g;
+          slot_of[g] = min(cnt, NLMAX - 1);  // the host checked cnt <= NLMAX
+          if (cnt < NLMAX) list[cnt] = g;
           ++cnt;
         }
-      nl_s[0] = min(cnt, COARSE_NLMAX);
+      nl_s[0] = min(cnt, NLMAX);
     }
     __syncthreads();
     nl = nl_s[0];
@@ -817,7 +823,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
     for (int rr = 0; rr < R; ++rr)
       if (my_row[rr] >= 0)
         for (int j = my_s0[rr]; j < my_s1[rr]; ++j)
-          atomicAdd(a.cz.E0 + (size_t)my_agg[rr] * ck + a.cz.agg[scol[rr * SPMV_NNZB + j]], sval[rr * SPMV_NNZB + j]);
+          atomicAdd(a.cz.E0 + (size_t)my_agg[rr] * ck + a.cz.agg[scol[rr * SL + j]], sval[rr * SL + j]);
     bar.sync();
     const double* Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, einv_s);
     for (int sidx = 0; sidx < nl; ++sidx)
@@ -874,8 +880,8 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
       const int nnz = blk_nnz[rr];
-      const double* sv = sval + rr * SPMV_NNZB;
-      const int* sc = scol + rr * SPMV_NNZB;
+      const double* sv = sval + rr * SL;
+      const int* sc = scol + rr * SL;
       for (int jb = 0; jb < nnz; jb += 128) {
         double t[4];
 #pragma unroll
@@ -1027,7 +1033,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
 
 template <int R>
 static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
-  const size_t smem = pcg_smem_bytes(R) + (ka.cz.agg != nullptr ? pcg_coarse_smem_bytes() : 0);
+  const size_t smem = pcg_smem_bytes(R, ka.cz.slice) + (ka.cz.agg != nullptr ? pcg_coarse_smem_bytes(ka.cz.nlmax) : 0);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     FX_CUDA(cudaFuncSetAttribute(k_pcg_res<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1050,10 +1056,22 @@ static int launch_pcg_res(fx_plan* P, KArgs& ka, int grid, cudaStream_t st) {
   return FX_OK;
 }
 
-bool pcg_resident_config(const fx_plan* P, int nrowblk, int* grid) {
-  if (nrowblk > P->num_sms * LA_WARPS) return false;  // one row block per warp, one CTA per SM
-  *grid = min(P->num_sms, (nrowblk + LA_WARPS - 1) / LA_WARPS);
-  return true;
+// Configuration of the resident CG kernel for a space: R row blocks per warp (0 = does not fit), the
+// shared-memory slice per block, the grid, and how many rows of E^-1 fit beside them (two-level variant).
+PcgConfig pcg_resident_config(const fx_plan* P, int nrowblk, int maxblknnz) {
+  PcgConfig c{0, 0, 0, 0};
+  if (nrowblk <= 0) return c;
+  const int warps = P->num_sms * LA_WARPS;
+  const int R = (nrowblk + warps - 1) / warps;
+  const int slice = std::max(32, (maxblknnz + 31) / 32 * 32);
+  const size_t budget = 227 * 1024 - 4096;  // opt-in shared memory per CTA minus the static arrays
+  if (R > PCG_MAXR || pcg_smem_bytes(R, slice) > budget) return c;
+  c.R = R; c.slice = slice;
+  c.grid = std::min(P->num_sms, (nrowblk + LA_WARPS * R - 1) / (LA_WARPS * R));
+  int nl = COARSE_NLMAX;
+  while (nl > 0 && pcg_smem_bytes(R, slice) + pcg_coarse_smem_bytes(nl) > budget) --nl;
+  c.nlmax = nl;
+  return c;
 }
 
 int la_krylov(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
@@ -1064,9 +1082,9 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg, gmres available)", method);
   if (pc != FX_PC_NONE && pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE)
     return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, jacobi_coarse available)", pc);
-  int grid1 = 0;
+  const PcgConfig pcfg = pcg_resident_config(P, p.nrowblk, p.maxblknnz);
   if (pc == FX_PC_JACOBI_COARSE &&
-      (method != FX_KSP_CG || p.nagg == 0 || rtol < 1e-9 || p.nelim != 0 || !pcg_resident_config(P, p.nrowblk, &grid1)))
+      (method != FX_KSP_CG || p.nagg == 0 || rtol < 1e-9 || p.nelim != 0 || pcfg.R == 0 || p.agg_nl > pcfg.nlmax))
     return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates), "
                      "rtol >= 1e-9 and a system that fits the resident CG kernel");
   const bool part = P->dist.world > 1;  // mesh-partitioned run: fused halo pushes + cross-GPU barriers
@@ -1087,9 +1105,9 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     ka.dd.nsend = p.nsend; ka.dd.s_first = p.s_first; ka.dd.s_peer = p.s_peer;
     ka.dd.s_local = p.s_local; ka.dd.s_remote = p.s_remote;
   }
-  ka.cz = Coarse{nullptr, 0, nullptr, nullptr, nullptr};
+  ka.cz = Coarse{pcfg.slice, pcfg.nlmax, nullptr, 0, nullptr, nullptr, nullptr};
   if (pc == FX_PC_JACOBI_COARSE)
-    ka.cz = Coarse{p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX * COARSE_KMAX,
+    ka.cz = Coarse{pcfg.slice, pcfg.nlmax, p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX * COARSE_KMAX,
                    P->coarse + (size_t)2 * COARSE_KMAX * COARSE_KMAX};
   static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
   ka.prof = prof_env;
@@ -1130,14 +1148,12 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     return FX_OK;
   }
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
-  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part) {
-    const int warps = P->num_sms * LA_WARPS;
-    const int R = (p.nrowblk + warps - 1) / warps;
-    if (R <= PCG_MAXR) {
-      const int grid = min(P->num_sms, (p.nrowblk + LA_WARPS - 1) / LA_WARPS);
-      if (R <= 1) return launch_pcg_res<1>(P, ka, grid, st);
-      if (R == 2) return launch_pcg_res<2>(P, ka, grid, st);
-      return launch_pcg_res<3>(P, ka, grid, st);
+  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part && pcfg.R > 0) {
+    switch (pcfg.R) {
+      case 1: return launch_pcg_res<1>(P, ka, pcfg.grid, st);
+      case 2: return launch_pcg_res<2>(P, ka, pcfg.grid, st);
+      case 3: return launch_pcg_res<3>(P, ka, pcfg.grid, st);
+      default: return launch_pcg_res<4>(P, ka, pcfg.grid, st);
     }
   }
   // big CTAs (1024 threads, one per SM) keep the grid barrier cheap: its cost grows with the number of

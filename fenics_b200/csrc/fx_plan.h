@@ -35,8 +35,10 @@ struct DevPattern {
   int nrowblk = 0;
   // block-triangular elimination (fx_plan_set_eliminated_dofs): trailing rows solved by back-substitution
   std::vector<int> rowblk_h;  // host copy of rowblk
+  int maxblknnz = 0;          // largest pattern entry count of a row block
   int* agg = nullptr;         // [n] aggregate of each dof (fx_plan_set_aggregates), null = none
   int nagg = 0;
+  int agg_nl = 0;             // most aggregates the rows of one CTA of the resident CG kernel touch
   uint8_t* elim = nullptr;    // [n] row mask: bit 0 eliminated, bit 1 ghost, bit 2 interface (fx_la_common.cuh MASK_*)
   int* elim_rows = nullptr;   // [nelim]
   int nelim = 0;
@@ -139,7 +141,8 @@ int la_dot(fx_plan* plan, int n, const double* x, const double* y, double* out_d
 int la_norm(fx_plan* plan, int n, const double* x, int kind, double* out_dev, cudaStream_t st);
 int la_lincomb3(int n, double* out, const double* coef, const double* x, const double* y, const double* z, cudaStream_t st);
 int la_dotw(fx_plan* plan, int n, const double* x, const double* y, const double* w, double* out_dev, cudaStream_t st);
-bool pcg_resident_config(const fx_plan* plan, int nrowblk, int* grid);  // R == 1 configuration of k_pcg_res
+struct PcgConfig { int R, slice, grid, nlmax; };  // R == 0: the system does not fit the resident CG kernel
+PcgConfig pcg_resident_config(const fx_plan* plan, int nrowblk, int maxblknnz);
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
 }  // namespace fx
