@@ -415,6 +415,51 @@ struct E_C4_RESTAU {  // project(restau0, Zd)  :467
   FX_HD static void value(const PtArgs& x, double* v) { jbp_restau(x, v); }
 };
 
+// ---- post-loop adaptive-refinement indicator -------------------------------------
+// incompressible_benchmarkEWM.py:903-917, fenepmp_jbp.py:691-705, comp_ewm_jpb.py:735-747 (identical):
+//   restau0 = We/dt*(tau1_vec - tau0_vec) + We*F1R_vec + tau1_vec - I_vec,   F1R = Fdef(u1, tau1)
+//   kapp = project(inner(restau0, restau0), Qt);  tau_average = project(sum(tau1_vec)/3, Qt);
+//   error_rat = |project(kapp/(tau_average + eps), Qt)|
+struct E_ADAPT_RES_SQ {  // degree: restau0 3 (u1 . grad tau1: 2 + 1), squared -> 6
+  static constexpr int QDEG = 6, NOUT = 1;
+  FX_HD static void value(const PtArgs& x, double* v) {
+    P2Phys b;
+    p2_phys(x.xi, x.et, x.g, b);
+    const double* p = x.p.v;
+    const Vel u = eval_vel(x.m, x.s.f[F_W1], x.cell, b);
+    const Tau t1 = eval_tau(x.m, x.s.f[F_TAU1], x.cell, b);
+    const Tau t0 = eval_tau(x.m, x.s.f[F_TAU0], x.cell, b);
+    const double We = p[P_WE], wd = We / p[P_DT];
+    const double dv = u.g00 + u.g11;
+    const double a0 = t1.t0.v, a1 = t1.t1.v, a2 = t1.t2.v;
+    const double F00 = u.u0 * t1.t0.x + u.u1 * t1.t1.x - 2.0 * (u.g00 * a0 + u.g01 * a1) + dv * a0;
+    const double F10 = u.u0 * t1.t1.x + u.u1 * t1.t2.x - (u.g10 * a0 + u.g11 * a1) - (a1 * u.g00 + a2 * u.g01)
+                       + dv * a1;
+    const double F11 = u.u0 * t1.t1.y + u.u1 * t1.t2.y - 2.0 * (u.g10 * a1 + u.g11 * a2) + dv * a2;
+    const double r0 = wd * (a0 - t0.t0.v) + We * F00 + a0 - 1.0;
+    const double r1 = wd * (a1 - t0.t1.v) + We * F10 + a1;
+    const double r2 = wd * (a2 - t0.t2.v) + We * F11 + a2 - 1.0;
+    v[0] = r0 * r0 + r1 * r1 + r2 * r2;
+  }
+};
+struct E_TAU_AVG {  // project((tau1_vec[0]+tau1_vec[1]+tau1_vec[2])/3.0, Qt)
+  static constexpr int QDEG = 2, NOUT = 1;
+  FX_HD static void value(const PtArgs& x, double* v) {
+    P2Phys b;
+    p2_phys(x.xi, x.et, x.g, b);
+    const Tau t = eval_tau(x.m, x.s.f[F_TAU1], x.cell, b);
+    v[0] = (t.t0.v + t.t1.v + t.t2.v) / 3.0;
+  }
+};
+struct E_ABS_KAPP_RATIO {  // absolute(project(kapp/(tau_average + eps), Qt)); tau_average in FX_F_QT_A, eps = FX_P_EPS
+  static constexpr int QDEG = 0, NOUT = 1;
+  FX_HD static void value(const PtArgs& x, double* v) {
+    const double k = eval_dg0(x.s.f[F_KAPP], x.m.dm[S_QT], x.m.nc, x.cell, 0);
+    const double ta = eval_dg0(x.s.f[F_QT_A], x.m.dm[S_QT], x.m.nc, x.cell, 0);
+    v[0] = fabs(k / (ta + x.p.v[P_EPS]));
+  }
+};
+
 // ---- functionals ---------------------------------------------------------------------------------
 struct C4_EE {  // (fene_func(tau1,b)*(tau1[0,0]+tau1[1,1]) - 2.)*dx   :636
   static constexpr int QDEG = 4;

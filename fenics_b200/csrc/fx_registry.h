@@ -120,7 +120,10 @@
   X(FX_EXPR_SQRT_QT_A, fx::ldc::E_SQRT_QT_A)      \
   X(FX_EXPR_H_KAPP, fx::ldc::E_H_KAPP)            \
   X(FX_EXPR_C4_RESTAU, fx::jbp::E_C4_RESTAU)      \
-  X(FX_EXPR_C5_RESTAU, fx::dgp::E_C5_RESTAU)
+  X(FX_EXPR_C5_RESTAU, fx::dgp::E_C5_RESTAU)      \
+  X(FX_EXPR_ADAPT_RES_SQ, fx::jbp::E_ADAPT_RES_SQ) \
+  X(FX_EXPR_TAU_AVG, fx::jbp::E_TAU_AVG)          \
+  X(FX_EXPR_ABS_KAPP_RATIO, fx::jbp::E_ABS_KAPP_RATIO)
 
 namespace fx {
 template <class F> constexpr bool has_facet() { return F::Facet::present; }

@@ -24,6 +24,7 @@ DOLFIN_EPS = 3.0e-16
 
 class EwmJBP(FenepmpJBP):
     direct_rtol = 1e-12
+    REFINE_RATIO, REFINE_EPS, MAX_REFINE = 0.2, DOLFIN_EPS, 2   # incompressible_benchmarkEWM.py:912,915; max_refine :52
 
     def __init__(self, mesh=None, dofmaps=None, dt=None, prepass=False, Re=10.0, We=0.000001, Ma=0.000001,
                  betav=1.0 - DOLFIN_EPS, A_0=0.0, k_ewm=0.0, B=0.0, al=0.001, Di=0.0025, Vh=0.0000069, Bi=0.2,

@@ -10,8 +10,11 @@ temperature, then the energies and the journal torque / load functionals on ds(0
 import csv
 
 import numpy as np
+import torch
 
 from .. import _abi as abi
+from .. import la
+from .._lib import check, lib
 from ..dolfin_api import ConsistentProjection, DirichletBC, Function, assemble_scalar_async, project
 from ..mesh import annulus_mesh
 from .ldc import _LDC
@@ -126,6 +129,46 @@ class FenepmpJBP(_LDC):
         t_rec = self.t
         self.t += self.p["dt"]                          # :690
         return self._result(t_rec, vals, dict(E_k=0, E_e=1, torque=2, F_x=3, F_y=4))
+
+    # -- post-loop adaptive refinement -------------------------------------------------
+    REFINE_RATIO, REFINE_EPS, MAX_REFINE = 0.3, 0.000001, 1   # fenepmp_jbp.py:701,704,708
+
+    def refinement_indicator(self, err_count=0):
+        """The stress-residual error indicator the journal-bearing scripts evaluate after a time loop
+        (fenepmp_jbp.py:691-711; the same statements at incompressible_benchmarkEWM.py:903-924 and
+        comp_ewm_jpb.py:735-753 with other constants):
+
+            kapp = project(inner(restau0, restau0), Qt);  norm_kapp = normalize_solution(kapp)   # in place
+            ratio = REFINE_RATIO/(err_count + 1);  tau_average = project(sum(tau1_vec)/3, Qt)
+            error_rat = absolute(project(kapp/(tau_average + eps), Qt))
+            refine iff error_rat.max() > 0.01 and err_count < MAX_REFINE
+
+        The three projections and the max run on the device; `markers` is what adaptive_refinement
+        (fenics_base.py:143-155) hands to dolfin's refine(): kapp at the cell midpoint (= the cell's DG0 value)
+        above the (1-ratio) percentile.  refine() itself and the rebuild of the plan on the new mesh stay with
+        dolfin / the caller.  Overwrites `kapp` (the next loop's first step recomputes the LPS indicator)."""
+        e, Qt = self.pr.expr, self.S["Qt"]
+        if not hasattr(self, "_error_rat"):
+            self._error_rat = Function(Qt, self.plan)
+            self._scale = torch.zeros(3, dtype=torch.float64, device=self.scal.device)
+        project(e(abi.FX_EXPR_ADAPT_RES_SQ), Qt, function=self.kapp)
+        kv = self.kapp.vector()
+        kmax = kv.norm("linf")                                         # normalize_solution: u /= max|u|
+        self._scale[0] = 1.0 / kmax
+        check(lib.fx_lincomb3_dev(kv.size(), la._ptr(kv.t), la._ptr(self._scale), la._ptr(kv.t), la._ptr(kv.t),
+                                  la._ptr(kv.t), la._stream()))
+        ratio = self.REFINE_RATIO / (1 * err_count + 1.0)
+        project(e(abi.FX_EXPR_TAU_AVG), Qt, function=self.res_orth_norm_sq)   # tau_average in the Qt scratch slot
+        eps_loop = self.pr.params[abi.FX_P_EPS]
+        self.pr.set_param(abi.FX_P_EPS, self.REFINE_EPS)
+        project(e(abi.FX_EXPR_ABS_KAPP_RATIO), Qt, function=self._error_rat)
+        self.pr.set_param(abi.FX_P_EPS, eps_loop)
+        err_max = self._error_rat.vector().norm("linf")
+        kapp = kv.get_local()
+        level = np.percentile(kapp, (1 - ratio) * 100)                  # adaptive_refinement(mesh, norm_kapp, ratio)
+        markers = kapp[np.asarray(Qt.cell_dofs)[:, 0]] > level
+        return dict(kapp=kapp, error_rat=self._error_rat.vector().get_local(), error_rat_max=err_max, ratio=ratio,
+                    refine=bool(err_max > 0.01 and err_count < self.MAX_REFINE), markers=markers)
 
     def fields(self):
         g = lambda fn: fn.vector().get_local()  # noqa: E731

@@ -122,7 +122,12 @@ typedef enum {
   FX_EXPR_SQRT_QT_A,        /* (QT_A)**0.5 -> Qt (:307-308)                                */
   FX_EXPR_H_KAPP,           /* h*kapp -> Qt (:434)                                         */
   FX_EXPR_C4_RESTAU,        /* cfg4 restau0 -> Zd (fenepmp_jbp.py:462-467)                 */
-  FX_EXPR_C5_RESTAU         /* cfg5 restau0 -> Zd (compressible_dgp.py:382-386)            */
+  FX_EXPR_C5_RESTAU,        /* cfg5 restau0 -> Zd (compressible_dgp.py:382-386)            */
+  /* post-loop adaptive-refinement indicator of the journal-bearing scripts (incompressible_benchmarkEWM.py:903-917,
+   * fenepmp_jbp.py:691-705, comp_ewm_jpb.py:735-747); refine() itself stays in dolfin                              */
+  FX_EXPR_ADAPT_RES_SQ,     /* inner(restau0,restau0) -> Qt, restau0 = We/dt (tau1-tau0) + We Fdef(u1,tau1) + tau1 - I */
+  FX_EXPR_TAU_AVG,          /* (tau1_vec[0]+tau1_vec[1]+tau1_vec[2])/3 -> Qt                */
+  FX_EXPR_ABS_KAPP_RATIO    /* |FX_F_KAPP / (FX_F_QT_A + FX_P_EPS)| -> Qt                   */
 } fx_expr;
 
 typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;

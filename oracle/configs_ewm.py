@@ -31,6 +31,7 @@ def phi_ewm(tau, T, k, B):  # fenics_base.py:240-241
 
 class EwmJBP(FenepmpJBP):
     """Config 3.  Geometry / markers / BC objects as config 4 (:262-302); parameters :56-100, :304-307."""
+    REFINE_RATIO, REFINE_EPS, MAX_REFINE = 0.2, fem.DOLFIN_EPS, 2  # incompressible_benchmarkEWM.py:912,915; max_refine :52
 
     def __init__(self, mesh, dofmaps=None, dt=None, prepass=False, Re=10, We=0.000001, Ma=0.000001,
                  betav=1.0 - fem.DOLFIN_EPS, A_0=0.0, k_ewm=0.0, B=0.0, al=0.001, Di=0.0025, Vh=0.0000069, Bi=0.2,

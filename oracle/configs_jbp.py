@@ -238,6 +238,31 @@ class FenepmpJBP:
         self.t += self.p["dt"]
         return out
 
+    REFINE_RATIO, REFINE_EPS, MAX_REFINE = 0.3, 0.000001, 1  # fenepmp_jbp.py:701,704,708
+
+    def refinement_indicator(self, err_count=0):
+        """post-loop adaptive-refinement indicator, fenepmp_jbp.py:691-711 (same statements at
+        incompressible_benchmarkEWM.py:903-924, comp_ewm_jpb.py:735-753) + adaptive_refinement's cell marking
+        (fenics_base.py:143-155)."""
+        S, p = self.S, self.p
+        We, dt = p["We"], p["dt"]
+        tau0_vec, tau1_vec = self.tau0_vec.expr(), self.tau1_vec.expr()
+        F1R = Fdef(self.u1, self.tau1)
+        F1R_vec = as_vector([F1R[0, 0], F1R[1, 0], F1R[1, 1]])
+        restau0 = We / dt * (tau1_vec - tau0_vec) + We * F1R_vec + tau1_vec - self.I_vec
+        res_test = inner(restau0, restau0)
+        kapp = fem.project(res_test, S["Qt"])
+        kapp.vec[:] = kapp.vec / np.max(np.abs(kapp.vec))  # normalize_solution (in place: norm_kapp is kapp)
+        ratio = self.REFINE_RATIO / (1 * err_count + 1.0)
+        tau_average = fem.project((tau1_vec[0] + tau1_vec[1] + tau1_vec[2]) / 3.0, S["Qt"])
+        error_rat = fem.project(kapp.expr() / (tau_average.expr() + self.REFINE_EPS), S["Qt"])
+        error_rat.vec[:] = np.absolute(error_rat.vec)
+        level = np.percentile(kapp.vec, (1 - ratio) * 100)
+        markers = kapp.vec[np.asarray(S["Qt"].cell_dofs)[:, 0]] > level  # kapp(cell midpoint) > kapp_level
+        self.res_sq_form = res_test
+        return dict(kapp=kapp.vec.copy(), error_rat=error_rat.vec.copy(), error_rat_max=float(error_rat.vec.max()),
+                    ratio=ratio, refine=bool(error_rat.vec.max() > 0.01 and err_count < self.MAX_REFINE), markers=markers)
+
     def fields(self):
         return dict(w1=self.w1.vec, p1=self.p1.vec, tau1=self.tau1_vec.vec, rho1=self.rho1.vec, T1=self.T1.vec,
                     kapp=self.kapp.vec)

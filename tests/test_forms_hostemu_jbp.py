@@ -78,3 +78,23 @@ def test_cfg4_lps_and_functionals():
         degs = {k: d for k, _, d in fem.quadrature_degrees(form, mesh)}
         q = plan.form_qdeg(fid)
         assert (q[0], q[1]) == (degs.get("dx", -1), degs.get("ds", -1)), (fid, q, degs)
+
+
+def test_adaptive_refinement_indicator_exprs():
+    """the three DG0 projections of the post-loop refinement indicator (fenepmp_jbp.py:691-705) against the
+    oracle, with UFL's quadrature degree for inner(restau0, restau0)."""
+    mesh, cfg, plan = _setup()
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    ref = cfg.refinement_indicator(err_count=0)
+    qd = [d for k, _, d in fem.quadrature_degrees(cfg.res_sq_form * dx, mesh) if k == "dx"][0]
+    assert qd == 6
+    kapp = plan.project_dg0(abi.FX_EXPR_ADAPT_RES_SQ, "Qt", st, par)
+    kapp = kapp / np.abs(kapp).max()
+    assert lc.rel_err(kapp, ref["kapp"]) < TOL
+    tau_avg = plan.project_dg0(abi.FX_EXPR_TAU_AVG, "Qt", st, par)
+    st2, par2 = dict(st), dict(par)
+    st2[abi.FX_F_KAPP], st2[abi.FX_F_QT_A] = kapp, tau_avg
+    par2[abi.FX_P_EPS] = cfg.REFINE_EPS
+    err = plan.project_dg0(abi.FX_EXPR_ABS_KAPP_RATIO, "Qt", st2, par2)
+    assert lc.rel_err(err, ref["error_rat"]) < 1e-11
+    assert ref["markers"].sum() in range(int(0.25 * len(kapp)), int(0.35 * len(kapp)) + 1)  # ratio 0.3 of the cells

@@ -90,3 +90,25 @@ def test_cfg4_ensemble_single_rank():
     res = ensemble.run_fenepmp_sweep(steps=2, n_theta=16, n_r=4)
     assert len(res) == 12 and [r["We"] for r in res[:4]] == [0.001, 0.1, 0.5, 1.0]
     assert all(np.isfinite(r["torque"]) and np.isfinite(r["chi"]) for r in res)
+
+
+def test_adaptive_refinement_indicator_matches_oracle():
+    """post-loop refinement indicator (fenepmp_jbp.py:691-711 + fenics_base.py:143-155): normalised kapp, error
+    ratio, the refine decision and the cell markers handed to dolfin's refine()."""
+    ocl, drv = _pair(nt=24, nr=6, We=0.5)
+    jb.randomize(ocl)
+    _push(ocl, drv)
+    eps_before = drv.pr.params[abi.FX_P_EPS]
+    for err_count in (0, 1):
+        ro, rd = ocl.refinement_indicator(err_count), drv.refinement_indicator(err_count)
+        assert lc.rel_err(rd["kapp"], ro["kapp"]) < TOL
+        assert lc.rel_err(rd["error_rat"], ro["error_rat"]) < 1e-11
+        assert abs(rd["error_rat_max"] - ro["error_rat_max"]) < 1e-11 * ro["error_rat_max"]
+        assert rd["ratio"] == ro["ratio"] and rd["refine"] == ro["refine"]
+        # markers can only differ on cells whose kapp sits within rounding of the percentile level
+        lvl = np.percentile(ro["kapp"], (1 - ro["ratio"]) * 100)
+        diff = rd["markers"] != ro["markers"]
+        kc = ro["kapp"][np.asarray(ocl.S["Qt"].cell_dofs)[:, 0]]
+        assert np.all(np.abs(kc[diff] - lvl) < 1e-12)
+        assert abs(rd["markers"].mean() - ro["ratio"]) < 0.02
+    assert drv.pr.params[abi.FX_P_EPS] == eps_before  # the loop's SU epsilon is restored
