@@ -218,9 +218,15 @@ static int check_form_params(int form, const AsmArgs& a) {
   if (form >= FX_FORM_C4_A0 && form <= FX_FORM_C4_FORCE_Y && a.p.v[jbp::P_LAMBDA_D] != 0.0)
     return set_error(FX_ERR_UNSUPPORTED, "config-4 forms are implemented for lambda_D = 0 only (got %g)",
                      a.p.v[jbp::P_LAMBDA_D]);
-  if (form >= FX_FORM_C3_A0 && form <= FX_FORM_C3_FORCE_Y && (a.p.v[jbp::P_A0] != 0.0 || a.p.v[ldc::P_CONV] == 0.0))
-    return set_error(FX_ERR_UNSUPPORTED, "config-3 forms are implemented for A_0 = 0 and conv != 0 only (got %g, %g)",
-                     a.p.v[jbp::P_A0], a.p.v[ldc::P_CONV]);
+  if (form >= FX_FORM_C3_A0 && form <= FX_FORM_C3_FORCE_Y && a.p.v[ldc::P_CONV] == 0.0)
+    return set_error(FX_ERR_UNSUPPORTED, "config-3 forms are implemented for conv != 0 only");
+  // the FX_FORM_C3_* functors below fold phi_s == phi_ewm == 1 (the script's A_0 = k_ewm = B = 0); the true EWM
+  // model goes through their FX_FORM_C3E_* counterparts
+  const bool folded = form == FX_FORM_C3_A1 || form == FX_FORM_C3_L1 || form == FX_FORM_C3_L2 || form == FX_FORM_C3_A4 ||
+                      form == FX_FORM_C3_L4 || form == FX_FORM_C3_L9;
+  if (folded && (a.p.v[jbp::P_A0] != 0.0 || a.p.v[jbp::P_K_EWM] != 0.0 || a.p.v[jbp::P_B_EWM] != 0.0))
+    return set_error(FX_ERR_UNSUPPORTED, "form %d assumes A_0 = k_ewm = B = 0 (got %g, %g, %g): use the FX_FORM_C3E_* forms",
+                     form, a.p.v[jbp::P_A0], a.p.v[jbp::P_K_EWM], a.p.v[jbp::P_B_EWM]);
   return FX_OK;
 }
 

@@ -19,12 +19,13 @@
 // Phase 1 stages the pointwise data of 32 cells x NQ points in shared memory; phase 2 computes
 // one row of the element tensor per thread in registers and scatter-adds it.
 #pragma once
+#include "../../include/fenics_b200.h"  // FX_NFIELDS / FX_NPARAMS: one source of truth for the table sizes
 #include "fx_elements.h"
 
 namespace fx {
 
-constexpr int NFIELDS = 24;
-constexpr int NPARAMS = 24;
+constexpr int NFIELDS = FX_NFIELDS;
+constexpr int NPARAMS = FX_NPARAMS;
 constexpr int CB = 32;  // cells per block
 
 struct MeshView {

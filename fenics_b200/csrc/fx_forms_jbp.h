@@ -15,7 +15,8 @@ namespace jbp {
 
 using namespace ldc;  // slot enums, shared building blocks
 
-enum : int { P_PR = 9, P_RA, P_DI, P_VH, P_BI, P_T0, P_TH_HOT, P_AL1, P_AL2, P_LAMBDA_D, P_B_FENE, P_A0, P_EPS, P_T };
+enum : int { P_PR = 9, P_RA, P_DI, P_VH, P_BI, P_T0, P_TH_HOT, P_AL1, P_AL2, P_LAMBDA_D, P_B_FENE, P_A0, P_EPS, P_T,
+             P_K_EWM, P_B_EWM, P_TH_T };
 
 FX_HD double fene_f(double t0, double t2, double b) { return 1.0 / (1.0 - (fabs(t0 + t2) - 2.0) / (b * b)); }
 FX_HD double sgn(double x) { return (x > 0.0) - (x < 0.0); }

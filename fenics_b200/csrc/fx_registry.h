@@ -31,6 +31,8 @@
   X(FX_FORM_C3_A7, fx::ewm::C3_A7)          \
   X(FX_FORM_C3_A4, fx::ewm::C3_A4)          \
   X(FX_FORM_C3_A9, fx::ewm::C3_A9)          \
+  X(FX_FORM_C3E_A1, fx::ewm::C3E_A1)        \
+  X(FX_FORM_C3E_A4, fx::ewm::C3E_A4)        \
   X(FX_FORM_C4_A0, fx::ldc::C2_A0)          \
   X(FX_FORM_C4_A2, fx::jbp::C4_A2)          \
   X(FX_FORM_C4_A5, fx::jbp::C4_A5)          \
@@ -71,6 +73,10 @@
   X(FX_FORM_C3_L7, fx::ewm::C3_L7)                          \
   X(FX_FORM_C3_L4, fx::ewm::C3_L4)                          \
   X(FX_FORM_C3_L9, fx::ewm::C3_L9)                          \
+  X(FX_FORM_C3E_L1, fx::ewm::C3E_L1)                        \
+  X(FX_FORM_C3E_L2, fx::ewm::C3E_L2)                        \
+  X(FX_FORM_C3E_L4, fx::ewm::C3E_L4)                        \
+  X(FX_FORM_C3E_L9, fx::ewm::C3E_L9)                        \
   X(FX_FORM_C4_L0, fx::ldc::C2_L0)                          \
   X(FX_FORM_C4_L2, fx::jbp::C4_L2)                          \
   X(FX_FORM_C4_L5, fx::jbp::C4_L5)                          \

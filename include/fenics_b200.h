@@ -60,7 +60,9 @@ typedef enum {
   FX_P_DT = 0, FX_P_RE, FX_P_WE, FX_P_BETAV, FX_P_C1, FX_P_C2, FX_P_TH, FX_P_CONV, FX_P_MA,
   FX_P_PR, FX_P_RA, FX_P_DI, FX_P_VH, FX_P_BI, FX_P_T0, FX_P_TH_HOT, FX_P_AL1, FX_P_AL2,
   FX_P_LAMBDA_D, FX_P_B_FENE, FX_P_A0, FX_P_EPS, FX_P_T,
-  FX_NPARAMS = 24
+  FX_P_K_EWM, FX_P_B_EWM,  /* extended White-Metzner exponents k_ewm, B (comp_ewm_jpb.py:89-90)             */
+  FX_P_TH_T,               /* weight of the temperature DEVSS terms: th (incompressible_benchmarkEWM.py:650) or 0 */
+  FX_NPARAMS = 32
 } fx_param;
 
 /* Forms.  Bilinear forms produce CSR values on the pattern of their space, linear forms a vector,
@@ -92,9 +94,13 @@ typedef enum {
    * A_0 = k_ewm = B = 0 (time loop :465-782; parameter FX_P_AL1 carries `al`): bilinear */
   FX_FORM_C3_A0 = 300, FX_FORM_C3_A1, FX_FORM_C3_A2, FX_FORM_C3_A5, FX_FORM_C3_A6, FX_FORM_C3_A7, FX_FORM_C3_A4,
   FX_FORM_C3_A9,
+  /* true extended White-Metzner variants (comp_ewm_jpb.py:421-732: A_0, k_ewm, B != 0 -> non-constant phi_s, phi_ewm);
+   * the other forms of that loop are the FX_FORM_C3_* ones (A2 already carries phi_s) */
+  FX_FORM_C3E_A1, FX_FORM_C3E_A4,
   /* cfg3: linear */
   FX_FORM_C3_L0 = 320, FX_FORM_C3_L1, FX_FORM_C3_L2, FX_FORM_C3_L5, FX_FORM_C3_L6, FX_FORM_C3_L7, FX_FORM_C3_L4,
   FX_FORM_C3_L9,
+  FX_FORM_C3E_L1, FX_FORM_C3E_L2, FX_FORM_C3E_L4, FX_FORM_C3E_L9,
   /* cfg3: functionals; torque / forces over ds(0) with sigmacon (:690-707) */
   FX_FORM_C3_EK = 340, FX_FORM_C3_EE, FX_FORM_C3_TORQUE, FX_FORM_C3_FORCE_X, FX_FORM_C3_FORCE_Y,
   /* cfg4 = "flow between eccentrically rotating cylinders"/fenepmp_jbp.py (lambda_D = 0): bilinear */

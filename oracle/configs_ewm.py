@@ -32,6 +32,9 @@ def phi_ewm(tau, T, k, B):  # fenics_base.py:240-241
 class EwmJBP(FenepmpJBP):
     """Config 3.  Geometry / markers / BC objects as config 4 (:262-302); parameters :56-100, :304-307."""
     REFINE_RATIO, REFINE_EPS, MAX_REFINE = 0.2, fem.DOLFIN_EPS, 2  # incompressible_benchmarkEWM.py:912,915; max_refine :52
+    SU_RHO_EPS = 0.0000000001  # alpha_supg = h/(magnitude(u12)+0.0000000001) :603
+    TEMP_DEVSS = True          # a9 += th*DEVSSl_T1 :650
+    ALWAYS_STRESS = False      # stress solve only `if We > 0.00001 or adaptive_loop == False ...` :660
 
     def __init__(self, mesh, dofmaps=None, dt=None, prepass=False, Re=10, We=0.000001, Ma=0.000001,
                  betav=1.0 - fem.DOLFIN_EPS, A_0=0.0, k_ewm=0.0, B=0.0, al=0.001, Di=0.0025, Vh=0.0000069, Bi=0.2,
@@ -43,6 +46,7 @@ class EwmJBP(FenepmpJBP):
         super().__init__(mesh, dofmaps, dt=dt, Re=Re, We=We, Ma=Ma, lambda_d=0.0, betav=betav, A_0=A_0, Di=Di, Vh=Vh,
                          Bi=Bi, T_0=T_0, T_h=T_h, th=th, conv=conv, x_1=x_1, **geo)
         self.p["al1"] = al
+        self.p.update(k_ewm=k_ewm, b_ewm=B, th_t=(th if self.TEMP_DEVSS else 0.0))
 
     def _forms(self):
         S, p = self.S, self.p
@@ -111,7 +115,7 @@ class EwmJBP(FenepmpJBP):
         a5 = inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx
         L5 = inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx
         # density update :603-615
-        alpha_supg = h / (magnitude(u12) + 0.0000000001)
+        alpha_supg = h / (magnitude(u12) + self.SU_RHO_EPS)
         SU_rho = inner(dot(u12, grad(rho)), alpha_supg * dot(u12, grad(q))) * dx
         rho_weak = inner((rho - rho0) / dt + dot(u12, grad(rho12)) - rho12 * div(u12), q) * dx
         a6, L6 = lhs(rho_weak), rhs(rho_weak)
@@ -128,8 +132,12 @@ class EwmJBP(FenepmpJBP):
         diffrhs_temp1 = Di * grad(thetar)
         a9 = inner(lhs_temp1, r) * dx + inner(difflhs_temp1, grad(r)) * dx
         L9 = inner(rhs_temp1, r) * dx + inner(diffrhs_temp1, grad(r)) * dx - Di * Bi * inner(theta0, r) * ds(1)
-        a9 += th * DEVSSl_T1
-        L9 += th * DEVSSr_T1
+        if self.TEMP_DEVSS:
+            a9 += th * DEVSSl_T1
+            L9 += th * DEVSSr_T1
+        else:  # comp_ewm_jpb.py: `a9+= 0.0*th*DEVSSl_T1` -- UFL folds the product to Zero
+            a9 += 0.0 * th * DEVSSl_T1
+            L9 += 0.0 * th * DEVSSr_T1
         # stress :660-677
         lhs_tau1 = (We * phi_ewm(tau0, theta1, k_ewm, B) / dt + 1.0) * tau \
             + We * phi_ewm(tau0, theta1, k_ewm, B) * FdefG(u1, D1, tau)
@@ -173,10 +181,26 @@ class EwmJBP(FenepmpJBP):
         system("a6", "L6", self.rho1, [])
         system("a7", "L7", self.w1, self.bcu)
         system("a9", "L9", self.T1, self.bcT)
-        if self.p["We"] > 0.00001 or self.prepass:  # :660
+        if self.p["We"] > 0.00001 or self.prepass or self.ALWAYS_STRESS:  # :660
             system("a4", "L4", self.tau1_vec, [])
         out = dict(t=self.t, E_k=fem.assemble(self.E_k_form), E_e=fem.assemble(self.E_e_form),
                    torque=fem.assemble(self.torque_form), F_x=fem.assemble(self.force_x_form),
                    F_y=fem.assemble(self.force_y_form))
         self.t += self.p["dt"]
         return out
+
+
+class CompEwmJBP(EwmJBP):
+    """"flow between eccentrically rotating cylinders"/comp_ewm_jpb.py time loop :421-732 -- the TRUE extended
+    White-Metzner model: A_0 = 120, k_ewm = -0.7, B = 0.1 (:88-90), so phi_s(theta0) and phi_ewm(tau, theta1) are
+    genuine coefficient functions.  Statement for statement the loop of incompressible_benchmarkEWM.py except:
+    the SU weight of the density update uses DOLFIN_EPS (`h/(magnitude(u12)+DOLFIN_EPS)`), the temperature DEVSS
+    terms are multiplied by the literal 0.0 (`a9+= 0.0*th*DEVSSl_T1`), and the stress solve is unconditional."""
+    SU_RHO_EPS = fem.DOLFIN_EPS
+    TEMP_DEVSS = False
+    ALWAYS_STRESS = True
+
+    def __init__(self, mesh, dofmaps=None, dt=None, Re=50.0, We=0.5, Ma=0.01, betav=0.5, A_0=120.0, k_ewm=-0.7, B=0.1,
+                 x_1=-0.80, **kw):
+        super().__init__(mesh, dofmaps, dt=dt, prepass=False, Re=Re, We=We, Ma=Ma, betav=betav, A_0=A_0, k_ewm=k_ewm,
+                         B=B, x_1=x_1, **kw)

@@ -8,7 +8,9 @@ _mod = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_mod)
 build = _mod.build
 
-NSPACES, NFIELDS, NPARAMS = 7, 24, 24
+from fenics_b200 import _abi as _abi_consts  # noqa: E402
+
+NSPACES, NFIELDS, NPARAMS = _abi_consts.NSPACES, _abi_consts.NFIELDS, _abi_consts.NPARAMS
 SPACES = {"W": 0, "Zc": 1, "Q": 2, "Zd": 3, "Qt": 4, "V": 5, "Vs": 6}
 LD = {"W": 15, "Zc": 18, "Q": 3, "Zd": 3, "Qt": 1, "V": 12, "Vs": 6}
 

@@ -53,14 +53,56 @@ def test_cfg3_forms_and_functionals_match_oracle(kw):
         assert np.array_equal(bo.dofs, bd.dofs)
 
 
-def test_cfg3_unsupported_material_functions_are_rejected_loudly():
-    with pytest.raises(NotImplementedError):
-        ewm.EwmJBP(n_theta=8, n_r=2, k_ewm=0.5)
+def test_cfg3_folded_functors_reject_material_functions_loudly():
+    """the FX_FORM_C3_* functors fold phi_s = phi_ewm = 1: with non-zero A_0 / k_ewm / B they refuse and name the
+    FX_FORM_C3E_* forms (which the driver picks by itself)."""
     _, drv = _pair(nt=8, nr=2)
     drv.pr.set_param(abi.FX_P_A0, 1.0)
     with pytest.raises(Exception) as e:
         dapi.assemble(drv.pr.form(abi.FX_FORM_C3_A1))
-    assert "A_0" in str(e.value)
+    assert "A_0" in str(e.value) and "C3E" in str(e.value)
+    assert ewm.EwmJBP(n_theta=8, n_r=2, k_ewm=0.5).ewm
+
+
+def _pair_comp(nt=16, nr=4, **kw):
+    from oracle.configs_ewm import CompEwmJBP as OracleComp
+    drv = ewm.CompEwmJBP(n_theta=nt, n_r=nr, **kw)
+    m = drv.mesh
+    om = fem.Mesh(m.coordinates(), m.cells())
+    ocl = OracleComp(om, dofmaps={k: s.cell_dofs for k, s in drv.S.items()}, **kw)
+    assert abs(ocl.p["dt"] - drv.p["dt"]) < 1e-15 * drv.p["dt"]
+    return ocl, drv
+
+
+def test_true_ewm_forms_match_oracle():
+    """comp_ewm_jpb.py: non-constant phi_s / phi_ewm through the C3E functors on the device."""
+    ocl, drv = _pair_comp(**ew.EWM_GENERAL)
+    ew.randomize(ocl)
+    _push(ocl, drv)
+    for name, (fid, space) in ew.C3E_FORMS.items():
+        drv.pr.set_param(abi.FX_P_EPS, drv.SU_RHO_EPS if name == "a6" else drv.SU_EPS)
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        err = lc.csr_rel_err(got.to_scipy(), ref) if name.startswith("a") else lc.rel_err(got.get_local(), ref)
+        assert err < TOL, (name, err)
+
+
+def test_true_ewm_k_steps_match_oracle():
+    """drivers.ewm.CompEwmJBP (comp_ewm_jpb.py:421-732, A_0 = 120, k_ewm = -0.7, B = 0.1) against the oracle's
+    transcription of that script: fields and journal load / torque after K steps within 1e-8."""
+    K = 3
+    ocl, drv = _pair_comp(nt=24, nr=6, **ew.EWM_GENERAL)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    ocl.t = drv.t = 0.45
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        for k in ("E_k", "torque", "F_x", "F_y"):
+            assert abs(ro[k] - rd[k]) < 1e-8 * max(abs(ro[k]), 1e-10), (k, ro[k], rd[k])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in ("w1", "p1", "tau1", "rho1", "T1"):
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+    assert len(drv.last_info) == 8 and all(i.converged == 1 for i in drv.last_info)
 
 
 @pytest.mark.parametrize("prepass", [True, False])
