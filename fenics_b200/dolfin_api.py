@@ -55,6 +55,7 @@ class Problem:
     def bind(self, slot, fn):
         self.fields[slot] = fn
         self._table[slot] = fn.vector().t.data_ptr()
+        fn._driver = getattr(self, "owner", None)
         return fn
 
     def set_param(self, slot, value):

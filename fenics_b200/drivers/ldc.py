@@ -89,6 +89,7 @@ class _LDC:
         self.plan = Plan(mesh, [W, Zc, Q, Zd, Qt, V, Vs], device)
         self.set_devss_elimination(self.eliminate_devss)
         self.pr = Problem(self.plan)
+        self.pr.owner = self  # Functions bound to the tables know their time loop (shims: stream_function(u))
         for k, v in self.p.items():
             self.pr.set_param(getattr(abi, "FX_P_" + k.upper()), v)
         F = lambda s: Function(self.S[s], self.plan)  # noqa: E731

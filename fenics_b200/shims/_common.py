@@ -1,0 +1,247 @@
+"""Shared implementation of the three shim modules (see package docstring)."""
+import math
+import os
+import sys
+
+import numpy as np
+
+from .. import mesh as _mesh
+from ..dolfin_api import Function
+
+pi = 3.14159265359  # the reference pins this literal (lid-driven-cavity/fenics_fem.py:20)
+DOLFIN_EPS = 3.0e-16
+
+# ---- algebra namespace of the symbolic helpers -----------------------------------------------------
+_ALG = None
+
+
+def set_algebra(namespace):
+    """namespace providing grad, div, dot, inner, transpose, Identity, as_matrix, nabla_grad (ufl, or
+    oracle.ufl_lite in the tests)."""
+    global _ALG
+    _ALG = namespace
+
+
+def alg():
+    global _ALG
+    if _ALG is None:
+        try:
+            import ufl
+            _ALG = ufl
+        except ImportError:
+            raise RuntimeError("symbolic tensor helper called without UFL: install dolfin/ufl (or set_algebra(...)). The "
+                               "GPU path never needs these -- each form has a hand-written functor (fx_form ids).")
+    return _ALG
+
+
+def _T(a):
+    A = alg()
+    return A.transpose(a) if hasattr(A, "transpose") else a.T
+
+
+# ---- host utilities ---------------------------------------------------------------------------------
+def update_progress(job_title, progress):
+    """text progress bar (lid-driven-cavity/fenics_fem.py:23-30)."""
+    width = 20
+    filled = int(round(width * progress))
+    line = "\r{0}: [{1}] {2}%".format(job_title, "#" * filled + "-" * (width - filled), round(progress * 100, 4))
+    if progress >= 1:
+        line += " DONE\r\n"
+    sys.stdout.write(line)
+    sys.stdout.flush()
+
+
+def chunks(l, n):
+    """successive n-sized pieces of l (fenics_fem.py:444-447)."""
+    for start in range(0, len(l), n):
+        yield l[start:start + n]
+
+
+def mesh2triang(mesh):
+    import matplotlib.tri as tri
+    xy = mesh.coordinates()
+    return tri.Triangulation(xy[:, 0], xy[:, 1], mesh.cells())
+
+
+def mplot(obj):
+    """tripcolor of a Function (cell-wise for DG0, vertex values otherwise) or triplot of a Mesh
+    (fenics_fem.py:36-51); values are copied from the device once."""
+    import matplotlib.pyplot as plt
+    plt.gca().set_aspect("equal")
+    if isinstance(obj, Function):
+        m, S = obj.function_space().mesh, obj.function_space()
+        vals = obj.vector().get_local()
+        if len(vals) == m.num_cells():
+            plt.tripcolor(mesh2triang(m), vals[np.asarray(S.cell_dofs)[:, 0]])
+        else:
+            plt.tripcolor(mesh2triang(m), compute_vertex_values(obj), shading="gouraud")
+    else:
+        plt.triplot(mesh2triang(obj), color="k")
+
+
+def compute_vertex_values(fn):
+    """values of a scalar P1/P2 Function at the mesh vertices (local dofs 0..2 of every cell are its vertices)."""
+    S = fn.function_space()
+    cd, cells = np.asarray(S.cell_dofs), S.mesh.cells()
+    out = np.zeros(S.mesh.num_vertices())
+    out[cells.ravel()] = fn.vector().get_local()[cd[:, :3].ravel()]
+    return out
+
+
+def _npy(name):
+    os.makedirs("data", exist_ok=True)
+    return os.path.join("data", name + ".npy")
+
+
+# ---- Functions living on the device -----------------------------------------------------------------
+def normalize_solution(u):
+    "u / max|u|, in place (fenics_fem.py:316-324)"
+    v = u.vector()
+    v.t.mul_(1.0 / v.norm("linf"))
+    return u
+
+
+def absolute(u):
+    "|u| entrywise, in place (fenics_fem.py:450-453)"
+    u.vector().t.abs_()
+    return u
+
+
+def min_location(u, mesh):
+    """coordinates of the dofs where the scalar Function u attains its minimum (fenics_fem.py:402-417)."""
+    vals = u.vector().get_local()
+    return u.function_space().tabulate_dof_coordinates().reshape((-1, 2))[np.where(vals == vals.min())]
+
+
+def max_location(u, mesh):
+    vals = u.vector().get_local()
+    return u.function_space().tabulate_dof_coordinates().reshape((-1, 2))[np.where(vals == vals.max())]
+
+
+def adaptive_refinement(mesh, kapp, ratio):
+    """fenics_fem.py:326-338 / fenics_base.py:143-155.  The cell marking (kapp at the cell midpoint above the
+    (1-ratio) percentile) is computed here; refine() is dolfin's (Plaza), so a dolfin mesh is refined and returned,
+    while for the library's own Mesh the boolean markers are returned for the caller to hand to dolfin."""
+    vals = kapp.vector().get_local()
+    level = np.percentile(vals, (1 - ratio) * 100)
+    markers = vals[np.asarray(kapp.function_space().cell_dofs)[:, 0]] > level
+    if hasattr(mesh, "ufl_cell"):  # a dolfin mesh
+        import dolfin
+        cd = dolfin.MeshFunction("bool", mesh, 2)
+        cd.array()[:] = markers
+        return dolfin.refine(mesh, cd, redistribute=True)
+    return markers
+
+
+def _needs_dolfin(name):
+    def f(*a, **k):
+        raise NotImplementedError("%s: mesh generation by mshr / Plaza refinement stay in dolfin (north_star); without "
+                                  "dolfin use the structured meshes of fenics_b200.mesh" % name)
+    f.__name__ = name
+    return f
+
+
+# ---- skew maps and structured meshes ------------------------------------------------------------------
+skewcavity, xskewcavity, yskewcavity, expskewcavity = (_mesh.skewcavity, _mesh.xskewcavity, _mesh.yskewcavity,
+                                                       _mesh.expskewcavity)
+Skew_Mesh, DGP_structured_mesh = _mesh.Skew_Mesh, _mesh.DGP_structured_mesh
+
+
+def LDC_Regular_Mesh(mm, B, L):
+    """uniform mm x mm right-diagonal mesh of [0,B]x[0,L] (fenics_fem.py:75-89)."""
+    return _mesh.RectangleMesh((0.0, 0.0), (B, L), mm, mm)
+
+
+# ---- symbolic tensor algebra (shared by all three helper modules) ---------------------------------------
+def tgrad(w):
+    "transpose of grad(w)"
+    return _T(alg().grad(w))
+
+
+def Dincomp(w):
+    "rate of strain, incompressible"
+    g = alg().grad(w)
+    return 0.5 * (g + _T(g))
+
+
+def Dcomp(w):
+    "rate of strain, compressible: deviatoric part"
+    A = alg()
+    g = A.grad(w)
+    return 0.5 * (g + _T(g)) - (1.0 / 3) * A.div(w) * A.Identity(len(w))
+
+
+def Fdef_incompressible(u, Tau):
+    "upper-convected terms u.grad(Tau) - grad(u) Tau - Tau grad(u)^T"
+    A = alg()
+    return A.dot(u, A.grad(Tau)) - A.dot(A.grad(u), Tau) - A.dot(Tau, tgrad(u))
+
+
+def Fdef_compressible(u, Tau):
+    A = alg()
+    return Fdef_incompressible(u, Tau) + A.div(u) * Tau
+
+
+def reshape_elements(D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec):
+    """the seven 3-vectors as symmetric 2x2 tensors [[a,b],[b,c]] (fenics_fem.py:210-225)."""
+    A = alg()
+    return tuple(A.as_matrix([[v[0], v[1]], [v[1], v[2]]])
+                 for v in (D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec))
+
+
+def magnitude(u):
+    return (u[0] * u[0] + u[1] * u[1]) ** 0.5
+
+
+# ---- spaces / functions ---------------------------------------------------------------------------------
+def function_spaces(mesh, order):
+    """(W, V, Vd, Z, Zd, Zc, Q, Qt, Qr) as the reference's function_spaces (fenics_fem.py:262-287); only the spaces the
+    loops use are built (the others are None)."""
+    from ..spaces import function_spaces as fs
+    return fs(mesh, order)
+
+
+class _Argument:
+    """placeholder for a Trial/TestFunction: forms are selected by id, not built from these."""
+
+    def __init__(self, space, role):
+        self.space, self.role = space, role
+
+    def __repr__(self):
+        return "<%s on %s>" % (self.role, getattr(self.space, "name", self.space))
+
+
+def trial_functions(Q, Z, W):
+    """(rho, p, T, tau_vec, u, D_vec, D, tau) -- fenics_fem.py:249-260.  Symbolic placeholders."""
+    t = lambda S: _Argument(S, "TrialFunction")  # noqa: E731
+    return t(Q), t(Q), t(Q), t(Z), t(W), t(W), t(W), t(Z)
+
+
+def make_solution_functions(plan):
+    """solution_functions(Q, W, V, Z) bound to a device plan: the reference's 22-tuple (fenics_fem.py:227-247) of
+    GPU Functions (sub-function / tensor views are the Functions themselves: kernels index components)."""
+    def solution_functions(Q, W, V, Z):
+        F = lambda S: Function(S, plan)  # noqa: E731
+        rho0, rho12, rho1, p0, p1, T0, T1 = (F(Q) for _ in range(7))
+        w0, w12, ws, w1 = (F(W) for _ in range(4))
+        tau0_vec, tau12_vec, tau1_vec = (F(Z) for _ in range(3))
+        # reference order: rho0, rho12, rho1, p0, p1, T0, T1, u0, u12, us, u1, D0_vec, D12_vec, Ds_vec, D1_vec,
+        #                  w0, w12, ws, w1, tau0_vec, tau12_vec, tau1_vec
+        return (rho0, rho12, rho1, p0, p1, T0, T1, w0, w12, ws, w1, w0, w12, ws, w1, w0, w12, ws, w1,
+                tau0_vec, tau12_vec, tau1_vec)
+    return solution_functions
+
+
+def solution_functions(Q, W, V, Z):
+    """needs the device plan of the run: every driver exposes `drv.plan`; without one, the spaces' own plan is
+    built on first use."""
+    from ..la import Plan
+    plan = getattr(W, "_shim_plan", None)
+    if plan is None:
+        plan = Plan(W.mesh, [s for s in (W, Z, Q) if s is not None])
+        W._shim_plan = plan
+    return make_solution_functions(plan)(Q, W, V, Z)
+
+
+def math_tanh(x):
+    return math.tanh(x)

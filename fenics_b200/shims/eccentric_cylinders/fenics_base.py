@@ -1,0 +1,163 @@
+"""Drop-in for "flow between eccentrically rotating cylinders"/fenics_base.py: same helper names and
+signatures.  See fenics_b200/shims/__init__.py."""
+from math import cos, fabs, sin, sqrt, tanh  # noqa: F401
+
+import numpy as np  # noqa: F401
+
+from fenics_b200 import mesh as _mesh
+from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, assemble, norm, parameters, project,  # noqa: F401
+                           solve)
+from fenics_b200.shims._common import (DOLFIN_EPS, Dcomp, Dincomp, _needs_dolfin, _T, absolute, adaptive_refinement, alg,  # noqa: F401
+                       chunks, function_spaces, magnitude, max_location, mesh2triang, min_location, mplot,
+                       normalize_solution, pi, reshape_elements, set_algebra, solution_functions, tgrad,
+                       trial_functions, update_progress)
+from fenics_b200.shims._common import Fdef_compressible as Fdef  # noqa: F401  (this module's Fdef carries + div(u) Tau, :189-190)
+from fenics_b200.shims.lid_driven_cavity.fenics_fem import (comp_stream_function, l2norm_solution, ramp_function,  # noqa: F401
+                                            shear_rate, stream_function)
+
+refine_boundaries = _needs_dolfin("refine_boundaries")
+refine_narrow = _needs_dolfin("refine_narrow")
+
+
+def JBP_mesh(mesh_res, x_1, x_2, y_1, y_2, r_a, r_b):
+    """the reference subtracts two mshr circles and calls generate_mesh (:70-91); mshr is not part of this
+    library, so the structured O-grid annulus with ~mesh_res cells across the gap stands in (inner circle centre
+    (x_1,y_1) radius r_a, outer (x_2,y_2) radius r_b)."""
+    n_r = max(2, int(mesh_res) // 4)
+    return _mesh.annulus_mesh(8 * n_r, n_r, x_1, y_1, r_a, x_2, y_2, r_b)
+
+
+def save_solution(u, filename):
+    """the reference writes dolfin HDF5 (:94-99); here the dof vector goes to `filename` as .npy-in-.h5-name unless
+    h5py is importable, in which case dataset "/f" holds it."""
+    vals = u.vector().get_local()
+    try:
+        import h5py
+        with h5py.File(filename, "w") as f:
+            f.create_dataset("f", data=vals)
+    except ImportError:
+        with open(filename, "wb") as f:
+            np.save(f, vals)
+
+
+def load_solution(filename, function_space, plan=None):
+    """inverse of save_solution (:102-108); `plan` = the device plan the new Function lives on (default: the one
+    solution_functions uses for that space)."""
+    try:
+        import h5py
+        with h5py.File(filename, "r") as f:
+            vals = np.asarray(f["f"])
+    except ImportError:
+        with open(filename, "rb") as f:
+            vals = np.load(f)
+    if plan is None:
+        plan = getattr(function_space, "_shim_plan", None)
+    if plan is None:
+        raise TypeError("load_solution: pass plan= (the device plan of the run)")
+    u = Function(function_space, plan)
+    u.vector().set_local(vals)
+    return u
+
+
+# ---- symbolic tensor helpers (:158-294) -------------------------------------------------------------------
+def DinG(D):
+    return 0.5 * (D + _T(D))
+
+
+def sigma(u, p, Tau, betav, We):
+    return 2 * betav * Dcomp(u) - p * alg().Identity(len(u)) + Tau
+
+
+def sigmacon(u, p, Tau, betav, We):
+    I = alg().Identity(len(u))
+    return 2 * betav * Dcomp(u) - p * I + ((1.0 - betav) / We) * (Tau - I)
+
+
+def _fene_polymer(u, Tau, b, lambda_d, betav, We):
+    I = alg().Identity(len(u))
+    return ((1. - betav) / We) * (phi_def(u, lambda_d) * (fene_func(Tau, b) * Tau - I))
+
+
+def fene_sigma(u, p, Tau, b, lambda_d, betav, We):
+    return 2.0 * betav * Dincomp(u) - p * alg().Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
+
+
+def fene_sigmacom(u, p, Tau, b, lambda_d, betav, We):
+    return 2.0 * betav * Dcomp(u) - p * alg().Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
+
+
+def FdefG(u, G, Tau):
+    """DEVSS-G upper-convected terms with the projected velocity gradient G"""
+    A = alg()
+    return A.dot(u, A.grad(Tau)) - A.dot(G, Tau) - A.dot(Tau, _T(G))
+
+
+def euc_norm(tau):
+    return (tau[0] * tau[0] + tau[1] * tau[1] + tau[2] * tau[2]) ** 0.5
+
+
+def Tr(tau):
+    return abs(tau[0, 0] + tau[1, 1])
+
+
+def Trace(tau):
+    return tau[0, 0] + tau[1, 1]
+
+
+def fene_func(tau, b):
+    return 1.0 / (1. - (Tr(tau) - 2.) / (b * b))
+
+
+def phi_s(T, A_0):
+    """solvent thinning 1 - A/(C + T), A = A_0/(k_b (T_h - T_0)), C = T_h/(T_h - T_0) with T_0 = 300, T_h = 350"""
+    T_0, T_h, k_b = 300.0, 350.0, 8.3144598
+    return 1. - (A_0 / (k_b * (T_h - T_0))) * (1. / (T_h / (T_h - T_0) + T))
+
+
+def phi_ewm(tau, T, k, B):
+    return (1. - B * (T / (1. + T))) * ((0.5 * Tr(tau) + 0.00001) ** k)
+
+
+def phi_ewm_inv(tau, T, k, B):
+    return 1.0 / phi_ewm(tau, T, k, B)
+
+
+def phi(u, p, T, A, B, K_0, N, betap):
+    """pressure / temperature / shear dependent viscosity function (:215-225); its inner project() needs the
+    caller's space Q, as in the reference (a module-level name there)."""
+    A_ = alg()
+    K = 1. + A * p - B * (T / (1. + T))
+    strain = (2 * A_.inner(Dincomp(u), Dincomp(u))) ** 0.5
+    ftheta = project(1. / (1. + (K_0 * K * strain) ** N), globals().get("Q"))
+    return (betap + (1. - betap) * ftheta) * K
+
+
+def orthog_proj(u, V, V_d):
+    u_d = project(u, V_d)
+    return project(u - u_d, V)
+
+
+def frob_norm(tau):
+    return Trace(tau * _T(tau)) ** 0.5
+
+
+def ernesto_k(u, h, c_a, c_b):
+    return c_a * h * magnitude(u) + c_b * h * h * frob_norm(alg().grad(u))
+
+
+def I_3(A):
+    return A[0, 0] * A[1, 1] - A[1, 0] * A[0, 1]
+
+
+def I_2(A):
+    return 0.5 * (A[0, 0] * A[0, 0] + A[1, 1] * A[1, 1] + 2 * A[1, 0] * A[0, 1])
+
+
+def phi_def(u, lambda_d):
+    D = Dincomp(u)
+    D_u = alg().as_matrix([[D[0, 0], D[0, 1]], [D[1, 0], D[1, 1]]])
+    return 1. + (lambda_d * 3 * I_3(D_u) / (I_2(D_u) + 0.0000001)) ** 2
+
+
+def psi_def(phi):
+    return 0.5 * (phi - 1.)

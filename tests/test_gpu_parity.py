@@ -390,3 +390,34 @@ def test_comp_ldc_sweep_script_steps():
     fo, fd = ocl.fields(), drv.fields()
     for k in fo:
         assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+
+
+def test_shim_helpers_on_device_functions():
+    """the reference's helper names (fenics_b200/shims) applied to the Functions of a GPU time loop."""
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    _, drv = _pair(2, n=8)
+    drv.t = 0.45
+    drv.pressure_method = "cg"
+    for _ in range(2):
+        drv.step()
+    psi = ff.comp_stream_function(drv.rho1, drv.w1)
+    ref = drv.stream_function(True).vector().get_local().copy()
+    assert np.array_equal(psi.vector().get_local(), ref)
+    loc = ff.min_location(psi, drv.mesh)
+    assert loc.shape[1] == 2 and 0.0 < loc[0, 0] < 1.0 and 0.0 < loc[0, 1] < 1.0  # the primary vortex eye is inside
+    k = drv.kapp.copy()
+    before = k.vector().get_local()
+    ff.normalize_solution(k)
+    assert lc.rel_err(k.vector().get_local(), before / np.abs(before).max()) < 1e-15
+    k.vector().set_local(-before)
+    ff.absolute(k)
+    assert np.array_equal(k.vector().get_local(), np.abs(before))
+    t = drv.tau1_vec.copy()
+    t._driver = drv
+    ff.l2norm_solution(t)
+    M = dapi.assemble(drv.pr.form(abi.FX_FORM_MASS_ZC)).to_scipy()
+    v = t.vector().get_local()
+    assert abs(v @ (M @ v) - 1.0) < 1e-12
+    Q, W, Zc = drv.S["Q"], drv.S["W"], drv.S["Zc"]
+    fs = ff.solution_functions(Q, W, None, Zc)
+    assert len(fs) == 22 and fs[0].vector().size() == Q.dim() and fs[-1].vector().size() == Zc.dim()
