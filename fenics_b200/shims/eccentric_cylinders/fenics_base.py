@@ -27,29 +27,23 @@ def JBP_mesh(mesh_res, x_1, x_2, y_1, y_2, r_a, r_b):
     return _mesh.annulus_mesh(8 * n_r, n_r, x_1, y_1, r_a, x_2, y_2, r_b)
 
 
-def save_solution(u, filename):
-    """the reference writes dolfin HDF5 (:94-99); here the dof vector goes to `filename` as .npy-in-.h5-name unless
-    h5py is importable, in which case dataset "/f" holds it."""
-    vals = u.vector().get_local()
-    try:
-        import h5py
-        with h5py.File(filename, "w") as f:
-            f.create_dataset("f", data=vals)
-    except ImportError:
-        with open(filename, "wb") as f:
-            np.save(f, vals)
+def save_solution(u, filename, writer=None):
+    """the reference writes dolfin HDF5 (:94-99).  Here the dof vector goes to `filename` (HDF5 dataset "/f" when h5py
+    is importable, else .npy bytes); with `writer` (fenics_b200.io.AsyncWriter) the call returns at once and the
+    device->host copy and the file write overlap the following time steps."""
+    from fenics_b200.io import AsyncWriter
+    if writer is not None:
+        writer.save(u, filename)
+        return
+    with AsyncWriter(depth=1) as w:
+        w.save(u, filename)
 
 
 def load_solution(filename, function_space, plan=None):
     """inverse of save_solution (:102-108); `plan` = the device plan the new Function lives on (default: the one
     solution_functions uses for that space)."""
-    try:
-        import h5py
-        with h5py.File(filename, "r") as f:
-            vals = np.asarray(f["f"])
-    except ImportError:
-        with open(filename, "rb") as f:
-            vals = np.load(f)
+    from fenics_b200.io import load_array
+    vals = load_array(filename)
     if plan is None:
         plan = getattr(function_space, "_shim_plan", None)
     if plan is None:
