@@ -58,6 +58,92 @@ __global__ void __launch_bounds__(LA_THREADS, 4) k_spmv_vec(const __grid_constan
   }
 }
 
+// Software-pipelined CSR-stream variant (experiment): the value / column stream of row block k+1 is copied
+// global -> shared with cp.async (LDGSTS: no registers, no L1 allocation) while the warp gathers and reduces block k,
+// so a block's dependent chain shrinks from [stream -> gather -> reduce] to [gather -> reduce] and the bytes in flight
+// are no longer bounded by registers.  Two staging buffers per warp; the products overwrite the values in place.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+constexpr int PIPE_NB = SPMV_NNZB + 8;  // staging capacity: a block plus the 16-byte alignment slack on both ends
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_spmv_pipe(const __grid_constant__ CsrView A,
+                                                             const double* __restrict__ x, double* __restrict__ y) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* vb[2];
+  int* cb[2];
+  {
+    unsigned char* base = dyn + (size_t)wib * 2 * PIPE_NB * 12;
+    vb[0] = reinterpret_cast<double*>(base);
+    vb[1] = vb[0] + PIPE_NB;
+    cb[0] = reinterpret_cast<int*>(vb[1] + PIPE_NB);
+    cb[1] = cb[0] + PIPE_NB;
+  }
+  const int nw = gridDim.x * WARPS, gw = blockIdx.x * WARPS + wib;
+  const int per = (A.nrowblk + nw - 1) / nw;
+  const int k0 = min(gw * per, A.nrowblk), k1 = min(k0 + per, A.nrowblk);
+  if (k0 >= k1) return;
+  auto bounds = [&](int k, int& r0, int& r1, int& j0, int& j1) {
+    r0 = A.rowblk[k]; r1 = A.rowblk[k + 1];
+    j0 = A.rowptr[r0]; j1 = A.rowptr[r1];
+  };
+  auto issue = [&](int j0, int j1, int b) {
+    const int s0 = j0 & ~3, m4 = (j1 - s0 + 3) >> 2;
+    for (int c = lane; c < m4; c += 32) cp_async16(cb[b] + 4 * c, A.col + s0 + 4 * c);
+    for (int c = lane; c < 2 * m4; c += 32) cp_async16(vb[b] + 2 * c, A.val + s0 + 2 * c);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int r0, r1, j0, j1, nr0 = 0, nr1 = 0, nj0 = 0, nj1 = 0;
+  bounds(k0, r0, r1, j0, j1);
+  issue(j0, j1, 0);
+  if (k0 + 1 < k1) bounds(k0 + 1, nr0, nr1, nj0, nj1);
+  for (int k = k0; k < k1; ++k) {
+    const int b = (k - k0) & 1;
+    int fr0 = 0, fr1 = 0, fj0 = 0, fj1 = 0;
+    if (k + 1 < k1) {
+      issue(nj0, nj1, b ^ 1);
+      if (k + 2 < k1) bounds(k + 2, fr0, fr1, fj0, fj1);  // two blocks ahead: in flight while this block is processed
+    } else {
+      asm volatile("cp.async.commit_group;" ::: "memory");  // empty group keeps the wait count uniform
+    }
+    const int row = r0 + lane;
+    const bool act = row < r1;
+    const int e1 = act ? A.rowptr[row + 1] : j0;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const int s0 = j0 & ~3, lo = j0 - s0, hi = j1 - s0;
+    double* pv = vb[b];
+    const int* pc = cb[b];
+    for (int jb = lo; jb < hi; jb += 256) {
+      double xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u * 32 + lane;
+        xv[u] = (j < hi) ? x[pc[j]] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u * 32 + lane;
+        if (j < hi) pv[j] *= xv[u];
+      }
+    }
+    __syncwarp();
+    const int t1 = e1 - s0;
+    int t0 = __shfl_up_sync(0xffffffffu, t1, 1);
+    if (lane == 0) t0 = lo;
+    if (act) {
+      double sum = 0.0;
+      for (int j = t0; j < t1; ++j) sum += pv[j];
+      y[row] = sum;
+    }
+    __syncwarp();
+    r0 = nr0; r1 = nr1; j0 = nj0; j1 = nj1;
+    nr0 = fr0; nr1 = fr1; nj0 = fj0; nj1 = fj1;
+  }
+}
+
 int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, double* y, int variant,
                     cudaStream_t st) {
   const DevPattern& p = P->sp[space];
@@ -71,6 +157,18 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
     case 3: k_spmv_vec<8, 2><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
     case 4: k_spmv_vec<16, 2><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
     case 5: k_spmv_vec<4, 8><<<nb, LA_THREADS, 0, st>>>(A, x, y); break;
+    case 6: case 7: {  // software-pipelined stream, 16 warps (6) or 8 warps x 2 CTAs (7) per SM
+      constexpr size_t per_warp = (size_t)2 * PIPE_NB * 12;
+      static bool attr = false;
+      if (!attr) {
+        FX_CUDA(cudaFuncSetAttribute(k_spmv_pipe<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * per_warp)));
+        FX_CUDA(cudaFuncSetAttribute(k_spmv_pipe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * per_warp)));
+        attr = true;
+      }
+      if (variant == 6) k_spmv_pipe<16><<<P->num_sms, 512, 16 * per_warp, st>>>(A, x, y);
+      else k_spmv_pipe<8><<<2 * P->num_sms, 256, 8 * per_warp, st>>>(A, x, y);
+      break;
+    }
     default: return set_error(FX_ERR_ARG, "unknown SpMV variant %d", variant);
   }
   count_launch(1);

@@ -24,7 +24,7 @@ for space, fid in (("W", abi.FX_FORM_C2_A1), ("Zc", abi.FX_FORM_C2_A4), ("Q", ab
     x.t.normal_()
     nbytes = 12 * A.nnz + 4 * (A.n + 1) + 16 * A.n
     ref = None
-    for variant in range(6):
+    for variant in range(8):
         def run():
             check(lib.fx_spmv_variant(drv.plan.h, abi.SPACE_ID[space], la._ptr(A.val), la._ptr(x.t), la._ptr(y.t), variant,
                                       la._stream()))
