@@ -47,7 +47,13 @@
   X(FX_FORM_C5_A6, fx::jbp::SU_RHO_A6)      \
   X(FX_FORM_C5_A7, fx::dgp::C5_A7)          \
   X(FX_FORM_C5_A4, fx::dgp::C5_A4)          \
-  X(FX_FORM_C5_A8, fx::dgp::C5_A8)
+  X(FX_FORM_C5_A8, fx::dgp::C5_A8)          \
+  X(FX_FORM_C6_A1, fx::dgp::C6_A12<true>)   \
+  X(FX_FORM_C6_A2, fx::dgp::C6_A12<false>)  \
+  X(FX_FORM_C6_A5, fx::ldc::C1_A5)          \
+  X(FX_FORM_C6_A7, fx::dgp::C6_A7)          \
+  X(FX_FORM_C6_A4, fx::ldc::LDC_A4)         \
+  X(FX_FORM_C6_A8, fx::dgp::C6_A8)
 
 #define FX_VECTOR_FORMS(X, XC)                              \
   XC(FX_FORM_C1_L1, fx::ldc::C1_L1<4>, fx::ldc::C1_L1<5>)   \
@@ -97,7 +103,14 @@
   X(FX_FORM_C5_L_THETA0, fx::dgp::C5_L_THETA<fx::ldc::F_T0>) \
   X(FX_FORM_C5_L_THETA1, fx::dgp::C5_L_THETA<fx::ldc::F_T1>) \
   X(FX_FORM_C5_L_THERM_INV, fx::dgp::C5_L_THERM_INV)        \
-  X(FX_FORM_C5_L_RHO1, fx::dgp::C5_L_RHO1)
+  X(FX_FORM_C5_L_RHO1, fx::dgp::C5_L_RHO1)                  \
+  X(FX_FORM_C6_L1, fx::dgp::C6_L12<true>)                   \
+  X(FX_FORM_C6_L2, fx::dgp::C6_L12<false>)                  \
+  X(FX_FORM_C6_L5, fx::ldc::C1_L5)                          \
+  X(FX_FORM_C6_L7, fx::dgp::C6_L7)                          \
+  X(FX_FORM_C6_L4, fx::jbp::C4_L4)                          \
+  X(FX_FORM_C6_L8, fx::dgp::C6_L8)                          \
+  X(FX_FORM_C6_L_RES_ORTH, fx::dgp::C6_L_RES_ORTH)
 
 #define FX_SCALAR_FORMS(X)              \
   X(FX_FORM_C1_EK, fx::ldc::C1_EK)      \
@@ -109,7 +122,9 @@
   X(FX_FORM_C4_EK, fx::ldc::C2_EK)      \
   X(FX_FORM_C4_EE, fx::jbp::C4_EE)      \
   X(FX_FORM_C5_EK, fx::ldc::C2_EK)      \
-  X(FX_FORM_C5_EE, fx::dgp::C5_EE)
+  X(FX_FORM_C5_EE, fx::dgp::C5_EE)      \
+  X(FX_FORM_C6_EK, fx::ldc::C1_EK)      \
+  X(FX_FORM_C6_EE, fx::dgp::C5_EE)
 
 #define FX_FACET_SCALAR_FORMS(X)                    \
   X(FX_FORM_C3_TORQUE, fx::ewm::C3_JOURNAL<0>)      \
@@ -118,7 +133,8 @@
   X(FX_FORM_C4_TORQUE, fx::jbp::C4_JOURNAL<0>)      \
   X(FX_FORM_C4_FORCE_X, fx::jbp::C4_JOURNAL<1>)     \
   X(FX_FORM_C4_FORCE_Y, fx::jbp::C4_JOURNAL<2>)     \
-  X(FX_FORM_C5_NUS, fx::dgp::C5_NUS)
+  X(FX_FORM_C5_NUS, fx::dgp::C5_NUS)                \
+  X(FX_FORM_C6_NUS, fx::dgp::C6_NUS)
 
 #define FX_DG0_EXPRS(X)                           \
   X(FX_EXPR_LDC_RESTAU, fx::ldc::E_LDC_RESTAU)    \
@@ -127,6 +143,7 @@
   X(FX_EXPR_H_KAPP, fx::ldc::E_H_KAPP)            \
   X(FX_EXPR_C4_RESTAU, fx::jbp::E_C4_RESTAU)      \
   X(FX_EXPR_C5_RESTAU, fx::dgp::E_C5_RESTAU)      \
+  X(FX_EXPR_C6_RESTAU, fx::dgp::E_C6_RESTAU)      \
   X(FX_EXPR_ADAPT_RES_SQ, fx::jbp::E_ADAPT_RES_SQ) \
   X(FX_EXPR_TAU_AVG, fx::jbp::E_TAU_AVG)          \
   X(FX_EXPR_ABS_KAPP_RATIO, fx::jbp::E_ABS_KAPP_RATIO)

@@ -118,7 +118,12 @@ typedef enum {
   FX_FORM_C5_L8, FX_FORM_C5_L_RES_ORTH, FX_FORM_C5_L_THETA0, FX_FORM_C5_L_THETA1, FX_FORM_C5_L_THERM_INV,
   FX_FORM_C5_L_RHO1,
   /* cfg5: functionals; NUS = assemble(-inner(grad(theta1), n)*ds(2)) with theta1 in field FX_F_Q_A (:581-583) */
-  FX_FORM_C5_EK = 540, FX_FORM_C5_EE, FX_FORM_C5_NUS
+  FX_FORM_C5_EK = 540, FX_FORM_C5_EE, FX_FORM_C5_NUS,
+  /* "cfg6" = buoyancy-driven-flow/incompressible_dgp.py (time loop :357-535).  Its a5/L5 (pure Neumann
+   * pressure Poisson problem; FX_P_RE must hold 1), a4, L4, E_k, E_e and theta1 projection are shared functors */
+  FX_FORM_C6_A1 = 600, FX_FORM_C6_A2, FX_FORM_C6_A5, FX_FORM_C6_A7, FX_FORM_C6_A4, FX_FORM_C6_A8,
+  FX_FORM_C6_L1 = 620, FX_FORM_C6_L2, FX_FORM_C6_L5, FX_FORM_C6_L7, FX_FORM_C6_L4, FX_FORM_C6_L8, FX_FORM_C6_L_RES_ORTH,
+  FX_FORM_C6_EK = 640, FX_FORM_C6_EE, FX_FORM_C6_NUS
 } fx_form;
 
 /* DG0 projections (diagonal mass => cell average), dolfin project(expr, Zd|Qt).               */
@@ -129,6 +134,7 @@ typedef enum {
   FX_EXPR_H_KAPP,           /* h*kapp -> Qt (:434)                                         */
   FX_EXPR_C4_RESTAU,        /* cfg4 restau0 -> Zd (fenepmp_jbp.py:462-467)                 */
   FX_EXPR_C5_RESTAU,        /* cfg5 restau0 -> Zd (compressible_dgp.py:382-386)            */
+  FX_EXPR_C6_RESTAU,        /* incompressible_dgp.py restau0 -> Zd (:369-373)             */
   /* post-loop adaptive-refinement indicator of the journal-bearing scripts (incompressible_benchmarkEWM.py:903-917,
    * fenepmp_jbp.py:691-705, comp_ewm_jpb.py:735-747); refine() itself stays in dolfin                              */
   FX_EXPR_ADAPT_RES_SQ,     /* inner(restau0,restau0) -> Qt, restau0 = We/dt (tau1-tau0) + We Fdef(u1,tau1) + tau1 - I */

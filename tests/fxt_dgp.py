@@ -41,3 +41,35 @@ def params_of(cfg):
     p = {PARAM_SLOT[k]: float(v) for k, v in cfg.p.items()}
     p[abi.FX_P_EPS] = SU_EPS
     return p
+
+
+# ---- incompressible_dgp.py ("cfg6") ------------------------------------------------------------------------------
+C6_PARAM_SLOT = dict(dt=abi.FX_P_DT, Ra=abi.FX_P_RA, We=abi.FX_P_WE, Pr=abi.FX_P_PR, betav=abi.FX_P_BETAV, c1=abi.FX_P_C1,
+                     c2=abi.FX_P_C2, th=abi.FX_P_TH, Vh=abi.FX_P_VH, Bi=abi.FX_P_BI, T0=abi.FX_P_T0, th_hot=abi.FX_P_TH_HOT)
+C6_FIELD_ATTR = {abi.FX_F_W0: "w0", abi.FX_F_W12: "w12", abi.FX_F_WS: "ws", abi.FX_F_W1: "w1", abi.FX_F_P0: "p0",
+                 abi.FX_F_P1: "p1", abi.FX_F_T0: "T0", abi.FX_F_T1: "T1", abi.FX_F_Q_A: "theta1",
+                 abi.FX_F_TAU0: "tau0_vec", abi.FX_F_TAU1: "tau1_vec", abi.FX_F_KAPP: "kapp"}
+C6_FORMS = dict(a1=(abi.FX_FORM_C6_A1, "W"), a2=(abi.FX_FORM_C6_A2, "W"), a5=(abi.FX_FORM_C6_A5, "Q"),
+                a7=(abi.FX_FORM_C6_A7, "W"), a4=(abi.FX_FORM_C6_A4, "Zc"), a8=(abi.FX_FORM_C6_A8, "Q"),
+                L1=(abi.FX_FORM_C6_L1, "W"), L2=(abi.FX_FORM_C6_L2, "W"), L5=(abi.FX_FORM_C6_L5, "Q"),
+                L7=(abi.FX_FORM_C6_L7, "W"), L4=(abi.FX_FORM_C6_L4, "Zc"), L8=(abi.FX_FORM_C6_L8, "Q"))
+
+
+def c6_randomize(cfg, seed=0):
+    rng = np.random.default_rng(seed)
+    for attr in set(C6_FIELD_ATTR.values()):
+        fn = getattr(cfg, attr)
+        fn.vec[:] = rng.standard_normal(fn.space.dim)
+    cfg.kapp.vec[:] = np.abs(cfg.kapp.vec)
+    for T in (cfg.T0, cfg.T1):
+        T.vec[:] = 325.0 + 10.0 * T.vec
+
+
+def c6_state_of(cfg):
+    return {slot: getattr(cfg, attr).vec for slot, attr in C6_FIELD_ATTR.items()}
+
+
+def c6_params_of(cfg):
+    p = {C6_PARAM_SLOT[k]: float(v) for k, v in cfg.p.items()}
+    p[abi.FX_P_RE] = 1.0  # the shared L5 functor (C1_L5) carries Re/dt; this loop has 1/dt
+    return p

@@ -74,3 +74,54 @@ def test_cfg5_faithful_first_roll_is_degenerate_like_the_reference():
         return
     ti = drv.therm_inv.vector().get_local()
     assert (not np.all(np.isfinite(ti))) or np.abs(ti).max() > 1e8
+
+
+# ---- incompressible_dgp.py ------------------------------------------------------------------------------------------
+def _pair6(n=6, **kw):
+    from oracle.configs_dgp import IncompDGP as OracleInc
+    drv = dgp.IncompDGP(mesh_resolution=n, **kw)
+    m = drv.mesh
+    om = fem.Mesh(m.coordinates(), m.cells())
+    ocl = OracleInc(om, dofmaps={k: s.cell_dofs for k, s in drv.S.items()}, **kw)
+    assert np.array_equal(om.bfacet_marker, m.bfacet_marker)
+    return ocl, drv
+
+
+def test_incompressible_dgp_forms_match_oracle():
+    ocl, drv = _pair6(We=0.4, Bi=0.3)
+    dg.c6_randomize(ocl)
+    for slot, attr in dg.C6_FIELD_ATTR.items():
+        getattr(drv, attr).vector().set_local(getattr(ocl, attr).vec)
+    for name, (fid, space) in dg.C6_FORMS.items():
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        err = lc.csr_rel_err(got.to_scipy(), ref) if name.startswith("a") else lc.rel_err(got.get_local(), ref)
+        assert err < TOL, (name, err)
+    for fid, form in ((abi.FX_FORM_C6_EK, ocl.E_k_form), (abi.FX_FORM_C6_EE, ocl.E_e_form), (abi.FX_FORM_C6_NUS, ocl.nus_form)):
+        ref = fem.assemble(form)
+        assert abs(dapi.assemble(drv.pr.form(fid)) - ref) < 1e-11 * max(1.0, abs(ref)), fid
+    for bo, bd in zip(ocl.bcu + ocl.bcT, drv.bcu + drv.bcT):
+        assert np.array_equal(bo.dofs, bd.dofs)
+
+
+def test_incompressible_dgp_k_steps_match_oracle():
+    """drivers.dgp.IncompDGP (incompressible_dgp.py:357-535) against the oracle: fields, energies and the Nusselt number
+    after K steps within 1e-8.  The pressure system is singular (pure Neumann): both sides pick the member of the
+    solution family that Jacobi-preconditioned Krylov iterations reach from the previous pressure, and p is compared
+    up to its mean as well."""
+    K = 4
+    ocl, drv = _pair6(n=8, Ra=5000.0, We=0.2)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    ocl.t = drv.t = 1.4  # thermal ramp 0.5(1+tanh(4(t-1.5))) is O(1) here
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        assert abs(ro["Nus"] - rd["Nus"]) < 1e-8 * abs(ro["Nus"]), (ro["Nus"], rd["Nus"])
+        assert abs(ro["E_k"] - rd["E_k"]) < 1e-8 * abs(ro["E_k"]) + 1e-25, (ro["E_k"], rd["E_k"])
+        assert abs(ro["E_e"] - rd["E_e"]) < 1e-8 * 2.0, (ro["E_e"], rd["E_e"])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+    # the gauge itself (not only p - mean(p)) agrees: sum_i A_ii p_i is what the Jacobi-Krylov iteration conserves
+    assert lc.rel_err(drv.p1.vector().get_local(), ocl.p1.vec) < 1e-7
+    assert len(drv.last_info) == 8 and all(i.converged == 1 for i in drv.last_info)
