@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=64, help="mesh size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-phase timing table here (json)")
+    ap.add_argument("--partition", action="store_true",
+                    help="under torchrun: ONE mesh-partitioned run over all ranks (strong scaling, fused peer-memory Krylov "
+                         "kernels) instead of the independent ensemble; same JSON keys, scaling = strong")
+    ap.add_argument("--dt", type=float, default=0.001)
     return ap.parse_args()
 
 
@@ -396,8 +400,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_partition(args):
+    """mesh-partitioned cfg2 step (tools/partition_bench.py is the same measurement as a stand-alone tool)."""
+    sys.argv = [sys.argv[0], str(args.n), str(args.steps), str(args.dt)]
+    import runpy
+    runpy.run_path(os.path.join(ROOT, "tools", "partition_bench.py"), run_name="__main__")
+
+
 def main():
     args = parse()
+    if args.partition:
+        return run_partition(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -89,10 +89,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_spmv_pipe(const __grid_consta
     r0 = A.rowblk[k]; r1 = A.rowblk[k + 1];
     j0 = A.rowptr[r0]; j1 = A.rowptr[r1];
   };
+  const int nnz_total = A.rowptr[A.n];
   auto issue = [&](int j0, int j1, int b) {
-    const int s0 = j0 & ~3, m4 = (j1 - s0 + 3) >> 2;
+    // 16-byte chunks from the aligned start; the last chunk of the whole matrix must not read past the arrays, so
+    // its (< 4) tail entries are copied with plain loads
+    const int s0 = j0 & ~3, m4 = min((j1 - s0 + 3) >> 2, (nnz_total - s0) >> 2);
     for (int c = lane; c < m4; c += 32) cp_async16(cb[b] + 4 * c, A.col + s0 + 4 * c);
     for (int c = lane; c < 2 * m4; c += 32) cp_async16(vb[b] + 2 * c, A.val + s0 + 2 * c);
+    for (int j = s0 + 4 * m4 + lane; j < j1; j += 32) { cb[b][j - s0] = A.col[j]; vb[b][j - s0] = A.val[j]; }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int r0, r1, j0, j1, nr0 = 0, nr1 = 0, nj0 = 0, nj1 = 0;

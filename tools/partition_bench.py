@@ -53,7 +53,9 @@ if world > 1:
     local_dofs = sum(drv.S[k].dim() for k in ("W", "Zc", "Q"))
 else:
     dofs = local_dofs = sum(drv.S[k].dim() for k in ("W", "Zc", "Q"))
-row = dict(workload="cfg2 comp_LDC_mesh_convergence.py step, skewed cavity n=%d, dt=%g, rtol 1e-5" % (n, dt), n_gpus=world,
+row = dict(metric="time-steps/s (assembly+solve), one mesh-partitioned run", value=round(1e3 / float(ms), 2), unit="steps/s",
+           scaling="strong", dtype="f64", data="synthetic", steps=steps, warmup=3,
+           workload="cfg2 comp_LDC_mesh_convergence.py step, skewed cavity n=%d, dt=%g, rtol 1e-5" % (n, dt), n_gpus=world,
            mode=("mesh partition (RCB), fused peer-memory Krylov kernels, replicated P1 solves" if world > 1 else "single GPU"),
            dofs=dofs, dofs_per_gpu_incl_ghosts=local_dofs, ms_per_step=round(float(ms), 3), steps_per_s=round(1e3 / float(ms), 2),
            dof_steps_per_s=round(dofs * 1e3 / float(ms)), pressure_coarse=coarse, iterations=iters, E_k=float(r["E_k"]),
