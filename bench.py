@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_MESH)
+    ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=N_MESH,
+                    help="mesh size (use --mesh-n under torchrun: its parser treats --n as an abbreviation of its own flags)")
     ap.add_argument("--cpu-n", type=int, default=64, help="mesh size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-phase timing table here (json)")
