@@ -123,6 +123,7 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
       d.rowblk_h = hp.rowblk;
       for (int b = 0; b < d.nrowblk; ++b)
         d.maxblknnz = std::max(d.maxblknnz, hp.rowptr[hp.rowblk[b + 1]] - hp.rowptr[hp.rowblk[b]]);
+      for (int r = 0; r < hp.n; ++r) d.maxrow = std::max(d.maxrow, hp.rowptr[r + 1] - hp.rowptr[r]);
     }
     maxn = std::max(maxn, (size_t)hp.n);
   }
@@ -130,6 +131,8 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
   for (int s = 0; s < S_N; ++s) {
     maxnnz = std::max(maxnnz, (size_t)P->sp[s].nnz);
     maxblk = std::max(maxblk, (size_t)P->sp[s].nrowblk);
+    if (P->sp[s].has_csr && P->sp[s].maxrow < SPMV_NNZB)  // blocks compact_reblock can build: (nnz + 16 n) / T + 2
+      maxblk = std::max(maxblk, ((size_t)P->sp[s].nnz + 16 * (size_t)P->sp[s].n) / (size_t)(SPMV_NNZB - P->sp[s].maxrow) + 2);
   }
   if (maxnnz > 0 &&
       (cudaMalloc((void**)&P->cval, sizeof(double) * maxnnz) != cudaSuccess ||
@@ -137,7 +140,9 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
        cudaMalloc((void**)&P->cre, sizeof(int) * maxn) != cudaSuccess ||
        cudaMalloc((void**)&P->cdesc, sizeof(int4) * (maxblk + 1)) != cudaSuccess ||
        cudaMalloc((void**)&P->cprefix, sizeof(int) * (maxblk + 2)) != cudaSuccess ||
-       cudaMalloc((void**)&P->scanpart, sizeof(int) * MAX_GRID) != cudaSuccess ||
+       cudaMalloc((void**)&P->scanpart, sizeof(int) * 2 * MAX_GRID) != cudaSuccess ||
+       cudaMalloc((void**)&P->rowpre, sizeof(int2) * (maxn + 1)) != cudaSuccess ||
+       cudaMalloc((void**)&P->nblk, 64) != cudaSuccess ||
        cudaMalloc((void**)&P->bar, 64) != cudaSuccess))
     return fail(set_error(FX_ERR_CUDA, "cudaMalloc compacted-matrix buffers failed"));
   P->part_cap = std::max((nc + 255) / 256, 148 * 8);
@@ -163,7 +168,7 @@ void fx_plan_destroy(fx_plan* P) {
     cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows); cudaFree(P->sp[s].agg);
     cudaFree(P->sp[s].s_first); cudaFree(P->sp[s].s_peer); cudaFree(P->sp[s].s_local); cudaFree(P->sp[s].s_remote);
   }
-  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->bar); cudaFree(P->coarse);
+  cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->rowpre); cudaFree(P->nblk); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->gmres_basis); cudaFree(P->red_big);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;

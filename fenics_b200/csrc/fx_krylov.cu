@@ -210,9 +210,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
 
   // setup: compacted matrix, balanced partition, dinv, r = M^-1 (b - A x), rhat = p = r, v = 0
   double acc[3] = {0.0, 0.0, 0.0};
-  acc[2] = (double)compact_zeros(A);
-  bar.sync();
-  const BlockRange rg = balance_partition(A, bar, sh_i);
+  int nb = A.nrowblk;
+  if (A.blk_target > 0) {
+    acc[2] = (double)compact_reblock(A, bar, sh_i, nb);
+  } else {
+    acc[2] = (double)compact_zeros(A);
+    bar.sync();
+  }
+  const BlockRange rg = balance_partition(A, bar, sh_i, nb);
   spmv_stream_c(A, rg, a.x, prod,
                 [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
                 [&](int row, double ax, const Ops2& o) {
@@ -372,9 +377,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   GridBarT<DIST> bar;
   bar.init(a.bar, &a.dd, sh_x);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  acc[3] = (double)compact_zeros(A);
-  bar.sync();
-  const BlockRange rg = balance_partition(A, bar, sh_i);
+  int nb = A.nrowblk;
+  if (A.blk_target > 0) {
+    acc[3] = (double)compact_reblock(A, bar, sh_i, nb);
+  } else {
+    acc[3] = (double)compact_zeros(A);
+    bar.sync();
+  }
+  const BlockRange rg = balance_partition(A, bar, sh_i, nb);
   spmv_stream_c(A, rg, a.x, prod,
                 [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
                 [&](int row, double ax, const Ops2& o) {
@@ -495,9 +505,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gmres(const __grid_constant__ KA
   int phase = 0, phase_big = 0;
   GridBar bar;
   bar.init(a.bar);
-  double bad[1] = {(double)compact_zeros(A)};
-  bar.sync();
-  const BlockRange rg = balance_partition(A, bar, sh_i);
+  int nb = A.nrowblk;
+  double bad[1] = {0.0};
+  if (A.blk_target > 0) {
+    bad[0] = (double)compact_reblock(A, bar, sh_i, nb);
+  } else {
+    bad[0] = (double)compact_zeros(A);
+    bar.sync();
+  }
+  const BlockRange rg = balance_partition(A, bar, sh_i, nb);
   double bn = 0.0, tol = 0.0, rn = 0.0;
   int it = 0;
   for (int cycle = 0;; ++cycle) {
@@ -1097,8 +1113,10 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   int rc = ensure_work(P, (size_t)p.n);
   if (rc) return rc;
   KArgs ka;
+  static const int reblock_env = getenv("FX_REBLOCK") ? atoi(getenv("FX_REBLOCK")) : 1;
   ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->cdesc, P->cre, P->ccol, P->cval,
-                 (p.nelim > 0 || part) ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart};
+                 (p.nelim > 0 || part) ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart,
+                 (reblock_env && p.maxrow <= SPMV_NNZB / 2) ? SPMV_NNZB - p.maxrow : 0, P->rowpre, P->nblk};
   ka.bar = P->bar;
   ka.dd = P->dist;
   if (part) {

@@ -152,7 +152,7 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
                     cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr};
   const int nb = P->num_sms * 8;
   switch (variant) {
     case 0: return la_spmv(P, space, val, x, y, st);
@@ -183,7 +183,7 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
 int la_spmv(fx_plan* P, int space, const double* val, const double* x, double* y, cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
-  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+  CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr};
   const int nb = max(1, min((p.nrowblk + LA_WARPS - 1) / LA_WARPS, P->num_sms * 8));
   k_spmv<<<nb, LA_THREADS, 0, st>>>(A, x, y);
   count_launch(1);

@@ -81,7 +81,7 @@ struct CsrView {
   const int* rowblk;
   int nrowblk;
   // compacted copy (structural zeros of the DOLFIN cell-block pattern dropped); desc == null: not compacted
-  int4* desc;   // [nrowblk] {first row, rows, first entry, one past the last entry} of the row block
+  int4* desc;   // [blocks] {first row, one past the last row, first entry, one past the last entry} of the row block
   int* re;      // [n] one past the last entry of row (rows of a block are stored back to back)
   int* col2;
   double* val2;
@@ -94,7 +94,11 @@ struct CsrView {
   int nelim;
   // cost-balanced contiguous partition of the row blocks over the warps (balance_partition)
   int* blkprefix;  // [nrowblk + 1] exclusive prefix of the per-block cost
-  int* scanpart;   // [gridDim] scratch of the scan
+  int* scanpart;   // [2 * gridDim] scratch of the scans
+  // re-blocking of the compacted matrix (compact_reblock): blk_target > 0 switches it on
+  int blk_target;  // entries-per-block target T = SPMV_NNZB - (longest pattern row): a block never exceeds SPMV_NNZB
+  int2* rowpre;    // [n] CTA-chunk-local exclusive prefixes (entries, weights) of the rows
+  int* nblk;       // [1] number of blocks built
 };
 constexpr unsigned char MASK_ELIM = 1, MASK_GHOST = 2, MASK_IFACE = 4, MASK_INACTIVE = MASK_ELIM | MASK_GHOST;
 
@@ -290,9 +294,111 @@ __device__ __forceinline__ int compact_zeros(const CsrView& A) {
         if (v != 0.0) { A.val2[dst] = v; A.col2[dst] = A.col[j]; ++dst; }
       }
     }
-    if (lane == 0) A.desc[k] = make_int4(r0, r1 - r0, j0, j0 + total);
+    if (lane == 0) A.desc[k] = make_int4(r0, r1, j0, j0 + total);
     __syncwarp();
   }
+  return bad;
+}
+
+// Compaction WITH re-blocking.  The plan's row blocks are cut on the PATTERN (<= SPMV_NNZB stored entries), but 36-58 %
+// of the stored values of the W systems are structural zeros (and eliminated / ghost rows are empty), so a pattern block
+// of a velocity system holds ~16 rows and ~300 real entries: the per-block latency chain of the SpMV is amortised over
+// little data and half the lanes idle in the epilogue.  Here the blocks are rebuilt from the ACTUAL counts, inside the
+// solve, with a grid-wide scan: row i gets the weight w_i = max(cnt_i, MINW) and block floor(W_i / T), W = exclusive
+// prefix of the weights, T = SPMV_NNZB - (longest pattern row).  A block therefore holds < T + longest row <= SPMV_NNZB
+// entries and at most T / MINW + 1 < 32 rows, and the compacted entries are stored densely at the exclusive prefix of
+// the counts.  Two passes over the values (count, copy) with one grid barrier between them and one after;
+// CTA b owns the contiguous rows [b L, (b+1) L).  Returns this thread's count of non-zero couplings A[active, eliminated];
+// nb = number of blocks (same value in every thread).
+constexpr int REBLOCK_MINW = 16;
+template <class Bar>
+__device__ __forceinline__ int compact_reblock(const CsrView& A, Bar& bar, int* sh_i, int& nb) {
+  const int n = A.n, G = gridDim.x, T = A.blk_target;
+  const int L = (n + G - 1) / G, c0 = min(n, (int)blockIdx.x * L), c1 = min(n, c0 + L);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int bad = 0, runE = 0, runW = 0;
+  for (int base = c0; base < c1; base += blockDim.x) {  // CTA-uniform trip count
+    const int row = base + threadIdx.x;
+    int cnt = 0;
+    if (row < c1 && !(A.elim != nullptr && (A.elim[row] & MASK_INACTIVE))) {
+      const int b = A.rowptr[row], e = A.rowptr[row + 1];
+      if (A.elim != nullptr) {
+        for (int j = b; j < e; ++j) {
+          const bool nz = A.val[j] != 0.0;
+          cnt += nz;
+          bad += (nz && (A.elim[A.col[j]] & MASK_ELIM));
+        }
+      } else {
+        for (int j = b; j < e; ++j) cnt += (A.val[j] != 0.0);
+      }
+    }
+    const int wt = row < c1 ? max(cnt, REBLOCK_MINW) : 0;
+    // block-wide exclusive scan of (cnt, wt) in row order
+    int ie = cnt, iw = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int te = __shfl_up_sync(0xffffffffu, ie, o), tw = __shfl_up_sync(0xffffffffu, iw, o);
+      if (lane >= o) { ie += te; iw += tw; }
+    }
+    __syncthreads();
+    if (lane == 31) { sh_i[w] = ie; sh_i[32 + w] = iw; }
+    __syncthreads();
+    int offe = 0, offw = 0, tote = 0, totw = 0;
+    for (int i = 0; i < nw; ++i) {
+      const int a = sh_i[i], c = sh_i[32 + i];
+      if (i < w) { offe += a; offw += c; }
+      tote += a; totw += c;
+    }
+    if (row < c1) {
+      A.rowpre[row] = make_int2(runE + offe + ie - cnt, runW + offw + iw - wt);
+      A.re[row] = cnt;
+    }
+    runE += tote; runW += totw;
+  }
+  if (threadIdx.x == 0) { A.scanpart[blockIdx.x] = runE; A.scanpart[G + blockIdx.x] = runW; }
+  bar.sync();
+  int offE = 0, offW = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += blockDim.x) {
+    offE += __ldcg(A.scanpart + j);
+    offW += __ldcg(A.scanpart + G + j);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    offE += __shfl_down_sync(0xffffffffu, offE, o);
+    offW += __shfl_down_sync(0xffffffffu, offW, o);
+  }
+  __syncthreads();
+  if (lane == 0) { sh_i[w] = offE; sh_i[32 + w] = offW; }
+  __syncthreads();
+  offE = 0; offW = 0;
+  for (int i = 0; i < nw; ++i) { offE += sh_i[i]; offW += sh_i[32 + i]; }
+  __syncthreads();
+  for (int base = c0; base < c1; base += blockDim.x) {
+    const int row = base + threadIdx.x;
+    if (row >= c1) continue;
+    const int2 pr = A.rowpre[row];  // written by this same thread above
+    const int cnt = A.re[row];
+    const int E = offE + pr.x, W = offW + pr.y;
+    const int blk = W / T, blk_next = (W + max(cnt, REBLOCK_MINW)) / T;
+    int4* d = A.desc;
+    if (row == 0) { d[0].x = 0; d[0].z = 0; }
+    if (blk_next != blk || row == n - 1) {  // last row of its block: closes it and opens the next one
+      d[blk].y = row + 1; d[blk].w = E + cnt;
+      if (row + 1 < n) { d[blk_next].x = row + 1; d[blk_next].z = E + cnt; }
+      else *A.nblk = blk + 1;
+    }
+    int dst = E;
+    if (cnt > 0) {
+      const int b = A.rowptr[row], e = A.rowptr[row + 1];
+      for (int j = b; j < e; ++j) {
+        const double v = A.val[j];
+        if (v != 0.0) { A.val2[dst] = v; A.col2[dst] = A.col[j]; ++dst; }
+      }
+    }
+    A.re[row] = E + cnt;
+  }
+  bar.sync();
+  nb = __ldcg(A.nblk);
   return bad;
 }
 
@@ -306,8 +412,8 @@ constexpr int BLOCK_OVERHEAD_NNZ = 192;
 // Distributed scan: each CTA sums its chunk of blocks, a barrier, offsets from the CTAs before it, a
 // barrier, then two binary searches per warp.  sh_i: 64 ints of shared memory.
 template <class Bar>
-__device__ __forceinline__ BlockRange balance_partition(const CsrView& A, Bar& bar, int* sh_i) {
-  const int nb = A.nrowblk, G = gridDim.x, wpb = blockDim.x >> 5;
+__device__ __forceinline__ BlockRange balance_partition(const CsrView& A, Bar& bar, int* sh_i, int nb) {
+  const int G = gridDim.x, wpb = blockDim.x >> 5;
   const int L = (nb + G - 1) / G;
   const int c0 = min(nb, (int)blockIdx.x * L), c1 = min(nb, c0 + L);
   // chunk-local inclusive scan by one warp (chunks are a few dozen blocks)
@@ -460,7 +566,7 @@ __device__ __forceinline__ void spmv_stream_c(const CsrView& A, const BlockRange
   for (int k = rg.k0; k < rg.k1; k += rg.kstep) {
     const int kn = k + rg.kstep;
     const int4 dn = (kn < rg.k1) ? __ldcg(A.desc + kn) : make_int4(0, 0, 0, 0);
-    const int r0 = d.x, nr = d.y, j0 = d.z, j1 = d.w;
+    const int r0 = d.x, nr = d.y - d.x, j0 = d.z, j1 = d.w;
     const int row = r0 + lane;
     const bool act = lane < nr;
     const int e1 = act ? __ldcg(A.re + row) : j0;

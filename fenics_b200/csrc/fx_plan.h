@@ -36,6 +36,7 @@ struct DevPattern {
   // block-triangular elimination (fx_plan_set_eliminated_dofs): trailing rows solved by back-substitution
   std::vector<int> rowblk_h;  // host copy of rowblk
   int maxblknnz = 0;          // largest pattern entry count of a row block
+  int maxrow = 0;             // longest pattern row
   int* agg = nullptr;         // [n] aggregate of each dof (fx_plan_set_aggregates), null = none
   int nagg = 0;
   int agg_nl = 0;             // most aggregates the rows of one CTA of the resident CG kernel touch
@@ -105,6 +106,8 @@ struct fx_plan {
   int *ccol = nullptr, *cre = nullptr;
   int4* cdesc = nullptr;  // per-row-block descriptors of the compacted copy
   int *cprefix = nullptr, *scanpart = nullptr;  // nnz-balanced partition of the row blocks (balance_partition)
+  int2* rowpre = nullptr;                       // compact_reblock: per-row prefixes
+  int* nblk = nullptr;                          // compact_reblock: number of blocks built
   double* coarse = nullptr;                     // two-level preconditioner scratch: E0, E1 (256^2 each), cvec [3][256]
   unsigned* bar = nullptr;                      // grid-barrier counter of the persistent Krylov kernels
   double* gmres_basis = nullptr;                // GMRES Krylov basis, (restart + 1) x n, allocated on first use
