@@ -673,5 +673,20 @@ struct STREAM_L {
   template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) { a.template add<QV>(d[0]); }
 };
 
+// shear_rate(u) (lid-driven-cavity/fenics_fem.py:380-398): L = inner(g, phi)*dx, g = inner(0.5*gamma, gamma),
+// gamma = grad(u) + grad(u)^T  ->  g = 2 u0,x^2 + (u0,y + u1,x)^2 + 2 u1,y^2;  same matrix as stream_function
+struct SHEAR_L {
+  using Space = SpVs; using Facet = NoFacet;
+  static constexpr int QDEG = 4, NP = 1;
+  FX_HD static void point(const PtArgs& x, double* d) {
+    P2Phys b;
+    p2_phys(x.xi, x.et, x.g, b);
+    const Vel u = eval_vel(x.m, x.s.f[F_W1], x.cell, b);
+    const double s = u.g01 + u.g10;
+    d[0] = 2.0 * u.g00 * u.g00 + s * s + 2.0 * u.g11 * u.g11;
+  }
+  template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) { a.template add<QV>(d[0]); }
+};
+
 }  // namespace ldc
 }  // namespace fx

@@ -60,6 +60,7 @@
   XC(FX_FORM_C1_L2, fx::ldc::C1_L2<4>, fx::ldc::C1_L2<5>)   \
   X(FX_FORM_STREAM_L, fx::ldc::STREAM_L<false>)             \
   X(FX_FORM_COMP_STREAM_L, fx::ldc::STREAM_L<true>)         \
+  X(FX_FORM_SHEAR_L, fx::ldc::SHEAR_L)                      \
   X(FX_FORM_C1_L5, fx::ldc::C1_L5)                          \
   X(FX_FORM_C1_L7, fx::ldc::C1_L7)                          \
   X(FX_FORM_C1_L4, fx::ldc::LDC_L4<false>)                  \

@@ -136,6 +136,22 @@ class _LDC:
         la.krylov_solve(self._Apsi, self._psi.vector(), self._bpsi, "cg", "jacobi", rtol=rtol, maxit=100000)
         return self._psi
 
+    def shear_rate(self, rtol=1e-12):
+        """shear_rate(u1) (lid-driven-cavity/fenics_fem.py:380-398; incomp_LDC.py:466, comp_LDC_mesh_convergence.py:613,
+        compressible_dgp.py:643): the stream function's Poisson matrix with the right-hand side
+        inner(0.5*gamma, gamma), gamma = grad(u1) + grad(u1)^T; CG + Jacobi to `rtol` where the reference uses LU."""
+        Vs = self.S["Vs"]
+        if not hasattr(self, "_gam"):
+            self._gam = Function(Vs, self.plan)
+            self._Agam, self._bgam = Matrix(self.plan, "Vs"), Vector(self.plan, "Vs")
+            self._bcgam = DirichletBC(Vs, 0.0, lambda x, on_boundary: on_boundary)
+        f = self.pr.form
+        assemble(f(abi.FX_FORM_STREAM_A), tensor=self._Agam)
+        assemble(f(abi.FX_FORM_SHEAR_L), tensor=self._bgam)
+        self._bcgam.apply(self._Agam, self._bgam)
+        la.krylov_solve(self._Agam, self._gam.vector(), self._bgam, "cg", "jacobi", rtol=rtol, maxit=100000)
+        return self._gam
+
     def min_location(self, fn):
         """min_location(u, mesh): coordinates of the dofs holding the minimum of `fn`."""
         v = fn.vector().get_local()

@@ -55,7 +55,9 @@ def comp_stream_function(rho, u):
 
 
 def shear_rate(u):
-    raise NotImplementedError("shear_rate (plot helper, :380-400) is outside the time-step path; evaluate it with dolfin")
+    """the stream function's Poisson problem with inner(0.5*gamma, gamma), gamma = grad u + grad u^T, on the right
+    (:380-398): CG on the device."""
+    return _driver_of(u).shear_rate()
 
 
 def l2norm_solution(u):

@@ -76,6 +76,7 @@ typedef enum {
   FX_FORM_STREAM_A = 10,      /* inner(grad(psi), grad(phi))*dx on VS                              */
   FX_FORM_STREAM_L,           /* inner(u[1].dx(0) - u[0].dx(1), phi)*dx, u = velocity of FX_F_W1   */
   FX_FORM_COMP_STREAM_L,      /* inner(rho*u[1].dx(0) - rho*u[0].dx(1), phi)*dx, rho = FX_F_RHO1   */
+  FX_FORM_SHEAR_L,            /* shear_rate(u): inner(inner(0.5*gamma, gamma), phi)*dx, gamma = grad u + grad u^T (:380-398) */
   /* cfg1: bilinear */
   FX_FORM_C1_A1 = 100, FX_FORM_C1_A2, FX_FORM_C1_A5, FX_FORM_C1_A7, FX_FORM_C1_A4,
   /* cfg1: linear */

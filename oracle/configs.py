@@ -53,6 +53,21 @@ def solve_zero_sum(A, b):
     return fem.solve_lu(K, np.concatenate([b, [0.0]]))[:n]
 
 
+def shear_rate(S, u):
+    """shear_rate(u) (lid-driven-cavity/fenics_fem.py:380-398): the stream function's Poisson problem with the
+    right-hand side inner(0.5*gamma, gamma), gamma = grad(u) + tgrad(u).  Returns (dof vector, a, L)."""
+    Vs = S["Vs"]
+    psi, phi = fem.TrialFunction(Vs), fem.TestFunction(Vs)
+    a = inner(grad(psi), grad(phi)) * dx
+    gamma = grad(u) + tgrad(u)
+    g = inner(0.5 * gamma, gamma)
+    L = inner(g, phi) * dx
+    A, b = fem.assemble(a), fem.assemble(L)
+    bc = fem.DirichletBC(Vs, (0,), 0.0, lambda x: np.ones(len(x), dtype=bool))
+    bc.apply(A, b)
+    return fem.solve_lu(A, b), a, L
+
+
 def make_spaces(mesh, dofmaps=None):
     """function_spaces(mesh, 2) (lid-driven-cavity/fenics_fem.py:262-287): the spaces the loops use."""
     dm = dofmaps or {}

@@ -160,3 +160,13 @@ def test_comp_ldc_sweep_script_forms():
         if hasattr(cfg, a) and hasattr(other, a) and hasattr(getattr(cfg, a), "vec"):
             getattr(other, a).vec[:] = getattr(cfg, a).vec
     assert lc.rel_err(fem.assemble(other.forms["L2"]), fem.assemble(cfg.forms["L2"])) > 1e-6
+
+
+def test_shear_rate_form():
+    """shear_rate(u1) (lid-driven-cavity/fenics_fem.py:380-398): right-hand side functor against the oracle, UFL degree."""
+    mesh, cfg, plan = _setup(2)
+    st, par = lc.state_of(cfg), lc.params_of(cfg)
+    _, a, L = configs.shear_rate(cfg.S, cfg.u1)
+    assert lc.rel_err(plan.assemble_vector(abi.FX_FORM_SHEAR_L, "Vs", st, par), fem.assemble(L)) < TOL
+    degs = {k: d for k, _, d in fem.quadrature_degrees(L, mesh)}
+    assert plan.form_qdeg(abi.FX_FORM_SHEAR_L)[0] == degs["dx"]

@@ -342,6 +342,10 @@ def test_stream_function_and_min_location(kind):
     lo, ld = configs.min_location(psi_o, ocl.S["Vs"]), drv.min_location(psi)
     assert lo.shape == ld.shape and np.allclose(lo, ld, atol=0, rtol=0)
     assert 0.2 < ld[0][0] < 0.8 and 0.5 < ld[0][1] < 1.0  # the primary vortex sits under the lid
+    gam_o, _, _ = configs.shear_rate(ocl.S, ocl.u1)     # shear_rate(u1) + max_location (:466-470 / :613-617)
+    gam = drv.shear_rate()
+    assert lc.rel_err(gam.vector().get_local(), gam_o) < 1e-8
+    assert np.array_equal(drv.max_location(gam), ocl.S["Vs"].tabulate_dof_coordinates()[np.where(gam_o == gam_o.max())])
 
 
 def test_full_size_properties():
