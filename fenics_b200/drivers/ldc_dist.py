@@ -3,7 +3,8 @@
 Krylov + ghost refresh) and the functionals (owned cells + all-reduce) differ, so every driver gets its
 partitioned variant from one mixin:
 
-    DistCompLDC (config 2), DistEwmJBP (config 3), DistFenepmpJBP (config 4), DistCompDGP (config 5)
+    DistCompLDC (config 2), DistEwmJBP (config 3), DistFenepmpJBP (config 4), DistCompDGP (config 5),
+    DistIncompDGP (incompressible_dgp.py)
 """
 import torch  # noqa: F401
 import torch.distributed as dist
@@ -12,7 +13,7 @@ from .. import dist_la
 from .._lib import check, lib
 from ..partition import LocalPartition, rcb_partition
 from ..spaces import function_spaces
-from .dgp import CompDGP
+from .dgp import CompDGP, IncompDGP
 from .ewm import EwmJBP
 from .jbp import FenepmpJBP
 from .ldc import CompLDC
@@ -85,3 +86,4 @@ DistCompLDC = distributed(CompLDC)
 DistEwmJBP = distributed(EwmJBP)
 DistFenepmpJBP = distributed(FenepmpJBP)
 DistCompDGP = distributed(CompDGP)
+DistIncompDGP = distributed(IncompDGP)  # singular pressure system: the replicated solve keeps the Jacobi-Krylov gauge

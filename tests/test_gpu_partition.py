@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("cfg,port,fused", [("cfg2", 29611, "1"), ("cfg3", 29614, "1"), ("cfg4", 29612, "1"),
-                                            ("cfg5", 29613, "1"), ("cfg2", 29615, "0")])
+                                            ("cfg5", 29613, "1"), ("cfg6", 29616, "1"), ("cfg2", 29615, "0")])
 def test_partitioned_matches_single_gpu(cfg, port, fused):
     """fields, energies and the boundary functionals (journal torque / load, Nusselt number) of the
     partitioned drivers against the single-GPU drivers."""

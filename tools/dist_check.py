@@ -21,7 +21,8 @@ GENERAL3 = dict(dt=0.002, Re=7.0, We=0.3, Ma=0.05, betav=0.6, al=0.2, Di=0.004, 
 CFG = {"cfg2": (ldc.CompLDC, ldc_dist.DistCompLDC, lambda k: pmesh.Skew_Mesh(k, 1, 1), {}),
        "cfg3": (ewm.EwmJBP, ldc_dist.DistEwmJBP, lambda k: pmesh.annulus_mesh(4 * k, max(2, k // 2), x_1=-0.9), GENERAL3),
        "cfg4": (jbp.FenepmpJBP, ldc_dist.DistFenepmpJBP, lambda k: pmesh.annulus_mesh(4 * k, max(2, k // 2)), dict(We=0.5)),
-       "cfg5": (dgp.CompDGP, ldc_dist.DistCompDGP, lambda k: dgp.DGP_Mesh(k, 1, 1), {})}
+       "cfg5": (dgp.CompDGP, ldc_dist.DistCompDGP, lambda k: dgp.DGP_Mesh(k, 1, 1), {}),
+       "cfg6": (dgp.IncompDGP, ldc_dist.DistIncompDGP, lambda k: dgp.DGP_Mesh(k, 1, 1), dict(Ra=5000.0, We=0.2))}
 Serial, Dist, make_mesh, params = CFG[cfg]
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local)
@@ -33,8 +34,7 @@ s = Serial(make_mesh(n), device=local, **params)
 for drv in (d, s):
     drv.solve_rtol = 1e-13
     drv.pressure_method = "cg"
-    if cfg != "cfg5":
-        drv.t = 0.45
+    drv.t = 1.4 if cfg in ("cfg5", "cfg6") else 0.45
 worst = 0.0
 for k in range(K):
     rd, rs = d.step(), s.step()
