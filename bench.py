@@ -29,7 +29,9 @@ METRIC = "time-steps/s at 1M DOFs (assembly+solve)"
 UNIT = "steps/s"
 N_MESH = 192
 T_START = 0.45
-WE_SWEEP = [0.25, 0.1, 0.5, 1.0, 0.001, 0.25, 0.1, 0.5]  # LDC/flow-parameters.csv row 2 values, per rank
+# ensemble members (We, Ma) per rank: values of lid-driven-cavity/flow-parameters.csv rows 2-3 that this mesh / time step
+# integrates stably (We = 0.001 at n=192, dt=0.001 blows up in the stress solve: the (1-betav)/We coupling is explicit)
+SWEEP = [(0.25, 0.001), (0.1, 0.001), (0.5, 0.001), (1.0, 0.001), (0.25, 0.01), (0.1, 0.01), (0.5, 0.01), (1.0, 0.01)]
 
 
 def parse():
@@ -184,7 +186,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     m = pmesh.Skew_Mesh(args.n, 1, 1)
-    drv = ldc.CompLDC(m, We=WE_SWEEP[rank % len(WE_SWEEP)], device=local)
+    we_member, ma_member = SWEEP[rank % len(SWEEP)]
+    drv = ldc.CompLDC(m, We=we_member, Ma=ma_member, device=local)
     drv.pressure_method = "cg"   # north_star: CG for the (symmetric) pressure system
     coarse = drv.enable_pressure_coarse(256)  # ... preconditioned by Jacobi + aggregate coarse correction
     drv.check = False            # solver outcomes fetched once per step, still raising on failure
@@ -378,9 +381,9 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "cfg2 lid-driven-cavity/comp_LDC_mesh_convergence.py time step on the n=%d "
-                                       "skewed cavity mesh (%d cells, %d DOFs), Re=10 We=%g Ma=0.001 dt=0.001, "
+                                       "skewed cavity mesh (%d cells, %d DOFs), Re=10 We=%g Ma=%g dt=0.001, "
                                        "solver rtol 1e-5 (reference default), t0=%.2f; pressure solve: CG with %s" %
-                                       (args.n, m.num_cells(), dofs, drv.p["We"], T_START,
+                                       (args.n, m.num_cells(), dofs, drv.p["We"], drv.p["Ma"], T_START,
                                         "Jacobi + 256-aggregate coarse correction" if coarse else "Jacobi"),
                            "dofs": dofs, "parallelism": "ensemble x%d (one independent run per GPU)" % world
                            if world > 1 else "single GPU",
