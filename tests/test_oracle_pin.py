@@ -155,3 +155,26 @@ def test_pattern_sizes_match_closed_forms():
         V = fem.FunctionSpace(m, comps)
         A = fem.assemble(inner(fem.TrialFunction(V), fem.TestFunction(V)) * dx)
         assert V.dim == dim and A.nnz == nnz
+
+
+def test_weighted_gauge_solve_of_the_singular_pressure_system():
+    """oracle.configs_dgp.solve_weighted_gauge: on a pure-Neumann P1 stiffness matrix (constants in the null space) it
+    returns A x = b with sum_i A_ii (x - x0)_i = 0 -- the invariant of LEFT-Jacobi-preconditioned Krylov iterations, checked
+    here against an actual Jacobi-preconditioned CG run from the same initial guess."""
+    import scipy.sparse.linalg as spla
+    from oracle.configs_dgp import solve_weighted_gauge
+    from oracle.ufl_lite import dx, grad, inner
+    mesh = fem.skew_mesh(6)
+    Q = fem.FunctionSpace(mesh, ["P1"])
+    p, q = fem.TrialFunction(Q), fem.TestFunction(Q)
+    A = fem.assemble(inner(grad(p), grad(q)) * dx).tocsr()
+    rng = np.random.default_rng(0)
+    b = A @ rng.standard_normal(A.shape[0])          # consistent right-hand side
+    x0 = rng.standard_normal(A.shape[0])
+    x = solve_weighted_gauge(A, b, x0)
+    d = A.diagonal()
+    assert np.abs(A @ x - b).max() < 1e-11 * np.abs(b).max()
+    assert abs(d @ (x - x0)) < 1e-10 * np.abs(d).max() * np.abs(x).max()
+    M = spla.LinearOperator(A.shape, lambda v: v / d)
+    xk, info = spla.cg(A, b, x0=x0.copy(), rtol=1e-14, atol=0.0, maxiter=5000, M=M)
+    assert info == 0 and np.abs(xk - x).max() < 1e-8 * np.abs(x).max()
