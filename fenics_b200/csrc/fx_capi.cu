@@ -439,12 +439,11 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
     if (count[g] == 0) return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: aggregate %d is empty", g);
   // the resident CG kernel gives CTA c the row blocks c*8R .. c*8R+8R-1 (R per warp); each CTA keeps the rows
   // of (P^T A P)^-1 of the aggregates its rows touch in shared memory
+  // (systems too large for the resident kernel use the coarse correction inside k_cg: no per-CTA limit)
   const PcgConfig cfg = pcg_resident_config(P, d.nrowblk, d.maxblknnz);
-  if (cfg.R == 0)
-    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: space %d is too large for the resident CG kernel", space);
-  const int per_cta = 8 * cfg.R;
+  const int per_cta = 8 * std::max(cfg.R, 1);
   int nl_max = 0;
-  for (int c = 0; c < cfg.grid; ++c) {
+  for (int c = 0; c < cfg.grid && cfg.R > 0; ++c) {
     std::vector<char> seen(k, 0);
     int nl = 0;
     for (int b = c * per_cta; b < std::min(d.nrowblk, (c + 1) * per_cta); ++b)
@@ -452,12 +451,12 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
         if (!seen[agg[r]]) { seen[agg[r]] = 1; ++nl; }
     nl_max = std::max(nl_max, nl);
   }
-  if (nl_max > cfg.nlmax)
+  if (cfg.R > 0 && nl_max > cfg.nlmax)
     return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: a CTA's rows touch %d aggregates (limit %d): aggregates "
                      "are not local in the dof numbering", nl_max, cfg.nlmax);
   d.agg_nl = nl_max;
   if (!P->coarse) {
-    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * COARSE_KMAX * COARSE_KMAX + 3 * COARSE_KMAX)));
+    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * COARSE_KMAX * COARSE_KMAX + 4 * COARSE_KMAX)));
   }
   FX_CUDA(cudaMalloc((void**)&d.agg, sizeof(int) * (size_t)d.n));
   FX_CUDA(cudaMemcpy(d.agg, agg, sizeof(int) * (size_t)d.n, cudaMemcpyHostToDevice));

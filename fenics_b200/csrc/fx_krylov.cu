@@ -165,7 +165,7 @@ __device__ __forceinline__ void leave(Bar& bar, const KArgs& a, int it, int conv
 }
 __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc) {
   if (A.elim != nullptr && (A.elim[row] & MASK_INACTIVE)) return 0.0;  // eliminated / ghost rows stay identically zero in the iteration
-  if (pc != FX_PC_JACOBI) return 1.0;
+  if (pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE) return 1.0;
   double dg = 0.0;
   for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j)
     if (A.col[j] == row) dg = A.val[j];
@@ -351,6 +351,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
   leave(bar, a, a.maxit, 0, rn, bn);
 }
 
+__device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k, GridBar& bar, double* scratch);
+
 // ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
 // u = M^-1 r, w = A u, p = u + beta p, s = w + beta s (= A p).  One SpMV and ONE fused reduction
 // (gamma = (r,u), delta = (w,u), ||u||^2) per iteration: two grid barriers instead of three.
@@ -385,16 +387,82 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
     bar.sync();
   }
   const BlockRange rg = balance_partition(A, bar, sh_i, nb);
+  // ---- two-level preconditioner M^-1 = D^-1 + P E^-1 P^T, E = P^T A P, for systems too large for the resident kernel
+  // (k_pcg_res): the coarse matrix is assembled from the values and inverted across the grid once per solve; every
+  // application costs two grid barriers: restriction c = P^T v (shared-memory atomics per CTA, one global reduction
+  // per aggregate and CTA) | e = E^-1 c, one warp per aggregate | prolongation.
+  const bool coarse = !DIST && a.cz.agg != nullptr;
+  const int ck = a.cz.k;
+  __shared__ double c_sh[DIST ? 1 : COARSE_KMAX];
+  const double* Einv = nullptr;
+  int cph = 0;
+  double* evec = a.cz.cvec + 3 * COARSE_KMAX;
+  // vout += P E^-1 P^T vin; with dsum != null also dsum[0] += (vin, vout), dsum[1] += (vout, vout) on the final values
+  auto coarse_apply = [&](const double* vin, double* vout, double* dsum) {
+    double* cur = a.cz.cvec + (cph % 3) * COARSE_KMAX;
+    for (int g = threadIdx.x; g < ck; g += blockDim.x) c_sh[g] = 0.0;
+    __syncthreads();
+    for (int i = gt; i < n; i += gs) atomicAdd(&c_sh[a.cz.agg[i]], vin[i]);
+    __syncthreads();
+    for (int g = threadIdx.x; g < ck; g += blockDim.x) {
+      const double v = c_sh[g];
+      if (v != 0.0) atomicAdd(cur + g, v);
+    }
+    if (blockIdx.x == 0)  // the buffer of the next application: nobody reads or adds to it now
+      for (int g = threadIdx.x; g < ck; g += blockDim.x) a.cz.cvec[((cph + 1) % 3) * COARSE_KMAX + g] = 0.0;
+    bar.sync();
+    const int lane = threadIdx.x & 31;
+    for (int g = gt >> 5; g < ck; g += gs >> 5) {  // one warp per aggregate (small systems run on a small grid)
+      double e = 0.0;
+      for (int h = lane; h < ck; h += 32) e += __ldcg(Einv + (size_t)g * ck + h) * __ldcg(cur + h);
+      e = warp_sum(e);
+      if (lane == 0) evec[g] = e;
+    }
+    bar.sync();
+    for (int g = threadIdx.x; g < ck; g += blockDim.x) c_sh[g] = __ldcg(evec + g);
+    __syncthreads();
+    for (int i = gt; i < n; i += gs) {
+      const double vo = vout[i] + c_sh[a.cz.agg[i]];
+      vout[i] = vo;
+      if (dsum != nullptr) { dsum[0] += vin[i] * vo; dsum[1] += vo * vo; }
+    }
+    __syncthreads();
+    ++cph;
+  };
+  if constexpr (!DIST) {
+    if (coarse) {
+      for (int i = gt; i < ck * ck; i += gs) a.cz.E0[i] = 0.0;
+      for (int i = gt; i < 4 * COARSE_KMAX; i += gs) a.cz.cvec[i] = 0.0;
+      bar.sync();
+      for (int row = gt; row < n; row += gs) {
+        const int ga = a.cz.agg[row];
+        for (int j = A.rowptr[row]; j < A.rowptr[row + 1]; ++j) {
+          const double v = A.val[j];
+          if (v != 0.0) atomicAdd(a.cz.E0 + (size_t)ga * ck + a.cz.agg[A.col[j]], v);
+        }
+      }
+      bar.sync();
+      Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, prod);  // scratch: the SpMV staging area (idle here)
+    }
+  }
   spmv_stream_c(A, rg, a.x, prod,
                 [&](int row) { return Ops2{row_diag_inv(A, row, a.pc), a.b[row]}; },
                 [&](int row, double ax, const Ops2& o) {
                   const double ri = o.b - ax, ui = o.a * ri, bi = o.a * o.b;
-                  dinv[row] = o.a; r[row] = ri; p[row] = 0.0; s[row] = 0.0;
+                  dinv[row] = o.a; r[row] = ri; p[row] = 0.0; s[row] = coarse ? bi : 0.0;
                   const unsigned char mk = mask != nullptr ? mask[row] : 0;
                   if (!(mk & MASK_GHOST)) u[row] = ui;
                   if (mk & MASK_IFACE) push_iface(a.dd, 1, row, ui);
-                  acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
+                  if (!coarse) { acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi; }
                 });
+  if (coarse) {  // u = M^-1 r and ||M^-1 b|| with the coarse part; s holds D^-1 b meanwhile
+    bar.sync();
+    double du[2] = {0.0, 0.0}, db[2] = {0.0, 0.0};
+    coarse_apply(r, u, du);
+    coarse_apply(a.b, s, db);
+    for (int i = gt; i < n; i += gs) s[i] = 0.0;
+    acc[0] = du[0]; acc[1] = du[1]; acc[2] = db[1];
+  }
   gsum<4>(a, bar, acc, phase, sh);
   if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); bar.save(); return; }
   double gamma = acc[0], un = sqrt(acc[1]);
@@ -431,9 +499,22 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
         const int i = a.dd.s_local[k];
         if (k == 0 || a.dd.s_local[k - 1] != i) upd(i, true);
       }
-    for (int i = gt; i < n; i += gs) {
-      if (DIST && (mask[i] & (MASK_GHOST | MASK_IFACE))) continue;
-      upd(i, false);
+    if (coarse) {  // u = D^-1 r here, the coarse part and the two sums follow in coarse_apply
+      for (int i = gt; i < n; i += gs) {
+        const double pi = u[i] + beta * p[i];
+        const double si = w[i] + beta * s[i];
+        p[i] = pi; s[i] = si;
+        a.x[i] += alpha * pi;
+        const double ri = r[i] - alpha * si;
+        r[i] = ri;
+        u[i] = dinv[i] * ri;
+      }
+      coarse_apply(r, u, d);
+    } else {
+      for (int i = gt; i < n; i += gs) {
+        if (DIST && (mask[i] & (MASK_GHOST | MASK_IFACE))) continue;
+        upd(i, false);
+      }
     }
     bar.sync();
     spmv_stream_c(A, rg, u, prod, [&](int row) { return Ops2{u[row], 0.0}; },
@@ -1098,11 +1179,14 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg, gmres available)", method);
   if (pc != FX_PC_NONE && pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE)
     return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, jacobi_coarse available)", pc);
-  const PcgConfig pcfg = pcg_resident_config(P, p.nrowblk, p.maxblknnz);
-  if (pc == FX_PC_JACOBI_COARSE &&
-      (method != FX_KSP_CG || p.nagg == 0 || rtol < 1e-9 || p.nelim != 0 || pcfg.R == 0 || p.agg_nl > pcfg.nlmax))
-    return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates), "
-                     "rtol >= 1e-9 and a system that fits the resident CG kernel");
+  PcgConfig pcfg = pcg_resident_config(P, p.nrowblk, p.maxblknnz);
+  static const int resident_env = getenv("FX_PCG_RESIDENT") ? atoi(getenv("FX_PCG_RESIDENT")) : 1;
+  if (!resident_env) pcfg.R = 0;  // testing aid: send CG solves through k_cg even when the system would fit k_pcg_res
+  // jacobi_coarse: the resident kernel when the system fits it (and rtol >= 1e-9: pipelined recurrences), else k_cg
+  const bool coarse_resident = pcfg.R > 0 && p.agg_nl <= pcfg.nlmax && rtol >= 1e-9;
+  if (pc == FX_PC_JACOBI_COARSE && (method != FX_KSP_CG || p.nagg == 0 || p.nelim != 0))
+    return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates) and no "
+                     "eliminated rows");
   const bool part = P->dist.world > 1;  // mesh-partitioned run: fused halo pushes + cross-GPU barriers
   if (part && !p.has_halo)
     return set_error(FX_ERR_ARG, "partitioned plan: space %d has no halo (fx_plan_set_halo)", space);
@@ -1166,7 +1250,8 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     return FX_OK;
   }
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
-  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part && pcfg.R > 0) {
+  if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part && pcfg.R > 0 &&
+      (pc != FX_PC_JACOBI_COARSE || coarse_resident)) {
     switch (pcfg.R) {
       case 1: return launch_pcg_res<1>(P, ka, pcfg.grid, st);
       case 2: return launch_pcg_res<2>(P, ka, pcfg.grid, st);

@@ -220,13 +220,35 @@ def test_two_level_pressure_preconditioner():
         assert lc.rel_err(x.get_local(), ref) < 1e-6, (pc, lc.rel_err(x.get_local(), ref))
         its[pc] = info.iterations
     assert its["jacobi_coarse"] < 0.6 * its["jacobi"], its
-    # not usable: BiCGStab, tight tolerances, spaces without aggregates -> loud errors, no silent fallback
+    # tight tolerances leave the pipelined resident kernel for the two-level CG inside k_cg (standard recurrences)
     x = la.Vector(drv.plan, "Q")
-    for kw in (dict(method="bicgstab", rtol=1e-5), dict(method="cg", rtol=1e-12)):
-        with pytest.raises(Exception) as e:
-            la.krylov_solve(A, x, b, kw["method"], "jacobi_coarse", rtol=kw["rtol"])
-        assert "jacobi_coarse" in str(e.value)
+    info = la.krylov_solve(A, x, b, "cg", "jacobi_coarse", rtol=1e-12, maxit=20000)
+    assert info.converged == 1 and info.iterations < 0.6 * its["jacobi"] * 1.6 and lc.rel_err(x.get_local(), ref) < 1e-9
+    # not usable: BiCGStab, spaces without aggregates -> loud errors, no silent fallback
+    with pytest.raises(Exception) as e:
+        la.krylov_solve(A, x, b, "bicgstab", "jacobi_coarse", rtol=1e-5)
+    assert "jacobi_coarse" in str(e.value)
     assert drv.plan.set_aggregates("Q", [], 0)
+
+
+def test_two_level_cg_outside_the_resident_kernel():
+    """systems too large for k_pcg_res (n > 384 for the pressure space) run the coarse correction inside k_cg; the
+    environment switch FX_PCG_RESIDENT=0 sends a small system down that path (read once per process -> subprocess)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "coarse_cg_check.py"), "32"], capture_output=True, text=True,
+                       timeout=300, env=dict(os.environ, FX_PCG_RESIDENT="0"))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    rows = {}
+    for line in r.stdout.splitlines():
+        m = re.match(r"(\w+) rtol (\S+) iterations (\d+) converged (-?\d+) .* err vs splu (\S+)", line)
+        if m:
+            rows[(m.group(1), float(m.group(2)))] = (int(m.group(3)), int(m.group(4)), float(m.group(5)))
+    assert len(rows) == 4 and all(v[1] == 1 for v in rows.values()), rows
+    assert rows[("jacobi_coarse", 1e-9)][0] < 0.6 * rows[("jacobi", 1e-9)][0] and rows[("jacobi_coarse", 1e-9)][2] < 1e-7, rows
 
 
 def test_krylov_nonconvergence_raises():
