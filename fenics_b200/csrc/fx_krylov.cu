@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
   const CsrView& A = a.A;
   const size_t n = (size_t)A.n;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nw = gridDim.x * LA_WARPS, gw = blockIdx.x * LA_WARPS + wib;
+  const int gw = blockIdx.x * LA_WARPS + wib;
   // per-warp shared slices
   const int SL = a.cz.slice;
   double* sval = reinterpret_cast<double*>(dyn) + (size_t)wib * R * SL;

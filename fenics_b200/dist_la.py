@@ -60,7 +60,6 @@ class DistContext:
         dist.barrier(group)  # every region is zero before anybody's first solve
         ptrs = (C.c_void_p * world)(*[int(p) for p in self._hdl.buffer_ptrs])
         check(lib.fx_plan_set_peer_regions(self.plan.h, rank, world, ptrs, nmax))
-        self._keep = []
         for sp in ("W", "Zc", "Q"):
             if sp not in lp.halo:
                 continue

@@ -1,5 +1,4 @@
 """Shared implementation of the three shim modules (see package docstring)."""
-import math
 import os
 import sys
 
@@ -242,6 +241,3 @@ def solution_functions(Q, W, V, Z):
         W._shim_plan = plan
     return make_solution_functions(plan)(Q, W, V, Z)
 
-
-def math_tanh(x):
-    return math.tanh(x)
