@@ -428,8 +428,8 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
   cudaFree(d.agg);
   d.agg = nullptr; d.nagg = 0;
   if (k == 0) return FX_OK;
-  if (k % 32 != 0 || k > COARSE_KMAX)
-    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: k must be a multiple of 32 and <= %d", COARSE_KMAX);
+  if (k % 32 != 0 || k > COARSE_KMAX_CG)
+    return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: k must be a multiple of 32 and <= %d", COARSE_KMAX_CG);
   std::vector<int> count(k, 0);
   for (int i = 0; i < d.n; ++i) {
     if (agg[i] < 0 || agg[i] >= k) return set_error(FX_ERR_ARG, "fx_plan_set_aggregates: agg[%d] = %d out of range", i, agg[i]);
@@ -443,7 +443,7 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
   const PcgConfig cfg = pcg_resident_config(P, d.nrowblk, d.maxblknnz);
   const int per_cta = 8 * std::max(cfg.R, 1);
   int nl_max = 0;
-  for (int c = 0; c < cfg.grid && cfg.R > 0; ++c) {
+  for (int c = 0; c < cfg.grid && cfg.R > 0 && k <= COARSE_KMAX; ++c) {
     std::vector<char> seen(k, 0);
     int nl = 0;
     for (int b = c * per_cta; b < std::min(d.nrowblk, (c + 1) * per_cta); ++b)
@@ -451,12 +451,12 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
         if (!seen[agg[r]]) { seen[agg[r]] = 1; ++nl; }
     nl_max = std::max(nl_max, nl);
   }
-  if (cfg.R > 0 && nl_max > cfg.nlmax)
+  if (cfg.R > 0 && k <= COARSE_KMAX && nl_max > cfg.nlmax)
     return set_error(FX_ERR_UNSUPPORTED, "fx_plan_set_aggregates: a CTA's rows touch %d aggregates (limit %d): aggregates "
                      "are not local in the dof numbering", nl_max, cfg.nlmax);
   d.agg_nl = nl_max;
   if (!P->coarse) {
-    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * COARSE_KMAX * COARSE_KMAX + 4 * COARSE_KMAX)));
+    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * (size_t)COARSE_KMAX_CG * COARSE_KMAX_CG + 4 * COARSE_KMAX_CG)));
   }
   FX_CUDA(cudaMalloc((void**)&d.agg, sizeof(int) * (size_t)d.n));
   FX_CUDA(cudaMemcpy(d.agg, agg, sizeof(int) * (size_t)d.n, cudaMemcpyHostToDevice));

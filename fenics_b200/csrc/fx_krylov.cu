@@ -393,13 +393,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   // per aggregate and CTA) | e = E^-1 c, one warp per aggregate | prolongation.
   const bool coarse = !DIST && a.cz.agg != nullptr;
   const int ck = a.cz.k;
-  __shared__ double c_sh[DIST ? 1 : COARSE_KMAX];
+  __shared__ double c_sh[DIST ? 1 : COARSE_KMAX_CG];
   const double* Einv = nullptr;
   int cph = 0;
-  double* evec = a.cz.cvec + 3 * COARSE_KMAX;
+  double* evec = a.cz.cvec + 3 * COARSE_KMAX_CG;
   // vout += P E^-1 P^T vin; with dsum != null also dsum[0] += (vin, vout), dsum[1] += (vout, vout) on the final values
   auto coarse_apply = [&](const double* vin, double* vout, double* dsum) {
-    double* cur = a.cz.cvec + (cph % 3) * COARSE_KMAX;
+    double* cur = a.cz.cvec + (cph % 3) * COARSE_KMAX_CG;
     for (int g = threadIdx.x; g < ck; g += blockDim.x) c_sh[g] = 0.0;
     __syncthreads();
     for (int i = gt; i < n; i += gs) atomicAdd(&c_sh[a.cz.agg[i]], vin[i]);
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
       if (v != 0.0) atomicAdd(cur + g, v);
     }
     if (blockIdx.x == 0)  // the buffer of the next application: nobody reads or adds to it now
-      for (int g = threadIdx.x; g < ck; g += blockDim.x) a.cz.cvec[((cph + 1) % 3) * COARSE_KMAX + g] = 0.0;
+      for (int g = threadIdx.x; g < ck; g += blockDim.x) a.cz.cvec[((cph + 1) % 3) * COARSE_KMAX_CG + g] = 0.0;
     bar.sync();
     const int lane = threadIdx.x & 31;
     for (int g = gt >> 5; g < ck; g += gs >> 5) {  // one warp per aggregate (small systems run on a small grid)
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   if constexpr (!DIST) {
     if (coarse) {
       for (int i = gt; i < ck * ck; i += gs) a.cz.E0[i] = 0.0;
-      for (int i = gt; i < 4 * COARSE_KMAX; i += gs) a.cz.cvec[i] = 0.0;
+      for (int i = gt; i < 4 * COARSE_KMAX_CG; i += gs) a.cz.cvec[i] = 0.0;
       bar.sync();
       for (int row = gt; row < n; row += gs) {
         const int ga = a.cz.agg[row];
@@ -1183,7 +1183,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   static const int resident_env = getenv("FX_PCG_RESIDENT") ? atoi(getenv("FX_PCG_RESIDENT")) : 1;
   if (!resident_env) pcfg.R = 0;  // testing aid: send CG solves through k_cg even when the system would fit k_pcg_res
   // jacobi_coarse: the resident kernel when the system fits it (and rtol >= 1e-9: pipelined recurrences), else k_cg
-  const bool coarse_resident = pcfg.R > 0 && p.agg_nl <= pcfg.nlmax && rtol >= 1e-9;
+  const bool coarse_resident = pcfg.R > 0 && p.nagg <= COARSE_KMAX && p.agg_nl <= pcfg.nlmax && rtol >= 1e-9;
   if (pc == FX_PC_JACOBI_COARSE && (method != FX_KSP_CG || p.nagg == 0 || p.nelim != 0))
     return set_error(FX_ERR_UNSUPPORTED, "jacobi_coarse needs CG, aggregates on the space (fx_plan_set_aggregates) and no "
                      "eliminated rows");
@@ -1209,8 +1209,8 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   }
   ka.cz = Coarse{pcfg.slice, pcfg.nlmax, nullptr, 0, nullptr, nullptr, nullptr};
   if (pc == FX_PC_JACOBI_COARSE)
-    ka.cz = Coarse{pcfg.slice, pcfg.nlmax, p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX * COARSE_KMAX,
-                   P->coarse + (size_t)2 * COARSE_KMAX * COARSE_KMAX};
+    ka.cz = Coarse{pcfg.slice, pcfg.nlmax, p.agg, p.nagg, P->coarse, P->coarse + (size_t)COARSE_KMAX_CG * COARSE_KMAX_CG,
+                   P->coarse + (size_t)2 * COARSE_KMAX_CG * COARSE_KMAX_CG};
   static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
   ka.prof = prof_env;
   FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));

@@ -65,7 +65,8 @@ struct DistDev {
 };
 
 constexpr int KRYLOV_NWORK = 12;
-constexpr int COARSE_KMAX = 256;   // aggregates of the two-level preconditioner
+constexpr int COARSE_KMAX = 256;   // aggregates of the two-level preconditioner in the resident kernel (E^-1 rows in shared memory)
+constexpr int COARSE_KMAX_CG = 1024;  // ... inside k_cg (systems beyond the resident kernel: a finer coarse space pays)
 constexpr int COARSE_NLMAX = 64;   // aggregates one CTA of the resident CG kernel may touch
 constexpr int RED_SLOTS = 4;       // values reduced at once
 constexpr int MAX_GRID = 148 * 16; // upper bound on cooperative grid size

@@ -161,13 +161,22 @@ class _LDC:
         v = fn.vector().get_local()
         return fn.function_space().tabulate_dof_coordinates()[np.where(v == v.max())]
 
-    def enable_pressure_coarse(self, k=256):
+    @staticmethod
+    def _coarse_size(ndofs, k=None):
+        """aggregates of the two-level preconditioner: 256 while the space fits the shared-memory-resident CG kernel
+        (<= ~148 k rows), 1024 beyond (the coarse correction then runs inside k_cg, where a finer coarse space pays);
+        always >= 8 dofs per aggregate and a multiple of 32."""
+        if k is None:
+            k = 256 if ndofs <= 150000 else 1024
+        return min(int(k), (ndofs // 8) // 32 * 32)
+
+    def enable_pressure_coarse(self, k=None):
         """Two-level preconditioner (Jacobi + aggregate coarse correction, fx_plan_set_aggregates) for the CG
         pressure solve; aggregates = recursive coordinate bisection of the P1 dof coordinates.  Only for
         non-singular pressure matrices (the compressible loops: the Ma^2/dt mass term).  Returns whether the
         library accepted the aggregates."""
         Q = self.S["Q"]
-        k = min(int(k), (Q.dim() // 8) // 32 * 32)  # >= 8 dofs per aggregate, multiple of 32
+        k = self._coarse_size(Q.dim(), k)
         ok = k >= 32 and self.plan.set_aggregates("Q", rcb_partition(Q.tabulate_dof_coordinates(), k), k)
         self.pressure_pc = "jacobi_coarse" if ok else None
         return bool(ok)

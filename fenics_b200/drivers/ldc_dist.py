@@ -40,13 +40,13 @@ def distributed(base):
             rep = (self.world > 1 and self.ctx.fused) if replicate_q is None else replicate_q
             self.rep_q = dist_la.ReplicatedSolver(self.ctx, mesh, Q, "Q") if rep else None
 
-        def enable_pressure_coarse(self, k=256):
+        def enable_pressure_coarse(self, k=None):
             """two-level preconditioner of the CG pressure solve: available on a partition only through the
             replicated Q solves (aggregates of the GLOBAL P1 space)."""
             if self.rep_q is None:
                 return False
             Q = self.global_spaces["Q"]
-            k = min(int(k), (Q.dim() // 8) // 32 * 32)
+            k = self._coarse_size(Q.dim(), k)
             ok = k >= 32 and self.rep_q.gplan.set_aggregates("Q", rcb_partition(Q.tabulate_dof_coordinates(), k), k)
             self.pressure_pc = "jacobi_coarse" if ok else None
             return bool(ok)

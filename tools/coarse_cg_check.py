@@ -11,12 +11,13 @@ from fenics_b200 import _abi as abi, dolfin_api as dapi, la, mesh as pmesh  # no
 from fenics_b200.drivers import ldc  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 drv = ldc.CompLDC(pmesh.Skew_Mesh(n, 1, 1))
 drv.t = 0.45
 drv.pressure_method = "cg"
 for _ in range(2):
     drv.step()                                   # plain Jacobi here
-print("coarse accepted:", drv.enable_pressure_coarse(256))
+print("coarse accepted:", drv.enable_pressure_coarse(k), "aggregates", drv._coarse_size(drv.S["Q"].dim(), k))
 A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
 b = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_L5))
 ref = spla.splu(A.to_scipy().tocsc()).solve(b.get_local())

@@ -24,7 +24,7 @@ mesh = pmesh.Skew_Mesh(n, 1, 1)
 drv = ldc_dist.DistCompLDC(mesh, device=local, dt=dt) if world > 1 else ldc.CompLDC(mesh, device=local, dt=dt)
 drv.t = 0.45
 drv.pressure_method = "cg"
-coarse = bool(drv.enable_pressure_coarse(256))
+coarse = bool(drv.enable_pressure_coarse())
 for _ in range(3):
     drv.step()
 torch.cuda.synchronize()
