@@ -102,6 +102,20 @@ def tabulate(kind, X):
     raise ValueError(kind)
 
 
+def tabulate_hessian(kind):
+    """constant reference second derivatives d2 phi_b / d xi_a d xi_c, shape (nb,2,2); zero for P1 / DG0.
+    P2 (UFC order): phi_i = l_i (2 l_i - 1), phi_3 = 4 l1 l2, phi_4 = 4 l0 l2, phi_5 = 4 l0 l1 with l0 = 1 - xi - eta."""
+    if kind != "P2":
+        return np.zeros((NB[kind], 2, 2))
+    dl = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])  # grad of l0, l1, l2
+    H = np.zeros((6, 2, 2))
+    for i in range(3):
+        H[i] = 4.0 * np.outer(dl[i], dl[i])
+    for b, (i, j) in zip((3, 4, 5), ((1, 2), (0, 2), (0, 1))):
+        H[b] = 4.0 * (np.outer(dl[i], dl[j]) + np.outer(dl[j], dl[i]))
+    return H
+
+
 # reference coordinates of the nodes (dof points) per element kind
 NODES = {"P1": np.array([[0.0, 0], [1, 0], [0, 1]]),
          "P2": np.array([[0.0, 0], [1, 0], [0, 1], [0.5, 0.5], [0, 0.5], [0.5, 0]]),
@@ -362,6 +376,27 @@ class Ctx:
 
     def coef_grad(self, fn, comps):
         return self._coef(fn, comps)[1]
+
+    def coef_hess(self, fn, comps):
+        """second derivatives of a Function's components, (ne,nq,ncomp,2,2) [.., i, j] = d2 f / dx_i dx_j: constant per
+        cell on affine triangles (K^T H_ref K), zero for P1 / DG0 components.  Needed by forms that differentiate a
+        function of grad(u), e.g. div(phi_def(u0) (...)) of fenepmp_jbp.py:519 with lambda_D != 0."""
+        key = ("h", id(fn), comps)
+        r = self.memo.get(key)
+        if r is None:
+            sp_ = fn.space
+            K = self.mesh.K[self.ents]  # (ne, a, i)
+            ne, nq = self.X.shape[:2]
+            out = []
+            for c in comps:
+                Href = tabulate_hessian(sp_.comps[c])  # (nb, a, c)
+                d = fn.vec[sp_.cell_dofs[self.ents, sp_.offs[c]:sp_.offs[c + 1]]]  # (ne,nb)
+                hc = np.einsum("eb,bac,eai,ecj->eij", d, Href, K, K)
+                out.append(np.broadcast_to(hc[:, None], (ne, nq, 2, 2)))
+            r = np.stack(out, -3)
+            self.memo[key] = r
+            self.keep.append(fn)
+        return r
 
 
 def _slots(space):

@@ -767,6 +767,14 @@ class Grad(Expr):
     def _ev(self, ctx):
         return self.a.gr(ctx)
 
+    def _gr(self, ctx):
+        # second derivatives: only of a Function (view) itself -- what the reference's forms need
+        # (grad of Dincomp(u0) inside div(phi_def(u0) ...), fenepmp_jbp.py:519 with lambda_D != 0)
+        if isinstance(self.a, Coef):
+            h = ctx.coef_hess(self.a.fn, self.a.comps)  # (ne,nq,ncomp,2,2)
+            return h[..., 0, :, :] if self.a.scalar else h
+        raise NotImplementedError("gradient of Grad(%s)" % type(self.a).__name__)
+
     def deg(self):
         return _dred(self.a.deg())
 

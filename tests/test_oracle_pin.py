@@ -178,3 +178,38 @@ def test_weighted_gauge_solve_of_the_singular_pressure_system():
     M = spla.LinearOperator(A.shape, lambda v: v / d)
     xk, info = spla.cg(A, b, x0=x0.copy(), rtol=1e-14, atol=0.0, maxiter=5000, M=M)
     assert info == 0 and np.abs(xk - x).max() < 1e-8 * np.abs(x).max()
+
+
+def test_second_derivatives_of_functions():
+    """oracle support for forms that differentiate a function of grad(u) -- div(phi_def(u0) (f tau0 - I)) of
+    fenepmp_jbp.py:519 with lambda_D != 0: (i) the Hessian of an interpolated quadratic is exact; (ii) the product rule
+    div(s M) = s div(M) + M grad(s) holds for s = phi_def(u); (iii) the lambda_D != 0 forms assemble with the
+    degrees SURVEY.md derived by hand (13, 13, 14)."""
+    from oracle.configs_jbp import FenepmpJBP, phi_def
+    from oracle.ufl_lite import div, dot, dx, grad, inner
+    mesh = fem.skew_mesh(4)
+    V = fem.FunctionSpace(mesh, ["P2", "P2"])
+    u = fem.Function(V)
+    xy, comp = V.tabulate_dof_coordinates(), V.dof_component()
+    x, y = xy[:, 0], xy[:, 1]
+    u.vec[:] = np.where(comp == 0, 1.5 * x * x - 0.5 * x * y + 2 * y * y + x, -x * x + 3 * x * y + 0.25 * y * y - y)
+    Q = fem.FunctionSpace(mesh, ["DG0"])
+    q = fem.TestFunction(Q)
+    area = fem.assemble(inner(1.0, q) * dx)
+    H = grad(grad(u.expr()))
+    for (c, i, j), val in {(0, 0, 0): 3.0, (0, 0, 1): -0.5, (0, 1, 1): 4.0, (1, 0, 0): -2.0, (1, 1, 0): 3.0, (1, 1, 1): 0.5}.items():
+        assert np.abs(fem.assemble(inner(H[c, i, j], q) * dx) / area - val).max() < 1e-11
+    Z = fem.FunctionSpace(mesh, ["P2"] * 3)
+    t = fem.Function(Z)
+    t.vec[:] = np.random.default_rng(0).standard_normal(Z.dim)
+    from oracle.configs import sym
+    M = sym(t.expr())
+    s = phi_def(u.expr(), 0.3)
+    v = fem.TestFunction(V)
+    lhs_ = fem.assemble(inner(div(s * M), v) * dx)
+    rhs_ = fem.assemble(inner(s * div(M) + dot(M, grad(s)), v) * dx)
+    assert np.abs(lhs_ - rhs_).max() < 1e-12 * np.abs(rhs_).max()
+    assert np.abs(fem.assemble(inner(dot(M, grad(s)), v) * dx)).max() > 1e-3 * np.abs(rhs_).max()  # the new term carries weight
+    cfg = FenepmpJBP(fem.annulus_mesh(8, 2), lambda_d=0.1)
+    degs = {n: max(d for _, _, d in fem.quadrature_degrees(cfg.forms[n], cfg.mesh)) for n in ("L2", "a4", "L9")}
+    assert degs == {"L2": 13, "a4": 13, "L9": 14}
