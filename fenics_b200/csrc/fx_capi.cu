@@ -167,7 +167,9 @@ void fx_plan_destroy(fx_plan* P) {
     cudaFree(P->sp[s].rowptr); cudaFree(P->sp[s].col); cudaFree(P->sp[s].pos); cudaFree(P->sp[s].dm_t); cudaFree(P->sp[s].rowblk);
     cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows); cudaFree(P->sp[s].agg);
     cudaFree(P->sp[s].s_first); cudaFree(P->sp[s].s_peer); cudaFree(P->sp[s].s_local); cudaFree(P->sp[s].s_remote);
+    P->sp[s].nb.release();
   }
+  cudaFree(P->nbval);
   cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->rowpre); cudaFree(P->nblk); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->gmres_basis); cudaFree(P->red_big);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
@@ -319,6 +321,7 @@ int fx_plan_set_owned_cells(fx_plan* P, int nc_owned) {
 
 // device row mask of a space = eliminated rows (bit 0) | ghost rows (bit 1) | interface rows (bit 2)
 static int rebuild_mask(DevPattern& d) {
+  d.nb.release();  // the node-block layout depends on the masks: rebuilt at the next solve
   cudaFree(d.elim);
   d.elim = nullptr;
   if (d.elim_h.empty() && d.halo_h.empty()) return FX_OK;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fx_la_common.cuh"
+#include "fx_nb.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -57,6 +58,7 @@ struct KArgs {
   double rtol, atol, dtol;
   int maxit, pc;
   fx_solve_info* info;
+  NbView nb;        // node-block solver layout of the space (k_bicgstab_nb)
   double* basis;    // GMRES: (GMRES_M + 1) x n Krylov basis
   double* red_big;  // GMRES: 2 x GMRES_NRED x MAX_GRID block partials of the Gram-Schmidt coefficients
 };
@@ -349,6 +351,177 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
     rho = rho_new;
   }
   leave(bar, a, a.maxit, 0, rn, bn);
+}
+
+// ---- BiCGStab on the node-block layout (fx_nb_host.h / fx_nb.cuh) ------------------------------------------------
+// Same recurrence, reductions and exits as k_bicgstab; what differs is the data layout: the work vectors live in the
+// internal node-major numbering (length N = nodes x bp), the matrix is the gathered block copy (one column index per
+// bs x bs node block, one aligned x-gather per block), and the set-up is a plain value gather -- no compaction scans.
+// x is permuted in at the start and out at every exit; eliminated rows (W's DG0 DEVSS rows) never enter the internal
+// vectors and are recovered by leave()'s back-substitution on the external arrays.
+template <int BS>
+__global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_constant__ KArgs a) {
+  __shared__ double sh[4 * 33];
+  extern __shared__ __align__(16) double prod_all[];
+  const NbView& B = a.nb;
+  const int N = B.N;
+  const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  double* r = a.w;
+  double* rh = a.w + ld;
+  double* p = a.w + 2 * ld;
+  double* v = a.w + 3 * ld;
+  double* s = a.w + 4 * ld;
+  double* t = a.w + 5 * ld;
+  double* dinv = a.w + 6 * ld;
+  double* xi = a.w + 7 * ld;
+  double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
+  const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
+  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  int phase = 0;
+  GridBar bar;
+  bar.init(a.bar);
+  auto out = [&](int it, int conv, double rn, double bn) {  // every exit: x back to the external numbering
+    for (int i = gt; i < N; i += gs) {
+      const int e = B.ext_of_int[i];
+      if (e >= 0) a.x[e] = xi[i];
+    }
+    leave(bar, a, it, conv, rn, bn);
+  };
+  double acc[3] = {0.0, 0.0, 0.0};
+  acc[2] = (double)nb_gather_values(B, a.A.val);
+  for (int i = gt; i < N; i += gs) {
+    const int e = B.ext_of_int[i];
+    xi[i] = e >= 0 ? a.x[e] : 0.0;
+  }
+  bar.sync();
+  spmv_nb<BS>(B, k0, k1, xi, prod,
+              [&](int i) {
+                const int e = B.ext_of_int[i];
+                return Ops2{nb_diag_inv<BS>(B, i, a.pc), e >= 0 ? a.b[e] : 0.0};
+              },
+              [&](int i, double ax, const Ops2& o) {
+                const double ri = o.a * (o.b - ax), bi = o.a * o.b;
+                dinv[i] = o.a; r[i] = ri; rh[i] = ri; v[i] = 0.0; p[i] = ri;
+                acc[0] += ri * ri; acc[1] += bi * bi;
+              });
+  gsum<3>(a, bar, acc, phase, sh);
+  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
+  double rn = sqrt(acc[0]);
+  const double bn = sqrt(acc[1]);
+  const double tol = fmax(a.rtol * bn, a.atol);
+  if (!(rn == rn)) { out(0, -1, rn, bn); return; }
+  if (rn <= tol) { out(0, 1, rn, bn); return; }
+  double rho = acc[0];
+  double rhn = rn;
+  int restarts = 0;
+  int np = 0;
+  stamp(a.prof, np);
+  for (int it = 1; it <= a.maxit; ++it) {
+    double d1[1] = {0.0};
+    spmv_nb<BS>(B, k0, k1, p, prod, [&](int i) { return Ops2{dinv[i], rh[i]}; },
+                [&](int i, double ap, const Ops2& o) {
+                  const double vi = o.a * ap;
+                  v[i] = vi;
+                  d1[0] += o.b * vi;
+                });
+    stamp(a.prof, np);
+    gsum<1, false>(a, bar, d1, phase, sh);
+    stamp(a.prof, np);
+    if (d1[0] == 0.0) { out(it - 1, -1, rn, bn); return; }
+    const double alpha = rho / d1[0];
+    double d2[1] = {0.0};
+    for (int i = gt; i < N; i += gs) {
+      const double si = r[i] - alpha * v[i];
+      s[i] = si;
+      d2[0] += si * si;
+    }
+    stamp(a.prof, np);
+    gsum<1, false>(a, bar, d2, phase, sh);
+    stamp(a.prof, np);
+    const double ss = d2[0];
+    if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
+      for (int i = gt; i < N; i += gs) xi[i] += alpha * p[i];
+      out(it, 1, sqrt(ss), bn);
+      return;
+    }
+    double d3[4] = {0.0, 0.0, 0.0, 0.0};
+    spmv_nb<BS>(B, k0, k1, s, prod, [&](int i) { return Ops3{dinv[i], s[i], rh[i]}; },
+                [&](int i, double as, const Ops3& o) {
+                  const double ti = o.a * as;
+                  t[i] = ti;
+                  d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
+                });
+    stamp(a.prof, np);
+    gsum<4, false>(a, bar, d3, phase, sh);
+    stamp(a.prof, np);
+    if (d3[1] == 0.0) { out(it, -1, sqrt(ss), bn); return; }
+    const double omega = d3[0] / d3[1];
+    double rho_new = d3[2] - omega * d3[3];
+    const double rn2 = ss - 2.0 * omega * d3[0] + omega * omega * d3[1];  // ||s - omega t||^2
+    rn = sqrt(fmax(rn2, 0.0));
+    if (!(rn2 == rn2) || rn > a.dtol * bn) { out(it, -1, rn, bn); return; }
+    const bool restart = fabs(rho_new) <= 1e-14 * rhn * rn || omega == 0.0;
+    if (restart && ++restarts > 50) { out(it, -1, rn, bn); return; }
+    const double beta = restart ? 0.0 : (rho_new / rho) * (alpha / omega);
+    const bool check = rn <= 2.0 * tol;  // confirm with a true norm
+    double d4[1] = {0.0};
+    for (int i = gt; i < N; i += gs) {
+      const double pi = p[i], si = s[i];
+      xi[i] += alpha * pi + omega * si;
+      const double ri = si - omega * t[i];
+      r[i] = ri;
+      p[i] = ri + beta * (pi - omega * v[i]);
+      if (restart) rh[i] = ri;
+      d4[0] += ri * ri;
+    }
+    stamp(a.prof, np);
+    if (check || restart) {
+      gsum<1, false>(a, bar, d4, phase, sh);
+      rn = sqrt(d4[0]);
+      if (rn <= tol) { out(it, 1, rn, bn); return; }
+      if (restart) { rho_new = d4[0]; rhn = rn; }
+    } else {
+      bar.sync();
+    }
+    stamp(a.prof, np);
+    rho = rho_new;
+  }
+  out(a.maxit, 0, rn, bn);
+}
+
+// y = A x through the node-block layout, stand-alone (tests and tools/spmv_bench.py): gathers the values, permutes x in,
+// runs `reps` products (a grid barrier between them, as inside a solve) and writes the rows of the node blocks to y
+template <int BS>
+__global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_constant__ KArgs a, int reps) {
+  extern __shared__ __align__(16) double prod_all[];
+  const NbView& B = a.nb;
+  const int N = B.N;
+  const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  double* xi = a.w;
+  double* yi = a.w + ld;
+  double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
+  const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
+  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  GridBar bar;
+  bar.init(a.bar);
+  const int bad = nb_gather_values(B, a.A.val);
+  if (bad) a.info->converged = -3;
+  for (int i = gt; i < N; i += gs) {
+    const int e = B.ext_of_int[i];
+    xi[i] = e >= 0 ? a.b[e] : 0.0;
+  }
+  bar.sync();
+  for (int rep = 0; rep < reps; ++rep) {
+    spmv_nb<BS>(B, k0, k1, xi, prod, [&](int i) { return Ops2{0.0, 0.0}; },
+                [&](int i, double ax, const Ops2&) { yi[i] = ax; });
+    bar.sync();
+  }
+  for (int i = gt; i < N; i += gs) {
+    const int e = B.ext_of_int[i];
+    if (e >= 0) a.x[e] = yi[i];
+  }
 }
 
 __device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k, GridBar& bar, double* scratch);
@@ -1171,9 +1344,107 @@ PcgConfig pcg_resident_config(const fx_plan* P, int nrowblk, int maxblknnz) {
   return c;
 }
 
+// Build (once) and upload the node-block layout of a space.  Spaces without a usable structure keep state -1 and the
+// reason; CUDA failures are the only errors.
+int nb_ensure(fx_plan* P, int space) {
+  DevPattern& d = P->sp[space];
+  DevPattern::NbDev& nb = d.nb;
+  if (nb.state != 0) return FX_OK;
+  int bs = 0, nloc = 0;
+  if (!d.has_csr || !nb_space_layout(space, bs, nloc)) { nb.state = -1; nb.why = "space has no node-block layout"; return FX_OK; }
+  const int nc = P->nc;
+  std::vector<int> rowptr((size_t)d.n + 1), col((size_t)d.nnz), dm((size_t)d.ld * nc);
+  FX_CUDA(cudaMemcpy(rowptr.data(), d.rowptr, sizeof(int) * rowptr.size(), cudaMemcpyDeviceToHost));
+  FX_CUDA(cudaMemcpy(col.data(), d.col, sizeof(int) * col.size(), cudaMemcpyDeviceToHost));
+  FX_CUDA(cudaMemcpy(dm.data(), d.dm_t, sizeof(int) * dm.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> mask;
+  if (!d.elim_h.empty() || !d.halo_h.empty()) {
+    mask.assign((size_t)d.n, 0);
+    for (int i = 0; i < d.n; ++i) mask[i] = (d.elim_h.empty() ? 0 : d.elim_h[i]) | (d.halo_h.empty() ? 0 : d.halo_h[i]);
+  }
+  NbHost H;
+  std::string why;
+  if (!nb_build(dm.data(), nc, d.ld, bs, nloc, d.n, rowptr.data(), col.data(), mask.empty() ? nullptr : mask.data(),
+                P->num_sms, H, why)) {
+    nb.state = -1; nb.why = why;
+    return FX_OK;
+  }
+  auto up = [](auto** dst, const auto& v) -> cudaError_t {
+    *dst = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, v.size() * sizeof(v[0]));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
+  };
+  int* desc_i = nullptr;
+  FX_CUDA(up(&desc_i, H.desc));
+  nb.desc = reinterpret_cast<int4*>(desc_i);
+  FX_CUDA(up(&nb.wrange, H.wrange));
+  FX_CUDA(up(&nb.bre, H.bre));
+  FX_CUDA(up(&nb.bcol, H.bcol));
+  FX_CUDA(up(&nb.src, H.src));
+  FX_CUDA(up(&nb.diag, H.diag));
+  FX_CUDA(up(&nb.ext_of_int, H.ext_of_int));
+  FX_CUDA(up(&nb.int_of_ext, H.int_of_ext));
+  FX_CUDA(up(&nb.zchk, H.zchk));
+  FX_CUDA(up(&nb.imask, H.imask));
+  nb.bs = H.bs; nb.bp = H.bp; nb.nn = H.nn; nb.N = H.N; nb.nchunks = H.nchunks; nb.grid = H.grid;
+  nb.nzchk = (int)H.zchk.size(); nb.ne = H.ne; nb.nslots = H.nslots;
+  if (P->nbval_cap < (size_t)H.nslots) {
+    cudaFree(P->nbval);
+    P->nbval = nullptr; P->nbval_cap = 0;
+    FX_CUDA(cudaMalloc((void**)&P->nbval, sizeof(double) * (size_t)H.nslots));
+    P->nbval_cap = (size_t)H.nslots;
+  }
+  nb.state = 1;
+  return FX_OK;
+}
+
+static NbView nb_view(const fx_plan* P, const DevPattern& d) {
+  const DevPattern::NbDev& nb = d.nb;
+  return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
+                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval};
+}
+
+template <int BS>
+static int launch_nb(void* fn, const DevPattern& d, KArgs& ka, int reps, cudaStream_t st) {
+  const size_t smem = sizeof(double) * NB_WARPS * nb_chunk(BS) * BS;
+  static bool attr[2] = {false, false};
+  const int ai = reps >= 0 ? 1 : 0;
+  if (!attr[ai]) {
+    FX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[ai] = true;
+  }
+  void* args1[] = {(void*)&ka};
+  void* args2[] = {(void*)&ka, (void*)&reps};
+  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(d.nb.grid), dim3(NB_WARPS * 32), reps >= 0 ? args2 : args1, smem, st));
+  count_launch(1);
+  return FX_OK;
+}
+
+// y = A x on the rows of the node blocks, through the node-block layout (variant 8 of fx_spmv_variant; reps products)
+int la_spmv_nb(fx_plan* P, int space, const double* val, const double* x, double* y, int reps, cudaStream_t st) {
+  DevPattern& p = P->sp[space];
+  int rc = nb_ensure(P, space);
+  if (rc) return rc;
+  if (p.nb.state != 1) return set_error(FX_ERR_UNSUPPORTED, "space %d: no node-block layout (%s)", space, p.nb.why.c_str());
+  if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
+  KArgs ka{};
+  ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, p.elim, p.elim_rows,
+                 p.nelim, nullptr, nullptr, 0, nullptr, nullptr};
+  ka.nb = nb_view(P, p);
+  ka.bar = P->bar; ka.w = P->work; ka.x = y; ka.b = x; ka.info = P->info + (FX_NTICKETS - 1);
+  FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
+  switch (p.nb.bs) {
+    case 1: return launch_nb<1>((void*)k_nb_spmv<1>, p, ka, reps, st);
+    case 2: return launch_nb<2>((void*)k_nb_spmv<2>, p, ka, reps, st);
+    default: return launch_nb<3>((void*)k_nb_spmv<3>, p, ka, reps, st);
+  }
+}
+
 int la_krylov(fx_plan* P, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st) {
-  const DevPattern& p = P->sp[space];
+  DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
   if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB && method != FX_KSP_GMRES)
     return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg, gmres available)", method);
@@ -1257,6 +1528,21 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
       case 2: return launch_pcg_res<2>(P, ka, pcfg.grid, st);
       case 3: return launch_pcg_res<3>(P, ka, pcfg.grid, st);
       default: return launch_pcg_res<4>(P, ka, pcfg.grid, st);
+    }
+  }
+  // BiCGStab on the node-block layout when the space has one (FX_NB=0: the scalar compacted-CSR kernel below)
+  static const int nb_env = getenv("FX_NB") ? atoi(getenv("FX_NB")) : 1;
+  if (nb_env && method == FX_KSP_BICGSTAB && !part) {
+    if ((rc = nb_ensure(P, space))) return rc;
+    if (p.nb.state == 1) {
+      if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
+      ka.w = P->work;
+      ka.nb = nb_view(P, p);
+      switch (p.nb.bs) {
+        case 1: return launch_nb<1>((void*)k_bicgstab_nb<1>, p, ka, -1, st);
+        case 2: return launch_nb<2>((void*)k_bicgstab_nb<2>, p, ka, -1, st);
+        default: return launch_nb<3>((void*)k_bicgstab_nb<3>, p, ka, -1, st);
+      }
     }
   }
   // big CTAs (1024 threads, one per SM) keep the grid barrier cheap: its cost grows with the number of

@@ -152,6 +152,8 @@ int la_spmv_variant(fx_plan* P, int space, const double* val, const double* x, d
                     cudaStream_t st) {
   const DevPattern& p = P->sp[space];
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
+  if ((variant & 0xff) == 8)  // node-block layout; bits 8.. = number of products (default 1)
+    return la_spmv_nb(P, space, val, x, y, std::max(1, variant >> 8), st);
   CsrView A{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr};
   const int nb = P->num_sms * 8;
   switch (variant) {

@@ -1,0 +1,145 @@
+// Device side of the node-block solver layout (fx_nb_host.h): value gather and the block CSR-stream SpMV.
+#pragma once
+#include "fx_la_common.cuh"
+#include "fx_nb_host.h"
+
+namespace fx {
+
+struct NbView {
+  int nn, N, nchunks, nzchk;
+  long long ne, nslots;
+  const int4* desc;
+  const int* wrange;
+  const int* bre;
+  const int* bcol;
+  const int* src;
+  const int* diag;
+  const int* ext_of_int;
+  const int* zchk;
+  const unsigned char* imask;
+  double* bval;  // [nslots] gathered per solve
+};
+
+template <int BS>
+__device__ __forceinline__ long long nb_pos_d(int e, int f) {
+  constexpr int B2 = BS * BS, NP2 = B2 / 2;
+  const long long g = e >> 5;
+  const int l = e & 31;
+  return g * 32 * B2 + (f < 2 * NP2 ? (f >> 1) * 64 + 2 * l + (f & 1) : NP2 * 64 + l);
+}
+
+// bval[k] = val[src[k]] for the whole grid (coalesced index reads and value writes, the DOLFIN CSR values are
+// gathered); returns this thread's count of non-zero couplings A[active, eliminated] (must total 0)
+__device__ __forceinline__ int nb_gather_values(const NbView& B, const double* __restrict__ val) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
+  for (long long k = gt; k < B.nslots; k += gs) {
+    const int s = ld_stream(B.src + k);
+    B.bval[k] = s >= 0 ? __ldg(val + s) : 0.0;
+  }
+  int bad = 0;
+  for (long long k = gt; k < B.nzchk; k += gs) bad += (__ldg(val + ld_stream(B.zchk + k)) != 0.0);
+  return bad;
+}
+
+// 1 / diagonal of internal row i (Jacobi); rows of empty block rows and padding slots: 0
+template <int BS>
+__device__ __forceinline__ double nb_diag_inv(const NbView& B, int i, int pc) {
+  constexpr int BP = nb_bp(BS);
+  const int node = i / BP, c = i - node * BP;
+  if (c >= BS) return 0.0;
+  const int e = B.diag[node];
+  if (e < 0) return 0.0;
+  if (pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE) return 1.0;
+  const double dg = B.bval[nb_pos_d<BS>(e, c * BS + c)];
+  return dg != 0.0 ? 1.0 / dg : 1.0;
+}
+
+// Block CSR-stream SpMV over the chunks [k0, k1) of this warp.
+//   stream phase: lane <-> block entry: bs^2 values (coalesced double2 planes, L1-bypassing), one block column, ONE
+//                 aligned gather of the bs components of x, bs partial sums to the warp's shared-memory slice;
+//   reduce phase: lane <-> (block row, component) = internal row index: sums its slice entries and runs the fused
+//                 epilogue post(i, (A x)_i, pre(i)); pre(i) is issued before the stream so its loads overlap it.
+// Padding components (bs = 3 -> 4) run the epilogue with (A x)_i = 0 so every work vector stays zero there.
+// smem: this warp's slice, nb_chunk(BS) * BS doubles.
+template <int BS>
+struct NbU { static constexpr int v = BS == 1 ? 8 : BS == 2 ? 2 : 1; };  // groups of 32 entries in flight per pass
+
+template <int BS, class Pre, class Post>
+__device__ __forceinline__ void spmv_nb(const NbView& B, int k0, int k1, const double* x, double* prod, Pre&& pre,
+                                        Post&& post) {
+  constexpr int BP = nb_bp(BS), B2 = BS * BS, NP2 = B2 / 2, U = NbU<BS>::v;
+  const int lane = threadIdx.x & 31;
+  const int rl = lane / BP, cl = lane - rl * BP;
+  int4 d = (k0 < k1) ? __ldcg(B.desc + k0) : make_int4(0, 0, 0, 0);
+  for (int k = k0; k < k1; ++k) {
+    const int4 dn = (k + 1 < k1) ? __ldcg(B.desc + k + 1) : make_int4(0, 0, 0, 0);
+    const int r0 = d.x, nr = d.y, e0 = d.z, e1 = d.w;
+    const bool act = rl < nr;
+    const int irow = (r0 + rl) * BP + cl;
+    const int myend = act ? __ldcg(B.bre + r0 + rl) : e0;
+    decltype(pre(0)) ops{};
+    if (act) ops = pre(irow);
+    for (int eb = e0; eb < e1; eb += 32 * U) {
+      double v[U][B2];
+      int c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = eb + u * 32 + lane;
+        c[u] = -1;
+        if (e < e1) {
+          c[u] = ld_stream(B.bcol + e);
+          const double* base = B.bval + (long long)(e >> 5) * (32 * B2) + 2 * (e & 31);
+#pragma unroll
+          for (int q = 0; q < NP2; ++q) {
+            double2 t;
+            asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(base + q * 64));
+            v[u][2 * q] = t.x; v[u][2 * q + 1] = t.y;
+          }
+          if (B2 & 1) v[u][B2 - 1] = ld_stream(B.bval + (long long)(e >> 5) * (32 * B2) + NP2 * 64 + (e & 31));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (c[u] < 0) continue;
+        double xv[BP];
+        if (BS == 1) {
+          xv[0] = x[c[u]];
+        } else {
+#pragma unroll
+          for (int h = 0; h < BP / 2; ++h) {
+            const double2 t = *reinterpret_cast<const double2*>(x + (long long)c[u] * BP + 2 * h);
+            xv[2 * h] = t.x; xv[2 * h + 1] = t.y;
+          }
+        }
+        double* dst = prod + (eb - e0 + u * 32 + lane) * BS;
+        double y[BS];
+#pragma unroll
+        for (int ci = 0; ci < BS; ++ci) {
+          y[ci] = 0.0;
+#pragma unroll
+          for (int cj = 0; cj < BS; ++cj) y[ci] += v[u][ci * BS + cj] * xv[cj];
+        }
+        if (BS == 2) {
+          *reinterpret_cast<double2*>(dst) = make_double2(y[0], y[BS - 1]);
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < BS; ++ci) dst[ci] = y[ci];
+        }
+      }
+    }
+    __syncwarp();
+    const int s1 = myend - e0;
+    int s0 = __shfl_up_sync(0xffffffffu, s1, BP);
+    if (rl == 0) s0 = 0;
+    if (act) {
+      double s = 0.0;
+      if (cl < BS)
+        for (int j = s0; j < s1; ++j) s += prod[j * BS + cl];
+      post(irow, s, ops);
+    }
+    __syncwarp();
+    d = dn;
+  }
+}
+
+}  // namespace fx

@@ -48,6 +48,22 @@ struct DevPattern {
   bool has_halo = false;
   int nsend = 0;
   int *s_first = nullptr, *s_peer = nullptr, *s_local = nullptr, *s_remote = nullptr;
+  // node-block solver layout (fx_nb_host.h), built lazily at the first solve that can use it and dropped whenever
+  // the row masks change; state 0 = not built yet, 1 = ready, -1 = the space has no usable node-block structure
+  struct NbDev {
+    int state = 0, bs = 0, bp = 0, nn = 0, N = 0, nchunks = 0, grid = 0, nzchk = 0;
+    long long ne = 0, nslots = 0;
+    std::string why;
+    int4* desc = nullptr;
+    int *wrange = nullptr, *bre = nullptr, *bcol = nullptr, *src = nullptr, *diag = nullptr, *ext_of_int = nullptr,
+        *int_of_ext = nullptr, *zchk = nullptr;
+    uint8_t* imask = nullptr;
+    void release() {
+      cudaFree(desc); cudaFree(wrange); cudaFree(bre); cudaFree(bcol); cudaFree(src); cudaFree(diag);
+      cudaFree(ext_of_int); cudaFree(int_of_ext); cudaFree(zchk); cudaFree(imask);
+      *this = NbDev();
+    }
+  } nb;
 };
 
 // peer-mapped regions of a partitioned run, as the Krylov kernels see them (layout: fx_la_common.cuh)
@@ -114,6 +130,8 @@ struct fx_plan {
   double* gmres_basis = nullptr;                // GMRES Krylov basis, (restart + 1) x n, allocated on first use
   size_t gmres_cap = 0;
   double* red_big = nullptr;                    // GMRES: block partials of the Gram-Schmidt coefficients
+  double* nbval = nullptr;                      // node-block value buffer (gathered inside every solve), nbval_cap doubles
+  size_t nbval_cap = 0;
   fx::DistDev dist;                             // world > 1: mesh-partitioned run (fx_plan_set_peer_regions)
 
   fx::MeshView view() const {
@@ -147,6 +165,8 @@ int la_lincomb3(int n, double* out, const double* coef, const double* x, const d
 int la_dotw(fx_plan* plan, int n, const double* x, const double* y, const double* w, double* out_dev, cudaStream_t st);
 struct PcgConfig { int R, slice, grid, nlmax; };  // R == 0: the system does not fit the resident CG kernel
 PcgConfig pcg_resident_config(const fx_plan* plan, int nrowblk, int maxblknnz);
+int la_spmv_nb(fx_plan* plan, int space, const double* val, const double* x, double* y, int reps, cudaStream_t st);
+int nb_ensure(fx_plan* plan, int space);  // builds the node-block layout of a space if possible; FX_OK either way unless CUDA fails
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
 }  // namespace fx

@@ -11,6 +11,7 @@
 #include "../../include/fenics_b200.h"
 #include "../../fenics_b200/csrc/fx_plan_host.h"
 #include "../../fenics_b200/csrc/fx_registry.h"
+#include "../../fenics_b200/csrc/fx_nb_host.h"
 
 using namespace fx;
 
@@ -193,6 +194,67 @@ int emu_form_qdeg(int form, int* qdx, int* qds, double conv) {
 #undef X
   }
   return FX_ERR_ARG;
+}
+
+// Node-block solver layout (fx_nb_host.h): builds it for a space and replays the device SpMV (fx_nb.cuh: chunk ->
+// stream phase over lanes/groups -> per-(row, component) reduce) on the host, with the same bounds the kernel relies
+// on asserted.  y gets (A x) on the rows inside node blocks; other entries are left alone.  Returns 0, or -1 when
+// the space has no usable node-block structure (why is printed), or > 0 = number of violated kernel invariants.
+int emu_nb_spmv(void* p, int space, const unsigned char* mask, int num_sms, const double* val, const double* x,
+                double* y, int* info /* [8]: bs, nn, N, ne, nchunks, grid, nzchk, bad zero-checks */) {
+  EmuPlan* P = (EmuPlan*)p;
+  const HostPattern& pat = P->pat[space];
+  int bs = 0, nloc = 0;
+  if (!nb_space_layout(space, bs, nloc)) return -1;
+  NbHost H;
+  std::string why;
+  if (!nb_build(pat.dm_t.data(), P->nc, pat.ld, bs, nloc, pat.n, pat.rowptr.data(), pat.col.data(), mask, num_sms, H, why)) {
+    std::fprintf(stderr, "emu_nb_spmv: %s\n", why.c_str());
+    return -1;
+  }
+  const int bp = H.bp, b2 = bs * bs, CH = nb_chunk(bs), RM = nb_rows(bs);
+  int viol = 0, bad = 0;
+  std::vector<double> bval((size_t)H.nslots);
+  for (long long k = 0; k < H.nslots; ++k) bval[k] = H.src[k] >= 0 ? val[H.src[k]] : 0.0;
+  for (int j : H.zchk) bad += (val[j] != 0.0);
+  std::vector<double> xi((size_t)H.N, 0.0), yi((size_t)H.N, 0.0), prod((size_t)CH * bs);
+  for (int i = 0; i < H.N; ++i) xi[i] = H.ext_of_int[i] >= 0 ? x[H.ext_of_int[i]] : 0.0;
+  const int nw = H.grid * NB_WARPS;
+  std::vector<char> row_done(H.nn, 0);
+  for (int w = 0; w < nw; ++w)
+    for (int k = H.wrange[w]; k < H.wrange[w + 1]; ++k) {
+      const int r0 = H.desc[4 * k], nr = H.desc[4 * k + 1], e0 = H.desc[4 * k + 2], e1 = H.desc[4 * k + 3];
+      if (nr < 1 || nr > RM || e1 - e0 > CH || e1 < e0) ++viol;
+      for (int e = e0; e < e1; ++e) {  // stream phase (lane = (e - e0) % 32)
+        const int c = H.bcol[e];
+        for (int ci = 0; ci < bs; ++ci) {
+          double sacc = 0.0;
+          for (int cj = 0; cj < bs; ++cj) sacc += bval[(size_t)nb_pos(e, ci * bs + cj, bs)] * xi[(size_t)c * bp + cj];
+          prod[(size_t)(e - e0) * bs + ci] = sacc;
+        }
+      }
+      for (int lane = 0; lane < 32; ++lane) {  // reduce phase
+        const int rl = lane / bp, cl = lane % bp;
+        if (rl >= nr) continue;
+        const int s1 = H.bre[r0 + rl] - e0, s0 = rl == 0 ? 0 : H.bre[r0 + rl - 1] - e0;
+        if (s0 < 0 || s1 < s0 || s1 > e1 - e0) ++viol;
+        double sacc = 0.0;
+        if (cl < bs)
+          for (int j = s0; j < s1; ++j) sacc += prod[(size_t)j * bs + cl];
+        yi[(size_t)(r0 + rl) * bp + cl] = sacc;
+        if (cl == 0) { if (row_done[r0 + rl]) ++viol; row_done[r0 + rl] = 1; }
+      }
+    }
+  for (int i = 0; i < H.nn; ++i) viol += !row_done[i];
+  if (H.wrange[nw] != H.nchunks) ++viol;
+  for (int i = 0; i < H.N; ++i)
+    if (H.ext_of_int[i] >= 0) y[H.ext_of_int[i]] = yi[i];
+  // the diagonal block entries
+  for (int i = 0; i < H.nn; ++i)
+    if (H.diag[i] >= 0 && H.bcol[H.diag[i]] != i) ++viol;
+  info[0] = bs; info[1] = H.nn; info[2] = H.N; info[3] = (int)H.ne; info[4] = H.nchunks; info[5] = H.grid;
+  info[6] = (int)H.zchk.size(); info[7] = bad;
+  return viol;
 }
 
 }  // extern "C"
