@@ -148,7 +148,7 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
   P->part_cap = std::max((nc + 255) / 256, 148 * 8);
   if (cudaMalloc((void**)&P->part, sizeof(double) * P->part_cap) != cudaSuccess ||
       cudaMalloc((void**)&P->scal, sizeof(double) * 64) != cudaSuccess ||
-      cudaMalloc((void**)&P->red, sizeof(double) * (2 * RED_SLOTS * MAX_GRID + 3 * RED_SLOTS)) != cudaSuccess ||
+      cudaMalloc((void**)&P->red, sizeof(double) * (2 * RED_SLOTS * MAX_GRID + 3 * RED_SLOTS + 64)) != cudaSuccess ||
       cudaMalloc((void**)&P->info, sizeof(fx_solve_info) * FX_NTICKETS) != cudaSuccess)
     return fail(set_error(FX_ERR_CUDA, "cudaMalloc scratch failed"));
   cudaMemset(P->info, 0, sizeof(fx_solve_info) * FX_NTICKETS);

@@ -120,6 +120,47 @@ __device__ __forceinline__ void grid_sum_atomic(Bar& bar, double (&v)[NV], doubl
   ++phase;
 }
 
+// Single-GPU variant with the block reduction folded into the barrier: warp sums -> shared memory -> (the barrier's
+// first __syncthreads) -> warp 0 finishes the NV sums, adds them to the rotating accumulator and arrives.  Two CTA
+// barriers per grid sum instead of five.  sh: NV x 32 doubles.
+constexpr int FAST_SLOTS = 8;
+template <int NV>
+__device__ __forceinline__ void grid_sum_fast(GridBar& bar, double (&v)[NV], double* red, int& phase, double* sh) {
+  static_assert(NV <= FAST_SLOTS, "too many values");
+  double* acc = red + (size_t)2 * RED_SLOTS * MAX_GRID + 3 * RED_SLOTS;  // [3][FAST_SLOTS]
+  double* cur = acc + (phase % 3) * FAST_SLOTS;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i * 32 + w] = v[i];
+  }
+  bar.target += gridDim.x;
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = lane < nw ? sh[i * 32 + lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(cur + i, t);
+    }
+    if (blockIdx.x == 0 && lane < FAST_SLOTS) acc[((phase + 1) % 3) * FAST_SLOTS + lane] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(bar.ctr, 1u);
+      bar.wait_local();
+      unsigned t;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(t) : "l"(bar.ctr) : "memory");
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldcg(cur + i);
+  ++phase;
+}
+
 // PUSHED = false: no thread stored halo values to a peer since the previous barrier
 template <int NV, bool PUSHED = true, class Bar>
 __device__ __forceinline__ void gsum(const KArgs& a, Bar& bar, double (&v)[NV], int& phase, double* sh) {
@@ -176,6 +217,7 @@ __device__ __forceinline__ double row_diag_inv(const CsrView& A, int row, int pc
 
 struct Ops2 { double a, b; };
 struct Ops3 { double a, b, c; };
+struct Ops4 { double a, b, c, d; };
 
 // ---- BiCGStab -------------------------------------------------------------------------------------------
 // The recurrence runs on M^-1 A; the monitored norm is ||M^-1 r||_2 and the test is
@@ -359,14 +401,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
 // bs x bs node block, one aligned x-gather per block), and the set-up is a plain value gather -- no compaction scans.
 // x is permuted in at the start and out at every exit; eliminated rows (W's DG0 DEVSS rows) never enter the internal
 // vectors and are recovered by leave()'s back-substitution on the external arrays.
-template <int BS>
+template <int BS, bool DUAL>
 __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_constant__ KArgs a) {
-  __shared__ double sh[4 * 33];
+  constexpr int BP = nb_bp(BS);
+  __shared__ double sh[5 * 32];
   extern __shared__ __align__(16) double prod_all[];
   const NbView& B = a.nb;
   const int N = B.N;
   const size_t ld = ((size_t)N + 3) & ~(size_t)3;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
   double* r = a.w;
   double* rh = a.w + ld;
   double* p = a.w + 2 * ld;
@@ -378,11 +422,19 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
   const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
   const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  // the warp OWNS the internal rows of its chunks (a contiguous range): it computes them in the SpMV epilogues and
+  // updates them in the vector passes, so a pass is one batch of coalesced loads per lane -- no grid-stride loop
+  int i0 = 0, i1 = 0;
+  if (k0 < k1) {
+    const int4 da = B.desc[k0], db = B.desc[k1 - 1];
+    i0 = da.x * BP; i1 = (db.x + db.y) * BP;
+  }
+  const unsigned long long pol = nb_make_policy(B.l2policy);
   int phase = 0;
   GridBar bar;
   bar.init(a.bar);
   auto out = [&](int it, int conv, double rn, double bn) {  // every exit: x back to the external numbering
-    for (int i = gt; i < N; i += gs) {
+    for (int i = i0 + lane; i < i1; i += 32) {
       const int e = B.ext_of_int[i];
       if (e >= 0) a.x[e] = xi[i];
     }
@@ -395,7 +447,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     xi[i] = e >= 0 ? a.x[e] : 0.0;
   }
   bar.sync();
-  spmv_nb<BS>(B, k0, k1, xi, prod,
+  spmv_nb<BS>(B, k0, k1, xi, prod, pol,
               [&](int i) {
                 const int e = B.ext_of_int[i];
                 return Ops2{nb_diag_inv<BS>(B, i, a.pc), e >= 0 ? a.b[e] : 0.0};
@@ -405,7 +457,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
                 dinv[i] = o.a; r[i] = ri; rh[i] = ri; v[i] = 0.0; p[i] = ri;
                 acc[0] += ri * ri; acc[1] += bi * bi;
               });
-  gsum<3>(a, bar, acc, phase, sh);
+  grid_sum_fast<3>(bar, acc, a.red, phase, sh);
   if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
@@ -417,44 +469,80 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   int restarts = 0;
   int np = 0;
   stamp(a.prof, np);
+  constexpr int PU = 2;  // pass unroll: 32 * PU owned entries per batch of loads
   for (int it = 1; it <= a.maxit; ++it) {
     double d1[1] = {0.0};
-    spmv_nb<BS>(B, k0, k1, p, prod, [&](int i) { return Ops2{dinv[i], rh[i]}; },
+    spmv_nb<BS>(B, k0, k1, p, prod, pol, [&](int i) { return Ops2{dinv[i], rh[i]}; },
                 [&](int i, double ap, const Ops2& o) {
                   const double vi = o.a * ap;
                   v[i] = vi;
                   d1[0] += o.b * vi;
                 });
     stamp(a.prof, np);
-    gsum<1, false>(a, bar, d1, phase, sh);
+    grid_sum_fast<1>(bar, d1, a.red, phase, sh);
     stamp(a.prof, np);
     if (d1[0] == 0.0) { out(it - 1, -1, rn, bn); return; }
     const double alpha = rho / d1[0];
+    double ss;
+    double d3[4] = {0.0, 0.0, 0.0, 0.0};
+    if constexpr (DUAL) {
+      // s = r - alpha v is never stored: the product gathers r and v and forms it on the fly, the owner of row i
+      // forms s_i for the dot products.  One barrier and one vector pass fewer; the half-step test moves behind
+      // the product (same outcome, one product later).
+      double d5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      spmv_nb<BS, true>(B, k0, k1, r, prod, pol, [&](int i) { return Ops4{dinv[i], r[i] - alpha * v[i], rh[i], 0.0}; },
+                        [&](int i, double as, const Ops4& o) {
+                          const double ti = o.a * as;
+                          t[i] = ti;
+                          d5[0] += ti * o.b; d5[1] += ti * ti; d5[2] += o.c * o.b; d5[3] += o.c * ti; d5[4] += o.b * o.b;
+                        }, v, -alpha);
+      stamp(a.prof, np); stamp(a.prof, np); stamp(a.prof, np);
+      grid_sum_fast<5>(bar, d5, a.red, phase, sh);
+      stamp(a.prof, np);
+      ss = d5[4];
+      d3[0] = d5[0]; d3[1] = d5[1]; d3[2] = d5[2]; d3[3] = d5[3];
+      if (sqrt(ss) <= tol) {
+        for (int i = i0 + lane; i < i1; i += 32) xi[i] += alpha * p[i];
+        out(it, 1, sqrt(ss), bn);
+        return;
+      }
+    } else {
     double d2[1] = {0.0};
-    for (int i = gt; i < N; i += gs) {
-      const double si = r[i] - alpha * v[i];
-      s[i] = si;
-      d2[0] += si * si;
+    for (int base = i0 + lane; base < i1; base += 32 * PU) {
+      double rr[PU], vv[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int i = base + 32 * u;
+        rr[u] = i < i1 ? r[i] : 0.0;
+        vv[u] = i < i1 ? v[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int i = base + 32 * u;
+        const double si = rr[u] - alpha * vv[u];
+        if (i < i1) s[i] = si;
+        d2[0] += si * si;
+      }
     }
     stamp(a.prof, np);
-    gsum<1, false>(a, bar, d2, phase, sh);
+    grid_sum_fast<1>(bar, d2, a.red, phase, sh);
     stamp(a.prof, np);
-    const double ss = d2[0];
+    ss = d2[0];
     if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
-      for (int i = gt; i < N; i += gs) xi[i] += alpha * p[i];
+      for (int i = i0 + lane; i < i1; i += 32) xi[i] += alpha * p[i];
       out(it, 1, sqrt(ss), bn);
       return;
     }
-    double d3[4] = {0.0, 0.0, 0.0, 0.0};
-    spmv_nb<BS>(B, k0, k1, s, prod, [&](int i) { return Ops3{dinv[i], s[i], rh[i]}; },
+    spmv_nb<BS>(B, k0, k1, s, prod, pol, [&](int i) { return Ops3{dinv[i], s[i], rh[i]}; },
                 [&](int i, double as, const Ops3& o) {
                   const double ti = o.a * as;
                   t[i] = ti;
                   d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
                 });
     stamp(a.prof, np);
-    gsum<4, false>(a, bar, d3, phase, sh);
+    grid_sum_fast<4>(bar, d3, a.red, phase, sh);
     stamp(a.prof, np);
+    }
     if (d3[1] == 0.0) { out(it, -1, sqrt(ss), bn); return; }
     const double omega = d3[0] / d3[1];
     double rho_new = d3[2] - omega * d3[3];
@@ -466,18 +554,32 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     const double beta = restart ? 0.0 : (rho_new / rho) * (alpha / omega);
     const bool check = rn <= 2.0 * tol;  // confirm with a true norm
     double d4[1] = {0.0};
-    for (int i = gt; i < N; i += gs) {
-      const double pi = p[i], si = s[i];
-      xi[i] += alpha * pi + omega * si;
-      const double ri = si - omega * t[i];
-      r[i] = ri;
-      p[i] = ri + beta * (pi - omega * v[i]);
-      if (restart) rh[i] = ri;
-      d4[0] += ri * ri;
+    for (int base = i0 + lane; base < i1; base += 32 * PU) {
+      double pp[PU], sv[PU], tt[PU], vv[PU], xx[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int i = base + 32 * u;
+        const bool ok = i < i1;
+        pp[u] = ok ? p[i] : 0.0; sv[u] = ok ? (DUAL ? r[i] : s[i]) : 0.0; tt[u] = ok ? t[i] : 0.0;
+        vv[u] = ok ? v[i] : 0.0; xx[u] = ok ? xi[i] : 0.0;
+        if (DUAL) sv[u] -= alpha * vv[u];
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int i = base + 32 * u;
+        const double ri = sv[u] - omega * tt[u];
+        if (i < i1) {
+          xi[i] = xx[u] + alpha * pp[u] + omega * sv[u];
+          r[i] = ri;
+          p[i] = ri + beta * (pp[u] - omega * vv[u]);
+          if (restart) rh[i] = ri;
+        }
+        d4[0] += ri * ri;
+      }
     }
     stamp(a.prof, np);
     if (check || restart) {
-      gsum<1, false>(a, bar, d4, phase, sh);
+      grid_sum_fast<1>(bar, d4, a.red, phase, sh);
       rn = sqrt(d4[0]);
       if (rn <= tol) { out(it, 1, rn, bn); return; }
       if (restart) { rho_new = d4[0]; rhn = rn; }
@@ -506,6 +608,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
   const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
   GridBar bar;
   bar.init(a.bar);
+  const unsigned long long pol = nb_make_policy(B.l2policy);
   const int bad = nb_gather_values(B, a.A.val);
   if (bad) a.info->converged = -3;
   for (int i = gt; i < N; i += gs) {
@@ -514,7 +617,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
   }
   bar.sync();
   for (int rep = 0; rep < reps; ++rep) {
-    spmv_nb<BS>(B, k0, k1, xi, prod, [&](int i) { return Ops2{0.0, 0.0}; },
+    spmv_nb<BS>(B, k0, k1, xi, prod, pol, [&](int i) { return Ops2{0.0, 0.0}; },
                 [&](int i, double ax, const Ops2&) { yi[i] = ax; });
     bar.sync();
   }
@@ -1402,18 +1505,19 @@ int nb_ensure(fx_plan* P, int space) {
 
 static NbView nb_view(const fx_plan* P, const DevPattern& d) {
   const DevPattern::NbDev& nb = d.nb;
+  static const int pol_env = getenv("FX_NB_L2POLICY") ? atoi(getenv("FX_NB_L2POLICY")) : 1;
+  static const int pre_env = getenv("FX_NB_DUAL") ? atoi(getenv("FX_NB_DUAL")) : 1;
   return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
-                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval};
+                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env};
 }
 
 template <int BS>
 static int launch_nb(void* fn, const DevPattern& d, KArgs& ka, int reps, cudaStream_t st) {
   const size_t smem = sizeof(double) * NB_WARPS * nb_chunk(BS) * BS;
-  static bool attr[2] = {false, false};
-  const int ai = reps >= 0 ? 1 : 0;
-  if (!attr[ai]) {
+  static std::vector<void*> done;
+  if (std::find(done.begin(), done.end(), fn) == done.end()) {
     FX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[ai] = true;
+    done.push_back(fn);
   }
   void* args1[] = {(void*)&ka};
   void* args2[] = {(void*)&ka, (void*)&reps};
@@ -1487,7 +1591,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
   static const int red_env = getenv("FX_RED_ATOMIC") ? atoi(getenv("FX_RED_ATOMIC")) : 1;
   ka.red_atomic = red_env;
-  if (red_env) FX_CUDA(cudaMemsetAsync(P->red + (size_t)2 * RED_SLOTS * MAX_GRID, 0, sizeof(double) * 3 * RED_SLOTS, st));
+  if (red_env) FX_CUDA(cudaMemsetAsync(P->red + (size_t)2 * RED_SLOTS * MAX_GRID, 0, sizeof(double) * (3 * RED_SLOTS + 3 * 8), st));
   ka.x = x; ka.b = b; ka.w = part ? P->dist.region[P->dist.rank] : P->work; ka.red = P->red;
   ka.rtol = rtol; ka.atol = atol; ka.dtol = 1e5; ka.maxit = maxit; ka.pc = pc;
   ka.info = P->info + ticket;
@@ -1538,11 +1642,24 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
       if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
       ka.w = P->work;
       ka.nb = nb_view(P, p);
+      const bool dual = ka.nb.dual != 0;
       switch (p.nb.bs) {
-        case 1: return launch_nb<1>((void*)k_bicgstab_nb<1>, p, ka, -1, st);
-        case 2: return launch_nb<2>((void*)k_bicgstab_nb<2>, p, ka, -1, st);
-        default: return launch_nb<3>((void*)k_bicgstab_nb<3>, p, ka, -1, st);
+        case 1: rc = launch_nb<1>(dual ? (void*)k_bicgstab_nb<1, true> : (void*)k_bicgstab_nb<1, false>, p, ka, -1, st); break;
+        case 2: rc = launch_nb<2>(dual ? (void*)k_bicgstab_nb<2, true> : (void*)k_bicgstab_nb<2, false>, p, ka, -1, st); break;
+        default: rc = launch_nb<3>(dual ? (void*)k_bicgstab_nb<3, true> : (void*)k_bicgstab_nb<3, false>, p, ka, -1, st); break;
       }
+      if (rc == FX_OK && prof_env && p.n > 100000) {  // debugging aid: per-phase microseconds of iterations 2..4
+        static unsigned long long h[1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+        fprintf(stderr, "[krylov prof nb] space %d grid %d [spmv1 red+bar pass_s red+bar spmv2 red+bar pass_p bar]:", space, p.nb.grid);
+        for (int it = 1; it < 4; ++it) {
+          fprintf(stderr, "  |");
+          for (int k = 0; k < 8; ++k) fprintf(stderr, " %.1f", (double)(h[1 + 8 * it + k] - h[8 * it + k]) * 1e-3);
+        }
+        fprintf(stderr, "\n");
+      }
+      return rc;
     }
   }
   // big CTAs (1024 threads, one per SM) keep the grid barrier cheap: its cost grows with the number of

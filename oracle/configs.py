@@ -134,8 +134,17 @@ class _LDCBase:
         self.last.update(res_test=res_test.vec, res_orth=res_orth.vec,
                          res_orth_norm_sq=res_orth_norm_sq.vec, kapp=kapp.vec)
 
+    #: "lu" (parity runs: exact solves) or (method, pc): the reference's own Krylov path, e.g. ("bicgstab", "ilu") =
+    #: solve(A, x, b, "bicgstab", "default") at PETSc's rtol 1e-5 from the previous solution (bench.py's CPU arm)
+    solver = "lu"
+    solver_rtol = 1e-5
+
     def _solve(self, A, x, b):
-        x[:] = fem.solve_lu(A, b)
+        if self.solver == "lu":
+            x[:] = fem.solve_lu(A, b)
+        else:
+            it = fem.solve_krylov_c(A, x, b, self.solver[0], self.solver[1], rtol=self.solver_rtol)[0]
+            self.last.setdefault("iterations", []).append(it)
 
 
 class IncompLDC(_LDCBase):

@@ -654,6 +654,44 @@ def solve_lu(A, b):
     return spla.splu(A.tocsc()).solve(b)
 
 
+_KLIB = None
+
+
+def solve_krylov_c(A, x, b, method="bicgstab", pc="ilu", rtol=1e-5, atol=1e-50, maxiter=10000):
+    """PETSc-like Krylov solve in C (oracle/krylov_c.c): KSPBCGS / KSPCG with ILU(0) ('ilu', PETSc's serial
+    "default"), Jacobi or no preconditioning, left-preconditioned residual test, x = initial guess (the reference sets
+    nonzero_initial_guess).  Returns (iterations, ||M^-1 r||, ||M^-1 b||); raises like dolfin on non-convergence."""
+    global _KLIB
+    import ctypes as C
+    if _KLIB is None:
+        import importlib.util
+        import os
+        here = os.path.dirname(os.path.abspath(__file__))
+        spec = importlib.util.spec_from_file_location("fx_oracle_build", os.path.join(here, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _KLIB = C.CDLL(mod.build())
+        _KLIB.fxo_krylov.restype = C.c_int
+    A = A.tocsr()
+    A.sort_indices()
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    va = np.ascontiguousarray(A.data, dtype=np.float64)
+    bb = np.ascontiguousarray(b, dtype=np.float64)
+    xx = np.ascontiguousarray(x, dtype=np.float64).copy()
+    out = np.zeros(3)
+    vp = C.c_void_p
+    rc = _KLIB.fxo_krylov(C.c_int(A.shape[0]), vp(rp.ctypes.data), vp(ci.ctypes.data), vp(va.ctypes.data),
+                          vp(xx.ctypes.data), vp(bb.ctypes.data), C.c_int({"bicgstab": 0, "cg": 1}[method]),
+                          C.c_int({"none": 0, "jacobi": 1, "ilu": 2, "default": 2}[pc]), C.c_double(rtol),
+                          C.c_double(atol), C.c_int(maxiter), vp(out.ctypes.data))
+    if rc != 1:
+        raise RuntimeError("Krylov solver (%s, %s) did not converge: status %d after %d iterations, residual %.3e"
+                           % (method, pc, rc, int(out[0]), out[1]))
+    x[:] = xx
+    return int(out[0]), float(out[1]), float(out[2])
+
+
 def solve(A, x, b, method="lu", pc="default", rtol=1e-5, atol=1e-50, maxiter=10000):
     """solve(A, x, b[, method, pc]) writing into the array x (initial guess = contents of x).
     method 'lu' (dolfin default when no method is given) or 'bicgstab'/'cg'/'gmres' with ILU(0)-like
