@@ -459,7 +459,7 @@ int fx_plan_set_aggregates(fx_plan* P, int space, const int* agg, int k) {
                      "are not local in the dof numbering", nl_max, cfg.nlmax);
   d.agg_nl = nl_max;
   if (!P->coarse) {
-    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * (size_t)COARSE_KMAX_CG * COARSE_KMAX_CG + 4 * COARSE_KMAX_CG)));
+    FX_CUDA(cudaMalloc((void**)&P->coarse, sizeof(double) * (2 * (size_t)COARSE_KMAX_CG * COARSE_KMAX_CG + 4 * COARSE_KMAX_CG + 16)));
   }
   FX_CUDA(cudaMalloc((void**)&d.agg, sizeof(int) * (size_t)d.n));
   FX_CUDA(cudaMemcpy(d.agg, agg, sizeof(int) * (size_t)d.n, cudaMemcpyHostToDevice));

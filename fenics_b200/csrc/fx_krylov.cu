@@ -629,6 +629,34 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
 
 __device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k, GridBar& bar, double* scratch);
 
+// Pure-Neumann pressure systems (config 1, incompressible_dgp.py): A 1 = 0, so the coarse matrix E = P^T A P is singular
+// along the constant coarse vector and cannot be inverted.  Detected on the device (largest |row sum| of E against its
+// largest diagonal entry; the same verdict in every CTA) and cured by the rank-one shift E + gamma 1 1^T: on the range
+// of E (all a consistent right-hand side ever excites: P^T r is orthogonal to 1 when r is) its inverse is the
+// pseudo-inverse of E, and M^-1 = D^-1 + P (E + gamma 1 1^T)^-1 P^T stays symmetric positive definite.
+// flag: 2 doubles, zeroed before E was assembled.  Call between the barrier that completes E and the inversion.
+__device__ __forceinline__ void coarse_fix_nullspace(double* E0, int k, GridBar& bar, double* flag) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+  double mrs = 0.0, mdg = 0.0;
+  for (int g = gt >> 5; g < k; g += gs >> 5) {
+    double rs = 0.0;
+    for (int h = lane; h < k; h += 32) rs += __ldcg(E0 + (size_t)g * k + h);
+    rs = warp_sum(rs);
+    if (lane == 0) { mrs = fmax(mrs, fabs(rs)); mdg = fmax(mdg, fabs(__ldcg(E0 + (size_t)g * k + g))); }
+  }
+  if (lane == 0 && mdg > 0.0) {  // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(flag), (unsigned long long)__double_as_longlong(mrs));
+    atomicMax(reinterpret_cast<unsigned long long*>(flag) + 1, (unsigned long long)__double_as_longlong(mdg));
+  }
+  bar.sync();
+  const double rs = __ldcg(flag), dg = __ldcg(flag + 1);
+  if (rs <= 1e-12 * dg) {
+    const double gamma = dg / k;
+    for (int i = gt; i < k * k; i += gs) E0[i] += gamma;
+    bar.sync();
+  }
+}
+
 // ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
 // u = M^-1 r, w = A u, p = u + beta p, s = w + beta s (= A p).  One SpMV and ONE fused reduction
 // (gamma = (r,u), delta = (w,u), ||u||^2) per iteration: two grid barriers instead of three.
@@ -708,7 +736,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
   if constexpr (!DIST) {
     if (coarse) {
       for (int i = gt; i < ck * ck; i += gs) a.cz.E0[i] = 0.0;
-      for (int i = gt; i < 4 * COARSE_KMAX_CG; i += gs) a.cz.cvec[i] = 0.0;
+      for (int i = gt; i < 4 * COARSE_KMAX_CG + 2; i += gs) a.cz.cvec[i] = 0.0;  // + the two null-space flags behind them
       bar.sync();
       for (int row = gt; row < n; row += gs) {
         const int ga = a.cz.agg[row];
@@ -718,6 +746,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
         }
       }
       bar.sync();
+      coarse_fix_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
       Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, prod);  // scratch: the SpMV staging area (idle here)
     }
   }
@@ -1191,6 +1220,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
     // E = P^T A P from the resident slices
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ck * ck; i += gridDim.x * blockDim.x) a.cz.E0[i] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * COARSE_KMAX; i += gridDim.x * blockDim.x) a.cz.cvec[i] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x < 2) a.cz.cvec[4 * COARSE_KMAX_CG + threadIdx.x] = 0.0;  // null-space flags
     bar.sync();
 #pragma unroll
     for (int rr = 0; rr < R; ++rr)
@@ -1198,6 +1228,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         for (int j = my_s0[rr]; j < my_s1[rr]; ++j)
           atomicAdd(a.cz.E0 + (size_t)my_agg[rr] * ck + a.cz.agg[scol[rr * SL + j]], sval[rr * SL + j]);
     bar.sync();
+    coarse_fix_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
     const double* Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, einv_s);
     for (int sidx = 0; sidx < nl; ++sidx)
       for (int h = threadIdx.x; h < ck; h += blockDim.x)

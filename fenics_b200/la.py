@@ -9,14 +9,47 @@ from . import _abi as abi
 from ._lib import SolveInfo, check, lib
 
 _KSP = {"bicgstab": abi.FX_KSP_BICGSTAB, "cg": abi.FX_KSP_CG, "gmres": abi.FX_KSP_GMRES}
-_PC = {"none": abi.FX_PC_NONE, "jacobi": abi.FX_PC_JACOBI, "ilu": abi.FX_PC_ILU0, "default": abi.FX_PC_JACOBI,
-       "jacobi_coarse": abi.FX_PC_JACOBI_COARSE}
+_PC = {"none": abi.FX_PC_NONE, "jacobi": abi.FX_PC_JACOBI, "ilu": abi.FX_PC_ILU0, "jacobi_coarse": abi.FX_PC_JACOBI_COARSE}
+# dolfin preconditioner names the library has no kernel for.  They are SUBSTITUTED, never silently: the first use of
+# each name warns (`parameters["preconditioner_substitution"]`: "warn" (default) | "silent" | "error").
+#   "default" (PETSc, serial: ILU(0))  -> "jacobi"        e.g. solve(A, x, b, "bicgstab", "default"), incomp_LDC.py:331
+#   "amg" / "petsc_amg" / "hypre_amg"  -> "jacobi_coarse" for CG on a space with aggregates (fx_plan_set_aggregates),
+#                                         else "jacobi"   e.g. KrylovSolver("cg", "amg"), fenepmp_jbp.py:437-445
+# Iteration counts therefore differ from PETSc's (CPU study in DESIGN.md section 4: ILU(0) needs 3-5x fewer iterations
+# than Jacobi on the W systems); the stopping rule (left-preconditioned residual, rtol 1e-5) is the same.
+_PC_SUBSTITUTE = {"default": "jacobi", "amg": "jacobi_coarse", "petsc_amg": "jacobi_coarse", "hypre_amg": "jacobi_coarse"}
+_warned = set()
+
+
+class PreconditionerSubstitution(UserWarning):
+    pass
+
+
+def resolve_pc(pc, method, A):
+    """name -> name of a preconditioner the library implements (see _PC_SUBSTITUTE)."""
+    if pc in _PC:
+        return pc
+    if pc not in _PC_SUBSTITUTE:
+        raise ValueError("unknown method/preconditioner %r/%r" % (method, pc))
+    to = _PC_SUBSTITUTE[pc]
+    if to == "jacobi_coarse" and not (method == "cg" and A.plan.has_aggregates(A.space)):
+        to = "jacobi"
+    mode = parameters.get("preconditioner_substitution", "warn")
+    if mode == "error":
+        raise ValueError("preconditioner %r is not implemented (would be served by %r)" % (pc, to))
+    if mode == "warn" and (pc, to) not in _warned:
+        import warnings
+        _warned.add((pc, to))
+        warnings.warn("fenics_b200: preconditioner %r is served by %r (no ILU/AMG kernel); iteration counts differ "
+                      "from PETSc's" % (pc, to), PreconditionerSubstitution, stacklevel=3)
+    return to
+
 
 # mirror of dolfin's global `parameters["krylov_solver"]` (PETSc defaults, SURVEY.md 3.4)
 parameters = {"krylov_solver": {"relative_tolerance": 1e-5, "absolute_tolerance": 1e-50,
                                 "maximum_iterations": 10000, "nonzero_initial_guess": True,
                                 "monitor_convergence": False, "error_on_nonconvergence": True},
-              "std_out_all_processes": False}
+              "std_out_all_processes": False, "preconditioner_substitution": "warn"}
 
 
 def _stream():
@@ -53,6 +86,7 @@ class Plan:
                                  bl.ctypes.data, bm.ctypes.data, len(bc_), self.device, C.byref(h)))
         self.h = h
         self._pat = {}
+        self._agg = set()
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -74,10 +108,16 @@ class Plan:
         (and leaves the space without aggregates) when the library cannot use them for this space."""
         a = np.ascontiguousarray(agg, dtype=np.int32)
         rc = lib.fx_plan_set_aggregates(self.h, abi.SPACE_ID[space], a.ctypes.data, int(k))
+        self._agg.discard(space)
         if rc == abi.FX_ERR_UNSUPPORTED:
             return False
         check(rc)
+        if int(k) > 0:
+            self._agg.add(space)
         return True
+
+    def has_aggregates(self, space):
+        return space in self._agg
 
     def dim(self, space):
         return lib.fx_space_dim(self.h, abi.SPACE_ID[space])
@@ -134,7 +174,13 @@ class Vector:
         self.t.copy_(torch.as_tensor(np.asarray(a, dtype=np.float64)), non_blocking=False)
 
     def __setitem__(self, key, value):
-        self.set_local(value)
+        """v[:] = a (the scripts' idiom) or any index / slice / index array torch accepts."""
+        if isinstance(key, slice) and key == slice(None):
+            self.set_local(value) if np.ndim(value) else self.t.fill_(float(value))
+        else:
+            if isinstance(key, np.ndarray):
+                key = torch.as_tensor(key, device=self.t.device)
+            self.t[key] = torch.as_tensor(np.asarray(value, dtype=np.float64), device=self.t.device)
 
     def zero(self):
         self.t.zero_()
@@ -197,8 +243,9 @@ def krylov_solve(A, x, b, method="bicgstab", pc="default", rtol=None, atol=None,
     maxit = ks["maximum_iterations"] if maxit is None else maxit
     if not ks["nonzero_initial_guess"]:
         x.t.zero_()
-    if method not in _KSP or pc not in _PC:
+    if method not in _KSP:
         raise ValueError("unknown method/preconditioner %r/%r" % (method, pc))
+    pc = resolve_pc(pc, method, A)
     args = (A.plan.h, abi.SPACE_ID[A.space], _ptr(A.val), _ptr(x.t), _ptr(b.t), _KSP[method], _PC[pc],
             float(rtol), float(atol), int(maxit))
     if ticket is not None:

@@ -113,3 +113,40 @@ def test_shuffled_cell_order_gives_the_same_matrices():
         got = dapi.assemble(drv.pr.form(fid))
         err = lc.csr_rel_err(got.to_scipy(), ref) if name.startswith("a") else lc.rel_err(got.get_local(), ref)
         assert err < 1e-12, (name, err)
+
+
+def test_vector_setitem_honours_the_key_and_pc_names_are_substituted_loudly():
+    import warnings
+    from fenics_b200 import dolfin_api as dapi, la, mesh as pmesh
+    from fenics_b200 import _abi as abi
+    from fenics_b200.drivers import ldc
+    drv = ldc.CompLDC(pmesh.Skew_Mesh(6, 1, 1))
+    v = la.Vector(drv.plan, "Q")
+    v[:] = np.arange(v.size(), dtype=float)
+    v[3] = -1.0
+    v[np.array([0, 5])] = [7.0, 8.0]
+    ref = np.arange(v.size(), dtype=float)
+    ref[3], ref[0], ref[5] = -1.0, 7.0, 8.0
+    assert np.array_equal(v.get_local(), ref)
+    v[:] = 2.0
+    assert np.all(v.get_local() == 2.0)
+    # "default" (PETSc ILU(0)) and "amg" are served by named substitutes, with a warning the first time
+    A = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_A5))
+    b = la.Vector(drv.plan, "Q")
+    b.set_local(np.random.default_rng(0).standard_normal(b.size()))
+    la._warned.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "bicgstab", "default")
+        la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "cg", "amg")
+        la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "cg", "amg")
+    msgs = [str(x.message) for x in w if issubclass(x.category, la.PreconditionerSubstitution)]
+    assert len(msgs) == 2 and "'default' is served by 'jacobi'" in msgs[0] and "'amg' is served by 'jacobi'" in msgs[1]
+    la.parameters["preconditioner_substitution"] = "error"
+    try:
+        with pytest.raises(ValueError):
+            la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "bicgstab", "default")
+    finally:
+        la.parameters["preconditioner_substitution"] = "warn"
+    with pytest.raises(ValueError):
+        la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "bicgstab", "nonsense")

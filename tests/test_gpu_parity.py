@@ -447,3 +447,31 @@ def test_shim_helpers_on_device_functions():
     Q, W, Zc = drv.S["Q"], drv.S["W"], drv.S["Zc"]
     fs = ff.solution_functions(Q, W, None, Zc)
     assert len(fs) == 22 and fs[0].vector().size() == Q.dim() and fs[-1].vector().size() == Zc.dim()
+
+
+def test_two_level_preconditioner_on_the_singular_pressure_system():
+    """config 1's pressure matrix is pure Neumann (A 1 = 0): the coarse matrix P^T A P is singular along the constant
+    vector; the kernels detect that on the device and shift it by gamma 1 1^T, so CG + jacobi_coarse solves the
+    consistent system: same pressure (up to the constant) as Jacobi-CG, far fewer iterations."""
+    for n, resident in ((40, True), (40, False)):
+        ocl, drv = _pair(1, n=n)
+        lc.randomize(ocl)
+        _push_state(ocl, drv)
+        assert drv.enable_pressure_coarse(k=64)
+        A = dapi.assemble(drv.pr.form(abi.FX_FORM_C1_A5))
+        b = dapi.assemble(drv.pr.form(abi.FX_FORM_C1_L5))
+        bv = b.get_local()
+        assert abs(bv.sum()) < 1e-10 * np.abs(bv).sum()          # consistent: b is orthogonal to the null space
+        As = A.to_scipy()
+        assert np.abs(As @ np.ones(As.shape[0])).max() < 1e-12 * np.abs(As.diagonal()).max()
+        sol, its = {}, {}
+        rtol = 1e-9 if resident else 1e-11                        # < 1e-9 leaves the resident kernel for k_cg
+        for pc in ("jacobi", "jacobi_coarse"):
+            x = la.Vector(drv.plan, "Q")
+            info = la.krylov_solve(A, x, b, "cg", pc, rtol=rtol, maxit=20000)
+            assert info.converged == 1
+            v = x.get_local()
+            sol[pc], its[pc] = v - v.mean(), info.iterations
+            assert np.linalg.norm(As @ v - bv) < 1e-6 * np.linalg.norm(bv)
+        assert lc.rel_err(sol["jacobi_coarse"], sol["jacobi"]) < 1e-6
+        assert its["jacobi_coarse"] < 0.6 * its["jacobi"], its

@@ -1,4 +1,5 @@
-"""Small ncu target: a few fixed-length BiCGStab solves of the cfg2 W and Zc systems at n (default 192).
+"""Small ncu target: fixed-length BiCGStab solves (K/4 and K iterations) of the cfg2 W and Zc systems at n (default 192);
+the time step before them launches 5 BiCGStab kernels (skip them with ncu -s 5).
 usage: python tools/nb_profile_target.py [n] [iterations]"""
 import os
 import sys
@@ -22,8 +23,8 @@ for space, fid, bcs in (("W", abi.FX_FORM_C2_A1, drv.bcu), ("Zc", abi.FX_FORM_C2
     b.t.normal_()
     for bc in bcs:
         bc.apply(A, b)
-    for _ in range(2):
+    for k in (K // 4, K):  # two lengths: DRAM bytes per iteration = difference / (K - K/4), the rest is set-up
         x.t.zero_()
-        la.krylov_solve(A, x, b, "bicgstab", "jacobi", rtol=0.0, atol=0.0, maxit=K, ticket=0)
+        la.krylov_solve(A, x, b, "bicgstab", "jacobi", rtol=0.0, atol=0.0, maxit=k, ticket=0)
     torch.cuda.synchronize()
 print("ok")

@@ -1,0 +1,143 @@
+"""Mesh-partitioned (strong-scaling) measurements that bench.py appends to its JSON line under torchrun (N > 1).
+
+For each case -- BASELINE config 2/5-style refined cavity and the config-3 eccentric annulus, both ~4M DOFs -- all ranks
+advance ONE mesh-partitioned run (fused peer-memory Krylov kernels); rank 0 then advances the same mesh
+alone on its GPU (the other ranks wait), which gives `ms_1gpu` and `speedup` measured in the same process on the same
+box.  Parity: the same partitioned-vs-single comparison at tight solver tolerance on a smaller mesh, owned entries
+gathered to rank 0 (`max_rel_err_vs_single_gpu`, north_star tolerance 1e-8 after K steps).
+"""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _mk(case, world, device, n, tight=False):
+    from fenics_b200 import mesh as pmesh
+    from fenics_b200.drivers import ewm, ldc, ldc_dist
+    from fenics_b200.mesh import annulus_mesh
+    if case == "cfg2":
+        mesh = pmesh.Skew_Mesh(n, 1, 1)
+        kw = dict(dt=0.001 * min(1.0, 192.0 / n))  # dt ~ h keeps the explicit stress coupling stable on the finer mesh
+        cls = ldc_dist.DistCompLDC if world > 1 else ldc.CompLDC
+    else:
+        mesh = annulus_mesh(4 * n, n // 4, -0.90, 0.0, 1.0, 0.0, 0.0, 2.0)
+        kw = dict(dt=10.0 * mesh.hmin() ** 2)  # the script's dt = 10 hmin^2 of the GLOBAL mesh (main pass)
+        cls = ldc_dist.DistEwmJBP if world > 1 else ewm.EwmJBP
+    d = cls(mesh, device=device, **kw)
+    d.t = 0.45
+    d.pressure_method = "cg"
+    d.enable_pressure_coarse()
+    if tight:
+        d.solve_rtol = 1e-12
+    return d, mesh
+
+
+def _dofs(d, world):
+    S = d.global_spaces if world > 1 else d.S
+    return int(sum(S[k].dim() for k in ("W", "Zc", "Q")))
+
+
+def _timed(d, warm, steps, world):
+    for _ in range(warm):
+        d.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = d.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms), r
+
+
+def _gather_fields(d, rank, world):
+    """owned entries of every result field -> global vectors on rank 0"""
+    out = {}
+    for name, (gid, val) in d.owned_fields().items():
+        objs = [None] * world if rank == 0 else None
+        dist.gather_object((gid, val), objs, dst=0)
+        if rank == 0:
+            n = max(int(g.max()) for g, _ in objs) + 1
+            v = np.full(n, np.nan)
+            for g, x in objs:
+                v[g] = x
+            out[name] = v
+    return out
+
+
+def _case(case, rank, world, local, n, steps=5, warm=3):
+    t0 = time.time()
+    d, mesh = _mk(case, world, local, n)
+    dofs = _dofs(d, world)
+    ms_part, r = _timed(d, warm, steps, world)
+    iters = dict(zip(d.solve_labels, [i.iterations for i in d.last_info]))
+    fused = bool(d.ctx.fused)
+    if hasattr(d, "ctx"):
+        d.ctx.close()
+    del d
+    torch.cuda.empty_cache()
+    dist.barrier()
+    row = dict(case=case, mesh_n=n, dofs=dofs, n_gpus=world, steps=steps, warmup=warm, ms_per_step=round(ms_part, 3),
+               fused=fused, iterations=iters, dof_steps_per_s=round(dofs * 1e3 / ms_part))
+    if rank == 0:  # the same mesh on ONE GPU, same process, same box
+        s, _ = _mk(case, 1, local, n)
+        ms_one, r1 = _timed(s, warm, steps, 1)
+        row.update(ms_1gpu=round(ms_one, 3), speedup=round(ms_one / ms_part, 3),
+                   iterations_1gpu=dict(zip(s.solve_labels, [i.iterations for i in s.last_info])),
+                   E_k=float(r["E_k"]), E_k_1gpu=float(r1["E_k"]))
+        del s
+        torch.cuda.empty_cache()
+    dist.barrier()
+    row["wall_s"] = round(time.time() - t0, 1)
+    return row
+
+
+def _parity(case, rank, world, local, n=64, steps=3):
+    """partitioned vs single-GPU fields after `steps` steps at solver rtol 1e-12"""
+    d, _ = _mk(case, world, local, n, tight=True)
+    for _ in range(steps):
+        d.step()
+    torch.cuda.synchronize()
+    got = _gather_fields(d, rank, world)
+    d.ctx.close()
+    del d
+    err = None
+    if rank == 0:
+        s, _ = _mk(case, 1, local, n, tight=True)
+        for _ in range(steps):
+            s.step()
+        ref = s.fields()
+        key = {"w1": "w1", "p1": "p1", "tau1_vec": "tau1", "rho1": "rho1", "T1": "T1"}
+        err = 0.0
+        for name, v in got.items():
+            rv = ref.get(key.get(name, name))
+            if rv is None:
+                continue
+            err = max(err, float(np.max(np.abs(v - rv)) / max(np.max(np.abs(rv)), 1e-300)))
+        del s
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return err
+
+
+def run(rank, world, local):
+    n_big = int(os.environ.get("FX_PARTITION_N", "384"))
+    out = {"mode": "mesh partition (RCB), owned/ghost dofs, fused peer-memory Krylov kernels (no NCCL inside a solve)",
+           "scaling": "strong", "cases": []}
+    for case in ("cfg2", "cfg3"):
+        try:
+            row = _case(case, rank, world, local, n_big)
+            row["max_rel_err_vs_single_gpu"] = _parity(case, rank, world, local)
+            row["parity_run"] = "n=64 mesh, 3 steps, solver rtol 1e-12, all result fields"
+        except Exception as exc:  # reported, not hidden
+            row = {"case": case, "error": repr(exc)[:400]}
+        out["cases"].append(row)
+    return out
