@@ -629,20 +629,27 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
 
 __device__ __forceinline__ double* invert_blocked(double* E0, double* E1, int k, GridBar& bar, double* scratch);
 
-// Pure-Neumann pressure systems (config 1, incompressible_dgp.py): A 1 = 0, so the coarse matrix E = P^T A P is singular
-// along the constant coarse vector and cannot be inverted.  Detected on the device (largest |row sum| of E against its
-// largest diagonal entry; the same verdict in every CTA) and cured by the rank-one shift E + gamma 1 1^T: on the range
-// of E (all a consistent right-hand side ever excites: P^T r is orthogonal to 1 when r is) its inverse is the
-// pseudo-inverse of E, and M^-1 = D^-1 + P (E + gamma 1 1^T)^-1 P^T stays symmetric positive definite.
-// flag: 2 doubles, zeroed before E was assembled.  Call between the barrier that completes E and the inversion.
-__device__ __forceinline__ void coarse_fix_nullspace(double* E0, int k, GridBar& bar, double* flag) {
+// Singular and nearly singular coarse matrices.  Pure-Neumann pressure systems (config 1, incompressible_dgp.py) have
+// A 1 = 0, so E = P^T A P is singular along the constant coarse vector; the compressible loops at Ma = 1e-6 (config 3's
+// script parameters: mass term 1e-12 / dt) make it singular to ~1e-10, which the unpivoted Gauss-Jordan cannot resolve
+// (CG then diverges at n = 384).  Both are detected on the device (largest |row sum| of E against its largest
+// diagonal entry; the same verdict in every CTA) and handled by a rank-one shift:
+//   1. invert  E^ = E + gamma 1 1^T  (well conditioned);
+//   2. undo the shift exactly with Sherman-Morrison:  E^-1 = E^^-1 + mu z z^T,  z = E^^-1 1,  mu = gamma / den,
+//      den = 1 - gamma 1^T z, evaluated WITHOUT the cancellation as den = (E 1)^T z / k from the row sums of the
+//      unshifted E (E^ z = 1  =>  E z = den 1).
+// mu z z^T is symmetric positive semi-definite however inaccurately the tiny denominator is known, so the
+// preconditioner stays SPD.  For an exactly singular E the denominator is rounding noise (<= 1e-14): step 2 is skipped
+// and E^^-1 acts as the pseudo-inverse on the range of E (all that a consistent right-hand side ever excites).
+// flag: 16 doubles (2 used, zeroed before E was assembled) followed by k row sums.  Returns gamma (0: E is regular).
+__device__ __forceinline__ double coarse_shift_nullspace(double* E0, int k, GridBar& bar, double* flag) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
   double mrs = 0.0, mdg = 0.0;
   for (int g = gt >> 5; g < k; g += gs >> 5) {
     double rs = 0.0;
     for (int h = lane; h < k; h += 32) rs += __ldcg(E0 + (size_t)g * k + h);
     rs = warp_sum(rs);
-    if (lane == 0) { mrs = fmax(mrs, fabs(rs)); mdg = fmax(mdg, fabs(__ldcg(E0 + (size_t)g * k + g))); }
+    if (lane == 0) { flag[16 + g] = rs; mrs = fmax(mrs, fabs(rs)); mdg = fmax(mdg, fabs(__ldcg(E0 + (size_t)g * k + g))); }
   }
   if (lane == 0 && mdg > 0.0) {  // non-negative doubles order like their bit patterns
     atomicMax(reinterpret_cast<unsigned long long*>(flag), (unsigned long long)__double_as_longlong(mrs));
@@ -650,11 +657,31 @@ __device__ __forceinline__ void coarse_fix_nullspace(double* E0, int k, GridBar&
   }
   bar.sync();
   const double rs = __ldcg(flag), dg = __ldcg(flag + 1);
-  if (rs <= 1e-12 * dg) {
-    const double gamma = dg / k;
-    for (int i = gt; i < k * k; i += gs) E0[i] += gamma;
-    bar.sync();
+  if (!(rs <= 1e-6 * dg)) return 0.0;
+  const double gamma = dg / k;
+  for (int i = gt; i < k * k; i += gs) E0[i] += gamma;
+  bar.sync();
+  return gamma;
+}
+__device__ __forceinline__ void coarse_unshift(double* Einv, int k, double gamma, GridBar& bar, double* z,
+                                               const double* flag, double* sh) {
+  if (gamma == 0.0) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+  for (int g = gt >> 5; g < k; g += gs >> 5) {
+    double rs = 0.0;
+    for (int h = lane; h < k; h += 32) rs += __ldcg(Einv + (size_t)g * k + h);
+    rs = warp_sum(rs);
+    if (lane == 0) z[g] = rs;
   }
+  bar.sync();
+  double part = 0.0;
+  for (int h = threadIdx.x; h < k; h += blockDim.x) part += __ldcg(flag + 16 + h) * __ldcg(z + h);
+  const double den = block_sum_bcast(part, sh) / k;  // fixed tree: the same value in every CTA
+  if (den > 1e-14) {
+    const double mu = gamma / den;
+    for (int i = gt; i < k * k; i += gs) Einv[i] += mu * __ldcg(z + i / k) * __ldcg(z + i % k);
+  }
+  bar.sync();
 }
 
 // ---- CG (Chronopoulos-Gear) ---------------------------------------------------------------------------------
@@ -746,8 +773,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_cg(const __grid_con
         }
       }
       bar.sync();
-      coarse_fix_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
-      Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, prod);  // scratch: the SpMV staging area (idle here)
+      const double shift = coarse_shift_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
+      double* Ei = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, prod);  // scratch: the SpMV staging area (idle here)
+      coarse_unshift(Ei, ck, shift, bar, evec, a.cz.cvec + 4 * COARSE_KMAX_CG, sh);
+      Einv = Ei;
     }
   }
   spmv_stream_c(A, rg, a.x, prod,
@@ -1228,8 +1257,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) k_pcg_res(const __grid_constant
         for (int j = my_s0[rr]; j < my_s1[rr]; ++j)
           atomicAdd(a.cz.E0 + (size_t)my_agg[rr] * ck + a.cz.agg[scol[rr * SL + j]], sval[rr * SL + j]);
     bar.sync();
-    coarse_fix_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
-    const double* Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, einv_s);
+    const double shift = coarse_shift_nullspace(a.cz.E0, ck, bar, a.cz.cvec + 4 * COARSE_KMAX_CG);
+    double* Einv = invert_blocked(a.cz.E0, a.cz.E1, ck, bar, einv_s);
+    coarse_unshift(Einv, ck, shift, bar, a.cz.cvec + 3 * COARSE_KMAX_CG, a.cz.cvec + 4 * COARSE_KMAX_CG, sh);
     for (int sidx = 0; sidx < nl; ++sidx)
       for (int h = threadIdx.x; h < ck; h += blockDim.x)
         einv_s[(size_t)sidx * COARSE_LD + h] = __ldcg(Einv + (size_t)list[sidx] * ck + h);

@@ -251,12 +251,13 @@ int fx_plan_set_eliminated_dofs(fx_plan* plan, int space, const int* rows, int n
  * (incompressible_benchmarkEWM.py:441-451): Jacobi-CG needs O(1/h) iterations of microseconds each; the
  * coarse space removes the smooth error modes that cost most of them.  The coarse matrix is rebuilt
  * from the current matrix values and inverted on the device inside every solve.  Requirements:
- * k a multiple of 32, every aggregate non-empty, A non-singular, CG, no eliminated rows.  Two kernels apply it:
- * the shared-memory-resident pipelined CG (k <= 256, the system small enough to stay resident -- P1 spaces up to
- * ~148 k rows -- with aggregates local to its row blocks, rtol >= 1e-9) and, for everything else (k <= 1024), the
- * general CG kernel with two extra grid barriers per iteration.  Returns FX_ERR_UNSUPPORTED (and leaves the space
- * without aggregates) when k is out of range or the aggregates of a resident-size system are not local.
- * k = 0 removes them.                                                                               */
+ * k a multiple of 32, every aggregate non-empty, CG, no eliminated rows.  A may be singular or nearly singular along
+ * the constant vector (pure-Neumann pressure systems; compressible ones at Ma -> 0): the kernels detect it on the
+ * device and invert the coarse matrix through a rank-one shift (exact Sherman-Morrison correction when the matrix is
+ * only nearly singular).  Two kernels apply it: the shared-memory-resident pipelined CG (k <= 256, the system small
+ * enough to stay resident -- P1 spaces up to ~148 k rows -- with aggregates local to its row blocks, rtol >= 1e-9) and,
+ * for everything else (k <= 1024), the general CG kernel with two extra grid barriers per iteration.  Returns
+ * FX_ERR_UNSUPPORTED (and leaves the space without aggregates) when k is out of range.  k = 0 removes them. */
 int fx_plan_set_aggregates(fx_plan* plan, int space, const int* agg, int k);
 
 /* ---- mesh-partitioned runs: one process per GPU, one plan per sub-mesh ---------------
