@@ -213,11 +213,15 @@ static int run_facet_scalar(fx_plan* P, AsmArgs a, double* out_dev, cudaStream_t
   return FX_OK;
 }
 
-// config 4 functors are written for lambda_D = 0 (phi_def == 1); anything else is rejected loudly
+// the config-4 functors that carry phi_def(u, lambda_D) exist in two instantiations: FX_FORM_C4_* fold phi_def to 1
+// (lambda_D = 0, as UFL does) and reject anything else loudly; FX_FORM_C4M_* keep it
 static int check_form_params(int form, const AsmArgs& a) {
-  if (form >= FX_FORM_C4_A0 && form <= FX_FORM_C4_FORCE_Y && a.p.v[jbp::P_LAMBDA_D] != 0.0)
-    return set_error(FX_ERR_UNSUPPORTED, "config-4 forms are implemented for lambda_D = 0 only (got %g)",
-                     a.p.v[jbp::P_LAMBDA_D]);
+  const bool phi_form = form == FX_FORM_C4_A4 || form == FX_FORM_C4_L2 || form == FX_FORM_C4_L9 ||
+                        form == FX_FORM_C4_L_RES_ORTH || form == FX_FORM_C4_TORQUE || form == FX_FORM_C4_FORCE_X ||
+                        form == FX_FORM_C4_FORCE_Y;
+  if (phi_form && a.p.v[jbp::P_LAMBDA_D] != 0.0)
+    return set_error(FX_ERR_UNSUPPORTED, "form %d folds phi_def to 1 (lambda_D = 0); lambda_D = %g needs its "
+                     "FX_FORM_C4M_* counterpart", form, a.p.v[jbp::P_LAMBDA_D]);
   if (form >= FX_FORM_C3_A0 && form <= FX_FORM_C3_FORCE_Y && a.p.v[ldc::P_CONV] == 0.0)
     return set_error(FX_ERR_UNSUPPORTED, "config-3 forms are implemented for conv != 0 only");
   // the FX_FORM_C3_* functors below fold phi_s == phi_ewm == 1 (the script's A_0 = k_ewm = B = 0); the true EWM
@@ -275,6 +279,9 @@ int launch_scalar(fx_plan* P, int form, const AsmArgs& a, double* out_dev, cudaS
 }
 
 int launch_dg0(fx_plan* P, int expr, const AsmArgs& a, cudaStream_t st) {
+  if (expr == FX_EXPR_C4_RESTAU && a.p.v[jbp::P_LAMBDA_D] != 0.0)
+    return set_error(FX_ERR_UNSUPPORTED, "FX_EXPR_C4_RESTAU folds phi_def to 1 (lambda_D = 0); lambda_D = %g needs "
+                     "FX_EXPR_C4M_RESTAU", a.p.v[jbp::P_LAMBDA_D]);
   switch (expr) {
 #define X(id, E) case id: return run_dg0<E>(P, a, st);
     FX_DG0_EXPRS(X)

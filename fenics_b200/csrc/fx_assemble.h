@@ -106,6 +106,30 @@ FX_HD Vel eval_vel(const MeshView& m, const double* w, int cell, const P2Phys& b
   const VG c = eval_p2(w, m.dm[S_W], m.nc, cell, 6, b);
   return Vel{a.v, c.v, a.x, a.y, c.x, c.y};
 }
+// second derivatives of the velocity components (P2: constant on a cell).  Needed where a form differentiates a
+// function of grad(u): div(phi_def(u0) (...)) of the FENE-P-MP predictor (fenepmp_jbp.py:519, fenics_base.py:287-291)
+struct VelH {
+  double a_xx, a_xy, a_yy;  // u_0
+  double c_xx, c_xy, c_yy;  // u_1
+};
+FX_HD VelH eval_vel_hess(const MeshView& m, const double* w, int cell, const Geo& g) {
+  // reference second derivatives of the UFC P2 basis (xi xi, xi eta, eta eta)
+  constexpr double fxx[6] = {4.0, 4.0, 0.0, 0.0, 0.0, -8.0};
+  constexpr double fxe[6] = {4.0, 0.0, 0.0, 4.0, -4.0, -4.0};
+  constexpr double fee[6] = {4.0, 0.0, 4.0, 0.0, -8.0, 0.0};
+  VelH h{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    // d/dx = k00 d/dxi + k10 d/deta,  d/dy = k01 d/dxi + k11 d/deta  (p2_phys)
+    const double hxx = g.k00 * g.k00 * fxx[i] + 2.0 * g.k00 * g.k10 * fxe[i] + g.k10 * g.k10 * fee[i];
+    const double hxy = g.k00 * g.k01 * fxx[i] + (g.k00 * g.k11 + g.k10 * g.k01) * fxe[i] + g.k10 * g.k11 * fee[i];
+    const double hyy = g.k01 * g.k01 * fxx[i] + 2.0 * g.k01 * g.k11 * fxe[i] + g.k11 * g.k11 * fee[i];
+    const double a = w[m.dm[S_W][(long)i * m.nc + cell]], c = w[m.dm[S_W][(long)(6 + i) * m.nc + cell]];
+    h.a_xx += a * hxx; h.a_xy += a * hxy; h.a_yy += a * hyy;
+    h.c_xx += c * hxx; h.c_xy += c * hxy; h.c_yy += c * hyy;
+  }
+  return h;
+}
 // DEVSS part (components 2,3,4) of a W-space vector
 struct Sym3 {
   double a, b, c;  // [[a,b],[b,c]]

@@ -1,8 +1,13 @@
 // Hand-written form functors for config 4:
 //   "flow between eccentrically rotating cylinders"/fenepmp_jbp.py  (time loop :454-690)
-// FENE-P-MP journal bearing at the CSV default lambda_D = 0 (fenepmp_jbp.py:297, parameters-fenep-mp.csv
-// row 4), where phi_def(u, lambda_D) folds to the literal 1 and the MP dissipation term to Zero
-// (SURVEY.md Appendix A.4).  lambda_D != 0 is rejected by the launchers (FX_ERR_UNSUPPORTED).
+// FENE-P-MP journal bearing.  At the CSV default lambda_D = 0 (fenepmp_jbp.py:297, parameters-fenep-mp.csv row 4)
+// phi_def(u, lambda_D) folds to the literal 1 and the MP dissipation term to Zero: the
+// functors instantiated with MP = false.  lambda_D != 0 (CSV row `Ld`: 0.05, 0.1, 0.15; plot_data.py:45-47) keeps
+//   phi_def(u) = 1 + (3 lambda_D I_3(D(u)) / (I_2(D(u)) + 1e-7))^2                       (fenics_base.py:287-291)
+// in five places -- the predictor's div(phi_def(u0)(f tau0 - I)) (needs the P2 Hessian of u0), the stress matrix and
+// the LPS residual (dissipation term), the viscous heating and the journal functionals (sigma_f) -- and raises UFL's
+// quadrature degrees to 13 / 13 / 14 (dx) and 12 (ds): the MP = true instantiations, form ids FX_FORM_C4M_*.
+// The MP = false ids reject lambda_D != 0 (FX_ERR_UNSUPPORTED) and name their C4M counterparts.
 // Helper algebra: fenics_base.py:158-294.  Notation as in fx_forms_ldc.h; additionally
 //   f(tau) = fene_func(tau, b) = 1 / (1 - (|tau00 + tau11| - 2)/b^2)            (fenics_base.py:246-257)
 //   phi_s(theta) = 1 - A/(C + theta),  A = A_0/(8.3144598*50), C = 7              (fenics_base.py:227-238)
@@ -18,6 +23,8 @@ using namespace ldc;  // slot enums, shared building blocks
 enum : int { P_PR = 9, P_RA, P_DI, P_VH, P_BI, P_T0, P_TH_HOT, P_AL1, P_AL2, P_LAMBDA_D, P_B_FENE, P_A0, P_EPS, P_T,
              P_K_EWM, P_B_EWM, P_TH_T };
 
+constexpr int QD_MP_RESTAU = 11, QD_MP_RES_ORTH = 13;  // UFL's degrees of the two LPS projections with lambda_D != 0
+
 FX_HD double fene_f(double t0, double t2, double b) { return 1.0 / (1.0 - (fabs(t0 + t2) - 2.0) / (b * b)); }
 FX_HD double sgn(double x) { return (x > 0.0) - (x < 0.0); }
 FX_HD double theta_of(double T, const double* p) { return (T - p[P_T0]) / (p[P_TH_HOT] - p[P_T0]); }
@@ -29,8 +36,31 @@ FX_HD double phi_s_of(double theta, double A0) {
 struct SigmaF {
   double s00, s01, s11;
 };
-FX_HD SigmaF sigma_f(const Vel& u, double p, const Tau& t, const double* par) {
-  const double bv = par[P_BETAV], ce = (1.0 - bv) / par[P_WE];
+// phi_def(u, lambda_D) and (with the Hessian) its gradient
+FX_HD double phi_def_of(const Vel& u, double lam) {
+  const double d00 = u.g00, d01 = 0.5 * (u.g01 + u.g10), d11 = u.g11;
+  const double i3 = d00 * d11 - d01 * d01, i2 = 0.5 * (d00 * d00 + d11 * d11 + 2.0 * d01 * d01);
+  const double q = lam * 3.0 * i3 / (i2 + 0.0000001);
+  return 1.0 + q * q;
+}
+FX_HD void phi_def_grad(const Vel& u, const VelH& h, double lam, double& px, double& py) {
+  const double d00 = u.g00, d01 = 0.5 * (u.g01 + u.g10), d11 = u.g11;
+  const double i3 = d00 * d11 - d01 * d01, i2e = 0.5 * (d00 * d00 + d11 * d11 + 2.0 * d01 * d01) + 0.0000001;
+  const double q = lam * 3.0 * i3 / i2e;
+  // d_j D00 = d_j d_0 u_0, d_j D11 = d_j d_1 u_1, d_j D01 = (d_j d_1 u_0 + d_j d_0 u_1) / 2
+  const double d00j[2] = {h.a_xx, h.a_xy}, d11j[2] = {h.c_xy, h.c_yy};
+  const double d01j[2] = {0.5 * (h.a_xy + h.c_xx), 0.5 * (h.a_yy + h.c_xy)};
+  double out[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double di3 = d00j[j] * d11 + d00 * d11j[j] - 2.0 * d01 * d01j[j];
+    const double di2 = d00 * d00j[j] + d11 * d11j[j] + 2.0 * d01 * d01j[j];
+    out[j] = 2.0 * q * lam * 3.0 * (di3 * i2e - i3 * di2) / (i2e * i2e);
+  }
+  px = out[0]; py = out[1];
+}
+FX_HD SigmaF sigma_f(const Vel& u, double p, const Tau& t, const double* par, double phi = 1.0) {
+  const double bv = par[P_BETAV], ce = phi * (1.0 - bv) / par[P_WE];
   const double f = fene_f(t.t0.v, t.t2.v, par[P_B_FENE]);
   const double dv3 = (u.g00 + u.g11) / 3.0;
   SigmaF s;
@@ -84,9 +114,11 @@ struct C4_A2 {
   }
 };
 // L2 = rhs(Fus) + th DEVSSGr_u1                                        :513-528, :495
-struct C4_L2 {
+// MP: div(phi (f S - I))_i = phi div(f S - I)_i + (f S - I)_ij d_j phi
+template <bool MP>
+struct C4_L2T {
   using Space = SpW; using Facet = NoFacet;
-  static constexpr int QDEG = 6, NP = 5;
+  static constexpr int QDEG = MP ? 13 : 6, NP = 5;
   enum { F0, F1, SXX, SXY, SYY };
   FX_HD static void point(const PtArgs& x, double* d) {
     P2Phys b; P1Phys b1;
@@ -105,8 +137,15 @@ struct C4_L2 {
     const double f = fene_f(t.t0.v, t.t2.v, p[P_B_FENE]);
     const double k = f * f * sgn(t.t0.v + t.t2.v) / bb;
     const double trx = t.t0.x + t.t2.x, try_ = t.t0.y + t.t2.y;
-    const double dm0 = f * (t.t0.x + t.t1.y) + k * (t.t0.v * trx + t.t1.v * try_);
-    const double dm1 = f * (t.t1.x + t.t2.y) + k * (t.t1.v * trx + t.t2.v * try_);
+    double dm0 = f * (t.t0.x + t.t1.y) + k * (t.t0.v * trx + t.t1.v * try_);
+    double dm1 = f * (t.t1.x + t.t2.y) + k * (t.t1.v * trx + t.t2.v * try_);
+    if constexpr (MP) {
+      const double phi = phi_def_of(u, p[P_LAMBDA_D]);
+      double px, py;
+      phi_def_grad(u, eval_vel_hess(x.m, x.s.f[F_W0], x.cell, x.g), p[P_LAMBDA_D], px, py);
+      dm0 = phi * dm0 + (f * t.t0.v - 1.0) * px + f * t.t1.v * py;
+      dm1 = phi * dm1 + f * t.t1.v * px + (f * t.t2.v - 1.0) * py;
+    }
     const double rr = p[P_RE] * rho, hc = 0.5 * p[P_CONV];
     d[F0] = rr * (u.u0 / p[P_DT] - hc * (u.g00 * u.u0 + u.g01 * u.u1)) + ce * dm0 - p0.x;
     d[F1] = rr * (u.u1 / p[P_DT] - hc * (u.g10 * u.u0 + u.g11 * u.u1)) + ce * dm1 - p0.y;
@@ -124,6 +163,8 @@ struct C4_L2 {
     a.template add<UYY>(d[SYY]);
   }
 };
+using C4_L2 = C4_L2T<false>;
+using C4M_L2 = C4_L2T<true>;
 // a5 = (Ma^2/dt)(p,q) + dt (grad p, grad q)                             :536-542
 struct C4_A5 {
   using Space = SpQ; using Facet = NoFacet;
@@ -238,10 +279,12 @@ struct C4_L7 {
 };
 // a4 = ((We/dt + f(tau0)) tau + We FdefG(u1, S(D1), tau), Rt) + 0.05 (kapp h grad tau, grad Rt)
 //      + 0.01 (kapp h div tau, div Rt)                                    :595-608, :473
-struct C4_A4 {
+// MP: - We (phi_def(u1) - 1)/2 (tau D(u1) + D(u1) tau, S(Rt))
+template <bool MP>
+struct C4_A4T {
   using Space = SpZc; using Facet = NoFacet;
-  static constexpr int QDEG = 6, NP = 7;
-  enum { M, U0, U1, GA, GB, GC, KH };
+  static constexpr int QDEG = MP ? 13 : 6, NP = MP ? 10 : 7;
+  enum { M, U0, U1, GA, GB, GC, KH, CD00, CD01, CD11 };
   FX_HD static void point(const PtArgs& x, double* d) {
     P2Phys b;
     p2_phys(x.xi, x.et, x.g, b);
@@ -252,9 +295,22 @@ struct C4_A4 {
     d[M] = p[P_WE] / p[P_DT] + fene_f(t0.t0.v, t0.t2.v, p[P_B_FENE]);
     d[U0] = u.u0; d[U1] = u.u1; d[GA] = D1.a; d[GB] = D1.b; d[GC] = D1.c;
     d[KH] = eval_dg0(x.s.f[F_KAPP], x.m.dm[S_QT], x.m.nc, x.cell, 0) * x.g.h;
+    if constexpr (MP) {
+      const double c = -p[P_WE] * 0.5 * (phi_def_of(u, p[P_LAMBDA_D]) - 1.0);
+      d[CD00] = c * u.g00; d[CD01] = c * 0.5 * (u.g01 + u.g10); d[CD11] = c * u.g11;
+    }
   }
   template <class A> FX_HDC static void terms(A& a, const double* d, const Par& p) {
     const double We = p.v[P_WE], m = d[M];
+    if constexpr (MP) {  // (tau D + D tau) : S(Rt), off-diagonal counted twice
+      a.template add<T0V, T0V>(2.0 * d[CD00]);
+      a.template add<T0V, T1V>(2.0 * d[CD01]);
+      a.template add<T1V, T0V>(2.0 * d[CD01]);
+      a.template add<T1V, T1V>(2.0 * (d[CD00] + d[CD11]));
+      a.template add<T1V, T2V>(2.0 * d[CD01]);
+      a.template add<T2V, T1V>(2.0 * d[CD01]);
+      a.template add<T2V, T2V>(2.0 * d[CD11]);
+    }
     a.template add<T0V, T0V>(m);
     a.template add<T1V, T1V>(2.0 * m);
     a.template add<T2V, T2V>(m);
@@ -292,6 +348,8 @@ struct C4_A4 {
     a.template add<T2Y, T2Y>(c2);
   }
 };
+using C4_A4 = C4_A4T<false>;
+using C4M_A4 = C4_A4T<true>;
 // L4 = ((We/dt) S(tau0) + I, S(Rt))                                       :597-601
 struct C4_L4 {
   using Space = SpZc; using Facet = NoFacet;
@@ -356,9 +414,10 @@ struct C4_L9_Facet {
   }
   template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) { a.template add<QV>(d[0]); }
 };
-struct C4_L9 {
+template <bool MP>
+struct C4_L9T {
   using Space = SpQ; using Facet = C4_L9_Facet;
-  static constexpr int QDEG = 6, NP = 1;
+  static constexpr int QDEG = MP ? 14 : 6, NP = 1;
   FX_HD static void point(const PtArgs& x, double* d) {
     P2Phys b; P1Phys b1;
     p2_phys(x.xi, x.et, x.g, b);
@@ -370,15 +429,20 @@ struct C4_L9 {
     const double rho1 = eval_q(x.m, x.s.f[F_RHO1], x.cell, b1).v;
     const double th0 = theta_of(eval_q(x.m, x.s.f[F_T0], x.cell, b1).v, p);
     const double thr = p[P_T0] / (p[P_TH_HOT] - p[P_T0]);
-    const SigmaF s = sigma_f(u0, p0, t0, p);
+    const SigmaF s = sigma_f(u0, p0, t0, p, MP ? phi_def_of(u0, p[P_LAMBDA_D]) : 1.0);
     const double gamdot = s.s00 * u0.g00 + s.s01 * (u0.g01 + u0.g10) + s.s11 * u0.g11;
     d[0] = rho1 / p[P_DT] * (thr + th0) + p[P_VH] * gamdot;
   }
   template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) { a.template add<QV>(d[0]); }
 };
 
+using C4_L9 = C4_L9T<false>;
+using C4M_L9 = C4_L9T<true>;
+
 // restau0 = (We/dt)(tau1v - tau0v) + We [F00,F10,F11] + f(tau0) tau1v - I_vec,  F = Fdef(u1,tau1) with
 // + div(u1) tau1 (fenics_base.py:189-190)                                   :462-468
+// MP: - We (phi_def(u1) - 1)/2 [tau1 D(u1) + D(u1) tau1]_{00,10,11}        :464-466
+template <bool MP>
 FX_HD void jbp_restau(const PtArgs& x, double* r) {
   P2Phys b;
   p2_phys(x.xi, x.et, x.g, b);
@@ -397,12 +461,20 @@ FX_HD void jbp_restau(const PtArgs& x, double* r) {
   r[0] = wd * (a0 - t0.t0.v) + We * F00 + f0 * a0 - 1.0;
   r[1] = wd * (a1 - t0.t1.v) + We * F10 + f0 * a1;
   r[2] = wd * (a2 - t0.t2.v) + We * F11 + f0 * a2 - 1.0;
+  if constexpr (MP) {
+    const double c = We * 0.5 * (phi_def_of(u, p[P_LAMBDA_D]) - 1.0);
+    const double d00 = u.g00, d01 = 0.5 * (u.g01 + u.g10), d11 = u.g11;
+    r[0] -= c * 2.0 * (a0 * d00 + a1 * d01);
+    r[1] -= c * (a0 * d01 + a1 * (d00 + d11) + a2 * d01);
+    r[2] -= c * 2.0 * (a1 * d01 + a2 * d11);
+  }
 }
-struct C4_L_RES_ORTH {  // RHS of project(restau0 - res_test, Zc)  :468
+template <bool MP>
+struct C4_L_RES_ORTHT {  // RHS of project(restau0 - res_test, Zc)  :468
   using Space = SpZc; using Facet = NoFacet;
-  static constexpr int QDEG = 6, NP = 3;
+  static constexpr int QDEG = MP ? QD_MP_RES_ORTH : 6, NP = 3;
   FX_HD static void point(const PtArgs& x, double* d) {
-    jbp_restau(x, d);
+    jbp_restau<MP>(x, d);
     for (int j = 0; j < 3; ++j) d[j] -= eval_dg0(x.s.f[F_RES_TEST], x.m.dm[S_ZD], x.m.nc, x.cell, j);
   }
   template <class A> FX_HDC static void vterms(A& a, const double* d, const Par&) {
@@ -411,10 +483,15 @@ struct C4_L_RES_ORTH {  // RHS of project(restau0 - res_test, Zc)  :468
     a.template add<T2V>(d[2]);
   }
 };
-struct E_C4_RESTAU {  // project(restau0, Zd)  :467
-  static constexpr int QDEG = 4, NOUT = 3;
-  FX_HD static void value(const PtArgs& x, double* v) { jbp_restau(x, v); }
+using C4_L_RES_ORTH = C4_L_RES_ORTHT<false>;
+using C4M_L_RES_ORTH = C4_L_RES_ORTHT<true>;
+template <bool MP>
+struct E_C4_RESTAUT {  // project(restau0, Zd)  :467
+  static constexpr int QDEG = MP ? QD_MP_RESTAU : 4, NOUT = 3;
+  FX_HD static void value(const PtArgs& x, double* v) { jbp_restau<MP>(x, v); }
 };
+using E_C4_RESTAU = E_C4_RESTAUT<false>;
+using E_C4M_RESTAU = E_C4_RESTAUT<true>;
 
 // ---- post-loop adaptive-refinement indicator -------------------------------------
 // incompressible_benchmarkEWM.py:903-917, fenepmp_jbp.py:691-705, comp_ewm_jpb.py:735-747 (identical):
@@ -473,22 +550,27 @@ struct C4_EE {  // (fene_func(tau1,b)*(tau1[0,0]+tau1[1,1]) - 2.)*dx   :636
 };
 // journal load and torque on ds(0)  (:639-649): sigma = sigma_f(u1,p1,tau1), tang = (n1,-n0)
 //   WHICH 0: innertorque = -inner(n, sigma tang); 1: innerforcex = (1,0).(sigma n); 2: innerforcey = (0,-1).(sigma n)
-template <int WHICH>
+template <int WHICH, bool MP = false>
 struct C4_JOURNAL {
-  static constexpr int QDEG = 4, MARKERS = 1 << 0;
+  static constexpr int QDEG = MP ? 12 : 4, MARKERS = 1 << 0;
   FX_HD static double integrand(const PtArgs& x) {
     P2Phys b; P1Phys b1;
     p2_phys(x.xi, x.et, x.g, b);
     p1_phys(x.xi, x.et, x.g, b1);
     const Vel u = eval_vel(x.m, x.s.f[F_W1], x.cell, b);
     const Tau t = eval_tau(x.m, x.s.f[F_TAU1], x.cell, b);
-    const SigmaF s = sigma_f(u, eval_q(x.m, x.s.f[F_P1], x.cell, b1).v, t, x.p.v);
+    const SigmaF s = sigma_f(u, eval_q(x.m, x.s.f[F_P1], x.cell, b1).v, t, x.p.v,
+                             MP ? phi_def_of(u, x.p.v[P_LAMBDA_D]) : 1.0);
     const double n0 = x.nx, n1 = x.ny;
     if (WHICH == 0) return -(n0 * (s.s00 * n1 - s.s01 * n0) + n1 * (s.s01 * n1 - s.s11 * n0));
     if (WHICH == 1) return s.s00 * n0 + s.s01 * n1;
     return -(s.s01 * n0 + s.s11 * n1);
   }
 };
+
+using C4M_TORQUE = C4_JOURNAL<0, true>;
+using C4M_FORCE_X = C4_JOURNAL<1, true>;
+using C4M_FORCE_Y = C4_JOURNAL<2, true>;
 
 }  // namespace jbp
 }  // namespace fx

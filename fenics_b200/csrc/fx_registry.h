@@ -40,6 +40,7 @@
   X(FX_FORM_C4_A7, fx::jbp::C4_A7)          \
   X(FX_FORM_C4_A4, fx::jbp::C4_A4)          \
   X(FX_FORM_C4_A9, fx::jbp::C4_A9)          \
+  X(FX_FORM_C4M_A4, fx::jbp::C4M_A4)        \
   X(FX_FORM_C5_A0, fx::ldc::C2_A0)          \
   X(FX_FORM_C5_A1, fx::dgp::C5_A12<true>)   \
   X(FX_FORM_C5_A2, fx::dgp::C5_A12<false>)  \
@@ -92,6 +93,9 @@
   X(FX_FORM_C4_L4, fx::jbp::C4_L4)                          \
   X(FX_FORM_C4_L9, fx::jbp::C4_L9)                          \
   X(FX_FORM_C4_L_RES_ORTH, fx::jbp::C4_L_RES_ORTH)          \
+  X(FX_FORM_C4M_L2, fx::jbp::C4M_L2)                        \
+  X(FX_FORM_C4M_L9, fx::jbp::C4M_L9)                        \
+  X(FX_FORM_C4M_L_RES_ORTH, fx::jbp::C4M_L_RES_ORTH)        \
   X(FX_FORM_C5_L0, fx::ldc::C2_L0)                          \
   X(FX_FORM_C5_L1, fx::dgp::C5_L12<true>)                   \
   X(FX_FORM_C5_L2, fx::dgp::C5_L12<false>)                  \
@@ -134,6 +138,9 @@
   X(FX_FORM_C4_TORQUE, fx::jbp::C4_JOURNAL<0>)      \
   X(FX_FORM_C4_FORCE_X, fx::jbp::C4_JOURNAL<1>)     \
   X(FX_FORM_C4_FORCE_Y, fx::jbp::C4_JOURNAL<2>)     \
+  X(FX_FORM_C4M_TORQUE, fx::jbp::C4M_TORQUE)        \
+  X(FX_FORM_C4M_FORCE_X, fx::jbp::C4M_FORCE_X)      \
+  X(FX_FORM_C4M_FORCE_Y, fx::jbp::C4M_FORCE_Y)      \
   X(FX_FORM_C5_NUS, fx::dgp::C5_NUS)                \
   X(FX_FORM_C6_NUS, fx::dgp::C6_NUS)
 
@@ -147,7 +154,8 @@
   X(FX_EXPR_C6_RESTAU, fx::dgp::E_C6_RESTAU)      \
   X(FX_EXPR_ADAPT_RES_SQ, fx::jbp::E_ADAPT_RES_SQ) \
   X(FX_EXPR_TAU_AVG, fx::jbp::E_TAU_AVG)          \
-  X(FX_EXPR_ABS_KAPP_RATIO, fx::jbp::E_ABS_KAPP_RATIO)
+  X(FX_EXPR_ABS_KAPP_RATIO, fx::jbp::E_ABS_KAPP_RATIO) \
+  X(FX_EXPR_C4M_RESTAU, fx::jbp::E_C4M_RESTAU)
 
 namespace fx {
 template <class F> constexpr bool has_facet() { return F::Facet::present; }

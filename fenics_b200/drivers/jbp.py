@@ -32,15 +32,17 @@ def read_parameters(input_csv=None):
     return {r[0]: [float(x) for x in r[1:]] for r in rows}
 
 
-def sweep(params=None):
+def sweep(params=None, all_lambda=False):
     """(j, jjj) -> parameters of the script's primary (We) and secondary (Ma) loops
     (fenepmp_jbp.py:153-154, :291-297, :1080-1094): Re = re_row[2], We = we_row[j], Ma = ma_row[jjj+1],
-    lambda_D = lambda_row[1]."""
+    lambda_D = lambda_row[1].  all_lambda: the sweep once per value of the CSV's `Ld` row (0, 0.05, 0.1, 0.15 -- the
+    runs behind plot_data.py:38-47) instead of lambda_row[1] only."""
     p = params or CSV_DEFAULT
     out = []
-    for jjj in range(len(p["Ma"])):
-        for j in range(1, len(p["We"]) + 1):
-            out.append(dict(j=j, jjj=jjj, Re=p["Re"][1], We=p["We"][j - 1], Ma=p["Ma"][jjj], lambda_d=p["Ld"][0]))
+    for lam in (p["Ld"] if all_lambda else p["Ld"][:1]):
+        for jjj in range(len(p["Ma"])):
+            for j in range(1, len(p["We"]) + 1):
+                out.append(dict(j=j, jjj=jjj, Re=p["Re"][1], We=p["We"][j - 1], Ma=p["Ma"][jjj], lambda_d=lam))
     return out
 
 
@@ -52,8 +54,16 @@ class FenepmpJBP(_LDC):
     def __init__(self, mesh=None, dofmaps=None, dt=0.00125, Re=25.0, We=0.1, Ma=0.01, lambda_d=0.0, betav=0.5,
                  b=20.0, A_0=1.0, Di=0.005, Vh=0.0000069, Bi=0.2, T_0=300.0, T_h=350.0, th=1.0, conv=1.0,
                  x_1=-0.80, y_1=0.0, x_2=0.0, y_2=0.0, r_a=1.0, r_b=2.0, n_theta=96, n_r=24, device=None):
-        if lambda_d != 0.0:
-            raise NotImplementedError("FENE-P-MP kernels are written for lambda_D = 0 (the CSV default)")
+        # lambda_D != 0 (FENE-P-MP proper, CSV row `Ld`): the seven forms / one projection that carry phi_def(u) have
+        # FX_FORM_C4M_* functors (UFL degrees 13 / 13 / 14, ds 12); lambda_D = 0 folds phi_def to 1 as UFL does
+        mp = lambda_d != 0.0
+        A = abi
+        self.F_A4, self.F_L2, self.F_L9 = ((A.FX_FORM_C4M_A4, A.FX_FORM_C4M_L2, A.FX_FORM_C4M_L9) if mp else
+                                           (A.FX_FORM_C4_A4, A.FX_FORM_C4_L2, A.FX_FORM_C4_L9))
+        self.F_RES_ORTH = A.FX_FORM_C4M_L_RES_ORTH if mp else A.FX_FORM_C4_L_RES_ORTH
+        self.E_RESTAU = A.FX_EXPR_C4M_RESTAU if mp else A.FX_EXPR_C4_RESTAU
+        self.F_JOURNAL = ((A.FX_FORM_C4M_TORQUE, A.FX_FORM_C4M_FORCE_X, A.FX_FORM_C4M_FORCE_Y) if mp else
+                          (A.FX_FORM_C4_TORQUE, A.FX_FORM_C4_FORCE_X, A.FX_FORM_C4_FORCE_Y))
         if mesh is None:
             mesh = annulus_mesh(n_theta, n_r, x_1, y_1, r_a, x_2, y_2, r_b)
         # boundary_parts: journal omega0 -> 0, bearing omega1 -> 1  (:212-237)
@@ -67,7 +77,7 @@ class FenepmpJBP(_LDC):
         self.rho0, self.rho12, self.rho1 = (b_(s, F("Q")) for s in (abi.FX_F_RHO0, abi.FX_F_RHO12, abi.FX_F_RHO1))
         self.T0, self.T1 = b_(abi.FX_F_T0, F("Q")), b_(abi.FX_F_T1, F("Q"))
         f = self.pr.form
-        self.proj_res_orth = ConsistentProjection(f(abi.FX_FORM_MASS_ZC), f(abi.FX_FORM_C4_L_RES_ORTH))
+        self.proj_res_orth = ConsistentProjection(f(abi.FX_FORM_MASS_ZC), f(self.F_RES_ORTH))
         W, Q = self.S["W"], self.S["Q"]
         tt = self._bct = {"t": 0.0}
 
@@ -94,7 +104,7 @@ class FenepmpJBP(_LDC):
         """LPS indicator of the FENE residual (fenepmp_jbp.py:462-473); |kapp| = kapp (sqrt >= 0)."""
         e = self.pr.expr
         with self._phase("project_dg0:restau"):
-            project(e(abi.FX_EXPR_C4_RESTAU), self.S["Zd"], function=self.res_test)
+            project(e(self.E_RESTAU), self.S["Zd"], function=self.res_test)
         self._project_consistent(self.proj_res_orth, self.res_orth, self.AZ, self.bZ, "res_orth")
         with self._phase("project_dg0:kappa"):
             project(e(abi.FX_EXPR_RES_ORTH_SQ), self.S["Qt"], function=self.res_orth_norm_sq)
@@ -113,17 +123,16 @@ class FenepmpJBP(_LDC):
             self.tau0_vec.assign(self.tau1_vec)
         A = abi
         self._system("rho12", A.FX_FORM_C4_A0, A.FX_FORM_C4_L0, self.AQ, self.bQ, self.rho12, ())      # :501-510
-        self._system("us", A.FX_FORM_C4_A2, A.FX_FORM_C4_L2, self.AW, self.bW, self.ws, self.bcu)      # :513-531
+        self._system("us", A.FX_FORM_C4_A2, self.F_L2, self.AW, self.bW, self.ws, self.bcu)      # :513-531
         self._system("p", A.FX_FORM_C4_A5, A.FX_FORM_C4_L5, self.AQ, self.bQ, self.p1, (),
                      method=self.pressure_method, pc=self._pressure_pc())                                                       # :536-549
         self._system("rho1", A.FX_FORM_C4_A6, A.FX_FORM_C4_L6, self.AQ, self.bQ, self.rho1, ())        # :553-570
         self._system("u1", A.FX_FORM_C4_A7, A.FX_FORM_C4_L7, self.AW, self.bW, self.w1, self.bcu)      # :573-586
-        self._system("tau", A.FX_FORM_C4_A4, A.FX_FORM_C4_L4, self.AZ, self.bZ, self.tau1_vec, ())     # :595-611
-        self._system("T", A.FX_FORM_C4_A9, A.FX_FORM_C4_L9, self.AQ, self.bQ, self.T1, self.bcT)       # :615-629
+        self._system("tau", self.F_A4, A.FX_FORM_C4_L4, self.AZ, self.bZ, self.tau1_vec, ())     # :595-611
+        self._system("T", A.FX_FORM_C4_A9, self.F_L9, self.AQ, self.bQ, self.T1, self.bcT)       # :615-629
         f = self.pr.form
         with self._phase("functionals"):
-            for i, fid in enumerate((A.FX_FORM_C4_EK, A.FX_FORM_C4_EE, A.FX_FORM_C4_TORQUE, A.FX_FORM_C4_FORCE_X,
-                                     A.FX_FORM_C4_FORCE_Y)):                                            # :635-649
+            for i, fid in enumerate((A.FX_FORM_C4_EK, A.FX_FORM_C4_EE) + self.F_JOURNAL):               # :635-649
                 assemble_scalar_async(f(fid), self.scal, i)
         vals = self._finish_step()
         t_rec = self.t

@@ -30,7 +30,7 @@ def run_ensemble(members, run_member, rank=None, world=None):
     return [r for _, r in flat]
 
 
-def run_fenepmp_sweep(steps, input_csv=None, device=None, **driver_kw):
+def run_fenepmp_sweep(steps, input_csv=None, device=None, all_lambda=False, **driver_kw):
     """The config-4 ensemble: every (j, jjj) member of the We x Ma sweep for `steps` time steps; each result is
     the member's parameters plus its last diagnostics (chi = F_x/F_y is the script's stability measure, :768)."""
     from .drivers import jbp
@@ -43,7 +43,7 @@ def run_fenepmp_sweep(steps, input_csv=None, device=None, **driver_kw):
             out = drv.step()
         out = dict(out)
         out["chi"] = out["F_x"] / out["F_y"] if out["F_y"] != 0.0 else float("nan")
-        out.update(j=m["j"], jjj=m["jjj"], We=m["We"], Ma=m["Ma"], Re=m["Re"])
+        out.update(j=m["j"], jjj=m["jjj"], We=m["We"], Ma=m["Ma"], Re=m["Re"], lambda_d=m["lambda_d"])
         return out
 
-    return run_ensemble(jbp.sweep(jbp.read_parameters(input_csv)), run_member)
+    return run_ensemble(jbp.sweep(jbp.read_parameters(input_csv), all_lambda=all_lambda), run_member)

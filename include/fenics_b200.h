@@ -111,6 +111,11 @@ typedef enum {
   FX_FORM_C4_L_RES_ORTH,
   /* cfg4: functionals; torque / force_x / force_y are exterior-facet integrals over ds(0) (fenepmp_jbp.py:639-649) */
   FX_FORM_C4_EK = 440, FX_FORM_C4_EE, FX_FORM_C4_TORQUE, FX_FORM_C4_FORCE_X, FX_FORM_C4_FORCE_Y,
+  /* cfg4 with lambda_D != 0 (FENE-P-MP proper: phi_def(u) = 1 + (3 lambda_D I_3(D)/(I_2(D) + 1e-7))^2,
+   * fenics_base.py:287-291, used at fenepmp_jbp.py:464,519,597,615,639): the forms that carry phi_def -- UFL degrees
+   * 13 (A4, L2, L_RES_ORTH), 14 (L9), 12 (ds functionals), 11 (restau0 -> Zd); every other cfg4 form is unchanged.  FX_P_LAMBDA_D holds lambda_D. */
+  FX_FORM_C4M_A4 = 460, FX_FORM_C4M_L2, FX_FORM_C4M_L9, FX_FORM_C4M_L_RES_ORTH,
+  FX_FORM_C4M_TORQUE = 470, FX_FORM_C4M_FORCE_X, FX_FORM_C4M_FORCE_Y,
   /* cfg5 = buoyancy-driven-flow/compressible_dgp.py: bilinear */
   FX_FORM_C5_A0 = 500, FX_FORM_C5_A1, FX_FORM_C5_A2, FX_FORM_C5_A5, FX_FORM_C5_A6, FX_FORM_C5_A7, FX_FORM_C5_A4,
   FX_FORM_C5_A8,
@@ -140,7 +145,8 @@ typedef enum {
    * fenepmp_jbp.py:691-705, comp_ewm_jpb.py:735-747); refine() itself stays in dolfin                              */
   FX_EXPR_ADAPT_RES_SQ,     /* inner(restau0,restau0) -> Qt, restau0 = We/dt (tau1-tau0) + We Fdef(u1,tau1) + tau1 - I */
   FX_EXPR_TAU_AVG,          /* (tau1_vec[0]+tau1_vec[1]+tau1_vec[2])/3 -> Qt                */
-  FX_EXPR_ABS_KAPP_RATIO    /* |FX_F_KAPP / (FX_F_QT_A + FX_P_EPS)| -> Qt                   */
+  FX_EXPR_ABS_KAPP_RATIO,   /* |FX_F_KAPP / (FX_F_QT_A + FX_P_EPS)| -> Qt                   */
+  FX_EXPR_C4M_RESTAU        /* cfg4 restau0 with the lambda_D != 0 dissipation term -> Zd (fenepmp_jbp.py:462-467) */
 } fx_expr;
 
 typedef enum { FX_KSP_BICGSTAB = 0, FX_KSP_CG = 1, FX_KSP_GMRES = 2 } fx_ksp;

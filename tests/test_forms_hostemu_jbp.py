@@ -98,3 +98,60 @@ def test_adaptive_refinement_indicator_exprs():
     err = plan.project_dg0(abi.FX_EXPR_ABS_KAPP_RATIO, "Qt", st2, par2)
     assert lc.rel_err(err, ref["error_rat"]) < 1e-11
     assert ref["markers"].sum() in range(int(0.25 * len(kapp)), int(0.35 * len(kapp)) + 1)  # ratio 0.3 of the cells
+
+
+# ---- FENE-P-MP proper: lambda_D != 0 (fenics_base.py:287-291; fenepmp_jbp.py:464, 519, 597, 615, 639) -------------
+C4M_FORMS = dict(a4=(abi.FX_FORM_C4M_A4, "Zc"), L2=(abi.FX_FORM_C4M_L2, "W"), L9=(abi.FX_FORM_C4M_L9, "Q"))
+
+
+@pytest.mark.parametrize("shuffle,lam", [(False, 0.1), (True, 0.15), (False, 0.05)])
+def test_cfg4_forms_with_lambda_d(shuffle, lam):
+    """the forms that carry phi_def(u, lambda_D): the predictor right-hand side differentiates it (P2 Hessian of u0),
+    the stress matrix and the viscous heating use it pointwise; UFL degrees 13 / 13 / 14 asserted.  Every OTHER form
+    of the loop is independent of lambda_D: checked against the lambda_D != 0 oracle with the lambda_D = 0 ids."""
+    mesh, cfg, plan = _setup(shuffle=shuffle, lambda_d=lam)
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    assert par[abi.FX_P_LAMBDA_D] == lam
+    cfg0 = FenepmpJBP(mesh, dofmaps={k: s.cell_dofs for k, s in cfg.S.items()}, lambda_d=0.0)
+    for a in set(jb.FIELD_ATTR.values()):
+        getattr(cfg0, a).vec[:] = getattr(cfg, a).vec
+    want = dict(a4=13, L2=13, L9=14)
+    for name, (fid, space) in jb.C4_FORMS.items():
+        if name in C4M_FORMS:
+            fid = C4M_FORMS[name][0]
+        ref = fem.assemble(cfg.forms[name])
+        if name.startswith("a"):
+            err = lc.csr_rel_err(plan.assemble_matrix(fid, space, st, par), ref)
+        else:
+            err = lc.rel_err(plan.assemble_vector(fid, space, st, par), ref)
+        assert err < TOL, (name, err)
+        degs = {k: d for k, _, d in fem.quadrature_degrees(cfg.forms[name], mesh)}
+        q = plan.form_qdeg(fid)
+        assert q[0] == degs["dx"] and q[1] == degs.get("ds", -1), (name, q, degs)
+        if name in want:
+            assert q[0] == want[name]
+            ref0 = fem.assemble(cfg0.forms[name])   # ... and lambda_D really changes the form
+            a_, b_ = (ref.data, ref0.data) if name.startswith("a") else (ref, ref0)
+            assert lc.rel_err(a_, b_) > (1e-6 if name != "L9" else 1e-11), name  # L9: phi_def sits behind Vh = 6.9e-6
+
+
+def test_cfg4_lps_and_functionals_with_lambda_d():
+    mesh, cfg, plan = _setup(lambda_d=0.1)
+    st, par = jb.state_of(cfg), jb.params_of(cfg)
+    cfg.lps_indicator()
+    last = cfg.last
+    res_test = plan.project_dg0(abi.FX_EXPR_C4M_RESTAU, "Zd", st, par)
+    assert lc.rel_err(res_test, last["res_test"]) < TOL
+    st[abi.FX_F_RES_TEST] = res_test
+    b = plan.assemble_vector(abi.FX_FORM_C4M_L_RES_ORTH, "Zc", st, par)
+    M = plan.assemble_matrix(abi.FX_FORM_MASS_ZC, "Zc", st, par)
+    assert lc.rel_err(fem.solve_lu(M, b), last["res_orth"]) < 1e-10
+    assert plan.form_qdeg(abi.FX_FORM_C4M_L_RES_ORTH)[0] == 13
+    for fid, form in ((abi.FX_FORM_C4M_TORQUE, cfg.torque_form), (abi.FX_FORM_C4M_FORCE_X, cfg.force_x_form),
+                      (abi.FX_FORM_C4M_FORCE_Y, cfg.force_y_form)):
+        ref = fem.assemble(form)
+        got = plan.assemble_scalar(fid, st, par)
+        assert abs(got - ref) < 1e-11 * max(1.0, abs(ref)), (fid, got, ref)
+        degs = {k: d for k, _, d in fem.quadrature_degrees(form, mesh)}
+        q = plan.form_qdeg(fid)
+        assert (q[0], q[1]) == (-1, degs["ds"]) and degs["ds"] == 12, (fid, q, degs)

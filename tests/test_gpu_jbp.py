@@ -57,14 +57,56 @@ def test_cfg4_forms_and_functionals_match_oracle():
         assert np.array_equal(bo.dofs, bd.dofs)
 
 
-def test_cfg4_lambda_d_nonzero_is_rejected_loudly():
-    with pytest.raises(NotImplementedError):
-        jbp.FenepmpJBP(n_theta=8, n_r=2, lambda_d=0.05)
+def test_cfg4_lambda_d_folded_ids_reject_nonzero_lambda_d():
+    """FX_FORM_C4_* fold phi_def to 1 (lambda_D = 0, as UFL does): with lambda_D != 0 they refuse and name the
+    FX_FORM_C4M_* functors, which keep it"""
     _, drv = _pair(nt=8, nr=2)
     drv.pr.set_param(abi.FX_P_LAMBDA_D, 0.05)
-    with pytest.raises(Exception) as e:
-        dapi.assemble(drv.pr.form(abi.FX_FORM_C4_A4))
-    assert "lambda_D" in str(e.value)
+    for fid in (abi.FX_FORM_C4_A4, abi.FX_FORM_C4_L2, abi.FX_FORM_C4_L9):
+        with pytest.raises(Exception) as e:
+            dapi.assemble(drv.pr.form(fid))
+        assert "C4M" in str(e.value)
+    dapi.assemble(drv.pr.form(abi.FX_FORM_C4M_A4))
+    dapi.assemble(drv.pr.form(abi.FX_FORM_C4_A2))  # forms without phi_def do not care
+
+
+@pytest.mark.parametrize("lam", [0.1])
+def test_cfg4_forms_and_k_steps_with_lambda_d(lam):
+    """FENE-P-MP proper (lambda_D != 0, fenics_base.py:287-291): the phi_def forms on the GPU against the oracle
+    (1e-12, UFL degrees 13 / 13 / 14), then fields + journal load / torque after K steps (1e-8)."""
+    ocl, drv = _pair(nt=16, nr=4, lambda_d=lam, We=0.5)
+    jb.randomize(ocl)
+    _push(ocl, drv)
+    for name, fid in (("a4", abi.FX_FORM_C4M_A4), ("L2", abi.FX_FORM_C4M_L2), ("L9", abi.FX_FORM_C4M_L9)):
+        ref = fem.assemble(ocl.forms[name])
+        got = dapi.assemble(drv.pr.form(fid))
+        if name.startswith("a"):
+            assert lc.csr_rel_err(got.to_scipy(), ref) < 1e-12, name
+        else:
+            assert lc.rel_err(got.get_local(), ref) < 1e-12, name
+    for fid, form in ((abi.FX_FORM_C4M_TORQUE, ocl.torque_form), (abi.FX_FORM_C4M_FORCE_X, ocl.force_x_form)):
+        ref = fem.assemble(form)
+        assert abs(dapi.assemble(drv.pr.form(fid)) - ref) < 1e-11 * max(1.0, abs(ref))
+    K = 3
+    ocl, drv = _pair(nt=24, nr=6, lambda_d=lam, We=0.5)
+    drv.solve_rtol = 1e-13
+    drv.pressure_method = "cg"
+    ocl.t = drv.t = 0.45
+    for _ in range(K):
+        ro, rd = ocl.step(), drv.step()
+        for k in ("E_k", "torque", "F_x", "F_y"):
+            assert abs(ro[k] - rd[k]) < 1e-8 * max(abs(ro[k]), 1e-10), (k, ro[k], rd[k])
+    fo, fd = ocl.fields(), drv.fields()
+    for k in fo:
+        assert lc.rel_err(fd[k], fo[k]) < 1e-8, k
+    # and lambda_D matters: the same steps with lambda_D = 0 end elsewhere
+    _, d0 = _pair(nt=24, nr=6, lambda_d=0.0, We=0.5)
+    d0.solve_rtol = 1e-13
+    d0.pressure_method = "cg"
+    d0.t = 0.45
+    for _ in range(K):
+        d0.step()
+    assert lc.rel_err(d0.fields()["tau1"], fo["tau1"]) > 1e-7
 
 
 def test_cfg4_k_steps_match_oracle():
