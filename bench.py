@@ -508,6 +508,34 @@ def run_ours(args):
     roof["assembly_plus_solve"] = {"achieved": allb / (allms * 1e-3) / 1e9, "frac": allb / (allms * 1e-3) / 1e9 / peak,
                                    "frac_of_nominal_8000": allb / (allms * 1e-3) / 1e9 / 8000.0, "ms_per_step": allms,
                                    "kernels": sorted(groups)}
+    # north_star (1) "mesh colouring, or atomics where colouring loses": the atomic scatter-add against the
+    # deterministic atomic-free row gather (FX_ASM_DETERMINISTIC), same forms, same state, CUDA events over 10 launches
+    if cfg == "cfg2":
+        from fenics_b200 import _abi as abi
+        from fenics_b200 import dolfin_api as dapi
+        ab = {}
+        for sp_, fid, ten in (("W", abi.FX_FORM_C2_A1, drv.AW), ("Zc", abi.FX_FORM_C2_A4, drv.AZ), ("Q", abi.FX_FORM_C2_A5, drv.AQ)):
+            n_, nnz_ = pat[sp_]
+            ld = {"W": 15, "Zc": 18, "Q": 3}[sp_]
+            by = 8 * nnz_ + m.num_cells() * (48 + 8 * ld) + 8 * n_
+            row = {"alg_bytes": by}
+            for mode in ("atomic", "deterministic"):
+                drv.plan.set_assembly_mode(mode)
+                f_ = drv.pr.form(fid)
+                for _ in range(3):
+                    dapi.assemble(f_, tensor=ten)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(10):
+                    dapi.assemble(f_, tensor=ten)
+                a1.record()
+                torch.cuda.synchronize()
+                t_ = a0.elapsed_time(a1) / 10
+                row[mode] = {"ms": round(t_, 4), "achieved": round(by / (t_ * 1e-3) / 1e9, 1),
+                             "frac": round(by / (t_ * 1e-3) / 1e9 / peak, 3)}
+            ab[sp_] = row
+        drv.plan.set_assembly_mode("atomic")
+        roof["assembly_atomic_vs_deterministic"] = ab
     total_ms = sum(r_["ms"] for r_ in rows)
     share = {}
     for r_ in rows:

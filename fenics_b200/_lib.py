@@ -55,6 +55,7 @@ def _load():
         "fx_lincomb3_dev": (i, [i, vp, vp, vp, vp, vp, vp]),
         "fx_dotw_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
         "fx_plan_set_owned_cells": (i, [vp, i]),
+        "fx_plan_set_assembly_mode": (i, [vp, i]),
         "fx_plan_set_eliminated_dofs": (i, [vp, i, vp, i]),
         "fx_plan_set_aggregates": (i, [vp, i, vp, i]),
         "fx_peer_region_bytes": (C.c_longlong, [C.c_longlong]),

@@ -1,5 +1,7 @@
 // CUDA kernels for finite-element assembly (K1-K5 of SURVEY.md 2.3) and their launchers.
 // The element arithmetic lives in fx_assemble.h / fx_forms_*.h; this file is the thread mapping.
+#include <vector>
+
 #include "fx_plan.h"
 #include "fx_registry.h"
 
@@ -132,15 +134,92 @@ __global__ void __launch_bounds__(256) k_project_dg0(const __grid_constant__ Asm
   if (c < a.m.nc) cell_project_dg0<E>(a, c);
 }
 
+// ---- deterministic (atomic-free) assembly: gather of the element-tensor buffer ---------------------------------
+// one thread per CSR entry / dof; contributions listed in ascending cell order => bitwise reproducible sums
+__global__ void __launch_bounds__(256) k_gather_matrix(const int* __restrict__ cptr, const int* __restrict__ contrib,
+                                                       const double* __restrict__ elt, double* __restrict__ val, int nnz) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  double s = 0.0;
+  for (int k = cptr[j]; k < cptr[j + 1]; ++k) s += elt[contrib[k]];
+  val[j] = s;
+}
+__global__ void __launch_bounds__(256) k_gather_vector(const int* __restrict__ aptr, const int* __restrict__ adj,
+                                                       const double* __restrict__ elt, double* __restrict__ vec, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = aptr[i]; k < aptr[i + 1]; ++k) s += elt[adj[k]];
+  vec[i] = s;
+}
+
+// contribution lists of a space (once per plan) + the element-tensor buffer
+static int det_ensure(fx_plan* P, int space, bool matrix) {
+  DevPattern& d = P->sp[space];
+  const size_t need = (size_t)P->nc * d.ld * (matrix ? d.ld : 1);
+  if (P->elt_cap < need) {
+    cudaFree(P->elt);
+    P->elt = nullptr; P->elt_cap = 0;
+    FX_CUDA(cudaMalloc((void**)&P->elt, sizeof(double) * need));
+    P->elt_cap = need;
+  }
+  if (d.det_ready) return FX_OK;
+  const int nc = P->nc, ld = d.ld;
+  std::vector<int> dm((size_t)ld * nc);
+  FX_CUDA(cudaMemcpy(dm.data(), d.dm_t, sizeof(int) * dm.size(), cudaMemcpyDeviceToHost));
+  {  // dof -> (cell, local row) pairs, ascending cell
+    std::vector<int> aptr((size_t)d.n + 1, 0), adj((size_t)nc * ld);
+    for (size_t i = 0; i < dm.size(); ++i) ++aptr[dm[i] + 1];
+    for (int i = 0; i < d.n; ++i) aptr[i + 1] += aptr[i];
+    std::vector<int> fill(aptr.begin(), aptr.end() - 1);
+    for (int c = 0; c < nc; ++c)
+      for (int a = 0; a < ld; ++a) adj[fill[dm[(size_t)a * nc + c]]++] = c * ld + a;
+    FX_CUDA(cudaMalloc((void**)&d.det_aptr, sizeof(int) * aptr.size()));
+    FX_CUDA(cudaMalloc((void**)&d.det_adj, sizeof(int) * adj.size()));
+    FX_CUDA(cudaMemcpy(d.det_aptr, aptr.data(), sizeof(int) * aptr.size(), cudaMemcpyHostToDevice));
+    FX_CUDA(cudaMemcpy(d.det_adj, adj.data(), sizeof(int) * adj.size(), cudaMemcpyHostToDevice));
+  }
+  if (d.has_csr) {  // CSR entry -> positions in the [cell][row][col] buffer, ascending cell
+    if ((size_t)nc * ld * ld > 2147483647u) return set_error(FX_ERR_UNSUPPORTED, "deterministic assembly: mesh too large for int32 indices");
+    std::vector<int> rowptr((size_t)d.n + 1);
+    std::vector<uint8_t> pos((size_t)nc * ld * ld);
+    FX_CUDA(cudaMemcpy(rowptr.data(), d.rowptr, sizeof(int) * rowptr.size(), cudaMemcpyDeviceToHost));
+    FX_CUDA(cudaMemcpy(pos.data(), d.pos, pos.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> cptr((size_t)d.nnz + 1, 0), contrib((size_t)nc * ld * ld);
+    auto entry = [&](int c, int a, int b) { return rowptr[dm[(size_t)a * nc + c]] + pos[((size_t)a * ld + b) * nc + c]; };
+    for (int c = 0; c < nc; ++c)
+      for (int a = 0; a < ld; ++a)
+        for (int b = 0; b < ld; ++b) ++cptr[entry(c, a, b) + 1];
+    for (int j = 0; j < d.nnz; ++j) cptr[j + 1] += cptr[j];
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int c = 0; c < nc; ++c)
+      for (int a = 0; a < ld; ++a)
+        for (int b = 0; b < ld; ++b) contrib[fill[entry(c, a, b)]++] = (c * ld + a) * ld + b;
+    FX_CUDA(cudaMalloc((void**)&d.det_cptr, sizeof(int) * cptr.size()));
+    FX_CUDA(cudaMalloc((void**)&d.det_contrib, sizeof(int) * contrib.size()));
+    FX_CUDA(cudaMemcpy(d.det_cptr, cptr.data(), sizeof(int) * cptr.size(), cudaMemcpyHostToDevice));
+    FX_CUDA(cudaMemcpy(d.det_contrib, contrib.data(), sizeof(int) * contrib.size(), cudaMemcpyHostToDevice));
+  }
+  d.det_ready = true;
+  return FX_OK;
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
 template <class F>
 static int run_matrix(fx_plan* P, AsmArgs a, cudaStream_t st) {
   using Sp = typename F::Space;
-  const DevPattern& pat = P->sp[space_id<Sp>::v];
+  DevPattern& pat = P->sp[space_id<Sp>::v];
   if (!pat.has_csr) return set_error(FX_ERR_ARG, "space %d has no dofmap/pattern in this plan", space_id<Sp>::v);
   a.rowptr = pat.rowptr;
   a.pos = pat.pos;
-  FX_CUDA(cudaMemsetAsync(a.val, 0, sizeof(double) * (size_t)pat.nnz, st));
+  a.elt = nullptr;
+  const bool det = P->asm_mode == FX_ASM_DETERMINISTIC;
+  if (det) {
+    if (int rc = det_ensure(P, space_id<Sp>::v, true)) return rc;
+    a.elt = P->elt;
+  } else {
+    FX_CUDA(cudaMemsetAsync(a.val, 0, sizeof(double) * (size_t)pat.nnz, st));
+  }
   constexpr int NQ = tri_npts(F::QDEG);
   constexpr size_t smem = sizeof(double) * (size_t)F::NP * NQ * CB;
   static bool attr_done = false;
@@ -158,6 +237,10 @@ static int run_matrix(fx_plan* P, AsmArgs a, cudaStream_t st) {
       count_launch(1);
     }
   }
+  if (det) {
+    k_gather_matrix<<<(pat.nnz + 255) / 256, 256, 0, st>>>(pat.det_cptr, pat.det_contrib, P->elt, a.val, pat.nnz);
+    count_launch(1);
+  }
   FX_CUDA(cudaGetLastError());
   return FX_OK;
 }
@@ -165,9 +248,17 @@ static int run_matrix(fx_plan* P, AsmArgs a, cudaStream_t st) {
 template <class F>
 static int run_vector(fx_plan* P, AsmArgs a, cudaStream_t st) {
   using Sp = typename F::Space;
-  const DevPattern& pat = P->sp[space_id<Sp>::v];
+  DevPattern& pat = P->sp[space_id<Sp>::v];
   if (!pat.present) return set_error(FX_ERR_ARG, "space %d has no dofmap in this plan", space_id<Sp>::v);
-  FX_CUDA(cudaMemsetAsync(a.vec, 0, sizeof(double) * (size_t)pat.n, st));
+  a.elt = nullptr;
+  const bool det = P->asm_mode == FX_ASM_DETERMINISTIC;
+  double* out = a.vec;
+  if (det) {
+    if (int rc = det_ensure(P, space_id<Sp>::v, false)) return rc;
+    a.elt = P->elt;
+  } else {
+    FX_CUDA(cudaMemsetAsync(a.vec, 0, sizeof(double) * (size_t)pat.n, st));
+  }
   constexpr int NQ = tri_npts(F::QDEG);
   constexpr size_t smem = sizeof(double) * (size_t)F::NP * NQ * CB;
   static bool attr_done = false;
@@ -184,6 +275,10 @@ static int run_vector(fx_plan* P, AsmArgs a, cudaStream_t st) {
       k_facet_vector<F><<<(n + 127) / 128, 128, 0, st>>>(a);
       count_launch(1);
     }
+  }
+  if (det) {
+    k_gather_vector<<<(pat.n + 255) / 256, 256, 0, st>>>(pat.det_aptr, pat.det_adj, P->elt, out, pat.n);
+    count_launch(1);
   }
   FX_CUDA(cudaGetLastError());
   return FX_OK;

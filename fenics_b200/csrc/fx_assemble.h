@@ -37,6 +37,10 @@ struct MeshView {
   const int* bf_local = nullptr;
   const int* bf_marker = nullptr;
   const double* bf_geo = nullptr;  // [3][nbf]: nx, ny, length
+  // boundary facets chained per cell (deterministic assembly): bf_first[f] != 0 for the lowest facet of its cell,
+  // bf_next[f] = the cell's next boundary facet or -1
+  const unsigned char* bf_first = nullptr;
+  const int* bf_next = nullptr;
 };
 struct State {
   const double* f[NFIELDS];
@@ -61,6 +65,10 @@ struct AsmArgs {
   // vector / scalar output
   double* vec;
   double* part;  // per-block partial sums (functionals)
+  // deterministic (atomic-free) assembly: non-null => the kernels store every element-tensor row / entry here
+  // ([cell][row][col] resp. [cell][row]) instead of scatter-adding it; k_gather_* then sum the contributions of each
+  // CSR entry / dof in a fixed order (ascending cell)
+  double* elt;
   int marker_mask;  // unused (facet functors carry their own MARKERS mask)
   int nc_owned;     // functionals: integrate over cells [0, nc_owned) only (partitioned mode)
 };
@@ -314,7 +322,11 @@ FX_HD void mat_rows(const AsmArgs& a, int cell0, int lane, int k, const double* 
   }
   // scatter only the entries this form can make non-zero (the values buffer was zeroed): the rest of
   // DOLFIN's cell-block pattern stays an explicit 0.0, exactly as after PETSc ADD_VALUES of zeros
-  {
+  if (a.elt != nullptr) {  // deterministic mode: the whole row (structural zeros included), gathered later
+    double* dst = a.elt + ((long)cell * Sp::LD + Sp::off(I) + k) * Sp::LD;
+#pragma unroll
+    for (int b = 0; b < Sp::LD; ++b) dst[b] = acc[b];
+  } else {
     const long nc = a.m.nc;
     const int arow = Sp::off(I) + k;
     const int r = a.m.dm[space_id<Sp>::v][arow * nc + cell];
@@ -350,6 +362,10 @@ FX_HD void vec_rows(const AsmArgs& a, int cell0, int lane, int k, const double* 
     for (int j = 0; j < F::NP; ++j) d[j] = smem[(j * NQ + q) * CB + lane];
     sum += vec_qp<F, I>(g, k, xi, et, w * g.adet, d, a.p);
   }
+  if (a.elt != nullptr) {
+    a.elt[(long)cell * Sp::LD + Sp::off(I) + k] = sum;
+    return;
+  }
   const int r = a.m.dm[space_id<Sp>::v][(long)(Sp::off(I) + k) * a.m.nc + cell];
   atomic_add(a.vec + r, sum);
 }
@@ -364,18 +380,17 @@ FX_HD void facet_ref_point(int lf, double s, double& xi, double& et) {
   et = ay * (1.0 - s) + by * s;
 }
 
+// adds row `arow` of facet f's element tensor to acc; false when the facet's marker is not integrated over
 template <class F>
-FX_HD void facet_mat_row(const AsmArgs& a, int f, int arow) {
+FX_HD bool facet_mat_row_acc(const AsmArgs& a, int f, int arow, double* acc) {
   using Sp = typename F::Space;
   using FF = typename F::Facet;
   constexpr int NQ = seg_npts(FF::QDEG);
   const int marker = a.m.bf_marker[f];
-  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return;  // ds(i) vs ds
+  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return false;  // ds(i) vs ds
   const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
   const Geo g = load_geo(a.m, cell);
   const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
-  double acc[Sp::LD];
-  for (int b = 0; b < Sp::LD; ++b) acc[b] = 0.0;
   const int I = Sp::dof_comp(arow);
   for (int q = 0; q < NQ; ++q) {
     double s, w, xi, et;
@@ -388,16 +403,33 @@ FX_HD void facet_mat_row(const AsmArgs& a, int f, int arow) {
       if (I == II) row_qp<FF, II>(g, arow - Sp::off(II), xi, et, w * len, d, a.p, acc);
     });
   }
-  scatter_row<Sp>(a, cell, arow, acc);
+  return true;
+}
+template <class F>
+FX_HD void facet_mat_row(const AsmArgs& a, int f, int arow) {
+  using Sp = typename F::Space;
+  double acc[Sp::LD];
+  for (int b = 0; b < Sp::LD; ++b) acc[b] = 0.0;
+  if (a.elt != nullptr) {  // deterministic mode: the cell's lowest facet adds ALL of the cell's facets, in order
+    if (!a.m.bf_first[f]) return;
+    bool any = false;
+    for (int g = f; g >= 0; g = a.m.bf_next[g]) any |= facet_mat_row_acc<F>(a, g, arow, acc);
+    if (!any) return;
+    double* dst = a.elt + ((long)a.m.bf_cell[f] * Sp::LD + arow) * Sp::LD;
+    for (int b = 0; b < Sp::LD; ++b) dst[b] += acc[b];
+    return;
+  }
+  if (facet_mat_row_acc<F>(a, f, arow, acc)) scatter_row<Sp>(a, a.m.bf_cell[f], arow, acc);
 }
 
+// value of facet f's contribution to entry `arow` of the element vector (0 when the marker is not integrated over)
 template <class F>
-FX_HD void facet_vec_row(const AsmArgs& a, int f, int arow) {
+FX_HD double facet_vec_row_val(const AsmArgs& a, int f, int arow) {
   using Sp = typename F::Space;
   using FF = typename F::Facet;
   constexpr int NQ = seg_npts(FF::QDEG);
   const int marker = a.m.bf_marker[f];
-  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return;  // ds(i) vs ds
+  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return 0.0;  // ds(i) vs ds
   const int cell = a.m.bf_cell[f], lf = a.m.bf_local[f];
   const Geo g = load_geo(a.m, cell);
   const double nx = a.m.bf_geo[f], ny = a.m.bf_geo[a.m.nbf + f], len = a.m.bf_geo[2 * a.m.nbf + f];
@@ -414,8 +446,24 @@ FX_HD void facet_vec_row(const AsmArgs& a, int f, int arow) {
       if (I == II) sum += vec_qp<FF, II>(g, arow - Sp::off(II), xi, et, w * len, d, a.p);
     });
   }
+  return sum;
+}
+template <class F>
+FX_HD void facet_vec_row(const AsmArgs& a, int f, int arow) {
+  using Sp = typename F::Space;
+  using FF = typename F::Facet;
+  const int cell = a.m.bf_cell[f];
+  if (a.elt != nullptr) {
+    if (!a.m.bf_first[f]) return;
+    double sum = 0.0;
+    for (int g = f; g >= 0; g = a.m.bf_next[g]) sum += facet_vec_row_val<F>(a, g, arow);
+    a.elt[(long)cell * Sp::LD + arow] += sum;
+    return;
+  }
+  const int marker = a.m.bf_marker[f];
+  if (FF::MARKERS != -1 && !((FF::MARKERS >> marker) & 1)) return;
   const int r = a.m.dm[space_id<Sp>::v][(long)arow * a.m.nc + cell];
-  atomic_add(a.vec + r, sum);
+  atomic_add(a.vec + r, facet_vec_row_val<F>(a, f, arow));
 }
 
 // ---- functionals and DG0 projections: one thread per cell ---------------------------------------

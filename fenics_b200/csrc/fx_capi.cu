@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/fenics_b200.h + plan construction.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "fx_plan.h"
@@ -100,6 +101,18 @@ int fx_plan_create(const double* xy, int nv, const int* cells, int nc, const int
   if ((rc = upload(&P->bf_cell, bfacet_cell, (size_t)nbf))) return fail(rc);
   if ((rc = upload(&P->bf_local, bfacet_local, (size_t)nbf))) return fail(rc);
   if ((rc = upload(&P->bf_marker, bfacet_marker, (size_t)nbf))) return fail(rc);
+  {  // boundary facets of one cell chained in ascending facet order (deterministic facet integrals)
+    std::vector<unsigned char> first((size_t)nbf, 1);
+    std::vector<int> next((size_t)nbf, -1), last((size_t)nc, -1);
+    for (int f = 0; f < nbf; ++f) {
+      const int c = bfacet_cell[f];
+      if (last[c] >= 0) { next[last[c]] = f; first[f] = 0; }
+      last[c] = f;
+    }
+    if ((rc = upload(&P->bf_first, first.data(), (size_t)nbf))) return fail(rc);
+    if ((rc = upload(&P->bf_next, next.data(), (size_t)nbf))) return fail(rc);
+  }
+  if (const char* e = getenv("FX_ASM_MODE")) P->asm_mode = atoi(e) ? 1 : 0;
   if (cudaMalloc((void**)&P->geom, sizeof(double) * 6 * (size_t)nc) != cudaSuccess ||
       cudaMalloc((void**)&P->bf_geo, sizeof(double) * (3 * (size_t)nbf + 1)) != cudaSuccess)
     return fail(set_error(FX_ERR_CUDA, "cudaMalloc geometry failed"));
@@ -168,8 +181,9 @@ void fx_plan_destroy(fx_plan* P) {
     cudaFree(P->sp[s].elim); cudaFree(P->sp[s].elim_rows); cudaFree(P->sp[s].agg);
     cudaFree(P->sp[s].s_first); cudaFree(P->sp[s].s_peer); cudaFree(P->sp[s].s_local); cudaFree(P->sp[s].s_remote);
     P->sp[s].nb.release();
+    cudaFree(P->sp[s].det_cptr); cudaFree(P->sp[s].det_contrib); cudaFree(P->sp[s].det_aptr); cudaFree(P->sp[s].det_adj);
   }
-  cudaFree(P->nbval);
+  cudaFree(P->nbval); cudaFree(P->elt); cudaFree(P->bf_first); cudaFree(P->bf_next);
   cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->rowpre); cudaFree(P->nblk); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->gmres_basis); cudaFree(P->red_big);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
@@ -311,6 +325,13 @@ int fx_dotw_dev(fx_plan* P, int n, const double* x, const double* y, const doubl
                 void* stream) {
   if (!P || n < 0 || !x || !y || !w || !out_dev) return set_error(FX_ERR_ARG, "fx_dotw_dev: bad argument");
   return la_dotw(P, n, x, y, w, out_dev, (cudaStream_t)stream);
+}
+
+int fx_plan_set_assembly_mode(fx_plan* P, int mode) {
+  if (!P || (mode != FX_ASM_ATOMIC && mode != FX_ASM_DETERMINISTIC))
+    return set_error(FX_ERR_ARG, "fx_plan_set_assembly_mode: bad argument");
+  P->asm_mode = mode;
+  return FX_OK;
 }
 
 int fx_plan_set_owned_cells(fx_plan* P, int nc_owned) {

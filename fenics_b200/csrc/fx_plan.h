@@ -48,6 +48,11 @@ struct DevPattern {
   bool has_halo = false;
   int nsend = 0;
   int *s_first = nullptr, *s_peer = nullptr, *s_local = nullptr, *s_remote = nullptr;
+  // deterministic (atomic-free) assembly, built lazily by det_ensure(): contributions of every CSR entry / dof as
+  // indices into the element-tensor buffer, ascending in the cell index
+  int *det_cptr = nullptr, *det_contrib = nullptr;  // [nnz + 1], [nc * ld * ld]   (matrix spaces)
+  int *det_aptr = nullptr, *det_adj = nullptr;      // [n + 1],   [nc * ld]
+  bool det_ready = false;
   // node-block solver layout (fx_nb_host.h), built lazily at the first solve that can use it and dropped whenever
   // the row masks change; state 0 = not built yet, 1 = ready, -1 = the space has no usable node-block structure
   struct NbDev {
@@ -130,6 +135,11 @@ struct fx_plan {
   double* gmres_basis = nullptr;                // GMRES Krylov basis, (restart + 1) x n, allocated on first use
   size_t gmres_cap = 0;
   double* red_big = nullptr;                    // GMRES: block partials of the Gram-Schmidt coefficients
+  int asm_mode = 0;                             // 0: atomic scatter-add (default), 1: deterministic row gather
+  double* elt = nullptr;                        // element-tensor buffer of the deterministic mode, elt_cap doubles
+  size_t elt_cap = 0;
+  unsigned char* bf_first = nullptr;            // boundary facets chained per cell (deterministic facet integrals)
+  int* bf_next = nullptr;
   double* nbval = nullptr;                      // node-block value buffer (gathered inside every solve), nbval_cap doubles
   size_t nbval_cap = 0;
   fx::DistDev dist;                             // world > 1: mesh-partitioned run (fx_plan_set_peer_regions)
@@ -139,6 +149,7 @@ struct fx_plan {
     m.nc = nc; m.geom = geom;
     for (int s = 0; s < fx::S_N; ++s) m.dm[s] = sp[s].dm_t;
     m.nbf = nbf; m.bf_cell = bf_cell; m.bf_local = bf_local; m.bf_marker = bf_marker; m.bf_geo = bf_geo;
+    m.bf_first = bf_first; m.bf_next = bf_next;
     return m;
   }
 };

@@ -97,6 +97,12 @@ class Plan:
         m = np.ascontiguousarray(markers, dtype=np.int32)
         check(lib.fx_plan_set_markers(self.h, m.ctypes.data, len(m)))
 
+    def set_assembly_mode(self, mode):
+        """"atomic" (default: fp64 atomicAdd scatter) or "deterministic" (atomic-free row gather, bitwise
+        reproducible): how assemble() adds element tensors into the global tensor (fx_plan_set_assembly_mode)."""
+        m = {"atomic": abi.FX_ASM_ATOMIC, "deterministic": abi.FX_ASM_DETERMINISTIC}[mode]
+        check(lib.fx_plan_set_assembly_mode(self.h, m))
+
     def set_eliminated_dofs(self, space, rows):
         """Krylov solves on `space` iterate on the other rows and back-substitute these (block-triangular
         systems, fx_plan_set_eliminated_dofs); an empty list switches it off."""

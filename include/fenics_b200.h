@@ -266,6 +266,18 @@ int fx_plan_set_eliminated_dofs(fx_plan* plan, int space, const int* rows, int n
  * FX_ERR_UNSUPPORTED (and leaves the space without aggregates) when k is out of range.  k = 0 removes them. */
 int fx_plan_set_aggregates(fx_plan* plan, int space, const int* agg, int k);
 
+/* How fx_assemble_matrix / fx_assemble_vector add the element tensors into the global tensor
+ * (north_star (1): "mesh colouring, or atomics where colouring loses"):
+ *   FX_ASM_ATOMIC         fp64 atomicAdd scatter through the uint8 position map (default; the sum order, and with it
+ *                         the last bits of the result, vary from run to run)
+ *   FX_ASM_DETERMINISTIC  atomic-free: the element kernels store every element-tensor row into a buffer, a gather
+ *                         kernel then sums the contributions of each CSR entry / dof in ascending cell order (facet
+ *                         integrals are folded into their cell's row first) -- bitwise reproducible, every value
+ *                         written exactly once (no memset).  The environment variable FX_ASM_MODE=1 makes it the
+ *                         default of new plans (bench.py A/B).                                                  */
+typedef enum { FX_ASM_ATOMIC = 0, FX_ASM_DETERMINISTIC = 1 } fx_asm_mode;
+int fx_plan_set_assembly_mode(fx_plan* plan, int mode);
+
 /* ---- mesh-partitioned runs: one process per GPU, one plan per sub-mesh ---------------
  * The partitioned analogue of what PETSc's MPI Mat/Vec + VecScatter do under dolfin's solve() when the
  * reference is run with mpirun, re-designed for NVLink peer memory: every rank owns a

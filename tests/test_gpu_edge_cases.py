@@ -150,3 +150,44 @@ def test_vector_setitem_honours_the_key_and_pc_names_are_substituted_loudly():
         la.parameters["preconditioner_substitution"] = "warn"
     with pytest.raises(ValueError):
         la.krylov_solve(A, la.Vector(drv.plan, "Q"), b, "bicgstab", "nonsense")
+
+
+def test_deterministic_assembly_is_bitwise_reproducible_and_equals_the_atomic_sum():
+    """FX_ASM_DETERMINISTIC (atomic-free row gather): the same matrix / vector bits on every run, equal to the atomic
+    scatter-add to rounding (1e-13), facet integrals included (cfg2 L1/L2 carry ds terms; cfg5 has ds(i) matrices)."""
+    from fenics_b200 import dolfin_api as dapi, mesh as pmesh
+    from fenics_b200 import _abi as abi
+    from fenics_b200.drivers import dgp, ldc
+    import fxt_common as lc
+    for drv, forms in ((ldc.CompLDC(pmesh.Skew_Mesh(14, 1, 1)),
+                        (abi.FX_FORM_C2_A1, abi.FX_FORM_C2_A4, abi.FX_FORM_C2_A5, abi.FX_FORM_C2_L1, abi.FX_FORM_C2_L4,
+                         abi.FX_FORM_C2_L5)),
+                       (dgp.IncompDGP(mesh_resolution=12),
+                        (abi.FX_FORM_C6_A1, abi.FX_FORM_C6_A8, abi.FX_FORM_C6_L1, abi.FX_FORM_C6_L8))):
+        rng = np.random.default_rng(4)
+        for fn in drv.pr.fields.values():
+            v = fn.vector()
+            v.set_local(rng.standard_normal(v.size()) * 0.3 + 1.0)
+        for fid in forms:
+            drv.plan.set_assembly_mode("atomic")
+            ref = dapi.assemble(drv.pr.form(fid))
+            ref = (ref.val if hasattr(ref, "val") else ref.t).clone()
+            drv.plan.set_assembly_mode("deterministic")
+            runs = []
+            for _ in range(3):
+                got = dapi.assemble(drv.pr.form(fid))
+                runs.append((got.val if hasattr(got, "val") else got.t).clone())
+            assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2]), fid
+            assert lc.rel_err(runs[0].cpu().numpy(), ref.cpu().numpy()) < 1e-13, fid
+        drv.plan.set_assembly_mode("atomic")
+    # a whole time step in deterministic mode stays on the oracle-checked trajectory
+    d1, d2 = ldc.CompLDC(pmesh.Skew_Mesh(10, 1, 1)), ldc.CompLDC(pmesh.Skew_Mesh(10, 1, 1))
+    d2.plan.set_assembly_mode("deterministic")
+    for d in (d1, d2):
+        d.t = 0.45
+        d.solve_rtol = 1e-13
+        for _ in range(2):
+            d.step()
+    f1, f2 = d1.fields(), d2.fields()
+    for k in f1:
+        assert lc.rel_err(f2[k], f1[k]) < 1e-9, k
