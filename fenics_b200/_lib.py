@@ -56,6 +56,8 @@ def _load():
         "fx_dotw_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
         "fx_plan_set_owned_cells": (i, [vp, i]),
         "fx_plan_set_assembly_mode": (i, [vp, i]),
+        "fx_space_solver_index": (i, [vp, i, vp, ip]),
+        "fx_plan_set_halo_solver_index": (i, [vp, i, i, vp]),
         "fx_plan_set_eliminated_dofs": (i, [vp, i, vp, i]),
         "fx_plan_set_aggregates": (i, [vp, i, vp, i]),
         "fx_peer_region_bytes": (C.c_longlong, [C.c_longlong]),

@@ -402,6 +402,7 @@ int fx_plan_set_halo(fx_plan* P, int space, int nsend, const int* peer, const in
   d.s_first = d.s_peer = d.s_local = d.s_remote = nullptr;
   d.nsend = 0; d.has_halo = false;
   d.halo_h.clear();
+  d.halo_order.clear(); d.halo_first_h.clear(); d.halo_remote_int.clear();
   if (!ghost) return rebuild_mask(d);  // halo removed
   std::vector<uint8_t> m((size_t)d.n, 0);
   for (int i = 0; i < d.n; ++i) m[i] = ghost[i] ? 2 : 0;
@@ -433,7 +434,35 @@ int fx_plan_set_halo(fx_plan* P, int space, int nsend, const int* peer, const in
   }
   d.nsend = nsend; d.has_halo = true;
   d.halo_h.swap(m);
+  d.halo_order = order;
+  d.halo_first_h = first;
   return rebuild_mask(d);
+}
+
+int fx_space_solver_index(fx_plan* P, int space, int* int_of_ext, int* n_internal) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_csr || !int_of_ext)
+    return set_error(FX_ERR_ARG, "fx_space_solver_index: bad argument");
+  int rc = nb_ensure(P, space);
+  if (rc) return rc;
+  DevPattern& d = P->sp[space];
+  if (d.nb.state != 1)
+    return set_error(FX_ERR_UNSUPPORTED, "space %d has no node-block solver layout (%s)", space, d.nb.why.c_str());
+  std::memcpy(int_of_ext, d.nb.int_of_ext_h.data(), sizeof(int) * (size_t)d.n);
+  if (n_internal) *n_internal = d.nb.N;
+  return FX_OK;
+}
+
+int fx_plan_set_halo_solver_index(fx_plan* P, int space, int nsend, const int* remote_internal) {
+  if (!P || space < 0 || space >= S_N || !P->sp[space].has_halo || nsend != P->sp[space].nsend ||
+      (nsend > 0 && !remote_internal))
+    return set_error(FX_ERR_ARG, "fx_plan_set_halo_solver_index: bad argument (call fx_plan_set_halo first)");
+  DevPattern& d = P->sp[space];
+  d.halo_remote_int.assign(remote_internal, remote_internal + nsend);
+  for (int k = 0; k < nsend; ++k)
+    if (remote_internal[k] < 0) return set_error(FX_ERR_ARG, "fx_plan_set_halo_solver_index: pair %d has no internal index", k);
+  int rc = nb_ensure(P, space);
+  if (rc) return rc;
+  return nb_attach_halo(P, space);
 }
 
 int fx_solve_results(fx_plan* P, int first, int count, fx_solve_info* info, void* stream) {

@@ -401,16 +401,33 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bicgstab(const __gr
 // bs x bs node block, one aligned x-gather per block), and the set-up is a plain value gather -- no compaction scans.
 // x is permuted in at the start and out at every exit; eliminated rows (W's DG0 DEVSS rows) never enter the internal
 // vectors and are recovered by leave()'s back-substitution on the external arrays.
-template <int BS, bool DUAL>
+// DIST: mesh-partitioned run -- ghost block rows are empty, the owner of an interface entry of p / s stores it straight
+// into the ghost slot of every neighbour's copy (P2P, internal indices exchanged at set-up: fx_plan_set_halo_solver_index),
+// and every grid barrier closes across the GPUs (GridBarT<true>), exactly as in k_bicgstab<.., DIST>.
+template <int BS, bool DUAL, bool DIST>
 __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_constant__ KArgs a) {
   constexpr int BP = nb_bp(BS);
   __shared__ double sh[5 * 32];
   extern __shared__ __align__(16) double prod_all[];
   const NbView& B = a.nb;
   const int N = B.N;
-  const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+  static_assert(!(DIST && DUAL), "the partitioned kernel keeps the s vector (its interface entries are pushed)");
+  const size_t ld = DIST ? (size_t)a.dd.nmax : (((size_t)N + 3) & ~(size_t)3);
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
+  const unsigned char* mk = DIST ? B.imask : nullptr;
+  auto ghost = [&](int i) { return DIST && (mk[i] & MASK_GHOST); };
+  auto push = [&](int j, int i, double val) {  // interface entry i of work vector j -> the neighbours' ghost slots
+    if (DIST && (mk[i] & MASK_IFACE)) {
+      int q = B.s_first[i];
+      for (;;) {
+        const int pe = a.dd.s_peer[q];
+        a.dd.region[pe & (DIST_MAXW - 1)][(long long)j * a.dd.nmax + B.s_remote[q]] = val;
+        if (pe & DIST_LAST) break;
+        ++q;
+      }
+    }
+  };
   double* r = a.w;
   double* rh = a.w + ld;
   double* p = a.w + 2 * ld;
@@ -431,15 +448,21 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   }
   const unsigned long long pol = nb_make_policy(B.l2policy);
   int phase = 0;
-  GridBar bar;
-  bar.init(a.bar);
+  __shared__ double sh_x[DIST ? DIST_MAXW * RED_SLOTS : 1];
+  GridBarT<DIST> bar;
+  bar.init(a.bar, &a.dd, sh_x);
   auto out = [&](int it, int conv, double rn, double bn) {  // every exit: x back to the external numbering
     for (int i = i0 + lane; i < i1; i += 32) {
       const int e = B.ext_of_int[i];
-      if (e >= 0) a.x[e] = xi[i];
+      if (e >= 0 && !ghost(i)) a.x[e] = xi[i];
     }
     leave(bar, a, it, conv, rn, bn);
   };
+#define NB_GSUM(NV, PUSHED, v)                                             \
+  do {                                                                     \
+    if constexpr (DIST) gsum<NV, PUSHED>(a, bar, v, phase, sh);            \
+    else grid_sum_fast<NV>(bar, v, a.red, phase, sh);                      \
+  } while (0)
   double acc[3] = {0.0, 0.0, 0.0};
   acc[2] = (double)nb_gather_values(B, a.A.val);
   for (int i = gt; i < N; i += gs) {
@@ -454,11 +477,12 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
               },
               [&](int i, double ax, const Ops2& o) {
                 const double ri = o.a * (o.b - ax), bi = o.a * o.b;
-                dinv[i] = o.a; r[i] = ri; rh[i] = ri; v[i] = 0.0; p[i] = ri;
+                dinv[i] = o.a; r[i] = ri; rh[i] = ri; v[i] = 0.0;
+                if (!ghost(i)) { p[i] = ri; push(2, i, ri); }  // ghost entries of p arrive from their owners
                 acc[0] += ri * ri; acc[1] += bi * bi;
               });
-  grid_sum_fast<3>(bar, acc, a.red, phase, sh);
-  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }  // A[active, eliminated] != 0: not block triangular
+  NB_GSUM(3, true, acc);
+  if (acc[2] != 0.0) { finish(a, 0, -3, 0.0, 0.0); bar.save(); return; }  // A[active, eliminated] != 0: not block triangular
   double rn = sqrt(acc[0]);
   const double bn = sqrt(acc[1]);
   const double tol = fmax(a.rtol * bn, a.atol);
@@ -479,7 +503,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
                   d1[0] += o.b * vi;
                 });
     stamp(a.prof, np);
-    grid_sum_fast<1>(bar, d1, a.red, phase, sh);
+    NB_GSUM(1, false, d1);
     stamp(a.prof, np);
     if (d1[0] == 0.0) { out(it - 1, -1, rn, bn); return; }
     const double alpha = rho / d1[0];
@@ -497,7 +521,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
                           d5[0] += ti * o.b; d5[1] += ti * ti; d5[2] += o.c * o.b; d5[3] += o.c * ti; d5[4] += o.b * o.b;
                         }, v, -alpha);
       stamp(a.prof, np); stamp(a.prof, np); stamp(a.prof, np);
-      grid_sum_fast<5>(bar, d5, a.red, phase, sh);
+      NB_GSUM(5, false, d5);
       stamp(a.prof, np);
       ss = d5[4];
       d3[0] = d5[0]; d3[1] = d5[1]; d3[2] = d5[2]; d3[3] = d5[3];
@@ -519,17 +543,18 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 #pragma unroll
       for (int u = 0; u < PU; ++u) {
         const int i = base + 32 * u;
-        const double si = rr[u] - alpha * vv[u];
-        if (i < i1) s[i] = si;
+        const double si = rr[u] - alpha * vv[u];  // 0 on ghost rows (r = v = 0 there)
+        if (i < i1 && !ghost(i)) { s[i] = si; push(4, i, si); }
         d2[0] += si * si;
       }
     }
     stamp(a.prof, np);
-    grid_sum_fast<1>(bar, d2, a.red, phase, sh);
+    NB_GSUM(1, true, d2);
     stamp(a.prof, np);
     ss = d2[0];
     if (sqrt(ss) <= tol) {  // early exit on the half step (KSPBCGS does the same)
-      for (int i = i0 + lane; i < i1; i += 32) xi[i] += alpha * p[i];
+      for (int i = i0 + lane; i < i1; i += 32)
+        if (!ghost(i)) xi[i] += alpha * p[i];
       out(it, 1, sqrt(ss), bn);
       return;
     }
@@ -540,7 +565,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
                   d3[0] += ti * o.b; d3[1] += ti * ti; d3[2] += o.c * o.b; d3[3] += o.c * ti;
                 });
     stamp(a.prof, np);
-    grid_sum_fast<4>(bar, d3, a.red, phase, sh);
+    NB_GSUM(4, false, d3);
     stamp(a.prof, np);
     }
     if (d3[1] == 0.0) { out(it, -1, sqrt(ss), bn); return; }
@@ -567,11 +592,14 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 #pragma unroll
       for (int u = 0; u < PU; ++u) {
         const int i = base + 32 * u;
-        const double ri = sv[u] - omega * tt[u];
-        if (i < i1) {
+        const bool own = i < i1 && !ghost(i);
+        const double ri = own ? sv[u] - omega * tt[u] : 0.0;
+        if (own) {
           xi[i] = xx[u] + alpha * pp[u] + omega * sv[u];
           r[i] = ri;
-          p[i] = ri + beta * (pp[u] - omega * vv[u]);
+          const double pn = ri + beta * (pp[u] - omega * vv[u]);
+          p[i] = pn;
+          push(2, i, pn);
           if (restart) rh[i] = ri;
         }
         d4[0] += ri * ri;
@@ -579,7 +607,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     }
     stamp(a.prof, np);
     if (check || restart) {
-      grid_sum_fast<1>(bar, d4, a.red, phase, sh);
+      NB_GSUM(1, true, d4);
       rn = sqrt(d4[0]);
       if (rn <= tol) { out(it, 1, rn, bn); return; }
       if (restart) { rho_new = d4[0]; rhn = rn; }
@@ -590,6 +618,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     rho = rho_new;
   }
   out(a.maxit, 0, rn, bn);
+#undef NB_GSUM
 }
 
 // y = A x through the node-block layout, stand-alone (tests and tools/spmv_bench.py): gathers the values, permutes x in,
@@ -1560,7 +1589,28 @@ int nb_ensure(fx_plan* P, int space) {
     FX_CUDA(cudaMalloc((void**)&P->nbval, sizeof(double) * (size_t)H.nslots));
     P->nbval_cap = (size_t)H.nslots;
   }
+  nb.int_of_ext_h = H.int_of_ext;
   nb.state = 1;
+  return nb_attach_halo(P, space);
+}
+
+// Partitioned run: the halo push lists of the space in INTERNAL numbering (needs the destinations' internal indices,
+// fx_plan_set_halo_solver_index).  No-op until both the layout and the indices exist.
+int nb_attach_halo(fx_plan* P, int space) {
+  DevPattern& d = P->sp[space];
+  DevPattern::NbDev& nb = d.nb;
+  cudaFree(nb.s_first); cudaFree(nb.s_remote);
+  nb.s_first = nb.s_remote = nullptr;
+  if (nb.state != 1 || !d.has_halo || (int)d.halo_remote_int.size() != d.nsend || d.halo_first_h.empty()) return FX_OK;
+  std::vector<int> ext_of_int((size_t)nb.N), first((size_t)nb.N, -1), remote((size_t)std::max(d.nsend, 1), 0);
+  FX_CUDA(cudaMemcpy(ext_of_int.data(), nb.ext_of_int, sizeof(int) * ext_of_int.size(), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nb.N; ++i)
+    if (ext_of_int[i] >= 0) first[i] = d.halo_first_h[ext_of_int[i]];
+  for (int k = 0; k < d.nsend; ++k) remote[k] = d.halo_remote_int[d.halo_order[k]];
+  FX_CUDA(cudaMalloc((void**)&nb.s_first, sizeof(int) * first.size()));
+  FX_CUDA(cudaMalloc((void**)&nb.s_remote, sizeof(int) * remote.size()));
+  FX_CUDA(cudaMemcpy(nb.s_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
+  FX_CUDA(cudaMemcpy(nb.s_remote, remote.data(), sizeof(int) * remote.size(), cudaMemcpyHostToDevice));
   return FX_OK;
 }
 
@@ -1569,7 +1619,7 @@ static NbView nb_view(const fx_plan* P, const DevPattern& d) {
   static const int pol_env = getenv("FX_NB_L2POLICY") ? atoi(getenv("FX_NB_L2POLICY")) : 1;
   static const int pre_env = getenv("FX_NB_DUAL") ? atoi(getenv("FX_NB_DUAL")) : 1;
   return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
-                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env};
+                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env, nb.s_first, nb.s_remote};
 }
 
 template <int BS>
@@ -1637,6 +1687,10 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   ka.A = CsrView{p.n, p.rowptr, p.col, val, p.rowblk, p.nrowblk, P->cdesc, P->cre, P->ccol, P->cval,
                  (p.nelim > 0 || part) ? p.elim : nullptr, p.elim_rows, p.nelim, P->cprefix, P->scanpart,
                  (reblock_env && p.maxrow <= SPMV_NNZB / 2) ? SPMV_NNZB - p.maxrow : 0, P->rowpre, P->nblk};
+  // partitioned run: every rank must take the SAME set-up branch (compact_reblock crosses two cross-GPU barriers,
+  // compact_zeros one).  It does: build_pattern rejects rows longer than 256 = SPMV_NNZB / 2 entries, so the
+  // condition above is true on every rank whatever its sub-mesh looks like.
+  static_assert(SPMV_NNZB / 2 >= 256, "rank-local maxrow would decide the number of cross-GPU barriers");
   ka.bar = P->bar;
   ka.dd = P->dist;
   if (part) {
@@ -1697,17 +1751,30 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   }
   // BiCGStab on the node-block layout when the space has one (FX_NB=0: the scalar compacted-CSR kernel below)
   static const int nb_env = getenv("FX_NB") ? atoi(getenv("FX_NB")) : 1;
-  if (nb_env && method == FX_KSP_BICGSTAB && !part) {
+  if (nb_env && method == FX_KSP_BICGSTAB) {
     if ((rc = nb_ensure(P, space))) return rc;
-    if (p.nb.state == 1) {
-      if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
-      ka.w = P->work;
+    // partitioned run: the halo pushes need the neighbours' INTERNAL indices (fx_plan_set_halo_solver_index) and the
+    // peer regions must hold the internal vectors; otherwise the scalar kernel below serves the solve
+    const bool nb_ok = p.nb.state == 1 && (!part || (p.nb.s_first != nullptr && (long long)p.nb.N <= P->dist.nmax));
+    if (nb_ok) {
+      if (!part) {
+        if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
+        ka.w = P->work;
+      }
       ka.nb = nb_view(P, p);
       const bool dual = ka.nb.dual != 0;
-      switch (p.nb.bs) {
-        case 1: rc = launch_nb<1>(dual ? (void*)k_bicgstab_nb<1, true> : (void*)k_bicgstab_nb<1, false>, p, ka, -1, st); break;
-        case 2: rc = launch_nb<2>(dual ? (void*)k_bicgstab_nb<2, true> : (void*)k_bicgstab_nb<2, false>, p, ka, -1, st); break;
-        default: rc = launch_nb<3>(dual ? (void*)k_bicgstab_nb<3, true> : (void*)k_bicgstab_nb<3, false>, p, ka, -1, st); break;
+      if (part) {
+        switch (p.nb.bs) {
+          case 1: rc = launch_nb<1>((void*)k_bicgstab_nb<1, false, true>, p, ka, -1, st); break;
+          case 2: rc = launch_nb<2>((void*)k_bicgstab_nb<2, false, true>, p, ka, -1, st); break;
+          default: rc = launch_nb<3>((void*)k_bicgstab_nb<3, false, true>, p, ka, -1, st); break;
+        }
+      } else {
+        switch (p.nb.bs) {
+          case 1: rc = launch_nb<1>(dual ? (void*)k_bicgstab_nb<1, true, false> : (void*)k_bicgstab_nb<1, false, false>, p, ka, -1, st); break;
+          case 2: rc = launch_nb<2>(dual ? (void*)k_bicgstab_nb<2, true, false> : (void*)k_bicgstab_nb<2, false, false>, p, ka, -1, st); break;
+          default: rc = launch_nb<3>(dual ? (void*)k_bicgstab_nb<3, true, false> : (void*)k_bicgstab_nb<3, false, false>, p, ka, -1, st); break;
+        }
       }
       if (rc == FX_OK && prof_env && p.n > 100000) {  // debugging aid: per-phase microseconds of iterations 2..4
         static unsigned long long h[1024];

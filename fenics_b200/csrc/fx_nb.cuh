@@ -20,6 +20,9 @@ struct NbView {
   double* bval;  // [nslots] gathered per solve
   int l2policy;  // L2 eviction priority of the value / column stream: 0 normal, 1 evict_first, 2 evict_last
   int dual;      // BiCGStab: 1 = second product gathers r - alpha v on the fly (no s vector, 3 barriers per iteration)
+  // partitioned run: halo push lists in internal numbering (null: not available)
+  const int* s_first;   // [N] first (dof, destination) pair of an interface entry (pairs shared with DistDev::s_peer)
+  const int* s_remote;  // [nsend] the destination's INTERNAL index of the ghost entry
 };
 
 // The block values and columns are read once per product; the work vectors (a few MB) are re-read every pass.  With

@@ -63,12 +63,17 @@ struct DevPattern {
     int *wrange = nullptr, *bre = nullptr, *bcol = nullptr, *src = nullptr, *diag = nullptr, *ext_of_int = nullptr,
         *int_of_ext = nullptr, *zchk = nullptr;
     uint8_t* imask = nullptr;
+    int *s_first = nullptr, *s_remote = nullptr;  // halo push lists in internal numbering (partitioned run)
+    std::vector<int> int_of_ext_h;                // host copy (fx_space_solver_index)
     void release() {
       cudaFree(desc); cudaFree(wrange); cudaFree(bre); cudaFree(bcol); cudaFree(src); cudaFree(diag);
-      cudaFree(ext_of_int); cudaFree(int_of_ext); cudaFree(zchk); cudaFree(imask);
+      cudaFree(ext_of_int); cudaFree(int_of_ext); cudaFree(zchk); cudaFree(imask); cudaFree(s_first); cudaFree(s_remote);
       *this = NbDev();
     }
   } nb;
+  std::vector<int> halo_order;       // fx_plan_set_halo: sorted position k <- caller's pair order[k]
+  std::vector<int> halo_first_h;     // host copy of s_first
+  std::vector<int> halo_remote_int;  // fx_plan_set_halo_solver_index: destination internal indices, caller's pair order
 };
 
 // peer-mapped regions of a partitioned run, as the Krylov kernels see them (layout: fx_la_common.cuh)
@@ -177,7 +182,8 @@ int la_dotw(fx_plan* plan, int n, const double* x, const double* y, const double
 struct PcgConfig { int R, slice, grid, nlmax; };  // R == 0: the system does not fit the resident CG kernel
 PcgConfig pcg_resident_config(const fx_plan* plan, int nrowblk, int maxblknnz);
 int la_spmv_nb(fx_plan* plan, int space, const double* val, const double* x, double* y, int reps, cudaStream_t st);
-int nb_ensure(fx_plan* plan, int space);  // builds the node-block layout of a space if possible; FX_OK either way unless CUDA fails
+int nb_ensure(fx_plan* plan, int space);
+int nb_attach_halo(fx_plan* plan, int space);  // builds the node-block layout of a space if possible; FX_OK either way unless CUDA fails
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
 }  // namespace fx

@@ -50,7 +50,9 @@ class DistContext:
         import torch.distributed._symmetric_memory as symm_mem
         lp, group = self.lp, self.group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        nmax = int(lp.n_local_max)
+        # stride of the work vectors inside a region: the Krylov kernels keep them in the internal node-major numbering,
+        # which pads the 3 stress components of a node to 4 doubles (fx_nb_host.h)
+        nmax = (4 * int(lp.n_local_max) + 2) // 3 + 8
         nbytes = int(lib.fx_peer_region_bytes(nmax))
         self._region = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
         self._region.zero_()
@@ -70,6 +72,24 @@ class DistContext:
             ghost = np.ascontiguousarray(~lp.owned[sp], dtype=np.uint8)
             check(lib.fx_plan_set_halo(self.plan.h, abi.SPACE_ID[sp], len(peer), peer.ctypes.data, local.ctypes.data,
                                        remote.ctypes.data, ghost.ctypes.data))
+            # the neighbours' INTERNAL (node-major) index of every ghost entry I push to: every rank publishes its
+            # ext -> internal map, one all-gather per space at set-up (a collective: all ranks take part even when a
+            # rank's space has no node-block layout -- then nobody uses it for this space)
+            idx = np.full(nmax + 1, -1, dtype=np.int32)
+            n_int = C.c_int(0)
+            n_loc = len(ghost)
+            mine = np.empty(n_loc, dtype=np.int32)
+            rc = lib.fx_space_solver_index(self.plan.h, abi.SPACE_ID[sp], mine.ctypes.data, C.byref(n_int))
+            if rc == 0 and os.environ.get("FX_NB", "1") != "0":
+                idx[:n_loc] = mine
+                idx[nmax] = 1
+            mine_t = torch.as_tensor(idx, device=dev)
+            allidx = [torch.empty_like(mine_t) for _ in range(world)]
+            dist.all_gather(allidx, mine_t, group=group)
+            allidx = torch.stack(allidx).cpu().numpy()
+            if (allidx[:, nmax] == 1).all() and len(peer):
+                rint = np.ascontiguousarray(allidx[peer, remote], dtype=np.int32)
+                check(lib.fx_plan_set_halo_solver_index(self.plan.h, abi.SPACE_ID[sp], len(peer), rint.ctypes.data))
 
     def close(self):
         """detach the plan from the peer regions (before the symmetric memory goes away)."""

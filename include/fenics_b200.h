@@ -304,6 +304,19 @@ int fx_plan_set_peer_regions(fx_plan* plan, int rank, int world, void* const* re
 int fx_plan_set_halo(fx_plan* plan, int space, int nsend, const int* peer, const int* local, const int* remote,
                      const unsigned char* ghost);
 
+/* The Krylov kernels keep their work vectors in an internal node-major numbering (all components of a mesh node
+ * adjacent; fenics_b200/csrc/fx_nb_host.h).  On a partition the owner of an interface value stores it straight into the
+ * neighbour's copy of the work vector, so it needs the neighbour's INTERNAL index of the ghost entry:
+ *   fx_space_solver_index          int_of_ext[n] of this rank's plan (-1: dof outside the node blocks, e.g. the eliminated
+ *                                  DEVSS rows); *n_internal = length of the internal vectors (peer regions must hold
+ *                                  vectors that long: pass nmax >= n_internal to fx_plan_set_peer_regions).  Call after
+ *                                  fx_plan_set_eliminated_dofs / fx_plan_set_halo.  FX_ERR_UNSUPPORTED: no such layout.
+ *   fx_plan_set_halo_solver_index  remote_internal[k] = the destination rank's int_of_ext[remote[k]] for every pair k of
+ *                                  the preceding fx_plan_set_halo call (same order).  Without it the partitioned
+ *                                  BiCGStab solves run on the scalar compacted-CSR kernel.                              */
+int fx_space_solver_index(fx_plan* plan, int space, int* int_of_ext, int* n_internal);
+int fx_plan_set_halo_solver_index(fx_plan* plan, int space, int nsend, const int* remote_internal);
+
 /* solve(A, x, b, "bicgstab"|"cg"|"gmres", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve (gmres: restart 30, classical Gram-Schmidt, PETSc KSPGMRES defaults; single-GPU plans); pc none,
  * jacobi or jacobi_coarse -- FX_PC_ILU0 returns FX_ERR_UNSUPPORTED.  x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
