@@ -402,7 +402,7 @@ int fx_plan_set_halo(fx_plan* P, int space, int nsend, const int* peer, const in
   d.s_first = d.s_peer = d.s_local = d.s_remote = nullptr;
   d.nsend = 0; d.has_halo = false;
   d.halo_h.clear();
-  d.halo_order.clear(); d.halo_first_h.clear(); d.halo_remote_int.clear();
+  d.halo_order.clear(); d.halo_first_h.clear(); d.halo_remote_int.clear(); d.ghost_owner_h.clear();
   if (!ghost) return rebuild_mask(d);  // halo removed
   std::vector<uint8_t> m((size_t)d.n, 0);
   for (int i = 0; i < d.n; ++i) m[i] = ghost[i] ? 2 : 0;
@@ -436,6 +436,7 @@ int fx_plan_set_halo(fx_plan* P, int space, int nsend, const int* peer, const in
   d.halo_h.swap(m);
   d.halo_order = order;
   d.halo_first_h = first;
+  d.ghost_owner_h.assign(ghost, ghost + d.n);
   return rebuild_mask(d);
 }
 
@@ -457,11 +458,19 @@ int fx_plan_set_halo_solver_index(fx_plan* P, int space, int nsend, const int* r
       (nsend > 0 && !remote_internal))
     return set_error(FX_ERR_ARG, "fx_plan_set_halo_solver_index: bad argument (call fx_plan_set_halo first)");
   DevPattern& d = P->sp[space];
-  d.halo_remote_int.assign(remote_internal, remote_internal + nsend);
-  for (int k = 0; k < nsend; ++k)
-    if (remote_internal[k] < 0) return set_error(FX_ERR_ARG, "fx_plan_set_halo_solver_index: pair %d has no internal index", k);
   int rc = nb_ensure(P, space);
   if (rc) return rc;
+  if (d.nb.state != 1) return set_error(FX_ERR_UNSUPPORTED, "space %d has no node-block solver layout (%s)", space, d.nb.why.c_str());
+  // pairs of dofs outside the node blocks (the eliminated DG0 rows of W) are never pushed by the Krylov kernels and
+  // carry -1 on both sides; every other pair needs the destination's internal index
+  std::vector<int> local_sorted((size_t)nsend);
+  FX_CUDA(cudaMemcpy(local_sorted.data(), d.s_local, sizeof(int) * (size_t)nsend, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < nsend; ++k) {
+    const int li = d.nb.int_of_ext_h[local_sorted[k]], ri = remote_internal[d.halo_order[k]];
+    if ((li >= 0) != (ri >= 0))
+      return set_error(FX_ERR_ARG, "fx_plan_set_halo_solver_index: pair %d: local internal index %d, remote %d", d.halo_order[k], li, ri);
+  }
+  d.halo_remote_int.assign(remote_internal, remote_internal + nsend);
   return nb_attach_halo(P, space);
 }
 

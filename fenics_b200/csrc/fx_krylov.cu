@@ -428,6 +428,11 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
       }
     }
   };
+  // one (dof, destination) pair: consecutive pairs address consecutive ghost slots of the destination (nb_build numbers
+  // ghost nodes per owner in the owner's order), so a warp's stores coalesce into a few NVLink packets
+  auto push_pair = [&](int j, int q, double val) {
+    a.dd.region[a.dd.s_peer[q] & (DIST_MAXW - 1)][(long long)j * a.dd.nmax + B.s_remote[q]] = val;
+  };
   double* r = a.w;
   double* rh = a.w + ld;
   double* p = a.w + 2 * ld;
@@ -532,6 +537,20 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
       }
     } else {
     double d2[1] = {0.0};
+    if constexpr (DIST) {
+      // interface entries: spread over the WHOLE grid (one (dof, destination) pair per thread) and first, so the P2P
+      // stores are in flight while the owned ranges are updated -- a warp's owned range would put the ~10^3 stores
+      // of a cut line on a handful of warps (measured: 17 us per pass instead of 3)
+      for (int q = gt; q < a.dd.nsend; q += gs) {
+        const int i = B.s_local[q];
+        if (i >= 0 && (q == 0 || B.s_local[q - 1] != i)) {  // first pair of the dof: update + all its destinations
+          const double si = r[i] - alpha * v[i];
+          for (int qq = q; qq < a.dd.nsend && B.s_local[qq] == i; ++qq) push_pair(4, qq, si);
+          s[i] = si;
+          d2[0] += si * si;
+        }
+      }
+    }
     for (int base = i0 + lane; base < i1; base += 32 * PU) {
       double rr[PU], vv[PU];
 #pragma unroll
@@ -543,8 +562,9 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 #pragma unroll
       for (int u = 0; u < PU; ++u) {
         const int i = base + 32 * u;
-        const double si = rr[u] - alpha * vv[u];  // 0 on ghost rows (r = v = 0 there)
-        if (i < i1 && !ghost(i)) { s[i] = si; push(4, i, si); }
+        const bool mine = i < i1 && !(DIST && (mk[i] & (MASK_GHOST | MASK_IFACE)));
+        const double si = mine ? rr[u] - alpha * vv[u] : 0.0;
+        if (mine) s[i] = si;
         d2[0] += si * si;
       }
     }
@@ -579,6 +599,22 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     const double beta = restart ? 0.0 : (rho_new / rho) * (alpha / omega);
     const bool check = rn <= 2.0 * tol;  // confirm with a true norm
     double d4[1] = {0.0};
+    if constexpr (DIST) {
+      for (int q = gt; q < a.dd.nsend; q += gs) {
+        const int i = B.s_local[q];
+        if (i >= 0 && (q == 0 || B.s_local[q - 1] != i)) {
+          const double pi = p[i], si = s[i];
+          const double ri = si - omega * t[i];
+          const double pn = ri + beta * (pi - omega * v[i]);
+          for (int qq = q; qq < a.dd.nsend && B.s_local[qq] == i; ++qq) push_pair(2, qq, pn);
+          xi[i] += alpha * pi + omega * si;
+          r[i] = ri;
+          p[i] = pn;
+          if (restart) rh[i] = ri;
+          d4[0] += ri * ri;
+        }
+      }
+    }
     for (int base = i0 + lane; base < i1; base += 32 * PU) {
       double pp[PU], sv[PU], tt[PU], vv[PU], xx[PU];
 #pragma unroll
@@ -592,14 +628,12 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 #pragma unroll
       for (int u = 0; u < PU; ++u) {
         const int i = base + 32 * u;
-        const bool own = i < i1 && !ghost(i);
+        const bool own = i < i1 && !(DIST && (mk[i] & (MASK_GHOST | MASK_IFACE)));
         const double ri = own ? sv[u] - omega * tt[u] : 0.0;
         if (own) {
           xi[i] = xx[u] + alpha * pp[u] + omega * sv[u];
           r[i] = ri;
-          const double pn = ri + beta * (pp[u] - omega * vv[u]);
-          p[i] = pn;
-          push(2, i, pn);
+          p[i] = ri + beta * (pp[u] - omega * vv[u]);
           if (restart) rh[i] = ri;
         }
         d4[0] += ri * ri;
@@ -1558,7 +1592,7 @@ int nb_ensure(fx_plan* P, int space) {
   NbHost H;
   std::string why;
   if (!nb_build(dm.data(), nc, d.ld, bs, nloc, d.n, rowptr.data(), col.data(), mask.empty() ? nullptr : mask.data(),
-                P->num_sms, H, why)) {
+                P->num_sms, H, why, d.ghost_owner_h.empty() ? nullptr : d.ghost_owner_h.data())) {
     nb.state = -1; nb.why = why;
     return FX_OK;
   }
@@ -1599,14 +1633,21 @@ int nb_ensure(fx_plan* P, int space) {
 int nb_attach_halo(fx_plan* P, int space) {
   DevPattern& d = P->sp[space];
   DevPattern::NbDev& nb = d.nb;
-  cudaFree(nb.s_first); cudaFree(nb.s_remote);
-  nb.s_first = nb.s_remote = nullptr;
+  cudaFree(nb.s_first); cudaFree(nb.s_remote); cudaFree(nb.s_local);
+  nb.s_first = nb.s_remote = nb.s_local = nullptr;
   if (nb.state != 1 || !d.has_halo || (int)d.halo_remote_int.size() != d.nsend || d.halo_first_h.empty()) return FX_OK;
   std::vector<int> ext_of_int((size_t)nb.N), first((size_t)nb.N, -1), remote((size_t)std::max(d.nsend, 1), 0);
   FX_CUDA(cudaMemcpy(ext_of_int.data(), nb.ext_of_int, sizeof(int) * ext_of_int.size(), cudaMemcpyDeviceToHost));
   for (int i = 0; i < nb.N; ++i)
     if (ext_of_int[i] >= 0) first[i] = d.halo_first_h[ext_of_int[i]];
-  for (int k = 0; k < d.nsend; ++k) remote[k] = d.halo_remote_int[d.halo_order[k]];
+  std::vector<int> local_ext((size_t)std::max(d.nsend, 1), 0), local_int((size_t)std::max(d.nsend, 1), -1);
+  if (d.nsend > 0) FX_CUDA(cudaMemcpy(local_ext.data(), d.s_local, sizeof(int) * (size_t)d.nsend, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < d.nsend; ++k) {
+    remote[k] = d.halo_remote_int[d.halo_order[k]];
+    local_int[k] = nb.int_of_ext_h[local_ext[k]];
+  }
+  FX_CUDA(cudaMalloc((void**)&nb.s_local, sizeof(int) * local_int.size()));
+  FX_CUDA(cudaMemcpy(nb.s_local, local_int.data(), sizeof(int) * local_int.size(), cudaMemcpyHostToDevice));
   FX_CUDA(cudaMalloc((void**)&nb.s_first, sizeof(int) * first.size()));
   FX_CUDA(cudaMalloc((void**)&nb.s_remote, sizeof(int) * remote.size()));
   FX_CUDA(cudaMemcpy(nb.s_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
@@ -1619,7 +1660,7 @@ static NbView nb_view(const fx_plan* P, const DevPattern& d) {
   static const int pol_env = getenv("FX_NB_L2POLICY") ? atoi(getenv("FX_NB_L2POLICY")) : 1;
   static const int pre_env = getenv("FX_NB_DUAL") ? atoi(getenv("FX_NB_DUAL")) : 1;
   return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
-                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env, nb.s_first, nb.s_remote};
+                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env, nb.s_first, nb.s_remote, nb.s_local};
 }
 
 template <int BS>

@@ -23,6 +23,7 @@ struct NbView {
   // partitioned run: halo push lists in internal numbering (null: not available)
   const int* s_first;   // [N] first (dof, destination) pair of an interface entry (pairs shared with DistDev::s_peer)
   const int* s_remote;  // [nsend] the destination's INTERNAL index of the ghost entry
+  const int* s_local;   // [nsend] my INTERNAL index of the pair's dof (-1: outside the node blocks)
 };
 
 // The block values and columns are read once per product; the work vectors (a few MB) are re-read every pass.  With

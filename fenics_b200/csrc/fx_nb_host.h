@@ -69,8 +69,12 @@ inline bool nb_space_layout(int space, int& bs, int& nloc) {
 // dm_t: transposed dofmap [ld][nc]; mask: null or [n] with bit 0 = eliminated, bit 1 = ghost, bit 2 = interface.
 // Returns false with `why` when the space has no node-block structure the solver can use (callers fall back to the
 // scalar CSR path).
+// ghost_owner: null or [n] = 1 + owner rank of a ghost dof (0: owned).  Ghost nodes are numbered LAST, grouped by owner
+// and in ascending external order inside a group -- the order in which the owner walks its interface nodes -- so the
+// owner's P2P stores of interface values land on consecutive addresses (coalesced NVLink writes).
 inline bool nb_build(const int* dm_t, int nc, int ld, int bs, int nloc, int n, const int* rowptr, const int* col,
-                     const uint8_t* mask, int num_sms, NbHost& H, std::string& why) {
+                     const uint8_t* mask, int num_sms, NbHost& H, std::string& why,
+                     const uint8_t* ghost_owner = nullptr) {
   const int bp = nb_bp(bs), b2 = bs * bs;
   H = NbHost();
   H.bs = bs; H.bp = bp;
@@ -89,8 +93,15 @@ inline bool nb_build(const int* dm_t, int nc, int ld, int bs, int nloc, int n, c
   // nodes in the order of their first component's external index (inherits the locality of the external numbering)
   std::vector<int> rank(n, -1);
   int nn = 0;
+  {
+    std::vector<int> heads;
+    for (int d = 0; d < n; ++d)
+      if (head[d] == d) heads.push_back(d);
+    if (ghost_owner != nullptr)
+      std::stable_sort(heads.begin(), heads.end(), [&](int a, int b) { return ghost_owner[a] < ghost_owner[b]; });
+    for (int h : heads) rank[h] = nn++;
+  }
   for (int d = 0; d < n; ++d) {
-    if (head[d] == d) rank[d] = nn++;
     const uint8_t m = mask ? mask[d] : 0;
     if (head[d] < 0 && !(m & 1)) { why = "a dof outside the node blocks is not eliminated"; return false; }
     if (head[d] >= 0 && (m & 1)) { why = "a node-block dof is eliminated"; return false; }

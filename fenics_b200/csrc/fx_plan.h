@@ -63,14 +63,15 @@ struct DevPattern {
     int *wrange = nullptr, *bre = nullptr, *bcol = nullptr, *src = nullptr, *diag = nullptr, *ext_of_int = nullptr,
         *int_of_ext = nullptr, *zchk = nullptr;
     uint8_t* imask = nullptr;
-    int *s_first = nullptr, *s_remote = nullptr;  // halo push lists in internal numbering (partitioned run)
+    int *s_first = nullptr, *s_remote = nullptr, *s_local = nullptr;  // halo push lists in internal numbering (partitioned run)
     std::vector<int> int_of_ext_h;                // host copy (fx_space_solver_index)
     void release() {
       cudaFree(desc); cudaFree(wrange); cudaFree(bre); cudaFree(bcol); cudaFree(src); cudaFree(diag);
-      cudaFree(ext_of_int); cudaFree(int_of_ext); cudaFree(zchk); cudaFree(imask); cudaFree(s_first); cudaFree(s_remote);
+      cudaFree(ext_of_int); cudaFree(int_of_ext); cudaFree(zchk); cudaFree(imask); cudaFree(s_first); cudaFree(s_remote); cudaFree(s_local);
       *this = NbDev();
     }
   } nb;
+  std::vector<uint8_t> ghost_owner_h; // fx_plan_set_halo: 1 + owner rank of a ghost dof (or just non-zero), 0 = owned
   std::vector<int> halo_order;       // fx_plan_set_halo: sorted position k <- caller's pair order[k]
   std::vector<int> halo_first_h;     // host copy of s_first
   std::vector<int> halo_remote_int;  // fx_plan_set_halo_solver_index: destination internal indices, caller's pair order

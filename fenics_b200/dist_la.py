@@ -69,7 +69,8 @@ class DistContext:
             peer = np.ascontiguousarray(np.repeat(np.arange(world), h.send_counts), dtype=np.int32)
             local = np.ascontiguousarray(h.send_idx_np, dtype=np.int32)
             remote = np.ascontiguousarray(h.send_remote_np, dtype=np.int32)
-            ghost = np.ascontiguousarray(~lp.owned[sp], dtype=np.uint8)
+            # 0 = owned, else 1 + owner rank: the solver layout numbers ghost nodes per owner, in the owner's order
+            ghost = np.ascontiguousarray(np.where(lp.owned[sp], 0, lp.owner[sp][lp.l2g[sp]] + 1), dtype=np.uint8)
             check(lib.fx_plan_set_halo(self.plan.h, abi.SPACE_ID[sp], len(peer), peer.ctypes.data, local.ctypes.data,
                                        remote.ctypes.data, ghost.ctypes.data))
             # the neighbours' INTERNAL (node-major) index of every ghost entry I push to: every rank publishes its

@@ -312,8 +312,9 @@ int fx_plan_set_halo(fx_plan* plan, int space, int nsend, const int* peer, const
  *                                  vectors that long: pass nmax >= n_internal to fx_plan_set_peer_regions).  Call after
  *                                  fx_plan_set_eliminated_dofs / fx_plan_set_halo.  FX_ERR_UNSUPPORTED: no such layout.
  *   fx_plan_set_halo_solver_index  remote_internal[k] = the destination rank's int_of_ext[remote[k]] for every pair k of
- *                                  the preceding fx_plan_set_halo call (same order).  Without it the partitioned
- *                                  BiCGStab solves run on the scalar compacted-CSR kernel.                              */
+ *                                  the preceding fx_plan_set_halo call (same order; -1 where the dof lies outside the
+ *                                  node blocks on both sides).  Without it the partitioned BiCGStab solves run on the
+ *                                  scalar compacted-CSR kernel.                                                        */
 int fx_space_solver_index(fx_plan* plan, int space, int* int_of_ext, int* n_internal);
 int fx_plan_set_halo_solver_index(fx_plan* plan, int space, int nsend, const int* remote_internal);
 
