@@ -172,9 +172,9 @@ class _LDC:
 
     def enable_pressure_coarse(self, k=None):
         """Two-level preconditioner (Jacobi + aggregate coarse correction, fx_plan_set_aggregates) for the CG
-        pressure solve; aggregates = recursive coordinate bisection of the P1 dof coordinates.  Only for
-        non-singular pressure matrices (the compressible loops: the Ma^2/dt mass term).  Returns whether the
-        library accepted the aggregates."""
+        pressure solve; aggregates = recursive coordinate bisection of the P1 dof coordinates.  Singular
+        (pure-Neumann: config 1, incompressible_dgp.py) and nearly singular (Ma -> 0) pressure matrices are handled on
+        the device (rank-one shift of the coarse matrix).  Returns whether the library accepted the aggregates."""
         Q = self.S["Q"]
         k = self._coarse_size(Q.dim(), k)
         ok = k >= 32 and self.plan.set_aggregates("Q", rcb_partition(Q.tabulate_dof_coordinates(), k), k)
