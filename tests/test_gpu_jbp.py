@@ -154,3 +154,24 @@ def test_adaptive_refinement_indicator_matches_oracle():
         assert np.all(np.abs(kc[diff] - lvl) < 1e-12)
         assert abs(rd["markers"].mean() - ro["ratio"]) < 0.02
     assert drv.pr.params[abi.FX_P_EPS] == eps_before  # the loop's SU epsilon is restored
+
+
+def test_soft_physics_pin_chi_increases_with_we():
+    """The only numbers the reference holds for this path: the journal-bearing stability measure chi = F_x / F_y at the
+    end of the loop (t = Tf = 1.5, fenepmp_jbp.py:305,768) for Re = 25, "flow between eccentrically rotating cylinders"/
+    plot_data.py:10: chi = 0.074, 0.188, 0.550 at We = 0.25, 0.5, 1.0 -- increasing in We.  Those runs used mshr meshes and
+    another script of the family, so this is a SOFT pin: on a script-sized O-grid the GPU loop must reproduce the trend
+    and the order of magnitude (factor 6), not the digits."""
+    published = {0.25: 0.074, 0.5: 0.188, 1.0: 0.550}
+    chi = {}
+    for We in published:
+        d = jbp.FenepmpJBP(n_theta=64, n_r=16, We=We)
+        d.pressure_method = "cg"
+        d.check = False
+        while d.t < 1.5:
+            r = d.step()
+        assert np.isfinite(r["F_x"]) and np.isfinite(r["F_y"]) and r["torque"] > 0.0
+        chi[We] = r["F_x"] / r["F_y"]
+    assert chi[0.25] < chi[0.5] < chi[1.0], chi
+    for We, ref in published.items():
+        assert ref / 6.0 < chi[We] < ref * 6.0, (We, chi[We], ref)
