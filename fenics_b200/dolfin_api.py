@@ -12,6 +12,7 @@ import torch
 
 from . import _abi as abi
 from . import la
+from . import symbolic
 from ._lib import check, lib
 from .la import Matrix, Plan, Vector, norm, parameters  # noqa: F401  (re-exported)
 from .mesh import DOLFIN_EPS, _call_inside, facets_inside  # noqa: F401
@@ -20,12 +21,17 @@ _P2_FACET_DOFS = np.array([[1, 2, 3], [0, 2, 4], [0, 1, 5]])
 _P1_FACET_DOFS = np.array([[1, 2], [0, 2], [0, 1]])
 
 
-class Function:
-    """dolfin Function stand-in living on the device."""
+class Function(symbolic.Operand):
+    """dolfin Function stand-in living on the device.  Inside a symbolic form (fenics_b200/symbolic.py) it is a
+    coefficient: `inner(p0, div(v))*dx`, `(u0, D0_vec) = w0.split()`."""
 
     def __init__(self, space, plan):
         self._space, self.plan = space, plan
         self._vec = Vector(plan, space.name)
+
+    def split(self):
+        from .form_registry import split
+        return split(self)
 
     def function_space(self):
         return self._space
@@ -55,7 +61,8 @@ class Problem:
     def bind(self, slot, fn):
         self.fields[slot] = fn
         self._table[slot] = fn.vector().t.data_ptr()
-        fn._driver = getattr(self, "owner", None)
+        if getattr(self, "owner", None) is not None:
+            fn._driver = self.owner
         return fn
 
     def set_param(self, slot, value):
@@ -97,9 +104,52 @@ class ConsistentProjection:
         self.mass_form, self.rhs_form = mass_form, rhs_form
 
 
+def TestFunction(V):
+    from .form_registry import arguments
+    return arguments(V, 0)
+
+
+def TrialFunction(V):
+    from .form_registry import arguments
+    return arguments(V, 1)
+
+
+TestFunctions, TrialFunctions = TestFunction, TrialFunction  # mixed spaces: arguments() already returns the split
+
+
+def _problem_of(plan):
+    """the field / parameter tables that literal (symbolic) forms of a plan are assembled with"""
+    pr = getattr(plan, "_sym_problem", None)
+    if pr is None:
+        pr = plan._sym_problem = Problem(plan)
+    return pr
+
+
+def _recognised(form):
+    """symbolic Form -> Form(problem, fx_form id) with the form's own Functions and Parameters bound"""
+    fid, coefs, params, what, space_objs = symbolic.recognise(form)
+    plan = None
+    for _, fn in coefs:
+        plan = plan or getattr(fn, "plan", None)
+    for sp in space_objs:
+        plan = plan or getattr(sp, "_shim_plan", None)
+    if plan is None:
+        raise RuntimeError("assemble(%s): no device plan reachable from the form (create the Functions with "
+                           "solution_functions / Function(V, plan) first)" % what)
+    pr = _problem_of(plan)
+    for slot, fn in coefs:
+        pr.bind(slot, fn)
+    for name, par in params.items():
+        pr.set_param(getattr(abi, "FX_P_" + name.upper()), par.value)
+    return Form(pr, fid)
+
+
 def assemble(form, tensor=None):
     """assemble(a) -> Matrix, assemble(L) -> Vector, assemble(M) -> float
-    (lid-driven-cavity/incomp_LDC.py:328-329, :420-421).  `tensor` reuses storage."""
+    (lid-driven-cavity/incomp_LDC.py:328-329, :420-421).  `tensor` reuses storage.  `form`: a Form of a Problem
+    (fx_form id) or a symbolic form built with the scripts' own statements (recognised by structure)."""
+    if isinstance(form, symbolic.Form):
+        form = _recognised(form)
     pr = form.problem
     st = la._stream()
     if form.rank == 2:

@@ -87,6 +87,8 @@ class Plan:
         self.h = h
         self._pat = {}
         self._agg = set()
+        for s in self.spaces.values():  # TestFunction(V) / literal forms find the device plan through their space
+            s._shim_plan = self
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None

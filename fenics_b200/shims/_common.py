@@ -21,20 +21,26 @@ def set_algebra(namespace):
     _ALG = namespace
 
 
-def alg():
+def alg(operand=None):
+    """the algebra namespace for an operand: the library's own symbolic module for its own expressions / Functions
+    (whatever set_algebra selected), else the configured one"""
     global _ALG
+    if operand is not None:
+        from .. import symbolic
+        if isinstance(operand, (symbolic.E, symbolic.Operand)):
+            return symbolic
     if _ALG is None:
         try:
             import ufl
             _ALG = ufl
         except ImportError:
-            raise RuntimeError("symbolic tensor helper called without UFL: install dolfin/ufl (or set_algebra(...)). The "
-                               "GPU path never needs these -- each form has a hand-written functor (fx_form ids).")
+            from .. import symbolic  # the library's own UFL-named algebra: forms built with it are recognised by
+            _ALG = symbolic          # structure and assembled by the hand-written functors (fenics_b200/symbolic.py)
     return _ALG
 
 
 def _T(a):
-    A = alg()
+    A = alg(a)
     return A.transpose(a) if hasattr(A, "transpose") else a.T
 
 
@@ -154,36 +160,36 @@ def LDC_Regular_Mesh(mm, B, L):
 # ---- symbolic tensor algebra (shared by all three helper modules) ---------------------------------------
 def tgrad(w):
     "transpose of grad(w)"
-    return _T(alg().grad(w))
+    return _T(alg(w).grad(w))
 
 
 def Dincomp(w):
     "rate of strain, incompressible"
-    g = alg().grad(w)
+    g = alg(w).grad(w)
     return 0.5 * (g + _T(g))
 
 
 def Dcomp(w):
     "rate of strain, compressible: deviatoric part"
-    A = alg()
+    A = alg(w)
     g = A.grad(w)
     return 0.5 * (g + _T(g)) - (1.0 / 3) * A.div(w) * A.Identity(len(w))
 
 
 def Fdef_incompressible(u, Tau):
     "upper-convected terms u.grad(Tau) - grad(u) Tau - Tau grad(u)^T"
-    A = alg()
+    A = alg(u)
     return A.dot(u, A.grad(Tau)) - A.dot(A.grad(u), Tau) - A.dot(Tau, tgrad(u))
 
 
 def Fdef_compressible(u, Tau):
-    A = alg()
+    A = alg(u)
     return Fdef_incompressible(u, Tau) + A.div(u) * Tau
 
 
 def reshape_elements(D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec):
     """the seven 3-vectors as symmetric 2x2 tensors [[a,b],[b,c]] (fenics_fem.py:210-225)."""
-    A = alg()
+    A = alg(D0_vec)
     return tuple(A.as_matrix([[v[0], v[1]], [v[1], v[2]]])
                  for v in (D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec))
 
@@ -200,20 +206,16 @@ def function_spaces(mesh, order):
     return fs(mesh, order)
 
 
-class _Argument:
-    """placeholder for a Trial/TestFunction: forms are selected by id, not built from these."""
-
-    def __init__(self, space, role):
-        self.space, self.role = space, role
-
-    def __repr__(self):
-        return "<%s on %s>" % (self.role, getattr(self.space, "name", self.space))
-
-
 def trial_functions(Q, Z, W):
-    """(rho, p, T, tau_vec, u, D_vec, D, tau) -- fenics_fem.py:249-260.  Symbolic placeholders."""
-    t = lambda S: _Argument(S, "TrialFunction")  # noqa: E731
-    return t(Q), t(Q), t(Q), t(Z), t(W), t(W), t(W), t(Z)
+    """(rho, p, T, tau_vec, u, D_vec, D, tau) -- fenics_fem.py:249-260, as symbolic arguments (fenics_b200/symbolic.py):
+    forms built from them with the scripts' statements are recognised and assembled by the hand-written functors."""
+    from ..dolfin_api import TrialFunction, TrialFunctions
+    from ..symbolic import as_matrix
+    rho, p, T, tau_vec = TrialFunction(Q), TrialFunction(Q), TrialFunction(Q), TrialFunction(Z)
+    (u, D_vec) = TrialFunctions(W)
+    D = as_matrix([[D_vec[0], D_vec[1]], [D_vec[1], D_vec[2]]])
+    tau = as_matrix([[tau_vec[0], tau_vec[1]], [tau_vec[1], tau_vec[2]]])
+    return rho, p, T, tau_vec, u, D_vec, D, tau
 
 
 def make_solution_functions(plan):

@@ -5,8 +5,10 @@ from math import cos, fabs, sin, sqrt, tanh  # noqa: F401  (the reference re-exp
 import numpy as np  # noqa: F401
 
 from fenics_b200 import mesh as _mesh
-from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, assemble, norm, parameters, project,  # noqa: F401
-                           solve)
+from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, TestFunction, TestFunctions,  # noqa: F401
+                           TrialFunction, TrialFunctions, assemble, norm, parameters, project, solve)
+from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
+                                  dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
 from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, Dincomp, LDC_Regular_Mesh, Skew_Mesh,  # noqa: F401
                        _needs_dolfin, _npy, absolute, adaptive_refinement, alg, chunks, expskewcavity,
                        function_spaces, max_location, mesh2triang, min_location, mplot, normalize_solution, pi,
@@ -14,6 +16,10 @@ from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, D
                        update_progress, xskewcavity, yskewcavity)
 from fenics_b200.shims._common import Fdef_compressible as Fdefcon  # noqa: F401
 from fenics_b200.shims._common import Fdef_incompressible as Fdef  # noqa: F401
+
+def end():
+    """dolfin's end() closes a begin()/end() log block (incomp_LDC.py:332): nothing to close here"""
+
 
 refine_boundary = _needs_dolfin("refine_boundary")
 refine_top = _needs_dolfin("refine_top")
@@ -26,13 +32,13 @@ def ramp_function(t):
 
 def sigmain(u, p, Tau, We, betav):
     """incompressible total stress 2 betav D(u) - p I + (1-betav)/We (Tau - I)  (:304-305)"""
-    I = alg().Identity(len(u))
+    I = alg(u).Identity(len(u))
     return 2 * betav * Dincomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
 
 
 def sigma(u, p, Tau, We, betav):
     """compressible total stress, deviatoric rate of strain (:307-308)"""
-    I = alg().Identity(len(u))
+    I = alg(u).Identity(len(u))
     return 2 * betav * Dcomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
 
 

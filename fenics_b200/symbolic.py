@@ -1,0 +1,400 @@
+"""Form recognition: makes the scripts' literal `assemble(a1)` work.
+
+The reference builds every UFL form inside its time loop and hands it to dolfin (`A1 = assemble(a1)`,
+lid-driven-cavity/incomp_LDC.py:317-331).  The GPU path has a hand-written functor per form (fx_form ids), so what is
+needed between the two is not a form compiler but a form RECOGNISER: this module is a small symbolic tensor algebra
+with UFL's operator names (grad, nabla_grad, div, dot, inner, transpose, as_matrix, Identity, `*dx`, `*ds(i)` ...) whose
+expression trees have a canonical structural signature.  The registry (`fenics_b200/form_registry.py`) executes the
+scripts' own form-building statements once on template objects and records signature -> fx_form id; a user form
+with the same structure is then assembled by that functor, its Functions bound to the functor's field slots in order
+of first appearance and its `Parameter`s written to the parameter table by name.  A form the library has no functor
+for raises `UnknownForm` naming what it is missing -- never a silent fallback.
+
+Scalars that parametrise the forms (Re, We, dt, betav ...) are `Parameter(name, value)` objects: the scripts hold them
+as Python floats, which Python would fold into anonymous numbers before any recogniser sees them; wrapping them is
+the one change a maintainer makes to a script's set-up section.  This module is pure Python and
+imports neither torch nor the CUDA library.
+"""
+import numbers
+
+import numpy as np
+
+
+class UnknownForm(KeyError):
+    pass
+
+
+def _num(x):
+    return repr(float(x))
+
+
+class E:
+    """expression node: op, children, tensor shape"""
+    __slots__ = ("op", "a", "shape", "data")
+    __array_priority__ = 1000  # numpy scalars defer to our reflected operators
+
+    def __init__(self, op, a=(), shape=(), data=None):
+        self.op, self.a, self.shape, self.data = op, tuple(a), tuple(shape), data
+
+    # ---- signature ----------------------------------------------------------------------------------
+    def sig(self, ctx):
+        if self.op == "num":
+            return _num(self.data)
+        if self.op == "par":
+            ctx.params[self.data.name] = self.data
+            return "P:" + self.data.name
+        if self.op == "arg":
+            number, space, comps, space_obj = self.data
+            ctx.args.add(number)
+            ctx.spaces.add(space)
+            if space_obj is not None:
+                ctx.space_objs.append(space_obj)
+            return "A%d:%s%s" % (number, space, list(comps))
+        if self.op == "coef":
+            fn, comps = self.data
+            if id(fn) not in ctx.coef_index:
+                ctx.coef_index[id(fn)] = len(ctx.coefs)
+                ctx.coefs.append(fn)
+            return "C%d:%s%s" % (ctx.coef_index[id(fn)], fn.function_space().name, list(comps))
+        if self.op in ("h", "n"):
+            return self.op
+        inner_ = ",".join(c.sig(ctx) for c in self.a)
+        extra = "" if self.data is None else "[%s]" % (self.data,)
+        return "%s%s(%s)" % (self.op, extra, inner_)
+
+    # ---- operators ------------------------------------------------------------------------------------
+    def __add__(self, o):
+        o = as_expr(o)
+        if o.op == "num" and o.data == 0.0 and self.shape != ():
+            return self
+        _same(self, o)
+        return E("add", (self, o), self.shape)
+
+    def __radd__(self, o):
+        return as_expr(o) + self
+
+    def __sub__(self, o):
+        o = as_expr(o)
+        _same(self, o)
+        return E("sub", (self, o), self.shape)
+
+    def __rsub__(self, o):
+        return as_expr(o) - self
+
+    def __neg__(self):
+        return E("neg", (self,), self.shape)
+
+    def __mul__(self, o):
+        if isinstance(o, Measure):
+            return Form([(self, o.kind, o.subdomain)])
+        if isinstance(o, Form):
+            return o.__rmul__(self)
+        o = as_expr(o)
+        if self.shape == () or o.shape == ():
+            return E("mul", (self, o), self.shape or o.shape)
+        if len(self.shape) == 2 and len(o.shape) == 1:  # UFL: matrix * vector
+            return dot(self, o)
+        if len(self.shape) == 2 and len(o.shape) == 2:
+            return dot(self, o)
+        raise TypeError("unsupported product of shapes %s and %s" % (self.shape, o.shape))
+
+    def __rmul__(self, o):
+        if isinstance(o, Form):
+            return NotImplemented
+        return as_expr(o) * self
+
+    def __truediv__(self, o):
+        o = as_expr(o)
+        if o.shape != ():
+            raise TypeError("division by a non-scalar")
+        return E("div", (self, o), self.shape)
+
+    def __rtruediv__(self, o):
+        return as_expr(o) / self
+
+    def __pow__(self, o):
+        return E("pow", (self, as_expr(o)), self.shape)
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        if len(idx) > len(self.shape) or any(not isinstance(i, (int, np.integer)) for i in idx):
+            raise IndexError("fixed integer indices only")
+        for i, n in zip(idx, self.shape):
+            if not 0 <= i < n:
+                raise IndexError(idx)
+        return E("idx", (self,), self.shape[len(idx):], tuple(int(i) for i in idx))
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError("scalar expression has no len()")
+        return self.shape[0]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    @property
+    def T(self):
+        return transpose(self)
+
+
+def _same(a, b):
+    if a.shape != b.shape:
+        raise TypeError("shape mismatch %s vs %s" % (a.shape, b.shape))
+
+
+class Parameter(E):
+    """named scalar of a run (Re, We, dt, betav ...): a symbolic leaf that remembers its parameter-table slot by
+    name and still behaves as a number where the scripts use it as one (float(), comparisons, printing)."""
+    __slots__ = ("name", "value")
+
+    def __init__(self, name, value):
+        E.__init__(self, "par", (), (), self)
+        self.name, self.value = name, float(value)
+
+    def __float__(self):
+        return self.value
+
+    def __repr__(self):
+        return repr(self.value)
+
+    def __lt__(self, o):
+        return self.value < float(o)
+
+    def __gt__(self, o):
+        return self.value > float(o)
+
+    def __le__(self, o):
+        return self.value <= float(o)
+
+    def __ge__(self, o):
+        return self.value >= float(o)
+
+
+class Operand:
+    """mixin for Function-like objects: inside a form they behave as their coefficient expression"""
+
+    def _sym_expr(self):
+        return coefficient(self)
+
+    def __add__(self, o):
+        return as_expr(self) + o
+
+    def __radd__(self, o):
+        return o + as_expr(self)
+
+    def __sub__(self, o):
+        return as_expr(self) - o
+
+    def __rsub__(self, o):
+        return o - as_expr(self)
+
+    def __neg__(self):
+        return -as_expr(self)
+
+    def __mul__(self, o):
+        return as_expr(self) * o
+
+    def __rmul__(self, o):
+        return o * as_expr(self)
+
+    def __truediv__(self, o):
+        return as_expr(self) / o
+
+    def __pow__(self, o):
+        return as_expr(self) ** o
+
+    def __getitem__(self, i):
+        return as_expr(self)[i]
+
+
+def as_expr(x):
+    if isinstance(x, E):
+        return x
+    if isinstance(x, (numbers.Real, np.floating, np.integer)):
+        return E("num", (), (), float(x))
+    if hasattr(x, "_sym_expr"):
+        return x._sym_expr()
+    raise TypeError("cannot use %r in a form" % (type(x).__name__,))
+
+
+# ---- leaves -------------------------------------------------------------------------------------------
+def argument(number, space, comps, space_obj=None):
+    """test (number 0) / trial (number 1) function of the space NAMED `space`, scalar components `comps`; space_obj: the
+    FunctionSpace (leads assemble() to the device plan when a form has no coefficient)"""
+    comps = tuple(comps)
+    return E("arg", (), (len(comps),) if len(comps) > 1 else (), (number, space, comps, space_obj))
+
+
+def coefficient(fn, comps=None):
+    """a (sub-)Function: comps = scalar components of its space it covers (None: all)"""
+    sp = fn.function_space()
+    if comps is None:
+        comps = tuple(range(len(sp.comps)))
+    comps = tuple(comps)
+    return E("coef", (), (len(comps),) if len(comps) > 1 else (), (fn, comps))
+
+
+def CellDiameter(mesh=None):
+    return E("h")
+
+
+def FacetNormal(mesh=None):
+    return E("n", (), (2,))
+
+
+def Identity(n):
+    return E("identity", (), (n, n), int(n))
+
+
+# ---- operators with UFL's names and index conventions ---------------------------------------------------
+def grad(e):
+    e = as_expr(e)
+    return E("grad", (e,), e.shape + (2,))
+
+
+def nabla_grad(e):
+    e = as_expr(e)
+    return E("nabla_grad", (e,), (2,) + e.shape)
+
+
+def div(e):
+    e = as_expr(e)
+    if not e.shape or e.shape[-1] != 2:
+        raise TypeError("div of shape %s" % (e.shape,))
+    return E("divop", (e,), e.shape[:-1])
+
+
+def dot(a, b):
+    a, b = as_expr(a), as_expr(b)
+    if not a.shape or not b.shape or a.shape[-1] != b.shape[0]:
+        raise TypeError("dot of shapes %s and %s" % (a.shape, b.shape))
+    return E("dot", (a, b), a.shape[:-1] + b.shape[1:])
+
+
+def inner(a, b):
+    a, b = as_expr(a), as_expr(b)
+    _same(a, b)
+    return E("inner", (a, b), ())
+
+
+def outer(a, b):
+    a, b = as_expr(a), as_expr(b)
+    return E("outer", (a, b), a.shape + b.shape)
+
+
+def transpose(e):
+    e = as_expr(e)
+    if len(e.shape) != 2:
+        raise TypeError("transpose of shape %s" % (e.shape,))
+    return E("T", (e,), e.shape[::-1])
+
+
+def tr(e):
+    e = as_expr(e)
+    return E("tr", (e,), ())
+
+
+def sym(e):
+    e = as_expr(e)
+    return E("sym", (e,), e.shape)
+
+
+def sqrt(e):
+    return E("sqrt", (as_expr(e),), ())
+
+
+def as_vector(items):
+    items = [as_expr(i) for i in items]
+    return E("vec", items, (len(items),))
+
+
+def as_matrix(rows):
+    rows = [[as_expr(i) for i in r] for r in rows]
+    return E("mat", [i for r in rows for i in r], (len(rows), len(rows[0])), len(rows[0]))
+
+
+# ---- measures and forms -----------------------------------------------------------------------------------
+class Measure:
+    def __init__(self, kind, subdomain=None):
+        self.kind, self.subdomain = kind, subdomain
+
+    def __call__(self, subdomain):
+        return Measure(self.kind, int(subdomain))
+
+    def __rmul__(self, e):
+        return as_expr(e) * self
+
+
+dx = Measure("dx")
+ds = Measure("ds")
+
+
+class Form:
+    """sum of integrals; supports the arithmetic the scripts do on forms (a += th*DEVSSl, L -= ..., lhs/rhs are not
+    needed: the loops of the supported configs write a and L separately or the registry holds the split form)"""
+
+    def __init__(self, integrals):
+        self.integrals = list(integrals)
+
+    def __add__(self, o):
+        if isinstance(o, numbers.Real) and o == 0:
+            return self
+        if not isinstance(o, Form):
+            return NotImplemented
+        return Form(self.integrals + o.integrals)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self + (-1.0) * o
+
+    def __neg__(self):
+        return (-1.0) * self
+
+    def __rmul__(self, c):
+        c = as_expr(c)
+        if c.shape != ():
+            raise TypeError("only scalars scale a form")
+        return Form([(E("mul", (c, e), e.shape), k, s) for e, k, s in self.integrals])
+
+    def __mul__(self, c):
+        return self.__rmul__(c)
+
+    def signature(self):
+        ctx = _Ctx()
+        parts = ["%s%s:%s" % (k, "" if s is None else "(%d)" % s, e.sig(ctx)) for e, k, s in self.integrals]
+        return "|".join(parts), ctx
+
+
+class _Ctx:
+    def __init__(self):
+        self.params, self.args, self.spaces, self.coefs, self.coef_index = {}, set(), set(), [], {}
+        self.space_objs = []
+
+
+# ---- registry ----------------------------------------------------------------------------------------------
+_REGISTRY = {}
+
+
+def register(form, form_id, slots, what):
+    """form: a Form built from template objects; slots: fx_field slot of every coefficient in order of first
+    appearance; what: the script statement it restates (file:line) for error messages"""
+    sig, ctx = form.signature()
+    if len(ctx.coefs) != len(slots):
+        raise ValueError("%s: %d coefficients in the form, %d slots given" % (what, len(ctx.coefs), len(slots)))
+    _REGISTRY[sig] = (int(form_id), tuple(int(s) for s in slots), what)
+
+
+def recognise(form):
+    """-> (fx_form id, [(slot, Function)], {parameter name: Parameter}, description, [FunctionSpace of the arguments]);
+    raises UnknownForm"""
+    from . import form_registry  # noqa: F401  (fills _REGISTRY on first use)
+    form_registry.load()
+    sig, ctx = form.signature()
+    hit = _REGISTRY.get(sig)
+    if hit is None:
+        raise UnknownForm("no hand-written functor matches this form (rank %d on %s, %d integrals, %d coefficients); "
+                          "the library recognises %d forms of the reference scripts -- see fenics_b200/form_registry.py"
+                          % (len(ctx.args), sorted(ctx.spaces), len(form.integrals), len(ctx.coefs), len(_REGISTRY)))
+    fid, slots, what = hit
+    return fid, list(zip(slots, ctx.coefs)), dict(ctx.params), what, ctx.space_objs

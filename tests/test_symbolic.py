@@ -1,0 +1,111 @@
+"""Form recognition (fenics_b200/symbolic.py, form_registry.py): the TEXT of the reference's loop body, read from the
+reference checkout and executed against the drop-in shim module, yields forms the registry maps to the right fx_form
+ids -- `A1 = assemble(a1)` (lid-driven-cavity/incomp_LDC.py:328) is literal.  CPU only: template Functions stand in
+for device Functions and `assemble` records what was recognised.  (The GPU test test_gpu_literal.py then really
+assembles and solves.)  Skipped where the reference checkout is absent."""
+import os
+import textwrap
+
+import pytest
+
+from fenics_b200 import _abi as abi
+from fenics_b200 import form_registry, symbolic
+from fenics_b200.form_registry import TemplateFunction as T
+
+REF = os.path.join(os.environ.get("FENICS_REFERENCE", "/root/reference"), "lid-driven-cavity", "incomp_LDC.py")
+
+
+def _namespace(rec):
+    """what the script's set-up section provides before the loop (:142-170, :259-262), on template objects"""
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    P = symbolic.Parameter
+    ns.update(Re=P("Re", 0.5), We=P("We", 0.25), dt=P("dt", 0.005), betav=P("betav", 0.5), th=P("th", 1.0),
+              conv=P("conv", 0.0), c1=P("c1", 0.05), c2=P("c2", 0.01))
+    A = abi
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    ns.update(w0=w0, w12=w12, ws=ws, w1=w1, p0=T("Q", A.FX_F_P0), p1=T("Q", A.FX_F_P1),
+              tau0_vec=T("Zc", A.FX_F_TAU0), tau1_vec=T("Zc", A.FX_F_TAU1), kapp=T("Qt", A.FX_F_KAPP),
+              h=symbolic.CellDiameter())
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], Ds_vec), (ns["u1"], D1_vec) = (f.split() for f in (w0, w12, ws, w1))
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
+    ns["q"] = ff.TestFunction("Q")
+    Rt_vec = ff.TestFunction("Zc")
+    (ns["v"], R_vec) = ff.TestFunctions("W")
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    ns["D0"], ns["D12"], _, _, ns["tau0"], _, ns["tau1"] = ff.reshape_elements(
+        D0_vec, D12_vec, Ds_vec, D1_vec, symbolic.as_expr(ns["tau0_vec"]), symbolic.as_expr(ns["tau0_vec"]),
+        symbolic.as_expr(ns["tau1_vec"]))
+    # :259-262 and :309, :313 (built before / at the top of the loop body)
+    exec(textwrap.dedent("""
+        DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx
+        DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx
+        DEVSSr_u1 = 2*(1-betav)*inner(D12,Dincomp(v))*dx
+    """), ns)
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return ("tensor", fid)
+
+    class _BC:
+        def apply(self, *a):
+            rec.append("bc.apply")
+    ns.update(assemble=assemble, bcu=[_BC(), _BC()], bcp=[], bctau=[],
+              solve=lambda A, x, b, *a: rec.append(("solve", A[1], a)))
+    for f in ("w12", "ws", "w1", "p1", "tau1_vec"):
+        ns[f].vector = lambda: None
+    return ns
+
+
+def _lines(a, b):
+    if not os.path.exists(REF):
+        pytest.skip("reference checkout not present")
+    src = open(REF).read().splitlines()[a - 1:b]
+    return textwrap.dedent("\n".join(src))
+
+
+def test_text_of_the_velocity_half_step_runs_against_the_shims():
+    """incomp_LDC.py:317-331 verbatim: builds a1 / L1, assemble, bc.apply, solve(..., "bicgstab", "default")"""
+    rec = []
+    ns = _namespace(rec)
+    exec(_lines(317, 331), ns)
+    assert rec[0] == (abi.FX_FORM_C1_A1, [], ["Re", "betav", "dt", "th"])
+    assert rec[1][0] == abi.FX_FORM_C1_L1 and rec[1][1] == [abi.FX_F_W0, abi.FX_F_P0, abi.FX_F_TAU0]
+    assert set(rec[1][2]) == {"Re", "betav", "conv", "dt", "th"}
+    assert rec[2:4] == ["bc.apply", "bc.apply"] and rec[4] == ("solve", abi.FX_FORM_C1_A1, ("bicgstab", "default"))
+
+
+@pytest.mark.parametrize("a,b,ids", [(355, 363, (abi.FX_FORM_C1_A2, abi.FX_FORM_C1_L2)),
+                                     (370, 375, (abi.FX_FORM_C1_A5, abi.FX_FORM_C1_L5)),
+                                     (379, 394, (abi.FX_FORM_C1_A7, abi.FX_FORM_C1_L7)),
+                                     (400, 416, (abi.FX_FORM_C1_A4, abi.FX_FORM_C1_L4)),
+                                     (420, 421, (abi.FX_FORM_C1_EK, abi.FX_FORM_C1_EE))])
+def test_text_of_the_other_sub_steps(a, b, ids):
+    rec = []
+    ns = _namespace(rec)
+    ns.update(a1=0, L1=0)  # :388-389 add this step's DEVSS terms to a1 / L1 (sic)
+    exec(_lines(a, b), ns)
+    got = [r[0] for r in rec if isinstance(r, tuple) and r[0] != "solve"]
+    assert tuple(got) == ids
+
+
+def test_unknown_forms_and_structure_sensitivity():
+    form_registry.load()
+    from fenics_b200.symbolic import Parameter, dx, grad, inner
+    q, p = form_registry.arguments("Q", 0), form_registry.arguments("Q", 1)
+    assert symbolic.recognise(inner(grad(p), grad(q)) * dx)[0] == abi.FX_FORM_C1_A5
+    with pytest.raises(symbolic.UnknownForm):
+        symbolic.recognise(inner(p, q) * dx + inner(grad(p), grad(q)) * dx)   # a Helmholtz matrix nobody registered
+    with pytest.raises(symbolic.UnknownForm):
+        symbolic.recognise(Parameter("Re", 2.0) * inner(grad(p), grad(q)) * dx)
+    # the coefficients are bound by order of first appearance, whatever objects they are
+    a, b = T("Q", -1), T("W", -1)
+    us = b.split()[0]
+    Re, dt = Parameter("Re", 3.0), Parameter("dt", 0.1)
+    fid, coefs, params, what, _ = symbolic.recognise(inner(grad(a), grad(q)) * dx + (Re / dt) * inner(us, grad(q)) * dx)
+    assert fid == abi.FX_FORM_C1_L5 and [s for s, _ in coefs] == [abi.FX_F_P0, abi.FX_F_WS] and coefs[0][1] is a
+    assert params["Re"].value == 3.0 and float(params["dt"]) == 0.1
