@@ -456,7 +456,7 @@ def run_ours(args):
         if lab.startswith("solve:"):
             if lab.endswith(":bicgstab"):
                 return "k_bicgstab_nb" if nb_on else "k_bicgstab"
-            return "k_pcg_res" if lab.split(":")[2] == "Q" else "k_cg"
+            return "k_pcg_res" if lab.split(":")[2] == "Q" else ("k_cg_nb" if nb_on else "k_cg")
         return "k_cell_matrix" if lab.startswith("assemble_matrix:") else None
     groups = {}
     for r_ in rows:

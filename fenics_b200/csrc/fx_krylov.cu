@@ -655,6 +655,120 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 #undef NB_GSUM
 }
 
+// ---- CG (Chronopoulos-Gear) on the node-block layout ------------------------------------------------------------
+// Same recurrence and stopping rule as k_cg (u = M^-1 r, w = A u, one fused reduction per iteration, two grid
+// barriers); data layout and set-up as k_bicgstab_nb.  Jacobi / none only: the two-level preconditioner stays with k_cg
+// and k_pcg_res.  Serves the consistent-mass projections of the loops (project(., Zc): 29 iterations per step on a 3 x 3
+// node-block matrix) and SPD systems too large or too tightly toleranced for the resident kernel.
+template <int BS>
+__global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constant__ KArgs a) {
+  constexpr int BP = nb_bp(BS);
+  __shared__ double sh[4 * 32];
+  extern __shared__ __align__(16) double prod_all[];
+  const NbView& B = a.nb;
+  const int N = B.N;
+  const size_t ld = ((size_t)N + 3) & ~(size_t)3;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  double* r = a.w;
+  double* u = a.w + ld;
+  double* w = a.w + 2 * ld;
+  double* p = a.w + 3 * ld;
+  double* s = a.w + 4 * ld;
+  double* dinv = a.w + 5 * ld;
+  double* xi = a.w + 6 * ld;
+  double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
+  const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
+  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  int i0 = 0, i1 = 0;
+  if (k0 < k1) {
+    const int4 da = B.desc[k0], db = B.desc[k1 - 1];
+    i0 = da.x * BP; i1 = (db.x + db.y) * BP;
+  }
+  const unsigned long long pol = nb_make_policy(B.l2policy);
+  int phase = 0;
+  GridBar bar;
+  bar.init(a.bar);
+  auto out = [&](int it, int conv, double rn, double bn) {
+    for (int i = i0 + lane; i < i1; i += 32) {
+      const int e = B.ext_of_int[i];
+      if (e >= 0) a.x[e] = xi[i];
+    }
+    leave(bar, a, it, conv, rn, bn);
+  };
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  acc[3] = (double)nb_gather_values(B, a.A.val);
+  for (int i = gt; i < N; i += gs) {
+    const int e = B.ext_of_int[i];
+    xi[i] = e >= 0 ? a.x[e] : 0.0;
+  }
+  bar.sync();
+  spmv_nb<BS>(B, k0, k1, xi, prod, pol,
+              [&](int i) {
+                const int e = B.ext_of_int[i];
+                return Ops2{nb_diag_inv<BS>(B, i, a.pc), e >= 0 ? a.b[e] : 0.0};
+              },
+              [&](int i, double ax, const Ops2& o) {
+                const double ri = o.b - ax, ui = o.a * ri, bi = o.a * o.b;
+                dinv[i] = o.a; r[i] = ri; u[i] = ui; p[i] = 0.0; s[i] = 0.0;
+                acc[0] += ri * ui; acc[1] += ui * ui; acc[2] += bi * bi;
+              });
+  grid_sum_fast<4>(bar, acc, a.red, phase, sh);
+  if (acc[3] != 0.0) { finish(a, 0, -3, 0.0, 0.0); return; }
+  double gamma = acc[0], un = sqrt(acc[1]);
+  const double bn = sqrt(acc[2]);
+  const double tol = fmax(a.rtol * bn, a.atol);
+  if (!(un == un)) { out(0, -1, un, bn); return; }
+  if (un <= tol) { out(0, 1, un, bn); return; }
+  double d0[1] = {0.0};
+  spmv_nb<BS>(B, k0, k1, u, prod, pol, [&](int i) { return Ops2{u[i], 0.0}; },
+              [&](int i, double au, const Ops2& o) {
+                w[i] = au;
+                d0[0] += au * o.a;
+              });
+  grid_sum_fast<1>(bar, d0, a.red, phase, sh);
+  if (!(d0[0] > 0.0)) { out(0, -1, un, bn); return; }
+  double alpha = gamma / d0[0], beta = 0.0;
+  constexpr int PU = 2;
+  for (int it = 1; it <= a.maxit; ++it) {
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int base = i0 + lane; base < i1; base += 32 * PU) {
+      double uu[PU], pp[PU], ww[PU], ss[PU], rr[PU], xx[PU], dd[PU];
+#pragma unroll
+      for (int q = 0; q < PU; ++q) {
+        const int i = base + 32 * q;
+        const bool ok = i < i1;
+        uu[q] = ok ? u[i] : 0.0; pp[q] = ok ? p[i] : 0.0; ww[q] = ok ? w[i] : 0.0; ss[q] = ok ? s[i] : 0.0;
+        rr[q] = ok ? r[i] : 0.0; xx[q] = ok ? xi[i] : 0.0; dd[q] = ok ? dinv[i] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < PU; ++q) {
+        const int i = base + 32 * q;
+        const double pi = uu[q] + beta * pp[q], si = ww[q] + beta * ss[q];
+        const double ri = rr[q] - alpha * si, ui = dd[q] * ri;
+        if (i < i1) { p[i] = pi; s[i] = si; xi[i] = xx[q] + alpha * pi; r[i] = ri; u[i] = ui; }
+        d[0] += ri * ui; d[1] += ui * ui;
+      }
+    }
+    bar.sync();
+    spmv_nb<BS>(B, k0, k1, u, prod, pol, [&](int i) { return Ops2{u[i], 0.0}; },
+                [&](int i, double au, const Ops2& o) {
+                  w[i] = au;
+                  d[2] += au * o.a;
+                });
+    grid_sum_fast<3>(bar, d, a.red, phase, sh);
+    un = sqrt(d[1]);
+    if (!(un == un) || un > a.dtol * bn) { out(it, -1, un, bn); return; }
+    if (un <= tol) { out(it, 1, un, bn); return; }
+    beta = d[0] / gamma;
+    const double denom = d[2] - beta * d[0] / alpha;
+    if (!(denom > 0.0)) { out(it, -1, un, bn); return; }  // not SPD / breakdown
+    alpha = d[0] / denom;
+    gamma = d[0];
+  }
+  out(a.maxit, 0, un, bn);
+}
+
 // y = A x through the node-block layout, stand-alone (tests and tools/spmv_bench.py): gathers the values, permutes x in,
 // runs `reps` products (a grid barrier between them, as inside a solve) and writes the rows of the node blocks to y
 template <int BS>
@@ -1658,9 +1772,13 @@ int nb_attach_halo(fx_plan* P, int space) {
 static NbView nb_view(const fx_plan* P, const DevPattern& d) {
   const DevPattern::NbDev& nb = d.nb;
   static const int pol_env = getenv("FX_NB_L2POLICY") ? atoi(getenv("FX_NB_L2POLICY")) : 1;
+  static const int pol_small_env = getenv("FX_NB_L2POLICY_SMALL") ? atoi(getenv("FX_NB_L2POLICY_SMALL")) : 2;
   static const int pre_env = getenv("FX_NB_DUAL") ? atoi(getenv("FX_NB_DUAL")) : 1;
   return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
-                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval, pol_env, pre_env, nb.s_first, nb.s_remote, nb.s_local};
+                nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval,
+                // matrices that fit the L2 beside the work vectors (<= 72 MB of block values) may ask for another policy
+                (pol_small_env >= 0 && nb.nslots * 8 + nb.ne * 4 <= (72ll << 20)) ? pol_small_env : pol_env, pre_env,
+                nb.s_first, nb.s_remote, nb.s_local};
 }
 
 template <int BS>
@@ -1779,6 +1897,24 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     FX_CUDA(cudaLaunchCooperativeKernel((void*)k_gmres<T>, dim3(grid), dim3(T), gargs, smem, st));
     count_launch(1);
     return FX_OK;
+  }
+  // CG on the node-block layout: everything the resident kernel below does not take (tight tolerances, systems that
+  // do not fit it, the 3 x 3-block Zc mass projections) with Jacobi / no preconditioning
+  static const int nb_cg_env = getenv("FX_NB") ? atoi(getenv("FX_NB")) : 1;
+  const bool resident = method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part && pcfg.R > 0 &&
+                        (pc != FX_PC_JACOBI_COARSE || coarse_resident);
+  if (nb_cg_env && method == FX_KSP_CG && !part && !resident && (pc == FX_PC_NONE || pc == FX_PC_JACOBI)) {
+    if ((rc = nb_ensure(P, space))) return rc;
+    if (p.nb.state == 1) {
+      if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;
+      ka.w = P->work;
+      ka.nb = nb_view(P, p);
+      switch (p.nb.bs) {
+        case 1: return launch_nb<1>((void*)k_cg_nb<1>, p, ka, -1, st);
+        case 2: return launch_nb<2>((void*)k_cg_nb<2>, p, ka, -1, st);
+        default: return launch_nb<3>((void*)k_cg_nb<3>, p, ka, -1, st);
+      }
+    }
   }
   // small SPD systems at loose tolerance: shared-memory-resident pipelined CG, one CTA per SM
   if (method == FX_KSP_CG && rtol >= 1e-9 && p.nelim == 0 && !part && pcfg.R > 0 &&
