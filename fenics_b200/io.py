@@ -9,8 +9,11 @@ file write would stall the step loop; AsyncWriter takes a consistent snapshot wi
      that produced the field; microseconds), so the loop may overwrite the field immediately;
   2. the device->host copy of the staging buffer into pinned memory on a SIDE stream (copy engine, overlaps the
      next steps' kernels);
-  3. a writer thread waits for that copy's event and writes the file (`.npy`, or HDF5 dataset "/f" when h5py is
-     importable and the name ends in .h5), then returns the slot to the ring.
+  3. a writer thread waits for that copy's event and writes the file, then returns the slot to the ring: `.npy`, or
+     -- for names ending in .h5 / .hdf5 -- the layout dolfin's `HDF5File.write(u, "/f")` produces, so the reference's
+     `load_solution` (fenics_base.py:102-108) can read it: group `/f` with `vector_0` (the dof vector), and for a
+     Function also `cell_dofs`, `x_cell_dofs` and `cells` (the cell-dof table and its offsets).  HDF5 needs h5py; without
+     it a .h5 name is an ERROR (surfaced by the next save()/flush()), never a silent change of container.
 
 `depth` slots bound the memory; when all are in flight, save() waits for the oldest (back-pressure instead of
 unbounded queues).  CPU tensors are accepted too (no streams; used by the CPU test of the ring / thread logic).
@@ -41,7 +44,10 @@ class AsyncWriter:
         """snapshot `field` (a Function, la.Vector or tensor) now, write it to `path` later; returns at once unless
         every slot is still in flight."""
         t = field
+        meta = None
         if not torch.is_tensor(t):
+            if hasattr(t, "function_space"):
+                meta = t.function_space()
             if hasattr(t, "vector"):
                 t = t.vector()
             t = t.t  # la.Vector -> its device tensor
@@ -70,7 +76,7 @@ class AsyncWriter:
             host = slot["host"][:n]
             host.copy_(t.reshape(-1))
             done = None
-        self._jobs.put((i, done, host, str(path)))
+        self._jobs.put((i, done, host, str(path), meta))
 
     def flush(self):
         """wait until everything handed over so far is on disk; raises the first write error."""
@@ -94,16 +100,22 @@ class AsyncWriter:
             raise self._errors.pop(0)
 
     @staticmethod
-    def _write(path, arr):
+    def _write(path, arr, space=None):
         if path.endswith((".h5", ".hdf5")):
             try:
                 import h5py
             except ImportError:
-                h5py = None
-            if h5py is not None:
-                with h5py.File(path, "w") as f:
-                    f.create_dataset("f", data=arr)
-                return
+                raise RuntimeError("cannot write %s: HDF5 output (dolfin's /f/vector_0 layout) needs h5py, which is not "
+                                   "installed -- use a .npy name" % path)
+            with h5py.File(path, "w") as f:
+                g = f.create_group("f")
+                g.create_dataset("vector_0", data=arr)
+                if space is not None and getattr(space, "cell_dofs", None) is not None:
+                    cd = np.asarray(space.cell_dofs)
+                    g.create_dataset("cell_dofs", data=cd.ravel().astype(np.int64))
+                    g.create_dataset("x_cell_dofs", data=np.arange(0, cd.size + 1, cd.shape[1], dtype=np.int64))
+                    g.create_dataset("cells", data=np.arange(cd.shape[0], dtype=np.int64))
+            return
         with open(path, "wb") as f:
             np.save(f, arr)
 
@@ -113,11 +125,11 @@ class AsyncWriter:
             if job is None:
                 self._jobs.task_done()
                 return
-            i, done, host, path = job
+            i, done, host, path, meta = job
             try:
                 if done is not None:
                     done.synchronize()
-                self._write(path, host.numpy())
+                self._write(path, host.numpy(), meta)
                 self.written.append(path)
             except Exception as e:  # surfaced by the next save()/flush()
                 self._errors.append(e)
@@ -127,13 +139,14 @@ class AsyncWriter:
 
 
 def load_array(path):
-    """read back what AsyncWriter wrote (either container)."""
+    """the dof vector of a file AsyncWriter (or dolfin's HDF5File.write(u, "/f")) wrote"""
     if path.endswith((".h5", ".hdf5")):
         try:
             import h5py
-            with h5py.File(path, "r") as f:
-                return np.asarray(f["f"])
-        except (ImportError, OSError):
-            pass
+        except ImportError:
+            raise RuntimeError("cannot read %s: HDF5 needs h5py, which is not installed" % path)
+        with h5py.File(path, "r") as f:
+            node = f["f"]
+            return np.asarray(node["vector_0"] if isinstance(node, h5py.Group) else node)
     with open(path, "rb") as f:
         return np.load(f)

@@ -28,9 +28,10 @@ def JBP_mesh(mesh_res, x_1, x_2, y_1, y_2, r_a, r_b):
 
 
 def save_solution(u, filename, writer=None):
-    """the reference writes dolfin HDF5 (:94-99).  Here the dof vector goes to `filename` (HDF5 dataset "/f" when h5py
-    is importable, else .npy bytes); with `writer` (fenics_b200.io.AsyncWriter) the call returns at once and the
-    device->host copy and the file write overlap the following time steps."""
+    """the reference writes dolfin HDF5 (:94-99).  Same layout here for .h5 names (group /f: vector_0, cell_dofs,
+    x_cell_dofs, cells; needs h5py -- without it a .h5 name raises), .npy otherwise; with `writer`
+    (fenics_b200.io.AsyncWriter) the call returns at once and the device->host copy and the file write overlap the
+    following time steps."""
     from fenics_b200.io import AsyncWriter
     if writer is not None:
         writer.save(u, filename)
