@@ -469,13 +469,14 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
     else grid_sum_fast<NV>(bar, v, a.red, phase, sh);                      \
   } while (0)
   double acc[3] = {0.0, 0.0, 0.0};
-  acc[2] = (double)nb_gather_values(B, a.A.val);
+  acc[2] = (double)nb_gather_values<BS>(B, a.A.val);
   for (int i = gt; i < N; i += gs) {
     const int e = B.ext_of_int[i];
     xi[i] = e >= 0 ? a.x[e] : 0.0;
   }
   bar.sync();
-  spmv_nb<BS>(B, k0, k1, xi, prod, pol,
+  const unsigned pm = B.planemask ? __ldcg(B.pmask) : 0xffffffffu;
+  spmv_nb<BS>(B, k0, k1, xi, prod, pol, pm,
               [&](int i) {
                 const int e = B.ext_of_int[i];
                 return Ops2{nb_diag_inv<BS>(B, i, a.pc), e >= 0 ? a.b[e] : 0.0};
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   constexpr int PU = 2;  // pass unroll: 32 * PU owned entries per batch of loads
   for (int it = 1; it <= a.maxit; ++it) {
     double d1[1] = {0.0};
-    spmv_nb<BS>(B, k0, k1, p, prod, pol, [&](int i) { return Ops2{dinv[i], rh[i]}; },
+    spmv_nb<BS>(B, k0, k1, p, prod, pol, pm, [&](int i) { return Ops2{dinv[i], rh[i]}; },
                 [&](int i, double ap, const Ops2& o) {
                   const double vi = o.a * ap;
                   v[i] = vi;
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
       // forms s_i for the dot products.  One barrier and one vector pass fewer; the half-step test moves behind
       // the product (same outcome, one product later).
       double d5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      spmv_nb<BS, true>(B, k0, k1, r, prod, pol, [&](int i) { return Ops4{dinv[i], r[i] - alpha * v[i], rh[i], 0.0}; },
+      spmv_nb<BS, true>(B, k0, k1, r, prod, pol, pm, [&](int i) { return Ops4{dinv[i], r[i] - alpha * v[i], rh[i], 0.0}; },
                         [&](int i, double as, const Ops4& o) {
                           const double ti = o.a * as;
                           t[i] = ti;
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
       out(it, 1, sqrt(ss), bn);
       return;
     }
-    spmv_nb<BS>(B, k0, k1, s, prod, pol, [&](int i) { return Ops3{dinv[i], s[i], rh[i]}; },
+    spmv_nb<BS>(B, k0, k1, s, prod, pol, pm, [&](int i) { return Ops3{dinv[i], s[i], rh[i]}; },
                 [&](int i, double as, const Ops3& o) {
                   const double ti = o.a * as;
                   t[i] = ti;
@@ -697,13 +698,14 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
     leave(bar, a, it, conv, rn, bn);
   };
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  acc[3] = (double)nb_gather_values(B, a.A.val);
+  acc[3] = (double)nb_gather_values<BS>(B, a.A.val);
   for (int i = gt; i < N; i += gs) {
     const int e = B.ext_of_int[i];
     xi[i] = e >= 0 ? a.x[e] : 0.0;
   }
   bar.sync();
-  spmv_nb<BS>(B, k0, k1, xi, prod, pol,
+  const unsigned pm = B.planemask ? __ldcg(B.pmask) : 0xffffffffu;
+  spmv_nb<BS>(B, k0, k1, xi, prod, pol, pm,
               [&](int i) {
                 const int e = B.ext_of_int[i];
                 return Ops2{nb_diag_inv<BS>(B, i, a.pc), e >= 0 ? a.b[e] : 0.0};
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
   if (!(un == un)) { out(0, -1, un, bn); return; }
   if (un <= tol) { out(0, 1, un, bn); return; }
   double d0[1] = {0.0};
-  spmv_nb<BS>(B, k0, k1, u, prod, pol, [&](int i) { return Ops2{u[i], 0.0}; },
+  spmv_nb<BS>(B, k0, k1, u, prod, pol, pm, [&](int i) { return Ops2{u[i], 0.0}; },
               [&](int i, double au, const Ops2& o) {
                 w[i] = au;
                 d0[0] += au * o.a;
@@ -751,7 +753,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
       }
     }
     bar.sync();
-    spmv_nb<BS>(B, k0, k1, u, prod, pol, [&](int i) { return Ops2{u[i], 0.0}; },
+    spmv_nb<BS>(B, k0, k1, u, prod, pol, pm, [&](int i) { return Ops2{u[i], 0.0}; },
                 [&](int i, double au, const Ops2& o) {
                   w[i] = au;
                   d[2] += au * o.a;
@@ -786,15 +788,16 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
   GridBar bar;
   bar.init(a.bar);
   const unsigned long long pol = nb_make_policy(B.l2policy);
-  const int bad = nb_gather_values(B, a.A.val);
+  const int bad = nb_gather_values<BS>(B, a.A.val);
   if (bad) a.info->converged = -3;
   for (int i = gt; i < N; i += gs) {
     const int e = B.ext_of_int[i];
     xi[i] = e >= 0 ? a.b[e] : 0.0;
   }
   bar.sync();
+  const unsigned pm = B.planemask ? __ldcg(B.pmask) : 0xffffffffu;
   for (int rep = 0; rep < reps; ++rep) {
-    spmv_nb<BS>(B, k0, k1, xi, prod, pol, [&](int i) { return Ops2{0.0, 0.0}; },
+    spmv_nb<BS>(B, k0, k1, xi, prod, pol, pm, [&](int i) { return Ops2{0.0, 0.0}; },
                 [&](int i, double ax, const Ops2&) { yi[i] = ax; });
     bar.sync();
   }
@@ -1787,13 +1790,14 @@ int nb_attach_halo(fx_plan* P, int space) {
 static NbView nb_view(const fx_plan* P, const DevPattern& d) {
   const DevPattern::NbDev& nb = d.nb;
   static const int pol_env = getenv("FX_NB_L2POLICY") ? atoi(getenv("FX_NB_L2POLICY")) : 1;
+  static const int planemask_env = getenv("FX_NB_PLANEMASK") ? atoi(getenv("FX_NB_PLANEMASK")) : 1;
   static const int pol_small_env = getenv("FX_NB_L2POLICY_SMALL") ? atoi(getenv("FX_NB_L2POLICY_SMALL")) : 2;
   static const int pre_env = getenv("FX_NB_DUAL") ? atoi(getenv("FX_NB_DUAL")) : 1;
   return NbView{nb.nn, nb.N, nb.nchunks, nb.nzchk, nb.ne, nb.nslots, nb.desc, nb.wrange, nb.bre, nb.bcol, nb.src,
                 nb.diag, nb.ext_of_int, nb.zchk, nb.imask, P->nbval,
                 // matrices that fit the L2 beside the work vectors (<= 72 MB of block values) may ask for another policy
                 (pol_small_env >= 0 && nb.nslots * 8 + nb.ne * 4 <= (72ll << 20)) ? pol_small_env : pol_env, pre_env,
-                nb.s_first, nb.s_remote, nb.s_local};
+                nb.s_first, nb.s_remote, nb.s_local, P->bar + 4, planemask_env};
 }
 
 template <int BS>
@@ -1823,7 +1827,7 @@ int la_spmv_nb(fx_plan* P, int space, const double* val, const double* x, double
                  p.nelim, nullptr, nullptr, 0, nullptr, nullptr};
   ka.nb = nb_view(P, p);
   ka.bar = P->bar; ka.w = P->work; ka.x = y; ka.b = x; ka.info = P->info + (FX_NTICKETS - 1);
-  FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
+  FX_CUDA(cudaMemsetAsync(P->bar, 0, 8 * sizeof(unsigned), st));  // barrier counter + the node-block plane mask
   switch (p.nb.bs) {
     case 1: return launch_nb<1>((void*)k_nb_spmv<1>, p, ka, reps, st);
     case 2: return launch_nb<2>((void*)k_nb_spmv<2>, p, ka, reps, st);
@@ -1877,7 +1881,7 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
                    P->coarse + (size_t)2 * COARSE_KMAX_CG * COARSE_KMAX_CG};
   static const int prof_env = getenv("FX_KRYLOV_PROF") ? atoi(getenv("FX_KRYLOV_PROF")) : 0;
   ka.prof = prof_env;
-  FX_CUDA(cudaMemsetAsync(P->bar, 0, sizeof(unsigned), st));
+  FX_CUDA(cudaMemsetAsync(P->bar, 0, 8 * sizeof(unsigned), st));  // barrier counter + the node-block plane mask
   static const int red_env = getenv("FX_RED_ATOMIC") ? atoi(getenv("FX_RED_ATOMIC")) : 1;
   ka.red_atomic = red_env;
   if (red_env) FX_CUDA(cudaMemsetAsync(P->red + (size_t)2 * RED_SLOTS * MAX_GRID, 0, sizeof(double) * (3 * RED_SLOTS + 3 * 8), st));

@@ -24,6 +24,8 @@ struct NbView {
   const int* s_first;   // [N] first (dof, destination) pair of an interface entry (pairs shared with DistDev::s_peer)
   const int* s_remote;  // [nsend] the destination's INTERNAL index of the ghost entry
   const int* s_local;   // [nsend] my INTERNAL index of the pair's dof (-1: outside the node blocks)
+  unsigned* pmask;      // [1] plane slots with a non-zero value in the current matrix (zeroed before the launch)
+  int planemask;        // 0: products load every plane (A/B switch FX_NB_PLANEMASK)
 };
 
 // The block values and columns are read once per product; the work vectors (a few MB) are re-read every pass.  With
@@ -56,19 +58,32 @@ __device__ __forceinline__ int ld_stream1(const int* p, unsigned long long pol) 
 template <int BS>
 __device__ __forceinline__ long long nb_pos_d(int e, int f) {
   constexpr int B2 = BS * BS, NP2 = B2 / 2;
+  const int j = nb_slot(BS, f);
   const long long g = e >> 5;
   const int l = e & 31;
-  return g * 32 * B2 + (f < 2 * NP2 ? (f >> 1) * 64 + 2 * l + (f & 1) : NP2 * 64 + l);
+  return g * 32 * B2 + (j < 2 * NP2 ? (j >> 1) * 64 + 2 * l + (j & 1) : NP2 * 64 + l);
 }
 
 // bval[k] = val[src[k]] for the whole grid (coalesced index reads and value writes, the DOLFIN CSR values are
 // gathered); returns this thread's count of non-zero couplings A[active, eliminated] (must total 0)
+// Also ORs into *B.pmask the plane slots that hold at least one non-zero value in THIS matrix (bit j = plane slot j):
+// the products skip the double2 planes whose two slots are both clear.
+template <int BS>
 __device__ __forceinline__ int nb_gather_values(const NbView& B, const double* __restrict__ val) {
+  constexpr int B2 = BS * BS, NP2 = B2 / 2;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
+  unsigned seen = 0;
   for (long long k = gt; k < B.nslots; k += gs) {
     const int s = ld_stream(B.src + k);
-    B.bval[k] = s >= 0 ? __ldg(val + s) : 0.0;
+    const double x = s >= 0 ? __ldg(val + s) : 0.0;
+    B.bval[k] = x;
+    if (x != 0.0) {
+      const int off = (int)(k % (32 * B2));
+      seen |= 1u << (off < 2 * NP2 * 32 ? 2 * (off / 64) + (off & 1) : B2 - 1);
+    }
   }
+  seen = __reduce_or_sync(0xffffffffu, seen);
+  if ((threadIdx.x & 31) == 0 && seen) atomicOr(B.pmask, seen);
   int bad = 0;
   for (long long k = gt; k < B.nzchk; k += gs) bad += (__ldg(val + ld_stream(B.zchk + k)) != 0.0);
   return bad;
@@ -98,10 +113,11 @@ template <int BS>
 struct NbU { static constexpr int v = BS == 1 ? 8 : BS == 2 ? 2 : 1; };  // groups of 32 entries in flight per pass
 
 // DUALG: the product's input is x + coef * x2, formed on the fly from two gathers.
+// pm: plane mask of the matrix (nb_gather_values); double2 planes without a non-zero value are not loaded.
 template <int BS, bool DUALG = false, class Pre, class Post>
 __device__ __forceinline__ void spmv_nb(const NbView& B, int k0, int k1, const double* x, double* prod,
-                                        unsigned long long pol, Pre&& pre, Post&& post, const double* x2 = nullptr,
-                                        double coef = 0.0) {
+                                        unsigned long long pol, unsigned pm, Pre&& pre, Post&& post,
+                                        const double* x2 = nullptr, double coef = 0.0) {
   constexpr int BP = nb_bp(BS), B2 = BS * BS, NP2 = B2 / 2, U = NbU<BS>::v;
   const int lane = threadIdx.x & 31;
   const int rl = lane / BP, cl = lane - rl * BP;
@@ -126,10 +142,15 @@ __device__ __forceinline__ void spmv_nb(const NbView& B, int k0, int k1, const d
           const double* base = B.bval + (long long)(e >> 5) * (32 * B2) + 2 * (e & 31);
 #pragma unroll
           for (int q = 0; q < NP2; ++q) {
-            const double2 t = ld_stream2(base + q * 64, pol);
-            v[u][2 * q] = t.x; v[u][2 * q + 1] = t.y;
+            double2 t = make_double2(0.0, 0.0);
+            if ((pm >> (2 * q)) & 3u) t = ld_stream2(base + q * 64, pol);  // warp-uniform
+            v[u][nb_f_of_slot(BS, 2 * q)] = t.x; v[u][nb_f_of_slot(BS, 2 * q + 1)] = t.y;
           }
-          if (B2 & 1) v[u][B2 - 1] = ld_stream1(B.bval + (long long)(e >> 5) * (32 * B2) + NP2 * 64 + (e & 31), pol);
+          if (B2 & 1) {
+            double t = 0.0;
+            if ((pm >> (B2 - 1)) & 1u) t = ld_stream1(B.bval + (long long)(e >> 5) * (32 * B2) + NP2 * 64 + (e & 31), pol);
+            v[u][nb_f_of_slot(BS, B2 - 1)] = t;
+          }
         }
       }
 #pragma unroll
@@ -139,6 +160,16 @@ __device__ __forceinline__ void spmv_nb(const NbView& B, int k0, int k1, const d
         if (BS == 1) {
           xv[0] = x[c[u]];
           if (DUALG) xv[0] += coef * x2[c[u]];
+        } else if (BP == 4) {  // one 256-bit load per node (sm_100: LDG.256) instead of two 128-bit ones: the gather's
+                               // L1 wavefronts, not HBM, bound the 3 x 3-block product
+          asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(xv[0]), "=d"(xv[1]), "=d"(xv[2]), "=d"(xv[3])
+                       : "l"(x + (long long)c[u] * 4) : "memory");
+          if (DUALG) {
+            double y0, y1, y2, y3;
+            asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(y0), "=d"(y1), "=d"(y2), "=d"(y3)
+                         : "l"(x2 + (long long)c[u] * 4) : "memory");
+            xv[0] += coef * y0; xv[1] += coef * y1; xv[2] += coef * y2; xv[3] += coef * y3;
+          }
         } else {
 #pragma unroll
           for (int h = 0; h < BP / 2; ++h) {

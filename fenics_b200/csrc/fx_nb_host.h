@@ -15,7 +15,8 @@
 // Value layout ("group planes"): block entries are numbered e = 0 .. ne-1 in block-row order; group g = e / 32 holds
 // 32 entries.  The bs^2 values f = ci*bs + cj of an entry are stored as double2 planes (f = 2q, 2q+1) and, when bs^2
 // is odd, one trailing double plane, so that a warp's loads are contiguous 512-byte (double2) / 256-byte runs:
-//     pos(e, f) = g*32*bs^2 + (f < 2*NP2 ? (f/2)*64 + 2*l + (f&1) : NP2*64 + l),   l = e % 32, NP2 = bs^2 / 2.
+//     pos(e, f) = g*32*bs^2 + (j < 2*NP2 ? (j/2)*64 + 2*l + (j&1) : NP2*64 + l),   l = e % 32, NP2 = bs^2 / 2,
+// j = nb_slot(bs, f) the plane slot of value f (see NB_ORDER below).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -31,11 +32,30 @@ constexpr int nb_chunk(int bs) { return bs == 1 ? 512 : bs == 2 ? 256 : 128; }  
 constexpr int nb_rows(int bs) { return 32 / nb_bp(bs); }                         // block rows per chunk (<=)
 constexpr int NB_WARPS = 32;                                                     // warps per CTA of the kernels using it
 
+// Storage order of the bs^2 values of a block: value f = ci*bs + cj lives in plane slot nb_slot(bs, f).  The order pairs
+// up the values that vanish TOGETHER in the scripts' operators, so a whole double2 plane can be skipped by the product
+// when a matrix has none of them (the per-solve plane mask of nb_gather_values):
+//   bs = 3 (stress):  (xx,xx)(xy,xy) | (yy,yy)(xx,xy) | (xy,xx)(xy,yy) | (xx,yy)(yy,xx) | (yy,xy)
+//                     the upper-convected operators never couple xx with yy (2 of 9 values), a mass matrix has the
+//                     diagonal only (planes 3-5 skipped: 4 of 9 values streamed)
+//   bs = 2 (velocity): (x,x)(y,y) | (x,y)(y,x)
+// plane slot -> f: {0,4,8,1,3,5,2,6,7} (bs = 3), {0,3,1,2} (bs = 2); written without a table so device code can call it
+constexpr int nb_f_of_slot(int bs, int j) {
+  return bs == 3 ? (j == 0 ? 0 : j == 1 ? 4 : j == 2 ? 8 : j == 3 ? 1 : j == 4 ? 3 : j == 5 ? 5 : j == 6 ? 2 : j == 7 ? 6 : 7)
+       : bs == 2 ? (j == 0 ? 0 : j == 1 ? 3 : j == 2 ? 1 : 2)
+                 : j;
+}
+constexpr int nb_slot(int bs, int f) {
+  for (int j = 0; j < bs * bs; ++j)
+    if (nb_f_of_slot(bs, j) == f) return j;
+  return -1;
+}
+
 inline long long nb_pos(long long e, int f, int bs) {
-  const int b2 = bs * bs, np2 = b2 / 2;
+  const int b2 = bs * bs, np2 = b2 / 2, j = nb_slot(bs, f);
   const long long g = e >> 5;
   const int l = (int)(e & 31);
-  return g * 32 * b2 + (f < 2 * np2 ? (f >> 1) * 64 + 2 * l + (f & 1) : np2 * 64 + l);
+  return g * 32 * b2 + (j < 2 * np2 ? (j >> 1) * 64 + 2 * l + (j & 1) : np2 * 64 + l);
 }
 
 struct NbHost {
