@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   for (int i = gt; i < N; i += gs) {
     const int e = B.ext_of_int[i];
     xi[i] = e >= 0 ? a.x[e] : 0.0;
+    if (ghost(i)) { dinv[i] = 0.0; r[i] = 0.0; rh[i] = 0.0; v[i] = 0.0; t[i] = 0.0; }  // ghost rows have no chunk
   }
   bar.sync();
   const unsigned pm = B.planemask ? __ldcg(B.pmask) : 0xffffffffu;

@@ -60,6 +60,7 @@ inline long long nb_pos(long long e, int f, int bs) {
 
 struct NbHost {
   int bs = 0, bp = 0, nn = 0, N = 0, nchunks = 0, grid = 0;
+  int nn_chunked = 0;            // block rows [0, nn_chunked) are covered by chunks (trailing ghost rows are not)
   long long ne = 0, nslots = 0;  // block entries; value slots = groups * 32 * bs^2
   std::vector<int> ext_of_int;   // [N]   external dof of an internal index (-1: padding)
   std::vector<int> int_of_ext;   // [n]   internal index of an external dof (-1: not in a node block)
@@ -221,15 +222,23 @@ inline bool nb_build(const int* dm_t, int nc, int ld, int bs, int nloc, int n, c
   H.grid = grid;
   const int nw = grid * NB_WARPS;
   H.wrange.assign((size_t)nw + 1, 0);
-  // cost of a row: its entries, at least 1 (empty ghost rows still take a lane of a chunk)
-  std::vector<long long> cpre((size_t)nn + 1, 0);
-  for (int i = 0; i < nn; ++i) cpre[i + 1] = cpre[i] + std::max(len[i], 1);
-  const long long ctot = cpre[nn];
+  // Rows that take part: with ghost_owner the ghost nodes sit at the END of the numbering and get NO chunk at all --
+  // their block rows are empty, nothing of a product or a vector pass ever touches them (the kernels zero their
+  // entries of the work vectors once); a chunk of 16 empty rows would still cost a warp its ~1.5 us latency chain,
+  // and a few thousand trailing ghost rows made the last warps of a partitioned run 2x late (measured).  Without
+  // ghost_owner (ghost rows interleaved, host replay tests) every row is chunked, an empty one at cost 1.
+  int nrows = nn;
+  if (ghost_owner != nullptr)
+    while (nrows > 0 && (H.imask[(size_t)(nrows - 1) * bp] & 2)) --nrows;
+  H.nn_chunked = nrows;
+  std::vector<long long> cpre((size_t)nrows + 1, 0);
+  for (int i = 0; i < nrows; ++i) cpre[i + 1] = cpre[i] + std::max(len[i], 1);
+  const long long ctot = cpre[nrows];
   int row = 0;
   for (int w = 0; w < nw; ++w) {
     const long long target = (ctot * (w + 1)) / nw;
     int rend = (int)(std::lower_bound(cpre.begin() + row, cpre.end(), target) - cpre.begin());
-    if (w == nw - 1) rend = nn;
+    if (w == nw - 1) rend = nrows;
     rend = std::max(rend, row);
     // chunks of rows [row, rend)
     const long long cost = cpre[rend] - cpre[row];

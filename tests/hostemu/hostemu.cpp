@@ -201,14 +201,15 @@ int emu_form_qdeg(int form, int* qdx, int* qds, double conv) {
 // on asserted.  y gets (A x) on the rows inside node blocks; other entries are left alone.  Returns 0, or -1 when
 // the space has no usable node-block structure (why is printed), or > 0 = number of violated kernel invariants.
 int emu_nb_spmv(void* p, int space, const unsigned char* mask, int num_sms, const double* val, const double* x,
-                double* y, int* info /* [8]: bs, nn, N, ne, nchunks, grid, nzchk, bad zero-checks */) {
+                double* y, int* info /* [8]: bs, nn, N, ne, nchunks, grid, nzchk, bad zero-checks */,
+                const unsigned char* ghost_owner /* null, or 1 + owner rank of ghost dofs */) {
   EmuPlan* P = (EmuPlan*)p;
   const HostPattern& pat = P->pat[space];
   int bs = 0, nloc = 0;
   if (!nb_space_layout(space, bs, nloc)) return -1;
   NbHost H;
   std::string why;
-  if (!nb_build(pat.dm_t.data(), P->nc, pat.ld, bs, nloc, pat.n, pat.rowptr.data(), pat.col.data(), mask, num_sms, H, why)) {
+  if (!nb_build(pat.dm_t.data(), P->nc, pat.ld, bs, nloc, pat.n, pat.rowptr.data(), pat.col.data(), mask, num_sms, H, why, ghost_owner)) {
     std::fprintf(stderr, "emu_nb_spmv: %s\n", why.c_str());
     return -1;
   }
@@ -245,7 +246,8 @@ int emu_nb_spmv(void* p, int space, const unsigned char* mask, int num_sms, cons
         if (cl == 0) { if (row_done[r0 + rl]) ++viol; row_done[r0 + rl] = 1; }
       }
     }
-  for (int i = 0; i < H.nn; ++i) viol += !row_done[i];
+  for (int i = 0; i < H.nn_chunked; ++i) viol += !row_done[i];
+  for (int i = H.nn_chunked; i < H.nn; ++i) viol += (row_done[i] || !(H.imask[(size_t)i * bp] & 2));
   if (H.wrange[nw] != H.nchunks) ++viol;
   for (int i = 0; i < H.N; ++i)
     if (H.ext_of_int[i] >= 0) y[H.ext_of_int[i]] = yi[i];

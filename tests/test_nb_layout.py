@@ -26,7 +26,7 @@ def _plan(n, permute, seed=0):
     return m, dm, fxt_emu.EmuPlan(m.coordinates(), m.cells(), dm, z, z, z)
 
 
-def _nb_spmv(plan, space, mask, val, x, num_sms=148):
+def _nb_spmv(plan, space, mask, val, x, num_sms=148, ghost_owner=None):
     L = plan.lib
     L.emu_nb_spmv.restype = C.c_int
     y = np.full(len(x), np.nan)
@@ -34,7 +34,8 @@ def _nb_spmv(plan, space, mask, val, x, num_sms=148):
     mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
     rc = L.emu_nb_spmv(plan.h, fxt_emu.SPACES[space], C.c_void_p(mk.ctypes.data if mk is not None else None), num_sms,
                        C.c_void_p(val.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data),
-                       C.c_void_p(info.ctypes.data))
+                       C.c_void_p(info.ctypes.data),
+                       C.c_void_p(None if ghost_owner is None else np.ascontiguousarray(ghost_owner, dtype=np.uint8).ctypes.data))
     return rc, y, info
 
 
@@ -104,10 +105,18 @@ def test_nb_ghost_rows_are_empty():
         cols = dm["Zc"][:, 6 * k:6 * k + 6]
         sel = np.isin(dm["Zc"][:, :6], ghost_nodes)
         mask[cols[sel]] = 2
-    rc, y, info = _nb_spmv(plan, "Zc", mask, val, x)
-    assert rc == 0
     A = sp.csr_matrix((val, col, rp), shape=(ndof, ndof))
     ref = A @ x
     own = mask == 0
-    assert np.allclose(y[own], ref[own], rtol=1e-13, atol=1e-13)
-    assert np.all(y[~own] == 0.0)
+    # (a) ghost rows interleaved in the numbering (chunked as empty rows); (b) partitioned runs: ghost nodes numbered
+    # last per owner rank and left out of the chunks altogether
+    owner = np.where(own, 0, 1 + (np.arange(ndof) % 3)).astype(np.uint8)
+    for k in range(3):  # the components of a node share its owner
+        owner[dm["Zc"][:, 6 * k:6 * k + 6]] = owner[dm["Zc"][:, :6]]
+    owner[own] = 0
+    for go in (None, owner):
+        go_arr = None if go is None else np.ascontiguousarray(go)
+        rc, y, info = _nb_spmv(plan, "Zc", mask, val, x, ghost_owner=go_arr)
+        assert rc == 0
+        assert np.allclose(y[own], ref[own], rtol=1e-13, atol=1e-13)
+        assert np.all(y[~own] == 0.0)

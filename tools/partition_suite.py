@@ -116,12 +116,12 @@ def _parity(case, rank, world, local, n=64, steps=3):
             s.step()
         ref = s.fields()
         key = {"w1": "w1", "p1": "p1", "tau1_vec": "tau1", "rho1": "rho1", "T1": "T1"}
-        err = 0.0
+        err = {}
         for name, v in got.items():
             rv = ref.get(key.get(name, name))
             if rv is None:
                 continue
-            err = max(err, float(np.max(np.abs(v - rv)) / max(np.max(np.abs(rv)), 1e-300)))
+            err[name] = float(np.max(np.abs(v - rv)) / max(np.max(np.abs(rv)), 1e-300))
         del s
     torch.cuda.empty_cache()
     dist.barrier()
@@ -135,8 +135,13 @@ def run(rank, world, local):
     for case in ("cfg2", "cfg3"):
         try:
             row = _case(case, rank, world, local, n_big)
-            row["max_rel_err_vs_single_gpu"] = _parity(case, rank, world, local)
-            row["parity_run"] = "n=64 mesh, 3 steps, solver rtol 1e-12, all result fields"
+            perr = _parity(case, rank, world, local)
+            if perr is not None:
+                row["max_rel_err_vs_single_gpu"] = max(perr.values())
+                row["rel_err_by_field"] = perr
+            row["parity_run"] = "n=64 mesh, 3 steps, solver rtol 1e-12, all result fields" + (
+                "; cfg3 at the script's Ma = 1e-6 has a pressure matrix singular to 1e-10: the pressure LEVEL is determined "
+                "to ~1e-7 only (both runs solve to 1e-12), the other fields agree to 1e-9" if case == "cfg3" else "")
         except Exception as exc:  # reported, not hidden
             row = {"case": case, "error": repr(exc)[:400]}
         out["cases"].append(row)
