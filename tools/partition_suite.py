@@ -14,7 +14,11 @@ import torch
 import torch.distributed as dist
 
 
-def _mk(case, world, device, n, tight=False):
+# config 3 away from the incompressible limit (tests/fxt_ewm.py GENERAL): the parity run's second parameter set
+GENERAL3 = dict(dt=0.002, Re=7.0, We=0.3, Ma=0.05, betav=0.6, al=0.2, Di=0.004, Vh=0.03, Bi=0.2, th=0.7)
+
+
+def _mk(case, world, device, n, tight=False, general=False):
     from fenics_b200 import mesh as pmesh
     from fenics_b200.drivers import ewm, ldc, ldc_dist
     from fenics_b200.mesh import annulus_mesh
@@ -25,6 +29,8 @@ def _mk(case, world, device, n, tight=False):
     else:
         mesh = annulus_mesh(4 * n, n // 4, -0.90, 0.0, 1.0, 0.0, 0.0, 2.0)
         kw = dict(dt=10.0 * mesh.hmin() ** 2)  # the script's dt = 10 hmin^2 of the GLOBAL mesh (main pass)
+        if general:
+            kw = dict(GENERAL3)
         cls = ldc_dist.DistEwmJBP if world > 1 else ewm.EwmJBP
     d = cls(mesh, device=device, **kw)
     d.t = 0.45
@@ -100,9 +106,9 @@ def _case(case, rank, world, local, n, steps=5, warm=3):
     return row
 
 
-def _parity(case, rank, world, local, n=64, steps=3):
+def _parity(case, rank, world, local, n=64, steps=3, general=False):
     """partitioned vs single-GPU fields after `steps` steps at solver rtol 1e-12"""
-    d, _ = _mk(case, world, local, n, tight=True)
+    d, _ = _mk(case, world, local, n, tight=True, general=general)
     for _ in range(steps):
         d.step()
     torch.cuda.synchronize()
@@ -111,7 +117,7 @@ def _parity(case, rank, world, local, n=64, steps=3):
     del d
     err = None
     if rank == 0:
-        s, _ = _mk(case, 1, local, n, tight=True)
+        s, _ = _mk(case, 1, local, n, tight=True, general=general)
         for _ in range(steps):
             s.step()
         ref = s.fields()
@@ -135,13 +141,18 @@ def run(rank, world, local):
     for case in ("cfg2", "cfg3"):
         try:
             row = _case(case, rank, world, local, n_big)
-            perr = _parity(case, rank, world, local)
+            perr = _parity(case, rank, world, local, general=(case == "cfg3"))
             if perr is not None:
                 row["max_rel_err_vs_single_gpu"] = max(perr.values())
                 row["rel_err_by_field"] = perr
-            row["parity_run"] = "n=64 mesh, 3 steps, solver rtol 1e-12, all result fields" + (
-                "; cfg3 at the script's Ma = 1e-6 has a pressure matrix singular to 1e-10: the pressure LEVEL is determined "
-                "to ~1e-7 only (both runs solve to 1e-12), the other fields agree to 1e-9" if case == "cfg3" else "")
+            row["parity_run"] = "n=64 mesh, 3 steps, solver rtol 1e-12, all result fields"
+            if case == "cfg3":
+                # the script's own parameters (Ma = 1e-6: pressure matrix singular to 1e-10, the constant pressure mode
+                # amplifies rounding by ~1e10) are ill-conditioned for ANY two summation orders: reported separately
+                row["parity_run"] += ", parameters away from the incompressible limit (Ma = 0.05, We = 0.3)"
+                ill = _parity(case, rank, world, local)
+                if ill is not None:
+                    row["rel_err_by_field_script_parameters"] = ill
         except Exception as exc:  # reported, not hidden
             row = {"case": case, "error": repr(exc)[:400]}
         out["cases"].append(row)
