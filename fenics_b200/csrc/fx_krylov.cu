@@ -1952,7 +1952,9 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
     if ((rc = nb_ensure(P, space))) return rc;
     // partitioned run: the halo pushes need the neighbours' INTERNAL indices (fx_plan_set_halo_solver_index) and the
     // peer regions must hold the internal vectors; otherwise the scalar kernel below serves the solve
-    const bool nb_ok = p.nb.state == 1 && (!part || (p.nb.s_first != nullptr && (long long)p.nb.N <= P->dist.nmax));
+    // (... and a vector stride that keeps every work vector 32-byte aligned: node blocks are gathered with 256-bit loads)
+    const bool nb_ok = p.nb.state == 1 &&
+                       (!part || (p.nb.s_first != nullptr && (long long)p.nb.N <= P->dist.nmax && P->dist.nmax % 4 == 0));
     if (nb_ok) {
       if (!part) {
         if ((rc = ensure_work(P, ((size_t)std::max(p.n, p.nb.N) + 3) & ~(size_t)3))) return rc;

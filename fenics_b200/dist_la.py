@@ -52,7 +52,8 @@ class DistContext:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         # stride of the work vectors inside a region: the Krylov kernels keep them in the internal node-major numbering,
         # which pads the 3 stress components of a node to 4 doubles (fx_nb_host.h)
-        nmax = (4 * int(lp.n_local_max) + 2) // 3 + 8
+        # (a multiple of 4 doubles: the kernels gather node blocks with 16- and 32-byte loads)
+        nmax = ((4 * int(lp.n_local_max) + 2) // 3 + 8 + 3) // 4 * 4
         nbytes = int(lib.fx_peer_region_bytes(nmax))
         self._region = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
         self._region.zero_()

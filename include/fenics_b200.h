@@ -309,7 +309,7 @@ int fx_plan_set_halo(fx_plan* plan, int space, int nsend, const int* peer, const
  * neighbour's copy of the work vector, so it needs the neighbour's INTERNAL index of the ghost entry:
  *   fx_space_solver_index          int_of_ext[n] of this rank's plan (-1: dof outside the node blocks, e.g. the eliminated
  *                                  DEVSS rows); *n_internal = length of the internal vectors (peer regions must hold
- *                                  vectors that long: pass nmax >= n_internal to fx_plan_set_peer_regions).  Call after
+ *                                  vectors that long: pass nmax >= n_internal, a multiple of 4, to fx_plan_set_peer_regions).  Call after
  *                                  fx_plan_set_eliminated_dofs / fx_plan_set_halo.  FX_ERR_UNSUPPORTED: no such layout.
  *   fx_plan_set_halo_solver_index  remote_internal[k] = the destination rank's int_of_ext[remote[k]] for every pair k of
  *                                  the preceding fx_plan_set_halo call (same order; -1 where the dof lies outside the
