@@ -165,13 +165,13 @@ class ReplicatedSolver:
         self.b = la.Vector(self.gplan, space, self.buf[self.nnz:self.nnz + self.n])
         self.x = la.Vector(self.gplan, space, self.buf[self.nnz + self.n:])
 
-    def solve(self, A, x, b, method, pc, rtol, atol=None, maxit=None):
+    def solve(self, A, x, b, method, pc, rtol, atol=None, maxit=None, ticket=None):
         self.buf.zero_()
         self.buf.index_copy_(0, self.dst, torch.cat([A.val.index_select(0, self.lpos), b.t.index_select(0, self.own),
                                                      x.t.index_select(0, self.own)]))
         if dist.is_initialized() and dist.get_world_size(self.ctx.group) > 1:
             dist.all_reduce(self.buf, group=self.ctx.group)
-        info = la.krylov_solve(self.A, self.x, self.b, method, pc, rtol=rtol, atol=atol, maxit=maxit)
+        info = la.krylov_solve(self.A, self.x, self.b, method, pc, rtol=rtol, atol=atol, maxit=maxit, ticket=ticket)
         torch.index_select(self.x.t, 0, self.l2g, out=x.t)
         return info
 
@@ -204,7 +204,7 @@ def _diag_inv(ctx, A, pc):
     return torch.where(d != 0, 1.0 / d, torch.ones_like(d))
 
 
-def krylov_solve(ctx, A, x, b, method="bicgstab", pc="default", rtol=1e-5, atol=1e-50, maxit=10000):
+def krylov_solve(ctx, A, x, b, method="bicgstab", pc="default", rtol=1e-5, atol=1e-50, maxit=10000, ticket=None):
     """Distributed solve(A, x, b, method, pc); x, b are la.Vector on the local (owned+ghost) dofs.
     Same stopping rule as the 1-GPU kernels: ||M^-1 r|| <= max(rtol ||M^-1 b||, atol).  Returns SolveInfo;
     raises RuntimeError like dolfin when not converged."""
@@ -214,6 +214,11 @@ def krylov_solve(ctx, A, x, b, method="bicgstab", pc="default", rtol=1e-5, atol=
         raise ValueError("distributed solver supports bicgstab/cg with jacobi/none")
     sp, n = A.space, A.n
     if ctx.fused:
+        if ticket is not None:  # enqueue only: the outcome lands in the plan's result slot (la.solve_results)
+            check(lib.fx_krylov_solve_async(ctx.plan.h, abi.SPACE_ID[sp], la._ptr(A.val), la._ptr(x.t), la._ptr(b.t),
+                                            la._KSP[method], la._PC[pc], float(rtol), float(atol), int(maxit), int(ticket),
+                                            la._stream()))
+            return None
         info = SolveInfo()
         rc = lib.fx_krylov_solve(ctx.plan.h, abi.SPACE_ID[sp], la._ptr(A.val), la._ptr(x.t), la._ptr(b.t),
                                  la._KSP[method], la._PC[pc], float(rtol), float(atol), int(maxit), C.byref(info), la._stream())

@@ -9,7 +9,7 @@ partitioned variant from one mixin:
 import torch  # noqa: F401
 import torch.distributed as dist
 
-from .. import dist_la
+from .. import dist_la, la
 from .._lib import check, lib
 from ..partition import LocalPartition, rcb_partition
 from ..spaces import function_spaces
@@ -56,15 +56,36 @@ def distributed(base):
             pc = pc or self.solver[1]
             rtol = (self.solve_rtol if rtol is None else rtol) or 1e-5
             self.solve_labels.append("%s:%s:%s" % (label, A.space, method))
+            # check = False: the solves are only enqueued (fused kernels / replicated solves) and their outcomes fetched
+            # once per step -- the host no longer waits for every solve before it can enqueue the next assembly
+            lazy = not self.check and self.ctx.fused
+            if self._ticket == 0:
+                self._order, self._qticket = [], 0
             with self._phase("solve:%s:%s:%s" % (label, A.space, method)):
                 if self.rep_q is not None and A.space == "Q":
-                    self.last_info.append(self.rep_q.solve(A, x.vector(), b, method, pc, rtol))
+                    info = self.rep_q.solve(A, x.vector(), b, method, pc, rtol, ticket=self._qticket if lazy else None)
+                    if lazy:
+                        self._order.append(("q", self._qticket))
+                        self._qticket += 1
                 else:
-                    self.last_info.append(dist_la.krylov_solve(self.ctx, A, x.vector(), b, method, pc, rtol=rtol))
+                    info = dist_la.krylov_solve(self.ctx, A, x.vector(), b, method, pc, rtol=rtol,
+                                                ticket=len(self._order) - self._qticket if lazy else None)
+                    if lazy:
+                        self._order.append(("l", len(self._order) - self._qticket))
+                if lazy:
+                    self._ticket += 1   # solves enqueued this step (base class: reset at the start of step())
+                else:
+                    self.last_info.append(info)
 
         def _finish_step(self, allow_pipeline=True):
             if self.world > 1:
                 dist.all_reduce(self.scal, group=self.group)  # functionals: owned cells summed over ranks
+            if not self.check and self.ctx.fused and self._ticket:
+                nq = self._qticket
+                got = {"l": la.solve_results(self.plan, 0, self._ticket - nq) if self._ticket > nq else [],
+                       "q": la.solve_results(self.rep_q.gplan, 0, nq) if nq else []}
+                self.last_info = [got[k][i] for k, i in self._order]
+                self._check_infos(self.last_info, self.solve_labels)
             self._scal_host.copy_(self.scal, non_blocking=False)
             return self._scal_host.numpy()
 
