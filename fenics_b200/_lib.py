@@ -8,7 +8,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfenics_b200.so")
+# FX_LIB: another build of the same library (tuning experiments: tools/build_variants.sh), never a different backend
+SO_PATH = os.environ.get("FX_LIB") or os.path.join(_HERE, "libfenics_b200.so")
 
 
 class FxError(RuntimeError):

@@ -20,6 +20,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef FX_NB_PU
+#define FX_NB_PU 2
+#endif
+
 namespace fx {
 
 // optional phase timestamps (FX_KRYLOV_PROF=1): block 0 / thread 0 stamps %globaltimer at phase boundaries
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   double* xi = a.w + 7 * ld;
   double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
   const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
-  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  const int k0 = B.wrange[gw * (NB_SLOTS / NB_WARPS)], k1 = B.wrange[(gw + 1) * (NB_SLOTS / NB_WARPS)];
   // the warp OWNS the internal rows of its chunks (a contiguous range): it computes them in the SpMV epilogues and
   // updates them in the vector passes, so a pass is one batch of coalesced loads per lane -- no grid-stride loop
   int i0 = 0, i1 = 0;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   int restarts = 0;
   int np = 0;
   stamp(a.prof, np);
-  constexpr int PU = 2;  // pass unroll: 32 * PU owned entries per batch of loads
+  constexpr int PU = FX_NB_PU;  // pass unroll: 32 * PU owned entries per batch of loads
   for (int it = 1; it <= a.maxit; ++it) {
     double d1[1] = {0.0};
     spmv_nb<BS>(B, k0, k1, p, prod, pol, pm, [&](int i) { return Ops2{dinv[i], rh[i]}; },
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
 // and k_pcg_res.  Serves the consistent-mass projections of the loops (project(., Zc): 29 iterations per step on a 3 x 3
 // node-block matrix) and SPD systems too large or too tightly toleranced for the resident kernel.
 template <int BS>
-__global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(NB_WARPS_CG * 32, 1) k_cg_nb(const __grid_constant__ KArgs a) {
   constexpr int BP = nb_bp(BS);
   __shared__ double sh[4 * 32];
   extern __shared__ __align__(16) double prod_all[];
@@ -680,8 +684,8 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
   double* dinv = a.w + 5 * ld;
   double* xi = a.w + 6 * ld;
   double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
-  const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
-  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  const int gw = blockIdx.x * NB_WARPS_CG + (threadIdx.x >> 5);
+  const int k0 = B.wrange[gw * (NB_SLOTS / NB_WARPS_CG)], k1 = B.wrange[(gw + 1) * (NB_SLOTS / NB_WARPS_CG)];
   int i0 = 0, i1 = 0;
   if (k0 < k1) {
     const int4 da = B.desc[k0], db = B.desc[k1 - 1];
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
   grid_sum_fast<1>(bar, d0, a.red, phase, sh);
   if (!(d0[0] > 0.0)) { out(0, -1, un, bn); return; }
   double alpha = gamma / d0[0], beta = 0.0;
-  constexpr int PU = 2;
+  constexpr int PU = FX_NB_PU;
   for (int it = 1; it <= a.maxit; ++it) {
     double d[3] = {0.0, 0.0, 0.0};
     for (int base = i0 + lane; base < i1; base += 32 * PU) {
@@ -775,7 +779,7 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_cg_nb(const __grid_constan
 // y = A x through the node-block layout, stand-alone (tests and tools/spmv_bench.py): gathers the values, permutes x in,
 // runs `reps` products (a grid barrier between them, as inside a solve) and writes the rows of the node blocks to y
 template <int BS>
-__global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_constant__ KArgs a, int reps) {
+__global__ void __launch_bounds__(NB_WARPS_CG * 32, 1) k_nb_spmv(const __grid_constant__ KArgs a, int reps) {
   extern __shared__ __align__(16) double prod_all[];
   const NbView& B = a.nb;
   const int N = B.N;
@@ -784,8 +788,8 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_nb_spmv(const __grid_const
   double* xi = a.w;
   double* yi = a.w + ld;
   double* prod = prod_all + (size_t)(threadIdx.x >> 5) * (nb_chunk(BS) * BS);
-  const int gw = blockIdx.x * NB_WARPS + (threadIdx.x >> 5);
-  const int k0 = B.wrange[gw], k1 = B.wrange[gw + 1];
+  const int gw = blockIdx.x * NB_WARPS_CG + (threadIdx.x >> 5);
+  const int k0 = B.wrange[gw * (NB_SLOTS / NB_WARPS_CG)], k1 = B.wrange[(gw + 1) * (NB_SLOTS / NB_WARPS_CG)];
   GridBar bar;
   bar.init(a.bar);
   const unsigned long long pol = nb_make_policy(B.l2policy);
@@ -1802,8 +1806,8 @@ static NbView nb_view(const fx_plan* P, const DevPattern& d) {
 }
 
 template <int BS>
-static int launch_nb(void* fn, const DevPattern& d, KArgs& ka, int reps, cudaStream_t st) {
-  const size_t smem = sizeof(double) * NB_WARPS * nb_chunk(BS) * BS;
+static int launch_nb(void* fn, const DevPattern& d, KArgs& ka, int reps, cudaStream_t st, int warps = NB_WARPS_CG) {
+  const size_t smem = sizeof(double) * warps * nb_chunk(BS) * BS;
   static std::vector<void*> done;
   if (std::find(done.begin(), done.end(), fn) == done.end()) {
     FX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1811,7 +1815,7 @@ static int launch_nb(void* fn, const DevPattern& d, KArgs& ka, int reps, cudaStr
   }
   void* args1[] = {(void*)&ka};
   void* args2[] = {(void*)&ka, (void*)&reps};
-  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(d.nb.grid), dim3(NB_WARPS * 32), reps >= 0 ? args2 : args1, smem, st));
+  FX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(d.nb.grid), dim3(warps * 32), reps >= 0 ? args2 : args1, smem, st));
   count_launch(1);
   return FX_OK;
 }
@@ -1964,15 +1968,15 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
       const bool dual = ka.nb.dual != 0;
       if (part) {
         switch (p.nb.bs) {
-          case 1: rc = launch_nb<1>((void*)k_bicgstab_nb<1, false, true>, p, ka, -1, st); break;
-          case 2: rc = launch_nb<2>((void*)k_bicgstab_nb<2, false, true>, p, ka, -1, st); break;
-          default: rc = launch_nb<3>((void*)k_bicgstab_nb<3, false, true>, p, ka, -1, st); break;
+          case 1: rc = launch_nb<1>((void*)k_bicgstab_nb<1, false, true>, p, ka, -1, st, NB_WARPS); break;
+          case 2: rc = launch_nb<2>((void*)k_bicgstab_nb<2, false, true>, p, ka, -1, st, NB_WARPS); break;
+          default: rc = launch_nb<3>((void*)k_bicgstab_nb<3, false, true>, p, ka, -1, st, NB_WARPS); break;
         }
       } else {
         switch (p.nb.bs) {
-          case 1: rc = launch_nb<1>(dual ? (void*)k_bicgstab_nb<1, true, false> : (void*)k_bicgstab_nb<1, false, false>, p, ka, -1, st); break;
-          case 2: rc = launch_nb<2>(dual ? (void*)k_bicgstab_nb<2, true, false> : (void*)k_bicgstab_nb<2, false, false>, p, ka, -1, st); break;
-          default: rc = launch_nb<3>(dual ? (void*)k_bicgstab_nb<3, true, false> : (void*)k_bicgstab_nb<3, false, false>, p, ka, -1, st); break;
+          case 1: rc = launch_nb<1>(dual ? (void*)k_bicgstab_nb<1, true, false> : (void*)k_bicgstab_nb<1, false, false>, p, ka, -1, st, NB_WARPS); break;
+          case 2: rc = launch_nb<2>(dual ? (void*)k_bicgstab_nb<2, true, false> : (void*)k_bicgstab_nb<2, false, false>, p, ka, -1, st, NB_WARPS); break;
+          default: rc = launch_nb<3>(dual ? (void*)k_bicgstab_nb<3, true, false> : (void*)k_bicgstab_nb<3, false, false>, p, ka, -1, st, NB_WARPS); break;
         }
       }
       if (rc == FX_OK && prof_env && p.n > 100000) {  // debugging aid: per-phase microseconds of iterations 2..4

@@ -475,29 +475,31 @@ __device__ __forceinline__ BlockRange balance_partition(const CsrView& A, Bar& b
   return BlockRange{k0, k1, 1};
 }
 
-// x[row] = (b[row] - sum_{j != row} A[row,j] x[j]) / A[row,row] for the eliminated rows, 16 lanes per row
+// x[row] = (b[row] - sum_{j != row} A[row,j] x[j]) / A[row,row] for the eliminated rows, 8 lanes per row
 // (exact for a trailing block with diagonal self-coupling, e.g. the DG0 DEVSS rows of the W systems).
 // Returns the number of non-zero couplings between DIFFERENT eliminated rows seen by this thread.
 __device__ __forceinline__ int back_substitute(const CsrView& A, double* x, const double* b) {
   int bad = 0;
-  const int sub = threadIdx.x & 15;
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, ng = (gridDim.x * blockDim.x) >> 4;
+  // (the DG0 rows hold 13 entries: 8 lanes keep twice as many rows in flight as 16 -- the loop is a chain of dependent
+  // loads, and the node-block kernels run it with 512 threads per CTA)
+  const int sub = threadIdx.x & 7;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ng = (gridDim.x * blockDim.x) >> 3;
   const int rounds = (A.nelim + ng - 1) / ng;  // uniform trip count: the shuffles need whole warps
   for (int it = 0; it < rounds; ++it) {
     const int k = it * ng + g;
     const int row = k < A.nelim ? A.elim_rows[k] : -1;
     double s = 0.0, dg = 0.0;
     if (row >= 0)
-      for (int j = A.rowptr[row] + sub; j < A.rowptr[row + 1]; j += 16) {
+      for (int j = A.rowptr[row] + sub; j < A.rowptr[row + 1]; j += 8) {
         const int c = A.col[j];
         const double v = A.val[j];
         if (c == row) dg = v;
         else if (v != 0.0) { s += v * x[c]; bad += (A.elim[c] & MASK_ELIM); }
       }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o, 16);
-      dg += __shfl_xor_sync(0xffffffffu, dg, o, 16);
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o, 8);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o, 8);
     }
     if (row >= 0 && sub == 0) x[row] = (b[row] - s) / dg;
   }

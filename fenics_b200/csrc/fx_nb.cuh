@@ -73,13 +73,28 @@ __device__ __forceinline__ int nb_gather_values(const NbView& B, const double* _
   constexpr int B2 = BS * BS, NP2 = B2 / 2;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
   unsigned seen = 0;
-  for (long long k = gt; k < B.nslots; k += gs) {
-    const int s = ld_stream(B.src + k);
-    const double x = s >= 0 ? __ldg(val + s) : 0.0;
-    B.bval[k] = x;
-    if (x != 0.0) {
-      const int off = (int)(k % (32 * B2));
-      seen |= 1u << (off < 2 * NP2 * 32 ? 2 * (off / 64) + (off & 1) : B2 - 1);
+  // GU independent (index -> value -> store) chains per thread: the gather is latency bound, not bandwidth bound
+  constexpr int GU = 4;
+  for (long long k0 = gt; k0 < B.nslots; k0 += GU * gs) {
+    int s[GU];
+    double x[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      const long long k = k0 + u * gs;
+      s[u] = k < B.nslots ? ld_stream(B.src + k) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) x[u] = s[u] >= 0 ? __ldg(val + s[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      const long long k = k0 + u * gs;
+      if (k < B.nslots) {
+        B.bval[k] = x[u];
+        if (x[u] != 0.0) {
+          const int off = (int)(k % (32 * B2));
+          seen |= 1u << (off < 2 * NP2 * 32 ? 2 * (off / 64) + (off & 1) : B2 - 1);
+        }
+      }
     }
   }
   seen = __reduce_or_sync(0xffffffffu, seen);
@@ -109,8 +124,15 @@ __device__ __forceinline__ double nb_diag_inv(const NbView& B, int i, int pc) {
 //                 epilogue post(i, (A x)_i, pre(i)); pre(i) is issued before the stream so its loads overlap it.
 // Padding components (bs = 3 -> 4) run the epilogue with (A x)_i = 0 so every work vector stays zero there.
 // smem: this warp's slice, nb_chunk(BS) * BS doubles.
+// tuning knobs (tools/build_variants.sh): rounds of 32 entries a lane keeps in flight per pass
+#ifndef FX_NB_U2
+#define FX_NB_U2 2
+#endif
+#ifndef FX_NB_U3
+#define FX_NB_U3 1
+#endif
 template <int BS>
-struct NbU { static constexpr int v = BS == 1 ? 8 : BS == 2 ? 2 : 1; };  // groups of 32 entries in flight per pass
+struct NbU { static constexpr int v = BS == 1 ? 8 : BS == 2 ? FX_NB_U2 : FX_NB_U3; };  // groups of 32 entries in flight per pass
 
 // DUALG: the product's input is x + coef * x2, formed on the fly from two gathers.
 // pm: plane mask of the matrix (nb_gather_values); double2 planes without a non-zero value are not loaded.

@@ -30,7 +30,22 @@ namespace fx {
 constexpr int nb_bp(int bs) { return bs == 3 ? 4 : bs; }                         // padded components per node
 constexpr int nb_chunk(int bs) { return bs == 1 ? 512 : bs == 2 ? 256 : 128; }   // block entries per chunk (<=)
 constexpr int nb_rows(int bs) { return 32 / nb_bp(bs); }                         // block rows per chunk (<=)
-constexpr int NB_WARPS = 32;                                                     // warps per CTA of the kernels using it
+// The layout splits the work of a CTA into NB_SLOTS contiguous chunk ranges; a kernel with W warps per CTA gives each warp
+// NB_SLOTS / W consecutive slots, so every kernel chooses its own CTA size on the SAME layout:
+//   BiCGStab: 16 warps x 128 registers -- the kernel keeps its whole working set in registers (at 32 warps x 64
+//     registers it spilled 0.6-1.1 KB per thread inside the product loops).  Per iteration at n = 192, 32 / 24 / 20 / 16
+//     / 12 warps: W 49.1 / 40.0 / 38.1 / 33.7 / 40.5 us, Zc 86.6 / 72.4 / 71.1 / 72.5 / 86.0 us (tools/build_variants.sh);
+//   CG and the stand-alone product: 32 warps (no spills at 64 registers; more loads in flight).
+constexpr int NB_SLOTS = 32;
+#ifndef FX_NB_WARPS
+#define FX_NB_WARPS 16
+#endif
+#ifndef FX_NB_WARPS_CG
+#define FX_NB_WARPS_CG 32
+#endif
+constexpr int NB_WARPS_CG = FX_NB_WARPS_CG;
+static_assert(NB_SLOTS % FX_NB_WARPS == 0 && NB_SLOTS % FX_NB_WARPS_CG == 0, "warps per CTA must divide the slot count");
+constexpr int NB_WARPS = FX_NB_WARPS;                                                     // warps per CTA of k_bicgstab_nb
 
 // Storage order of the bs^2 values of a block: value f = ci*bs + cj lives in plane slot nb_slot(bs, f).  The order pairs
 // up the values that vanish TOGETHER in the scripts' operators, so a whole double2 plane can be skipped by the product
@@ -69,7 +84,7 @@ struct NbHost {
   std::vector<int> bre;          // [nn]  one past the last block entry of the block row
   std::vector<int> diag;         // [nn]  block entry of the diagonal block (-1: empty row)
   std::vector<int> desc;         // [4*nchunks] {first block row, block rows, first entry, one past the last entry}
-  std::vector<int> wrange;       // [grid*NB_WARPS + 1] chunk range of every warp
+  std::vector<int> wrange;       // [grid*NB_SLOTS + 1] chunk range of every warp slot
   std::vector<int> zchk;         // CSR value positions A[active, eliminated] that must be exactly zero
   std::vector<uint8_t> imask;    // [N] row mask in internal numbering (MASK_GHOST / MASK_IFACE bits; 0 for padding)
 };
@@ -217,10 +232,10 @@ inline bool nb_build(const int* dm_t, int nc, int ld, int bs, int nloc, int n, c
   // chunks of <= nb_rows block rows and <= nb_chunk entries of (nearly) equal size
   const int CH = nb_chunk(bs), RM = nb_rows(bs);
   const long long per_warp_min = CH / 2;
-  int grid = (int)std::min<long long>(num_sms, std::max<long long>(1, (ne + NB_WARPS * per_warp_min - 1) / (NB_WARPS * per_warp_min)));
-  grid = std::max(grid, std::min(num_sms, (nn + NB_WARPS * RM - 1) / (NB_WARPS * RM)));  // rows without entries still need lanes
+  int grid = (int)std::min<long long>(num_sms, std::max<long long>(1, (ne + NB_SLOTS * per_warp_min - 1) / (NB_SLOTS * per_warp_min)));
+  grid = std::max(grid, std::min(num_sms, (nn + NB_SLOTS * RM - 1) / (NB_SLOTS * RM)));  // rows without entries still need lanes
   H.grid = grid;
-  const int nw = grid * NB_WARPS;
+  const int nw = grid * NB_SLOTS;
   H.wrange.assign((size_t)nw + 1, 0);
   // Rows that take part: with ghost_owner the ghost nodes sit at the END of the numbering and get NO chunk at all --
   // their block rows are empty, nothing of a product or a vector pass ever touches them (the kernels zero their

@@ -220,7 +220,7 @@ int emu_nb_spmv(void* p, int space, const unsigned char* mask, int num_sms, cons
   for (int j : H.zchk) bad += (val[j] != 0.0);
   std::vector<double> xi((size_t)H.N, 0.0), yi((size_t)H.N, 0.0), prod((size_t)CH * bs);
   for (int i = 0; i < H.N; ++i) xi[i] = H.ext_of_int[i] >= 0 ? x[H.ext_of_int[i]] : 0.0;
-  const int nw = H.grid * NB_WARPS;
+  const int nw = H.grid * NB_SLOTS;
   std::vector<char> row_done(H.nn, 0);
   for (int w = 0; w < nw; ++w)
     for (int k = H.wrange[w]; k < H.wrange[w + 1]; ++k) {
