@@ -3,6 +3,11 @@
 #include "fx_la_common.cuh"
 #include "fx_nb_host.h"
 
+// tuning knob (tools/build_variants.sh): independent index -> value -> store chains per thread of the value gather
+#ifndef FX_NB_GU
+#define FX_NB_GU 4
+#endif
+
 namespace fx {
 
 struct NbView {
@@ -74,7 +79,7 @@ __device__ __forceinline__ int nb_gather_values(const NbView& B, const double* _
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
   unsigned seen = 0;
   // GU independent (index -> value -> store) chains per thread: the gather is latency bound, not bandwidth bound
-  constexpr int GU = 4;
+  constexpr int GU = FX_NB_GU;
   for (long long k0 = gt; k0 < B.nslots; k0 += GU * gs) {
     int s[GU];
     double x[GU];
