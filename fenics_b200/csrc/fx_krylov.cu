@@ -461,9 +461,19 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   GridBarT<DIST> bar;
   bar.init(a.bar, &a.dd, sh_x);
   auto out = [&](int it, int conv, double rn, double bn) {  // every exit: x back to the external numbering
-    for (int i = i0 + lane; i < i1; i += 32) {
-      const int e = B.ext_of_int[i];
-      if (e >= 0 && !ghost(i)) a.x[e] = xi[i];
+    for (int ib = i0 + lane; ib < i1; ib += 32 * 4) {       // (4 independent index -> store chains per lane)
+      int e[4];
+      double xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = ib + 32 * u;
+        e[u] = i < i1 ? B.ext_of_int[i] : -1;
+        xv[u] = i < i1 ? xi[i] : 0.0;
+        if (i < i1 && ghost(i)) e[u] = -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e[u] >= 0) a.x[e[u]] = xv[u];
     }
     leave(bar, a, it, conv, rn, bn);
   };
@@ -474,10 +484,24 @@ __global__ void __launch_bounds__(NB_WARPS * 32, 1) k_bicgstab_nb(const __grid_c
   } while (0)
   double acc[3] = {0.0, 0.0, 0.0};
   acc[2] = (double)nb_gather_values<BS>(B, a.A.val);
-  for (int i = gt; i < N; i += gs) {
-    const int e = B.ext_of_int[i];
-    xi[i] = e >= 0 ? a.x[e] : 0.0;
-    if (ghost(i)) { dinv[i] = 0.0; r[i] = 0.0; rh[i] = 0.0; v[i] = 0.0; t[i] = 0.0; }  // ghost rows have no chunk
+  for (int ib = gt; ib < N; ib += 4 * gs) {  // x into the internal numbering (4 independent gathers per thread)
+    int e[4];
+    double xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = ib + u * gs;
+      e[u] = i < N ? B.ext_of_int[i] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = e[u] >= 0 ? a.x[e[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = ib + u * gs;
+      if (i < N) {
+        xi[i] = xv[u];
+        if (ghost(i)) { dinv[i] = 0.0; r[i] = 0.0; rh[i] = 0.0; v[i] = 0.0; t[i] = 0.0; }  // ghost rows have no chunk
+      }
+    }
   }
   bar.sync();
   const unsigned pm = B.planemask ? __ldcg(B.pmask) : 0xffffffffu;
