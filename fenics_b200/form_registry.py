@@ -5,8 +5,10 @@ Functions that only know their space and their fx_field slot, `Parameter`s named
 registers the resulting signature.  A script that builds the same forms (same statements) with its own Functions and
 Parameters is then served by the hand-written functors: `assemble(a1)` is literal.
 
-Covered: lid-driven-cavity/incomp_LDC.py (config 1), all ten forms and both functionals of the time loop.  The other
-loops are driven through `fenics_b200.drivers.*` (fx_form ids directly); their forms can be registered the same way.
+Covered: lid-driven-cavity/incomp_LDC.py (config 1: ten forms, both functionals) and
+lid-driven-cavity/comp_LDC_mesh_convergence.py (config 2, the bench configuration: twelve forms through lhs() / rhs(), both
+functionals).  The other loops are driven through `fenics_b200.drivers.*` (fx_form ids directly); their forms can be
+registered the same way.
 """
 from . import _abi as abi
 from . import symbolic as S
@@ -129,6 +131,93 @@ def _register_cfg1():
     del DEVSSl_u1, DEVSSr_u1
 
 
+def _register_cfg2():
+    """lid-driven-cavity/comp_LDC_mesh_convergence.py (config 2): trial/test functions :203-217, DEVSS :343-349, loop
+    :392-549.  The script writes the two momentum steps and the stress step as ONE residual each and splits it with
+    lhs() / rhs(); symbolic.lhs / rhs do the same split, so the registered trees are the script's."""
+    from .shims._common import Dcomp, Dincomp, Fdef_incompressible as Fdef, ldc_sigma as sigma
+    from .symbolic import CellDiameter, FacetNormal, Parameter, div, dot, ds, dx, grad, inner, lhs, nabla_grad, rhs
+    A = abi
+    Re, We, Ma, dt, betav, th, conv, c1, c2 = (Parameter(n_, 1.0) for n_ in
+                                               ("Re", "We", "Ma", "dt", "betav", "th", "conv", "c1", "c2"))
+    T = TemplateFunction
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    p0, p1, rho0, rho1 = T("Q", A.FX_F_P0), T("Q", A.FX_F_P1), T("Q", A.FX_F_RHO0), T("Q", A.FX_F_RHO1)
+    tau0_vec, tau1_vec, kapp = T("Zc", A.FX_F_TAU0), T("Zc", A.FX_F_TAU1), T("Qt", A.FX_F_KAPP)
+    h, n = CellDiameter(), FacetNormal()
+    rho = p = arguments("Q", 1)
+    q = arguments("Q", 0)
+    tau_vec, Rt_vec = arguments("Zc", 1), arguments("Zc", 0)
+    (u, D_vec), (v, R_vec) = arguments("W", 1), arguments("W", 0)
+    D, tau, R, Rt = _sym3(D_vec), _sym3(tau_vec), _sym3(R_vec), _sym3(Rt_vec)
+    (u0, D0_vec), (u12, D12_vec), (us, _), (u1, _) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D12, tau0 = _sym3(D0_vec), _sym3(D12_vec), _sym3(S.as_expr(tau0_vec))
+
+    DEVSSl_u12 = 2 * (1 - betav) * inner(Dcomp(u), Dincomp(v)) * dx            # :346
+    DEVSSl_u1 = 2 * (1 - betav) * inner(Dcomp(u), Dincomp(v)) * dx             # :348
+    LPSl_stress = inner(kapp * h * c1 * grad(tau), grad(Rt)) * dx + inner(kapp * h * c2 * div(tau), div(Rt)) * dx  # :402
+    DEVSSr_u12 = 2 * (1 - betav) * inner(D0, Dincomp(v)) * dx                  # :412
+    U = 0.5 * (u + u0)                                                         # :414
+    # density half step :417-421
+    rho_eq = 2.0 * (rho - rho0) / dt + dot(u0, grad(rho0)) - rho0 * div(u0)
+    rho_weak = inner(rho_eq, q) * dx
+    _reg(lhs(rho_weak), A.FX_FORM_C2_A0, "a0 = lhs(rho_weak) (comp_LDC_mesh_convergence.py:420)")
+    _reg(rhs(rho_weak), A.FX_FORM_C2_L0, "L0 = rhs(rho_weak) (comp_LDC_mesh_convergence.py:421)")
+    # velocity half step :430-443
+    lhsFu12 = Re * rho0 * (2.0 * (u - u0) / dt + conv * dot(u0, nabla_grad(u0)))
+    Fu12 = dot(lhsFu12, v) * dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v)) * dx \
+        + dot(p0 * n, v) * ds - dot(betav * nabla_grad(U) * n, v) * ds - (1.0 / 3) * betav * dot(div(U) * n, v) * ds \
+        - dot(tau0 * n, v) * ds \
+        + inner(D - Dcomp(u), R) * dx
+    a1, L1 = lhs(Fu12), rhs(Fu12)
+    a1 += th * DEVSSl_u12
+    L1 += th * DEVSSr_u12
+    _reg(a1, A.FX_FORM_C2_A1, "a1 = lhs(Fu12) + th*DEVSSl_u12 (comp_LDC_mesh_convergence.py:439,442)")
+    _reg(L1, A.FX_FORM_C2_L1, "L1 = rhs(Fu12) + th*DEVSSr_u12 (comp_LDC_mesh_convergence.py:440,443)")
+    DEVSSr_u1 = 2 * (1 - betav) * inner(D12, Dincomp(v)) * dx                  # :454
+    # predictor :458-473
+    lhsFus = Re * rho0 * ((u - u0) / dt + conv * dot(u12, nabla_grad(u12)))
+    Fus = dot(lhsFus, v) * dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v)) * dx \
+        + 0.5 * dot(p0 * n, v) * ds - dot(betav * nabla_grad(U) * n, v) * ds - (1.0 / 3) * betav * dot(div(U) * n, v) * ds \
+        - dot(tau0 * n, v) * ds \
+        + inner(D - Dcomp(u), R) * dx
+    a2, L2 = lhs(Fus), rhs(Fus)
+    a2 += th * DEVSSl_u1
+    L2 += th * DEVSSr_u1
+    _reg(a2, A.FX_FORM_C2_A2, "a2 = lhs(Fus) + th*DEVSSl_u1 (comp_LDC_mesh_convergence.py:469,472)")
+    _reg(L2, A.FX_FORM_C2_L2, "L2 = rhs(Fus) + th*DEVSSr_u1 (comp_LDC_mesh_convergence.py:470,473)")
+    # pressure :483-490
+    lhs_p_1 = (Ma * Ma / (dt * Re)) * p
+    rhs_p_1 = (Ma * Ma / (dt * Re)) * p0 - rho0 * div(us) + dot(grad(rho0), us)
+    lhs_p_2 = 0.5 * dt * grad(p)
+    rhs_p_2 = 0.5 * dt * grad(p0)
+    _reg(inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx, A.FX_FORM_C2_A5, "a5 (comp_LDC_mesh_convergence.py:489)")
+    _reg(inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx, A.FX_FORM_C2_L5, "L5 (comp_LDC_mesh_convergence.py:490)")
+    # velocity update :506-512 (rho1 is the PROJECTED density, a Function of Q, :502)
+    lhs_u1 = (Re / dt) * rho1 * u
+    rhs_u1 = (Re / dt) * rho1 * us
+    a7 = inner(lhs_u1, v) * dx + inner(D - Dcomp(u), R) * dx
+    L7 = inner(rhs_u1, v) * dx + 0.5 * inner(p1 - p0, div(v)) * dx - 0.5 * dot(p1 * n, v) * ds
+    a7 += 0
+    L7 += 0
+    _reg(a7, A.FX_FORM_C2_A7, "a7 (comp_LDC_mesh_convergence.py:509)")
+    _reg(L7, A.FX_FORM_C2_L7, "L7 (comp_LDC_mesh_convergence.py:510)")
+    # stress :528-537
+    lhs_tau1 = (We / dt + 1.0) * tau + We * Fdef(u1, tau)
+    rhs_tau1 = (We / dt) * tau0 + 2.0 * (1.0 - betav) * Dcomp(u1)
+    Ares = inner(lhs_tau1, Rt) * dx - inner(rhs_tau1, Rt) * dx
+    a4, L4 = lhs(Ares), rhs(Ares)
+    a4 += LPSl_stress
+    L4 += 0
+    _reg(a4, A.FX_FORM_C2_A4, "a4 = lhs(A) + LPSl_stress (comp_LDC_mesh_convergence.py:533,536)")
+    _reg(L4, A.FX_FORM_C2_L4, "L4 = rhs(A) (comp_LDC_mesh_convergence.py:534,537)")
+    # energies :548-549
+    _reg(0.5 * rho1 * dot(u1, u1) * dx, A.FX_FORM_C2_EK, "E_k (comp_LDC_mesh_convergence.py:548)")
+    _reg((tau1_vec[0] + tau1_vec[2]) * dx, A.FX_FORM_C2_EE, "E_e (comp_LDC_mesh_convergence.py:549)")
+
+
 def _reg(form, fid, what):
     _, ctx = form.signature()
     S.register(form, fid, [c.slot for c in ctx.coefs], what)
@@ -139,3 +228,4 @@ def load():
     if not _loaded:
         _loaded = True
         _register_cfg1()
+        _register_cfg2()

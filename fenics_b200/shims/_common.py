@@ -187,6 +187,18 @@ def Fdef_compressible(u, Tau):
     return Fdef_incompressible(u, Tau) + A.div(u) * Tau
 
 
+def ldc_sigmain(u, p, Tau, We, betav):
+    """lid-driven-cavity/fenics_fem.py:304-305: incompressible total stress 2 betav D(u) - p I + (1-betav)/We (Tau - I)"""
+    I = alg(u).Identity(len(u))
+    return 2 * betav * Dincomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
+
+
+def ldc_sigma(u, p, Tau, We, betav):
+    """lid-driven-cavity/fenics_fem.py:307-308: compressible total stress, deviatoric rate of strain"""
+    I = alg(u).Identity(len(u))
+    return 2 * betav * Dcomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
+
+
 def reshape_elements(D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec):
     """the seven 3-vectors as symmetric 2x2 tensors [[a,b],[b,c]] (fenics_fem.py:210-225)."""
     A = alg(D0_vec)

@@ -7,6 +7,7 @@ import numpy as np  # noqa: F401
 from fenics_b200 import mesh as _mesh
 from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, TestFunction, TestFunctions,  # noqa: F401
                            TrialFunction, TrialFunctions, assemble, norm, parameters, project, solve)
+from fenics_b200.symbolic import lhs, rhs, system  # noqa: F401
 from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
                                   dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
 from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, Dincomp, LDC_Regular_Mesh, Skew_Mesh,  # noqa: F401
@@ -15,6 +16,7 @@ from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, D
                        reshape_elements, set_algebra, skewcavity, solution_functions, tgrad, trial_functions,
                        update_progress, xskewcavity, yskewcavity)
 from fenics_b200.shims._common import Fdef_compressible as Fdefcon  # noqa: F401
+from fenics_b200.shims._common import ldc_sigma as sigma, ldc_sigmain as sigmain  # noqa: F401
 from fenics_b200.shims._common import Fdef_incompressible as Fdef  # noqa: F401
 
 def end():
@@ -28,18 +30,6 @@ refine_top = _needs_dolfin("refine_top")
 def ramp_function(t):
     """lid ramp 1 + tanh(8(t - 1/2)) (:204-206)"""
     return 1.0 + tanh(8 * (t - 0.5))
-
-
-def sigmain(u, p, Tau, We, betav):
-    """incompressible total stress 2 betav D(u) - p I + (1-betav)/We (Tau - I)  (:304-305)"""
-    I = alg(u).Identity(len(u))
-    return 2 * betav * Dincomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
-
-
-def sigma(u, p, Tau, We, betav):
-    """compressible total stress, deviatoric rate of strain (:307-308)"""
-    I = alg(u).Identity(len(u))
-    return 2 * betav * Dcomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
 
 
 def _driver_of(u):

@@ -84,6 +84,9 @@ class E:
     def __neg__(self):
         return E("neg", (self,), self.shape)
 
+    def __pos__(self):  # the scripts write `... + \ + inner(...)*dx` (comp_LDC_mesh_convergence.py:432-433)
+        return self
+
     def __mul__(self, o):
         if isinstance(o, Measure):
             return Form([(self, o.kind, o.subdomain)])
@@ -330,8 +333,7 @@ ds = Measure("ds")
 
 
 class Form:
-    """sum of integrals; supports the arithmetic the scripts do on forms (a += th*DEVSSl, L -= ..., lhs/rhs are not
-    needed: the loops of the supported configs write a and L separately or the registry holds the split form)"""
+    """sum of integrals; supports the arithmetic the scripts do on forms (a += th*DEVSSl, L -= ...; lhs / rhs below)"""
 
     def __init__(self, integrals):
         self.integrals = list(integrals)
@@ -350,6 +352,9 @@ class Form:
 
     def __neg__(self):
         return (-1.0) * self
+
+    def __pos__(self):
+        return self
 
     def __rmul__(self, c):
         c = as_expr(c)
@@ -372,6 +377,89 @@ class _Ctx:
         self.space_objs = []
 
 
+# ---- lhs / rhs: the scripts that write one residual F(u; v) = 0 and let UFL split it --------------------------
+# (comp_LDC_mesh_convergence.py:439-440 `a1 = lhs(Fu12); L1 = rhs(Fu12)`).  The split is structural: every node is
+# separated into the part that contains the trial function (linearly) and the part that does not.
+_LINEAR_UNARY = ("grad", "nabla_grad", "divop", "T", "tr", "sym", "idx", "neg")
+_BILINEAR = ("mul", "dot", "inner", "outer")
+
+
+def _zero_like(e):
+    z = E("num", data=0.0)
+    return z if e.shape == () else E("zero", (), e.shape)
+
+
+def _split_trial(e):
+    """(part with the trial function, part without); either may be None (= zero)"""
+    if e.op == "arg":
+        return (e, None) if e.data[0] == 1 else (None, e)
+    if not e.a:
+        return None, e
+    if e.op in ("add", "sub"):
+        (aw, ao), (bw, bo) = _split_trial(e.a[0]), _split_trial(e.a[1])
+
+        def comb(x, y):
+            if x is None and y is None:
+                return None
+            if y is None:
+                return x
+            if x is None:
+                return y if e.op == "add" else E("neg", (y,), y.shape)
+            return E(e.op, (x, y), e.shape)
+        return comb(aw, bw), comb(ao, bo)
+    if e.op in _LINEAR_UNARY:
+        w, o = _split_trial(e.a[0])
+        mk = lambda x: None if x is None else E(e.op, (x,), e.shape, e.data)  # noqa: E731
+        return mk(w), mk(o)
+    if e.op in ("vec", "mat"):
+        parts = [_split_trial(c) for c in e.a]
+        if all(w is None for w, _ in parts):
+            return None, e
+        mk = lambda k: E(e.op, [p[k] if p[k] is not None else _zero_like(c) for p, c in zip(parts, e.a)], e.shape, e.data)  # noqa: E731
+        return mk(0), (None if all(o is None for _, o in parts) else mk(1))
+    if e.op in _BILINEAR:
+        (aw, ao), (bw, bo) = _split_trial(e.a[0]), _split_trial(e.a[1])
+        if aw is not None and bw is not None:
+            raise ValueError("lhs/rhs: the form is not linear in the trial function")
+        mk = lambda x, y: E(e.op, (x, y), e.shape, e.data)  # noqa: E731
+        terms = [mk(x, y) for x, y in ((aw, bo), (ao, bw)) if x is not None and y is not None]
+        w = None if not terms else terms[0] if len(terms) == 1 else E("add", terms, e.shape)
+        return w, (mk(ao, bo) if ao is not None and bo is not None else None)
+    if e.op == "div":
+        (aw, ao), (bw, _) = _split_trial(e.a[0]), _split_trial(e.a[1])
+        if bw is not None:
+            raise ValueError("lhs/rhs: trial function in a denominator")
+        mk = lambda x: None if x is None else E("div", (x, e.a[1]), e.shape)  # noqa: E731
+        return mk(aw), mk(ao)
+    if any(_split_trial(c)[0] is not None for c in e.a):  # pow, sqrt ...
+        raise ValueError("lhs/rhs: trial function inside the non-linear operator %r" % e.op)
+    return None, e
+
+
+def lhs(form):
+    """the bilinear part of F (UFL's lhs)"""
+    out = []
+    for e, k, s in form.integrals:
+        w, _ = _split_trial(e)
+        if w is not None:
+            out.append((w, k, s))
+    return Form(out)
+
+
+def rhs(form):
+    """minus the part of F without the trial function (UFL's rhs: F = a - L)"""
+    out = []
+    for e, k, s in form.integrals:
+        _, o = _split_trial(e)
+        if o is not None:
+            out.append((E("neg", (o,), o.shape), k, s))
+    return Form(out)
+
+
+def system(form):
+    return lhs(form), rhs(form)
+
+
 # ---- registry ----------------------------------------------------------------------------------------------
 _REGISTRY = {}
 
@@ -382,7 +470,9 @@ def register(form, form_id, slots, what):
     sig, ctx = form.signature()
     if len(ctx.coefs) != len(slots):
         raise ValueError("%s: %d coefficients in the form, %d slots given" % (what, len(ctx.coefs), len(slots)))
-    _REGISTRY[sig] = (int(form_id), tuple(int(s) for s in slots), what)
+    # two scripts may write the SAME form (the stress matrix of configs 1 and 2 is one operator, served by one functor
+    # under two ids): the first registration stands
+    _REGISTRY.setdefault(sig, (int(form_id), tuple(int(s) for s in slots), what))
 
 
 def recognise(form):

@@ -79,3 +79,97 @@ def test_literal_velocity_half_step_equals_the_driver():
     (u1, D1_vec) = drv.w1.split()
     E_k = assemble(0.5*ff.dot(u1,u1)*dx)
     assert abs(E_k - dapi.assemble(drv.pr.form(abi.FX_FORM_C1_EK))) <= 1e-14 * abs(E_k)
+
+
+def test_literal_config2_forms_through_lhs_rhs_equal_the_driver():
+    """comp_LDC_mesh_convergence.py:414-549: every form of the compressible loop written as the script writes it -- one
+    residual per momentum / stress step, split with lhs() / rhs() -- assembles to what the driver's fx_form ids give."""
+    from fenics_b200.shims.lid_driven_cavity.fenics_fem import (CellDiameter, Dcomp, Dincomp, FacetNormal, Fdef, Parameter,
+                                                                TestFunction, TestFunctions, assemble, div, dot, ds, dx,
+                                                                grad, inner, lhs, nabla_grad, rhs, sigma, trial_functions)
+    drv = ldc.CompLDC(pmesh.Skew_Mesh(12, 1, 1))
+    drv.t = 0.45
+    drv.step()
+    drv.step()                                            # every field non-trivial, w0 != w1
+    S = drv.S
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    pv = drv.p
+    Re, We, Ma, dt, betav, th, conv, c1, c2 = (Parameter(k, pv[k]) for k in
+                                               ("Re", "We", "Ma", "dt", "betav", "th", "conv", "c1", "c2"))
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = trial_functions(Q, Zc, W)
+    rho, q = p, TestFunction(Q)
+    Rt = m3(TestFunction(Zc))
+    (v, R_vec) = TestFunctions(W)
+    R = m3(R_vec)
+    h, n = CellDiameter(drv.mesh), FacetNormal(drv.mesh)
+    w0, w12, ws, w1, p0, p1, rho0, rho1 = drv.w0, drv.w12, drv.ws, drv.w1, drv.p0, drv.p1, drv.rho0, drv.rho1
+    tau0_vec, tau1_vec, kapp = drv.tau0_vec, drv.tau1_vec, drv.kapp
+    (u0, D0_vec), (u12, D12_vec), (us, Ds_vec), (u1, D1_vec) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D12, tau0 = m3(D0_vec), m3(D12_vec), m3(symbolic.as_expr(tau0_vec))
+    DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+    DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+    LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx
+    DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx
+    DEVSSr_u1 = 2*(1-betav)*inner(D12,Dincomp(v))*dx
+    U = 0.5*(u + u0)
+    forms = {}
+    # ---- :417-421
+    rho_eq = 2.0*(rho - rho0)/dt + dot(u0, grad(rho0)) - rho0*div(u0)
+    rho_weak = inner(rho_eq,q)*dx
+    forms["A0"], forms["L0"] = lhs(rho_weak), rhs(rho_weak)
+    # ---- :430-443
+    lhsFu12 = Re*rho0*(2.0*(u - u0) / dt + conv*dot(u0, nabla_grad(u0)))
+    Fu12 = dot(lhsFu12, v)*dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \
+        + dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \
+        - dot(tau0*n, v)*ds \
+        +  inner(D-Dcomp(u),R)*dx
+    a1 = lhs(Fu12)
+    L1 = rhs(Fu12)
+    a1+= th*DEVSSl_u12
+    L1+= th*DEVSSr_u12
+    forms["A1"], forms["L1"] = a1, L1
+    # ---- :458-473
+    lhsFus = Re*rho0*((u - u0)/dt + conv*dot(u12, nabla_grad(u12)))
+    Fus = dot(lhsFus, v)*dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \
+        + 0.5*dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \
+        - dot(tau0*n, v)*ds\
+        +  inner(D-Dcomp(u),R)*dx
+    a2= lhs(Fus)
+    L2= rhs(Fus)
+    a2+= th*DEVSSl_u1
+    L2+= th*DEVSSr_u1
+    forms["A2"], forms["L2"] = a2, L2
+    # ---- :483-490
+    lhs_p_1 = (Ma*Ma/(dt*Re))*p
+    rhs_p_1 = (Ma*Ma/(dt*Re))*p0 - rho0*div(us) + dot(grad(rho0),us)
+    lhs_p_2 = 0.5*dt*grad(p)
+    rhs_p_2 = 0.5*dt*grad(p0)
+    forms["A5"] = inner(lhs_p_1,q)*dx + inner(lhs_p_2,grad(q))*dx
+    forms["L5"] = inner(rhs_p_1,q)*dx + inner(rhs_p_2,grad(q))*dx
+    # ---- :506-512
+    lhs_u1 = (Re/dt)*rho1*u
+    rhs_u1 = (Re/dt)*rho1*us
+    forms["A7"] = inner(lhs_u1,v)*dx  + inner(D-Dcomp(u),R)*dx
+    forms["L7"] = inner(rhs_u1,v)*dx + 0.5*inner(p1-p0,div(v))*dx - 0.5*dot(p1*n, v)*ds
+    # ---- :528-537
+    lhs_tau1 = (We/dt+1.0)*tau  +  We*Fdef(u1,tau)
+    rhs_tau1= (We/dt)*tau0 + 2.0*(1.0-betav)*Dcomp(u1)
+    A = inner(lhs_tau1,Rt)*dx - inner(rhs_tau1,Rt)*dx
+    a4 = lhs(A)
+    L4 = rhs(A)
+    a4 += LPSl_stress
+    L4 += 0
+    forms["A4"], forms["L4"] = a4, L4
+    for name, form in forms.items():
+        fid = getattr(abi, "FX_FORM_C2_" + name)
+        got, want = assemble(form), dapi.assemble(drv.pr.form(fid))
+        a, b = (got.val, want.val) if name.startswith("A") else (got.t, want.t)
+        assert lc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-13, name
+        assert float(b.abs().max()) > 0.0, name
+    E_k = assemble(0.5*rho1*dot(u1,u1)*dx)
+    E_e = assemble((tau1_vec[0]+tau1_vec[2])*dx)
+    assert abs(E_k - dapi.assemble(drv.pr.form(abi.FX_FORM_C2_EK))) <= 1e-14 * abs(E_k)
+    assert abs(E_e - dapi.assemble(drv.pr.form(abi.FX_FORM_C2_EE))) <= 1e-13 * max(abs(E_e), 1e-12)

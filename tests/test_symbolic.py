@@ -109,3 +109,97 @@ def test_unknown_forms_and_structure_sensitivity():
     fid, coefs, params, what, _ = symbolic.recognise(inner(grad(a), grad(q)) * dx + (Re / dt) * inner(us, grad(q)) * dx)
     assert fid == abi.FX_FORM_C1_L5 and [s for s, _ in coefs] == [abi.FX_F_P0, abi.FX_F_WS] and coefs[0][1] is a
     assert params["Re"].value == 3.0 and float(params["dt"]) == 0.1
+
+
+# ---- config 2: lid-driven-cavity/comp_LDC_mesh_convergence.py, whose loop writes residuals and splits them with lhs()/rhs() --
+REF2 = os.path.join(os.path.dirname(REF), "comp_LDC_mesh_convergence.py")
+
+
+def _namespace2(rec):
+    """what the script's set-up section provides before / at the top of the loop body (:201-217, :343-349, :402-414)"""
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    P = symbolic.Parameter
+    ns.update(Re=P("Re", 10.0), We=P("We", 0.25), Ma=P("Ma", 0.001), dt=P("dt", 0.001), betav=P("betav", 0.5),
+              th=P("th", 1.0), conv=P("conv", 1.0), c1=P("c1", 0.1), c2=P("c2", 0.01))
+    A = abi
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    ns.update(w0=w0, w12=w12, ws=ws, w1=w1, p0=T("Q", A.FX_F_P0), p1=T("Q", A.FX_F_P1), rho0=T("Q", A.FX_F_RHO0),
+              rho12=T("Q", A.FX_F_RHO12), rho1=T("Q", A.FX_F_RHO1), tau0_vec=T("Zc", A.FX_F_TAU0),
+              tau1_vec=T("Zc", A.FX_F_TAU1), kapp=T("Qt", A.FX_F_KAPP), h=symbolic.CellDiameter(), n=symbolic.FacetNormal())
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], Ds_vec), (ns["u1"], D1_vec) = (f.split() for f in (w0, w12, ws, w1))
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
+    ns["rho"] = ns["p"]
+    ns["q"] = ff.TestFunction("Q")
+    Rt_vec = ff.TestFunction("Zc")
+    (ns["v"], R_vec) = ff.TestFunctions("W")
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    ns["D0"], ns["D12"], ns["tau0"] = m3(D0_vec), m3(D12_vec), m3(symbolic.as_expr(ns["tau0_vec"]))
+    exec(textwrap.dedent("""
+        DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx
+        DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx
+        DEVSSr_u1 = 2*(1-betav)*inner(D12,Dincomp(v))*dx
+        U = 0.5*(u + u0)
+    """), ns)
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return ("tensor", fid)
+
+    class _BC:
+        def apply(self, *a):
+            rec.append("bc.apply")
+    ns.update(assemble=assemble, bcu=[_BC(), _BC()], bcp=[], bctau=[],
+              solve=lambda A, x, b, *a: rec.append(("solve", A[1], a)))
+    for f in ("w12", "ws", "w1", "p1", "tau1_vec", "rho12"):
+        ns[f].vector = lambda: None
+    return ns
+
+
+def _lines2(a, b):
+    if not os.path.exists(REF2):
+        pytest.skip("reference checkout not present")
+    return textwrap.dedent("\n".join(open(REF2).read().splitlines()[a - 1:b]))
+
+
+@pytest.mark.parametrize("a,b,ids", [(417, 426, (abi.FX_FORM_C2_A0, abi.FX_FORM_C2_L0)),
+                                     (430, 447, (abi.FX_FORM_C2_A1, abi.FX_FORM_C2_L1)),
+                                     (458, 476, (abi.FX_FORM_C2_A2, abi.FX_FORM_C2_L2)),
+                                     (483, 497, (abi.FX_FORM_C2_A5, abi.FX_FORM_C2_L5)),
+                                     (506, 519, (abi.FX_FORM_C2_A7, abi.FX_FORM_C2_L7)),
+                                     (528, 544, (abi.FX_FORM_C1_A4, abi.FX_FORM_C2_L4)),   # a4: one operator, one functor
+                                     (548, 549, (abi.FX_FORM_C2_EK, abi.FX_FORM_C2_EE))])
+def test_text_of_config2_sub_steps_with_lhs_rhs(a, b, ids):
+    """comp_LDC_mesh_convergence.py, one sub-step at a time, verbatim: `a1 = lhs(Fu12); L1 = rhs(Fu12)` (:439-440) ..."""
+    rec = []
+    ns = _namespace2(rec)
+    exec(_lines2(a, b), ns)
+    got = [r[0] for r in rec if isinstance(r, tuple) and r[0] != "solve"]
+    assert tuple(got) == ids
+    if ids[0] == abi.FX_FORM_C2_A1:
+        assert rec[0][1] == [abi.FX_F_RHO0] and set(rec[0][2]) == {"Re", "betav", "dt", "th"}
+        assert rec[1][1] == [abi.FX_F_RHO0, abi.FX_F_W0, abi.FX_F_P0, abi.FX_F_TAU0]
+        assert set(rec[1][2]) == {"Re", "We", "betav", "conv", "dt", "th"}
+        assert rec[-1] == ("solve", abi.FX_FORM_C2_A1, ("bicgstab", "default"))
+
+
+def test_lhs_rhs_split():
+    from fenics_b200.symbolic import Parameter, dx, grad, inner, lhs, rhs, sqrt
+    q, p = form_registry.arguments("Q", 0), form_registry.arguments("Q", 1)
+    f, c = symbolic.as_expr(T("Q", -1)), Parameter("dt", 0.1)
+    F = inner((p - f) / c, q) * dx + inner(grad(0.5 * (p + f)), grad(q)) * dx - f * q * dx
+    a, L = lhs(F), rhs(F)
+    (_, ca), (_, cl) = a.signature(), L.signature()
+    assert ca.args == {0, 1} and not ca.coefs            # every term with the trial function, none of the data
+    assert cl.args == {0} and len(cl.coefs) == 1 and len(L.integrals) == 3 and len(a.integrals) == 2
+    assert all(e.op == "neg" for e, _, _ in L.integrals)  # F = a - L
+    with pytest.raises(ValueError):
+        lhs(inner(p * p, q) * dx)
+    with pytest.raises(ValueError):
+        lhs(inner(sqrt(p), q) * dx)
+    with pytest.raises(ValueError):
+        lhs(inner(f / p, q) * dx)
