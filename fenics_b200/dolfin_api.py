@@ -277,4 +277,14 @@ def project(v, V, function=None, rtol=None):
         la.krylov_solve(M, out.vector(), rhs, "cg", "jacobi",
                         rtol=parameters.get("projection_rtol", 1e-13) if rtol is None else rtol)
         return out
-    raise TypeError("project(): expected a DG0Expr or ConsistentProjection")
+    if isinstance(v, (symbolic.E, symbolic.Operand)):
+        # the script's own expression (`rho1 = project(rho0 + (Ma*Ma/Re)*(p1-p0), Q)`, comp_LDC_mesh_convergence.py:
+        # 501-502): dolfin.project's two forms, recognised like any other literal form
+        w, Pv = TestFunction(V), TrialFunction(V)
+        M = assemble(symbolic.inner(w, Pv) * symbolic.dx)
+        rhs = assemble(symbolic.inner(w, v) * symbolic.dx)
+        out = function if function is not None else Function(V, M.plan)
+        la.krylov_solve(M, out.vector(), rhs, "cg", "jacobi",
+                        rtol=parameters.get("projection_rtol", 1e-13) if rtol is None else rtol)
+        return out
+    raise TypeError("project(): expected a DG0Expr, a ConsistentProjection or a symbolic expression")

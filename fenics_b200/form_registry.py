@@ -195,6 +195,11 @@ def _register_cfg2():
     rhs_p_2 = 0.5 * dt * grad(p0)
     _reg(inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx, A.FX_FORM_C2_A5, "a5 (comp_LDC_mesh_convergence.py:489)")
     _reg(inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx, A.FX_FORM_C2_L5, "L5 (comp_LDC_mesh_convergence.py:490)")
+    # equation of state :501-502: rho1 = project(rho0 + (Ma*Ma/Re)*(p1-p0), Q) -- dolfin.project's mass matrix and
+    # right-hand side (dolfin_api.project builds inner(w, Pv)*dx and inner(w, v)*dx)
+    _reg(inner(q, p) * dx, A.FX_FORM_MASS_Q, "project(., Q): mass matrix")
+    _reg(inner(q, rho0 + (Ma * Ma / Re) * (p1 - p0)) * dx, A.FX_FORM_C2_L_RHO1,
+         "project(rho0 + (Ma*Ma/Re)*(p1-p0), Q) (comp_LDC_mesh_convergence.py:501-502)")
     # velocity update :506-512 (rho1 is the PROJECTED density, a Function of Q, :502)
     lhs_u1 = (Re / dt) * rho1 * u
     rhs_u1 = (Re / dt) * rho1 * us

@@ -173,3 +173,141 @@ def test_literal_config2_forms_through_lhs_rhs_equal_the_driver():
     E_e = assemble((tau1_vec[0]+tau1_vec[2])*dx)
     assert abs(E_k - dapi.assemble(drv.pr.form(abi.FX_FORM_C2_EK))) <= 1e-14 * abs(E_k)
     assert abs(E_e - dapi.assemble(drv.pr.form(abi.FX_FORM_C2_EE))) <= 1e-13 * max(abs(E_e), 1e-12)
+
+
+# the loop body of comp_LDC_mesh_convergence.py:414-549 (statements as the script writes them; the LPS block :392-402 and
+# the field roll :558-562 are the driver's -- they are projections / assignments, not forms)
+CFG2_LOOP_BODY = '''
+U = 0.5*(u + u0)
+rho_eq = 2.0*(rho - rho0)/dt + dot(u0, grad(rho0)) - rho0*div(u0)
+rho_weak = inner(rho_eq,q)*dx
+a0 = lhs(rho_weak)
+L0 = rhs(rho_weak)
+A0 = assemble(a0)
+b0 = assemble(L0)
+[bc.apply(A0, b0) for bc in bcp]
+solve(A0, rho12.vector(), b0, "bicgstab", "default")
+end()
+lhsFu12 = Re*rho0*(2.0*(u - u0) / dt + conv*dot(u0, nabla_grad(u0)))
+Fu12 = dot(lhsFu12, v)*dx + \\
+    + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \\
+    + dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \\
+    - dot(tau0*n, v)*ds \\
+    +  inner(D-Dcomp(u),R)*dx
+a1 = lhs(Fu12)
+L1 = rhs(Fu12)
+a1+= th*DEVSSl_u12
+L1+= th*DEVSSr_u12
+A1 = assemble(a1)
+b1= assemble(L1)
+[bc.apply(A1, b1) for bc in bcu]
+solve(A1, w12.vector(), b1, "bicgstab", "default")
+end()
+(u12, D12_vec) = w12.split()
+D12 = as_matrix([[D12_vec[0], D12_vec[1]],
+                [D12_vec[1], D12_vec[2]]])
+DEVSSr_u1 = 2*(1-betav)*inner(D12,Dincomp(v))*dx
+lhsFus = Re*rho0*((u - u0)/dt + conv*dot(u12, nabla_grad(u12)))
+Fus = dot(lhsFus, v)*dx + \\
+    + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \\
+    + 0.5*dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \\
+    - dot(tau0*n, v)*ds\\
+    +  inner(D-Dcomp(u),R)*dx
+a2= lhs(Fus)
+L2= rhs(Fus)
+a2+= th*DEVSSl_u1
+L2+= th*DEVSSr_u1
+A2 = assemble(a2)
+b2 = assemble(L2)
+[bc.apply(A2, b2) for bc in bcu]
+solve(A2, ws.vector(), b2, "bicgstab", "default")
+end()
+(us, Ds_vec) = ws.split()
+lhs_p_1 = (Ma*Ma/(dt*Re))*p
+rhs_p_1 = (Ma*Ma/(dt*Re))*p0 - rho0*div(us) + dot(grad(rho0),us)
+lhs_p_2 = 0.5*dt*grad(p)
+rhs_p_2 = 0.5*dt*grad(p0)
+a5=inner(lhs_p_1,q)*dx + inner(lhs_p_2,grad(q))*dx
+L5=inner(rhs_p_1,q)*dx + inner(rhs_p_2,grad(q))*dx
+A5 = assemble(a5)
+b5 = assemble(L5)
+[bc.apply(A5, b5) for bc in bcp]
+solve(A5, p1.vector(), b5, "bicgstab", "default")
+end()
+rho1 = rho0 + (Ma*Ma/Re)*(p1-p0)
+rho1 = project(rho1,Q)
+lhs_u1 = (Re/dt)*rho1*u
+rhs_u1 = (Re/dt)*rho1*us
+a7=inner(lhs_u1,v)*dx  + inner(D-Dcomp(u),R)*dx
+L7=inner(rhs_u1,v)*dx + 0.5*inner(p1-p0,div(v))*dx - 0.5*dot(p1*n, v)*ds
+a7+= 0
+L7+= 0
+A7 = assemble(a7)
+b7 = assemble(L7)
+[bc.apply(A7, b7) for bc in bcu]
+solve(A7, w1.vector(), b7, "bicgstab", "default")
+end()
+(u1, D1_vec) = w1.split()
+lhs_tau1 = (We/dt+1.0)*tau  +  We*Fdef(u1,tau)
+rhs_tau1= (We/dt)*tau0 + 2.0*(1.0-betav)*Dcomp(u1)
+A = inner(lhs_tau1,Rt)*dx - inner(rhs_tau1,Rt)*dx
+a4 = lhs(A)
+L4 = rhs(A)
+a4 += LPSl_stress
+L4 += 0
+A4=assemble(a4)
+b4=assemble(L4)
+[bc.apply(A4, b4) for bc in bctau]
+solve(A4, tau1_vec.vector(), b4, "bicgstab", "default")
+end()
+E_k=assemble(0.5*rho1*dot(u1,u1)*dx)
+E_e=assemble((tau1_vec[0]+tau1_vec[2])*dx)
+'''
+
+
+def test_literal_config2_time_step_equals_the_driver_step():
+    """One whole time step of the bench configuration executed from the script's statements (assemble / bc.apply /
+    solve / project, 6 linear systems + the density projection) against the driver's step from the same state."""
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    mk = lambda: ldc.CompLDC(pmesh.Skew_Mesh(12, 1, 1))  # noqa: E731
+    drv, twin = mk(), mk()
+    drv.t = 0.45
+    drv.step()
+    drv.step()
+    for slot, fn in drv.pr.fields.items():                 # the twin starts from the same state (all bound Functions)
+        twin.pr.fields[slot].vector().t.copy_(fn.vector().t)
+    twin.t = drv.t
+    twin.solve_rtol = 1e-12
+    want = twin.step()
+    # ---- the script's set-up section on the driver's Functions (:201-217, :343-349) and the top of the loop (:392-412)
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    S, pv = drv.S, drv.p
+    ns.update({k: ff.Parameter(k, pv[k]) for k in ("Re", "We", "Ma", "dt", "betav", "th", "conv", "c1", "c2")})
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = ff.trial_functions(Q, Zc, W)
+    (v, R_vec) = ff.TestFunctions(W)
+    ns.update(Q=Q, p=p, rho=p, q=ff.TestFunction(Q), u=u, D=D, tau=tau, v=v, R=m3(R_vec), Rt=m3(ff.TestFunction(Zc)),
+              h=ff.CellDiameter(drv.mesh), n=ff.FacetNormal(drv.mesh), bcu=drv.bcu, bcp=[], bctau=[])
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "tau0_vec", "tau1_vec", "kapp"):
+        ns[name] = getattr(drv, name)
+    drv._bct["t"] = drv.t                                  # ulidreg.t = t (:379)
+    drv.lps_indicator()                                    # :392-401 -> kapp
+    (ns["u0"], D0_vec) = drv.w0.split()                    # :408-412
+    ns["D0"], ns["tau0"] = m3(D0_vec), m3(symbolic.as_expr(drv.tau0_vec))
+    exec("DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx\n"
+         "DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx\n"
+         "LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx\n"
+         "DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx\n", ns)
+    ks = la.parameters["krylov_solver"]
+    old = ks["relative_tolerance"], la.parameters.get("preconditioner_substitution")
+    ks["relative_tolerance"], la.parameters["preconditioner_substitution"] = 1e-12, "silent"
+    try:
+        exec(CFG2_LOOP_BODY, ns)
+    finally:
+        ks["relative_tolerance"], la.parameters["preconditioner_substitution"] = old
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("rho1", twin.rho1),
+                      ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].vector().get_local(), ref.vector().get_local()) < 1e-8, name
+    assert abs(ns["E_k"] - want["E_k"]) < 1e-9 * abs(want["E_k"])
+    assert abs(ns["E_e"] - want["E_e"]) < 1e-9 * max(abs(want["E_e"]), 1e-12)

@@ -203,3 +203,21 @@ def test_lhs_rhs_split():
         lhs(inner(sqrt(p), q) * dx)
     with pytest.raises(ValueError):
         lhs(inner(f / p, q) * dx)
+
+
+def test_text_of_config2_density_projection():
+    """comp_LDC_mesh_convergence.py:501-502 `rho1 = project(rho0 + (Ma*Ma/Re)*(p1-p0), Q)`: the two forms dolfin_api.project
+    builds for a symbolic expression are registered (mass matrix of Q, right-hand side FX_FORM_C2_L_RHO1)"""
+    rec = []
+    ns = _namespace2(rec)
+
+    def project(expr, V):
+        w, Pv = form_registry.arguments(V, 0), form_registry.arguments(V, 1)
+        rec.append(symbolic.recognise(symbolic.inner(w, Pv) * symbolic.dx)[0])
+        fid, coefs, params, _, _ = symbolic.recognise(symbolic.inner(w, expr) * symbolic.dx)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return T("Q", abi.FX_F_RHO1)
+    ns.update(project=project, Q="Q")
+    exec(_lines2(501, 502), ns)
+    assert rec[0] == abi.FX_FORM_MASS_Q
+    assert rec[1] == (abi.FX_FORM_C2_L_RHO1, [abi.FX_F_RHO0, abi.FX_F_P1, abi.FX_F_P0], ["Ma", "Re"])
