@@ -14,7 +14,7 @@ from fenics_b200.drivers import ldc  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 192
 REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-drv = ldc.CompLDC(pmesh.Skew_Mesh(n, 1, 1))
+drv = ldc.CompLDC(pmesh.Skew_Mesh(n, 1, 1), dt=0.001 * min(1.0, 192.0 / n))  # dt ~ h beyond the bench mesh (stability)
 drv.t = 0.45
 for _ in range(3):
     drv.step()

@@ -1,11 +1,12 @@
 """profiles/r02_top_kernel_traffic.json from an `ncu --set full` raw CSV of tools/nb_profile_target.py (4 launches:
 W K/4, W K, Zc K/4, Zc K iterations): DRAM bytes per BiCGStab iteration and per launch set-up, per system.
-usage: python tools/ncu_traffic.py raw.csv K out.json"""
+usage: python tools/ncu_traffic.py raw.csv K out.json [n]"""
 import csv
 import json
 import sys
 
 raw, K, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+n_mesh = int(sys.argv[4]) if len(sys.argv) > 4 else 192
 rows = list(csv.reader(open(raw)))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
@@ -20,7 +21,7 @@ def val(r, name):
 
 sel = [r for r in rows[2:] if "k_bicgstab_nb" in r[ix["Kernel Name"]]][-4:]  # the capture may include the time step's solves
 assert len(sel) == 4 and "<2" in sel[0][ix["Kernel Name"]] and "<3" in sel[3][ix["Kernel Name"]], [r[ix["Kernel Name"]] for r in sel]
-res = {"kernel": "k_bicgstab_nb", "n": 192, "source": raw, "K": K, "dram_bytes_per_iteration": {}, "dram_bytes_setup": {},
+res = {"kernel": "k_bicgstab_nb", "n": n_mesh, "source": raw, "K": K, "dram_bytes_per_iteration": {}, "dram_bytes_setup": {},
        "launches": []}
 for sp, (a, b) in (("W", sel[0:2]), ("Zc", sel[2:4])):
     by = [val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") for r in (a, b)]
