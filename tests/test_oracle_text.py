@@ -127,3 +127,44 @@ def test_config1_forms_are_the_scripts_statements():
         _same(ns[name], cfg.forms[name], name)
     _same(ns["E_k"], cfg.E_k_form, "E_k")
     _same(ns["E_e"], cfg.E_e_form, "E_e")
+
+
+def test_config5_forms_are_the_scripts_statements():
+    """buoyancy-driven-flow/compressible_dgp.py: DEVSS :336-338, LPS :391, per-step projections :404-416 and the eight
+    sub-steps :420-583 (16 forms, the energies, the Nusselt functional and every expression handed to project())"""
+    from oracle import configs_dgp as cd
+    import fxt_dgp as dg
+    script = os.path.join("..", "buoyancy-driven-flow", "compressible_dgp.py")
+    cfg = cd.CompDGP(cd.dgp_mesh(5))
+    dg.randomize(cfg)
+    ns = _namespace(cfg)
+    p = cfg.p
+    ns.update({k: getattr(cd, k) for k in ("sigmacom", "Fdefcom", "magnitude")})
+    ns.update(T_0=p["T0"], T_h=p["th_hot"], al_1=p["al1"], al_2=p["al2"], C=200.0, DOLFIN_EPS=fem.DOLFIN_EPS,
+              k=ufl.Const(np.array([0.0, 1.0]), degree=2), r=ns["q"], T=ns["p"], T0=cfg.T0.expr(), T1=cfg.T1.expr(),
+              rho12=cfg.rho12.expr(), thetar=cfg.thetar.expr())
+    for name in ("Ra", "Pr", "Vh", "Bi"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                      # :294
+    handed = []
+    returns = [None, cfg.theta0.expr(), cfg.therm_inv.expr(), cfg.rho1.expr(), cfg.theta1.expr()]
+
+    def project(e, V):
+        handed.append(e)
+        return returns[len(handed) - 1]
+    ns.update(project=project, bcT=[])
+    exec(_lines(script, 336, 338), ns)
+    exec(_lines(script, 391, 391), ns)
+    body = _lines(script, 404, 583)
+    body = "\n".join(l for l in body.splitlines() if not l.strip().startswith(("solve(", "solvertau.")))
+    # the script keeps a dead alternative stress step inside a string literal (:455-468): harmless to execute
+    exec(body, ns)
+    for name in ("a0", "L0", "a1", "L1", "a2", "L2", "a5", "L5", "a6", "L6", "a7", "L7", "a4", "L4", "a8", "L8"):
+        _same(ns[name], cfg.forms[name], name)
+    _same(ns["E_k"], cfg.E_k_form, "E_k")
+    _same(ns["E_e"], cfg.E_e_form, "E_e")
+    _same(ns["Nus"], cfg.nus_form, "Nus")
+    qq = fem.TestFunction(cfg.S["Q"])
+    for got, want, what in ((handed[1], cfg.theta0_expr, "theta0"), (handed[2], cfg.therm_inv_expr, "therm_inv"),
+                            (handed[3], cfg.rho1_expr, "rho1"), (handed[4], cfg.theta1_expr, "theta1")):
+        _same(ufl.inner(got, qq) * ufl.dx, ufl.inner(want, qq) * ufl.dx, what)
