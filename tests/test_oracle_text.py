@@ -23,7 +23,9 @@ def _lines(script, a, b):
     path = os.path.join(REF, script)
     if not os.path.exists(path):
         pytest.skip("reference checkout not present")
-    return textwrap.dedent("\n".join(open(path).read().splitlines()[a - 1:b]))
+    # the loop bodies sit at 8-16 spaces of indentation with comment lines further left (textwrap.dedent stops at those):
+    # execute the block as it is, under an `if True:`
+    return "if True:\n" + "\n".join(open(path).read().splitlines()[a - 1:b]) + "\n"
 
 
 class _Split:
@@ -117,7 +119,7 @@ def test_config1_forms_are_the_scripts_statements():
     exec(_lines(script, 309, 309), ns)
     exec(_lines(script, 313, 313), ns)
     ns.update(a1=0, L1=0)
-    for a, b in ((317, 331), (335, 335), (355, 363), (370, 375), (379, 385), (400, 416), (420, 421)):
+    for a, b in ((317, 331), (334, 336), (355, 363), (370, 375), (379, 385), (400, 416), (420, 421)):
         body = "\n".join(l for l in _lines(script, a, b).splitlines() if not l.strip().startswith("solve("))
         exec(body, ns)
         if (a, b) == (317, 331):
@@ -168,3 +170,41 @@ def test_config5_forms_are_the_scripts_statements():
     for got, want, what in ((handed[1], cfg.theta0_expr, "theta0"), (handed[2], cfg.therm_inv_expr, "therm_inv"),
                             (handed[3], cfg.rho1_expr, "rho1"), (handed[4], cfg.theta1_expr, "theta1")):
         _same(ufl.inner(got, qq) * ufl.dx, ufl.inner(want, qq) * ufl.dx, what)
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.1])
+def test_config4_forms_are_the_scripts_statements(lam):
+    """"flow between eccentrically rotating cylinders"/fenepmp_jbp.py: DEVSS-G :413-416, temperature DEVSS :406-407, LPS
+    :473 and the sub-steps :489-649 (14 forms, energies, journal torque / load integrals), FENE-P (lambda_D = 0) and
+    FENE-P-MP (lambda_D != 0: the predictor differentiates phi_def(u0))"""
+    from oracle import configs_jbp as cj
+    import fxt_jbp as jb
+    script = os.path.join("..", "flow between eccentrically rotating cylinders", "fenepmp_jbp.py")
+    cfg = cj.FenepmpJBP(fem.annulus_mesh(12, 3), lambda_d=lam)
+    jb.randomize(cfg)
+    ns = _namespace(cfg)
+    p = cfg.p
+    ns.update({k: getattr(cj, k) for k in ("Fdef", "FdefG", "Tr", "fene_func", "phi_def", "phi_s", "fene_sigmacom",
+                                           "magnitude")})
+    ns.update(T_0=p["T0"], T_h=p["th_hot"], lambda_d=p["lambda_d"], b=p["b_fene"], A_0=p["a0"], DOLFIN_EPS=fem.DOLFIN_EPS,
+              r=ns["q"], T=ns["p"], T0=cfg.T0.expr(), T1=cfg.T1.expr(), rho12=cfg.rho12.expr(), thetar=cfg.thetar.expr(),
+              mesh_refinement=False, bcT=[], Constant=lambda v: ufl.Const(np.array(v, dtype=float)),
+              tang=ufl.as_vector([ns["n"][1], -ns["n"][0]]))                                   # :182
+    for name in ("Re", "We", "Ma", "Di", "Vh", "Bi", "th", "conv", "betav", "dt"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                                           # :391
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])                            # :394
+    exec(_lines(script, 406, 407), ns)
+    exec(_lines(script, 413, 413), ns)
+    exec(_lines(script, 415, 415), ns)
+    exec(_lines(script, 473, 473), ns)
+    body = _lines(script, 489, 649)
+    body = "\n".join(l for l in body.splitlines() if not l.strip().startswith(("solve(", "solvertau.")))
+    exec(body, ns)
+    for name in ("a0", "L0", "a2", "L2", "a5", "L5", "a6", "L6", "a7", "L7", "a4", "L4", "a9", "L9"):
+        _same(ns[name], cfg.forms[name], name)
+    _same(ns["E_k"], cfg.E_k_form, "E_k")
+    _same(ns["E_e"], cfg.E_e_form, "E_e")
+    _same(ns["innertorque"], cfg.torque_form, "torque")
+    _same(ns["innerforcex"], cfg.force_x_form, "force_x")
+    _same(ns["innerforcey"], cfg.force_y_form, "force_y")
