@@ -126,6 +126,7 @@ class _LDCBase:
         Dcomp1_vec = as_vector([Dc[0, 0], Dc[1, 0], Dc[1, 1]])
         restau0 = p["We"] / p["dt"] * (tau1_vec - tau0_vec) + p["We"] * F1R_vec + tau1_vec \
             - 2 * (1 - p["betav"]) * Dcomp1_vec
+        self.restau0 = restau0
         res_test = fem.project(restau0, S["Zd"])
         res_orth = fem.project(restau0 - res_test.expr(), S["Zc"])
         res_orth_norm_sq = fem.project(inner(res_orth.expr(), res_orth.expr()), S["Qt"])

@@ -89,6 +89,12 @@ def _same(got, want, what):
         assert np.abs(B).max() > 0
 
 
+def _same_vec3(cfg, got, want, what):
+    """two 3-vector expressions (LPS residuals), compared through inner(., test function of Zc)*dx"""
+    tv = fem.TestFunction(cfg.S["Zc"])
+    _same(ufl.inner(got, tv) * ufl.dx, ufl.inner(want, tv) * ufl.dx, what)
+
+
 def test_config2_forms_are_the_scripts_statements():
     """comp_LDC_mesh_convergence.py: DEVSS / LPS definitions :343-349, :402, :408-414 and the six sub-steps :417-537"""
     cfg = configs.CompLDC(fem.skew_mesh(5))
@@ -96,6 +102,9 @@ def test_config2_forms_are_the_scripts_statements():
     ns = _namespace(cfg)
     script = "comp_LDC_mesh_convergence.py"
     ns["project"] = lambda e, V: ns.__setitem__("rho1_projected_expr", e) or cfg.rho1.expr()
+    exec(_lines(script, 393, 396), ns)        # the LPS residual restau0 (top of the loop)
+    cfg._lps_indicator()
+    _same_vec3(cfg, ns["restau0"], cfg.restau0, "restau0")
     exec(_lines(script, 343, 349), ns)        # devss_Z, DEVSSl_u12, DEVSSl_u1 (and the pre-loop DEVSSr, overwritten below)
     exec(_lines(script, 402, 402), ns)        # LPSl_stress
     exec(_lines(script, 412, 414), ns)        # DEVSSr_u12, U
@@ -118,6 +127,9 @@ def test_config1_forms_are_the_scripts_statements():
     lc.randomize(cfg)
     ns = _namespace(cfg)
     script = "incomp_LDC.py"
+    exec(_lines(script, 300, 303), ns)        # the LPS residual restau0
+    cfg._lps_indicator()
+    _same_vec3(cfg, ns["restau0"], cfg.restau0, "restau0")
     exec(_lines(script, 259, 262), ns)
     exec(_lines(script, 309, 309), ns)
     exec(_lines(script, 313, 313), ns)
@@ -158,6 +170,9 @@ def test_config5_forms_are_the_scripts_statements():
         handed.append(e)
         return returns[len(handed) - 1]
     ns.update(project=project, bcT=[])
+    ns["I_vec"] = cfg.I_vec
+    exec(_lines(script, 382, 385), ns)        # the LPS residual restau0
+    _same_vec3(cfg, ns["restau0"], cfg.restau0, "restau0")
     exec(_lines(script, 336, 338), ns)
     exec(_lines(script, 391, 391), ns)
     body = _lines(script, 404, 583)
@@ -197,6 +212,9 @@ def test_config4_forms_are_the_scripts_statements(lam):
         ns[name] = float(p[name])
     ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                                           # :391
     ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])                            # :394
+    ns["I_vec"] = cfg.I_vec
+    exec(_lines(script, 462, 466), ns)        # the LPS residual restau0 (with the FENE function and the dissipation term)
+    _same_vec3(cfg, ns["restau0"], cfg.restau0, "restau0")
     exec(_lines(script, 406, 407), ns)
     exec(_lines(script, 413, 413), ns)
     exec(_lines(script, 415, 415), ns)
