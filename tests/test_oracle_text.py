@@ -2,8 +2,9 @@
 
 `oracle/configs.py` restates the form-building statements of the scripts (file:line cited there).  Here the statements
 themselves -- read from the reference checkout, executed verbatim -- build the forms on the oracle's UFL-semantics
-algebra (`oracle/ufl_lite.py`) and on the oracle's Functions, and every form is assembled next to the oracle's own:
-they must agree to rounding.  This removes transcription as a source of error between the reference scripts and the
+algebra (`oracle/ufl_lite.py`) and on the oracle's Functions -- with the reference's own helper functions (Dcomp, sigma, Fdef, phi_def, fene_func ...:
+their `def` blocks compiled from fenics_fem.py / fenics_base.py as they stand) -- and every form is assembled next to the
+oracle's own: they must agree to rounding.  This removes transcription as a source of error between the reference scripts and the
 oracle for configs 1 and 2 (what remains unpinned are dolfin's conventions themselves).
 CPU only; skipped where the reference checkout is absent."""
 import os
@@ -26,6 +27,32 @@ def _lines(script, a, b):
     # the loop bodies sit at 8-16 spaces of indentation with comment lines further left (textwrap.dedent stops at those):
     # execute the block as it is, under an `if True:`
     return "if True:\n" + "\n".join(open(path).read().splitlines()[a - 1:b]) + "\n"
+
+
+class _NP:
+    """numpy for the scripts' text: np.power(expr, 0.5) on a symbolic expression is expr ** 0.5 (what dolfin's UFL
+    operators make of it); everything else is numpy"""
+    power = staticmethod(lambda a, b: a ** b)
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+def _ref_helpers(relpath, names, ns):
+    """define the reference's OWN helper functions (fenics_fem.py / fenics_base.py: Dcomp, sigma, Fdef, phi_def ...) in
+    `ns`: their `def` blocks are taken from the reference file and compiled as they stand, so they act on whatever
+    algebra `ns` provides (here: the oracle's)"""
+    import ast
+    path = os.path.join(REF, relpath)
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    tree = ast.parse(open(path).read())
+    found = set()
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], type_ignores=[]), path, "exec"), ns)
+            found.add(node.name)
+    assert found == set(names), set(names) - found
 
 
 class _Split:
@@ -54,9 +81,8 @@ def _namespace(cfg):
     W, Q, Zc = S["W"], S["Q"], S["Zc"]
     ns = {k: getattr(ufl, k) for k in ("inner", "dot", "grad", "nabla_grad", "div", "dx", "ds", "lhs", "rhs", "as_matrix",
                                        "as_vector", "Identity", "transpose", "tr", "sqrt")}
-    ns.update({k: getattr(configs, k) for k in ("tgrad", "Dincomp", "Dcomp", "sigma", "Fdef", "Fdefcon")})
     ns.update({k: float(v) for k, v in cfg.p.items()})
-    ns.update(np=np, h=ufl.CellDiameter(), n=ufl.FacetNormal(), Q=Q)
+    ns.update(np=_NP(), h=ufl.CellDiameter(), n=ufl.FacetNormal(), Q=Q)
     u, D_vec = fem.TrialFunction(W, (0, 1)), fem.TrialFunction(W, (2, 3, 4))
     v, R_vec = fem.TestFunction(W, (0, 1)), fem.TestFunction(W, (2, 3, 4))
     ns.update(u=u, v=v, D=configs.sym(D_vec), R=configs.sym(R_vec), p=fem.TrialFunction(Q), rho=fem.TrialFunction(Q),
@@ -89,6 +115,10 @@ def _same(got, want, what):
         assert np.abs(B).max() > 0
 
 
+_BASE_HELPERS = ("tgrad", "Dincomp", "Dcomp", "sigma", "sigmacon", "fene_sigma", "fene_sigmacom", "Fdef", "FdefG", "magnitude",
+                 "phi_s", "phi_ewm", "Tr", "Trace", "fene_func", "I_3", "I_2", "phi_def")
+
+
 def _same_vec3(cfg, got, want, what):
     """two 3-vector expressions (LPS residuals), compared through inner(., test function of Zc)*dx"""
     tv = fem.TestFunction(cfg.S["Zc"])
@@ -100,6 +130,7 @@ def test_config2_forms_are_the_scripts_statements():
     cfg = configs.CompLDC(fem.skew_mesh(5))
     lc.randomize(cfg)
     ns = _namespace(cfg)
+    _ref_helpers("fenics_fem.py", ("tgrad", "Dincomp", "Dcomp", "sigmain", "sigma", "Fdef", "Fdefcon"), ns)
     script = "comp_LDC_mesh_convergence.py"
     ns["project"] = lambda e, V: ns.__setitem__("rho1_projected_expr", e) or cfg.rho1.expr()
     exec(_lines(script, 393, 396), ns)        # the LPS residual restau0 (top of the loop)
@@ -126,6 +157,7 @@ def test_config1_forms_are_the_scripts_statements():
     cfg = configs.IncompLDC(fem.skew_mesh(5), conv=1.0)   # conv = 1: the convective terms of L1 / L2 take part
     lc.randomize(cfg)
     ns = _namespace(cfg)
+    _ref_helpers("fenics_fem.py", ("tgrad", "Dincomp", "Dcomp", "sigmain", "sigma", "Fdef", "Fdefcon"), ns)
     script = "incomp_LDC.py"
     exec(_lines(script, 300, 303), ns)        # the LPS residual restau0
     cfg._lps_indicator()
@@ -156,7 +188,8 @@ def test_config5_forms_are_the_scripts_statements():
     dg.randomize(cfg)
     ns = _namespace(cfg)
     p = cfg.p
-    ns.update({k: getattr(cd, k) for k in ("sigmacom", "Fdefcom", "magnitude")})
+    _ref_helpers(os.path.join("..", "buoyancy-driven-flow", "fenics_fem.py"),
+                 ("tgrad", "Dincomp", "Dcomp", "sigma", "sigma_n", "sigmacom", "Fdef", "Fdefcom", "magnitude"), ns)
     ns.update(T_0=p["T0"], T_h=p["th_hot"], al_1=p["al1"], al_2=p["al2"], C=200.0, DOLFIN_EPS=fem.DOLFIN_EPS,
               k=ufl.Const(np.array([0.0, 1.0]), degree=2), r=ns["q"], T=ns["p"], T0=cfg.T0.expr(), T1=cfg.T1.expr(),
               rho12=cfg.rho12.expr(), thetar=cfg.thetar.expr())
@@ -202,8 +235,7 @@ def test_config4_forms_are_the_scripts_statements(lam):
     jb.randomize(cfg)
     ns = _namespace(cfg)
     p = cfg.p
-    ns.update({k: getattr(cj, k) for k in ("Fdef", "FdefG", "Tr", "fene_func", "phi_def", "phi_s", "fene_sigmacom",
-                                           "magnitude")})
+    _ref_helpers(os.path.join("..", "flow between eccentrically rotating cylinders", "fenics_base.py"), _BASE_HELPERS, ns)
     ns.update(T_0=p["T0"], T_h=p["th_hot"], lambda_d=p["lambda_d"], b=p["b_fene"], A_0=p["a0"], DOLFIN_EPS=fem.DOLFIN_EPS,
               r=ns["q"], T=ns["p"], T0=cfg.T0.expr(), T1=cfg.T1.expr(), rho12=cfg.rho12.expr(), thetar=cfg.thetar.expr(),
               mesh_refinement=False, bcT=[], Constant=lambda v: ufl.Const(np.array(v, dtype=float)),
@@ -244,8 +276,7 @@ def test_config3_forms_are_the_scripts_statements(kw):
     jb.randomize(cfg)
     ns = _namespace(cfg)
     p = cfg.p
-    ns.update({k: getattr(cj, k) for k in ("Fdef", "FdefG", "phi_s", "magnitude")})
-    ns.update(sigmacon=ce.sigmacon, phi_ewm=ce.phi_ewm)
+    _ref_helpers(os.path.join("..", "flow between eccentrically rotating cylinders", "fenics_base.py"), _BASE_HELPERS, ns)
     ns.update(T_0=p["T0"], T_h=p["th_hot"], A_0=p["a0"], k_ewm=cfg.k_ewm, B=cfg.B, al=cfg.al, DOLFIN_EPS=fem.DOLFIN_EPS,
               r=ns["q"], T=ns["p"], T0=cfg.T0.expr(), T1=cfg.T1.expr(), rho12=cfg.rho12.expr(), thetar=cfg.thetar.expr(),
               bcT=[], Constant=lambda v: ufl.Const(np.array(v, dtype=float)), adaptive_loop=False, err_count=0, max_refine=2,
