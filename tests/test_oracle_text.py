@@ -304,3 +304,75 @@ def test_config3_forms_are_the_scripts_statements(kw):
     _same(ns["innertorque"], cfg.torque_form, "torque")
     _same(ns["innerforcex"], cfg.force_x_form, "force_x")
     _same(ns["innerforcey"], cfg.force_y_form, "force_y")
+
+
+# ---- Dirichlet data: the scripts' Expression strings against the oracle's boundary-value functions -----------------
+def _expression_strings(relpath, name, nth=0):
+    """the string tuple of the nth `name = Expression((...), ...)` assignment in a script (dolfin compiles these C++
+    strings; their syntax -- tanh, x[0], arithmetic -- is also Python's)"""
+    import ast
+    path = os.path.join(REF, relpath)
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    hits = []
+    for node in ast.walk(ast.parse(open(path).read())):
+        if (isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and node.targets[0].id == name
+                and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", "") == "Expression"):
+            arg = ast.literal_eval(node.value.args[0])
+            hits.append((node.lineno, arg if isinstance(arg, tuple) else (arg,)))
+    hits.sort()
+    return hits[nth][1]
+
+
+def _eval_expression(strings, pts, **params):
+    from math import tanh
+    out = np.empty((len(pts), len(strings)))
+    for i, x in enumerate(pts):
+        for j, s in enumerate(strings):
+            out[i, j] = eval(s, {"tanh": tanh, "x": x, **params})
+    return out
+
+
+@pytest.mark.parametrize("script", ["incomp_LDC.py", "comp_LDC_mesh_convergence.py"])
+def test_lid_velocity_is_the_scripts_expression(script):
+    """drive1 = DirichletBC(W.sub(0), ulidreg, top) with ulidreg.t = t (incomp_LDC.py:214,293)"""
+    S = configs.make_spaces(fem.skew_mesh(4))
+    bcs, holder = configs.lid_boundary_conditions(S["W"])
+    pts = np.random.default_rng(1).random((20, 2))
+    strings = _expression_strings(script, "ulidreg")
+    for t in (0.0, 0.45, 0.5, 1.3):
+        holder["t"] = t
+        assert np.allclose(bcs[1].value(pts), _eval_expression(strings, pts, t=t, L=1.0), rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("which", ["cfg4", "cfg3_ramped", "cfg3_prepass"])
+def test_journal_spin_is_the_scripts_expression(which):
+    """spin = DirichletBC(W.sub(0), w, omega0), w.t = t (fenepmp_jbp.py:247-249,458; incompressible_benchmarkEWM.py:292-295)"""
+    from oracle import configs_ewm as ce
+    from oracle import configs_jbp as cj
+    base = "flow between eccentrically rotating cylinders"
+    if which == "cfg4":
+        cfg, strings = cj.FenepmpJBP(fem.annulus_mesh(8, 2)), _expression_strings(os.path.join("..", base, "fenepmp_jbp.py"), "w", 1)
+    else:
+        pre = which == "cfg3_prepass"
+        cfg = ce.EwmJBP(fem.annulus_mesh(8, 2), prepass=pre)
+        strings = _expression_strings(os.path.join("..", base, "incompressible_benchmarkEWM.py"), "w", 1 if pre else 0)
+    spin = cfg.bcu[1]
+    pts = np.random.default_rng(2).random((20, 2)) * 2 - 1
+    g = cfg.geo
+    for t in (0.0, 0.3, 0.5, 2.0):
+        cfg._tt["t"] = t
+        want = _eval_expression(strings, pts, t=t, r_a=g["r_a"], x1=g["x_1"], y1=g["y_1"])
+        assert np.allclose(spin.value(pts), want, rtol=1e-14, atol=1e-16)
+
+
+def test_hot_wall_temperature_is_the_scripts_expression():
+    """temp_left = DirichletBC(Q, ramp_function, left), ramp_function.t = t (compressible_dgp.py:174,195)"""
+    from oracle import configs_dgp as cd
+    cfg = cd.CompDGP(cd.dgp_mesh(4))
+    strings = _expression_strings(os.path.join("..", "buoyancy-driven-flow", "compressible_dgp.py"), "ramp_function")
+    pts = np.random.default_rng(3).random((5, 2))
+    for t in (0.0, 1.4, 1.5, 3.0):
+        cfg._tt["t"] = t
+        want = _eval_expression(strings, pts, t=t, T_0=cfg.p["T0"], T_h=cfg.p["th_hot"])[:, 0]
+        assert np.allclose(cfg.bcT[0].value(pts), want, rtol=1e-14, atol=0)
