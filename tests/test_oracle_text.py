@@ -376,3 +376,144 @@ def test_hot_wall_temperature_is_the_scripts_expression():
         cfg._tt["t"] = t
         want = _eval_expression(strings, pts, t=t, T_0=cfg.p["T0"], T_h=cfg.p["th_hot"])[:, 0]
         assert np.allclose(cfg.bcT[0].value(pts), want, rtol=1e-14, atol=0)
+
+
+# ---- the whole loop body as the time stepper: the scripts' text drives the oracle backend for K steps ---------------
+class _DF(ufl.Coef):
+    """dolfin Function stand-in on an oracle Function: usable inside forms (a Coef that reads the vector at assembly
+    time) and as the object the scripts call .assign / .vector / .split on"""
+
+    def __init__(self, fn):
+        super().__init__(fn, range(fn.space.ncomp()), fn.space.scalar)
+
+    def assign(self, other):
+        self.fn.vec[:] = other.fn.vec
+
+    def vector(self):
+        return self
+
+    def get_local(self):
+        return self.fn.vec
+
+    def split(self, num=None):
+        if num is not None:                    # ufl_lite's own lhs / rhs protocol (Expr.split(num))
+            return super().split(num)
+        return self.fn.split_comps([(0, 1), (2, 3, 4)])   # dolfin's w.split()
+
+
+class _TimeExpr:
+    """Expression with a settable .t (ulidreg.t = t): forwards it to the oracle's boundary-value closure"""
+
+    def __init__(self, holder=None):
+        object.__setattr__(self, "holder", holder)
+
+    def __setattr__(self, k, v):
+        if k == "t" and self.holder is not None:
+            self.holder["t"] = v
+
+
+def _mini_dolfin(cfg, ns):
+    """assemble / project / solve / end of the scripts on the oracle's exact-LU backend"""
+    def solve(A, x, b, *a):
+        x.fn.vec[:] = fem.solve_lu(A, b)
+    ns.update(assemble=fem.assemble, project=lambda e, V: _DF(fem.project(e, V)), solve=solve, end=lambda: None)
+    for k, sp in cfg.S.items():
+        ns[k] = sp
+
+
+def test_config2_loop_body_text_drives_the_oracle_for_k_steps():
+    """comp_LDC_mesh_convergence.py:377-565 -- the COMPLETE loop body (LPS block with its four projections, six linear
+    systems, density projection, energies, field roll, t += dt) executed K times on a mini-dolfin made of the oracle's
+    assemble / project / LU, against K calls of the oracle's own step(): the same trajectory.  Pins the sequencing the
+    oracle (and through the K-step parity tests the GPU drivers) restate: which solution feeds which form, the roll
+    order, the time at which the lid velocity is evaluated."""
+    import datetime
+    import time
+    K = 3
+    mesh = fem.skew_mesh(6)
+    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
+    cfg.t = twin.t = 0.45                       # a time at which the lid moves (the script starts at t = dt)
+    script = "comp_LDC_mesh_convergence.py"
+    ns = _namespace(cfg)
+    _ref_helpers("fenics_fem.py", ("tgrad", "Dincomp", "Dcomp", "sigmain", "sigma", "Fdef", "Fdefcon"), ns)
+    _mini_dolfin(cfg, ns)
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "tau0_vec", "tau1_vec"):
+        ns[name] = _DF(getattr(cfg, name))
+    dummy = fem.Function(cfg.S["Q"])
+    ns.update(T0=_DF(dummy), T1=_DF(dummy), bcu=cfg.bcu, bcp=[], bctau=[], time=time, datetime=datetime,
+              update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0, elapsed=0.0, iter=0, t=cfg.t,
+              ramp_function=_TimeExpr(), rampd=_TimeExpr(), ulid=_TimeExpr(), ulidreg=_TimeExpr(cfg._bct), Ret=_TimeExpr(),
+              Wet=_TimeExpr(), t_array=[], ek_array=[], ee_array=[])
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))        # :262-281 of the set-up section
+    (ns["u0"], _), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns["D12"] = m3(D12_vec)
+    exec(_lines(script, 343, 349), ns)                                 # DEVSS definitions before the loop
+    body = _lines(script, 377, 565)
+    got, want = [], []
+    for _ in range(K):
+        exec(body, ns)
+        got.append((ns["E_k"], ns["E_e"]))
+        r = twin.step()
+        want.append((r["E_k"], r["E_e"]))
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for (a, b), (c, d) in zip(got, want):
+        assert abs(a - c) <= 1e-10 * abs(c) and abs(b - d) <= 1e-10 * max(abs(d), 1e-14)
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("w0", twin.w0), ("rho0", twin.rho0),
+                      ("tau0_vec", twin.tau0_vec), ("p0", twin.p0), ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
+    assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-10
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-8
+    assert np.abs(twin.w1.vec).max() > 1e-3
+
+
+def test_config1_loop_body_text_drives_the_oracle_for_k_steps():
+    """incomp_LDC.py:281-447 -- the complete loop body (LPS block, five linear systems incl. the singular pure-Neumann
+    pressure system, energies, the error indicator and the divergence test with its `break`, field roll) executed K
+    times on the oracle backend, against K calls of the oracle's own step()."""
+    import datetime
+    import time
+    K = 5
+    mesh = fem.skew_mesh(6)
+    cfg, twin = configs.IncompLDC(mesh), configs.IncompLDC(mesh)
+    cfg.t = twin.t = 0.49                       # crosses t = 0.5, where the divergence test (:437-441) switches on
+    script = "incomp_LDC.py"
+    ns = _namespace(cfg)
+    _ref_helpers("fenics_fem.py", ("tgrad", "Dincomp", "Dcomp", "sigmain", "sigma", "Fdef", "Fdefcon"), ns)
+    _mini_dolfin(cfg, ns)
+
+    def solve(A, x, b, *a):
+        singular = abs(A @ np.ones(A.shape[0])).max() < 1e-12 * abs(A).max()
+        x.fn.vec[:] = configs.solve_zero_sum(A, b) if singular else fem.solve_lu(A, b)   # bcp = []: pure Neumann (:227)
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "tau0_vec", "tau1_vec"):
+        ns[name] = _DF(getattr(cfg, name))
+    dummy = fem.Function(cfg.S["Q"])
+    ns.update(solve=solve, norm=lambda v, kind: fem.norm(v.get_local(), kind), T0=_DF(dummy), T1=_DF(dummy), bcu=cfg.bcu,
+              bcp=[], bctau=[], time=time, datetime=datetime, update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0,
+              elapsed=0.0, total_elapsed=0.0, iter=0, t=cfg.t, rampd=_TimeExpr(), ulid=_TimeExpr(),
+              ulidreg=_TimeExpr(cfg._bct), t_array=[], ek_array=[], ee_array=[], err_array=[])
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec))
+    exec(_lines(script, 259, 263), ns)
+    ns.update(a1=0, L1=0)
+    raw = _lines(script, 281, 447).split("\n", 1)[1]                    # without the `if True:` header: the body holds a `break`
+    body = "for once_ in (0,):\n" + raw + "\n            completed_ = True\n"
+    for step in range(K):
+        ns["completed_"] = False
+        exec(body, ns)
+        r = twin.step()
+        assert ns["completed_"] == (not r["diverged"])
+        assert abs(ns["E_k"] - r["E_k"]) <= 1e-10 * abs(r["E_k"]) and abs(ns["E_e"] - r["E_e"]) <= 1e-10 * max(abs(r["E_e"]), 1e-14)
+        assert abs(ns["err_array"][-1] - r["err"]) <= 1e-8 * max(r["err"], 1e-14)
+        tested_divergence = ns["t"] > 0.5
+        if r["diverged"]:                       # the script leaves the loop BEFORE the field roll
+            break
+    assert tested_divergence and abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == step + 1
+    rolled = () if r["diverged"] else (("w0", twin.w0), ("tau0_vec", twin.tau0_vec))
+    for name, ref in (("w1", twin.w1), ("tau1_vec", twin.tau1_vec), ("w12", twin.w12), ("ws", twin.ws)) + rolled:
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
+    pm = lambda v: v - v.mean()  # noqa: E731  (the pressure is defined up to a constant)
+    assert lc.rel_err(pm(ns["p1"].fn.vec), pm(twin.p1.vec)) < 1e-9
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-8
