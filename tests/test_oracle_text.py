@@ -395,6 +395,9 @@ class _DF(ufl.Coef):
     def get_local(self):
         return self.fn.vec
 
+    def __setitem__(self, key, value):             # `u.vector()[:] = u_array` (fenics_base.py absolute())
+        self.fn.vec[key] = value
+
     def split(self, num=None):
         if num is not None:                    # ufl_lite's own lhs / rhs protocol (Expr.split(num))
             return super().split(num)
@@ -517,3 +520,167 @@ def test_config1_loop_body_text_drives_the_oracle_for_k_steps():
     pm = lambda v: v - v.mean()  # noqa: E731  (the pressure is defined up to a constant)
     assert lc.rel_err(pm(ns["p1"].fn.vec), pm(twin.p1.vec)) < 1e-9
     assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-8
+
+
+class _KrylovSolver:
+    """solvertau = KrylovSolver("bicgstab", "default") of the scripts: .solve(A, x, b) on the exact-LU backend"""
+
+    def solve(self, A, x, b):
+        x.fn.vec[:] = fem.solve_lu(A, b)
+
+
+class _TimeExprT(_TimeExpr):
+    def __getattr__(self, k):          # `str(ramp_function.t)` in the progress line
+        return self.holder["t"] if k == "t" else object.__getattribute__(self, k)
+
+
+def test_config5_loop_body_text_drives_the_oracle_for_k_steps():
+    """buoyancy-driven-flow/compressible_dgp.py:369-595 -- the complete loop body (double `iter += 1`: the roll happens
+    from the first pass; LPS block, three per-step projections, eight linear systems, density projection, energies,
+    Nusselt number) executed K times on the oracle backend, against K calls of the oracle's own step()."""
+    import datetime
+    import time
+    from oracle import configs_dgp as cd
+    K = 3
+    script = os.path.join("..", "buoyancy-driven-flow", "compressible_dgp.py")
+    mesh = cd.dgp_mesh(6)
+    cfg, twin = cd.CompDGP(mesh), cd.CompDGP(mesh)
+    cfg.t = twin.t = 1.4                        # the hot wall is being ramped (tanh(4 (t - 1.5)))
+    ns = _namespace(cfg)
+    _ref_helpers(os.path.join("..", "buoyancy-driven-flow", "fenics_fem.py"),
+                 ("tgrad", "Dincomp", "Dcomp", "sigma", "sigma_n", "sigmacom", "Fdef", "Fdefcom", "magnitude"), ns)
+    _mini_dolfin(cfg, ns)
+    p = cfg.p
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "tau0_vec", "tau1_vec", "T0", "T1", "thetar"):
+        ns[name] = _DF(getattr(cfg, name))
+    ns.update(T_0=p["T0"], T_h=p["th_hot"], al_1=p["al1"], al_2=p["al2"], C=200.0, DOLFIN_EPS=fem.DOLFIN_EPS, I_vec=cfg.I_vec,
+              k=ufl.Const(np.array([0.0, 1.0]), degree=2), r=ns["q"], T=ns["p"], bcu=cfg.bcu, bcp=[], bctau=[], bcT=cfg.bcT,
+              solvertau=_KrylovSolver(), time=time, datetime=datetime, update_progress=lambda *a: None, j=0, Tf=10.0,
+              elapsed=0.0, total_elapsed=0.0, iter=0, t=cfg.t, ramp_function=_TimeExprT(cfg._tt), t_array=[], ek_array=[],
+              ee_array=[], nus_array=[])
+    for name in ("Ra", "Pr", "Vh", "Bi"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                      # :294
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
+    (ns["u0"], _), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns["D12"] = m3(D12_vec)
+    exec(_lines(script, 336, 338), ns)
+    body = _lines(script, 369, 595)
+    for _ in range(K):
+        exec(body, ns)
+        r = twin.step()
+        for key in ("E_k", "E_e", "Nus"):
+            assert abs(ns[key] - r[key]) <= 1e-9 * max(abs(r[key]), 1e-12), key
+    assert abs(ns["t"] - twin.t) < 1e-14
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("w0", twin.w0),
+                      ("rho0", twin.rho0), ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws), ("rho12", twin.rho12)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
+    assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-10
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-6
+
+
+def test_config4_loop_body_text_drives_the_oracle_for_k_steps():
+    """fenepmp_jbp.py:455-690 -- the complete loop body of the FENE-P-MP journal bearing (lambda_D = 0.1: LPS block with
+    `absolute(kapp)`, `if iter > 1` roll, seven linear systems, energies, journal torque / load integrals) executed K
+    times on the oracle backend, against K calls of the oracle's own step()."""
+    from oracle import configs_jbp as cj
+    K = 3
+    base = os.path.join("..", "flow between eccentrically rotating cylinders")
+    script = os.path.join(base, "fenepmp_jbp.py")
+    mesh = fem.annulus_mesh(12, 3)
+    cfg, twin = cj.FenepmpJBP(mesh, lambda_d=0.1, We=0.5), cj.FenepmpJBP(mesh, lambda_d=0.1, We=0.5)
+    cfg.t = twin.t = 0.45
+    ns = _namespace(cfg)
+    _ref_helpers(os.path.join(base, "fenics_base.py"), _BASE_HELPERS + ("absolute",), ns)
+    _mini_dolfin(cfg, ns)
+    p = cfg.p
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "tau0_vec", "tau1_vec", "T0", "T1", "thetar"):
+        ns[name] = _DF(getattr(cfg, name))
+    ns.update(T_0=p["T0"], T_h=p["th_hot"], lambda_d=p["lambda_d"], b=p["b_fene"], A_0=p["a0"], DOLFIN_EPS=fem.DOLFIN_EPS,
+              I_vec=cfg.I_vec, r=ns["q"], T=ns["p"], bcu=cfg.bcu, bcp=[], bctau=[], bcT=cfg.bcT, solvertau=_KrylovSolver(),
+              mesh_refinement=False, Constant=lambda v: ufl.Const(np.array(v, dtype=float)), update_progress=lambda *a: None,
+              jjj=0, j=1, Tf=10.0, iter=0, t=cfg.t, w=_TimeExpr(cfg._tt), tang=ufl.as_vector([ns["n"][1], -ns["n"][0]]),
+              x1=[], ek1=[], ee1=[], y1=[], zx1=[], z1=[])
+    for name in ("Re", "We", "Ma", "Di", "Vh", "Bi", "th", "conv", "betav", "dt"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])        # :394 (an expression of T0, not a projection)
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
+    (ns["u0"], _), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns["D12"] = m3(D12_vec)
+    exec(_lines(script, 406, 407), ns)
+    exec(_lines(script, 413, 413), ns)
+    exec(_lines(script, 415, 415), ns)
+    body = _lines(script, 455, 690)
+    for step in range(K):
+        exec(body, ns)
+        r = twin.step()
+        for key, got in (("E_k", ns["E_k"]), ("E_e", ns["E_e"]), ("torque", ns["y1"][-1]), ("F_x", ns["zx1"][-1]),
+                         ("F_y", ns["z1"][-1])):
+            scale = max(abs(r["F_x"]), abs(r["F_y"])) if key in ("F_x", "F_y") else abs(r[key])
+            assert abs(got - r[key]) <= 1e-9 * max(scale, 1e-12), (step, key)
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("rho1", twin.rho1),
+                      ("w0", twin.w0), ("rho0", twin.rho0), ("T0", twin.T0), ("ws", twin.ws), ("rho12", twin.rho12)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-3
+
+
+@pytest.mark.parametrize("prepass", [False, True])
+def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
+    """incompressible_benchmarkEWM.py:466-782 -- the complete loop body of the EWM journal bearing (SU term from u1 before
+    the `iter > 1` roll, eight linear systems with the stress step behind `if We > 0.00001 or adaptive_loop == False
+    and err_count < max_refine`, energies, torque / load, the divergence `break`) executed K times on the oracle backend,
+    against K calls of the oracle's own step(): main pass (ramped spin, stress step skipped at We = 1e-6) and pre-pass
+    (un-ramped spin, stress solved).  General material parameters so that phi_s, phi_ewm take part."""
+    from oracle import configs_ewm as ce
+    K = 3
+    base = os.path.join("..", "flow between eccentrically rotating cylinders")
+    script = os.path.join(base, "incompressible_benchmarkEWM.py")
+    mesh = fem.annulus_mesh(12, 3)
+    kw = dict(prepass=prepass, Ma=0.05, betav=0.6, A_0=0.4, k_ewm=0.7, B=0.2, dt=0.002)
+    cfg, twin = ce.EwmJBP(mesh, **kw), ce.EwmJBP(mesh, **kw)
+    cfg.t = twin.t = 0.45
+    ns = _namespace(cfg)
+    _ref_helpers(os.path.join(base, "fenics_base.py"), _BASE_HELPERS, ns)
+    _mini_dolfin(cfg, ns)
+    p = cfg.p
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "tau0_vec", "tau1_vec", "T0", "T1", "thetar"):
+        ns[name] = _DF(getattr(cfg, name))
+    ns.update(T_0=p["T0"], T_h=p["th_hot"], A_0=p["a0"], k_ewm=cfg.k_ewm, B=cfg.B, al=cfg.al, DOLFIN_EPS=fem.DOLFIN_EPS,
+              r=ns["q"], T=ns["p"], bcu=cfg.bcu, bcp=[], bctau=[], bcT=cfg.bcT, Constant=lambda v: ufl.Const(np.array(v, dtype=float)),
+              update_progress=lambda *a: None, norm=lambda v, kind: fem.norm(v.get_local(), kind), secondary_loop=0,
+              primary_loop=1, adaptive_loop=not prepass, err_count=0, max_refine=2, Tf=10.0, iter=0, t=cfg.t,
+              w=_TimeExpr(cfg._tt), Ret=_TimeExpr(), Wet=_TimeExpr(), tang=ufl.as_vector([ns["n"][1], -ns["n"][0]]),
+              x1=[], ek1=[], ee1=[], y1=[], zx1=[], z1=[])
+    for name in ("Re", "We", "Ma", "Di", "Vh", "Bi", "th", "conv", "betav", "dt"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec))
+    exec(_lines(script, 402, 402), ns)
+    exec(_lines(script, 410, 411), ns)
+    exec(_lines(script, 415, 416), ns)
+    exec(_lines(script, 422, 422), ns)
+    raw = _lines(script, 466, 782).split("\n", 1)[1]
+    body = "for once_ in (0,):\n" + raw + "\n        completed_ = True\n"
+    for step in range(K):
+        ns["completed_"] = False
+        exec(body, ns)
+        assert ns["completed_"]
+        r = twin.step()
+        for key, got in (("E_k", ns["E_k"]), ("E_e", ns["E_e"]), ("torque", ns["y1"][-1]), ("F_y", ns["z1"][-1])):
+            scale = max(abs(r["F_x"]), abs(r["F_y"])) if key == "F_y" else abs(r[key])
+            assert abs(got - r[key]) <= 1e-9 * max(scale, 1e-12), (step, key)
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("rho1", twin.rho1),
+                      ("w0", twin.w0), ("rho0", twin.rho0), ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
+    assert np.abs(twin.w1.vec).max() > 1e-3
