@@ -424,8 +424,11 @@ def _mini_dolfin(cfg, ns):
         ns[k] = sp
 
 
-def test_config2_loop_body_text_drives_the_oracle_for_k_steps():
-    """comp_LDC_mesh_convergence.py:377-565 -- the COMPLETE loop body (LPS block with its four projections, six linear
+@pytest.mark.parametrize("script,cls,devss,rng", [("comp_LDC_mesh_convergence.py", "CompLDC", (343, 349), (377, 565)),
+                                                   ("comp_LDC.py", "CompLDCSweep", (334, 340), (365, 594))])
+def test_config2_loop_body_text_drives_the_oracle_for_k_steps(script, cls, devss, rng):
+    """comp_LDC_mesh_convergence.py:377-565 (and the sweep script comp_LDC.py:365-594, whose convective terms carry
+    Re*conv) -- the COMPLETE loop body (LPS block with its four projections, six linear
     systems, density projection, energies, field roll, t += dt) executed K times on a mini-dolfin made of the oracle's
     assemble / project / LU, against K calls of the oracle's own step(): the same trajectory.  Pins the sequencing the
     oracle (and through the K-step parity tests the GPU drivers) restate: which solution feeds which form, the roll
@@ -434,9 +437,8 @@ def test_config2_loop_body_text_drives_the_oracle_for_k_steps():
     import time
     K = 3
     mesh = fem.skew_mesh(6)
-    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
+    cfg, twin = getattr(configs, cls)(mesh), getattr(configs, cls)(mesh)
     cfg.t = twin.t = 0.45                       # a time at which the lid moves (the script starts at t = dt)
-    script = "comp_LDC_mesh_convergence.py"
     ns = _namespace(cfg)
     _ref_helpers("fenics_fem.py", ("tgrad", "Dincomp", "Dcomp", "sigmain", "sigma", "Fdef", "Fdefcon"), ns)
     _mini_dolfin(cfg, ns)
@@ -444,15 +446,15 @@ def test_config2_loop_body_text_drives_the_oracle_for_k_steps():
         ns[name] = _DF(getattr(cfg, name))
     dummy = fem.Function(cfg.S["Q"])
     ns.update(T0=_DF(dummy), T1=_DF(dummy), bcu=cfg.bcu, bcp=[], bctau=[], time=time, datetime=datetime,
-              update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0, elapsed=0.0, iter=0, t=cfg.t,
+              update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0, elapsed=0.0, total_elapsed=0.0, iter=0, t=cfg.t,
               ramp_function=_TimeExpr(), rampd=_TimeExpr(), ulid=_TimeExpr(), ulidreg=_TimeExpr(cfg._bct), Ret=_TimeExpr(),
               Wet=_TimeExpr(), t_array=[], ek_array=[], ee_array=[])
     m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
     ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))        # :262-281 of the set-up section
     (ns["u0"], _), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
     ns["D12"] = m3(D12_vec)
-    exec(_lines(script, 343, 349), ns)                                 # DEVSS definitions before the loop
-    body = _lines(script, 377, 565)
+    exec(_lines(script, *devss), ns)                                   # DEVSS definitions before the loop
+    body = _lines(script, *rng)
     got, want = [], []
     for _ in range(K):
         exec(body, ns)
@@ -630,7 +632,7 @@ def test_config4_loop_body_text_drives_the_oracle_for_k_steps():
     assert np.abs(twin.w1.vec).max() > 1e-3
 
 
-@pytest.mark.parametrize("prepass", [False, True])
+@pytest.mark.parametrize("prepass", [False, True, "true_ewm"])
 def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
     """incompressible_benchmarkEWM.py:466-782 -- the complete loop body of the EWM journal bearing (SU term from u1 before
     the `iter > 1` roll, eight linear systems with the stress step behind `if We > 0.00001 or adaptive_loop == False
@@ -640,10 +642,17 @@ def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
     from oracle import configs_ewm as ce
     K = 3
     base = os.path.join("..", "flow between eccentrically rotating cylinders")
-    script = os.path.join(base, "incompressible_benchmarkEWM.py")
     mesh = fem.annulus_mesh(12, 3)
-    kw = dict(prepass=prepass, Ma=0.05, betav=0.6, A_0=0.4, k_ewm=0.7, B=0.2, dt=0.002)
-    cfg, twin = ce.EwmJBP(mesh, **kw), ce.EwmJBP(mesh, **kw)
+    if prepass == "true_ewm":
+        # comp_ewm_jpb.py:422-732, the TRUE extended White-Metzner loop (A_0 = 120, k = -0.7, B = 0.1 :88-90): SU weight of
+        # the density update with DOLFIN_EPS, `a9 += 0.0*th*DEVSSl_T1`, unconditional stress solve
+        script, pre, loop, rec = os.path.join(base, "comp_ewm_jpb.py"), ((368, 368), (376, 377), (381, 382), (388, 388)), (422, 732), "j"
+        cfg, twin = ce.CompEwmJBP(mesh, dt=0.002), ce.CompEwmJBP(mesh, dt=0.002)
+        prepass = False
+    else:
+        script, pre, loop, rec = os.path.join(base, "incompressible_benchmarkEWM.py"), ((402, 402), (410, 411), (415, 416), (422, 422)), (466, 782), "primary_loop"
+        kw = dict(prepass=prepass, Ma=0.05, betav=0.6, A_0=0.4, k_ewm=0.7, B=0.2, dt=0.002)
+        cfg, twin = ce.EwmJBP(mesh, **kw), ce.EwmJBP(mesh, **kw)
     cfg.t = twin.t = 0.45
     ns = _namespace(cfg)
     _ref_helpers(os.path.join(base, "fenics_base.py"), _BASE_HELPERS, ns)
@@ -654,7 +663,7 @@ def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
     ns.update(T_0=p["T0"], T_h=p["th_hot"], A_0=p["a0"], k_ewm=cfg.k_ewm, B=cfg.B, al=cfg.al, DOLFIN_EPS=fem.DOLFIN_EPS,
               r=ns["q"], T=ns["p"], bcu=cfg.bcu, bcp=[], bctau=[], bcT=cfg.bcT, Constant=lambda v: ufl.Const(np.array(v, dtype=float)),
               update_progress=lambda *a: None, norm=lambda v, kind: fem.norm(v.get_local(), kind), secondary_loop=0,
-              primary_loop=1, adaptive_loop=not prepass, err_count=0, max_refine=2, Tf=10.0, iter=0, t=cfg.t,
+              primary_loop=1, j=1, jjj=0, adaptive_loop=not prepass, err_count=0, max_refine=2, Tf=10.0, iter=0, t=cfg.t,
               w=_TimeExpr(cfg._tt), Ret=_TimeExpr(), Wet=_TimeExpr(), tang=ufl.as_vector([ns["n"][1], -ns["n"][0]]),
               x1=[], ek1=[], ee1=[], y1=[], zx1=[], z1=[])
     for name in ("Re", "We", "Ma", "Di", "Vh", "Bi", "th", "conv", "betav", "dt"):
@@ -665,12 +674,11 @@ def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
     ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
     (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
     ns.update(D0=m3(D0_vec), D12=m3(D12_vec))
-    exec(_lines(script, 402, 402), ns)
-    exec(_lines(script, 410, 411), ns)
-    exec(_lines(script, 415, 416), ns)
-    exec(_lines(script, 422, 422), ns)
-    raw = _lines(script, 466, 782).split("\n", 1)[1]
-    body = "for once_ in (0,):\n" + raw + "\n        completed_ = True\n"
+    for a, b in pre:
+        exec(_lines(script, a, b), ns)
+    raw = _lines(script, *loop).split("\n", 1)[1]
+    indent = " " * (len(raw) - len(raw.lstrip(" ")))                      # the two scripts nest their loops differently
+    body = "for once_ in (0,):\n" + raw + "\n" + indent + "completed_ = True\n"
     for step in range(K):
         ns["completed_"] = False
         exec(body, ns)
@@ -684,3 +692,56 @@ def test_config3_loop_body_text_drives_the_oracle_for_k_steps(prepass):
                       ("w0", twin.w0), ("rho0", twin.rho0), ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws)):
         assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-10, name
     assert np.abs(twin.w1.vec).max() > 1e-3
+
+
+def test_incompressible_dgp_loop_body_text_drives_the_oracle_for_k_steps():
+    """buoyancy-driven-flow/incompressible_dgp.py:358-535 -- the complete loop body of the incompressible
+    double-glazing problem: LPS block with absolute(kapp), `iter > 1` roll, two momentum systems, the singular pure-
+    Neumann pressure system (solved by BiCGStab from the previous pressure in the script: the member of the solution
+    family that left-Jacobi Krylov iterations reach, oracle `solve_weighted_gauge`), velocity update, stress (behind
+    `if betav < 0.99`), temperature, energies, Nusselt number -- K steps against the oracle's own step()."""
+    import datetime
+    import time
+    from oracle import configs_dgp as cd
+    K = 3
+    script = os.path.join("..", "buoyancy-driven-flow", "incompressible_dgp.py")
+    mesh = cd.dgp_mesh(6)
+    cfg, twin = cd.IncompDGP(mesh), cd.IncompDGP(mesh)
+    cfg.t = twin.t = 1.4
+    ns = _namespace(cfg)
+    _ref_helpers(os.path.join("..", "buoyancy-driven-flow", "fenics_fem.py"),
+                 ("tgrad", "Dincomp", "Dcomp", "sigma", "sigma_n", "sigmacom", "Fdef", "Fdefcom", "magnitude", "absolute"), ns)
+    _mini_dolfin(cfg, ns)
+    p = cfg.p
+
+    def solve(A, x, b, *a):
+        singular = abs(A @ np.ones(A.shape[0])).max() < 1e-12 * abs(A).max()
+        x.fn.vec[:] = cd.solve_weighted_gauge(A, b, x.fn.vec) if singular else fem.solve_lu(A, b)
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho1", "tau0_vec", "tau1_vec", "T0", "T1", "thetar"):
+        ns[name] = _DF(getattr(cfg, name))
+    ns.update(solve=solve, T_0=p["T0"], T_h=p["th_hot"], DOLFIN_EPS=fem.DOLFIN_EPS, I_vec=cfg.I_vec, al=0.0,
+              f=ufl.Const(np.array([0.0, -1.0]), degree=2), k=ufl.Const(np.array([0.0, 1.0]), degree=2), r=ns["q"], T=ns["p"],
+              bcu=cfg.bcu, bcp=[], bctau=[], bcT=cfg.bcT, solvertau=_KrylovSolver(), time=time, datetime=datetime,
+              update_progress=lambda *a: None, j=0, jjj=0, Tf=10.0, elapsed=0.0, total_elapsed=0.0, iter=0, t=cfg.t,
+              ramp_function=_TimeExprT(cfg._tt), t_array=[], ek_array=[], ee_array=[], nus_array=[])
+    for name in ("Ra", "Pr", "Vh", "Bi"):
+        ns[name] = float(p[name])
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
+    m3 = lambda v: ufl.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns.update(tau0=m3(ns["tau0_vec"]), tau1=m3(ns["tau1_vec"]))
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k_].split() for k_ in ("w0", "w12", "ws", "w1"))
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec))
+    exec(_lines(script, 326, 329), ns)
+    body = _lines(script, 358, 535)
+    for _ in range(K):
+        exec(body, ns)
+        r = twin.step()
+        for key in ("E_k", "E_e", "Nus"):
+            assert abs(ns[key] - r[key]) <= 1e-9 * max(abs(r[key]), 1e-12), key
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("w0", twin.w0),
+                      ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-6
