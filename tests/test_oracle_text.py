@@ -745,3 +745,27 @@ def test_incompressible_dgp_loop_body_text_drives_the_oracle_for_k_steps():
         assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
     assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
     assert np.abs(twin.w1.vec).max() > 1e-6
+
+
+def test_refinement_indicator_text_against_the_oracle():
+    """fenepmp_jbp.py:694-705 -- the post-loop adaptive-refinement indicator (residual norm projected onto DG0,
+    normalize_solution, tau average, |kapp / (tau_average + 1e-6)|) with the reference's own normalize_solution / absolute
+    helpers, against the oracle's refinement_indicator()."""
+    from oracle import configs_jbp as cj
+    import fxt_jbp as jb
+    base = os.path.join("..", "flow between eccentrically rotating cylinders")
+    script = os.path.join(base, "fenepmp_jbp.py")
+    cfg = cj.FenepmpJBP(fem.annulus_mesh(12, 3))
+    jb.randomize(cfg)
+    ns = _namespace(cfg)
+    _ref_helpers(os.path.join(base, "fenics_base.py"), _BASE_HELPERS + ("absolute", "normalize_solution"), ns)
+    _mini_dolfin(cfg, ns)
+    for name in ("Re", "We", "Ma", "dt"):
+        ns[name] = float(cfg.p[name])
+    ns.update(I_vec=cfg.I_vec, err_count=0)
+    exec(_lines(script, 694, 705), ns)
+    want = cfg.refinement_indicator(err_count=0)
+    assert lc.rel_err(ns["norm_kapp"].fn.vec, want["kapp"]) < 1e-12
+    assert lc.rel_err(ns["error_rat"].fn.vec, want["error_rat"]) < 1e-10
+    assert abs(ns["ratio"] - want["ratio"]) < 1e-15
+    assert ns["norm_kapp"] is ns["kapp"]          # normalize_solution works in place: kapp IS the normalised function
