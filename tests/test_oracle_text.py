@@ -769,3 +769,76 @@ def test_refinement_indicator_text_against_the_oracle():
     assert lc.rel_err(ns["error_rat"].fn.vec, want["error_rat"]) < 1e-10
     assert abs(ns["ratio"] - want["ratio"]) < 1e-15
     assert ns["norm_kapp"] is ns["kapp"]          # normalize_solution works in place: kapp IS the normalised function
+
+
+# ---- post-loop helpers of lid-driven-cavity/fenics_fem.py: stream_function, comp_stream_function, shear_rate ----------
+class _VProxy:
+    """V = u.function_space().sub(0).collapse(): the oracle's scalar P2 space behind dolfin's method names"""
+
+    def __init__(self, space):
+        self.space = space
+
+    def sub(self, i):
+        return self
+
+    def collapse(self):
+        return self
+
+    def mesh(self):
+        return self
+
+    def topology(self):
+        return self
+
+    def dim(self):
+        return 2
+
+
+class _VelocityView(ufl.Coef):
+    """the `u1` the scripts hand to stream_function(u1): a .split() view that still knows its function space"""
+
+    def __init__(self, fn, Vs):
+        super().__init__(fn, (0, 1), False)
+        self._proxy = _VProxy(Vs)
+
+    def function_space(self):
+        return self._proxy
+
+
+def _post_namespace(cfg):
+    ns = _namespace(cfg)
+    everywhere = lambda x: np.ones(len(x), dtype=bool)  # noqa: E731
+
+    def assemble_system(a, L, bc):
+        A, b = fem.assemble(a), fem.assemble(L)
+        bc.apply(A, b)        # dolfin's assemble_system eliminates symmetrically: the same solution
+        return A, b
+
+    def solve(A, x, b, *a):
+        x.fn.vec[:] = fem.solve_lu(A, b)
+    ns.update(TrialFunction=lambda V: fem.TrialFunction(V.space), TestFunction=lambda V: fem.TestFunction(V.space),
+              Function=lambda V: _DF(fem.Function(V.space)), Constant=lambda c: c, DomainBoundary=lambda: everywhere,
+              DirichletBC=lambda V, g, where: fem.DirichletBC(V.space, (0,), float(g), where),
+              assemble_system=assemble_system, solve=solve)
+    return ns
+
+
+@pytest.mark.parametrize("which", ["stream_function", "comp_stream_function", "shear_rate"])
+def test_post_loop_helpers_text_against_the_oracle(which):
+    """lid-driven-cavity/fenics_fem.py:340-398, the functions the scripts call after the loop (incomp_LDC.py:457-470,
+    comp_LDC_mesh_convergence.py:604-617): their `def` blocks run on the oracle backend against the oracle's
+    stream_function / shear_rate (the diagnostics north_star names: location of the stream-function minimum)."""
+    cfg = configs.CompLDC(fem.skew_mesh(6))
+    lc.randomize(cfg)
+    ns = _post_namespace(cfg)
+    _ref_helpers("fenics_fem.py", ("tgrad", which), ns)
+    u1 = _VelocityView(cfg.w1, cfg.S["Vs"])
+    if which == "stream_function":
+        got, want = ns[which](u1), configs.stream_function(cfg.S, cfg.u1)[0]
+    elif which == "comp_stream_function":
+        got, want = ns[which](cfg.rho1.expr(), u1), configs.stream_function(cfg.S, cfg.u1, cfg.rho1.expr())[0]
+    else:
+        got, want = ns[which](u1), configs.shear_rate(cfg.S, cfg.u1)[0]
+    assert lc.rel_err(got.fn.vec, want) < 1e-11 and np.abs(want).max() > 0
+    xy = cfg.S["Vs"].tabulate_dof_coordinates()
+    assert np.array_equal(xy[np.argmin(got.fn.vec)], xy[np.argmin(want)])       # min_location(psi)
