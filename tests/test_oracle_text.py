@@ -842,3 +842,46 @@ def test_post_loop_helpers_text_against_the_oracle(which):
     assert lc.rel_err(got.fn.vec, want) < 1e-11 and np.abs(want).max() > 0
     xy = cfg.S["Vs"].tabulate_dof_coordinates()
     assert np.array_equal(xy[np.argmin(got.fn.vec)], xy[np.argmin(want)])       # min_location(psi)
+
+
+# ---- function_spaces(mesh, 2): the element choice of the three helper modules -----------------------------------------
+class _El:
+    """FiniteElement / VectorElement / MixedElement stand-in: records the scalar components (family, degree)"""
+
+    def __init__(self, comps):
+        self.comps = tuple(comps)
+
+    def __mul__(self, other):              # V_s*Z_d
+        return _El(self.comps + other.comps)
+
+
+@pytest.mark.parametrize("relpath", ["fenics_fem.py", os.path.join("..", "buoyancy-driven-flow", "fenics_fem.py"),
+                                     os.path.join("..", "flow between eccentrically rotating cylinders", "fenics_base.py")])
+def test_function_spaces_text_gives_the_elements_the_oracle_and_the_library_use(relpath):
+    """function_spaces(mesh, 2) of each helper module (lid-driven-cavity/fenics_fem.py:262-287 and its two siblings), run on
+    recording stand-ins for dolfin's element classes: W = P2 x P2 x DG0^3, V = P2^2, Zd = DG0^3, Zc = P2^3, Q = P1,
+    Qt = DG0 -- what oracle.configs.make_spaces and fenics_b200.spaces.ELEMENTS hard-code."""
+    from fenics_b200.spaces import ELEMENTS
+    kind = {("CG", 2): "P2", ("CG", 1): "P1", ("DG", 0): "DG0", ("DG", 1): "DG1", ("Bubble", 3): "B3"}
+
+    class _Cell:
+        def ufl_cell(self):
+            return "triangle"
+
+    def FiniteElement(family, cell, degree, *a):
+        return _El([kind[(family, degree)]])
+
+    def VectorElement(family, cell, degree, dim=2):
+        return _El([kind[(family, degree)]] * dim)
+
+    def FunctionSpace(mesh, el, degree=None):
+        return _El([kind[(el, degree)]]) if isinstance(el, str) else el
+    ns = dict(FiniteElement=FiniteElement, VectorElement=VectorElement, FunctionSpace=FunctionSpace)
+    _ref_helpers(relpath, ("function_spaces",), ns)
+    W, V, Vd, Z, Zd, Zc, Q, Qt, Qr = ns["function_spaces"](_Cell(), 2)
+    got = dict(W=W.comps, V=V.comps, Zd=Zd.comps, Zc=Zc.comps, Q=Q.comps, Qt=Qt.comps)
+    ora = configs.make_spaces(fem.skew_mesh(2))
+    for name, comps in got.items():
+        assert tuple(ora[name].comps) == comps, name
+        assert tuple(ELEMENTS[name]) == comps, name
+    assert Qr.comps == Q.comps
