@@ -885,3 +885,72 @@ def test_function_spaces_text_gives_the_elements_the_oracle_and_the_library_use(
         assert tuple(ora[name].comps) == comps, name
         assert tuple(ELEMENTS[name]) == comps, name
     assert Qr.comps == Q.comps
+
+
+# ---- mesh generators: Skew_Mesh / DGP_Mesh text on a recording MeshEditor ---------------------------------------------
+@pytest.mark.parametrize("relpath,fn,maps", [("fenics_fem.py", "Skew_Mesh", ("yskewcavity",)),
+                                             (os.path.join("..", "buoyancy-driven-flow", "fenics_fem.py"), "DGP_Mesh", ("xskewcavity",))])
+def test_mesh_generator_text_against_oracle_and_library(relpath, fn, maps):
+    """Skew_Mesh(mm, B, L) (lid-driven-cavity/fenics_fem.py:91-140) and DGP_Mesh (buoyancy-driven-flow/fenics_fem.py:261-311):
+    their text -- RectangleMesh, the vertex loop through y-/xskewcavity (with the module's own `pi`), MeshEditor -- run on
+    a RectangleMesh stand-in with dolfin's vertex / cell order ('right' diagonal: the oracle's assumption) and a
+    recording MeshEditor: vertices and cells equal the oracle's and the library's meshes."""
+    import ast
+    from fenics_b200 import mesh as pmesh
+    path = os.path.join(REF, relpath)
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    made = {}
+
+    class Point:
+        def __init__(self, x, y):
+            self.xy = (x, y)
+
+    class RectangleMesh:
+        def __init__(self, p0, p1, nx, ny):
+            self.m = fem.rectangle_mesh(p0.xy[0], p0.xy[1], p1.xy[0], p1.xy[1], nx, ny)
+
+        def num_vertices(self):
+            return len(self.m.coords)
+
+        def num_cells(self):
+            return len(self.m.cells)
+
+        def coordinates(self):
+            return self.m.coords
+
+        def cells(self):
+            return self.m.cells
+
+    class Mesh:
+        pass
+
+    class MeshEditor:
+        def open(self, mesh, cell, tdim, gdim):
+            assert (cell, tdim, gdim) == ("triangle", 2, 2)
+
+        def init_vertices(self, n):
+            made["x"] = np.zeros((n, 2))
+
+        def init_cells(self, n):
+            made["c"] = np.zeros((n, 3), dtype=np.int64)
+
+        def add_vertex(self, i, x):
+            made["x"][i] = x
+
+        def add_cell(self, i, c):
+            made["c"][i] = c
+
+        def close(self):
+            pass
+    ns = dict(np=np, Point=Point, RectangleMesh=RectangleMesh, Mesh=Mesh, MeshEditor=MeshEditor)
+    for node in ast.parse(open(path).read()).body:      # the module's own `pi = 3.14159265359`
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "pi":
+            exec(compile(ast.Module([node], type_ignores=[]), path, "exec"), ns)
+    _ref_helpers(relpath, maps + (fn,), ns)
+    mm = 5
+    ns[fn](mm, 1, 1)
+    ora = fem.skew_mesh(mm) if fn == "Skew_Mesh" else __import__("oracle.configs_dgp", fromlist=["x"]).dgp_mesh(mm)
+    lib = pmesh.Skew_Mesh(mm, 1, 1) if fn == "Skew_Mesh" else pmesh.DGP_structured_mesh(mm, 0, 0, 1, 1, 1, 1)
+    assert np.array_equal(made["c"], ora.cells) and np.abs(made["x"] - ora.coords).max() < 1e-15
+    assert np.array_equal(made["c"], np.asarray(lib.cells())) and np.abs(made["x"] - np.asarray(lib.coordinates())).max() < 1e-15
