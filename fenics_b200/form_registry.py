@@ -175,6 +175,15 @@ def _register_cfg2():
     L1 += th * DEVSSr_u12
     _reg(a1, A.FX_FORM_C2_A1, "a1 = lhs(Fu12) + th*DEVSSl_u12 (comp_LDC_mesh_convergence.py:439,442)")
     _reg(L1, A.FX_FORM_C2_L1, "L1 = rhs(Fu12) + th*DEVSSr_u12 (comp_LDC_mesh_convergence.py:440,443)")
+    # the sweep script comp_LDC.py writes the same step with `Re*conv*dot(u0, nabla_grad(u0))` (:418): same functor, its
+    # `conv` slot holding Re*conv
+    re_conv = dict(conv=lambda P: P["Re"] * P["conv"])
+    Fu12s = dot(Re * rho0 * (2.0 * (u - u0) / dt + Re * conv * dot(u0, nabla_grad(u0))), v) * dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v)) * dx \
+        + dot(p0 * n, v) * ds - dot(betav * nabla_grad(U) * n, v) * ds - (1.0 / 3) * betav * dot(div(U) * n, v) * ds \
+        - dot(tau0 * n, v) * ds \
+        + inner(D - Dcomp(u), R) * dx
+    _reg(rhs(Fu12s) + th * DEVSSr_u12, A.FX_FORM_C2_L1, "L1 = rhs(Fu12) + th*DEVSSr_u12 (comp_LDC.py:418-431)", re_conv)
     DEVSSr_u1 = 2 * (1 - betav) * inner(D12, Dincomp(v)) * dx                  # :454
     # predictor :458-473
     lhsFus = Re * rho0 * ((u - u0) / dt + conv * dot(u12, nabla_grad(u12)))
@@ -188,6 +197,12 @@ def _register_cfg2():
     L2 += th * DEVSSr_u1
     _reg(a2, A.FX_FORM_C2_A2, "a2 = lhs(Fus) + th*DEVSSl_u1 (comp_LDC_mesh_convergence.py:469,472)")
     _reg(L2, A.FX_FORM_C2_L2, "L2 = rhs(Fus) + th*DEVSSr_u1 (comp_LDC_mesh_convergence.py:470,473)")
+    Fuss = dot(Re * rho0 * ((u - u0) / dt + Re * conv * dot(u12, nabla_grad(u12))), v) * dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v)) * dx \
+        + 0.5 * dot(p0 * n, v) * ds - dot(betav * nabla_grad(U) * n, v) * ds - (1.0 / 3) * betav * dot(div(U) * n, v) * ds \
+        - dot(tau0 * n, v) * ds \
+        + inner(D - Dcomp(u), R) * dx
+    _reg(rhs(Fuss) + th * DEVSSr_u1, A.FX_FORM_C2_L2, "L2 = rhs(Fus) + th*DEVSSr_u1 (comp_LDC.py:468-481)", re_conv)
     # pressure :483-490
     lhs_p_1 = (Ma * Ma / (dt * Re)) * p
     rhs_p_1 = (Ma * Ma / (dt * Re)) * p0 - rho0 * div(us) + dot(grad(rho0), us)
@@ -223,9 +238,9 @@ def _register_cfg2():
     _reg((tau1_vec[0] + tau1_vec[2]) * dx, A.FX_FORM_C2_EE, "E_e (comp_LDC_mesh_convergence.py:549)")
 
 
-def _reg(form, fid, what):
+def _reg(form, fid, what, derived=None):
     _, ctx = form.signature()
-    S.register(form, fid, [c.slot for c in ctx.coefs], what)
+    S.register(form, fid, [c.slot for c in ctx.coefs], what, derived)
 
 
 def load():

@@ -464,15 +464,17 @@ def system(form):
 _REGISTRY = {}
 
 
-def register(form, form_id, slots, what):
+def register(form, form_id, slots, what, derived=None):
     """form: a Form built from template objects; slots: fx_field slot of every coefficient in order of first
-    appearance; what: the script statement it restates (file:line) for error messages"""
+    appearance; what: the script statement it restates (file:line) for error messages; derived: {parameter name:
+    f(values by name)} for a functor whose parameter slot holds a COMBINATION of the script's scalars (comp_LDC.py writes
+    `Re*conv*dot(u, nabla_grad(u))` where the functor multiplies by its `conv` slot)"""
     sig, ctx = form.signature()
     if len(ctx.coefs) != len(slots):
         raise ValueError("%s: %d coefficients in the form, %d slots given" % (what, len(ctx.coefs), len(slots)))
     # two scripts may write the SAME form (the stress matrix of configs 1 and 2 is one operator, served by one functor
     # under two ids): the first registration stands
-    _REGISTRY.setdefault(sig, (int(form_id), tuple(int(s) for s in slots), what))
+    _REGISTRY.setdefault(sig, (int(form_id), tuple(int(s) for s in slots), what, dict(derived or {})))
 
 
 def recognise(form):
@@ -486,5 +488,10 @@ def recognise(form):
         raise UnknownForm("no hand-written functor matches this form (rank %d on %s, %d integrals, %d coefficients); "
                           "the library recognises %d forms of the reference scripts -- see fenics_b200/form_registry.py"
                           % (len(ctx.args), sorted(ctx.spaces), len(form.integrals), len(ctx.coefs), len(_REGISTRY)))
-    fid, slots, what = hit
-    return fid, list(zip(slots, ctx.coefs)), dict(ctx.params), what, ctx.space_objs
+    fid, slots, what, derived = hit
+    params = dict(ctx.params)
+    if derived:
+        values = {k: float(v.value) for k, v in params.items()}
+        for name, fn in derived.items():
+            params[name] = Parameter(name, fn(values))
+    return fid, list(zip(slots, ctx.coefs)), params, what, ctx.space_objs

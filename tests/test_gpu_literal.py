@@ -311,3 +311,46 @@ def test_literal_config2_time_step_equals_the_driver_step():
         assert lc.rel_err(ns[name].vector().get_local(), ref.vector().get_local()) < 1e-8, name
     assert abs(ns["E_k"] - want["E_k"]) < 1e-9 * abs(want["E_k"])
     assert abs(ns["E_e"] - want["E_e"]) < 1e-9 * max(abs(want["E_e"]), 1e-12)
+
+
+def test_literal_sweep_script_right_hand_sides_bind_re_times_conv():
+    """comp_LDC.py:418-431 on the GPU: the literal L1 with `Re*conv*dot(u0, nabla_grad(u0))` equals the sweep driver's
+    (CompLDCSweep: the functor's conv slot holds Re*conv), and differs from the mesh-convergence form with the same conv."""
+    from fenics_b200.shims.lid_driven_cavity.fenics_fem import (Dcomp, Dincomp, FacetNormal, Parameter, TestFunctions,
+                                                                assemble, div, dot, ds, dx, inner, nabla_grad, rhs, sigma,
+                                                                trial_functions)
+    drv = ldc.CompLDCSweep(pmesh.Skew_Mesh(12, 1, 1), Re=25.0, conv=0.5)
+    drv.t = 0.45
+    drv.step()
+    drv.step()
+    S, pv = drv.S, drv.p
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    Re, We, dt, betav, th = (Parameter(k, pv[k]) for k in ("Re", "We", "dt", "betav", "th"))
+    conv = Parameter("conv", 0.5)                          # the script's conv (the driver's table holds Re*conv = 12.5)
+    assert pv["conv"] == 12.5
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = trial_functions(Q, Zc, W)
+    (v, R_vec) = TestFunctions(W)
+    R, n = m3(R_vec), FacetNormal(drv.mesh)
+    rho0, p0 = drv.rho0, drv.p0
+    (u0, D0_vec) = drv.w0.split()
+    D0, tau0 = m3(D0_vec), m3(symbolic.as_expr(drv.tau0_vec))
+    DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx
+    U = 0.5*(u + u0)
+    lhsFu12 = Re*rho0*(2.0*(u - u0) / dt + Re*conv*dot(u0, nabla_grad(u0)))
+    Fu12 = dot(lhsFu12, v)*dx + \
+        + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \
+        + dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \
+        - dot(tau0*n, v)*ds \
+        +  inner(D-Dcomp(u),R)*dx
+    L1 = rhs(Fu12)
+    L1+= th*DEVSSr_u12
+    got = assemble(L1).t.cpu().numpy()
+    want = dapi.assemble(drv.pr.form(abi.FX_FORM_C2_L1)).t.cpu().numpy()
+    assert lc.rel_err(got, want) < 1e-13
+    lhs_mc = Re*rho0*(2.0*(u - u0) / dt + conv*dot(u0, nabla_grad(u0)))   # the mesh-convergence form with conv = 0.5
+    F_mc = dot(lhs_mc, v)*dx + inner(sigma(U, p0, tau0, We, betav), Dincomp(v))*dx \
+        + dot(p0*n, v)*ds - dot(betav*nabla_grad(U)*n, v)*ds - (1.0/3)*betav*dot(div(U)*n,v)*ds \
+        - dot(tau0*n, v)*ds + inner(D-Dcomp(u),R)*dx
+    other = assemble(rhs(F_mc) + th*DEVSSr_u12).t.cpu().numpy()
+    assert lc.rel_err(other, want) > 1e-6

@@ -221,3 +221,26 @@ def test_text_of_config2_density_projection():
     exec(_lines2(501, 502), ns)
     assert rec[0] == abi.FX_FORM_MASS_Q
     assert rec[1] == (abi.FX_FORM_C2_L_RHO1, [abi.FX_F_RHO0, abi.FX_F_P1, abi.FX_F_P0], ["Ma", "Re"])
+
+
+def test_text_of_the_sweep_script_binds_re_times_conv():
+    """lid-driven-cavity/comp_LDC.py:418-441, :468-481: the sweep script writes `Re*conv*dot(u, nabla_grad(u))`; its two
+    momentum right-hand sides are served by config 2's functors with the `conv` slot holding Re*conv (derived parameter)"""
+    ref3 = os.path.join(os.path.dirname(REF), "comp_LDC.py")
+    if not os.path.exists(ref3):
+        pytest.skip("reference checkout not present")
+    src = open(ref3).read().splitlines()
+    for (a, b), ids in (((418, 441), (abi.FX_FORM_C2_A1, abi.FX_FORM_C2_L1)), ((468, 489), (abi.FX_FORM_C2_A2, abi.FX_FORM_C2_L2))):
+        rec = []
+        ns = _namespace2(rec)
+        ns["Re"], ns["conv"] = symbolic.Parameter("Re", 25.0), symbolic.Parameter("conv", 0.5)
+        seen = {}
+
+        def assemble(form, seen=seen):
+            fid, coefs, params, what, _ = symbolic.recognise(form)
+            seen[fid] = params
+            return ("tensor", fid)
+        ns["assemble"] = assemble
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+        assert tuple(seen) == ids
+        assert seen[ids[1]]["conv"].value == 25.0 * 0.5 and seen[ids[1]]["Re"].value == 25.0
