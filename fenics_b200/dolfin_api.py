@@ -138,7 +138,8 @@ def _recognised(form):
                            "solution_functions / Function(V, plan) first)" % what)
     pr = _problem_of(plan)
     for slot, fn in coefs:
-        pr.bind(slot, fn)
+        if slot >= 0:   # slot -1: a coefficient the functor replaces by a constant of its own (form_registry.py)
+            pr.bind(slot, fn)
     for name, par in params.items():
         pr.set_param(getattr(abi, "FX_P_" + name.upper()), par.value)
     return Form(pr, fid)

@@ -7,8 +7,9 @@ Parameters is then served by the hand-written functors: `assemble(a1)` is litera
 
 Covered: lid-driven-cavity/incomp_LDC.py (config 1: ten forms, both functionals) and
 lid-driven-cavity/comp_LDC_mesh_convergence.py (config 2, the bench configuration: twelve forms through lhs() / rhs(), both
-functionals).  The other loops are driven through `fenics_b200.drivers.*` (fx_form ids directly); their forms can be
-registered the same way.
+functionals), its sweep sibling comp_LDC.py, and buoyancy-driven-flow/compressible_dgp.py (config 5: sixteen forms, four
+projections, three functionals).  The journal-bearing loops are driven through `fenics_b200.drivers.*` (fx_form ids
+directly); their forms can be registered the same way.
 """
 from . import _abi as abi
 from . import symbolic as S
@@ -238,6 +239,131 @@ def _register_cfg2():
     _reg((tau1_vec[0] + tau1_vec[2]) * dx, A.FX_FORM_C2_EE, "E_e (comp_LDC_mesh_convergence.py:549)")
 
 
+def _register_cfg5():
+    """buoyancy-driven-flow/compressible_dgp.py (config 5): trial/test functions :100-118, theta :294-296, DEVSS :336-338,
+    LPS :391, loop :404-583.  Parameters named like the parameter slots (T_0 -> "T0", T_h -> "th_hot", al_1 -> "al1",
+    al_2 -> "al2"); DOLFIN_EPS of the SU weight (:510) is a number in the script: the functor reads it from FX_P_EPS."""
+    from .shims._common import (DOLFIN_EPS, Dcomp, Dincomp, Fdef_compressible as Fdefcom, dgp_sigmacom as sigmacom,
+                                magnitude)
+    from .symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_vector, div, dot, ds, dx, grad, inner, lhs,
+                           nabla_grad, rhs)
+    A = abi
+    Ra, Pr, We, Ma, dt, betav, th, Vh, Bi, c1, c2, T_0, T_h, al_1, al_2 = (
+        Parameter(n_, 1.0) for n_ in ("Ra", "Pr", "We", "Ma", "dt", "betav", "th", "Vh", "Bi", "c1", "c2", "T0", "th_hot",
+                                      "al1", "al2"))
+    eps = dict(eps=lambda P: DOLFIN_EPS)
+    T_ = TemplateFunction
+    w0, w12, ws, w1 = T_("W", A.FX_F_W0), T_("W", A.FX_F_W12), T_("W", A.FX_F_WS), T_("W", A.FX_F_W1)
+    p0, p1 = T_("Q", A.FX_F_P0), T_("Q", A.FX_F_P1)
+    rho0, rho12, rho1 = T_("Q", A.FX_F_RHO0), T_("Q", A.FX_F_RHO12), T_("Q", A.FX_F_RHO1)
+    T0, T1 = T_("Q", A.FX_F_T0), T_("Q", A.FX_F_T1)
+    theta0, therm_inv, theta1 = T_("Q", A.FX_F_THETA0), T_("Q", A.FX_F_THERM_INV), T_("Q", A.FX_F_Q_A)
+    tau0_vec, tau1_vec, kapp = T_("Zc", A.FX_F_TAU0), T_("Zc", A.FX_F_TAU1), T_("Qt", A.FX_F_KAPP)
+    h, n = CellDiameter(), FacetNormal()
+    k = as_vector([0.0, 1.0])                                                   # Expression(('0','1'), degree=2) :177
+    rho = p = T = arguments("Q", 1)
+    q = r = arguments("Q", 0)
+    tau_vec, Rt_vec = arguments("Zc", 1), arguments("Zc", 0)
+    (u, D_vec), (v, R_vec) = arguments("W", 1), arguments("W", 0)
+    D, tau, R, Rt = _sym3(D_vec), _sym3(tau_vec), _sym3(R_vec), _sym3(Rt_vec)
+    (u0, D0_vec), (u12, D12_vec), (us, _), (u1, _) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D12 = _sym3(D0_vec), _sym3(D12_vec)
+    tau0, tau1 = _sym3(S.as_expr(tau0_vec)), _sym3(S.as_expr(tau1_vec))
+    thetal = (T) / (T_h - T_0)                                                  # :294
+    thetar = T_("Q", -1)   # :295-296 project(T_0/(T_h-T_0), Q): a Function in the script, a constant inside the functors
+    #                        (slot -1: recognised as a coefficient of the form, not handed to the kernel)
+    DEVSSl_u12 = 2 * (1 - betav) * inner(Dcomp(u), Dincomp(v)) * dx             # :336
+    DEVSSl_u1 = 2 * (1 - betav) * inner(Dcomp(u), Dincomp(v)) * dx              # :338
+    LPSl_stress = inner(kapp * h * c1 * grad(tau), grad(Rt)) * dx + inner(kapp * h * c2 * div(tau), div(Rt)) * dx  # :391
+    # per-step projections :405-408
+    _reg(inner(q, (T0 - T_0) / (T_h - T_0)) * dx, A.FX_FORM_C5_L_THETA0, "project((T0-T_0)/(T_h-T_0), Q) (compressible_dgp.py:405)")
+    therm = (al_1 + al_2 * theta0)
+    _reg(inner(q, 1.0 / therm) * dx, A.FX_FORM_C5_L_THERM_INV, "project(1.0/therm, Q) (compressible_dgp.py:408)")
+    DEVSSr_u12 = 2 * (1 - betav) * inner(D0, Dincomp(v)) * dx                   # :413
+    U = 0.5 * (u + u0)                                                          # :416
+    # density half step :418-421 (same statements as config 2: the first registration of that signature stands)
+    rho_eq = 2.0 * (rho - rho0) / dt + dot(u0, grad(rho0)) - rho0 * div(u0)
+    rho_weak = inner(rho_eq, q) * dx
+    _reg(lhs(rho_weak), A.FX_FORM_C5_A0, "a0 (compressible_dgp.py:420)")
+    _reg(rhs(rho_weak), A.FX_FORM_C5_L0, "L0 (compressible_dgp.py:421)")
+    # velocity half step :432-442
+    Du12Dt = rho0 * (2.0 * (u - u0) / dt + dot(u0, nabla_grad(u0)))
+    Fu12 = dot(Du12Dt, v) * dx + \
+        + inner(sigmacom(U, p0, tau0, We, Pr, betav), Dincomp(v)) * dx + Ra * Pr * inner(rho0 * therm_inv * k, v) * dx \
+        + dot(p0 * n, v) * ds - betav * Pr * (dot(nabla_grad(U) * n, v) * ds + (1.0 / 3) * dot(div(U) * n, v) * ds) \
+        - (Pr * (1 - betav) / We) * dot(tau0 * n, v) * ds \
+        + inner(D - Dincomp(u), R) * dx
+    a1, L1 = lhs(Fu12), rhs(Fu12)
+    a1 += th * DEVSSl_u12
+    L1 += th * DEVSSr_u12
+    _reg(a1, A.FX_FORM_C5_A1, "a1 (compressible_dgp.py:439,441)")
+    _reg(L1, A.FX_FORM_C5_L1, "L1 (compressible_dgp.py:440,442)")
+    DEVSSr_u1 = 2 * (1 - betav) * inner(D12, Dincomp(v)) * dx                   # :453
+    # predictor :473-483
+    lhsFus = rho0 * ((u - u0) / dt + dot(u12, nabla_grad(U)))
+    Fus = dot(lhsFus, v) * dx + \
+        + inner(sigmacom(U, p0, tau0, We, Pr, betav), Dincomp(v)) * dx + Ra * Pr * inner(rho0 * therm_inv * k, v) * dx \
+        + dot(p0 * n, v) * ds - betav * Pr * (dot(nabla_grad(U) * n, v) * ds + (1.0 / 3) * dot(div(U) * n, v) * ds) \
+        - (Pr * (1.0 - betav) / We) * dot(tau0 * n, v) * ds \
+        + inner(D - Dincomp(u), R) * dx
+    a2, L2 = lhs(Fus), rhs(Fus)
+    a2 += th * DEVSSl_u1
+    L2 += th * DEVSSr_u1
+    _reg(a2, A.FX_FORM_C5_A2, "a2 (compressible_dgp.py:480,482)")
+    _reg(L2, A.FX_FORM_C5_L2, "L2 (compressible_dgp.py:481,483)")
+    # pressure :493-500
+    lhs_p_1 = (Ma * Ma / (dt)) * p
+    rhs_p_1 = (Ma * Ma / (dt)) * p0 - therm * dot(grad(rho0), us) - therm * rho0 * div(us)
+    lhs_p_2 = therm * 0.5 * dt * grad(p)
+    rhs_p_2 = therm * 0.5 * dt * grad(p0)
+    _reg(inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx, A.FX_FORM_C5_A5, "a5 (compressible_dgp.py:499)")
+    _reg(inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx, A.FX_FORM_C5_L5, "L5 (compressible_dgp.py:500)")
+    # SU density update :510-517
+    alpha_supg = h / (magnitude(u12) + DOLFIN_EPS)
+    SU_rho = inner(dot(u12, grad(rho)), alpha_supg * dot(u12, grad(q))) * dx
+    rho_eq = (rho - rho0) / dt + dot(u12, grad(rho12)) - rho12 * div(u12)
+    rho_weak = inner(rho_eq, q) * dx
+    a6, L6 = lhs(rho_weak), rhs(rho_weak)
+    a6 += SU_rho
+    _reg(a6, A.FX_FORM_C5_A6, "a6 (compressible_dgp.py:515,517)", eps)
+    _reg(L6, A.FX_FORM_C5_L6, "L6 (compressible_dgp.py:516)")
+    # equation of state :529-530
+    _reg(inner(q, rho0 + (Ma * Ma) * therm_inv * (p1 - p0)) * dx, A.FX_FORM_C5_L_RHO1,
+         "project(rho0 + (Ma*Ma)*therm_inv*(p1-p0), Q) (compressible_dgp.py:529-530)")
+    # velocity update :533-537
+    lhs_u1 = (1. / dt) * rho1 * u
+    rhs_u1 = (1. / dt) * rho0 * us
+    a7 = inner(lhs_u1, v) * dx + inner(D - Dincomp(u), R) * dx
+    L7 = inner(rhs_u1, v) * dx + 0.5 * (inner(p1 - p0, div(v)) * dx - dot((p1 - p0) * n, v) * ds)
+    a7 += 0
+    L7 += 0
+    _reg(a7, A.FX_FORM_C5_A7, "a7 (compressible_dgp.py:535)")
+    _reg(L7, A.FX_FORM_C5_L7, "L7 (compressible_dgp.py:536)")
+    # stress :550-555
+    stress_eq = ((We / dt) + 1.0) * tau + We * Fdefcom(u1, tau) - (We / dt) * tau0 - Identity(len(u))
+    Ast = inner(stress_eq, Rt) * dx
+    a4, L4 = lhs(Ast), rhs(Ast)
+    a4 += LPSl_stress
+    L4 += 0
+    _reg(a4, A.FX_FORM_C5_A4, "a4 (compressible_dgp.py:552,554)")
+    _reg(L4, A.FX_FORM_C5_L4, "L4 (compressible_dgp.py:553,555)")
+    # temperature :563-567
+    gamdot = inner(sigmacom(u1, p1, tau1, We, Pr, betav), grad(u1))
+    lhs_theta1 = (1.0 / dt) * rho1 * thetal + rho1 * dot(u1, grad(thetal))
+    rhs_theta1 = (1.0 / dt) * rho0 * thetar + rho1 * dot(u1, grad(thetar)) + (1.0 / dt) * rho0 * theta0 + Vh * gamdot
+    a8 = inner(lhs_theta1, r) * dx + inner(grad(thetal), grad(r)) * dx
+    L8 = inner(rhs_theta1, r) * dx + inner(grad(thetar), grad(r)) * dx + Bi * inner(grad(theta0), n * r) * ds(3) \
+        + Bi * inner(grad(theta0), n * r) * ds(4) + inner(We * tau1 * grad(thetar), grad(r)) * dx
+    _reg(a8, A.FX_FORM_C5_A8, "a8 (compressible_dgp.py:566)")
+    _reg(L8, A.FX_FORM_C5_L8, "L8 (compressible_dgp.py:567)")
+    # energies, Nusselt number :577-583
+    _reg(0.5 * rho1 * dot(u1, u1) * dx, A.FX_FORM_C5_EK, "E_k (compressible_dgp.py:577)")
+    _reg((tau1[0, 0] + tau1[1, 1] - 2.0) * dx, A.FX_FORM_C5_EE, "E_e (compressible_dgp.py:578)")
+    _reg(inner(q, (T1 - T_0) / (T_h - T_0)) * dx, A.FX_FORM_C5_L_THETA1, "project((T1-T_0)/(T_h-T_0), Q) (compressible_dgp.py:581)")
+    Tdx = inner(grad(theta1), n)
+    _reg(-Tdx * ds(2), A.FX_FORM_C5_NUS, "Nus (compressible_dgp.py:582-583)")
+
+
 def _reg(form, fid, what, derived=None):
     _, ctx = form.signature()
     S.register(form, fid, [c.slot for c in ctx.coefs], what, derived)
@@ -249,3 +375,4 @@ def load():
         _loaded = True
         _register_cfg1()
         _register_cfg2()
+        _register_cfg5()

@@ -199,6 +199,30 @@ def ldc_sigma(u, p, Tau, We, betav):
     return 2 * betav * Dcomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
 
 
+def end():
+    """dolfin's end() closes a begin()/end() log block (every sub-step of the loops calls it): nothing to close here"""
+
+
+def dgp_sigma(u, p, Tau, We, Pr, betav):
+    """buoyancy-driven-flow/fenics_fem.py:68-72: Prandtl-scaled incompressible stress; the polymer part is dropped for
+    betav >= 1"""
+    I = alg(u).Identity(len(u))
+    s = 2 * Pr * betav * Dincomp(u) - p * I
+    return s + Pr * ((1 - betav) / We) * (Tau - I) if betav < 1 else s
+
+
+def dgp_sigma_n(U, p, tau, n, We, Pr, betav):
+    """buoyancy-driven-flow/fenics_fem.py:74-78: traction sigma.n as the scripts write it"""
+    t = Pr * betav * alg(U).nabla_grad(U) * n - p * n
+    return t + (Pr * (1 - betav) / We) * tau * n if betav < 1 else t
+
+
+def dgp_sigmacom(u, p, Tau, We, Pr, betav):
+    """buoyancy-driven-flow/fenics_fem.py:80-81"""
+    I = alg(u).Identity(len(u))
+    return 2 * Pr * betav * Dcomp(u) - p * I + Pr * ((1 - betav) / We) * (Tau - I)
+
+
 def reshape_elements(D0_vec, D12_vec, Ds_vec, D1_vec, tau0_vec, tau12_vec, tau1_vec):
     """the seven 3-vectors as symmetric 2x2 tensors [[a,b],[b,c]] (fenics_fem.py:210-225)."""
     A = alg(D0_vec)

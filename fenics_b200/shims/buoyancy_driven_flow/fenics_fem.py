@@ -12,7 +12,13 @@ from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, D
                        mesh2triang, min_location, mplot, normalize_solution, pi, reshape_elements, set_algebra,
                        skewcavity, solution_functions, tgrad, trial_functions, update_progress, xskewcavity)
 from fenics_b200.shims._common import Fdef_compressible as Fdefcom  # noqa: F401
+from fenics_b200.shims._common import dgp_sigma as sigma, dgp_sigma_n as sigma_n, dgp_sigmacom as sigmacom  # noqa: F401
+from fenics_b200.symbolic import lhs, rhs, system  # noqa: F401
+from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
+                                  dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
+from fenics_b200.dolfin_api import TestFunction, TestFunctions, TrialFunction, TrialFunctions  # noqa: F401
 from fenics_b200.shims._common import Fdef_incompressible as Fdef  # noqa: F401
+from fenics_b200.shims._common import end  # noqa: F401
 from fenics_b200.shims.lid_driven_cavity.fenics_fem import (comp_stream_function, l2norm_solution, ramp_function,  # noqa: F401
                                             shear_rate, stream_function)
 
@@ -20,25 +26,6 @@ DGP_unstructured_mesh = _needs_dolfin("DGP_unstructured_mesh")
 refine_boundary = _needs_dolfin("refine_boundary")
 refine_top = _needs_dolfin("refine_top")
 refine_walls = _needs_dolfin("refine_walls")
-
-
-def sigma(u, p, Tau, We, Pr, betav):
-    """Prandtl-scaled incompressible stress; the polymer part is dropped for betav >= 1 (:68-72)"""
-    I = alg().Identity(len(u))
-    s = 2 * Pr * betav * Dincomp(u) - p * I
-    return s + Pr * ((1 - betav) / We) * (Tau - I) if betav < 1 else s
-
-
-def sigma_n(U, p, tau, n, We, Pr, betav):
-    """traction sigma.n as the scripts write it (:74-78)"""
-    A = alg()
-    t = Pr * betav * A.nabla_grad(U) * n - p * n
-    return t + (Pr * (1 - betav) / We) * tau * n if betav < 1 else t
-
-
-def sigmacom(u, p, Tau, We, Pr, betav):
-    I = alg().Identity(len(u))
-    return 2 * Pr * betav * Dcomp(u) - p * I + Pr * ((1 - betav) / We) * (Tau - I)
 
 
 def _tag(loop, subloop, tag):

@@ -7,6 +7,7 @@ import numpy as np  # noqa: F401
 from fenics_b200 import mesh as _mesh
 from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, assemble, norm, parameters, project,  # noqa: F401
                            solve)
+from fenics_b200.shims._common import end  # noqa: F401
 from fenics_b200.shims._common import (DOLFIN_EPS, Dcomp, Dincomp, _needs_dolfin, _T, absolute, adaptive_refinement, alg,  # noqa: F401
                        chunks, function_spaces, magnitude, max_location, mesh2triang, min_location, mplot,
                        normalize_solution, pi, reshape_elements, set_algebra, solution_functions, tgrad,

@@ -354,3 +354,115 @@ def test_literal_sweep_script_right_hand_sides_bind_re_times_conv():
         - dot(tau0*n, v)*ds + inner(D-Dcomp(u),R)*dx
     other = assemble(rhs(F_mc) + th*DEVSSr_u12).t.cpu().numpy()
     assert lc.rel_err(other, want) > 1e-6
+
+
+def test_literal_config5_forms_equal_the_driver():
+    """buoyancy-driven-flow/compressible_dgp.py:405-583: the forms of the buoyancy-driven loop written as the script
+    writes them (sigmacom, the Boussinesq source Ra*Pr*rho0*therm_inv*k, `lhs` / `rhs`, ds(3) / ds(4) / ds(2)) assemble
+    to what the driver's fx_form ids give; so do the four projections the script hands to project()."""
+    import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
+    from fenics_b200.drivers import dgp
+    drv = dgp.CompDGP(mesh_resolution=8)
+    drv.t = 1.4
+    for _ in range(3):
+        drv.step()
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    S, pv = drv.S, drv.p
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    P = ff.Parameter
+    ns.update({k: P(k, pv[k]) for k in ("Ra", "Pr", "We", "Ma", "dt", "betav", "th", "Vh", "Bi", "c1", "c2")})
+    ns.update(T_0=P("T0", pv["T0"]), T_h=P("th_hot", pv["th_hot"]), al_1=P("al1", pv["al1"]), al_2=P("al2", pv["al2"]))
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = ff.trial_functions(Q, Zc, W)
+    (v, R_vec) = ff.TestFunctions(W)
+    q = ff.TestFunction(Q)
+    ns.update(Q=Q, p=p, rho=p, T=p, q=q, r=q, u=u, D=D, tau=tau, v=v, R=m3(R_vec), Rt=m3(ff.TestFunction(Zc)),
+              h=ff.CellDiameter(drv.mesh), n=ff.FacetNormal(drv.mesh), k=ff.as_vector([0.0, 1.0]))
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "T0", "T1", "theta0", "therm_inv", "theta1",
+                 "tau0_vec", "tau1_vec", "kapp"):
+        ns[name] = getattr(drv, name)
+    thetar = dapi.Function(Q, drv.plan)
+    thetar.vector().t.fill_(pv["T0"] / (pv["th_hot"] - pv["T0"]))        # project(T_0/(T_h-T_0), Q): exact for a constant
+    ns["thetar"] = thetar
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (drv.w0.split(), drv.w12.split(), drv.ws.split(),
+                                                                            drv.w1.split())
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec), tau0=m3(symbolic.as_expr(drv.tau0_vec)), tau1=m3(symbolic.as_expr(drv.tau1_vec)))
+    exec('''
+thetal = (T)/(T_h-T_0)
+DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx
+therm = (al_1+al_2*theta0)
+DEVSSr_u12 = 2*(1-betav)*inner(D0,Dincomp(v))*dx
+U = 0.5*(u + u0)
+rho_eq = 2.0*(rho - rho0)/dt + dot(u0, grad(rho0)) - rho0*div(u0)
+rho_weak = inner(rho_eq,q)*dx
+a0 = lhs(rho_weak)
+L0 = rhs(rho_weak)
+Du12Dt = rho0*(2.0*(u - u0) / dt + dot(u0, nabla_grad(u0)))
+Fu12 = dot(Du12Dt, v)*dx + \\
+    + inner(sigmacom(U, p0, tau0, We, Pr, betav), Dincomp(v))*dx + Ra*Pr*inner(rho0*therm_inv*k,v)*dx \\
+    + dot(p0*n, v)*ds - betav*Pr*(dot(nabla_grad(U)*n, v)*ds + (1.0/3)*dot(div(U)*n,v)*ds)\\
+    - (Pr*(1-betav)/We)*dot(tau0*n, v)*ds\\
+    + inner(D-Dincomp(u),R)*dx
+a1 = lhs(Fu12)
+L1 = rhs(Fu12)
+a1+= th*DEVSSl_u12
+L1+= th*DEVSSr_u12
+DEVSSr_u1 = 2*(1-betav)*inner(D12,Dincomp(v))*dx
+lhsFus = rho0*((u - u0)/dt + dot(u12, nabla_grad(U)))
+Fus = dot(lhsFus, v)*dx + \\
+    + inner(sigmacom(U, p0, tau0, We, Pr, betav), Dincomp(v))*dx + Ra*Pr*inner(rho0*therm_inv*k,v)*dx \\
+    + dot(p0*n, v)*ds - betav*Pr*(dot(nabla_grad(U)*n, v)*ds + (1.0/3)*dot(div(U)*n,v)*ds) \\
+    - (Pr*(1.0-betav)/We)*dot(tau0*n, v)*ds\\
+    + inner(D-Dincomp(u),R)*dx
+a2= lhs(Fus)
+L2= rhs(Fus)
+a2+= th*DEVSSl_u1
+L2+= th*DEVSSr_u1
+lhs_p_1 = (Ma*Ma/(dt))*p
+rhs_p_1 = (Ma*Ma/(dt))*p0 - therm*dot(grad(rho0),us) - therm*rho0*div(us)
+lhs_p_2 = therm*0.5*dt*grad(p)
+rhs_p_2 = therm*0.5*dt*grad(p0)
+a5=inner(lhs_p_1,q)*dx + inner(lhs_p_2,grad(q))*dx
+L5=inner(rhs_p_1,q)*dx + inner(rhs_p_2,grad(q))*dx
+alpha_supg = h/(magnitude(u12)+DOLFIN_EPS)
+SU_rho = inner(dot(u12, grad(rho)), alpha_supg*dot(u12,grad(q)))*dx
+rho_eq = (rho - rho0)/dt + dot(u12, grad(rho12)) - rho12*div(u12)
+rho_weak = inner(rho_eq,q)*dx
+a6 = lhs(rho_weak)
+L6 = rhs(rho_weak)
+a6+= SU_rho
+lhs_u1 = (1./dt)*rho1*u
+rhs_u1 = (1./dt)*rho0*us
+a7=inner(lhs_u1,v)*dx +inner(D-Dincomp(u),R)*dx
+L7=inner(rhs_u1,v)*dx + 0.5*(inner(p1-p0,div(v))*dx - dot((p1-p0)*n, v)*ds)
+stress_eq = ((We/dt)+1.0)*tau  +  We*Fdefcom(u1,tau) - (We/dt)*tau0 - Identity(len(u))
+A = inner(stress_eq,Rt)*dx
+a4 = lhs(A)
+L4 = rhs(A)
+a4 += LPSl_stress
+gamdot = inner(sigmacom(u1, p1, tau1, We, Pr, betav), grad(u1))
+lhs_theta1 = (1.0/dt)*rho1*thetal + rho1*dot(u1,grad(thetal))
+rhs_theta1 = (1.0/dt)*rho0*thetar + rho1*dot(u1,grad(thetar)) + (1.0/dt)*rho0*theta0 + Vh*gamdot
+a8 = inner(lhs_theta1,r)*dx + inner(grad(thetal),grad(r))*dx
+L8 = inner(rhs_theta1,r)*dx + inner(grad(thetar),grad(r))*dx + Bi*inner(grad(theta0),n*r)*ds(3) + Bi*inner(grad(theta0),n*r)*ds(4) + inner(We*tau1*grad(thetar),grad(r))*dx
+Tdx = inner(grad(theta1),n)
+''', ns)
+    for name in ("a0", "L0", "a1", "L1", "a2", "L2", "a5", "L5", "a6", "L6", "a7", "L7", "a4", "L4", "a8", "L8"):
+        fid = getattr(abi, "FX_FORM_C5_" + name.upper())
+        got, want = ff.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
+        a, b = (got.val, want.val) if name.startswith("a") else (got.t, want.t)
+        assert lc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-13, name
+        assert float(b.abs().max()) > 0.0, name
+    for expr, fid in ((ns["rho0"] + (ns["Ma"]*ns["Ma"])*ns["therm_inv"]*(ns["p1"]-ns["p0"]), abi.FX_FORM_C5_L_RHO1),
+                      ((ns["T0"]-ns["T_0"])/(ns["T_h"]-ns["T_0"]), abi.FX_FORM_C5_L_THETA0),
+                      ((ns["T1"]-ns["T_0"])/(ns["T_h"]-ns["T_0"]), abi.FX_FORM_C5_L_THETA1),
+                      (1.0/ns["therm"], abi.FX_FORM_C5_L_THERM_INV)):
+        got = ff.assemble(ff.inner(q, expr) * ff.dx).t.cpu().numpy()
+        want = dapi.assemble(drv.pr.form(fid)).t.cpu().numpy()
+        assert lc.rel_err(got, want) < 1e-13, fid
+    for form, fid in ((0.5*ns["rho1"]*ff.dot(ns["u1"], ns["u1"])*ff.dx, abi.FX_FORM_C5_EK),
+                      ((ns["tau1"][0, 0]+ns["tau1"][1, 1]-2.0)*ff.dx, abi.FX_FORM_C5_EE), (-ns["Tdx"]*ff.ds(2), abi.FX_FORM_C5_NUS)):
+        got, want = ff.assemble(form), dapi.assemble(drv.pr.form(fid))
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-12), fid

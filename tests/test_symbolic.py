@@ -244,3 +244,95 @@ def test_text_of_the_sweep_script_binds_re_times_conv():
         exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
         assert tuple(seen) == ids
         assert seen[ids[1]]["conv"].value == 25.0 * 0.5 and seen[ids[1]]["Re"].value == 25.0
+
+
+# ---- config 5: buoyancy-driven-flow/compressible_dgp.py ---------------------------------------------------------------------
+REF5 = os.path.join(os.path.dirname(os.path.dirname(REF)), "buoyancy-driven-flow", "compressible_dgp.py")
+
+
+def _namespace5(rec):
+    import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    P = symbolic.Parameter
+    ns.update(Ra=P("Ra", 100.0), Pr=P("Pr", 2.0), We=P("We", 0.1), Ma=P("Ma", 0.05), dt=P("dt", 0.0005), betav=P("betav", 0.1),
+              th=P("th", 0.5), Vh=P("Vh", 0.005), Bi=P("Bi", 0.2), c1=P("c1", 0.05), c2=P("c2", 0.001), T_0=P("T0", 300.0),
+              T_h=P("th_hot", 350.0), al_1=P("al1", 1.0), al_2=P("al2", 1.0 / 6.0), C=200.0)
+    A = abi
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    ns.update(w0=w0, w12=w12, ws=ws, w1=w1, p0=T("Q", A.FX_F_P0), p1=T("Q", A.FX_F_P1), rho0=T("Q", A.FX_F_RHO0),
+              rho12=T("Q", A.FX_F_RHO12), rho1=T("Q", A.FX_F_RHO1), T0=T("Q", A.FX_F_T0), T1=T("Q", A.FX_F_T1),
+              thetar=T("Q", -1), tau0_vec=T("Zc", A.FX_F_TAU0), tau1_vec=T("Zc", A.FX_F_TAU1), kapp=T("Qt", A.FX_F_KAPP),
+              h=symbolic.CellDiameter(), n=symbolic.FacetNormal(), k=symbolic.as_vector([0.0, 1.0]), Q="Q")
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], Ds_vec), (ns["u1"], D1_vec) = (f.split() for f in (w0, w12, ws, w1))
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
+    ns["rho"] = ns["T"] = ns["p"]
+    ns["q"] = ns["r"] = ff.TestFunction("Q")
+    Rt_vec = ff.TestFunction("Zc")
+    (ns["v"], R_vec) = ff.TestFunctions("W")
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    ns["D0"], ns["D12"] = m3(D0_vec), m3(D12_vec)
+    ns["tau0"], ns["tau1"] = m3(symbolic.as_expr(ns["tau0_vec"])), m3(symbolic.as_expr(ns["tau1_vec"]))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    exec(textwrap.dedent("""
+        DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        DEVSSl_u1 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+        LPSl_stress = inner(kapp*h*c1*grad(tau),grad(Rt))*dx + inner(kapp*h*c2*div(tau),div(Rt))*dx
+    """), ns)
+    projected = {abi.FX_FORM_C5_L_THETA0: T("Q", A.FX_F_THETA0), abi.FX_FORM_C5_L_THERM_INV: T("Q", A.FX_F_THERM_INV),
+                 abi.FX_FORM_C5_L_RHO1: T("Q", A.FX_F_RHO1)}
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return ("tensor", fid)
+
+    def project(expr, V):
+        w = form_registry.arguments(V, 0)
+        try:
+            fid = symbolic.recognise(symbolic.inner(w, expr) * symbolic.dx)[0]
+        except symbolic.UnknownForm:
+            assert not rec                   # only phi0 (:404), the first statement: dead in the script, no functor
+            rec.append(("project", None))
+            return None
+        rec.append(("project", fid))
+        return projected[fid]
+
+    class _BC:
+        def apply(self, *a):
+            pass
+
+    class _Solver:
+        def solve(self, *a):
+            pass
+    ns.update(assemble=assemble, project=project, bcu=[_BC()], bcp=[], bctau=[], bcT=[_BC()], solvertau=_Solver(),
+              solve=lambda *a: None)
+    for f in ("w12", "ws", "w1", "p1", "tau1_vec", "rho12", "rho1", "T1"):
+        ns[f].vector = lambda: None
+    for f in projected.values():
+        f.vector = lambda: None
+    return ns
+
+
+def test_text_of_config5_loop_body_is_recognised():
+    """compressible_dgp.py:404-583 verbatim (three per-step projections, eight systems, density projection, energies,
+    Nusselt number): every assemble() / project() the text issues maps to config 5's functors, in the script's order"""
+    if not os.path.exists(REF5):
+        pytest.skip("reference checkout not present")
+    rec = []
+    ns = _namespace5(rec)
+    body = "if True:\n" + "\n".join(open(REF5).read().splitlines()[403:583]) + "\n"
+    exec(body, ns)
+    A = abi
+    got = [r[1] if r[0] == "project" else r[0] for r in rec]
+    assert got == [None, A.FX_FORM_C5_L_THETA0, A.FX_FORM_C5_L_THERM_INV,
+                   A.FX_FORM_C2_A0, A.FX_FORM_C2_L0,            # the density half step is config 2's, word for word
+                   A.FX_FORM_C5_A1, A.FX_FORM_C5_L1, A.FX_FORM_C5_A2, A.FX_FORM_C5_L2, A.FX_FORM_C5_A5, A.FX_FORM_C5_L5,
+                   A.FX_FORM_C5_A6, A.FX_FORM_C5_L6, A.FX_FORM_C5_L_RHO1, A.FX_FORM_C5_A7, A.FX_FORM_C5_L7,
+                   A.FX_FORM_C5_A4, A.FX_FORM_C5_L4, A.FX_FORM_C5_A8, A.FX_FORM_C5_L8, A.FX_FORM_C2_EK, A.FX_FORM_C5_EE,
+                   A.FX_FORM_C5_L_THETA0,   # project((T1-T_0)/(T_h-T_0), Q) :581 has theta0's structure: the same functor, T1 bound
+                   A.FX_FORM_C5_NUS]
+    a6 = [r for r in rec if r[0] == A.FX_FORM_C5_A6][0]
+    assert "eps" in a6[2]                      # DOLFIN_EPS of the SU weight reaches the functor's FX_P_EPS
+    L8 = [r for r in rec if r[0] == A.FX_FORM_C5_L8][0]
+    assert -1 in L8[1]                         # thetar: a coefficient of the form, a constant inside the functor
