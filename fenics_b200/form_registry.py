@@ -8,8 +8,9 @@ Parameters is then served by the hand-written functors: `assemble(a1)` is litera
 Covered: lid-driven-cavity/incomp_LDC.py (config 1: ten forms, both functionals) and
 lid-driven-cavity/comp_LDC_mesh_convergence.py (config 2, the bench configuration: twelve forms through lhs() / rhs(), both
 functionals), its sweep sibling comp_LDC.py, and buoyancy-driven-flow/compressible_dgp.py (config 5: sixteen forms, four
-projections, three functionals).  The journal-bearing loops are driven through `fenics_b200.drivers.*` (fx_form ids
-directly); their forms can be registered the same way.
+projections, three functionals) and "flow between eccentrically rotating cylinders"/fenepmp_jbp.py (config 4: fourteen
+forms, five functionals, FENE-P and FENE-P-MP variants).  The EWM journal-bearing loop (config 3) is driven through
+`fenics_b200.drivers.ewm` (fx_form ids directly); its forms can be registered the same way.
 """
 from . import _abi as abi
 from . import symbolic as S
@@ -364,6 +365,123 @@ def _register_cfg5():
     _reg(-Tdx * ds(2), A.FX_FORM_C5_NUS, "Nus (compressible_dgp.py:582-583)")
 
 
+def _register_cfg4():
+    """"flow between eccentrically rotating cylinders"/fenepmp_jbp.py (config 4): theta :391-394, DEVSS :406-416, LPS :473,
+    loop :489-649.  The forms that carry phi_def(u, lambda_d) are registered twice: with lambda_d a `Parameter` (FENE-P-MP,
+    FX_FORM_C4M_* functors, UFL degrees 13 / 13 / 14) and with the plain number 0.0 the CSV default gives (UFL folds
+    phi_def to 1: the FX_FORM_C4_* functors)."""
+    from .shims._common import (DOLFIN_EPS, Dincomp, FdefG, fene_func, fene_sigmacom, magnitude, phi_def, phi_s)
+    from .symbolic import (CellDiameter, Constant, FacetNormal, Identity, Parameter, as_vector, div, dot, ds, dx, grad,
+                           inner, lhs, nabla_grad, rhs)
+    A = abi
+    Re, We, Ma, dt, betav, th, conv, b, A_0, Di, Vh, Bi, T_0, T_h = (
+        Parameter(n_, 1.0) for n_ in ("Re", "We", "Ma", "dt", "betav", "th", "conv", "b_fene", "a0", "Di", "Vh", "Bi", "T0",
+                                      "th_hot"))
+    su_eps = dict(eps=lambda P: 0.0000000001)
+    T_ = TemplateFunction
+    w0, w12, ws, w1 = T_("W", A.FX_F_W0), T_("W", A.FX_F_W12), T_("W", A.FX_F_WS), T_("W", A.FX_F_W1)
+    p0, p1 = T_("Q", A.FX_F_P0), T_("Q", A.FX_F_P1)
+    rho0, rho12, rho1 = T_("Q", A.FX_F_RHO0), T_("Q", A.FX_F_RHO12), T_("Q", A.FX_F_RHO1)
+    T0, T1, thetar = T_("Q", A.FX_F_T0), T_("Q", A.FX_F_T1), T_("Q", -1)
+    tau0_vec, tau1_vec, kapp = T_("Zc", A.FX_F_TAU0), T_("Zc", A.FX_F_TAU1), T_("Qt", A.FX_F_KAPP)
+    h, n = CellDiameter(), FacetNormal()
+    tang = as_vector([n[1], -n[0]])                                             # :182
+    rho = p = T = arguments("Q", 1)
+    q = r = arguments("Q", 0)
+    tau_vec, Rt_vec = arguments("Zc", 1), arguments("Zc", 0)
+    (u, D_vec), (v, R_vec) = arguments("W", 1), arguments("W", 0)
+    D, tau, R, Rt = _sym3(D_vec), _sym3(tau_vec), _sym3(R_vec), _sym3(Rt_vec)
+    (u0, D0_vec), (u12, _), (us, _), (u1, D1_vec) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D1 = _sym3(D0_vec), _sym3(D1_vec)
+    tau0, tau1 = _sym3(S.as_expr(tau0_vec)), _sym3(S.as_expr(tau1_vec))
+    thetal = (T) / (T_h - T_0)                                                  # :391
+    theta0 = (T0 - T_0) / (T_h - T_0)                                           # :394
+    DEVSSl_T1 = (1. - Di) * inner(grad(thetal), grad(r)) * dx                   # :406
+    DEVSSr_T1 = inner((1. - Di) * (grad(thetar) + grad(theta0)), grad(r)) * dx  # :407
+    DEVSSGl_u1 = 2.0 * (1. - betav) * inner(Dincomp(u), Dincomp(v)) * dx        # :415
+    LPSl_stress = inner(kapp * h * 0.05 * grad(tau), grad(Rt)) * dx + inner(kapp * h * 0.01 * div(tau), div(Rt)) * dx  # :473
+    DEVSSGr_u1 = (1. - betav) * inner(D0 + D0.T, Dincomp(v)) * dx               # :495
+    U = 0.5 * (u + u0)                                                          # :496
+    # density half step :499-503 (config 2's statements)
+    rho_weak = inner(2.0 * (rho - rho0) / dt + dot(u0, grad(rho0)) - rho0 * div(u0), q) * dx
+    _reg(lhs(rho_weak), A.FX_FORM_C4_A0, "a0 (fenepmp_jbp.py:502)")
+    _reg(rhs(rho_weak), A.FX_FORM_C4_L0, "L0 (fenepmp_jbp.py:503)")
+    # pressure :536-543
+    lhs_p_1 = (Ma * Ma / (dt)) * p
+    rhs_p_1 = (Ma * Ma / (dt)) * p0 - Re * div(rho0 * us)
+    lhs_p_2 = dt * grad(p)
+    rhs_p_2 = dt * grad(p0)
+    _reg(inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx, A.FX_FORM_C4_A5, "a5 (fenepmp_jbp.py:542)")
+    _reg(inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx, A.FX_FORM_C4_L5, "L5 (fenepmp_jbp.py:543)")
+    # density update :553-562
+    alpha_supg = h / (magnitude(u12) + 0.0000000001)
+    SU_rho = inner(dot(u12, grad(rho)), alpha_supg * dot(u12, grad(q))) * dx
+    rho_weak = inner((rho - rho0) / dt + dot(u12, grad(rho12)) - rho12 * div(u12), q) * dx
+    a6, L6 = lhs(rho_weak), rhs(rho_weak)
+    a6 += SU_rho
+    _reg(a6, A.FX_FORM_C4_A6, "a6 (fenepmp_jbp.py:559,561)", su_eps)
+    _reg(L6, A.FX_FORM_C4_L6, "L6 (fenepmp_jbp.py:560)")
+    # velocity update :573-580
+    lhs_u1 = (Re / dt) * rho1 * u
+    rhs_u1 = (Re / dt) * rho0 * us
+    a7 = inner(lhs_u1, v) * dx + inner(D - grad(u), R) * dx
+    L7 = inner(rhs_u1, v) * dx - 0.5 * inner(grad(p1 - p0), (v)) * dx
+    a7 += th * DEVSSGl_u1
+    L7 += th * DEVSSGr_u1
+    _reg(a7, A.FX_FORM_C4_A7, "a7 (fenepmp_jbp.py:577,579)")
+    _reg(L7, A.FX_FORM_C4_L7, "L7 (fenepmp_jbp.py:578,580)")
+    _reg(0.5 * rho1 * dot(u1, u1) * dx, A.FX_FORM_C4_EK, "E_k (fenepmp_jbp.py:635)")
+    _reg((fene_func(tau1, b) * (tau1[0, 0] + tau1[1, 1]) - 2.) * dx, A.FX_FORM_C4_EE, "E_e (fenepmp_jbp.py:636)")
+    for lambda_d, mp in ((Parameter("lambda_d", 1.0), True), (0.0, False)):
+        ids = (dict(L2=A.FX_FORM_C4M_L2, A4=A.FX_FORM_C4M_A4, L9=A.FX_FORM_C4M_L9, TQ=A.FX_FORM_C4M_TORQUE,
+                    FX=A.FX_FORM_C4M_FORCE_X, FY=A.FX_FORM_C4M_FORCE_Y) if mp else
+               dict(L2=A.FX_FORM_C4_L2, A4=A.FX_FORM_C4_A4, L9=A.FX_FORM_C4_L9, TQ=A.FX_FORM_C4_TORQUE,
+                    FX=A.FX_FORM_C4_FORCE_X, FY=A.FX_FORM_C4_FORCE_Y))
+        tag = " [lambda_D != 0]" if mp else " [lambda_D = 0.0]"
+        # predictor :513-524
+        lhsFus = Re * rho0 * ((u - u0) / dt + conv * dot(u0, nabla_grad(U)))
+        Fus = dot(lhsFus, v) * dx + \
+            + inner(2.0 * betav * phi_s(theta0, A_0) * Dincomp(U), Dincomp(v)) * dx \
+            + (1.0 / 3) * inner(betav * phi_s(theta0, A_0) * div(U), div(v)) * dx \
+            - ((1. - betav) / (We + DOLFIN_EPS)) * inner(
+                div(phi_def(u0, lambda_d) * (fene_func(tau0, b) * tau0 - Identity(len(u)))), v) * dx \
+            + inner(grad(p0), v) * dx \
+            + inner(D - grad(u), R) * dx
+        a2, L2 = lhs(Fus), rhs(Fus)
+        a2 += th * DEVSSGl_u1
+        L2 += th * DEVSSGr_u1
+        _reg(a2, A.FX_FORM_C4_A2, "a2 (fenepmp_jbp.py:521,523)")
+        _reg(L2, ids["L2"], "L2 (fenepmp_jbp.py:522,524)" + tag)
+        # stress :595-606
+        lhs_tau1 = (We / dt) * tau + fene_func(tau0, b) * tau + We * FdefG(u1, D1, tau) \
+            - We * 0.5 * (phi_def(u1, lambda_d) - 1.) * (tau * Dincomp(u1) + Dincomp(u1) * tau)
+        rhs_tau1 = (We / dt) * tau0 + Identity(len(u))
+        Astress = inner(lhs_tau1, Rt) * dx - inner(rhs_tau1, Rt) * dx
+        a4, L4 = lhs(Astress), rhs(Astress)
+        a4 += LPSl_stress
+        L4 += 0
+        _reg(a4, ids["A4"], "a4 (fenepmp_jbp.py:601,604)" + tag)
+        _reg(L4, A.FX_FORM_C4_L4, "L4 (fenepmp_jbp.py:602,605)")
+        # temperature :615-624
+        gamdot = inner(fene_sigmacom(u0, p0, tau0, b, lambda_d, betav, We), grad(u0))
+        lhs_temp1 = (1.0 / dt) * rho1 * thetal + rho1 * dot(u1, grad(thetal))
+        difflhs_temp1 = Di * grad(thetal) + (Di / We) * tau1 * grad(thetal)
+        rhs_temp1 = (1.0 / dt) * rho1 * thetar + rho1 * dot(u1, grad(thetar)) + (1.0 / dt) * rho1 * theta0 + Vh * gamdot
+        diffrhs_temp1 = Di * grad(thetar) + (Di / We) * tau1 * grad(thetar)
+        a9 = inner(lhs_temp1, r) * dx + inner(difflhs_temp1, grad(r)) * dx
+        L9 = inner(rhs_temp1, r) * dx + inner(diffrhs_temp1, grad(r)) * dx - Di * Bi * inner(theta0, r) * ds(1)
+        a9 += 0.0 * th * DEVSSl_T1
+        L9 += 0.0 * th * DEVSSr_T1
+        _reg(a9, A.FX_FORM_C4_A9, "a9 (fenepmp_jbp.py:620,623)")
+        _reg(L9, ids["L9"], "L9 (fenepmp_jbp.py:621,624)" + tag)
+        # journal torque / load :639-649
+        sigma0 = dot(fene_sigmacom(u1, p1, tau1, b, lambda_d, betav, We), tang)
+        omegaf0 = dot(fene_sigmacom(u1, p1, tau1, b, lambda_d, betav, We), n)
+        _reg(inner(Constant((1.0, 0.0)), omegaf0) * ds(0), ids["FX"], "innerforcex (fenepmp_jbp.py:647)" + tag)
+        _reg(inner(Constant((0.0, -1.0)), omegaf0) * ds(0), ids["FY"], "innerforcey (fenepmp_jbp.py:648)" + tag)
+        _reg(-inner(n, sigma0) * ds(0), ids["TQ"], "innertorque (fenepmp_jbp.py:649)" + tag)
+
+
 def _reg(form, fid, what, derived=None):
     _, ctx = form.signature()
     S.register(form, fid, [c.slot for c in ctx.coefs], what, derived)
@@ -376,3 +494,4 @@ def load():
         _register_cfg1()
         _register_cfg2()
         _register_cfg5()
+        _register_cfg4()

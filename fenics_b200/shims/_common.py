@@ -199,6 +199,72 @@ def ldc_sigma(u, p, Tau, We, betav):
     return 2 * betav * Dcomp(u) - p * I + ((1 - betav) / We) * (Tau - I)
 
 
+# ---- "flow between eccentrically rotating cylinders"/fenics_base.py:158-294: operand-aware, shared by the drop-in module and
+# the form registry (so a script's forms and the registered ones are built by the same code) -----------------------------
+def jbp_sigma(u, p, Tau, betav, We):
+    return 2 * betav * Dcomp(u) - p * alg(u).Identity(len(u)) + Tau
+
+
+def jbp_sigmacon(u, p, Tau, betav, We):
+    I = alg(u).Identity(len(u))
+    return 2 * betav * Dcomp(u) - p * I + ((1.0 - betav) / We) * (Tau - I)
+
+
+def _fene_polymer(u, Tau, b, lambda_d, betav, We):
+    I = alg(u).Identity(len(u))
+    return ((1. - betav) / We) * (phi_def(u, lambda_d) * (fene_func(Tau, b) * Tau - I))
+
+
+def fene_sigma(u, p, Tau, b, lambda_d, betav, We):
+    return 2.0 * betav * Dincomp(u) - p * alg(u).Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
+
+
+def fene_sigmacom(u, p, Tau, b, lambda_d, betav, We):
+    return 2.0 * betav * Dcomp(u) - p * alg(u).Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
+
+
+def FdefG(u, G, Tau):
+    """DEVSS-G upper-convected terms with the projected velocity gradient G"""
+    A = alg(u)
+    return A.dot(u, A.grad(Tau)) - A.dot(G, Tau) - A.dot(Tau, _T(G))
+
+
+def Tr(tau):
+    return abs(tau[0, 0] + tau[1, 1])
+
+
+def Trace(tau):
+    return tau[0, 0] + tau[1, 1]
+
+
+def fene_func(tau, b):
+    return 1.0 / (1. - (Tr(tau) - 2.) / (b * b))
+
+
+def phi_s(T, A_0):
+    """solvent thinning 1 - A/(C + T), A = A_0/(k_b (T_h - T_0)), C = T_h/(T_h - T_0) with T_0 = 300, T_h = 350"""
+    T_0, T_h, k_b = 300.0, 350.0, 8.3144598
+    return 1. - (A_0 / (k_b * (T_h - T_0))) * (1. / (T_h / (T_h - T_0) + T))
+
+
+def phi_ewm(tau, T, k, B):
+    return (1. - B * (T / (1. + T))) * ((0.5 * Tr(tau) + 0.00001) ** k)
+
+
+def I_3(A):
+    return A[0, 0] * A[1, 1] - A[1, 0] * A[0, 1]
+
+
+def I_2(A):
+    return 0.5 * (A[0, 0] * A[0, 0] + A[1, 1] * A[1, 1] + 2 * A[1, 0] * A[0, 1])
+
+
+def phi_def(u, lambda_d):
+    D = Dincomp(u)
+    D_u = alg(u).as_matrix([[D[0, 0], D[0, 1]], [D[1, 0], D[1, 1]]])
+    return 1. + (lambda_d * 3 * I_3(D_u) / (I_2(D_u) + 0.0000001)) ** 2
+
+
 def end():
     """dolfin's end() closes a begin()/end() log block (every sub-step of the loops calls it): nothing to close here"""
 

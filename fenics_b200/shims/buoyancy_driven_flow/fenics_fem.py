@@ -13,7 +13,7 @@ from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, D
                        skewcavity, solution_functions, tgrad, trial_functions, update_progress, xskewcavity)
 from fenics_b200.shims._common import Fdef_compressible as Fdefcom  # noqa: F401
 from fenics_b200.shims._common import dgp_sigma as sigma, dgp_sigma_n as sigma_n, dgp_sigmacom as sigmacom  # noqa: F401
-from fenics_b200.symbolic import lhs, rhs, system  # noqa: F401
+from fenics_b200.symbolic import Constant, lhs, rhs, system  # noqa: F401
 from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
                                   dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
 from fenics_b200.dolfin_api import TestFunction, TestFunctions, TrialFunction, TrialFunctions  # noqa: F401

@@ -8,6 +8,13 @@ from fenics_b200 import mesh as _mesh
 from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, assemble, norm, parameters, project,  # noqa: F401
                            solve)
 from fenics_b200.shims._common import end  # noqa: F401
+from fenics_b200.shims._common import (FdefG, I_2, I_3, Tr, Trace, fene_func, fene_sigma, fene_sigmacom, phi_def, phi_ewm,  # noqa: F401
+                                       phi_s)
+from fenics_b200.shims._common import jbp_sigma as sigma, jbp_sigmacon as sigmacon  # noqa: F401
+from fenics_b200.symbolic import Constant, lhs, rhs, system  # noqa: F401
+from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
+                                  dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
+from fenics_b200.dolfin_api import TestFunction, TestFunctions, TrialFunction, TrialFunctions  # noqa: F401
 from fenics_b200.shims._common import (DOLFIN_EPS, Dcomp, Dincomp, _needs_dolfin, _T, absolute, adaptive_refinement, alg,  # noqa: F401
                        chunks, function_spaces, magnitude, max_location, mesh2triang, min_location, mplot,
                        normalize_solution, pi, reshape_elements, set_algebra, solution_functions, tgrad,
@@ -60,58 +67,8 @@ def DinG(D):
     return 0.5 * (D + _T(D))
 
 
-def sigma(u, p, Tau, betav, We):
-    return 2 * betav * Dcomp(u) - p * alg().Identity(len(u)) + Tau
-
-
-def sigmacon(u, p, Tau, betav, We):
-    I = alg().Identity(len(u))
-    return 2 * betav * Dcomp(u) - p * I + ((1.0 - betav) / We) * (Tau - I)
-
-
-def _fene_polymer(u, Tau, b, lambda_d, betav, We):
-    I = alg().Identity(len(u))
-    return ((1. - betav) / We) * (phi_def(u, lambda_d) * (fene_func(Tau, b) * Tau - I))
-
-
-def fene_sigma(u, p, Tau, b, lambda_d, betav, We):
-    return 2.0 * betav * Dincomp(u) - p * alg().Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
-
-
-def fene_sigmacom(u, p, Tau, b, lambda_d, betav, We):
-    return 2.0 * betav * Dcomp(u) - p * alg().Identity(len(u)) + _fene_polymer(u, Tau, b, lambda_d, betav, We)
-
-
-def FdefG(u, G, Tau):
-    """DEVSS-G upper-convected terms with the projected velocity gradient G"""
-    A = alg()
-    return A.dot(u, A.grad(Tau)) - A.dot(G, Tau) - A.dot(Tau, _T(G))
-
-
 def euc_norm(tau):
     return (tau[0] * tau[0] + tau[1] * tau[1] + tau[2] * tau[2]) ** 0.5
-
-
-def Tr(tau):
-    return abs(tau[0, 0] + tau[1, 1])
-
-
-def Trace(tau):
-    return tau[0, 0] + tau[1, 1]
-
-
-def fene_func(tau, b):
-    return 1.0 / (1. - (Tr(tau) - 2.) / (b * b))
-
-
-def phi_s(T, A_0):
-    """solvent thinning 1 - A/(C + T), A = A_0/(k_b (T_h - T_0)), C = T_h/(T_h - T_0) with T_0 = 300, T_h = 350"""
-    T_0, T_h, k_b = 300.0, 350.0, 8.3144598
-    return 1. - (A_0 / (k_b * (T_h - T_0))) * (1. / (T_h / (T_h - T_0) + T))
-
-
-def phi_ewm(tau, T, k, B):
-    return (1. - B * (T / (1. + T))) * ((0.5 * Tr(tau) + 0.00001) ** k)
 
 
 def phi_ewm_inv(tau, T, k, B):
@@ -139,20 +96,6 @@ def frob_norm(tau):
 
 def ernesto_k(u, h, c_a, c_b):
     return c_a * h * magnitude(u) + c_b * h * h * frob_norm(alg().grad(u))
-
-
-def I_3(A):
-    return A[0, 0] * A[1, 1] - A[1, 0] * A[0, 1]
-
-
-def I_2(A):
-    return 0.5 * (A[0, 0] * A[0, 0] + A[1, 1] * A[1, 1] + 2 * A[1, 0] * A[0, 1])
-
-
-def phi_def(u, lambda_d):
-    D = Dincomp(u)
-    D_u = alg().as_matrix([[D[0, 0], D[0, 1]], [D[1, 0], D[1, 1]]])
-    return 1. + (lambda_d * 3 * I_3(D_u) / (I_2(D_u) + 0.0000001)) ** 2
 
 
 def psi_def(phi):

@@ -7,7 +7,7 @@ import numpy as np  # noqa: F401
 from fenics_b200 import mesh as _mesh
 from fenics_b200.dolfin_api import (DirichletBC, Function, KrylovSolver, TestFunction, TestFunctions,  # noqa: F401
                            TrialFunction, TrialFunctions, assemble, norm, parameters, project, solve)
-from fenics_b200.symbolic import lhs, rhs, system  # noqa: F401
+from fenics_b200.symbolic import Constant, lhs, rhs, system  # noqa: F401
 from fenics_b200.symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_matrix, as_vector, div, dot, ds,  # noqa: F401
                                   dx, grad, inner, nabla_grad, outer, sym, tr, transpose)
 from fenics_b200.shims._common import (DGP_structured_mesh, DOLFIN_EPS, Dcomp, Dincomp, LDC_Regular_Mesh, Skew_Mesh,  # noqa: F401

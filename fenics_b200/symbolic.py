@@ -84,6 +84,9 @@ class E:
     def __neg__(self):
         return E("neg", (self,), self.shape)
 
+    def __abs__(self):  # Tr(tau) = abs(tau[0,0] + tau[1,1]) (fenics_base.py:246-247)
+        return E("abs", (self,), self.shape)
+
     def __pos__(self):  # the scripts write `... + \ + inner(...)*dx` (comp_LDC_mesh_convergence.py:432-433)
         return self
 
@@ -235,6 +238,13 @@ def coefficient(fn, comps=None):
         comps = tuple(range(len(sp.comps)))
     comps = tuple(comps)
     return E("coef", (), (len(comps),) if len(comps) > 1 else (), (fn, comps))
+
+
+def Constant(value):
+    """dolfin Constant inside a form: a literal number / vector of numbers (`Constant((1.0, 0.0))`, fenepmp_jbp.py:647)"""
+    if isinstance(value, (tuple, list)):
+        return as_vector([float(v) for v in value])
+    return as_expr(float(value))
 
 
 def CellDiameter(mesh=None):

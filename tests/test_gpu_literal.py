@@ -466,3 +466,118 @@ Tdx = inner(grad(theta1),n)
                       ((ns["tau1"][0, 0]+ns["tau1"][1, 1]-2.0)*ff.dx, abi.FX_FORM_C5_EE), (-ns["Tdx"]*ff.ds(2), abi.FX_FORM_C5_NUS)):
         got, want = ff.assemble(form), dapi.assemble(drv.pr.form(fid))
         assert abs(got - want) <= 1e-12 * max(abs(want), 1e-12), fid
+
+
+CFG4_FORMS = '''
+thetal = (T)/(T_h-T_0)
+theta0 = (T0-T_0)/(T_h-T_0)
+DEVSSl_T1 = (1.-Di)*inner(grad(thetal), grad(r))*dx
+DEVSSr_T1 = inner((1.-Di)*(grad(thetar) + grad(theta0)), grad(r))*dx
+DEVSSGl_u1 = 2.0*(1.-betav)*inner(Dincomp(u),Dincomp(v))*dx
+LPSl_stress = inner(kapp*h*0.05*grad(tau),grad(Rt))*dx + inner(kapp*h*0.01*div(tau),div(Rt))*dx
+DEVSSGr_u1 = (1.-betav)*inner(D0 + D0.T,Dincomp(v))*dx
+U = 0.5*(u + u0)
+rho_eq = 2.0*(rho - rho0)/dt + dot(u0, grad(rho0)) - rho0*div(u0)
+rho_weak = inner(rho_eq,q)*dx
+a0 = lhs(rho_weak)
+L0 = rhs(rho_weak)
+lhsFus = Re*rho0*((u - u0)/dt + conv*dot(u0, nabla_grad(U)))
+Fus = dot(lhsFus, v)*dx + \\
+    + inner(2.0*betav*phi_s(theta0,A_0)*Dincomp(U), Dincomp(v))*dx + (1.0/3)*inner(betav*phi_s(theta0,A_0)*div(U),div(v))*dx \\
+        - ((1.-betav)/(We+DOLFIN_EPS))*inner(div( phi_def(u0, lambda_d)*(fene_func(tau0, b)*tau0 - Identity(len(u)) ) ), v)*dx + inner(grad(p0),v)*dx\\
+    + inner(D-grad(u),R)*dx
+a2= lhs(Fus)
+L2= rhs(Fus)
+a2+= th*DEVSSGl_u1
+L2+= th*DEVSSGr_u1
+lhs_p_1 = (Ma*Ma/(dt))*p
+rhs_p_1 = (Ma*Ma/(dt))*p0 - Re*div(rho0*us)
+lhs_p_2 = dt*grad(p)
+rhs_p_2 = dt*grad(p0)
+a5=inner(lhs_p_1,q)*dx + inner(lhs_p_2,grad(q))*dx
+L5=inner(rhs_p_1,q)*dx + inner(rhs_p_2,grad(q))*dx
+alpha_supg = h/(magnitude(u12)+0.0000000001)
+SU_rho = inner(dot(u12, grad(rho)), alpha_supg*dot(u12,grad(q)))*dx
+rho_eq = (rho - rho0)/dt + dot(u12, grad(rho12)) - rho12*div(u12)
+rho_weak = inner(rho_eq,q)*dx
+a6 = lhs(rho_weak)
+L6 = rhs(rho_weak)
+a6+= SU_rho
+lhs_u1 = (Re/dt)*rho1*u
+rhs_u1 = (Re/dt)*rho0*us
+a7=inner(lhs_u1,v)*dx + inner(D-grad(u),R)*dx
+L7=inner(rhs_u1,v)*dx - 0.5*inner(grad(p1-p0),(v))*dx
+a7+= th*DEVSSGl_u1
+L7+= th*DEVSSGr_u1
+lhs_tau1 = (We/dt)*tau + fene_func(tau0, b)*tau + We*FdefG(u1, D1, tau) - We*0.5*(phi_def(u1, lambda_d)-1.)*(tau*Dincomp(u1) + Dincomp(u1)*tau)
+rhs_tau1= (We/dt)*tau0  + Identity(len(u))
+Astress = inner(lhs_tau1,Rt)*dx - inner(rhs_tau1,Rt)*dx
+a4 = lhs(Astress)
+L4 = rhs(Astress)
+a4 += LPSl_stress
+gamdot = inner(fene_sigmacom(u0, p0, tau0, b, lambda_d, betav, We),grad(u0))
+lhs_temp1 = (1.0/dt)*rho1*thetal + rho1*dot(u1,grad(thetal))
+difflhs_temp1 = Di*grad(thetal) + (Di/We)*tau1*grad(thetal)
+rhs_temp1 = (1.0/dt)*rho1*thetar + rho1*dot(u1,grad(thetar)) + (1.0/dt)*rho1*theta0 + Vh*gamdot
+diffrhs_temp1 = Di*grad(thetar) + (Di/We)*tau1*grad(thetar)
+a9 = inner(lhs_temp1,r)*dx + inner(difflhs_temp1,grad(r))*dx
+L9 = inner(rhs_temp1,r)*dx + inner(diffrhs_temp1,grad(r))*dx - Di*Bi*inner(theta0,r)*ds(1)
+a9+= 0.0*th*DEVSSl_T1
+L9+= 0.0*th*DEVSSr_T1
+E_k = 0.5*rho1*dot(u1,u1)*dx
+E_e = (fene_func(tau1, b)*(tau1[0,0]+tau1[1,1])-2.)*dx
+sigma0 = dot(fene_sigmacom(u1, p1, tau1, b,lambda_d, betav, We), tang)
+omegaf0 = dot(fene_sigmacom(u1, p1, tau1, b,lambda_d, betav, We), n)
+innerforcex = inner(Constant((1.0, 0.0)), omegaf0)*ds(0)
+innerforcey = inner(Constant((0.0, -1.0)), omegaf0)*ds(0)
+innertorque = -inner(n, sigma0)*ds(0)
+'''
+
+
+@pytest.mark.parametrize("lam", [0.1, 0.0])
+def test_literal_config4_forms_equal_the_driver(lam):
+    """fenepmp_jbp.py:489-649: the FENE-P-MP journal-bearing forms written as the script writes them (phi_s, fene_func,
+    phi_def inside a divergence, FdefG, the journal torque / load on ds(0)) assemble to what the driver's fx_form ids
+    give -- with lambda_d a Parameter (lambda_D = 0.1: the C4M functors) and with the plain 0.0 (the folded C4 ones)."""
+    import fenics_b200.shims.eccentric_cylinders.fenics_base as fb
+    from fenics_b200.drivers import jbp
+    drv = jbp.FenepmpJBP(n_theta=32, n_r=6, lambda_d=lam, We=0.5)
+    drv.t = 0.45
+    for _ in range(3):
+        drv.step()
+    ns = {k: getattr(fb, k) for k in dir(fb) if not k.startswith("_")}
+    S, pv = drv.S, drv.p
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    P = fb.Parameter
+    ns.update({k: P(k, pv[k]) for k in ("Re", "We", "Ma", "dt", "betav", "th", "conv", "Di", "Vh", "Bi")})
+    ns.update(T_0=P("T0", pv["T0"]), T_h=P("th_hot", pv["th_hot"]), b=P("b_fene", pv["b_fene"]), A_0=P("a0", pv["a0"]),
+              lambda_d=P("lambda_d", lam) if lam else 0.0)
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = fb.trial_functions(Q, Zc, W)
+    (v, R_vec) = fb.TestFunctions(W)
+    q = fb.TestFunction(Q)
+    n = fb.FacetNormal(drv.mesh)
+    ns.update(Q=Q, p=p, rho=p, T=p, q=q, r=q, u=u, D=D, tau=tau, v=v, R=m3(R_vec), Rt=m3(fb.TestFunction(Zc)),
+              h=fb.CellDiameter(drv.mesh), n=n, tang=fb.as_vector([n[1], -n[0]]))
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "T0", "T1", "tau0_vec", "tau1_vec", "kapp"):
+        ns[name] = getattr(drv, name)
+    thetar = dapi.Function(Q, drv.plan)
+    thetar.vector().t.fill_(pv["T0"] / (pv["th_hot"] - pv["T0"]))
+    ns["thetar"] = thetar
+    (ns["u0"], D0_vec), (ns["u12"], _), (ns["us"], _), (ns["u1"], D1_vec) = (drv.w0.split(), drv.w12.split(), drv.ws.split(),
+                                                                           drv.w1.split())
+    ns.update(D0=m3(D0_vec), D1=m3(D1_vec), tau0=m3(symbolic.as_expr(drv.tau0_vec)), tau1=m3(symbolic.as_expr(drv.tau1_vec)))
+    exec(CFG4_FORMS, ns)
+    A = abi
+    ids = dict(a0=A.FX_FORM_C4_A0, L0=A.FX_FORM_C4_L0, a2=A.FX_FORM_C4_A2, L2=drv.F_L2, a5=A.FX_FORM_C4_A5, L5=A.FX_FORM_C4_L5,
+               a6=A.FX_FORM_C4_A6, L6=A.FX_FORM_C4_L6, a7=A.FX_FORM_C4_A7, L7=A.FX_FORM_C4_L7, a4=drv.F_A4, L4=A.FX_FORM_C4_L4,
+               a9=A.FX_FORM_C4_A9, L9=drv.F_L9)
+    for name, fid in ids.items():
+        got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
+        a, b = (got.val, want.val) if name.startswith("a") else (got.t, want.t)
+        assert lc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-13, name
+        assert float(b.abs().max()) > 0.0, name
+    for name, fid in (("E_k", A.FX_FORM_C4_EK), ("E_e", A.FX_FORM_C4_EE), ("innertorque", drv.F_JOURNAL[0]),
+                      ("innerforcex", drv.F_JOURNAL[1]), ("innerforcey", drv.F_JOURNAL[2])):
+        got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-10), name

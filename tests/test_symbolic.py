@@ -336,3 +336,81 @@ def test_text_of_config5_loop_body_is_recognised():
     assert "eps" in a6[2]                      # DOLFIN_EPS of the SU weight reaches the functor's FX_P_EPS
     L8 = [r for r in rec if r[0] == A.FX_FORM_C5_L8][0]
     assert -1 in L8[1]                         # thetar: a coefficient of the form, a constant inside the functor
+
+
+# ---- config 4: "flow between eccentrically rotating cylinders"/fenepmp_jbp.py ---------------------------------------------------
+REF4 = os.path.join(os.path.dirname(os.path.dirname(REF)), "flow between eccentrically rotating cylinders", "fenepmp_jbp.py")
+
+
+def _namespace4(rec, lambda_d):
+    import fenics_b200.shims.eccentric_cylinders.fenics_base as fb
+    ns = {k: getattr(fb, k) for k in dir(fb) if not k.startswith("_")}
+    P = symbolic.Parameter
+    ns.update(Re=P("Re", 25.0), We=P("We", 0.1), Ma=P("Ma", 0.01), dt=P("dt", 0.00125), betav=P("betav", 0.5), th=P("th", 1.0),
+              conv=P("conv", 1.0), b=P("b_fene", 20.0), A_0=P("a0", 1.0), Di=P("Di", 0.005), Vh=P("Vh", 0.0000069),
+              Bi=P("Bi", 0.2), T_0=P("T0", 300.0), T_h=P("th_hot", 350.0), lambda_d=lambda_d, mesh_refinement=False, j=1,
+              x1=[], ek1=[], ee1=[], y1=[], zx1=[], z1=[], t=0.0)
+    A = abi
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    ns.update(w0=w0, w12=w12, ws=ws, w1=w1, p0=T("Q", A.FX_F_P0), p1=T("Q", A.FX_F_P1), rho0=T("Q", A.FX_F_RHO0),
+              rho12=T("Q", A.FX_F_RHO12), rho1=T("Q", A.FX_F_RHO1), T0=T("Q", A.FX_F_T0), T1=T("Q", A.FX_F_T1),
+              thetar=T("Q", -1), tau0_vec=T("Zc", A.FX_F_TAU0), tau1_vec=T("Zc", A.FX_F_TAU1), kapp=T("Qt", A.FX_F_KAPP),
+              h=symbolic.CellDiameter(), n=symbolic.FacetNormal())
+    ns["tang"] = symbolic.as_vector([ns["n"][1], -ns["n"][0]])
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], Ds_vec), (ns["u1"], D1_vec) = (f.split() for f in (w0, w12, ws, w1))
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = fb.trial_functions("Q", "Zc", "W")
+    ns["rho"] = ns["T"] = ns["p"]
+    ns["q"] = ns["r"] = fb.TestFunction("Q")
+    Rt_vec = fb.TestFunction("Zc")
+    (ns["v"], R_vec) = fb.TestFunctions("W")
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    ns["D0"], ns["D12"] = m3(D0_vec), m3(D12_vec)
+    ns["tau0"], ns["tau1"] = m3(symbolic.as_expr(ns["tau0_vec"])), m3(symbolic.as_expr(ns["tau1_vec"]))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return ("tensor", fid)
+
+    class _BC:
+        def apply(self, *a):
+            pass
+
+    class _Solver:
+        def solve(self, *a):
+            pass
+    ns.update(assemble=assemble, bcu=[_BC()], bcp=[], bctau=[], bcT=[_BC()], solvertau=_Solver(), solve=lambda *a: None)
+    for f in ("w12", "ws", "w1", "p1", "tau1_vec", "rho12", "rho1", "T1"):
+        ns[f].vector = lambda: None
+    return ns
+
+
+@pytest.mark.parametrize("mp", [True, False])
+def test_text_of_config4_loop_body_is_recognised(mp):
+    """fenepmp_jbp.py:489-658 verbatim (seven systems, energies, journal torque / load integrals): every assemble() of
+    the text maps to config 4's functors in the script's order -- FENE-P-MP ids with lambda_d a Parameter, the folded
+    FENE-P ids with the plain 0.0 the CSV default gives"""
+    if not os.path.exists(REF4):
+        pytest.skip("reference checkout not present")
+    rec = []
+    ns = _namespace4(rec, symbolic.Parameter("lambda_d", 0.1) if mp else 0.0)
+    src = open(REF4).read().splitlines()
+    for a, b in ((406, 407), (413, 413), (415, 415), (473, 473)):
+        exec("if True:\n" + "\n".join(src[a - 1:b]) + "\n", ns)
+    exec("if True:\n" + "\n".join(src[488:658]) + "\n", ns)   # ... through the `if j==1:` record block
+    A = abi
+    M = (lambda x, y: x) if mp else (lambda x, y: y)
+    assert [r[0] for r in rec] == [
+        A.FX_FORM_C2_A0, A.FX_FORM_C2_L0,                       # the density half step is config 2's, word for word
+        A.FX_FORM_C4_A2, M(A.FX_FORM_C4M_L2, A.FX_FORM_C4_L2), A.FX_FORM_C4_A5, A.FX_FORM_C4_L5, A.FX_FORM_C4_A6,
+        A.FX_FORM_C5_L6,                                        # ... and L6 is config 5's (one functor, fx::jbp::SU_RHO_L6)
+        A.FX_FORM_C4_A7, A.FX_FORM_C4_L7, M(A.FX_FORM_C4M_A4, A.FX_FORM_C4_A4), A.FX_FORM_C4_L4, A.FX_FORM_C4_A9,
+        M(A.FX_FORM_C4M_L9, A.FX_FORM_C4_L9), A.FX_FORM_C2_EK, A.FX_FORM_C4_EE, M(A.FX_FORM_C4M_TORQUE, A.FX_FORM_C4_TORQUE),
+        M(A.FX_FORM_C4M_FORCE_X, A.FX_FORM_C4_FORCE_X), M(A.FX_FORM_C4M_FORCE_Y, A.FX_FORM_C4_FORCE_Y)]
+    a6 = [r for r in rec if r[0] == A.FX_FORM_C4_A6][0]
+    assert "eps" in a6[2]
+    if mp:
+        assert "lambda_d" in [r for r in rec if r[0] == A.FX_FORM_C4M_L2][0][2]
