@@ -9,8 +9,8 @@ Covered: lid-driven-cavity/incomp_LDC.py (config 1: ten forms, both functionals)
 lid-driven-cavity/comp_LDC_mesh_convergence.py (config 2, the bench configuration: twelve forms through lhs() / rhs(), both
 functionals), its sweep sibling comp_LDC.py, and buoyancy-driven-flow/compressible_dgp.py (config 5: sixteen forms, four
 projections, three functionals) and "flow between eccentrically rotating cylinders"/fenepmp_jbp.py (config 4: fourteen
-forms, five functionals, FENE-P and FENE-P-MP variants).  The EWM journal-bearing loop (config 3) is driven through
-`fenics_b200.drivers.ewm` (fx_form ids directly); its forms can be registered the same way.
+forms, five functionals, FENE-P and FENE-P-MP variants) and incompressible_benchmarkEWM.py (config 3: sixteen forms, five
+functionals, folded and material-function variants).
 """
 from . import _abi as abi
 from . import symbolic as S
@@ -482,6 +482,139 @@ def _register_cfg4():
         _reg(-inner(n, sigma0) * ds(0), ids["TQ"], "innertorque (fenepmp_jbp.py:649)" + tag)
 
 
+def _register_cfg3():
+    """"flow between eccentrically rotating cylinders"/incompressible_benchmarkEWM.py (config 3): theta :398-402, DEVSS
+    :410-422, SU :474-475, loop :488-706.  The forms that carry phi_s(theta0, A_0) / phi_ewm(tau, theta1, k_ewm, B) are
+    registered twice: with A_0, k_ewm, B as `Parameter`s (the FX_FORM_C3E_* functors) and with the plain numbers 0.0 the
+    script sets (:81-84; UFL folds both functions to 1: the FX_FORM_C3_* functors).  The functors keep the temperature
+    DEVSS weight in FX_P_TH_T and the SU epsilon in FX_P_EPS (derived parameters)."""
+    from .shims._common import (DOLFIN_EPS, Dcomp, Dincomp, FdefG, jbp_sigmacon as sigmacon, magnitude, phi_ewm, phi_s)
+    from .symbolic import (CellDiameter, Constant, FacetNormal, Identity, Parameter, as_vector, div, dot, ds, dx, grad,
+                           inner, lhs, nabla_grad, rhs)
+    A = abi
+    Re, We, Ma, dt, betav, th, conv, al, Di, Vh, Bi, T_0, T_h = (
+        Parameter(n_, 1.0) for n_ in ("Re", "We", "Ma", "dt", "betav", "th", "conv", "al1", "Di", "Vh", "Bi", "T0", "th_hot"))
+    su_eps = dict(eps=lambda P: 0.0000000001)
+    th_t = dict(th_t=lambda P: P["th"])
+    T_ = TemplateFunction
+    w0, w12, ws, w1 = T_("W", A.FX_F_W0), T_("W", A.FX_F_W12), T_("W", A.FX_F_WS), T_("W", A.FX_F_W1)
+    p0, p1 = T_("Q", A.FX_F_P0), T_("Q", A.FX_F_P1)
+    rho0, rho12, rho1 = T_("Q", A.FX_F_RHO0), T_("Q", A.FX_F_RHO12), T_("Q", A.FX_F_RHO1)
+    T0, T1, thetar = T_("Q", A.FX_F_T0), T_("Q", A.FX_F_T1), T_("Q", -1)
+    tau0_vec, tau1_vec = T_("Zc", A.FX_F_TAU0), T_("Zc", A.FX_F_TAU1)
+    h, n = CellDiameter(), FacetNormal()
+    tang = as_vector([n[1], -n[0]])                                             # :168
+    rho = p = T = arguments("Q", 1)
+    q = r = arguments("Q", 0)
+    tau_vec, Rt_vec = arguments("Zc", 1), arguments("Zc", 0)
+    (u, D_vec), (v, R_vec) = arguments("W", 1), arguments("W", 0)
+    D, tau, R, Rt = _sym3(D_vec), _sym3(tau_vec), _sym3(R_vec), _sym3(Rt_vec)
+    (u0, D0_vec), (u12, _), (us, _), (u1, D1_vec) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D1 = _sym3(D0_vec), _sym3(D1_vec)
+    tau0, tau1 = _sym3(S.as_expr(tau0_vec)), _sym3(S.as_expr(tau1_vec))
+    thetal = (T) / (T_h - T_0)                                                  # :398
+    theta0 = (T0 - T_0) / (T_h - T_0)                                           # :401
+    theta1 = S.as_expr(T1) - T_0 / (T_h - T_0)                                  # :402, :658 (sic)
+    DEVSSl_u12 = 2 * (1 - betav) * inner(Dcomp(u), Dincomp(v)) * dx             # :410
+    DEVSSr_u12 = 2 * inner(D0, Dincomp(v)) * dx                                 # :411
+    DEVSSl_T1 = (1. - Di) * inner(grad(thetal), grad(r)) * dx                   # :415
+    DEVSSr_T1 = inner((1. - Di) * (grad(thetar) + grad(theta0)), grad(r)) * dx  # :416
+    DEVSSGl_u1 = 2.0 * (1. - betav) * inner(Dincomp(u), Dincomp(v)) * dx        # :422
+    alpha_supg = h / (magnitude(u1) + 0.0000000001)                             # :474
+    SU = inner(dot(u1, grad(tau)), alpha_supg * dot(u1, grad(Rt))) * dx         # :475
+    DEVSSGr_u1 = (1. - betav) * inner(D0 + D0.T, Dincomp(v)) * dx               # :491
+    U = 0.5 * (u + u0)                                                          # :492
+    # density half step :497-503 (config 2's statements)
+    rho_weak = inner(2.0 * (rho - rho0) / dt + dot(u0, grad(rho0)) - rho0 * div(u0), q) * dx
+    _reg(lhs(rho_weak), A.FX_FORM_C3_A0, "a0 (incompressible_benchmarkEWM.py:502)")
+    _reg(rhs(rho_weak), A.FX_FORM_C3_L0, "L0 (incompressible_benchmarkEWM.py:503)")
+    # pressure :586-593
+    lhs_p_1 = (Ma * Ma / (dt)) * p
+    rhs_p_1 = (Ma * Ma / (dt)) * p0 - Re * (1 + al * theta0) * div(rho0 * us)
+    lhs_p_2 = (1 + al * theta0) * dt * grad(p)
+    rhs_p_2 = (1 + al * theta0) * dt * grad(p0)
+    _reg(inner(lhs_p_1, q) * dx + inner(lhs_p_2, grad(q)) * dx, A.FX_FORM_C3_A5, "a5 (incompressible_benchmarkEWM.py:592)")
+    _reg(inner(rhs_p_1, q) * dx + inner(rhs_p_2, grad(q)) * dx, A.FX_FORM_C3_L5, "L5 (incompressible_benchmarkEWM.py:593)")
+    # density update :598-608
+    alpha_supg = h / (magnitude(u12) + 0.0000000001)
+    SU_rho = inner(dot(u12, grad(rho)), alpha_supg * dot(u12, grad(q))) * dx
+    rho_weak = inner((rho - rho0) / dt + dot(u12, grad(rho12)) - rho12 * div(u12), q) * dx
+    a6, L6 = lhs(rho_weak), rhs(rho_weak)
+    a6 += SU_rho
+    _reg(a6, A.FX_FORM_C3_A6, "a6 (incompressible_benchmarkEWM.py:605,607)", su_eps)
+    _reg(L6, A.FX_FORM_C3_L6, "L6 (incompressible_benchmarkEWM.py:606)")
+    # velocity update :617-624 (`a7 += 0`, `L7 += 0`)
+    lhs_u1 = (Re / dt) * rho1 * u
+    rhs_u1 = (Re / dt) * rho0 * us
+    a7 = inner(lhs_u1, v) * dx + inner(D - grad(u), R) * dx
+    L7 = inner(rhs_u1, v) * dx - 0.5 * inner(grad(p1 - p0), (v)) * dx
+    a7 += 0
+    L7 += 0
+    _reg(a7, A.FX_FORM_C3_A7, "a7 (incompressible_benchmarkEWM.py:620)")
+    _reg(L7, A.FX_FORM_C3_L7, "L7 (incompressible_benchmarkEWM.py:621)")
+    # energies, journal torque / load :684-706
+    _reg(0.5 * rho1 * dot(u1, u1) * dx, A.FX_FORM_C3_EK, "E_k (incompressible_benchmarkEWM.py:684)")
+    _reg((tau1_vec[0] + tau1_vec[2] - 2.0) * dx, A.FX_FORM_C3_EE, "E_e (incompressible_benchmarkEWM.py:685)")
+    sigma0 = dot(sigmacon(u1, p1, tau1, betav, We), tang)
+    omegaf0 = dot(sigmacon(u1, p1, tau1, betav, We), n)
+    _reg(inner(Constant((1.0, 0.0)), omegaf0) * ds(0), A.FX_FORM_C3_FORCE_X, "innerforcex (incompressible_benchmarkEWM.py:703)")
+    _reg(-inner(Constant((0.0, 1.0)), omegaf0) * ds(0), A.FX_FORM_C3_FORCE_Y, "innerforcey (incompressible_benchmarkEWM.py:704)")
+    _reg(-inner(n, sigma0) * ds(0), A.FX_FORM_C3_TORQUE, "innertorque (incompressible_benchmarkEWM.py:706)")
+    for (A_0, k_ewm, B), gen in (((Parameter("a0", 1.0), Parameter("k_ewm", 1.0), Parameter("b_ewm", 1.0)), True),
+                                  ((0.0, 0.0, 0.0), False)):
+        ids = (dict(A1=A.FX_FORM_C3E_A1, L1=A.FX_FORM_C3E_L1, L2=A.FX_FORM_C3E_L2, A4=A.FX_FORM_C3E_A4, L4=A.FX_FORM_C3E_L4,
+                    L9=A.FX_FORM_C3E_L9) if gen else
+               dict(A1=A.FX_FORM_C3_A1, L1=A.FX_FORM_C3_L1, L2=A.FX_FORM_C3_L2, A4=A.FX_FORM_C3_A4, L4=A.FX_FORM_C3_L4,
+                    L9=A.FX_FORM_C3_L9))
+        tag = " [material functions]" if gen else " [A_0 = k_ewm = B = 0.0]"
+        # velocity half step :517-531
+        lhsv_eq = 2.0 * Re * ((rho12 * u - rho0 * u0) / dt + conv * dot(u0, nabla_grad(U)))
+        v_weak12 = dot(lhsv_eq, v) * dx + \
+            + inner(2.0 * betav * phi_s(theta0, A_0) * Dincomp(U), Dincomp(v)) * dx \
+            + (1.0 / 3) * inner(betav * phi_s(theta0, A_0) * div(U), div(v)) * dx \
+            - ((1. - betav) / (We + DOLFIN_EPS)) * inner(div(tau0 - rho0 * Identity(len(u))), v) * dx \
+            + inner(grad(p0), v) * dx \
+            + inner(D - grad(u), R) * dx
+        a1, L1 = lhs(v_weak12), rhs(v_weak12)
+        a1 += th * DEVSSl_u12
+        L1 += th * DEVSSr_u12
+        _reg(a1, ids["A1"], "a1 (incompressible_benchmarkEWM.py:527,530)" + tag)
+        _reg(L1, ids["L1"], "L1 (incompressible_benchmarkEWM.py:528,531)" + tag)
+        # predictor :563-575
+        lhsFus = Re * rho0 * ((u - u0) / dt + conv * dot(u0, nabla_grad(U)))
+        Fus = dot(lhsFus, v) * dx + \
+            + inner(2.0 * betav * phi_s(theta0, A_0) * Dincomp(U), Dincomp(v)) * dx \
+            + (1.0 / 3) * inner(betav * phi_s(theta0, A_0) * div(U), div(v)) * dx \
+            - ((1. - betav) / (We + DOLFIN_EPS)) * inner(div(tau0 - rho0 * Identity(len(u))), v) * dx \
+            + inner(grad(p0), v) * dx \
+            + inner(D - grad(u), R) * dx
+        a2, L2 = lhs(Fus), rhs(Fus)
+        a2 += th * DEVSSGl_u1
+        L2 += th * DEVSSGr_u1
+        _reg(a2, A.FX_FORM_C3_A2, "a2 (incompressible_benchmarkEWM.py:571,574)")
+        _reg(L2, ids["L2"], "L2 (incompressible_benchmarkEWM.py:572,575)" + tag)
+        # temperature :641-651
+        gamdot = inner(sigmacon(u0, p0, tau0, betav, We), grad(u0))
+        lhs_temp1 = (1.0 / dt) * rho1 * thetal + rho1 * dot(u1, grad(thetal))
+        difflhs_temp1 = Di * grad(thetal)
+        rhs_temp1 = (1.0 / dt) * rho1 * thetar + rho1 * dot(u1, grad(thetar)) + (1.0 / dt) * rho1 * theta0 \
+            + Vh * phi_ewm(tau1, theta1, k_ewm, B) * gamdot
+        diffrhs_temp1 = Di * grad(thetar)
+        a9 = inner(lhs_temp1, r) * dx + inner(difflhs_temp1, grad(r)) * dx
+        L9 = inner(rhs_temp1, r) * dx + inner(diffrhs_temp1, grad(r)) * dx - Di * Bi * inner(theta0, r) * ds(1)
+        a9 += th * DEVSSl_T1
+        L9 += th * DEVSSr_T1
+        _reg(a9, A.FX_FORM_C3_A9, "a9 (incompressible_benchmarkEWM.py:646,650)", th_t)
+        _reg(L9, ids["L9"], "L9 (incompressible_benchmarkEWM.py:647,651)" + tag, th_t)
+        # stress :663-673
+        lhs_tau1 = (We * phi_ewm(tau0, theta1, k_ewm, B) / dt + 1.0) * tau + We * phi_ewm(tau0, theta1, k_ewm, B) * FdefG(u1, D1, tau)
+        rhs_tau1 = (We * phi_ewm(tau0, theta1, k_ewm, B) / dt) * tau0 + rho0 * Identity(len(u))
+        Ftau = inner(lhs_tau1, Rt) * dx - inner(rhs_tau1, Rt) * dx
+        a4, L4 = lhs(Ftau), rhs(Ftau)
+        _reg(a4 + SU, ids["A4"], "a4_stab = a4 + SU (incompressible_benchmarkEWM.py:668,672)" + tag, su_eps)
+        _reg(L4, ids["L4"], "L4_stab = L4 (incompressible_benchmarkEWM.py:669,673)" + tag)
+
+
 def _reg(form, fid, what, derived=None):
     _, ctx = form.signature()
     S.register(form, fid, [c.slot for c in ctx.coefs], what, derived)
@@ -495,3 +628,4 @@ def load():
         _register_cfg2()
         _register_cfg5()
         _register_cfg4()
+        _register_cfg3()

@@ -581,3 +581,139 @@ def test_literal_config4_forms_equal_the_driver(lam):
                       ("innerforcex", drv.F_JOURNAL[1]), ("innerforcey", drv.F_JOURNAL[2])):
         got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
         assert abs(got - want) <= 1e-12 * max(abs(want), 1e-10), name
+
+
+CFG3_FORMS = '''
+thetal = (T)/(T_h-T_0)
+theta0 = (T0-T_0)/(T_h-T_0)
+theta1 = T1-T_0/(T_h-T_0)
+DEVSSl_u12 = 2*(1-betav)*inner(Dcomp(u),Dincomp(v))*dx
+DEVSSr_u12 = 2*inner(D0,Dincomp(v))*dx
+DEVSSl_T1 = (1.-Di)*inner(grad(thetal), grad(r))*dx
+DEVSSr_T1 = inner((1.-Di)*(grad(thetar) + grad(theta0)), grad(r))*dx
+DEVSSGl_u1 = 2.0*(1.-betav)*inner(Dincomp(u),Dincomp(v))*dx
+alpha_supg = h/(magnitude(u1) + 0.0000000001)
+SU = inner(dot(u1, grad(tau)), alpha_supg*dot(u1,grad(Rt)))*dx
+DEVSSGr_u1 = (1.-betav)*inner(D0 + D0.T,Dincomp(v))*dx
+U = 0.5*(u + u0)
+rho_eq = 2.0*(rho - rho0)/dt + dot(u0, grad(rho0)) - rho0*div(u0)
+rho_weak = inner(rho_eq,q)*dx
+a0 = lhs(rho_weak)
+L0 = rhs(rho_weak)
+lhsv_eq = 2.0*Re*((rho12*u - rho0*u0)/dt + conv*dot(u0, nabla_grad(U)))
+v_weak12 = dot(lhsv_eq, v)*dx + \\
+    + inner(2.0*betav*phi_s(theta0,A_0)*Dincomp(U), Dincomp(v))*dx + (1.0/3)*inner(betav*phi_s(theta0,A_0)*div(U),div(v))*dx \\
+    - ((1.-betav)/(We+DOLFIN_EPS))*inner(div(tau0-rho0*Identity(len(u))), v)*dx + inner(grad(p0),v)*dx\\
+    + inner(D-grad(u),R)*dx
+a1 = lhs(v_weak12)
+L1 = rhs(v_weak12)
+a1+= th*DEVSSl_u12
+L1+= th*DEVSSr_u12
+lhsFus = Re*rho0*((u - u0)/dt + conv*dot(u0, nabla_grad(U)))
+Fus = dot(lhsFus, v)*dx + \\
+    + inner(2.0*betav*phi_s(theta0,A_0)*Dincomp(U), Dincomp(v))*dx + (1.0/3)*inner(betav*phi_s(theta0,A_0)*div(U),div(v))*dx \\
+    - ((1.-betav)/(We+DOLFIN_EPS))*inner(div(tau0-rho0*Identity(len(u))), v)*dx + inner(grad(p0),v)*dx\\
+    + inner(D-grad(u),R)*dx
+a2= lhs(Fus)
+L2= rhs(Fus)
+a2+= th*DEVSSGl_u1
+L2+= th*DEVSSGr_u1
+lhs_p_1 = (Ma*Ma/(dt))*p
+rhs_p_1 = (Ma*Ma/(dt))*p0 - Re*(1+al*theta0)*div(rho0*us)
+lhs_p_2 = (1+al*theta0)*dt*grad(p)
+rhs_p_2 = (1+al*theta0)*dt*grad(p0)
+a5=inner(lhs_p_1,q)*dx + inner(lhs_p_2,grad(q))*dx
+L5=inner(rhs_p_1,q)*dx + inner(rhs_p_2,grad(q))*dx
+alpha_supg = h/(magnitude(u12)+0.0000000001)
+SU_rho = inner(dot(u12, grad(rho)), alpha_supg*dot(u12,grad(q)))*dx
+rho_eq = (rho - rho0)/dt + dot(u12, grad(rho12)) - rho12*div(u12)
+rho_weak = inner(rho_eq,q)*dx
+a6 = lhs(rho_weak)
+L6 = rhs(rho_weak)
+a6+= SU_rho
+lhs_u1 = (Re/dt)*rho1*u
+rhs_u1 = (Re/dt)*rho0*us
+a7=inner(lhs_u1,v)*dx + inner(D-grad(u),R)*dx
+L7=inner(rhs_u1,v)*dx - 0.5*inner(grad(p1-p0),(v))*dx
+a7+= 0
+L7+= 0
+gamdot = inner(sigmacon(u0, p0, tau0, betav, We),grad(u0))
+lhs_temp1 = (1.0/dt)*rho1*thetal + rho1*dot(u1,grad(thetal))
+difflhs_temp1 = Di*grad(thetal)
+rhs_temp1 = (1.0/dt)*rho1*thetar + rho1*dot(u1,grad(thetar)) + (1.0/dt)*rho1*theta0 + Vh*phi_ewm(tau1, theta1, k_ewm, B)*gamdot
+diffrhs_temp1 = Di*grad(thetar)
+a9 = inner(lhs_temp1,r)*dx + inner(difflhs_temp1,grad(r))*dx
+L9 = inner(rhs_temp1,r)*dx + inner(diffrhs_temp1,grad(r))*dx - Di*Bi*inner(theta0,r)*ds(1)
+a9+= th*DEVSSl_T1
+L9+= th*DEVSSr_T1
+lhs_tau1 = (We*phi_ewm(tau0, theta1, k_ewm, B)/dt+1.0)*tau  +  We*phi_ewm(tau0, theta1, k_ewm, B)*FdefG(u1, D1, tau)
+rhs_tau1= (We*phi_ewm(tau0, theta1, k_ewm, B)/dt)*tau0 + rho0*Identity(len(u))
+Ftau = inner(lhs_tau1,Rt)*dx - inner(rhs_tau1,Rt)*dx
+a4 = lhs(Ftau)
+L4 = rhs(Ftau)
+a4_stab = a4 + SU
+L4_stab = L4
+E_k = 0.5*rho1*dot(u1,u1)*dx
+E_e = (tau1_vec[0]+tau1_vec[2]-2.0)*dx
+sigma0 = dot(sigmacon(u1, p1, tau1, betav, We), tang)
+omegaf0 = dot(sigmacon(u1, p1, tau1, betav, We), n)
+innerforcex = inner(Constant((1.0, 0.0)), omegaf0)*ds(0)
+innerforcey = -inner(Constant((0.0, 1.0)), omegaf0)*ds(0)
+innertorque = -inner(n, sigma0)*ds(0)
+'''
+
+
+@pytest.mark.parametrize("general", [True, False])
+def test_literal_config3_forms_equal_the_driver(general):
+    """incompressible_benchmarkEWM.py:488-706: the EWM journal-bearing forms written as the script writes them assemble to
+    what the driver's fx_form ids give -- with A_0, k_ewm, B wrapped as Parameters (material functions active: the C3E
+    functors) and with the script's plain 0.0 (phi_s = phi_ewm = 1: the folded C3 functors)."""
+    import fenics_b200.shims.eccentric_cylinders.fenics_base as fb
+    from fenics_b200.drivers import ewm
+    kw = dict(A_0=0.4, k_ewm=0.7, B=0.2) if general else {}
+    drv = ewm.EwmJBP(n_theta=32, n_r=6, prepass=True, We=0.3, Ma=0.05, betav=0.6, dt=0.002, **kw)
+    drv.t = 0.45
+    for _ in range(3):
+        drv.step()
+    assert drv.ewm == general
+    ns = {k: getattr(fb, k) for k in dir(fb) if not k.startswith("_")}
+    S, pv = drv.S, drv.p
+    W, Zc, Q = S["W"], S["Zc"], S["Q"]
+    P = fb.Parameter
+    ns.update({k: P(k, pv[k]) for k in ("Re", "We", "Ma", "dt", "betav", "th", "conv", "Di", "Vh", "Bi")})
+    ns.update(T_0=P("T0", pv["T0"]), T_h=P("th_hot", pv["th_hot"]), al=P("al1", pv["al1"]),
+              A_0=P("a0", pv["a0"]) if general else 0.0, k_ewm=P("k_ewm", pv["k_ewm"]) if general else 0.0,
+              B=P("b_ewm", pv["b_ewm"]) if general else 0.0)
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, p, _, tau_vec, u, D_vec, D, tau = fb.trial_functions(Q, Zc, W)
+    (v, R_vec) = fb.TestFunctions(W)
+    q = fb.TestFunction(Q)
+    n = fb.FacetNormal(drv.mesh)
+    ns.update(Q=Q, p=p, rho=p, T=p, q=q, r=q, u=u, D=D, tau=tau, v=v, R=m3(R_vec), Rt=m3(fb.TestFunction(Zc)),
+              h=fb.CellDiameter(drv.mesh), n=n, tang=fb.as_vector([n[1], -n[0]]))
+    for name in ("w0", "w12", "ws", "w1", "p0", "p1", "rho0", "rho12", "rho1", "T0", "T1", "tau0_vec", "tau1_vec"):
+        ns[name] = getattr(drv, name)
+    thetar = dapi.Function(Q, drv.plan)
+    thetar.vector().t.fill_(pv["T0"] / (pv["th_hot"] - pv["T0"]))
+    ns["thetar"] = thetar
+    (ns["u0"], D0_vec), (ns["u12"], _), (ns["us"], _), (ns["u1"], D1_vec) = (drv.w0.split(), drv.w12.split(), drv.ws.split(),
+                                                                           drv.w1.split())
+    ns.update(D0=m3(D0_vec), D1=m3(D1_vec), tau0=m3(symbolic.as_expr(drv.tau0_vec)), tau1=m3(symbolic.as_expr(drv.tau1_vec)))
+    exec(CFG3_FORMS, ns)
+    A = abi
+    E = (lambda x, y: x) if general else (lambda x, y: y)
+    ids = dict(a0=A.FX_FORM_C3_A0, L0=A.FX_FORM_C3_L0, a1=E(A.FX_FORM_C3E_A1, A.FX_FORM_C3_A1), L1=E(A.FX_FORM_C3E_L1, A.FX_FORM_C3_L1),
+               a2=A.FX_FORM_C3_A2, L2=E(A.FX_FORM_C3E_L2, A.FX_FORM_C3_L2), a5=A.FX_FORM_C3_A5, L5=A.FX_FORM_C3_L5,
+               a6=A.FX_FORM_C3_A6, L6=A.FX_FORM_C3_L6, a7=A.FX_FORM_C3_A7, L7=A.FX_FORM_C3_L7, a9=A.FX_FORM_C3_A9,
+               L9=E(A.FX_FORM_C3E_L9, A.FX_FORM_C3_L9), a4_stab=E(A.FX_FORM_C3E_A4, A.FX_FORM_C3_A4),
+               L4_stab=E(A.FX_FORM_C3E_L4, A.FX_FORM_C3_L4))
+    for name, fid in ids.items():
+        drv.pr.set_param(A.FX_P_EPS, drv.SU_RHO_EPS if name == "a6" else drv.SU_EPS)
+        got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
+        a, b = (got.val, want.val) if name.startswith("a") else (got.t, want.t)
+        assert lc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-13, name
+        assert float(b.abs().max()) > 0.0, name
+    for name, fid in (("E_k", A.FX_FORM_C3_EK), ("E_e", A.FX_FORM_C3_EE), ("innertorque", A.FX_FORM_C3_TORQUE),
+                      ("innerforcex", A.FX_FORM_C3_FORCE_X), ("innerforcey", A.FX_FORM_C3_FORCE_Y)):
+        got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-10), name

@@ -414,3 +414,57 @@ def test_text_of_config4_loop_body_is_recognised(mp):
     assert "eps" in a6[2]
     if mp:
         assert "lambda_d" in [r for r in rec if r[0] == A.FX_FORM_C4M_L2][0][2]
+
+
+
+def _functor_of():
+    """fx_form id -> functor class (fenics_b200/csrc/fx_registry.h): several configs share statements, hence functors
+    (the registry keeps the first id registered for a signature)"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "fenics_b200", "csrc", "fx_registry.h")).read()
+    return {getattr(abi, name): cls for name, cls in re.findall(r"X\((FX_FORM_\w+),\s*([\w:<>, ]+?)\)", txt) if hasattr(abi, name)}
+
+
+# ---- config 3: incompressible_benchmarkEWM.py --------------------------------------------------------------------------------
+REF3 = os.path.join(os.path.dirname(REF4), "incompressible_benchmarkEWM.py")
+
+
+@pytest.mark.parametrize("general", [True, False])
+def test_text_of_config3_loop_body_is_recognised(general):
+    """incompressible_benchmarkEWM.py:488-706 verbatim (eight systems incl. the stress step behind its `if`, energies,
+    journal torque / load): every assemble() maps to config 3's functors in the script's order -- the C3E ids with A_0,
+    k_ewm, B wrapped as Parameters, the folded C3 ids with the plain 0.0 the script sets (:81-84); the temperature DEVSS
+    weight `th` reaches the functors' FX_P_TH_T, the SU epsilon FX_P_EPS"""
+    if not os.path.exists(REF3):
+        pytest.skip("reference checkout not present")
+    import numpy as np
+    rec = []
+    ns = _namespace4(rec, 0.0)
+    P = symbolic.Parameter
+    ns.update(al=P("al1", 0.001), adaptive_loop=False, err_count=0, max_refine=2, primary_loop=1, np=np,
+              A_0=P("a0", 0.4) if general else 0.0, k_ewm=P("k_ewm", 0.7) if general else 0.0,
+              B=P("b_ewm", 0.2) if general else 0.0, norm=lambda *a: 0.0)
+
+    class _V:
+        def get_local(self):
+            return np.zeros(1)
+    for f in ("w0", "w1", "tau0_vec", "tau1_vec"):
+        ns[f].vector = lambda: _V()
+    src = open(REF3).read().splitlines()
+    for a, b in ((402, 402), (410, 411), (415, 416), (422, 422), (472, 475)):
+        exec("if True:\n" + "\n".join(src[a - 1:b]) + "\n", ns)
+    exec("if True:\n" + "\n".join(src[487:706]) + "\n", ns)
+    A = abi
+    M = (lambda x, y: x) if general else (lambda x, y: y)
+    fo = _functor_of()
+    want = [A.FX_FORM_C3_A0, A.FX_FORM_C3_L0, M(A.FX_FORM_C3E_A1, A.FX_FORM_C3_A1), M(A.FX_FORM_C3E_L1, A.FX_FORM_C3_L1),
+            A.FX_FORM_C3_A2, M(A.FX_FORM_C3E_L2, A.FX_FORM_C3_L2), A.FX_FORM_C3_A5, A.FX_FORM_C3_L5, A.FX_FORM_C3_A6,
+            A.FX_FORM_C3_L6, A.FX_FORM_C3_A7, A.FX_FORM_C3_L7, A.FX_FORM_C3_A9, M(A.FX_FORM_C3E_L9, A.FX_FORM_C3_L9),
+            M(A.FX_FORM_C3E_A4, A.FX_FORM_C3_A4), M(A.FX_FORM_C3E_L4, A.FX_FORM_C3_L4), A.FX_FORM_C3_EK, A.FX_FORM_C3_EE]
+    assert [fo[r[0]] for r in rec] == [fo[i] for i in want]     # the same functors, whichever config's id came first
+    assert "th_t" in rec[12][2] and "th_t" in rec[13][2]
+    assert "eps" in rec[14][2] and "eps" in rec[8][2]
+    # the script assembles the torque / load integrals inside `if primary_loop == 1:` (:711-716)
+    for name, fid in (("innertorque", A.FX_FORM_C3_TORQUE), ("innerforcex", A.FX_FORM_C3_FORCE_X), ("innerforcey", A.FX_FORM_C3_FORCE_Y)):
+        assert fo[symbolic.recognise(ns[name])[0]] == fo[fid]
