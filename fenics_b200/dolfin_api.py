@@ -126,7 +126,8 @@ def _problem_of(plan):
 
 
 def _recognised(form):
-    """symbolic Form -> Form(problem, fx_form id) with the form's own Functions and Parameters bound"""
+    """symbolic Form -> Form(problem, fx_form id) with the form's own Functions and Parameters bound (or DG0Expr(problem,
+    fx_expr id) for the right-hand side of a projection onto a DG0 space)"""
     fid, coefs, params, what, space_objs = symbolic.recognise(form)
     plan = None
     for _, fn in coefs:
@@ -142,6 +143,8 @@ def _recognised(form):
             pr.bind(slot, fn)
     for name, par in params.items():
         pr.set_param(getattr(abi, "FX_P_" + name.upper()), par.value)
+    if isinstance(fid, tuple):
+        return DG0Expr(pr, fid[1])
     return Form(pr, fid)
 
 
@@ -282,8 +285,11 @@ def project(v, V, function=None, rtol=None):
         # the script's own expression (`rho1 = project(rho0 + (Ma*Ma/Re)*(p1-p0), Q)`, comp_LDC_mesh_convergence.py:
         # 501-502): dolfin.project's two forms, recognised like any other literal form
         w, Pv = TestFunction(V), TrialFunction(V)
+        target = _recognised(symbolic.inner(w, v) * symbolic.dx)
+        if isinstance(target, DG0Expr):   # DG0 target (Zd, Qt): diagonal mass matrix, one cell-average kernel
+            return project(target, V, function=function)
         M = assemble(symbolic.inner(w, Pv) * symbolic.dx)
-        rhs = assemble(symbolic.inner(w, v) * symbolic.dx)
+        rhs = assemble(target)
         out = function if function is not None else Function(V, M.plan)
         la.krylov_solve(M, out.vector(), rhs, "cg", "jacobi",
                         rtol=parameters.get("projection_rtol", 1e-13) if rtol is None else rtol)

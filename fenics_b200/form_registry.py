@@ -615,6 +615,51 @@ def _register_cfg3():
         _reg(L4, ids["L4"], "L4_stab = L4 (incompressible_benchmarkEWM.py:669,673)" + tag)
 
 
+def _register_lps():
+    """the LPS indicator block at the top of the loops (incomp_LDC.py:298-308 == comp_LDC_mesh_convergence.py:392-401;
+    compressible_dgp.py:382-390; fenepmp_jbp.py:462-472): four project() calls.  A projection is recognised through the
+    right-hand side dolfin.project assembles, inner(w, expr)*dx -- onto Zd / Qt (DG0) that is one cell-average kernel
+    (("expr", fx_expr id)), onto Zc the consistent mass matrix + the registered right-hand side."""
+    from .shims._common import (Dcomp, Dincomp, Fdef_compressible as Fdefcon, fene_func, phi_def)
+    from .symbolic import Parameter, as_vector, dx, inner
+    A = abi
+    We, dt, betav, b = (Parameter(n_, 1.0) for n_ in ("We", "dt", "betav", "b_fene"))
+    T_ = TemplateFunction
+    w1, tau0_vec, tau1_vec = T_("W", A.FX_F_W1), T_("Zc", A.FX_F_TAU0), T_("Zc", A.FX_F_TAU1)
+    res_test, res_orth, qt_a = T_("Zd", A.FX_F_RES_TEST), T_("Zc", A.FX_F_RES_ORTH), T_("Qt", A.FX_F_QT_A)
+    (u1, _) = w1.split()
+    tau0, tau1 = _sym3(S.as_expr(tau0_vec)), _sym3(S.as_expr(tau1_vec))
+    wd, wc, wq = arguments("Zd", 0), arguments("Zc", 0), arguments("Qt", 0)
+    I_vec = as_vector([1.0, 0.0, 1.0])                    # Expression(('1.0','0.0','1.0'), degree=2)
+
+    def block(restau0, expr_id, orth_id, what):
+        _reg(inner(wd, restau0) * dx, ("expr", expr_id), "project(restau0, Zd) " + what)
+        _reg(inner(wc, restau0 - res_test) * dx, orth_id, "project(restau0-res_test, Zc) " + what)
+    _reg(inner(wc, arguments("Zc", 1)) * dx, A.FX_FORM_MASS_ZC, "project(., Zc): mass matrix")
+    _reg(inner(wq, inner(res_orth, res_orth)) * dx, ("expr", A.FX_EXPR_RES_ORTH_SQ), "project(inner(res_orth,res_orth), Qt)")
+    _reg(inner(wq, S.as_expr(qt_a) ** 0.5) * dx, ("expr", A.FX_EXPR_SQRT_QT_A), "project(np.power(res_orth_norm_sq, 0.5), Qt)")
+    # lid-driven cavity (configs 1, 2): F1R written out with + div(u1)*tau1, deviatoric rate of strain
+    from .symbolic import div, dot, grad
+    from .shims._common import tgrad
+    F1R = dot(u1, grad(tau1)) - dot(grad(u1), tau1) - dot(tau1, tgrad(u1)) + div(u1) * tau1
+    F1R_vec = as_vector([F1R[0, 0], F1R[1, 0], F1R[1, 1]])
+    Dcomp1_vec = as_vector([Dcomp(u1)[0, 0], Dcomp(u1)[1, 0], Dcomp(u1)[1, 1]])
+    block(We / dt * (tau1_vec - tau0_vec) + We * F1R_vec + tau1_vec - 2 * (1 - betav) * Dcomp1_vec,
+          A.FX_EXPR_LDC_RESTAU, A.FX_FORM_LDC_L_RES_ORTH, "(incomp_LDC.py:300-305)")
+    # buoyancy-driven flow (config 5): Fdefcom, - I_vec
+    F1R = Fdefcon(u1, tau1)
+    F1R_vec = as_vector([F1R[0, 0], F1R[1, 0], F1R[1, 1]])
+    block(We / dt * (tau1_vec - tau0_vec) + We * F1R_vec + tau1_vec - I_vec,
+          A.FX_EXPR_C5_RESTAU, A.FX_FORM_C5_L_RES_ORTH, "(compressible_dgp.py:382-387)")
+    # journal bearing (config 4): FENE function and the dissipation term; lambda_d Parameter / plain 0.0 as in _register_cfg4
+    for lambda_d, eid, oid in ((Parameter("lambda_d", 1.0), A.FX_EXPR_C4M_RESTAU, A.FX_FORM_C4M_L_RES_ORTH),
+                               (0.0, A.FX_EXPR_C4_RESTAU, A.FX_FORM_C4_L_RES_ORTH)):
+        dissipation = We * 0.5 * (phi_def(u1, lambda_d) - 1.) * (tau1 * Dincomp(u1) + Dincomp(u1) * tau1)
+        diss_vec = as_vector([dissipation[0, 0], dissipation[1, 0], dissipation[1, 1]])
+        block(We / dt * (tau1_vec - tau0_vec) + We * F1R_vec + fene_func(tau0, b) * tau1_vec - diss_vec - I_vec,
+              eid, oid, "(fenepmp_jbp.py:462-468)")
+
+
 def _reg(form, fid, what, derived=None):
     _, ctx = form.signature()
     S.register(form, fid, [c.slot for c in ctx.coefs], what, derived)
@@ -629,3 +674,4 @@ def load():
         _register_cfg5()
         _register_cfg4()
         _register_cfg3()
+        _register_lps()

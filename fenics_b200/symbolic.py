@@ -87,6 +87,9 @@ class E:
     def __abs__(self):  # Tr(tau) = abs(tau[0,0] + tau[1,1]) (fenics_base.py:246-247)
         return E("abs", (self,), self.shape)
 
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        return _numpy_ufunc(ufunc, method, inputs)
+
     def __pos__(self):  # the scripts write `... + \ + inner(...)*dx` (comp_LDC_mesh_convergence.py:432-433)
         return self
 
@@ -176,11 +179,30 @@ class Parameter(E):
         return self.value >= float(o)
 
 
+def _numpy_ufunc(ufunc, method, inputs):
+    """the scripts apply numpy to UFL objects -- `res_orth_norm = np.power(res_orth_norm_sq, 0.5)` (incomp_LDC.py:307),
+    `np.power(u[0]*u[0]+u[1]*u[1], 0.5)` (magnitude): the same operators, symbolically"""
+    name = getattr(ufunc, "__name__", "")
+    if method == "__call__" and name == "power" and len(inputs) == 2:
+        return as_expr(inputs[0]) ** inputs[1]
+    if method == "__call__" and name in ("absolute", "fabs") and len(inputs) == 1:
+        return abs(as_expr(inputs[0]))
+    if method == "__call__" and name == "sqrt" and len(inputs) == 1:
+        return as_expr(inputs[0]) ** 0.5
+    return NotImplemented
+
+
 class Operand:
     """mixin for Function-like objects: inside a form they behave as their coefficient expression"""
 
     def _sym_expr(self):
         return coefficient(self)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        return _numpy_ufunc(ufunc, method, inputs)
+
+    def __abs__(self):
+        return abs(as_expr(self))
 
     def __add__(self, o):
         return as_expr(self) + o
@@ -484,7 +506,8 @@ def register(form, form_id, slots, what, derived=None):
         raise ValueError("%s: %d coefficients in the form, %d slots given" % (what, len(ctx.coefs), len(slots)))
     # two scripts may write the SAME form (the stress matrix of configs 1 and 2 is one operator, served by one functor
     # under two ids): the first registration stands
-    _REGISTRY.setdefault(sig, (int(form_id), tuple(int(s) for s in slots), what, dict(derived or {})))
+    fid = form_id if isinstance(form_id, tuple) else int(form_id)   # ("expr", id): a DG0 projection kernel (fx_project_dg0)
+    _REGISTRY.setdefault(sig, (fid, tuple(int(s) for s in slots), what, dict(derived or {})))
 
 
 def recognise(form):

@@ -468,3 +468,26 @@ def test_text_of_config3_loop_body_is_recognised(general):
     # the script assembles the torque / load integrals inside `if primary_loop == 1:` (:711-716)
     for name, fid in (("innertorque", A.FX_FORM_C3_TORQUE), ("innerforcex", A.FX_FORM_C3_FORCE_X), ("innerforcey", A.FX_FORM_C3_FORCE_Y)):
         assert fo[symbolic.recognise(ns[name])[0]] == fo[fid]
+
+
+def test_text_of_the_lps_indicator_block_is_recognised():
+    """incomp_LDC.py:298-308 verbatim: four project() calls.  Onto Zd / Qt (DG0) the right-hand side dolfin.project would
+    assemble is recognised as a cell-average kernel (("expr", fx_expr id)); onto Zc as the registered right-hand side next
+    to the consistent mass matrix.  `np.power(res_orth_norm_sq, 0.5)` on a Function is the symbolic power."""
+    import numpy as np
+    rec = []
+    ns = _namespace(rec)
+    out = {"Zd": T("Zd", abi.FX_F_RES_TEST), "Zc": T("Zc", abi.FX_F_RES_ORTH), "Qt": T("Qt", abi.FX_F_QT_A)}
+
+    def project(expr, V):
+        w = form_registry.arguments(V, 0)
+        fid, coefs, params, _, _ = symbolic.recognise(symbolic.inner(w, expr) * symbolic.dx)
+        rec.append((V, fid, [s for s, _ in coefs], sorted(params)))
+        return out[V]
+    ns.update(project=project, Zd="Zd", Zc="Zc", Qt="Qt", np=np)
+    exec(_lines(298, 308), ns)
+    assert rec[0] == ("Zd", ("expr", abi.FX_EXPR_LDC_RESTAU), [abi.FX_F_TAU1, abi.FX_F_TAU0, abi.FX_F_W1],
+                      ["We", "betav", "dt"])
+    assert rec[1][:2] == ("Zc", abi.FX_FORM_LDC_L_RES_ORTH) and abi.FX_F_RES_TEST in rec[1][2]
+    assert rec[2] == ("Qt", ("expr", abi.FX_EXPR_RES_ORTH_SQ), [abi.FX_F_RES_ORTH], [])
+    assert rec[3] == ("Qt", ("expr", abi.FX_EXPR_SQRT_QT_A), [abi.FX_F_QT_A], [])
