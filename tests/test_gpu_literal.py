@@ -717,3 +717,42 @@ def test_literal_config3_forms_equal_the_driver(general):
                       ("innerforcex", A.FX_FORM_C3_FORCE_X), ("innerforcey", A.FX_FORM_C3_FORCE_Y)):
         got, want = fb.assemble(ns[name]), dapi.assemble(drv.pr.form(fid))
         assert abs(got - want) <= 1e-12 * max(abs(want), 1e-10), name
+
+
+def test_literal_lps_indicator_block_equals_the_driver():
+    """incomp_LDC.py:298-308 as the script writes it -- four `project` calls (Zd, Zc, Qt, Qt) and numpy's power on a
+    Function -- against the driver's lps_indicator() from the same state."""
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    from fenics_b200.shims.lid_driven_cavity.fenics_fem import (Dcomp, Parameter, as_vector, div, dot, grad, inner,  # noqa: F401
+                                                                project, tgrad)
+    drv = ldc.IncompLDC(pmesh.Skew_Mesh(12, 1, 1))
+    drv.t = 0.45
+    drv.step()
+    drv.step()
+    S, pv = drv.S, drv.p
+    Zd, Zc, Qt = S["Zd"], S["Zc"], S["Qt"]
+    We, dt, betav = (Parameter(k, pv[k]) for k in ("We", "dt", "betav"))
+    tau0_vec, tau1_vec = drv.tau0_vec, drv.tau1_vec
+    (u1, D1_vec) = drv.w1.split()
+    tau1 = symbolic.as_matrix([[tau1_vec[0], tau1_vec[1]], [tau1_vec[1], tau1_vec[2]]])
+    # ---- incomp_LDC.py:298-308 -------------------------------------------------------------------------
+    F1R = dot(u1,grad(tau1)) - dot(grad(u1),tau1) - dot(tau1,tgrad(u1)) + div(u1)*tau1
+    F1R_vec = as_vector([F1R[0,0], F1R[1,0], F1R[1,1]])
+    Dcomp1_vec = as_vector([Dcomp(u1)[0,0], Dcomp(u1)[1,0], Dcomp(u1)[1,1]])
+    restau0 = We/dt*(tau1_vec-tau0_vec) + We*F1R_vec + tau1_vec - 2*(1-betav)*Dcomp1_vec
+    res_test = project(restau0, Zd)
+    res_orth = project(restau0-res_test, Zc)
+    res_orth_norm_sq = project(inner(res_orth,res_orth), Qt)
+    res_orth_norm = np.power(res_orth_norm_sq, 0.5)
+    kapp = project(res_orth_norm, Qt)
+    # ---- the driver's own indicator (fx_expr ids), bound back to its own Functions ------------------------
+    for slot, fn in ((abi.FX_F_RES_TEST, drv.res_test), (abi.FX_F_RES_ORTH, drv.res_orth),
+                     (abi.FX_F_QT_A, drv.res_orth_norm_sq), (abi.FX_F_TAU0, drv.tau0_vec), (abi.FX_F_TAU1, drv.tau1_vec),
+                     (abi.FX_F_W1, drv.w1)):
+        drv.pr.bind(slot, fn)
+    drv.lps_indicator()
+    assert lc.rel_err(res_test.vector().get_local(), drv.res_test.vector().get_local()) < 1e-13
+    assert lc.rel_err(res_orth.vector().get_local(), drv.res_orth.vector().get_local()) < 1e-9
+    assert lc.rel_err(kapp.vector().get_local(), drv.kapp.vector().get_local()) < 1e-9
+    assert float(np.abs(kapp.vector().get_local()).max()) > 0.0
+    assert ff.project is dapi.project
