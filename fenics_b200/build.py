@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 SO = os.path.join(HERE, "libfenics_b200.so")
-SOURCES = ["fx_asm.cu", "fx_la.cu", "fx_krylov.cu", "fx_capi.cu"]
+SOURCES = ["fx_asm.cu", "fx_la.cu", "fx_krylov.cu", "fx_ilu.cu", "fx_capi.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"] + \
     os.environ.get("FX_NVCC_EXTRA", "").split()  # e.g. FX_NVCC_EXTRA=-DSPMV_INFLIGHT=6 for tuning experiments

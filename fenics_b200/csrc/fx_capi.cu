@@ -186,6 +186,7 @@ void fx_plan_destroy(fx_plan* P) {
   cudaFree(P->nbval); cudaFree(P->elt); cudaFree(P->bf_first); cudaFree(P->bf_next);
   cudaFree(P->cval); cudaFree(P->ccol); cudaFree(P->cre); cudaFree(P->cdesc); cudaFree(P->cprefix); cudaFree(P->scanpart); cudaFree(P->rowpre); cudaFree(P->nblk); cudaFree(P->bar); cudaFree(P->coarse);
   cudaFree(P->gmres_basis); cudaFree(P->red_big);
+  ilu_release(P);
   cudaFree(P->part); cudaFree(P->scal); cudaFree(P->work); cudaFree(P->red); cudaFree(P->info);
   delete P;
 }

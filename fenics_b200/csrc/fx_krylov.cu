@@ -1870,8 +1870,10 @@ int la_krylov(fx_plan* P, int space, const double* val, double* x, const double*
   if (!p.has_csr) return set_error(FX_ERR_ARG, "space %d has no CSR pattern", space);
   if (method != FX_KSP_CG && method != FX_KSP_BICGSTAB && method != FX_KSP_GMRES)
     return set_error(FX_ERR_UNSUPPORTED, "Krylov method %d not implemented (bicgstab, cg, gmres available)", method);
+  if (pc == FX_PC_ILU0)  // PETSc's serial default: natural-ordering ILU(0), dependency-driven kernels (fx_ilu.cu)
+    return la_krylov_ilu0(P, space, val, x, b, method, rtol, atol, maxit, ticket, st);
   if (pc != FX_PC_NONE && pc != FX_PC_JACOBI && pc != FX_PC_JACOBI_COARSE)
-    return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, jacobi_coarse available)", pc);
+    return set_error(FX_ERR_UNSUPPORTED, "preconditioner %d not implemented (none, jacobi, ilu, jacobi_coarse available)", pc);
   PcgConfig pcfg = pcg_resident_config(P, p.nrowblk, p.maxblknnz);
   static const int resident_env = getenv("FX_PCG_RESIDENT") ? atoi(getenv("FX_PCG_RESIDENT")) : 1;
   if (!resident_env) pcfg.R = 0;  // testing aid: send CG solves through k_cg even when the system would fit k_pcg_res

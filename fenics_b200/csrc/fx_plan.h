@@ -148,6 +148,7 @@ struct fx_plan {
   int* bf_next = nullptr;
   double* nbval = nullptr;                      // node-block value buffer (gathered inside every solve), nbval_cap doubles
   size_t nbval_cap = 0;
+  void* ilu = nullptr;                          // FX_PC_ILU0 workspace (fx_ilu.cu: factors, epoch flags, work vectors), built on first use
   fx::DistDev dist;                             // world > 1: mesh-partitioned run (fx_plan_set_peer_regions)
 
   fx::MeshView view() const {
@@ -187,4 +188,8 @@ int nb_ensure(fx_plan* plan, int space);
 int nb_attach_halo(fx_plan* plan, int space);  // builds the node-block layout of a space if possible; FX_OK either way unless CUDA fails
 int la_krylov(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, int pc,
               double rtol, double atol, int maxit, int ticket, cudaStream_t st);
+// fx_ilu.cu: BiCGStab / CG with ILU(0) in the natural ordering (PETSc's serial "default")
+int la_krylov_ilu0(fx_plan* plan, int space, const double* val, double* x, const double* b, int method, double rtol,
+                   double atol, int maxit, int ticket, cudaStream_t st);
+void ilu_release(fx_plan* plan);
 }  // namespace fx

@@ -10,13 +10,16 @@ from ._lib import SolveInfo, check, lib
 
 _KSP = {"bicgstab": abi.FX_KSP_BICGSTAB, "cg": abi.FX_KSP_CG, "gmres": abi.FX_KSP_GMRES}
 _PC = {"none": abi.FX_PC_NONE, "jacobi": abi.FX_PC_JACOBI, "ilu": abi.FX_PC_ILU0, "jacobi_coarse": abi.FX_PC_JACOBI_COARSE}
-# dolfin preconditioner names the library has no kernel for.  They are SUBSTITUTED, never silently: the first use of
-# each name warns (`parameters["preconditioner_substitution"]`: "warn" (default) | "silent" | "error").
+# dolfin preconditioner names that are SUBSTITUTED, never silently: the first use of each name warns
+# (`parameters["preconditioner_substitution"]`: "warn" (default) | "silent" | "error").
 #   "default" (PETSc, serial: ILU(0))  -> "jacobi"        e.g. solve(A, x, b, "bicgstab", "default"), incomp_LDC.py:331
+#                                         or, with parameters["default_preconditioner"] = "ilu", the library's own
+#                                         natural-ordering ILU(0) (csrc/fx_ilu.cu): PETSc's operator and iteration
+#                                         counts, at the price of its serial dependency chain
 #   "amg" / "petsc_amg" / "hypre_amg"  -> "jacobi_coarse" for CG on a space with aggregates (fx_plan_set_aggregates),
 #                                         else "jacobi"   e.g. KrylovSolver("cg", "amg"), fenepmp_jbp.py:437-445
-# Iteration counts therefore differ from PETSc's (CPU study in DESIGN.md section 4: ILU(0) needs 3-5x fewer iterations
-# than Jacobi on the W systems); the stopping rule (left-preconditioned residual, rtol 1e-5) is the same.
+# With the substitutes iteration counts differ from PETSc's (ILU(0) needs 3-5x fewer iterations than Jacobi on the W
+# systems); the stopping rule (left-preconditioned residual, rtol 1e-5) is the same.
 _PC_SUBSTITUTE = {"default": "jacobi", "amg": "jacobi_coarse", "petsc_amg": "jacobi_coarse", "hypre_amg": "jacobi_coarse"}
 _warned = set()
 
@@ -29,6 +32,8 @@ def resolve_pc(pc, method, A):
     """name -> name of a preconditioner the library implements (see _PC_SUBSTITUTE)."""
     if pc in _PC:
         return pc
+    if pc == "default" and parameters.get("default_preconditioner", "jacobi") == "ilu":
+        return "ilu"
     if pc not in _PC_SUBSTITUTE:
         raise ValueError("unknown method/preconditioner %r/%r" % (method, pc))
     to = _PC_SUBSTITUTE[pc]
@@ -40,8 +45,9 @@ def resolve_pc(pc, method, A):
     if mode == "warn" and (pc, to) not in _warned:
         import warnings
         _warned.add((pc, to))
-        warnings.warn("fenics_b200: preconditioner %r is served by %r (no ILU/AMG kernel); iteration counts differ "
-                      "from PETSc's" % (pc, to), PreconditionerSubstitution, stacklevel=3)
+        warnings.warn("fenics_b200: preconditioner %r is served by %r; iteration counts differ from PETSc's%s"
+                      % (pc, to, " (parameters['default_preconditioner'] = 'ilu' selects the ILU(0) kernels)"
+                         if pc == "default" else " (no AMG kernel)"), PreconditionerSubstitution, stacklevel=3)
     return to
 
 
@@ -49,7 +55,7 @@ def resolve_pc(pc, method, A):
 parameters = {"krylov_solver": {"relative_tolerance": 1e-5, "absolute_tolerance": 1e-50,
                                 "maximum_iterations": 10000, "nonzero_initial_guess": True,
                                 "monitor_convergence": False, "error_on_nonconvergence": True},
-              "std_out_all_processes": False, "preconditioner_substitution": "warn"}
+              "std_out_all_processes": False, "preconditioner_substitution": "warn", "default_preconditioner": "jacobi"}
 
 
 def _stream():

@@ -76,7 +76,7 @@ def test_argument_errors_return_codes():
     info = SolveInfo()
     args = (h, abi.SPACE_ID["Q"], la._ptr(A.val), la._ptr(x.t), la._ptr(b.t))
     assert lib.fx_krylov_solve(*args, 7, 1, 1e-5, 1e-50, 10, C.byref(info), la._stream()) == abi.FX_ERR_UNSUPPORTED
-    assert lib.fx_krylov_solve(*args, abi.FX_KSP_CG, abi.FX_PC_ILU0, 1e-5, 1e-50, 10, C.byref(info), la._stream()) \
+    assert lib.fx_krylov_solve(*args, abi.FX_KSP_GMRES, abi.FX_PC_ILU0, 1e-5, 1e-50, 10, C.byref(info), la._stream()) \
         == abi.FX_ERR_UNSUPPORTED and b"not implemented" in lib.fx_last_error()
     assert lib.fx_assemble_matrix(h, 424242, drv.pr.state_ptr(), drv.pr.params_ptr(), la._ptr(A.val), la._stream()) \
         == abi.FX_ERR_ARG
