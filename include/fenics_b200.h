@@ -320,7 +320,9 @@ int fx_plan_set_halo_solver_index(fx_plan* plan, int space, int nsend, const int
 
 /* solve(A, x, b, "bicgstab"|"cg"|"gmres", pc) (incomp_LDC.py:331): one persistent cooperative kernel per
  * solve (gmres: restart 30, classical Gram-Schmidt, PETSc KSPGMRES defaults; single-GPU plans); pc none,
- * jacobi or jacobi_coarse -- FX_PC_ILU0 returns FX_ERR_UNSUPPORTED.  x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
+ * jacobi or jacobi_coarse.  FX_PC_ILU0 (bicgstab, cg; single-GPU plans): PETSc's serial "default", ILU(0) in the
+ * natural ordering, dependency-driven factorisation and triangular solves (csrc/fx_ilu.cu) -- PETSc's iteration
+ * counts at the cost of its serial chain; this variant waits for the solve even through the _async entry.  x holds the initial guess (parameters['krylov_solver']['nonzero_initial_guess']=True,
  * incomp_LDC.py:267).  Convergence: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol) (PETSc default
  * for left preconditioning).  Synchronous: waits for the solve, fills *info (may be NULL) and
  * returns FX_ERR_NOCONV on failure, like dolfin's RuntimeError.                                 */
