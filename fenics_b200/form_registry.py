@@ -615,6 +615,94 @@ def _register_cfg3():
         _reg(L4, ids["L4"], "L4_stab = L4 (incompressible_benchmarkEWM.py:669,673)" + tag)
 
 
+def _register_incomp_dgp():
+    """buoyancy-driven-flow/incompressible_dgp.py: theta :285-288, DEVSS :326-329 (+ :421 inside the loop),
+    loop :369-523.  The script's DOLFIN_EPS in the DEVSS weights is a number in the form and in the functors
+    (fx_forms_dgp.h C6_A12 / C6_L12); its pressure right-hand side carries 1/dt where config 1's carries Re/dt: the shared
+    functor reads FX_P_RE, handed over as the derived parameter re = 1."""
+    from .shims._common import DOLFIN_EPS, Dincomp, Fdef_incompressible as Fdef, dgp_sigma as sigma, dgp_sigma_n as sigma_n
+    from .symbolic import (CellDiameter, FacetNormal, Identity, Parameter, as_vector, div, dot, ds, dx, grad, inner, lhs,
+                           nabla_grad, rhs)
+    A = abi
+    Ra, Pr, We, dt, th, Vh, Bi, c1, c2, T_0, T_h = (
+        Parameter(n_, 1.0) for n_ in ("Ra", "Pr", "We", "dt", "th", "Vh", "Bi", "c1", "c2", "T0", "th_hot"))
+    betav = Parameter("betav", 0.5)          # sigma / sigma_n branch on betav < 1 (fenics_fem.py:69, :75): the polymeric branch
+    T_ = TemplateFunction
+    w0, w12, ws, w1 = T_("W", A.FX_F_W0), T_("W", A.FX_F_W12), T_("W", A.FX_F_WS), T_("W", A.FX_F_W1)
+    p0, p1, T0, T1 = T_("Q", A.FX_F_P0), T_("Q", A.FX_F_P1), T_("Q", A.FX_F_T0), T_("Q", A.FX_F_T1)
+    theta1 = T_("Q", A.FX_F_Q_A)
+    tau0_vec, tau1_vec, kapp = T_("Zc", A.FX_F_TAU0), T_("Zc", A.FX_F_TAU1), T_("Qt", A.FX_F_KAPP)
+    h, n = CellDiameter(), FacetNormal()
+    f = as_vector([0.0, -1.0])                                                  # Expression(('0','-1'), degree=2) :155
+    p = T = arguments("Q", 1)
+    q = r = arguments("Q", 0)
+    tau_vec, Rt_vec = arguments("Zc", 1), arguments("Zc", 0)
+    (u, D_vec), (v, R_vec) = arguments("W", 1), arguments("W", 0)
+    D, tau, R, Rt = _sym3(D_vec), _sym3(tau_vec), _sym3(R_vec), _sym3(Rt_vec)
+    (u0, D0_vec), (u12, D12_vec), (us, _), (u1, _) = w0.split(), w12.split(), ws.split(), w1.split()
+    D0, D12 = _sym3(D0_vec), _sym3(D12_vec)
+    tau0, tau1 = _sym3(S.as_expr(tau0_vec)), _sym3(S.as_expr(tau1_vec))
+    thetal = (T) / (T_h - T_0)                                                  # :285
+    thetar = T_("Q", -1)                                                        # :286-287 project(T_0/(T_h-T_0), Q)
+    theta0 = (T0 - T_0) / (T_h - T_0)                                           # :288 (an expression of T0 here)
+    DEVSSl_u12 = 2 * (1 - betav + DOLFIN_EPS) * inner(Dincomp(u), Dincomp(v)) * dx   # :326
+    DEVSSr_u12 = 2 * inner(D0, Dincomp(v)) * dx                                 # :327
+    DEVSSl_u1 = 2 * (1 - betav + DOLFIN_EPS) * inner(Dincomp(u), Dincomp(v)) * dx    # :328
+    LPSl_stress = inner(kapp * h * c1 * grad(tau), grad(Rt)) * dx + inner(kapp * h * c2 * div(tau), div(Rt)) * dx  # :380
+    U = 0.5 * (u + u0)                                                          # :395
+    # velocity half step :397-408
+    Du12Dt = (2.0 * (u - u0) / dt + dot(u0, nabla_grad(u0)))
+    Fu12 = dot(Du12Dt, v) * dx + \
+        + inner(sigma(U, p0, tau0, We, Pr, betav), Dincomp(v)) * dx + Ra * Pr * inner(theta0 * f, v) * dx \
+        + inner(D - Dincomp(u), R) * dx \
+        - dot(sigma_n(U, p0, tau0, n, We, Pr, betav), v) * ds
+    a1, L1 = lhs(Fu12), rhs(Fu12)
+    a1 += th * DEVSSl_u12
+    L1 += th * DEVSSr_u12
+    _reg(a1, A.FX_FORM_C6_A1, "a1 (incompressible_dgp.py:403,407)")
+    _reg(L1, A.FX_FORM_C6_L1, "L1 (incompressible_dgp.py:404,408)")
+    DEVSSr_u1 = 2 * Pr * (1. - betav + DOLFIN_EPS) * inner(D12, Dincomp(v)) * dx     # :421
+    # predictor :439-450
+    lhsFus = ((u - u0) / dt + dot(u12, nabla_grad(U)))
+    Fus = dot(lhsFus, v) * dx + inner(D - Dincomp(u), R) * dx + \
+        + inner(sigma(U, p0, tau0, We, Pr, betav), Dincomp(v)) * dx + Ra * Pr * inner(theta0 * f, v) * dx \
+        - dot(sigma_n(U, p0, tau0, n, We, Pr, betav), v) * ds
+    a2, L2 = lhs(Fus), rhs(Fus)
+    _reg(a2 + th * DEVSSl_u1, A.FX_FORM_C6_A2, "a2_stab (incompressible_dgp.py:447,449)")
+    _reg(L2 + th * DEVSSr_u1, A.FX_FORM_C6_L2, "L2_stab (incompressible_dgp.py:448,450)")
+    # pressure correction :459-460 (a5 is config 1's Laplacian, word for word)
+    _reg(inner(grad(p), grad(q)) * dx, A.FX_FORM_C6_A5, "a5 (incompressible_dgp.py:459)")
+    _reg(inner(grad(p0), grad(q)) * dx + (1.0 / dt) * inner(us, grad(q)) * dx, A.FX_FORM_C6_L5,
+         "L5 (incompressible_dgp.py:460)", dict(re=lambda P: 1.0))
+    # velocity update :469-472
+    lhs_u1 = (1. / dt) * u
+    rhs_u1 = (1. / dt) * us
+    _reg(inner(lhs_u1, v) * dx + inner(D - Dincomp(u), R) * dx, A.FX_FORM_C6_A7, "a7 (incompressible_dgp.py:471)")
+    _reg(inner(rhs_u1, v) * dx + 0.5 * inner(p1 - p0, div(v)) * dx - 0.5 * dot((p1 - p0) * n, v) * ds, A.FX_FORM_C6_L7,
+         "L7 (incompressible_dgp.py:472)")
+    # stress :487-492
+    stress_eq = (We / dt + 1.0) * tau + We * Fdef(u1, tau) - (We / dt) * tau0 - Identity(len(u))
+    Ast = inner(stress_eq, Rt) * dx
+    a4, L4 = lhs(Ast), rhs(Ast)
+    L4 += 0
+    _reg(a4 + LPSl_stress, A.FX_FORM_C6_A4, "a4_stab (incompressible_dgp.py:489,491)")
+    _reg(L4, A.FX_FORM_C6_L4, "L4 (incompressible_dgp.py:490,492)")
+    # temperature :503-507
+    gamdot = inner(sigma(u1, p1, tau1, We, Pr, betav), grad(u1))
+    lhs_theta1 = (1.0 / dt) * thetal + dot(u1, grad(thetal))
+    rhs_theta1 = (1.0 / dt) * thetar + dot(u1, grad(thetar)) + (1.0 / dt) * theta0 + Vh * gamdot
+    a8 = inner(lhs_theta1, r) * dx + inner(grad(thetal), grad(r)) * dx + inner(We * tau1 * grad(thetal), grad(r)) * dx
+    L8 = inner(rhs_theta1, r) * dx + inner(grad(thetar), grad(r)) * dx + Bi * inner(grad(theta0), n * r) * ds(1) \
+        + Bi * inner(grad(theta0), n * r) * ds(4) + inner(We * tau1 * grad(thetar), grad(r)) * dx
+    _reg(a8, A.FX_FORM_C6_A8, "a8 (incompressible_dgp.py:506)")
+    _reg(L8, A.FX_FORM_C6_L8, "L8 (incompressible_dgp.py:507)")
+    # energies (config 1's E_k, config 5's E_e, word for word), Nusselt number :517-523
+    _reg(0.5 * dot(u1, u1) * dx, A.FX_FORM_C6_EK, "E_k (incompressible_dgp.py:517)")
+    _reg((tau1[0, 0] + tau1[1, 1] - 2.0) * dx, A.FX_FORM_C6_EE, "E_e (incompressible_dgp.py:518)")
+    Tdx = inner(grad(theta1), n)
+    _reg(Tdx * ds(2), A.FX_FORM_C6_NUS, "Nus (incompressible_dgp.py:522-523)")
+
+
 def _register_lps():
     """the LPS indicator block at the top of the loops (incomp_LDC.py:298-308 == comp_LDC_mesh_convergence.py:392-401;
     compressible_dgp.py:382-390; fenepmp_jbp.py:462-472): four project() calls.  A projection is recognised through the
@@ -651,6 +739,12 @@ def _register_lps():
     F1R_vec = as_vector([F1R[0, 0], F1R[1, 0], F1R[1, 1]])
     block(We / dt * (tau1_vec - tau0_vec) + We * F1R_vec + tau1_vec - I_vec,
           A.FX_EXPR_C5_RESTAU, A.FX_FORM_C5_L_RES_ORTH, "(compressible_dgp.py:382-387)")
+    # incompressible double glazing (incompressible_dgp.py:369-378): Fdef without the div(u) term
+    from .shims._common import Fdef_incompressible as Fdef
+    F1R = Fdef(u1, tau1)
+    F1R_vec_i = as_vector([F1R[0, 0], F1R[1, 0], F1R[1, 1]])
+    block(We / dt * (tau1_vec - tau0_vec) + We * F1R_vec_i + tau1_vec - I_vec,
+          A.FX_EXPR_C6_RESTAU, A.FX_FORM_C6_L_RES_ORTH, "(incompressible_dgp.py:369-374)")
     # journal bearing (config 4): FENE function and the dissipation term; lambda_d Parameter / plain 0.0 as in _register_cfg4
     for lambda_d, eid, oid in ((Parameter("lambda_d", 1.0), A.FX_EXPR_C4M_RESTAU, A.FX_FORM_C4M_L_RES_ORTH),
                                (0.0, A.FX_EXPR_C4_RESTAU, A.FX_FORM_C4_L_RES_ORTH)):
@@ -674,4 +768,5 @@ def load():
         _register_cfg5()
         _register_cfg4()
         _register_cfg3()
+        _register_incomp_dgp()
         _register_lps()

@@ -491,3 +491,92 @@ def test_text_of_the_lps_indicator_block_is_recognised():
     assert rec[1][:2] == ("Zc", abi.FX_FORM_LDC_L_RES_ORTH) and abi.FX_F_RES_TEST in rec[1][2]
     assert rec[2] == ("Qt", ("expr", abi.FX_EXPR_RES_ORTH_SQ), [abi.FX_F_RES_ORTH], [])
     assert rec[3] == ("Qt", ("expr", abi.FX_EXPR_SQRT_QT_A), [abi.FX_F_QT_A], [])
+
+
+# ---- buoyancy-driven-flow/incompressible_dgp.py --------------------------------------------------------------
+REF6 = os.path.join(os.path.dirname(os.path.dirname(REF)), "buoyancy-driven-flow", "incompressible_dgp.py")
+
+
+def test_text_of_incompressible_dgp_loop_body_is_recognised():
+    """incompressible_dgp.py:369-523 verbatim (the LPS indicator block with its four projections, six systems, energies,
+    the theta1 projection and the Nusselt number): every assemble() / project() the text issues maps to the functors of
+    drivers/dgp.py:IncompDGP, in the script's order"""
+    if not os.path.exists(REF6):
+        pytest.skip("reference checkout not present")
+    import numpy as np
+    import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
+    rec = []
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    P = symbolic.Parameter
+    ns.update(Ra=P("Ra", 1000.0), Pr=P("Pr", 1.0), We=P("We", 0.1), dt=P("dt", 0.001), betav=P("betav", 0.5), th=P("th", 0.5),
+              Vh=P("Vh", 0.005), Bi=P("Bi", 3e-16), c1=P("c1", 0.05), c2=P("c2", 0.001), T_0=P("T0", 300.0),
+              T_h=P("th_hot", 350.0), np=np, iter=1, Zd="Zd", Zc="Zc", Qt="Qt", Q="Q")
+    A = abi
+    w0, w12, ws, w1 = T("W", A.FX_F_W0), T("W", A.FX_F_W12), T("W", A.FX_F_WS), T("W", A.FX_F_W1)
+    ns.update(w0=w0, w12=w12, ws=ws, w1=w1, p0=T("Q", A.FX_F_P0), p1=T("Q", A.FX_F_P1), T0=T("Q", A.FX_F_T0),
+              T1=T("Q", A.FX_F_T1), thetar=T("Q", -1), tau0_vec=T("Zc", A.FX_F_TAU0), tau1_vec=T("Zc", A.FX_F_TAU1),
+              h=symbolic.CellDiameter(), n=symbolic.FacetNormal(), f=symbolic.as_vector([0.0, -1.0]),
+              I_vec=symbolic.as_vector([1.0, 0.0, 1.0]))
+    (ns["u0"], D0_vec), (ns["u1"], D1_vec), (_, D12_vec) = w0.split(), w1.split(), w12.split()
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
+    ns["T"] = ns["p"]
+    ns["q"] = ns["r"] = ff.TestFunction("Q")
+    Rt_vec = ff.TestFunction("Zc")
+    (ns["v"], R_vec) = ff.TestFunctions("W")
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    ns["D0"], ns["D12"] = m3(D0_vec), m3(D12_vec)
+    ns["tau0"], ns["tau1"] = m3(symbolic.as_expr(ns["tau0_vec"])), m3(symbolic.as_expr(ns["tau1_vec"]))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                       # :285
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])        # :288
+    exec(textwrap.dedent("\n".join(open(REF6).read().splitlines()[325:329])), ns)   # DEVSS :326-329
+    projected = {("expr", A.FX_EXPR_C6_RESTAU): T("Zd", A.FX_F_RES_TEST), A.FX_FORM_C6_L_RES_ORTH: T("Zc", A.FX_F_RES_ORTH),
+                 ("expr", A.FX_EXPR_RES_ORTH_SQ): T("Qt", A.FX_F_QT_A), ("expr", A.FX_EXPR_SQRT_QT_A): T("Qt", A.FX_F_KAPP),
+                 A.FX_FORM_C5_L_THETA0: T("Q", A.FX_F_Q_A)}
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        rec.append((fid, [s for s, _ in coefs], sorted(params)))
+        return ("tensor", fid)
+
+    def project(expr, V):
+        fid = symbolic.recognise(symbolic.inner(form_registry.arguments(V, 0), expr) * symbolic.dx)[0]
+        rec.append(("project", fid))
+        return projected[fid]
+
+    class _BC:
+        def apply(self, *a):
+            pass
+
+    class _Solver:
+        def solve(self, *a):
+            pass
+    ns.update(assemble=assemble, project=project, absolute=lambda k: k, bcu=[_BC()], bcp=[], bctau=[], bcT=[_BC()],
+              solvertau=_Solver(), solve=lambda *a: None)
+    for f in ("w12", "ws", "w1", "p1", "tau1_vec", "T1"):
+        ns[f].vector = lambda: None
+    body = "if True:\n" + "\n".join(open(REF6).read().splitlines()[368:523]) + "\n"
+    exec(body, ns)
+    got = [r[1] if r[0] == "project" else r[0] for r in rec]
+    # statements other scripts write word for word keep their first registration: one functor under two ids, as the
+    # kernel registry (csrc/fx_registry.h) says
+    same = {A.FX_FORM_C1_A5: A.FX_FORM_C6_A5, A.FX_FORM_C1_EK: A.FX_FORM_C6_EK, A.FX_FORM_C5_EE: A.FX_FORM_C6_EE,
+            A.FX_FORM_C1_A4: A.FX_FORM_C6_A4, A.FX_FORM_C5_L4: A.FX_FORM_C6_L4}
+    import re
+    reg = open(os.path.join(os.path.dirname(form_registry.__file__), "csrc", "fx_registry.h")).read()
+    functor = dict(re.findall(r"X\((FX_FORM_\w+),\s*([\w:<>, ]+?)\)", reg))
+    name = {v: k for k, v in abi.ENUM.items() if k.startswith("FX_FORM_")}
+    for a_, b_ in same.items():
+        assert functor[name[a_]] == functor[name[b_]], (name[a_], name[b_])
+    got = [same.get(g, g) for g in got]
+    assert got == [("expr", A.FX_EXPR_C6_RESTAU), A.FX_FORM_C6_L_RES_ORTH, ("expr", A.FX_EXPR_RES_ORTH_SQ),
+                   ("expr", A.FX_EXPR_SQRT_QT_A),
+                   A.FX_FORM_C6_A1, A.FX_FORM_C6_L1, A.FX_FORM_C6_A2, A.FX_FORM_C6_L2, A.FX_FORM_C6_A5, A.FX_FORM_C6_L5,
+                   A.FX_FORM_C6_A7, A.FX_FORM_C6_L7, A.FX_FORM_C6_A4, A.FX_FORM_C6_L4, A.FX_FORM_C6_A8, A.FX_FORM_C6_L8,
+                   A.FX_FORM_C6_EK, A.FX_FORM_C6_EE, A.FX_FORM_C5_L_THETA0, A.FX_FORM_C6_NUS]
+    L5 = [r for r in rec if r[0] == A.FX_FORM_C6_L5][0]
+    assert "re" in L5[2]                       # the shared pressure functor's Re/dt slot is handed 1 (derived parameter)
+    L1 = [r for r in rec if r[0] == A.FX_FORM_C6_L1][0]
+    assert set(L1[1]) == {A.FX_F_W0, A.FX_F_P0, A.FX_F_TAU0, A.FX_F_T0}
+    L8 = [r for r in rec if r[0] == A.FX_FORM_C6_L8][0]
+    assert -1 in L8[1] and A.FX_F_T0 in L8[1] and A.FX_F_P1 in L8[1]
