@@ -560,6 +560,7 @@ def _register_cfg3():
     _reg(inner(Constant((1.0, 0.0)), omegaf0) * ds(0), A.FX_FORM_C3_FORCE_X, "innerforcex (incompressible_benchmarkEWM.py:703)")
     _reg(-inner(Constant((0.0, 1.0)), omegaf0) * ds(0), A.FX_FORM_C3_FORCE_Y, "innerforcey (incompressible_benchmarkEWM.py:704)")
     _reg(-inner(n, sigma0) * ds(0), A.FX_FORM_C3_TORQUE, "innertorque (incompressible_benchmarkEWM.py:706)")
+    _reg(inner(Constant((0.0, -1.0)), omegaf0) * ds(0), A.FX_FORM_C3_FORCE_Y, "innerforcey (comp_ewm_jpb.py:653)")
     for (A_0, k_ewm, B), gen in (((Parameter("a0", 1.0), Parameter("k_ewm", 1.0), Parameter("b_ewm", 1.0)), True),
                                   ((0.0, 0.0, 0.0), False)):
         ids = (dict(A1=A.FX_FORM_C3E_A1, L1=A.FX_FORM_C3E_L1, L2=A.FX_FORM_C3E_L2, A4=A.FX_FORM_C3E_A4, L4=A.FX_FORM_C3E_L4,
@@ -606,6 +607,16 @@ def _register_cfg3():
         L9 += th * DEVSSr_T1
         _reg(a9, A.FX_FORM_C3_A9, "a9 (incompressible_benchmarkEWM.py:646,650)", th_t)
         _reg(L9, ids["L9"], "L9 (incompressible_benchmarkEWM.py:647,651)" + tag, th_t)
+        # comp_ewm_jpb.py:601-605 switches the temperature DEVSS terms off by writing 0.0*th*DEVSSl_T1:
+        # the same functors with the weight FX_P_TH_T = 0.  Every other statement of its loop (:426-659) is written like
+        # incompressible_benchmarkEWM.py's, fenepmp_jbp.py's or compressible_dgp.py's and is registered above.
+        a9 = inner(lhs_temp1, r) * dx + inner(difflhs_temp1, grad(r)) * dx
+        L9 = inner(rhs_temp1, r) * dx + inner(diffrhs_temp1, grad(r)) * dx - Di * Bi * inner(theta0, r) * ds(1)
+        a9 += 0.0 * th * DEVSSl_T1
+        L9 += 0.0 * th * DEVSSr_T1
+        off = dict(th_t=lambda P: 0.0)
+        _reg(a9, A.FX_FORM_C3_A9, "a9 (comp_ewm_jpb.py:601,604)", off)
+        _reg(L9, ids["L9"], "L9 (comp_ewm_jpb.py:602,605)" + tag, off)
         # stress :663-673
         lhs_tau1 = (We * phi_ewm(tau0, theta1, k_ewm, B) / dt + 1.0) * tau + We * phi_ewm(tau0, theta1, k_ewm, B) * FdefG(u1, D1, tau)
         rhs_tau1 = (We * phi_ewm(tau0, theta1, k_ewm, B) / dt) * tau0 + rho0 * Identity(len(u))

@@ -580,3 +580,48 @@ def test_text_of_incompressible_dgp_loop_body_is_recognised():
     assert set(L1[1]) == {A.FX_F_W0, A.FX_F_P0, A.FX_F_TAU0, A.FX_F_T0}
     L8 = [r for r in rec if r[0] == A.FX_FORM_C6_L8][0]
     assert -1 in L8[1] and A.FX_F_T0 in L8[1] and A.FX_F_P1 in L8[1]
+
+
+def test_text_of_comp_ewm_jpb_loop_body_is_recognised():
+    """comp_ewm_jpb.py:426-659 verbatim (the true extended White-Metzner loop): all eight systems, energies and
+    the journal torque / load map to the functors drivers/ewm.py:CompEwmJBP runs -- most statements are written like
+    incompressible_benchmarkEWM.py's; the three that differ: DOLFIN_EPS in the density SU weight (-> FX_P_EPS), the
+    temperature DEVSS terms switched off by `0.0*th*` (-> FX_P_TH_T = 0), innerforcey's sign written into the Constant"""
+    ref = os.path.join(os.path.dirname(REF3), "comp_ewm_jpb.py")
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present")
+    import numpy as np
+    from fenics_b200.shims._common import DOLFIN_EPS
+    rec = []
+    ns = _namespace4(rec, 0.0)
+    P = symbolic.Parameter
+    ns.update(al=P("al1", 0.001), np=np, A_0=P("a0", 120.0), k_ewm=P("k_ewm", -0.7), B=P("b_ewm", 0.1), norm=lambda *a: 0.0,
+              iter=1)
+
+    class _V:
+        def get_local(self):
+            return np.zeros(1)
+    for f in ("w0", "w1", "tau0_vec", "tau1_vec"):
+        ns[f].vector = lambda: _V()
+    src = open(ref).read().splitlines()
+    for a, b in ((368, 368), (376, 377), (381, 382), (386, 389)):   # theta1, DEVSS / DEVSS-G terms of the set-up section
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+    full = []
+
+    def assemble(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        full.append((fid, params))
+        return ("tensor", fid)
+    ns["assemble"] = assemble
+    exec("if True:\n" + "\n".join(src[425:659]) + "\n", ns)
+    A = abi
+    fo = _functor_of()
+    want = [A.FX_FORM_C3_A0, A.FX_FORM_C3_L0, A.FX_FORM_C3E_A1, A.FX_FORM_C3E_L1, A.FX_FORM_C3_A2, A.FX_FORM_C3E_L2,
+            A.FX_FORM_C3_A5, A.FX_FORM_C3_L5, A.FX_FORM_C3_A6, A.FX_FORM_C3_L6, A.FX_FORM_C3_A7, A.FX_FORM_C3_L7,
+            A.FX_FORM_C3_A9, A.FX_FORM_C3E_L9, A.FX_FORM_C3E_A4, A.FX_FORM_C3E_L4, A.FX_FORM_C3_EK, A.FX_FORM_C3_EE]
+    assert [fo[f[0]] for f in full] == [fo[i] for i in want]
+    assert full[8][1]["eps"].value == DOLFIN_EPS                            # a6: alpha_supg = h/(magnitude(u12)+DOLFIN_EPS) :552
+    assert full[12][1]["th_t"].value == 0.0 and full[13][1]["th_t"].value == 0.0   # a9 / L9: 0.0*th*DEVSS*_T1 :604-605
+    assert full[14][1]["eps"].value == 1e-10                                # a4: SU weight h/(magnitude(u1)+0.0000000001) :429
+    for name, fid in (("innertorque", A.FX_FORM_C3_TORQUE), ("innerforcex", A.FX_FORM_C3_FORCE_X), ("innerforcey", A.FX_FORM_C3_FORCE_Y)):
+        assert fo[symbolic.recognise(ns[name])[0]] == fo[fid]
