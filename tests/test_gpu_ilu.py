@@ -82,7 +82,7 @@ def test_default_preconditioner_parameter_and_edge_cases():
         with warnings.catch_warnings():
             warnings.simplefilter("error", la.PreconditionerSubstitution)    # "default" IS ILU(0) now: no substitution
             x.zero()
-            assert la.krylov_solve(A, x, b, "bicgstab", "default").iterations == want
+            assert abs(la.krylov_solve(A, x, b, "bicgstab", "default").iterations - want) <= 1   # (atomic dot products)
     finally:
         la.parameters["default_preconditioner"] = "jacobi"
     # a matrix with a structurally present but zero pivot is reported (status -2), not looped on
