@@ -157,7 +157,7 @@ typedef enum {
 
 typedef struct {
   int iterations;
-  int converged;      /* 1 converged, 0 maxit, -1 breakdown/diverged          */
+  int converged;      /* 1 converged, 0 maxit, -1 breakdown/diverged, -2 ILU(0): missing or zero pivot, -3 singular eliminated block */
   double residual;    /* final (preconditioned) residual 2-norm               */
   double residual0;   /* reference norm the relative tolerance is applied to  */
 } fx_solve_info;
