@@ -497,15 +497,9 @@ def test_text_of_the_lps_indicator_block_is_recognised():
 REF6 = os.path.join(os.path.dirname(os.path.dirname(REF)), "buoyancy-driven-flow", "incompressible_dgp.py")
 
 
-def test_text_of_incompressible_dgp_loop_body_is_recognised():
-    """incompressible_dgp.py:369-523 verbatim (the LPS indicator block with its four projections, six systems, energies,
-    the theta1 projection and the Nusselt number): every assemble() / project() the text issues maps to the functors of
-    drivers/dgp.py:IncompDGP, in the script's order"""
-    if not os.path.exists(REF6):
-        pytest.skip("reference checkout not present")
+def _namespace6(rec):
     import numpy as np
     import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
-    rec = []
     ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
     P = symbolic.Parameter
     ns.update(Ra=P("Ra", 1000.0), Pr=P("Pr", 1.0), We=P("We", 0.1), dt=P("dt", 0.001), betav=P("betav", 0.5), th=P("th", 0.5),
@@ -555,6 +549,19 @@ def test_text_of_incompressible_dgp_loop_body_is_recognised():
               solvertau=_Solver(), solve=lambda *a: None)
     for f in ("w12", "ws", "w1", "p1", "tau1_vec", "T1"):
         ns[f].vector = lambda: None
+    ns["_projected"] = projected
+    return ns
+
+
+def test_text_of_incompressible_dgp_loop_body_is_recognised():
+    """incompressible_dgp.py:369-523 verbatim (the LPS indicator block with its four projections, six systems, energies,
+    the theta1 projection and the Nusselt number): every assemble() / project() the text issues maps to the functors of
+    drivers/dgp.py:IncompDGP, in the script's order"""
+    if not os.path.exists(REF6):
+        pytest.skip("reference checkout not present")
+    rec = []
+    ns = _namespace6(rec)
+    A = abi
     body = "if True:\n" + "\n".join(open(REF6).read().splitlines()[368:523]) + "\n"
     exec(body, ns)
     got = [r[1] if r[0] == "project" else r[0] for r in rec]
