@@ -26,16 +26,20 @@ TOL = 1e-12
 class Translator:
     """symbolic.E tree -> oracle expression; template Functions -> oracle Functions with random data"""
 
-    def __init__(self, spaces, seed=0):
-        self.S, self.rng, self.fn = spaces, np.random.default_rng(seed), {}
+    def __init__(self, spaces, seed=0, by_slot=None):
+        self.S, self.rng, self.fn, self.by_slot = spaces, np.random.default_rng(seed), {}, dict(by_slot or {})
 
     def function(self, tmpl, const=None):
+        """the oracle Function standing behind a template: the randomised field of the oracle config in that slot (value
+        ranges chosen by the config's own test helpers), else random data"""
         if id(tmpl) not in self.fn:
-            sp_ = self.S[tmpl.function_space().name]
-            f = fem.Function(sp_)
-            f.vec[:] = self.rng.standard_normal(sp_.dim)
-            if sp_ is self.S["Qt"]:
-                f.vec[:] = np.abs(f.vec)                      # kappa, |res_orth|^2: non-negative by construction
+            f = self.by_slot.get(getattr(tmpl, "slot", None))
+            if f is None:
+                sp_ = self.S[tmpl.function_space().name]
+                f = fem.Function(sp_)
+                f.vec[:] = self.rng.standard_normal(sp_.dim)
+                if sp_ is self.S["Qt"]:
+                    f.vec[:] = np.abs(f.vec)                  # kappa, |res_orth|^2: non-negative by construction
             if const is not None:
                 f.vec[:] = const
             self.fn[id(tmpl)] = (f, tmpl)
@@ -115,33 +119,18 @@ class Translator:
         return out
 
 
-def test_incompressible_dgp_literal_forms_equal_their_functors_numerically():
-    if not os.path.exists(ts.REF6):
-        pytest.skip("reference checkout not present")
-    mesh = dgp_mesh(5)
-    cfg = IncompDGP(mesh, Ra=700.0, We=0.4, Pr=1.7, betav=0.3, th=0.8, Vh=0.02, Bi=0.3)
-    plan = EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local, mesh.bfacet_marker)
-    rec = []
-    ns = ts._namespace6(rec)
-    P = symbolic.Parameter
-    ns.update(Ra=P("Ra", 700.0), Pr=P("Pr", 1.7), We=P("We", 0.4), dt=P("dt", 0.002), betav=P("betav", 0.3), th=P("th", 0.8),
-              Vh=P("Vh", 0.02), Bi=P("Bi", 0.3), c1=P("c1", 0.07), c2=P("c2", 0.003), T_0=P("T0", 300.0), T_h=P("th_hot", 350.0))
-    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
-    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
-    src = open(ts.REF6).read().splitlines()
-    import textwrap
-    exec(textwrap.dedent("\n".join(src[325:329])), ns)            # DEVSS terms again, with this test's parameters
-    tr = Translator(cfg.S)
-    tr.function(ns["thetar"], const=300.0 / (350.0 - 300.0))      # project(T_0/(T_h-T_0), Q): the constant at every dof
-    for name in ("T0", "T1"):
-        f = tr.function(ns[name])
-        f.vec[:] = 325.0 + 10.0 * f.vec
+
+def _close(ns, tr, plan, projected=None, base_par=None):
+    """install assemble / project that check every form both ways; returns the list of statements checked.  base_par: the
+    parameter table as the run's earlier statements left it (a Problem keeps its parameters between forms: a functor
+    that folds a projected constant -- thetar = T_0/(T_h-T_0) -- reads T_0, T_h although the form no longer names them)"""
     checked = []
 
     def both(form):
         fid, coefs, params, what, _ = symbolic.recognise(form)
         st = {slot: tr.function(t).vec for slot, t in coefs if slot >= 0}
-        par = {getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()}
+        par = dict(base_par or {})
+        par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()})
         spaces = sorted(form.signature()[1].spaces)
         ref = fem.assemble(tr.form(form))
         return fid, st, par, spaces, ref, what
@@ -153,15 +142,17 @@ def test_incompressible_dgp_literal_forms_equal_their_functors_numerically():
         elif np.ndim(ref) == 1:
             err = lc.rel_err(plan.assemble_vector(fid, spaces[0], st, par), ref)
         else:
-            got = plan.assemble_scalar(fid, st, par)
-            err = abs(got - ref) / max(abs(ref), 1e-300)
+            err = abs(plan.assemble_scalar(fid, st, par) - ref) / max(abs(ref), 1e-300)
         assert err < TOL, (what, err)
         checked.append(what)
         return ("tensor", fid)
 
     def project(expr, V):
         w = form_registry.arguments(V, 0)
-        fid, st, par, spaces, ref, what = both(symbolic.inner(w, expr) * symbolic.dx)
+        try:
+            fid, st, par, spaces, ref, what = both(symbolic.inner(w, expr) * symbolic.dx)
+        except symbolic.UnknownForm:                                # compressible_dgp.py:404, dead in the script
+            return None
         if isinstance(fid, tuple):                                  # DG0 target: cell averages, one kernel
             mass = fem.assemble(tr.form(symbolic.inner(w, form_registry.arguments(V, 1)) * symbolic.dx)).diagonal()
             err = lc.rel_err(plan.project_dg0(fid[1], V, st, par), ref / mass)
@@ -169,7 +160,143 @@ def test_incompressible_dgp_literal_forms_equal_their_functors_numerically():
             err = lc.rel_err(plan.assemble_vector(fid, V, st, par), ref)
         assert err < TOL, (what, err)
         checked.append(what)
-        return ns["_projected"][fid]
+        return projected[fid] if projected is not None and fid in projected else tr_result(V, fid)
+
+    def tr_result(V, fid):
+        raise KeyError("project(): no template registered for the result of %r on %s" % (fid, V))
     ns.update(assemble=assemble, project=project)
+    return checked
+
+
+def _params_from(ns, values):
+    """the namespace's Parameters take the oracle config's values (same objects: forms built earlier see them)"""
+    for v in ns.values():
+        if isinstance(v, symbolic.Parameter) and v.name in values:
+            v.value = float(values[v.name])
+
+
+def _plan(mesh, cfg):
+    return EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local, mesh.bfacet_marker)
+
+
+def test_incompressible_dgp_literal_forms_equal_their_functors_numerically():
+    """buoyancy-driven-flow/incompressible_dgp.py:369-523"""
+    if not os.path.exists(ts.REF6):
+        pytest.skip("reference checkout not present")
+    import fxt_dgp as dg
+    mesh = dgp_mesh(5)
+    cfg = IncompDGP(mesh, Ra=700.0, We=0.4, Pr=1.7, betav=0.3, th=0.8, Vh=0.02, Bi=0.3, dt=0.002, c1=0.07, c2=0.003)
+    dg.c6_randomize(cfg)
+    ns = ts._namespace6([])
+    _params_from(ns, cfg.p)
+    tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in dg.C6_FIELD_ATTR.items()})
+    tr.function(ns["thetar"], const=cfg.p["T0"] / (cfg.p["th_hot"] - cfg.p["T0"]))   # project(T_0/(T_h-T_0), Q) :286-287
+    checked = _close(ns, tr, _plan(mesh, cfg), ns["_projected"],
+                     base_par={abi.FX_P_T0: cfg.p["T0"], abi.FX_P_TH_HOT: cfg.p["th_hot"]})
+    src = open(ts.REF6).read().splitlines()
     exec("if True:\n" + "\n".join(src[368:523]) + "\n", ns)
     assert len(checked) == 20, checked
+
+
+def test_config1_literal_forms_equal_their_functors_numerically():
+    """lid-driven-cavity/incomp_LDC.py:298-308 (LPS block), :317-421 (five systems, energies)"""
+    if not os.path.exists(ts.REF):
+        pytest.skip("reference checkout not present")
+    from oracle import configs
+    mesh = fem.skew_mesh(5)
+    cfg = configs.IncompLDC(mesh)
+    lc.randomize(cfg)
+    ns = ts._namespace([])
+    _params_from(ns, cfg.p)
+    T = ts.T
+    tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in lc.FIELD_ATTR.items() if hasattr(cfg, a)})
+    projected = {("expr", abi.FX_EXPR_LDC_RESTAU): T("Zd", abi.FX_F_RES_TEST), abi.FX_FORM_LDC_L_RES_ORTH: T("Zc", abi.FX_F_RES_ORTH),
+                 ("expr", abi.FX_EXPR_RES_ORTH_SQ): T("Qt", abi.FX_F_QT_A), ("expr", abi.FX_EXPR_SQRT_QT_A): T("Qt", abi.FX_F_KAPP)}
+    ns.update(Zd="Zd", Zc="Zc", Qt="Qt", np=np)
+    checked = _close(ns, tr, _plan(mesh, cfg), projected)
+    for a, b in ((298, 308), (317, 331), (355, 363), (370, 375), (379, 394), (400, 416), (420, 421)):
+        exec(ts._lines(a, b), ns)
+    assert len(checked) == 4 + 10 + 2, checked
+
+
+def test_config2_literal_forms_equal_their_functors_numerically():
+    """lid-driven-cavity/comp_LDC_mesh_convergence.py:417-549 (six systems through lhs / rhs, the density projection,
+    energies) and the two momentum steps of the sweep script comp_LDC.py (Re*conv -> the functor's conv slot)"""
+    if not os.path.exists(ts.REF2):
+        pytest.skip("reference checkout not present")
+    from oracle import configs
+    mesh = fem.skew_mesh(5)
+    cfg = configs.CompLDC(mesh)
+    lc.randomize(cfg)
+    ns = ts._namespace2([])
+    _params_from(ns, cfg.p)
+    by_slot = {slot: getattr(cfg, a) for slot, a in lc.FIELD_ATTR.items() if hasattr(cfg, a)}
+    tr = Translator(cfg.S, by_slot=by_slot)
+    projected = {abi.FX_FORM_C2_L_RHO1: ts.T("Q", abi.FX_F_RHO1)}
+    ns.update(Q="Q")
+    checked = _close(ns, tr, _plan(mesh, cfg), projected)
+    for a, b in ((417, 426), (430, 447), (458, 476), (483, 497), (501, 502), (506, 519), (528, 544), (548, 549)):
+        exec(ts._lines2(a, b), ns)
+    assert len(checked) == 12 + 1 + 2, checked
+    ref3 = os.path.join(os.path.dirname(ts.REF), "comp_LDC.py")
+    src = open(ref3).read().splitlines()
+    import textwrap
+    for a, b in ((418, 441), (468, 489)):
+        ns = ts._namespace2([])
+        _params_from(ns, dict(cfg.p, Re=25.0, conv=0.5))
+        checked = _close(ns, Translator(cfg.S, by_slot=by_slot), _plan(mesh, cfg))
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+        assert len(checked) == 2, checked
+
+
+def test_config5_literal_forms_equal_their_functors_numerically():
+    """buoyancy-driven-flow/compressible_dgp.py:404-583"""
+    if not os.path.exists(ts.REF5):
+        pytest.skip("reference checkout not present")
+    import fxt_dgp as dg
+    from oracle.configs_dgp import CompDGP
+    mesh = dgp_mesh(5)
+    cfg = CompDGP(mesh)
+    dg.randomize(cfg)
+    ns = ts._namespace5([])
+    _params_from(ns, cfg.p)
+    A = abi
+    tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in dg.FIELD_ATTR.items()})
+    tr.function(ns["thetar"], const=cfg.p["T0"] / (cfg.p["th_hot"] - cfg.p["T0"]))
+    projected = {A.FX_FORM_C5_L_THETA0: ts.T("Q", A.FX_F_THETA0), A.FX_FORM_C5_L_THERM_INV: ts.T("Q", A.FX_F_THERM_INV),
+                 A.FX_FORM_C5_L_RHO1: ts.T("Q", A.FX_F_RHO1)}
+    calls = {"n": 0}
+    first = projected[A.FX_FORM_C5_L_THETA0]
+
+    class _Proj(dict):                     # :581 projects theta1 with theta0's functor: its result feeds the Nusselt integral
+        def __getitem__(self, fid):
+            if fid == A.FX_FORM_C5_L_THETA0:
+                calls["n"] += 1
+                return first if calls["n"] == 1 else ts.T("Q", A.FX_F_Q_A)
+            return dict.__getitem__(self, fid)
+    checked = _close(ns, tr, _plan(mesh, cfg), _Proj(projected),
+                     base_par={A.FX_P_T0: cfg.p["T0"], A.FX_P_TH_HOT: cfg.p["th_hot"]})
+    exec("if True:\n" + "\n".join(open(ts.REF5).read().splitlines()[403:583]) + "\n", ns)
+    assert len(checked) == 16 + 4 + 3, checked
+
+
+@pytest.mark.parametrize("mp", [True, False])
+def test_config4_literal_forms_equal_their_functors_numerically(mp):
+    """"flow between eccentrically rotating cylinders"/fenepmp_jbp.py:489-658, FENE-P-MP (lambda_d = 0.1) and FENE-P"""
+    if not os.path.exists(ts.REF4):
+        pytest.skip("reference checkout not present")
+    import fxt_jbp as jb
+    from oracle.configs_jbp import FenepmpJBP
+    mesh = fem.annulus_mesh(12, 3)
+    cfg = FenepmpJBP(mesh, lambda_d=0.1 if mp else 0.0)
+    jb.randomize(cfg)
+    ns = ts._namespace4([], symbolic.Parameter("lambda_d", 0.1) if mp else 0.0)
+    _params_from(ns, cfg.p)
+    tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in jb.FIELD_ATTR.items()})
+    tr.function(ns["thetar"], const=cfg.p["T0"] / (cfg.p["th_hot"] - cfg.p["T0"]))
+    checked = _close(ns, tr, _plan(mesh, cfg), base_par={abi.FX_P_T0: cfg.p["T0"], abi.FX_P_TH_HOT: cfg.p["th_hot"]})
+    src = open(ts.REF4).read().splitlines()
+    for a, b in ((406, 407), (413, 413), (415, 415), (473, 473)):
+        exec("if True:\n" + "\n".join(src[a - 1:b]) + "\n", ns)
+    exec("if True:\n" + "\n".join(src[488:658]) + "\n", ns)
+    assert len(checked) == 19, checked
