@@ -300,3 +300,68 @@ def test_config4_literal_forms_equal_their_functors_numerically(mp):
         exec("if True:\n" + "\n".join(src[a - 1:b]) + "\n", ns)
     exec("if True:\n" + "\n".join(src[488:658]) + "\n", ns)
     assert len(checked) == 19, checked
+
+
+def _run_ewm(ref, cfg, mesh, ns, setup_ranges, body, n_expected):
+    import fxt_jbp as jb
+    _params_from(ns, cfg.p)
+    tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in jb.FIELD_ATTR.items() if hasattr(cfg, a)})
+    tr.function(ns["thetar"], const=cfg.p["T0"] / (cfg.p["th_hot"] - cfg.p["T0"]))
+    checked = _close(ns, tr, _plan(mesh, cfg), base_par={abi.FX_P_T0: cfg.p["T0"], abi.FX_P_TH_HOT: cfg.p["th_hot"]})
+    src = open(ref).read().splitlines()
+    import textwrap
+    for a, b in setup_ranges:
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+    exec("if True:\n" + "\n".join(src[body[0]:body[1]]) + "\n", ns)
+    for name in ("innertorque", "innerforcex", "innerforcey"):      # assembled behind the scripts' record blocks
+        ns["assemble"](ns[name])
+    assert len(checked) == n_expected, checked
+
+
+@pytest.mark.parametrize("general", [True, False])
+def test_config3_literal_forms_equal_their_functors_numerically(general):
+    """incompressible_benchmarkEWM.py:488-706 with the material functions as Parameters (C3E functors) and with the script's
+    plain 0.0 (folded C3 functors)"""
+    if not os.path.exists(ts.REF3):
+        pytest.skip("reference checkout not present")
+    import fxt_ewm as ew
+    from oracle.configs_ewm import EwmJBP
+    mesh = fem.annulus_mesh(12, 3, x_1=-0.9)
+    kw = dict(ew.GENERAL, A_0=0.4, k_ewm=0.7, B=0.2) if general else dict(ew.GENERAL)
+    cfg = EwmJBP(mesh, **kw)
+    ew.randomize(cfg)
+    ns = ts._namespace4([], 0.0)
+    P = symbolic.Parameter
+    ns.update(al=P("al1", 0.001), adaptive_loop=False, err_count=0, max_refine=2, primary_loop=1, np=np,
+              A_0=P("a0", 0.4) if general else 0.0, k_ewm=P("k_ewm", 0.7) if general else 0.0,
+              B=P("b_ewm", 0.2) if general else 0.0, norm=lambda *a: 0.0)
+
+    class _V:
+        def get_local(self):
+            return np.zeros(1)
+    for f in ("w0", "w1", "tau0_vec", "tau1_vec"):
+        ns[f].vector = lambda: _V()
+    _run_ewm(ts.REF3, cfg, mesh, ns, ((402, 402), (410, 411), (415, 416), (422, 422), (472, 475)), (487, 706), 18 + 3)
+
+
+def test_comp_ewm_jpb_literal_forms_equal_their_functors_numerically():
+    """comp_ewm_jpb.py:426-659: the true extended White-Metzner loop"""
+    ref = os.path.join(os.path.dirname(ts.REF3), "comp_ewm_jpb.py")
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present")
+    import fxt_ewm as ew
+    from oracle.configs_ewm import CompEwmJBP
+    mesh = fem.annulus_mesh(12, 3, x_1=-0.8)
+    cfg = CompEwmJBP(mesh, **{k: v for k, v in ew.EWM_GENERAL.items()})
+    ew.randomize(cfg)
+    ns = ts._namespace4([], 0.0)
+    P = symbolic.Parameter
+    ns.update(al=P("al1", 0.001), np=np, A_0=P("a0", 120.0), k_ewm=P("k_ewm", -0.7), B=P("b_ewm", 0.1), norm=lambda *a: 0.0,
+              iter=1)
+
+    class _V:
+        def get_local(self):
+            return np.zeros(1)
+    for f in ("w0", "w1", "tau0_vec", "tau1_vec"):
+        ns[f].vector = lambda: _V()
+    _run_ewm(ref, cfg, mesh, ns, ((368, 368), (376, 377), (381, 382), (386, 389)), (425, 659), 18 + 3)
