@@ -2,9 +2,10 @@
 drop-in names; every form it hands to `assemble` / `project` is (i) recognised -> fx_form id, field slots, parameters
 (fenics_b200/symbolic.py, form_registry.py) and assembled by that functor through the host emulation of the CUDA element
 kernels (tests/hostemu: the same csrc headers), and (ii) translated node by node into the oracle's UFL restatement
-(oracle/ufl_lite.py) and assembled there on the same random data.  Equal to 1e-12: the structure the registry keys on
-really is the operator the hand-written functor computes -- for buoyancy-driven-flow/incompressible_dgp.py:369-523
-(SURVEY.md 8f.2), whose literal path has no GPU comparison of its own."""
+(oracle/ufl_lite.py) and assembled there on the same random data.  Equal to 1e-12, and the functor's quadrature degrees
+equal UFL's estimate for the script's form: the structure the registry keys on really is the operator the hand-written
+functor computes.  All eight scripts: configs 1-5, comp_LDC.py, comp_ewm_jpb.py, incompressible_dgp.py (the last two have
+no GPU comparison of their literal path of their own)."""
 import os
 
 import numpy as np
@@ -132,7 +133,15 @@ def _close(ns, tr, plan, projected=None, base_par=None):
         par = dict(base_par or {})
         par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()})
         spaces = sorted(form.signature()[1].spaces)
-        ref = fem.assemble(tr.form(form))
+        oform = tr.form(form)
+        ref = fem.assemble(oform)
+        if not isinstance(fid, tuple):          # ... integrated with the rule UFL's degree estimation gives the script's form
+            degs = {}
+            for k, _, d in fem.quadrature_degrees(oform, plan.mesh):
+                degs[k] = max(degs.get(k, -1), d)
+            q = plan.form_qdeg(fid, par.get(abi.FX_P_CONV, 1.0))
+            assert q[0] == degs.get("dx", -1) or "dx" not in degs, (what, q, degs)
+            assert q[1] == degs.get("ds", -1) or "ds" not in degs, (what, q, degs)
         return fid, st, par, spaces, ref, what
 
     def assemble(form):
@@ -176,7 +185,9 @@ def _params_from(ns, values):
 
 
 def _plan(mesh, cfg):
-    return EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local, mesh.bfacet_marker)
+    plan = EmuPlan(mesh.coords, mesh.cells, lc.dofmaps_of(cfg), mesh.bfacet_cell, mesh.bfacet_local, mesh.bfacet_marker)
+    plan.mesh = mesh
+    return plan
 
 
 def test_incompressible_dgp_literal_forms_equal_their_functors_numerically():
