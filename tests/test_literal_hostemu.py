@@ -22,6 +22,7 @@ from oracle import ufl_lite as ufl
 from oracle.configs_dgp import IncompDGP, dgp_mesh
 
 TOL = 1e-12
+_HIT = set()      # registry signatures the tests of this module have closed numerically (see the last test)
 
 
 class Translator:
@@ -129,6 +130,7 @@ def _close(ns, tr, plan, projected=None, base_par=None):
 
     def both(form):
         fid, coefs, params, what, _ = symbolic.recognise(form)
+        _HIT.add(form.signature()[0])
         st = {slot: tr.function(t).vec for slot, t in coefs if slot >= 0}
         par = dict(base_par or {})
         par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()})
@@ -167,6 +169,9 @@ def _close(ns, tr, plan, projected=None, base_par=None):
             err = lc.rel_err(plan.project_dg0(fid[1], V, st, par), ref / mass)
         else:
             err = lc.rel_err(plan.assemble_vector(fid, V, st, par), ref)
+            # ... next to the consistent mass matrix dolfin.project assembles (dolfin_api.project: recognised like any form)
+            mid, _, mpar, _, mref, mwhat = both(symbolic.inner(w, form_registry.arguments(V, 1)) * symbolic.dx)
+            assert lc.csr_rel_err(plan.assemble_matrix(mid, V, {}, mpar), mref) < TOL, mwhat
         assert err < TOL, (what, err)
         checked.append(what)
         return projected[fid] if projected is not None and fid in projected else tr_result(V, fid)
@@ -175,6 +180,13 @@ def _close(ns, tr, plan, projected=None, base_par=None):
         raise KeyError("project(): no template registered for the result of %r on %s" % (fid, V))
     ns.update(assemble=assemble, project=project)
     return checked
+
+
+def _lps_results(restau_expr, res_orth_form):
+    """templates standing for the results of the four project() calls of an LPS indicator block"""
+    A, T = abi, ts.T
+    return {("expr", restau_expr): T("Zd", A.FX_F_RES_TEST), res_orth_form: T("Zc", A.FX_F_RES_ORTH),
+            ("expr", A.FX_EXPR_RES_ORTH_SQ): T("Qt", A.FX_F_QT_A), ("expr", A.FX_EXPR_SQRT_QT_A): T("Qt", A.FX_F_KAPP)}
 
 
 def _params_from(ns, values):
@@ -285,10 +297,16 @@ def test_config5_literal_forms_equal_their_functors_numerically():
                 calls["n"] += 1
                 return first if calls["n"] == 1 else ts.T("Q", A.FX_F_Q_A)
             return dict.__getitem__(self, fid)
+    projected.update(_lps_results(A.FX_EXPR_C5_RESTAU, A.FX_FORM_C5_L_RES_ORTH))
+    ns.update(Zd="Zd", Zc="Zc", Qt="Qt", np=np, I_vec=symbolic.as_vector([1.0, 0.0, 1.0]))
     checked = _close(ns, tr, _plan(mesh, cfg), _Proj(projected),
                      base_par={A.FX_P_T0: cfg.p["T0"], A.FX_P_TH_HOT: cfg.p["th_hot"]})
-    exec("if True:\n" + "\n".join(open(ts.REF5).read().splitlines()[403:583]) + "\n", ns)
-    assert len(checked) == 16 + 4 + 3, checked
+    src = open(ts.REF5).read().splitlines()
+    exec("if True:\n" + "\n".join(src[381:391]) + "\n", ns)        # the LPS indicator block :382-391
+    assert len(checked) == 4, checked
+    ns["kapp"] = ts.T("Qt", A.FX_F_KAPP)
+    exec("if True:\n" + "\n".join(src[403:583]) + "\n", ns)
+    assert len(checked) == 4 + 16 + 4 + 3, checked
 
 
 @pytest.mark.parametrize("mp", [True, False])
@@ -305,12 +323,19 @@ def test_config4_literal_forms_equal_their_functors_numerically(mp):
     _params_from(ns, cfg.p)
     tr = Translator(cfg.S, by_slot={slot: getattr(cfg, a) for slot, a in jb.FIELD_ATTR.items()})
     tr.function(ns["thetar"], const=cfg.p["T0"] / (cfg.p["th_hot"] - cfg.p["T0"]))
-    checked = _close(ns, tr, _plan(mesh, cfg), base_par={abi.FX_P_T0: cfg.p["T0"], abi.FX_P_TH_HOT: cfg.p["th_hot"]})
+    A = abi
+    projected = _lps_results(A.FX_EXPR_C4M_RESTAU if mp else A.FX_EXPR_C4_RESTAU,
+                             A.FX_FORM_C4M_L_RES_ORTH if mp else A.FX_FORM_C4_L_RES_ORTH)
+    ns.update(Zd="Zd", Zc="Zc", Qt="Qt", np=np, I_vec=symbolic.as_vector([1.0, 0.0, 1.0]), absolute=lambda k: k)
+    checked = _close(ns, tr, _plan(mesh, cfg), projected,
+                     base_par={abi.FX_P_T0: cfg.p["T0"], abi.FX_P_TH_HOT: cfg.p["th_hot"]})
     src = open(ts.REF4).read().splitlines()
-    for a, b in ((406, 407), (413, 413), (415, 415), (473, 473)):
+    for a, b in ((406, 407), (413, 413), (415, 415)):
         exec("if True:\n" + "\n".join(src[a - 1:b]) + "\n", ns)
+    exec("if True:\n" + "\n".join(src[460:473]) + "\n", ns)        # the LPS indicator block :461-473
+    assert len(checked) == 4, checked
     exec("if True:\n" + "\n".join(src[488:658]) + "\n", ns)
-    assert len(checked) == 19, checked
+    assert len(checked) == 4 + 19, checked
 
 
 def _run_ewm(ref, cfg, mesh, ns, setup_ranges, body, n_expected):
@@ -355,8 +380,10 @@ def test_config3_literal_forms_equal_their_functors_numerically(general):
     _run_ewm(ts.REF3, cfg, mesh, ns, ((402, 402), (410, 411), (415, 416), (422, 422), (472, 475)), (487, 706), 18 + 3)
 
 
-def test_comp_ewm_jpb_literal_forms_equal_their_functors_numerically():
-    """comp_ewm_jpb.py:426-659: the true extended White-Metzner loop"""
+@pytest.mark.parametrize("general", [True, False])
+def test_comp_ewm_jpb_literal_forms_equal_their_functors_numerically(general):
+    """comp_ewm_jpb.py:426-659: the true extended White-Metzner loop (and with A_0 = k_ewm = B = 0.0, where
+    the material functions fold away)"""
     ref = os.path.join(os.path.dirname(ts.REF3), "comp_ewm_jpb.py")
     if not os.path.exists(ref):
         pytest.skip("reference checkout not present")
@@ -367,8 +394,9 @@ def test_comp_ewm_jpb_literal_forms_equal_their_functors_numerically():
     ew.randomize(cfg)
     ns = ts._namespace4([], 0.0)
     P = symbolic.Parameter
-    ns.update(al=P("al1", 0.001), np=np, A_0=P("a0", 120.0), k_ewm=P("k_ewm", -0.7), B=P("b_ewm", 0.1), norm=lambda *a: 0.0,
-              iter=1)
+    ns.update(al=P("al1", 0.001), np=np, norm=lambda *a: 0.0, iter=1,
+              A_0=P("a0", 120.0) if general else 0.0, k_ewm=P("k_ewm", -0.7) if general else 0.0,
+              B=P("b_ewm", 0.1) if general else 0.0)
 
     class _V:
         def get_local(self):
@@ -376,3 +404,13 @@ def test_comp_ewm_jpb_literal_forms_equal_their_functors_numerically():
     for f in ("w0", "w1", "tau0_vec", "tau1_vec"):
         ns[f].vector = lambda: _V()
     _run_ewm(ref, cfg, mesh, ns, ((368, 368), (376, 377), (381, 382), (386, 389)), (425, 659), 18 + 3)
+
+
+def test_every_registered_signature_is_closed_numerically():
+    """nothing in the registry is there on trust: run after the tests above (whole module), every signature of
+    form_registry.py has been assembled both ways"""
+    form_registry.load()
+    if len(_HIT) < 60:
+        pytest.skip("run the whole module: this test sums up the others")
+    missing = [v[2] for k, v in symbolic._REGISTRY.items() if k not in _HIT]
+    assert not missing, missing
