@@ -414,3 +414,135 @@ def test_every_registered_signature_is_closed_numerically():
         pytest.skip("run the whole module: this test sums up the others")
     missing = [v[2] for k, v in symbolic._REGISTRY.items() if k not in _HIT]
     assert not missing, missing
+
+
+# ---- the whole loop body, literally, on the functors -----------------------------------------------------------------------
+class _EmuVector:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def get_local(self):
+        return self.fn.vec
+
+
+class _EmuFunction(symbolic.Operand):
+    """CPU stand-in for dolfin_api.Function: a symbolic operand backed by an oracle Function's vector"""
+
+    def __init__(self, fn, name):
+        self.fn, self._space = fn, form_registry._Space(name)
+
+    def function_space(self):
+        return self._space
+
+    def split(self):
+        return form_registry.split(self)
+
+    def vector(self):
+        return _EmuVector(self.fn)
+
+    def assign(self, other):
+        self.fn.vec[:] = other.fn.vec
+
+
+def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
+    """comp_LDC_mesh_convergence.py:377-565 -- the bench configuration's COMPLETE loop body (LPS block with its four
+    projections, six linear systems, density projection, energies, field roll, t += dt), written against the drop-in
+    names, executed K times with `assemble` = recognise + the recognised functor (host emulation of the CUDA element
+    kernels), `project` likewise, `bc.apply` / LU on the host: the trajectory of the oracle's own step().  (On the GPU the
+    same text runs through dolfin_api: tests/test_gpu_literal.py.)"""
+    if not os.path.exists(ts.REF2):
+        pytest.skip("reference checkout not present")
+    import datetime
+    import textwrap
+    import time
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    from oracle import configs
+    K = 3
+    mesh = fem.skew_mesh(6)
+    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
+    cfg.t = twin.t = 0.45
+    plan = _plan(mesh, cfg)
+    ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
+    ns.update({k: symbolic.Parameter(k, v) for k, v in cfg.p.items()})
+    F = {}
+    for name, space in (("w0", "W"), ("w12", "W"), ("ws", "W"), ("w1", "W"), ("p0", "Q"), ("p1", "Q"), ("rho0", "Q"),
+                        ("rho12", "Q"), ("rho1", "Q"), ("tau0_vec", "Zc"), ("tau1_vec", "Zc")):
+        F[name] = ns[name] = _EmuFunction(getattr(cfg, name), space)
+    ns["T0"], ns["T1"] = (_EmuFunction(fem.Function(cfg.S["Q"]), "Q") for _ in range(2))   # rolled by the script, unused (:560)
+    m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
+    _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
+    ns["rho"], ns["q"] = ns["p"], ff.TestFunction("Q")
+    (ns["v"], R_vec), Rt_vec = ff.TestFunctions("W"), ff.TestFunction("Zc")
+    ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (F[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec), tau0=m3(symbolic.as_expr(F["tau0_vec"])), tau1=m3(symbolic.as_expr(F["tau1_vec"])),
+              h=symbolic.CellDiameter(), n=symbolic.FacetNormal(), Q="Q", Zd="Zd", Zc="Zc", Qt="Qt", np=np)
+    par = {}
+
+    def run(form):
+        fid, coefs, params, what, _ = symbolic.recognise(form)
+        par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()})   # a Problem keeps them
+        st = {slot: f.fn.vec for slot, f in coefs if slot >= 0}
+        return fid, st, sorted(form.signature()[1].spaces), len(form.signature()[1].args)
+
+    def assemble(form):
+        fid, st, spaces, rank = run(form)
+        if rank == 2:
+            return plan.assemble_matrix(fid, spaces[0], st, par)
+        if rank == 1:
+            return plan.assemble_vector(fid, spaces[0], st, par)
+        return plan.assemble_scalar(fid, st, par)
+
+    def project(expr, V):
+        w = form_registry.arguments(V, 0)
+        fid, st, _, _ = run(symbolic.inner(w, expr) * symbolic.dx)
+        out = _EmuFunction(fem.Function(cfg.S[V]), V)
+        if isinstance(fid, tuple):
+            out.fn.vec[:] = plan.project_dg0(fid[1], V, st, par)
+        else:
+            M = assemble(symbolic.inner(w, form_registry.arguments(V, 1)) * symbolic.dx)
+            out.fn.vec[:] = fem.solve_lu(M, plan.assemble_vector(fid, V, st, par))
+        return out
+
+    def solve(A, x, b, *a):
+        x.fn.vec[:] = fem.solve_lu(A, b)
+
+    class _T:                                                       # ulidreg.t = t -> the oracle's boundary-value closure
+        def __setattr__(self, k, v):
+            if k == "t":
+                cfg._bct["t"] = v
+    ns.update(assemble=assemble, project=project, solve=solve, end=lambda: None, bcu=cfg.bcu, bcp=[], bctau=[], time=time,
+              datetime=datetime, update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0, elapsed=0.0, total_elapsed=0.0, iter=0,
+              t=cfg.t, ulidreg=_T(), ulid=_T(), rampd=_T(), ramp_function=_T(), Ret=_T(), Wet=_T(), t_array=[], ek_array=[],
+              ee_array=[])
+    src = open(ts.REF2).read().splitlines()
+    exec(textwrap.dedent("\n".join(src[342:349])), ns)               # DEVSS definitions :343-349
+    body = "if True:\n" + "\n".join(src[376:565]) + "\n"
+    def number(e):                      # `t += dt` with dt a Parameter leaves a constant tree: its value
+        if not isinstance(e, symbolic.E):
+            return float(e)
+        if e.op == "num":
+            return float(e.data)
+        if e.op == "par":
+            return float(e.data.value)
+        a = [number(c) for c in e.a]
+        return {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1],
+                "div": lambda: a[0] / a[1], "neg": lambda: -a[0]}[e.op]()
+
+    class _Clock:                       # the progress bar's datetime.timedelta(seconds=...) gets such trees too
+        @staticmethod
+        def timedelta(seconds=0):
+            return number(seconds)
+    ns["datetime"] = _Clock
+    for _ in range(K):
+        exec(body, ns)
+        ns["t"] = number(ns["t"])
+        r = twin.step()
+        assert abs(ns["E_k"] - r["E_k"]) <= 1e-10 * abs(r["E_k"]) and abs(ns["E_e"] - r["E_e"]) <= 1e-10 * max(abs(r["E_e"]), 1e-14)
+    assert abs(float(ns["t"]) - twin.t) < 1e-14 and ns["iter"] == K
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("w0", twin.w0), ("rho0", twin.rho0),
+                      ("tau0_vec", twin.tau0_vec), ("p0", twin.p0), ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
+    assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-9
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-3
