@@ -444,44 +444,74 @@ class _EmuFunction(symbolic.Operand):
         self.fn.vec[:] = other.fn.vec
 
 
-def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
-    """comp_LDC_mesh_convergence.py:377-565 -- the bench configuration's COMPLETE loop body (LPS block with its four
-    projections, six linear systems, density projection, energies, field roll, t += dt), written against the drop-in
-    names, executed K times with `assemble` = recognise + the recognised functor (host emulation of the CUDA element
-    kernels), `project` likewise, `bc.apply` / LU on the host: the trajectory of the oracle's own step().  (On the GPU the
-    same text runs through dolfin_api: tests/test_gpu_literal.py.)"""
-    if not os.path.exists(ts.REF2):
-        pytest.skip("reference checkout not present")
-    import datetime
-    import textwrap
+def _number(e):
+    """`t += dt` with dt a Parameter leaves a constant tree: its value"""
+    if not isinstance(e, symbolic.E):
+        return float(e)
+    if e.op == "num":
+        return float(e.data)
+    if e.op == "par":
+        return float(e.data.value)
+    a = [_number(c) for c in e.a]
+    return {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1],
+            "div": lambda: a[0] / a[1], "neg": lambda: -a[0]}[e.op]()
+
+
+class _Clock:                           # the progress bar's datetime.timedelta(seconds=...) gets such trees too
+    @staticmethod
+    def timedelta(seconds=0):
+        return _number(seconds)
+
+
+class _Setter:
+    """Expression with a settable .t (ulidreg.t = t): forwards it to the oracle's boundary-value closure"""
+
+    def __init__(self, holder=None, key="t"):
+        object.__setattr__(self, "_h", (holder, key))
+
+    def __setattr__(self, k, v):
+        holder, key = self._h
+        if k == "t" and holder is not None:
+            holder[key] = _number(v)
+
+    def __getattr__(self, k):          # `str(ramp_function.t)` in compressible_dgp.py's progress line
+        holder, key = object.__getattribute__(self, "_h")
+        if k == "t":
+            return holder[key] if holder is not None else 0.0
+        raise AttributeError(k)
+
+
+class _EmuSolver:
+    def __init__(self, solve):
+        self._solve = solve
+
+    def solve(self, A, x, b):
+        self._solve(A, x, b)
+
+
+def _emu_runtime(ff, cfg, plan, fields, params):
+    """namespace of a script's set-up section on the CPU stand-ins: the drop-in module's names, Parameters, Functions backed
+    by the oracle config's vectors, and assemble / project / solve served by the recognised functors + host LU"""
     import time
-    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
-    from oracle import configs
-    K = 3
-    mesh = fem.skew_mesh(6)
-    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
-    cfg.t = twin.t = 0.45
-    plan = _plan(mesh, cfg)
     ns = {k: getattr(ff, k) for k in dir(ff) if not k.startswith("_")}
-    ns.update({k: symbolic.Parameter(k, v) for k, v in cfg.p.items()})
-    F = {}
-    for name, space in (("w0", "W"), ("w12", "W"), ("ws", "W"), ("w1", "W"), ("p0", "Q"), ("p1", "Q"), ("rho0", "Q"),
-                        ("rho12", "Q"), ("rho1", "Q"), ("tau0_vec", "Zc"), ("tau1_vec", "Zc")):
-        F[name] = ns[name] = _EmuFunction(getattr(cfg, name), space)
-    ns["T0"], ns["T1"] = (_EmuFunction(fem.Function(cfg.S["Q"]), "Q") for _ in range(2))   # rolled by the script, unused (:560)
+    ns.update({script_name: symbolic.Parameter(slot_name, cfg.p[slot_name]) for script_name, slot_name in params.items()})
+    for name, space in fields.items():
+        ns[name] = _EmuFunction(getattr(cfg, name), space)
     m3 = lambda v: symbolic.as_matrix([[v[0], v[1]], [v[1], v[2]]])  # noqa: E731
     _, ns["p"], _, tau_vec, ns["u"], D_vec, ns["D"], ns["tau"] = ff.trial_functions("Q", "Zc", "W")
-    ns["rho"], ns["q"] = ns["p"], ff.TestFunction("Q")
+    ns["rho"] = ns["T"] = ns["p"]
+    ns["q"] = ns["r"] = ff.TestFunction("Q")
     (ns["v"], R_vec), Rt_vec = ff.TestFunctions("W"), ff.TestFunction("Zc")
     ns["R"], ns["Rt"] = m3(R_vec), m3(Rt_vec)
-    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (F[k].split() for k in ("w0", "w12", "ws", "w1"))
-    ns.update(D0=m3(D0_vec), D12=m3(D12_vec), tau0=m3(symbolic.as_expr(F["tau0_vec"])), tau1=m3(symbolic.as_expr(F["tau1_vec"])),
-              h=symbolic.CellDiameter(), n=symbolic.FacetNormal(), Q="Q", Zd="Zd", Zc="Zc", Qt="Qt", np=np)
+    (ns["u0"], D0_vec), (ns["u12"], D12_vec), (ns["us"], _), (ns["u1"], _) = (ns[k].split() for k in ("w0", "w12", "ws", "w1"))
+    ns.update(D0=m3(D0_vec), D12=m3(D12_vec), tau0=m3(symbolic.as_expr(ns["tau0_vec"])), tau1=m3(symbolic.as_expr(ns["tau1_vec"])),
+              h=symbolic.CellDiameter(), n=symbolic.FacetNormal(), Q="Q", Zd="Zd", Zc="Zc", Qt="Qt", np=np,
+              I_vec=symbolic.as_vector([1.0, 0.0, 1.0]))
     par = {}
 
     def run(form):
-        fid, coefs, params, what, _ = symbolic.recognise(form)
-        par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params.items()})   # a Problem keeps them
+        fid, coefs, params_, what, _ = symbolic.recognise(form)
+        par.update({getattr(abi, "FX_P_" + k.upper()): float(v.value) for k, v in params_.items()})   # a Problem keeps them
         st = {slot: f.fn.vec for slot, f in coefs if slot >= 0}
         return fid, st, sorted(form.signature()[1].spaces), len(form.signature()[1].args)
 
@@ -495,7 +525,10 @@ def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
 
     def project(expr, V):
         w = form_registry.arguments(V, 0)
-        fid, st, _, _ = run(symbolic.inner(w, expr) * symbolic.dx)
+        try:
+            fid, st, _, _ = run(symbolic.inner(w, expr) * symbolic.dx)
+        except symbolic.UnknownForm:                                 # compressible_dgp.py:404: dead in the script
+            return None
         out = _EmuFunction(fem.Function(cfg.S[V]), V)
         if isinstance(fid, tuple):
             out.fn.vec[:] = plan.project_dg0(fid[1], V, st, par)
@@ -507,42 +540,85 @@ def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
     def solve(A, x, b, *a):
         x.fn.vec[:] = fem.solve_lu(A, b)
 
-    class _T:                                                       # ulidreg.t = t -> the oracle's boundary-value closure
-        def __setattr__(self, k, v):
-            if k == "t":
-                cfg._bct["t"] = v
-    ns.update(assemble=assemble, project=project, solve=solve, end=lambda: None, bcu=cfg.bcu, bcp=[], bctau=[], time=time,
-              datetime=datetime, update_progress=lambda *a: None, jjj=0, j=0, Tf=1.0, elapsed=0.0, total_elapsed=0.0, iter=0,
-              t=cfg.t, ulidreg=_T(), ulid=_T(), rampd=_T(), ramp_function=_T(), Ret=_T(), Wet=_T(), t_array=[], ek_array=[],
-              ee_array=[])
+    def absolute(f):
+        f.fn.vec[:] = np.abs(f.fn.vec)
+        return f
+    ns.update(assemble=assemble, project=project, solve=solve, absolute=absolute, solvertau=_EmuSolver(solve), end=lambda: None,
+              bcu=cfg.bcu, bcp=[], bctau=[], time=time, datetime=_Clock, update_progress=lambda *a: None, jjj=0, j=0, Tf=10.0,
+              elapsed=0.0, total_elapsed=0.0, iter=0, t=cfg.t, t_array=[], ek_array=[], ee_array=[], nus_array=[],
+              ulid=_Setter(), rampd=_Setter(), Ret=_Setter(), Wet=_Setter())
+    return ns
+
+
+def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
+    """comp_LDC_mesh_convergence.py:377-565 -- the bench configuration's COMPLETE loop body (LPS block with its four
+    projections, six linear systems, density projection, energies, field roll, t += dt), written against the drop-in
+    names, executed K times with `assemble` = recognise + the recognised functor (host emulation of the CUDA element
+    kernels), `project` likewise, `bc.apply` / LU on the host: the trajectory of the oracle's own step().  (On the GPU the
+    same text runs through dolfin_api: tests/test_gpu_literal.py.)"""
+    if not os.path.exists(ts.REF2):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    from oracle import configs
+    K = 3
+    mesh = fem.skew_mesh(6)
+    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
+    cfg.t = twin.t = 0.45
+    fields = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", rho0="Q", rho12="Q", rho1="Q", tau0_vec="Zc", tau1_vec="Zc")
+    ns = _emu_runtime(ff, cfg, _plan(mesh, cfg), fields, {k: k for k in cfg.p})
+    ns["T0"], ns["T1"] = (_EmuFunction(fem.Function(cfg.S["Q"]), "Q") for _ in range(2))   # rolled by the script, unused (:560)
+    ns.update(ulidreg=_Setter(cfg._bct), ramp_function=_Setter(), Tf=1.0)
     src = open(ts.REF2).read().splitlines()
     exec(textwrap.dedent("\n".join(src[342:349])), ns)               # DEVSS definitions :343-349
     body = "if True:\n" + "\n".join(src[376:565]) + "\n"
-    def number(e):                      # `t += dt` with dt a Parameter leaves a constant tree: its value
-        if not isinstance(e, symbolic.E):
-            return float(e)
-        if e.op == "num":
-            return float(e.data)
-        if e.op == "par":
-            return float(e.data.value)
-        a = [number(c) for c in e.a]
-        return {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1],
-                "div": lambda: a[0] / a[1], "neg": lambda: -a[0]}[e.op]()
-
-    class _Clock:                       # the progress bar's datetime.timedelta(seconds=...) gets such trees too
-        @staticmethod
-        def timedelta(seconds=0):
-            return number(seconds)
-    ns["datetime"] = _Clock
     for _ in range(K):
         exec(body, ns)
-        ns["t"] = number(ns["t"])
+        ns["t"] = _number(ns["t"])
         r = twin.step()
         assert abs(ns["E_k"] - r["E_k"]) <= 1e-10 * abs(r["E_k"]) and abs(ns["E_e"] - r["E_e"]) <= 1e-10 * max(abs(r["E_e"]), 1e-14)
-    assert abs(float(ns["t"]) - twin.t) < 1e-14 and ns["iter"] == K
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
     for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("w0", twin.w0), ("rho0", twin.rho0),
                       ("tau0_vec", twin.tau0_vec), ("p0", twin.p0), ("w12", twin.w12), ("ws", twin.ws)):
         assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
     assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-9
     assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
     assert np.abs(twin.w1.vec).max() > 1e-3
+
+
+def test_config5_loop_body_text_runs_on_the_functors_for_k_steps():
+    """buoyancy-driven-flow/compressible_dgp.py:369-595 -- LPS block, three per-step projections, eight linear systems,
+    density projection, energies, Nusselt number, the hot wall ramped in time: K steps from the text on the functors"""
+    if not os.path.exists(ts.REF5):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
+    from oracle.configs_dgp import CompDGP
+    K = 3
+    mesh = dgp_mesh(6)
+    cfg, twin = CompDGP(mesh), CompDGP(mesh)
+    cfg.t = twin.t = 1.4                        # the hot wall is being ramped (tanh(4 (t - 1.5)))
+    fields = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", rho0="Q", rho12="Q", rho1="Q", tau0_vec="Zc", tau1_vec="Zc",
+                  T0="Q", T1="Q", thetar="Q")
+    names = dict(Ra="Ra", Pr="Pr", We="We", Ma="Ma", dt="dt", betav="betav", th="th", Vh="Vh", Bi="Bi", c1="c1", c2="c2",
+                 T_0="T0", T_h="th_hot", al_1="al1", al_2="al2")
+    ns = _emu_runtime(ff, cfg, _plan(mesh, cfg), fields, names)
+    ns["thetar"].slot = -1                      # project(T_0/(T_h-T_0), Q) :295-296: a constant inside the functors
+    ns.update(C=200.0, k=symbolic.as_vector([0.0, 1.0]), bcT=cfg.bcT, ramp_function=_Setter(cfg._tt))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])                  # :294
+    src = open(ts.REF5).read().splitlines()
+    exec(textwrap.dedent("\n".join(src[335:338])), ns)               # DEVSS definitions :336-338
+    body = "if True:\n" + "\n".join(src[368:595]) + "\n"
+    for _ in range(K):
+        exec(body, ns)
+        ns["t"] = _number(ns["t"])
+        r = twin.step()
+        for key in ("E_k", "E_e", "Nus"):
+            assert abs(ns[key] - r[key]) <= 1e-9 * max(abs(r[key]), 1e-12), key
+    assert abs(ns["t"] - twin.t) < 1e-14
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("w0", twin.w0),
+                      ("rho0", twin.rho0), ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws), ("rho12", twin.rho12)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
+    assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-9
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-6
