@@ -737,6 +737,8 @@ def _register_lps():
     _reg(inner(wc, arguments("Zc", 1)) * dx, A.FX_FORM_MASS_ZC, "project(., Zc): mass matrix")
     _reg(inner(wq, inner(res_orth, res_orth)) * dx, ("expr", A.FX_EXPR_RES_ORTH_SQ), "project(inner(res_orth,res_orth), Qt)")
     _reg(inner(wq, S.as_expr(qt_a) ** 0.5) * dx, ("expr", A.FX_EXPR_SQRT_QT_A), "project(np.power(res_orth_norm_sq, 0.5), Qt)")
+    kapp = T_("Qt", A.FX_F_KAPP)
+    _reg(inner(wq, S.CellDiameter() * kapp) * dx, ("expr", A.FX_EXPR_H_KAPP), "err = project(h*kapp, Qt) (incomp_LDC.py:434)")
     # lid-driven cavity (configs 1, 2): F1R written out with + div(u1)*tau1, deviatoric rate of strain
     from .symbolic import div, dot, grad
     from .shims._common import tgrad

@@ -145,6 +145,49 @@ class E:
     def T(self):
         return transpose(self)
 
+    # ---- constant trees are numbers -------------------------------------------------------------------
+    # With dt a Parameter the scripts' own bookkeeping -- `t += dt` ... `if t > 0.5:` (incomp_LDC.py:429, :437),
+    # `(Tf-t)/dt * elapsed` (:284) -- builds trees of numbers and Parameters only: they evaluate where a number is needed.
+    def __float__(self):
+        return _const_value(self)
+
+    def __lt__(self, o):
+        return float(self) < float(o)
+
+    def __gt__(self, o):
+        return float(self) > float(o)
+
+    def __le__(self, o):
+        return float(self) <= float(o)
+
+    def __ge__(self, o):
+        return float(self) >= float(o)
+
+
+def _const_value(e):
+    if e.op == "num":
+        return float(e.data)
+    if e.op == "par":
+        return float(e.data.value)
+    if e.op in ("add", "sub", "mul", "div", "neg", "pow", "abs", "sqrt") and e.shape == ():
+        a = [_const_value(c) for c in e.a]
+        if e.op == "add":
+            return a[0] + a[1]
+        if e.op == "sub":
+            return a[0] - a[1]
+        if e.op == "mul":
+            return a[0] * a[1]
+        if e.op == "div":
+            return a[0] / a[1]
+        if e.op == "neg":
+            return -a[0]
+        if e.op == "pow":
+            return a[0] ** a[1]
+        if e.op == "abs":
+            return abs(a[0])
+        return a[0] ** 0.5
+    raise TypeError("expression with fields or arguments (%s) used as a number" % e.op)
+
 
 def _same(a, b):
     if a.shape != b.shape:

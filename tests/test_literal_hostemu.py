@@ -237,9 +237,10 @@ def test_config1_literal_forms_equal_their_functors_numerically():
                  ("expr", abi.FX_EXPR_RES_ORTH_SQ): T("Qt", abi.FX_F_QT_A), ("expr", abi.FX_EXPR_SQRT_QT_A): T("Qt", abi.FX_F_KAPP)}
     ns.update(Zd="Zd", Zc="Zc", Qt="Qt", np=np)
     checked = _close(ns, tr, _plan(mesh, cfg), projected)
-    for a, b in ((298, 308), (317, 331), (355, 363), (370, 375), (379, 394), (400, 416), (420, 421)):
+    projected[("expr", abi.FX_EXPR_H_KAPP)] = T("Qt", -1)
+    for a, b in ((298, 308), (317, 331), (355, 363), (370, 375), (379, 394), (400, 416), (420, 421), (434, 434)):
         exec(ts._lines(a, b), ns)
-    assert len(checked) == 4 + 10 + 2, checked
+    assert len(checked) == 4 + 10 + 2 + 1, checked
 
 
 def test_config2_literal_forms_equal_their_functors_numerically():
@@ -445,16 +446,8 @@ class _EmuFunction(symbolic.Operand):
 
 
 def _number(e):
-    """`t += dt` with dt a Parameter leaves a constant tree: its value"""
-    if not isinstance(e, symbolic.E):
-        return float(e)
-    if e.op == "num":
-        return float(e.data)
-    if e.op == "par":
-        return float(e.data.value)
-    a = [_number(c) for c in e.a]
-    return {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1],
-            "div": lambda: a[0] / a[1], "neg": lambda: -a[0]}[e.op]()
+    """`t += dt` with dt a Parameter leaves a constant tree: its value (symbolic.E.__float__)"""
+    return float(e)
 
 
 class _Clock:                           # the progress bar's datetime.timedelta(seconds=...) gets such trees too
@@ -622,3 +615,48 @@ def test_config5_loop_body_text_runs_on_the_functors_for_k_steps():
     assert lc.rel_err(ns["rho1"].fn.vec, twin.rho1.vec) < 1e-9
     assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
     assert np.abs(twin.w1.vec).max() > 1e-6
+
+
+def test_config1_loop_body_text_runs_on_the_functors_for_k_steps():
+    """lid-driven-cavity/incomp_LDC.py:281-447 -- LPS block, five linear systems incl. the singular pure-Neumann pressure
+    system, energies, the error indicator and the divergence test with its `break`, field roll: K steps from the text on
+    the functors"""
+    if not os.path.exists(ts.REF):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    import fenics_b200.shims.lid_driven_cavity.fenics_fem as ff
+    from oracle import configs
+    K = 5
+    mesh = fem.skew_mesh(6)
+    cfg, twin = configs.IncompLDC(mesh), configs.IncompLDC(mesh)
+    cfg.t = twin.t = 0.49                       # crosses t = 0.5, where the divergence test (:437-441) switches on
+    fields = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", tau0_vec="Zc", tau1_vec="Zc")
+    ns = _emu_runtime(ff, cfg, _plan(mesh, cfg), fields, {k: k for k in cfg.p})
+
+    def solve(A, x, b, *a):
+        singular = abs(A @ np.ones(A.shape[0])).max() < 1e-12 * abs(A).max()
+        x.fn.vec[:] = configs.solve_zero_sum(A, b) if singular else fem.solve_lu(A, b)   # bcp = []: pure Neumann (:227)
+    ns["T0"], ns["T1"] = (_EmuFunction(fem.Function(cfg.S["Q"]), "Q") for _ in range(2))
+    ns.update(solve=solve, norm=lambda v, kind: fem.norm(v.get_local(), kind), ulidreg=_Setter(cfg._bct), Tf=1.0, err_array=[])
+    src = open(ts.REF).read().splitlines()
+    exec(textwrap.dedent("\n".join(src[258:263])), ns)                # DEVSS / LPS definitions :259-263
+    ns.update(a1=0, L1=0)
+    raw = textwrap.dedent("\n".join(src[280:447]))
+    body = "for once_ in (0,):\n" + textwrap.indent(raw, "    ") + "\n    completed_ = True\n"
+    for step in range(K):
+        ns["completed_"] = False
+        exec(body, ns)
+        ns["t"] = _number(ns["t"])
+        r = twin.step()
+        assert ns["completed_"] == (not r["diverged"])
+        assert abs(ns["E_k"] - r["E_k"]) <= 1e-9 * abs(r["E_k"]) and abs(ns["E_e"] - r["E_e"]) <= 1e-9 * max(abs(r["E_e"]), 1e-14)
+        assert abs(ns["err_array"][-1] - r["err"]) <= 1e-7 * max(r["err"], 1e-14)
+        if r["diverged"]:
+            break
+    assert ns["t"] > 0.5 and abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == step + 1
+    rolled = () if r["diverged"] else (("w0", twin.w0), ("tau0_vec", twin.tau0_vec))
+    for name, ref in (("w1", twin.w1), ("tau1_vec", twin.tau1_vec), ("w12", twin.w12), ("ws", twin.ws)) + rolled:
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-9, name
+    pm = lambda v: v - v.mean()  # noqa: E731  (the pressure is defined up to a constant)
+    assert lc.rel_err(pm(ns["p1"].fn.vec), pm(twin.p1.vec)) < 1e-8
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
