@@ -660,3 +660,98 @@ def test_config1_loop_body_text_runs_on_the_functors_for_k_steps():
     pm = lambda v: v - v.mean()  # noqa: E731  (the pressure is defined up to a constant)
     assert lc.rel_err(pm(ns["p1"].fn.vec), pm(twin.p1.vec)) < 1e-8
     assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+
+
+_JBP_FIELDS = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", rho0="Q", rho12="Q", rho1="Q", tau0_vec="Zc", tau1_vec="Zc",
+                   T0="Q", T1="Q", thetar="Q")
+_JBP_NAMES = dict(Re="Re", We="We", Ma="Ma", dt="dt", betav="betav", th="th", conv="conv", Di="Di", Vh="Vh", Bi="Bi", T_0="T0",
+                  T_h="th_hot")
+
+
+def _jbp_runtime(cfg, mesh, extra_names):
+    import fenics_b200.shims.eccentric_cylinders.fenics_base as fb
+    ns = _emu_runtime(fb, cfg, _plan(mesh, cfg), _JBP_FIELDS, dict(_JBP_NAMES, **extra_names))
+    ns["thetar"].slot = -1
+    ns.update(bcT=cfg.bcT, w=_Setter(cfg._tt), tang=symbolic.as_vector([ns["n"][1], -ns["n"][0]]), mesh_refinement=False,
+              j=1, primary_loop=1, secondary_loop=0, x1=[], ek1=[], ee1=[], y1=[], zx1=[], z1=[],
+              norm=lambda v, kind: fem.norm(v.get_local(), kind))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
+    return ns
+
+
+def _jbp_compare(ns, twin, K, fields, keys):
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for name in fields:
+        assert lc.rel_err(ns[name].fn.vec, getattr(twin, name).vec) < 1e-9, name
+    assert np.abs(twin.w1.vec).max() > 1e-3
+
+
+def test_config4_loop_body_text_runs_on_the_functors_for_k_steps():
+    """fenepmp_jbp.py:455-690, FENE-P-MP (lambda_D = 0.1): LPS block with absolute(kapp), `if iter > 1` roll, seven linear
+    systems, energies, journal torque / load -- K steps from the text on the functors"""
+    if not os.path.exists(ts.REF4):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    from oracle.configs_jbp import FenepmpJBP
+    K = 3
+    mesh = fem.annulus_mesh(12, 3)
+    cfg, twin = FenepmpJBP(mesh, lambda_d=0.1, We=0.5), FenepmpJBP(mesh, lambda_d=0.1, We=0.5)
+    cfg.t = twin.t = 0.45
+    ns = _jbp_runtime(cfg, mesh, dict(lambda_d="lambda_d", b="b_fene", A_0="a0"))
+    src = open(ts.REF4).read().splitlines()
+    for a, b in ((406, 407), (413, 413), (415, 415)):
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+    body = "if True:\n" + "\n".join(src[454:690]) + "\n"
+    for step in range(K):
+        exec(body, ns)
+        ns["t"] = _number(ns["t"])
+        r = twin.step()
+        for key, got in (("E_k", ns["E_k"]), ("E_e", ns["E_e"]), ("torque", ns["y1"][-1]), ("F_x", ns["zx1"][-1]),
+                         ("F_y", ns["z1"][-1])):
+            scale = max(abs(r["F_x"]), abs(r["F_y"])) if key in ("F_x", "F_y") else abs(r[key])
+            assert abs(got - r[key]) <= 1e-8 * max(scale, 1e-12), (step, key)
+    _jbp_compare(ns, twin, K, ("w1", "p1", "tau1_vec", "T1", "rho1", "w0", "rho0", "T0", "ws", "rho12"), ())
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+
+
+@pytest.mark.parametrize("which", ["main", "prepass", "true_ewm"])
+def test_config3_loop_body_text_runs_on_the_functors_for_k_steps(which):
+    """incompressible_benchmarkEWM.py:466-782 (main pass: ramped spin, stress step behind its `if`; pre-pass: un-ramped spin)
+    and comp_ewm_jpb.py:422-732 (the true extended White-Metzner loop) -- K steps from the text on the functors"""
+    if not os.path.exists(ts.REF3):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    from oracle import configs_ewm as ce
+    K = 3
+    mesh = fem.annulus_mesh(12, 3)
+    if which == "true_ewm":
+        script, pre, loop = os.path.join(os.path.dirname(ts.REF3), "comp_ewm_jpb.py"), ((368, 368), (376, 377), (381, 382), (386, 389)), (422, 732)
+        cfg, twin = ce.CompEwmJBP(mesh, dt=0.002), ce.CompEwmJBP(mesh, dt=0.002)
+        prepass = False
+    else:
+        prepass = which == "prepass"
+        script, pre, loop = ts.REF3, ((402, 402), (410, 411), (415, 416), (422, 422)), (466, 782)
+        kw = dict(prepass=prepass, Ma=0.05, betav=0.6, A_0=0.4, k_ewm=0.7, B=0.2, dt=0.002)
+        cfg, twin = ce.EwmJBP(mesh, **kw), ce.EwmJBP(mesh, **kw)
+    cfg.t = twin.t = 0.45
+    ns = _jbp_runtime(cfg, mesh, dict(A_0="a0", al="al1"))
+    P = symbolic.Parameter
+    ns.update(k_ewm=P("k_ewm", cfg.k_ewm), B=P("b_ewm", cfg.B), adaptive_loop=not prepass, err_count=0, max_refine=2)
+    src = open(script).read().splitlines()
+    for a, b in pre:
+        exec(textwrap.dedent("\n".join(src[a - 1:b])), ns)
+    raw = "\n".join(src[loop[0] - 1:loop[1]])
+    indent = " " * (len(raw) - len(raw.lstrip(" ")))                  # the two scripts nest their loops differently
+    body = "for once_ in (0,):\n" + raw + "\n" + indent + "completed_ = True\n"
+    for step in range(K):
+        ns["completed_"] = False
+        exec(body, ns)
+        assert ns["completed_"]
+        ns["t"] = _number(ns["t"])
+        r = twin.step()
+        for key, got in (("E_k", ns["E_k"]), ("E_e", ns["E_e"]), ("torque", ns["y1"][-1]), ("F_y", ns["z1"][-1])):
+            scale = max(abs(r["F_x"]), abs(r["F_y"])) if key == "F_y" else abs(r[key])
+            floor = 1e-4 if key == "E_e" else 1e-12    # E_e = int(tr(tau) - 2) cancels to ~1e-10 at the start of the pre-pass: 1e-12 absolute
+            assert abs(got - r[key]) <= 1e-8 * max(scale, floor), (step, key)
+    _jbp_compare(ns, twin, K, ("w1", "p1", "tau1_vec", "T1", "rho1", "w0", "rho0", "T0", "w12", "ws"), ())
