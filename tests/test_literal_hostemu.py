@@ -543,8 +543,11 @@ def _emu_runtime(ff, cfg, plan, fields, params):
     return ns
 
 
-def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
-    """comp_LDC_mesh_convergence.py:377-565 -- the bench configuration's COMPLETE loop body (LPS block with its four
+@pytest.mark.parametrize("script,cls,devss,rng", [("comp_LDC_mesh_convergence.py", "CompLDC", (343, 349), (377, 565)),
+                                                   ("comp_LDC.py", "CompLDCSweep", (334, 340), (365, 594))])
+def test_config2_loop_body_text_runs_on_the_functors_for_k_steps(script, cls, devss, rng):
+    """comp_LDC_mesh_convergence.py:377-565 (and the sweep script comp_LDC.py:365-594, whose convective terms carry Re*conv)
+    -- the bench configuration's COMPLETE loop body (LPS block with its four
     projections, six linear systems, density projection, energies, field roll, t += dt), written against the drop-in
     names, executed K times with `assemble` = recognise + the recognised functor (host emulation of the CUDA element
     kernels), `project` likewise, `bc.apply` / LU on the host: the trajectory of the oracle's own step().  (On the GPU the
@@ -556,15 +559,15 @@ def test_config2_loop_body_text_runs_on_the_functors_for_k_steps():
     from oracle import configs
     K = 3
     mesh = fem.skew_mesh(6)
-    cfg, twin = configs.CompLDC(mesh), configs.CompLDC(mesh)
+    cfg, twin = getattr(configs, cls)(mesh), getattr(configs, cls)(mesh)
     cfg.t = twin.t = 0.45
     fields = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", rho0="Q", rho12="Q", rho1="Q", tau0_vec="Zc", tau1_vec="Zc")
     ns = _emu_runtime(ff, cfg, _plan(mesh, cfg), fields, {k: k for k in cfg.p})
     ns["T0"], ns["T1"] = (_EmuFunction(fem.Function(cfg.S["Q"]), "Q") for _ in range(2))   # rolled by the script, unused (:560)
     ns.update(ulidreg=_Setter(cfg._bct), ramp_function=_Setter(), Tf=1.0)
-    src = open(ts.REF2).read().splitlines()
-    exec(textwrap.dedent("\n".join(src[342:349])), ns)               # DEVSS definitions :343-349
-    body = "if True:\n" + "\n".join(src[376:565]) + "\n"
+    src = open(os.path.join(os.path.dirname(ts.REF2), script)).read().splitlines()
+    exec(textwrap.dedent("\n".join(src[devss[0] - 1:devss[1]])), ns)   # DEVSS definitions before the loop
+    body = "if True:\n" + "\n".join(src[rng[0] - 1:rng[1]]) + "\n"
     for _ in range(K):
         exec(body, ns)
         ns["t"] = _number(ns["t"])
@@ -755,3 +758,47 @@ def test_config3_loop_body_text_runs_on_the_functors_for_k_steps(which):
             floor = 1e-4 if key == "E_e" else 1e-12    # E_e = int(tr(tau) - 2) cancels to ~1e-10 at the start of the pre-pass: 1e-12 absolute
             assert abs(got - r[key]) <= 1e-8 * max(scale, floor), (step, key)
     _jbp_compare(ns, twin, K, ("w1", "p1", "tau1_vec", "T1", "rho1", "w0", "rho0", "T0", "w12", "ws"), ())
+
+
+def test_incompressible_dgp_loop_body_text_runs_on_the_functors_for_k_steps():
+    """buoyancy-driven-flow/incompressible_dgp.py:358-535 -- LPS block with absolute(kapp), `iter > 1` roll, two momentum
+    systems, the singular pure-Neumann pressure system, velocity update, stress (behind `if betav < 0.99`), temperature,
+    energies, Nusselt number: K steps from the text on the functors"""
+    if not os.path.exists(ts.REF6):
+        pytest.skip("reference checkout not present")
+    import textwrap
+    import fenics_b200.shims.buoyancy_driven_flow.fenics_fem as ff
+    from oracle import configs_dgp as cd
+    K = 3
+    mesh = dgp_mesh(6)
+    cfg, twin = cd.IncompDGP(mesh), cd.IncompDGP(mesh)
+    cfg.t = twin.t = 1.4
+    fields = dict(w0="W", w12="W", ws="W", w1="W", p0="Q", p1="Q", rho0="Q", rho1="Q", tau0_vec="Zc", tau1_vec="Zc", T0="Q",
+                  T1="Q", thetar="Q")
+    names = dict(Ra="Ra", Pr="Pr", We="We", dt="dt", betav="betav", th="th", Vh="Vh", Bi="Bi", c1="c1", c2="c2", T_0="T0",
+                 T_h="th_hot")
+    ns = _emu_runtime(ff, cfg, _plan(mesh, cfg), fields, names)
+    ns["thetar"].slot = -1
+
+    def solve(A, x, b, *a):
+        singular = abs(A @ np.ones(A.shape[0])).max() < 1e-12 * abs(A).max()
+        x.fn.vec[:] = cd.solve_weighted_gauge(A, b, x.fn.vec) if singular else fem.solve_lu(A, b)
+    ns.update(solve=solve, solvertau=_EmuSolver(solve), al=0.0, f=symbolic.as_vector([0.0, -1.0]), k=symbolic.as_vector([0.0, 1.0]),
+              bcT=cfg.bcT, ramp_function=_Setter(cfg._tt))
+    ns["thetal"] = ns["T"] / (ns["T_h"] - ns["T_0"])
+    ns["theta0"] = (ns["T0"] - ns["T_0"]) / (ns["T_h"] - ns["T_0"])
+    src = open(ts.REF6).read().splitlines()
+    exec(textwrap.dedent("\n".join(src[325:329])), ns)
+    body = "if True:\n" + "\n".join(src[357:535]) + "\n"
+    for _ in range(K):
+        exec(body, ns)
+        ns["t"] = _number(ns["t"])
+        r = twin.step()
+        for key in ("E_k", "E_e", "Nus"):
+            assert abs(ns[key] - r[key]) <= 1e-8 * max(abs(r[key]), 1e-4 if key == "E_e" else 1e-12), key
+    assert abs(ns["t"] - twin.t) < 1e-14 and ns["iter"] == K
+    for name, ref in (("w1", twin.w1), ("p1", twin.p1), ("tau1_vec", twin.tau1_vec), ("T1", twin.T1), ("w0", twin.w0),
+                      ("T0", twin.T0), ("w12", twin.w12), ("ws", twin.ws)):
+        assert lc.rel_err(ns[name].fn.vec, ref.vec) < 1e-8, name
+    assert lc.rel_err(ns["kapp"].fn.vec, twin.kapp.vec) < 1e-7
+    assert np.abs(twin.w1.vec).max() > 1e-6
