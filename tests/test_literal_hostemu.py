@@ -5,7 +5,11 @@ kernels (tests/hostemu: the same csrc headers), and (ii) translated node by node
 (oracle/ufl_lite.py) and assembled there on the same random data.  Equal to 1e-12, and the functor's quadrature degrees
 equal UFL's estimate for the script's form: the structure the registry keys on really is the operator the hand-written
 functor computes.  All eight scripts: configs 1-5, comp_LDC.py, comp_ewm_jpb.py, incompressible_dgp.py (the last two have
-no GPU comparison of their literal path of their own)."""
+no GPU comparison of their literal path of their own).
+
+Second half of the module: the COMPLETE loop bodies of all eight scripts, executed K times from their text against the
+drop-in module's names with `assemble` / `project` served by the recognised functors (host emulation), `bc.apply` and
+exact LU on the host, follow the oracle's own step() trajectory -- the drop-in claim without a GPU."""
 import os
 
 import numpy as np
